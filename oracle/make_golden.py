@@ -1,0 +1,278 @@
+"""Generate the golden fixtures under tests/golden/ from the REAL reference (harness only).
+
+Run in the build container (where /root/reference exists):
+
+    python -m oracle.make_golden [case ...]
+
+Each fixture is one ``.npz`` holding
+  * the Program (generated ``vector_field`` assignment stream + argument arrays) exactly as the
+    reference's NumPy backend produced it (captured at ``BaseBackend.generate_func`` /
+    ``BaseBackend.run``, pyrates/backend/base/base_backend.py:537,596),
+  * ``rec_<solver>``: the state recording returned by the reference's own ``BaseBackend.run`` for
+    solvers 'euler' and 'heun' (the reference's aliased Heun), and — because the reference has no
+    fixed-step RK4 / textbook Heun — ``rec_rk4`` / ``rec_heun_true`` computed by
+    ``oracle.numpy_oracle`` around the reference-generated function (flagged ``oracle_defined``),
+  * ``__run__``: T, dt, dts, solver list, float precision.
+The GPU box has no reference; tests there compare the CUDA path against these files.
+"""
+from __future__ import annotations
+
+import copy
+import json
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+from oracle.ref_env import import_reference  # noqa: E402
+from oracle import numpy_oracle as orc       # noqa: E402
+from pyrates_b200.program import Program     # noqa: E402
+
+GOLDEN = os.path.join(_ROOT, "tests", "golden")
+
+
+class Capture:
+    """Monkey-patches the reference NumPy backend to record what it generates and returns."""
+
+    def __init__(self):
+        import pyrates.backend.base.base_backend as bb
+        import pyrates.backend.computegraph as cg
+        self.bb, self.cg = bb, cg
+        self.source = None
+        self.func_args = None
+        self.names = None
+        self.state_vars = None
+        self.rec = None
+        self.labels = None
+        self._orig = (bb.BaseBackend.generate_func, bb.BaseBackend.run, cg.ComputeGraph.to_func)
+        cap = self
+
+        def generate_func(self_, func_name, to_file=True, **kw):
+            cap.source = self_.generate()
+            return cap._orig[0](self_, func_name, to_file=to_file, **kw)
+
+        def run(self_, func, func_args, T, dt, dts, solver, **kw):
+            cap.func_args = [np.array(a, copy=True) for a in func_args]
+            out = cap._orig[1](self_, func, func_args, T, dt, dts, solver, **kw)
+            cap.rec = np.array(out[0], copy=True)
+            return out
+
+        def to_func(self_, *a, **kw):
+            out = cap._orig[2](self_, *a, **kw)
+            cap.names = list(out[2])
+            cap.state_vars = dict(out[3])
+            return out
+
+        bb.BaseBackend.generate_func = generate_func
+        bb.BaseBackend.run = run
+        cg.ComputeGraph.to_func = to_func
+
+    def close(self):
+        self.bb.BaseBackend.generate_func, self.bb.BaseBackend.run, self.cg.ComputeGraph.to_func = self._orig
+
+
+# ----------------------------------------------------------------------------- case builders
+def _yaml(path):
+    def build():
+        from pyrates import CircuitTemplate
+        return CircuitTemplate.from_yaml(path)
+    return build
+
+
+def _wc_pop(N, seed=42):
+    def build():
+        from pyrates import CircuitTemplate, NodeTemplate
+        from pyrates.frontend.template.population import PopulationTemplate, Connectivity
+        rng = np.random.default_rng(seed)
+        W = rng.normal(0.0, 1.0 / np.sqrt(N), (N, N))
+        np.fill_diagonal(W, 15.0)
+        exc = NodeTemplate.from_yaml("model_templates.neural_mass_models.wilsoncowan.exc_pop")
+        pop = PopulationTemplate(name="e", node=exc, n=N)
+        conn = Connectivity(source="e/rate_op/r", target="e/se_op/r_in", weights=W)
+        return CircuitTemplate(name=f"wc_n{N}", populations={"e": pop}, connections=[conn])
+    return build
+
+
+def _qif_sfa_pop(N, variant, seed=42):
+    def build():
+        from pyrates import CircuitTemplate, NodeTemplate
+        from pyrates.frontend.template.population import PopulationTemplate, Connectivity
+        rng = np.random.default_rng(seed)
+        eta = rng.normal(-5.0, 1.0, N)
+        W = rng.normal(0.0, 1.0 / np.sqrt(N), (N, N))
+        qs = NodeTemplate.from_yaml("model_templates.neural_mass_models.qif.qif_sfa_pop")
+        if variant in ("cascade", "ring"):
+            pop = PopulationTemplate(name="p", node=qs, n=N, params={"qif_sfa_op/eta": list(eta)})
+            kw = dict(delays=4e-3, spread=2e-3) if variant == "cascade" else dict(delays=4e-3)
+            conn = Connectivity(source="p/qif_sfa_op/r", target="p/qif_sfa_op/r_in", weights=W, **kw)
+            return CircuitTemplate(name=f"qsfa_{variant}", populations={"p": pop}, connections=[conn])
+        p1 = PopulationTemplate(name="p1", node=qs, n=N, params={"qif_sfa_op/eta": list(eta)})
+        p2 = PopulationTemplate(name="p2", node=qs, n=N, params={"qif_sfa_op/eta": list(eta[::-1])})
+        W2 = rng.normal(0.0, 1.0 / np.sqrt(N), (N, N))
+        c12 = Connectivity(source="p1/qif_sfa_op/r", target="p2/qif_sfa_op/r_in", weights=W, delays=4e-3, spread=2e-3)
+        c21 = Connectivity(source="p2/qif_sfa_op/r", target="p1/qif_sfa_op/r_in", weights=W2, delays=3e-3)
+        return CircuitTemplate(name="qsfa_both", populations={"p1": p1, "p2": p2}, connections=[c12, c21])
+    return build
+
+
+def _kuramoto(N, dense=True):
+    def build():
+        from pyrates import CircuitTemplate, NodeTemplate, EdgeTemplate
+        from pyrates.frontend.template.population import PopulationTemplate, Connectivity
+        phase_pop = NodeTemplate.from_yaml("model_templates.oscillators.kuramoto.phase_pop")
+        sin_edge = EdgeTemplate.from_yaml("model_templates.oscillators.kuramoto.sin_edge")
+        theta = np.random.default_rng(1).uniform(0, 2 * np.pi, N)
+        omega = np.random.default_rng(1).normal(10, 1, N)
+        pop = PopulationTemplate(name="e", node=phase_pop, n=N,
+                                 params={"phase_op/theta": list(theta), "phase_op/omega": list(omega)})
+        W = np.random.default_rng(2).uniform(0, 2.0 / N, (N, N)) if dense else 1.0 / N
+        conn = Connectivity(source="e/phase_op/theta", target="e/phase_op/s_in", weights=W, edge=sin_edge,
+                            edge_var_map={"theta_s": "source", "theta_t": "e/phase_op/theta"})
+        return CircuitTemplate(name="kuramoto", populations={"e": pop}, connections=[conn])
+    return build
+
+
+def _matrix_delay_test(kind):
+    """The reference's own known-answer set-ups, tests/test_population_connectivity.py:361-476."""
+    def build():
+        from pyrates import CircuitTemplate, NodeTemplate, OperatorTemplate
+        from pyrates.frontend.template.population import PopulationTemplate, Connectivity
+        node_op = OperatorTemplate(name="rate_op_d", equations=["r' = (-r + eta + s_in) / tau_r"],
+                                   variables={"r": "output", "eta": 5.0, "tau_r": 0.1, "s_in": "input"})
+        node = NodeTemplate(name="rate_node_d", operators=[node_op])
+        pop = PopulationTemplate(name="p", node=node, n=2,
+                                 params={"rate_op_d/eta": [5.0, 8.0], "rate_op_d/r": [1.0, 2.0]})
+        W = np.array([[0., 0.5], [0.5, 0.]])
+        kw = dict(delays=4e-3) if kind == "ring" else dict(delays=5e-3, spread=2e-3)
+        conn = Connectivity(source="p/rate_op_d/r", target="p/rate_op_d/s_in", weights=W, **kw)
+        return CircuitTemplate(name="dtest", populations={"p": pop}, connections=[conn])
+    return build
+
+
+def _sin_input(n, cols=None):
+    t = np.arange(n) * 1e-3
+    if cols is None:
+        return np.sin(2 * np.pi * 5.0 * t) * 3.0
+    return np.stack([np.sin(2 * np.pi * (3.0 + k) * t) * (1.0 + k) for k in range(cols)], axis=1)
+
+
+TB = "model_templates.test_resources.test_backend."
+NM = "model_templates.neural_mass_models."
+
+# name -> dict(build, T, dt, dts, outputs (any valid output, only used to drive run()), inputs, precisions)
+CASES = {
+    "qif":        dict(build=_yaml(NM + "qif.qif"), T=1.0, dt=1e-3, out="p/qif_op/r"),
+    "qif_f32":    dict(build=_yaml(NM + "qif.qif"), T=1.0, dt=1e-3, out="p/qif_op/r", precision="float32"),
+    "qif_dt2":    dict(build=_yaml(NM + "qif.qif"), T=2.0, dt=1e-2, dts=2e-2, out="p/qif_op/r"),
+    "qif_input":  dict(build=_yaml(NM + "qif.qif"), T=0.5, dt=1e-3, out="p/qif_op/r",
+                       inputs=lambda: {"p/qif_op/I_ext": _sin_input(500)}),
+    "qif_sfa":    dict(build=_yaml(NM + "qif.qif_sfa"), T=1.0, dt=1e-3, dts=5e-3, out="p/qif_sfa_op/r"),
+    "jrc":        dict(build=_yaml(NM + "jansenrit.JRC"), T=0.2, dt=1e-4, dts=1e-3, out="pc/rpo_e_in/v"),
+    "jrc_2delay": dict(build=_yaml(NM + "jansenrit.JRC_2delaycoupled"), T=0.1, dt=1e-4, dts=1e-3,
+                       out="jrc1/pc/rpo_e_in/v"),
+    "net0":  dict(build=_yaml(TB + "net0"), T=0.2, dt=1e-3, out="pop0/op0/a"),
+    "net1":  dict(build=_yaml(TB + "net1"), T=0.2, dt=1e-3, out="pop0/op1/a",
+                  inputs=lambda: {"pop0/op1/u": _sin_input(200)}),
+    "net2":  dict(build=_yaml(TB + "net2"), T=0.2, dt=1e-3, out="pop0/op2/a"),
+    "net3":  dict(build=_yaml(TB + "net3"), T=0.2, dt=1e-3, out="pop0/op3/a",
+                  inputs=lambda: {"pop0/op3/u": _sin_input(200)}),
+    "net6":  dict(build=_yaml(TB + "net6"), T=0.2, dt=1e-3, out="pop0/op1/a"),
+    "net7":  dict(build=_yaml(TB + "net7"), T=0.2, dt=1e-3, out="pop0/op1/a"),
+    "net8":  dict(build=_yaml(TB + "net8"), T=0.2, dt=1e-3, out="pop0/op0/a"),
+    "net9":  dict(build=_yaml(TB + "net9"), T=0.2, dt=1e-3, out="pop0/op1/a",
+                  inputs=lambda: {"pop1/op7/inp": _sin_input(200)}),
+    "net10": dict(build=_yaml(TB + "net10"), T=1.5, dt=1e-3, dts=1e-2, out="pop0/op8/a"),
+    "net11": dict(build=_yaml(TB + "net11"), T=0.6, dt=1e-3, dts=2e-3, out="pop0/op1/a",
+                  inputs=lambda: {"pop1/op7/inp": _sin_input(600)}),
+    "net12": dict(build=_yaml(TB + "net12"), T=0.4, dt=1e-3, dts=2e-3, out="pop0/op7/a",
+                  inputs=lambda: {"pop0/op7/inp": _sin_input(400, cols=2)}),
+    "net13": dict(build=_yaml(TB + "net13"), T=0.2, dt=1e-3, out="p1/op9/a"),
+    "ring_kat":    dict(build=_matrix_delay_test("ring"), T=10e-3, dt=1e-3, out="p/rate_op_d/r"),
+    "gamma_kat":   dict(build=_matrix_delay_test("gamma"), T=20e-3, dt=1e-3, out="p/rate_op_d/r"),
+    "wc_n8":       dict(build=_wc_pop(8), T=0.2, dt=1e-3, out="e/rate_op/r"),
+    "wc_n128":     dict(build=_wc_pop(128), T=0.1, dt=1e-3, dts=2e-3, out="e/rate_op/r"),
+    "wc_n128_f32": dict(build=_wc_pop(128), T=0.1, dt=1e-3, dts=2e-3, out="e/rate_op/r", precision="float32"),
+    "qsfa_cascade_n8":   dict(build=_qif_sfa_pop(8, "cascade"), T=0.1, dt=1e-3, out="p/qif_sfa_op/r"),
+    "qsfa_ring_n8":      dict(build=_qif_sfa_pop(8, "ring"), T=0.1, dt=1e-3, out="p/qif_sfa_op/r"),
+    "qsfa_both_n8":      dict(build=_qif_sfa_pop(8, "both"), T=0.1, dt=1e-3, out="p1/qif_sfa_op/r"),
+    "qsfa_both_n96":     dict(build=_qif_sfa_pop(96, "both"), T=0.05, dt=1e-3, out="p1/qif_sfa_op/r"),
+    "kuramoto_n8":       dict(build=_kuramoto(8), T=0.2, dt=1e-3, out="e/phase_op/theta"),
+    "kuramoto_n128":     dict(build=_kuramoto(128), T=0.05, dt=1e-3, out="e/phase_op/theta"),
+    "kuramoto_scalar_n128": dict(build=_kuramoto(128, dense=False), T=0.05, dt=1e-3, out="e/phase_op/theta"),
+}
+
+
+def make_case(name: str, spec: dict, cap: Capture) -> str:
+    from pyrates import clear
+    from pyrates.ir.node import clear_ir_caches
+    precision = spec.get("precision", "float64")
+    T, dt, dts = spec["T"], spec["dt"], spec.get("dts")
+    recs = {}
+    prog = None
+    first_args = None
+    cwd = os.getcwd()
+    for solver in ("euler", "heun"):
+        clear_ir_caches()
+        circuit = spec["build"]()
+        inputs = spec["inputs"]() if "inputs" in spec else None
+        with tempfile.TemporaryDirectory() as tmp:
+            os.chdir(tmp)
+            try:
+                circuit.run(simulation_time=T, step_size=dt, sampling_step_size=dts, solver=solver,
+                            outputs={"o": spec["out"]}, inputs=inputs, backend="default",
+                            float_precision=precision, verbose=False, clear=True)
+            finally:
+                os.chdir(cwd)
+        recs[solver] = cap.rec
+        if prog is None:
+            first_args = cap.func_args
+            prog = Program.from_source(cap.source, list(zip(cap.names, cap.func_args)),
+                                       state_vars=cap.state_vars, float_precision=precision)
+        try:
+            clear(circuit)
+        except Exception:
+            pass
+    # oracle-defined solvers (no reference implementation): run around the reference-generated text
+    func = orc.build_vector_field(prog.source())
+    for solver in ("heun_true", "rk4"):
+        args = [np.array(a, copy=True) for a in first_args]
+        rec, _ = orc.run(func, args, T, dt, dts, solver)
+        recs[solver] = rec
+    # cross-check: the oracle must reproduce the reference bit-for-bit on the reference's solvers
+    for solver in ("euler", "heun"):
+        args = [np.array(a, copy=True) for a in first_args]
+        rec, _ = orc.run(func, args, T, dt, dts, solver)
+        diff = float(np.max(np.abs(rec - recs[solver]))) if rec.size else 0.0
+        assert diff == 0.0 or not np.isfinite(diff), f"{name}/{solver}: oracle != reference (max abs diff {diff})"
+    run_meta = {"T": T, "dt": dt, "dts": dts, "solver": "euler", "precision": precision,
+                "reference_solvers": ["euler", "heun"], "oracle_defined": ["heun_true", "rk4"],
+                "reference_version": "1.2.3", "out": spec["out"]}
+    path = os.path.join(GOLDEN, f"{name}.npz")
+    prog.save(path, __run__=np.frombuffer(json.dumps(run_meta).encode(), dtype=np.uint8),
+              **{f"rec_{k}": v for k, v in recs.items()})
+    return path
+
+
+def main(argv):
+    warnings.filterwarnings("ignore")
+    if import_reference() is None:
+        raise SystemExit("reference PyRates not importable here; fixtures can only be regenerated in the build container")
+    os.makedirs(GOLDEN, exist_ok=True)
+    names = argv or list(CASES)
+    cap = Capture()
+    try:
+        for n in names:
+            p = make_case(n, CASES[n], cap)
+            print(f"{n:24s} -> {os.path.relpath(p, _ROOT)}  ({os.path.getsize(p) / 1024:.1f} KiB)")
+    finally:
+        cap.close()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

@@ -1,0 +1,187 @@
+"""CPU oracle for the PyRates numerical-integration hot path  —  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs (``cpu_baseline`` and
+``--impl reference``) may import this module.  The product (``pyrates_b200``) never does: it fails
+loudly when its CUDA library is missing.
+
+This is a restatement, in plain NumPy, of the reference NumPy backend's algorithm for the path
+"generated vector field + fixed-step solver + state recording":
+
+* ``build_vector_field``  <- ``BaseBackend.generate_func`` (pyrates/backend/base/base_backend.py:537-578):
+  the generated ``vector_field(t, y, dy, *consts)`` text is exec'd against the reference's op table
+  (pyrates/backend/base/base_funcs.py:135-177: ``dot``, ``roll``, ``sum``, ``einsum``-based ``wsum``,
+  ``sigmoid``, ``broadcast_pre/post`` ...).  The function writes ``dy`` in place and returns it
+  (pyrates/backend/computegraph.py:1220-1228, base_backend.py:532-535).
+* ``solve_euler``  <- ``BaseBackend._solve_euler`` (base_backend.py:712-740).
+* ``solve_heun``   <- ``BaseBackend._solve_heun``  (base_backend.py:742-769) INCLUDING its buffer
+  aliasing: ``rhs`` is the in-place ``dy`` buffer, the second call overwrites it, so the update is
+  ``y += dt/2*(k2 + k2)`` (SURVEY.md headline 4).  ``solve_heun_true`` is the textbook scheme.
+* ``solve_rk4``: the reference has NO fixed-step RK4 (``SUPPORTED_SOLVERS``, base_backend.py:241).
+  Definition used by this project: classic RK4 around the reference rhs, every stage
+  called with the same integer ``step`` (inputs piecewise constant over a step, like the reference's
+  Heun which passes ``step`` to both calls, base_backend.py:763-765), each stage result copied because
+  the rhs returns its in-place buffer.  Mutable buffers (delay rings) advance once per *evaluation*.
+* ``run``          <- ``BaseBackend.run`` (base_backend.py:596-611): sample times and dispatch.
+
+Pinning: ``tests/test_oracle.py`` checks this module against (a) trajectories produced by the real
+reference in the build container (``tests/golden/*.npz``, made by ``oracle/make_golden.py``) with
+max-abs-diff 0.0 for euler/heun, and (b) the reference's own hand-computed known-answer loops
+(tests/test_population_connectivity.py:238-283, 361-415, 422-476; tests/test_backend_simulations.py).
+RK4 has no reference implementation, so it is pinned only against the analytic solution of linear
+test problems and against 4th-order convergence ("parity unpinned" w.r.t. the reference for rk4).
+"""
+from __future__ import annotations
+
+import json
+from typing import Callable, List, Sequence, Tuple
+
+import numpy as np
+
+# ----------------------------------------------------------------------------- op table
+# restates pyrates/backend/base/base_funcs.py:42-177 (names as they appear in generated code)
+
+
+def _sigmoid(x):
+    return 1. / (1. + np.exp(-x))
+
+
+def _wsum(weight, coupling):
+    return np.einsum('ij,ij->i', weight, coupling)
+
+
+def _interp_rows(t, time, inp):
+    return np.array([np.interp(t, time, inp[:, k]) for k in range(inp.shape[1])])
+
+
+OPS = {
+    'pi': np.pi, 'sqrt': np.sqrt, 'maximum': np.maximum, 'minimum': np.minimum, 'round': np.round,
+    'sum': np.sum, 'mean': np.mean, 'dot': np.dot, 'roll': np.roll, 'tanh': np.tanh, 'sinh': np.sinh,
+    'cosh': np.cosh, 'arctan': np.arctan, 'arcsin': np.arcsin, 'arccos': np.arccos, 'sin': np.sin,
+    'cos': np.cos, 'tan': np.tan, 'exp': np.exp, 'interp': np.interp, 'interp_rows': _interp_rows,
+    'sigmoid': _sigmoid, 'broadcast_pre': lambda x: x[None, :], 'broadcast_post': lambda x: x[:, None],
+    'wsum': _wsum, 'einsum': np.einsum, 'reshape2d': lambda x, n, m: x.reshape(n, m),
+    'flatten1d': lambda x: x.reshape(-1), 'identity': lambda x: x, 'abs': np.abs, 'sign': np.sign,
+    'log': np.log, 'concatenate': np.concatenate, 'real': np.real, 'imag': np.imag,
+    'conjugate': np.conjugate, 'array': np.array,
+}
+
+
+def build_vector_field(source: str, func_name: str = "vector_field") -> Callable:
+    """exec the generated function text (base_backend.py:537-578) against the op table."""
+    ns = dict(OPS)
+    body = source[source.index(f"def {func_name}"):]
+    exec(compile(body, f"<oracle:{func_name}>", "exec"), ns)
+    return ns[func_name]
+
+
+# ----------------------------------------------------------------------------- solvers
+def _prep(T, dt, dts, y):
+    steps = int(np.round(T / dt))
+    store_steps = int(np.round(T / dts))
+    store_step = int(np.round(dts / dt))
+    rec = np.empty((store_steps, y.shape[0]) if y.shape else (store_steps, 1), dtype=y.dtype)
+    return steps, store_step, rec
+
+
+def solve_euler(func, args, T, dt, dts, y, t0):
+    """base_backend.py:712-740 (sample before update; integer step passed as t)."""
+    steps, store_step, rec = _prep(T, dt, dts, y)
+    idx = 0
+    for i in range(steps):
+        if i % store_step == 0:
+            rec[idx, :] = y
+            idx += 1
+        step = i + t0
+        rhs = func(step, y, *args)
+        y += dt * rhs
+    return rec
+
+
+def solve_heun(func, args, T, dt, dts, y, t0):
+    """base_backend.py:742-769 verbatim semantics, including the in-place ``dy`` aliasing."""
+    steps, store_step, rec = _prep(T, dt, dts, y)
+    idx = 0
+    for i in range(steps):
+        if i % store_step == 0:
+            rec[idx, :] = y
+            idx += 1
+        step = i + t0
+        rhs = func(step, y, *args)
+        y_0 = y + dt * rhs
+        y += dt / 2 * (rhs + func(step, y_0, *args))
+    return rec
+
+
+def solve_heun_true(func, args, T, dt, dts, y, t0):
+    """Textbook Heun (explicit trapezoid): the first stage is copied before the second call."""
+    steps, store_step, rec = _prep(T, dt, dts, y)
+    idx = 0
+    for i in range(steps):
+        if i % store_step == 0:
+            rec[idx, :] = y
+            idx += 1
+        step = i + t0
+        k1 = func(step, y, *args).copy()
+        y_0 = y + dt * k1
+        k2 = func(step, y_0, *args)
+        y += dt / 2 * (k1 + k2)
+    return rec
+
+
+def solve_rk4(func, args, T, dt, dts, y, t0):
+    """Classic RK4 around the reference rhs (project definition, see module docstring)."""
+    steps, store_step, rec = _prep(T, dt, dts, y)
+    idx = 0
+    for i in range(steps):
+        if i % store_step == 0:
+            rec[idx, :] = y
+            idx += 1
+        step = i + t0
+        k1 = func(step, y, *args).copy()
+        k2 = func(step, y + (dt / 2) * k1, *args).copy()
+        k3 = func(step, y + (dt / 2) * k2, *args).copy()
+        k4 = func(step, y + dt * k3, *args)
+        y += (dt / 6) * (k1 + 2 * k2 + 2 * k3 + k4)
+    return rec
+
+
+SOLVERS = {"euler": solve_euler, "heun": solve_heun, "heun_true": solve_heun_true, "rk4": solve_rk4}
+
+
+def run(func, func_args: Sequence, T: float, dt: float, dts: float = None, solver: str = "euler"):
+    """base_backend.py:596-611: returns ``(state_rec[round(T/dts), n_state], times)``.
+    ``func_args = (t0, y0, dy, *consts)``; ``y0`` and mutable buffers are modified in place like
+    the reference does."""
+    t0, y0 = func_args[0], func_args[1]
+    step = dts if dts else dt
+    times = np.linspace(0.0, T, num=round(T / step), endpoint=False)
+    rec = SOLVERS[solver](func, tuple(func_args[2:]), T, dt, step, y0, t0)
+    return rec, times
+
+
+# ----------------------------------------------------------------------------- fixtures
+def load_fixture(path: str) -> dict:
+    """Load a golden fixture written by oracle/make_golden.py (format of pyrates_b200.Program.save
+    plus reference outputs).  Independent of the product package on purpose."""
+    with np.load(path, allow_pickle=False) as d:
+        meta = json.loads(bytes(np.asarray(d["__program__"]).tobytes()).decode())
+        args = [np.array(d[f"arg{i}"]) for i in range(len(meta["args"]))]
+        extra = {k: np.array(d[k]) for k in d.files if not k.startswith("arg") and k != "__program__"}
+    names = [a["name"] for a in meta["args"]]
+    lines = [f"def {meta['func_name']}({','.join(names)}):"]
+    for lhs, rhs, idx in meta["stmts"]:
+        lines.append(f"\t{lhs}[{idx}] = {rhs}" if idx is not None else f"\t{lhs} = {rhs}")
+    lines.append(f"\treturn {names[2]}")
+    run_meta = json.loads(bytes(extra.pop("__run__").tobytes()).decode()) if "__run__" in extra else {}
+    return {"meta": meta, "args": args, "names": names, "source": "\n".join(lines) + "\n",
+            "run": run_meta, "extra": extra}
+
+
+def run_fixture(fx: dict, solver: str = None, T: float = None, dt: float = None, dts: float = None):
+    """Integrate a loaded fixture with the oracle; returns ``(state_rec, times)``."""
+    r = fx["run"]
+    func = build_vector_field(fx["source"], fx["meta"]["func_name"])
+    args = [np.array(a, copy=True) for a in fx["args"]]
+    args[0] = args[0][()] if args[0].ndim == 0 else args[0]
+    return run(func, args, T if T is not None else r["T"], dt if dt is not None else r["dt"],
+               dts if dts is not None else r.get("dts"), solver or r["solver"])
