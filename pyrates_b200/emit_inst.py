@@ -1,0 +1,230 @@
+"""CUDA C emitter for the *instance* execution model (one thread = one sweep instance).
+
+Input: the scalar DAG produced by ``scalarize`` (walks the same compute-graph assignment stream the
+reference's NumPy backend prints, pyrates/backend/computegraph.py:1109-1228).  Output: one CUDA C
+translation unit = kernel ABI + generated ``prb_rhs`` / ``prb_record`` + the hand-written solver
+template ``csrc/templates/inst_kernel.cuh`` (fused rhs + Euler/Heun/RK4 update + decimated observer store).
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import numpy as np
+
+from .scalarize import ScalarRhs
+
+_TPL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "templates")
+
+SOLVER_IDS = {"euler": 0, "heun": 1, "heun_ref": 1, "heun_true": 2, "rk4": 3}
+
+_FUNC = {"exp": "exp", "log": "log", "sin": "sin", "cos": "cos", "tan": "tan", "tanh": "tanh", "sinh": "sinh",
+         "cosh": "cosh", "arctan": "atan", "arcsin": "asin", "arccos": "acos", "sqrt": "sqrt", "abs": "fabs",
+         "round": "rint"}
+
+
+def read_template(name: str) -> str:
+    with open(os.path.join(_TPL, name)) as f:
+        return f.read()
+
+
+@dataclass
+class InstKernel:
+    source: str
+    n_state: int
+    n_params: int
+    n_slots: int
+    n_obs: int
+    ring_elems: int          # total ring elements per instance
+    ring_init: np.ndarray    # [ring_elems] initial contents (physical layout == logical at head 0)
+    ring_rolls: List[int]
+    ring_lengths: List[int]
+    table_values: np.ndarray  # packed tables
+    slot_init: np.ndarray
+    param_defaults: np.ndarray
+    block: int
+    solver: str
+    precision: str
+    evals_per_step: int
+    kernel_name: str = "prb_integrate"
+
+
+def _lit(v: float, f32: bool) -> str:
+    if math.isnan(v):
+        return "(real)NAN" if False else ("__int_as_float(0x7fc00000)" if f32 else "__longlong_as_double(0x7ff8000000000000LL)")
+    if math.isinf(v):
+        s = "-" if v < 0 else ""
+        return f"({s}__int_as_float(0x7f800000))" if f32 else f"({s}__longlong_as_double(0x7ff0000000000000LL))"
+    if f32:
+        r = repr(float(np.float32(v)))
+        if "e" not in r and "." not in r:
+            r += ".0"
+        r += "f"
+    else:
+        r = repr(float(v))
+        if "e" not in r and "." not in r:
+            r += ".0"
+    return f"({r})" if r.startswith("-") else r
+
+
+def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool) -> List[str]:
+    """Straight-line statements computing dy[] (+ ring / slot stores) from y[], T."""
+    g = rhs.graph
+    ring_off = np.cumsum([0] + [r.rows * r.length for r in rhs.rings])
+    tab_off = np.cumsum([0] + [int(np.prod(t.shape)) for t in rhs.tables])
+    lines: List[str] = []
+
+    def ref(i: int, want_real: bool = True) -> str:
+        op = g.ops[i]
+        if op == "const":
+            v = g.const_value(i)
+            if g.isint[i]:
+                return _lit(float(v), f32) if want_real else (f"({int(v)}LL)" if v < 0 else f"{int(v)}LL")
+            return _lit(float(v), f32)
+        if op == "state":
+            return f"y[{g.payload[i]}]"
+        if op == "param":
+            return f"T.p[{g.payload[i]}]"
+        if op == "t":
+            return "((real)t)" if want_real else "t"
+        name = f"v{i}"
+        if g.isint[i] and want_real:
+            return f"((real){name})"
+        return name
+
+    for i in rhs.live_nodes():
+        op, a = g.ops[i], g.args[i]
+        if op in ("const", "state", "param", "t"):
+            continue
+        if g.isint[i]:
+            x, y_ = (ref(a[0], False), ref(a[1], False) if len(a) > 1 else None)
+            expr = {"add": f"{x} + {y_}", "sub": f"{x} - {y_}", "mul": f"{x} * {y_}", "neg": f"-{x}"}[op]
+            lines.append(f"const long long v{i} = {expr};")
+            continue
+        if op == "slot":
+            expr = f"T.slots[{g.payload[i]}LL * T.B + T.b]"
+        elif op == "table":
+            tab, tnode, col, ncols = g.payload[i]
+            expr = f"T.tables[{int(tab_off[tab])}LL + {ref(tnode, False)} * {ncols}LL + {col}LL]"
+        elif op == "ring":
+            ring, row, col, shift = g.payload[i]
+            L = rhs.rings[ring].length
+            expr = (f"T.rings[({int(ring_off[ring]) + row * L}LL + prb_ring_pos(T.head[{ring}], {col - shift}, {L})) "
+                    f"* T.B + T.b]")
+        elif op == "add":
+            expr = f"{ref(a[0])} + {ref(a[1])}"
+        elif op == "sub":
+            expr = f"{ref(a[0])} - {ref(a[1])}"
+        elif op == "mul":
+            expr = f"{ref(a[0])} * {ref(a[1])}"
+        elif op == "div":
+            if const_div_to_mul and g.is_const(a[1]) and float(g.const_value(a[1])) != 0.0:
+                c = float(g.const_value(a[1]))
+                inv = float(np.float32(1.0) / np.float32(c)) if f32 else 1.0 / c
+                expr = f"{ref(a[0])} * {_lit(inv, f32)}"
+            else:
+                expr = f"{ref(a[0])} / {ref(a[1])}"
+        elif op == "neg":
+            expr = f"-{ref(a[0])}"
+        elif op == "pow":
+            expr = f"pow({ref(a[0])}, {ref(a[1])})"
+        elif op == "maximum":
+            expr = f"prb_max({ref(a[0])}, {ref(a[1])})"
+        elif op == "minimum":
+            expr = f"prb_min({ref(a[0])}, {ref(a[1])})"
+        elif op == "sign":
+            expr = f"prb_sign({ref(a[0])})"
+        elif op in _FUNC:
+            expr = f"{_FUNC[op]}({ref(a[0])})"
+        else:
+            raise NotImplementedError(f"no CUDA lowering for op `{op}`")
+        lines.append(f"const real v{i} = {expr};")
+    for j, n in enumerate(rhs.dy):
+        lines.append(f"dy[{j}] = {ref(n)};")
+    for ring, row, col, node in rhs.ring_writes:
+        spec = rhs.rings[ring]
+        L = spec.length
+        lines.append(f"T.rings[({int(ring_off[ring]) + row * L}LL + prb_ring_pos(T.head[{ring}], "
+                     f"{col - spec.rolls_per_eval}, {L})) * T.B + T.b] = {ref(node)};")
+    for slot, node in rhs.slot_writes:
+        lines.append(f"T.slots[{slot}LL * T.B + T.b] = {ref(node)};")
+    for k, r in enumerate(rhs.rings):
+        if r.rolls_per_eval:
+            lines.append(f"T.head[{k}] = (T.head[{k}] + {r.rolls_per_eval % r.length}) % {r.length};")
+    return lines
+
+
+def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: Sequence[int],
+                     block: int = 128, const_div_to_mul: bool = False) -> InstKernel:
+    """Generate the full CUDA C source of the fused rhs+solver instance kernel."""
+    if solver not in SOLVER_IDS:
+        raise ValueError(f"unknown solver `{solver}`; supported: {sorted(SOLVER_IDS)}")
+    f32 = precision == "float32"
+    ns = rhs.n_state
+    nrings = len(rhs.rings)
+    body = emit_rhs_body(rhs, f32, const_div_to_mul)
+    np_ = len(rhs.params)
+    src: List[str] = []
+    src.append("// Generated by pyrates_b200.emit_inst — do not edit.  Instance execution model (1 thread = 1 instance).")
+    src.append(read_template("prb_kernel_abi.cuh"))
+    src.append(f"typedef {'float' if f32 else 'double'} real;")
+    src.append(f"#define PRB_NS {ns}")
+    src.append(f"#define PRB_NP {np_}")
+    src.append(f"#define PRB_NOBS {len(observers)}")
+    src.append(f"#define PRB_NRINGS {nrings}")
+    src.append(f"#define PRB_SOLVER {SOLVER_IDS[solver]}")
+    src.append(f"#define PRB_BLOCK {block}")
+    if ns > 64:
+        src.append("#define PRB_UNROLL_NS")        # big states: keep loops rolled (state spills to local memory)
+    src.append("""
+struct PrbThread {
+    long long b, B;
+    real p[PRB_NP > 0 ? PRB_NP : 1];
+    int head[PRB_NRINGS > 0 ? PRB_NRINGS : 1];
+    real* __restrict__ slots;
+    real* __restrict__ rings;
+    const real* __restrict__ tables;
+};
+__device__ __forceinline__ real prb_max(real a, real b) { return (a != a || b != b) ? a + b : (a > b ? a : b); }
+__device__ __forceinline__ real prb_min(real a, real b) { return (a != a || b != b) ? a + b : (a < b ? a : b); }
+__device__ __forceinline__ real prb_sign(real a) { return (real)((a > (real)0) - (a < (real)0)); }
+// physical ring position of logical column `col` (may be negative by the pending roll) at head `head`
+__device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
+    int p = col - head;
+    p += (p < 0) ? L : 0;
+    p += (p < 0) ? L : 0;
+    return (long long)p;
+}
+""")
+    init = ["__device__ __forceinline__ void prb_thread_init(PrbThread& T, const prb_kernel_args& A, long long b) {",
+            "    T.b = b; T.B = A.n_inst;",
+            "    T.slots = (real*)A.slots; T.rings = (real*)A.rings; T.tables = (const real*)A.tables;"]
+    if np_:
+        init.append("    const real* __restrict__ P = (const real*)A.params;")
+        init.append("    _Pragma(\"unroll\") for (int k = 0; k < PRB_NP; ++k) T.p[k] = P[(long long)k * T.B + b];")
+    for k, r in enumerate(rhs.rings):
+        init.append(f"    T.head[{k}] = (int)((A.eval0 * {r.rolls_per_eval}LL) % {r.length}LL);")
+    init.append("}")
+    init.append("__device__ __forceinline__ void prb_thread_exit(PrbThread&, const prb_kernel_args&, long long) {}")
+    src.append("\n".join(init))
+    src.append("__device__ __forceinline__ void prb_rhs(const long long t, const real (&y)[PRB_NS], real (&dy)[PRB_NS], PrbThread& T) {")
+    src.extend("    " + l for l in body)
+    src.append("}")
+    rec = ["__device__ __forceinline__ void prb_record(const real (&y)[PRB_NS], real* __restrict__ row, long long b, long long B) {"]
+    for o, idx in enumerate(observers):
+        if not 0 <= idx < ns:
+            raise ValueError(f"observer index {idx} out of range")
+        rec.append(f"    row[{o}LL * B + b] = y[{idx}];")
+    rec.append("}")
+    src.append("\n".join(rec))
+    src.append(read_template("inst_kernel.cuh"))
+
+    ring_init = np.concatenate([r.init.reshape(-1) for r in rhs.rings]) if rhs.rings else np.zeros(0)
+    tabs = np.concatenate([np.asarray(t.value, dtype=np.float64).reshape(-1) for t in rhs.tables]) if rhs.tables else np.zeros(0)
+    evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4}[solver]
+    return InstKernel("\n".join(src) + "\n", ns, np_, len(rhs.slots), len(observers), int(ring_init.size), ring_init,
+                      [r.rolls_per_eval for r in rhs.rings], [r.length for r in rhs.rings], tabs,
+                      np.array([s[2] for s in rhs.slots], dtype=np.float64),
+                      np.array([p.default for p in rhs.params], dtype=np.float64), block, solver, precision, evals)

@@ -1,0 +1,185 @@
+"""Host-side driver of the instance execution model: Program -> JIT kernel -> device session -> results.
+
+This is the CUDA counterpart of ``BaseBackend.run`` + ``_solve_*`` (pyrates/backend/base/base_backend.py:
+596-611, 693-769): ``InstanceModel`` owns the compiled kernel of one model, ``InstanceSession`` the
+device buffers of one batch of B sweep instances.  Everything numerical happens in the generated kernel;
+the host only allocates, copies and launches through the C ABI (``pyrates_b200.runtime``).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import runtime as rt
+from .emit_inst import InstKernel, emit_inst_kernel
+from .program import Program
+from .scalarize import ScalarRhs, scalarize
+
+__all__ = ["InstanceModel", "InstanceSession", "n_steps_for", "FIXED_STEP_SOLVERS"]
+
+FIXED_STEP_SOLVERS = ("euler", "heun", "heun_true", "rk4")
+
+
+def n_steps_for(T: float, dt: float, dts: Optional[float]) -> Tuple[int, int, int]:
+    """(steps, store_step, n_samples) exactly as the reference computes them (base_backend.py:716-719)."""
+    dts = dts if dts else dt
+    steps = int(np.round(T / dt))
+    n_samples = int(np.round(T / dts))
+    store_step = int(np.round(dts / dt))
+    return steps, max(store_step, 1), n_samples
+
+
+class InstanceModel:
+    """One model compiled for the instance execution model (one thread per sweep instance)."""
+
+    def __init__(self, prog: Program, *, solver: str = "euler", sweep: Sequence[Tuple[str, int]] = (),
+                 observers: Optional[Sequence[int]] = None, block: int = 128, fmad: bool = True,
+                 const_div_to_mul: bool = False, max_nodes: int = 60000):
+        if solver not in FIXED_STEP_SOLVERS:
+            raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
+                                      f"Supported solvers: {list(FIXED_STEP_SOLVERS)}.")
+        self.prog = prog
+        self.solver = solver
+        self.precision = prog.float_precision
+        self.real = prog.real_dtype
+        self.rhs: ScalarRhs = scalarize(prog, sweep, max_nodes=max_nodes)
+        self.observers = list(range(prog.n_state)) if observers is None else [int(o) for o in observers]
+        self.kernel: InstKernel = emit_inst_kernel(self.rhs, solver=solver, precision=self.precision,
+                                                   observers=self.observers, block=block,
+                                                   const_div_to_mul=const_div_to_mul)
+        self.fmad = fmad
+        self._module: Optional[rt.Module] = None
+        self.t0 = int(np.asarray(prog.arg_by_kind("t").value))
+
+    @property
+    def module(self) -> rt.Module:
+        if self._module is None:
+            self._module = rt.compile_module(self.kernel.source, f"prb_inst_{self.solver}.cu", fmad=self.fmad)
+        return self._module
+
+    @property
+    def n_state(self) -> int:
+        return self.kernel.n_state
+
+    @property
+    def n_params(self) -> int:
+        return self.kernel.n_params
+
+    def session(self, n_inst: int = 1, n_samples: int = 0, stream=None) -> "InstanceSession":
+        return InstanceSession(self, n_inst, n_samples, stream)
+
+    # convenience: the drop-in path of BaseBackend.run for a single instance
+    def run(self, T: float, dt: float, dts: Optional[float] = None, *, params: Optional[np.ndarray] = None,
+            y0: Optional[np.ndarray] = None, n_inst: Optional[int] = None):
+        steps, store_step, n_samples = n_steps_for(T, dt, dts)
+        if n_inst is None:
+            n_inst = 1 if params is None else int(np.asarray(params).shape[-1])
+        s = self.session(n_inst, n_samples)
+        try:
+            s.reset(y0=y0, params=params)
+            s.launch(steps, dt, store_step)
+            out = s.download()
+            y_final = s.download_state()
+        finally:
+            s.free()
+        return out, y_final
+
+
+class InstanceSession:
+    """Device buffers of a batch of B instances of one ``InstanceModel``."""
+
+    def __init__(self, model: InstanceModel, n_inst: int, n_samples: int, stream=None):
+        self.m = model
+        k = model.kernel
+        self.B = int(n_inst)
+        self.n_samples = int(n_samples)
+        self.stream = stream
+        r = np.dtype(model.real).itemsize
+        B = self.B
+        self.d_y = rt.DeviceBuffer(k.n_state * B * r)
+        self.d_out = rt.DeviceBuffer(max(self.n_samples * k.n_obs * B * r, 8))
+        self.d_params = rt.DeviceBuffer(max(k.n_params * B * r, 8))
+        self.d_slots = rt.DeviceBuffer(max(k.n_slots * B * r, 8))
+        self.d_rings = rt.DeviceBuffer(max(k.ring_elems * B * r, 8))
+        self.d_tables = rt.DeviceBuffer.from_host(np.asarray(k.table_values, dtype=model.real)) \
+            if k.table_values.size else rt.DeviceBuffer(8)
+        self.steps_done = 0
+        self.samples_done = 0
+
+    # -- state management
+    def reset(self, y0: Optional[np.ndarray] = None, params: Optional[np.ndarray] = None):
+        """(Re-)initialise state, parameters, slots and ring buffers; host->device copies."""
+        k, B, real = self.m.kernel, self.B, self.m.real
+        y0 = self.m.prog.y0 if y0 is None else np.asarray(y0)
+        if y0.ndim == 1:
+            y0 = np.repeat(y0.astype(real)[:, None], B, axis=1)
+        if y0.shape != (k.n_state, B):
+            raise ValueError(f"y0 must have shape ({k.n_state},) or ({k.n_state}, {B})")
+        self.d_y.upload(np.ascontiguousarray(y0, dtype=real), self.stream)
+        if k.n_params:
+            if params is None:
+                params = np.repeat(k.param_defaults.astype(real)[:, None], B, axis=1)
+            self.upload_params(params)
+        if k.n_slots:
+            self.d_slots.upload(np.repeat(k.slot_init.astype(real)[:, None], B, axis=1), self.stream)
+        if k.ring_elems:
+            self.d_rings.upload(np.repeat(k.ring_init.astype(real)[:, None], B, axis=1), self.stream)
+        self.steps_done = 0
+        self.samples_done = 0
+
+    def upload_params(self, params: np.ndarray):
+        k, B = self.m.kernel, self.B
+        params = np.ascontiguousarray(params, dtype=self.m.real)
+        if params.shape != (k.n_params, B):
+            raise ValueError(f"params must have shape ({k.n_params}, {B}), got {params.shape}")
+        self.d_params.upload(params, self.stream)
+
+    # -- launch
+    def launch(self, n_steps: int, dt: float, store_step: int = 1):
+        """Advance all instances by ``n_steps`` solver steps (asynchronous on the session's stream)."""
+        k = self.m.kernel
+        new_samples = 0
+        if n_steps > 0:
+            first = (-self.steps_done) % store_step
+            if first < n_steps:
+                new_samples = (n_steps - 1 - first) // store_step + 1
+        if self.samples_done + new_samples > self.n_samples:
+            raise ValueError(f"launch would record {self.samples_done + new_samples} samples but the session "
+                             f"holds only {self.n_samples}")
+        a = rt.KernelArgs()
+        a.n_steps, a.store_step, a.step0 = int(n_steps), int(store_step), int(self.steps_done)
+        a.t0, a.eval0 = self.m.t0, int(self.steps_done) * k.evals_per_step
+        a.n_inst, a.sample0, a.dt = self.B, int(self.samples_done), float(dt)
+        a.y, a.out, a.params = self.d_y.ptr, self.d_out.ptr, self.d_params.ptr
+        a.slots, a.rings, a.tables = self.d_slots.ptr, self.d_rings.ptr, self.d_tables.ptr
+        a.consts = a.iconsts = a.work = a.sync = None
+        self.m.module.run(k.kernel_name, a, block=k.block, stream=self.stream)
+        self.steps_done += int(n_steps)
+        self.samples_done += new_samples
+
+    # -- results
+    def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Recorded observers as ``[n_samples, n_obs, B]`` (row k = state at step k*store_step)."""
+        k = self.m.kernel
+        shape = (self.n_samples, k.n_obs, self.B)
+        if out is None:
+            out = np.empty(shape, dtype=self.m.real)
+        self.d_out.download(out.reshape(-1)[: int(np.prod(shape))].reshape(shape) if out.shape != shape else out,
+                            self.stream)
+        if self.stream is not None:
+            self.stream.synchronize() if hasattr(self.stream, "synchronize") else rt.synchronize()
+        return out
+
+    def download_state(self) -> np.ndarray:
+        y = np.empty((self.m.kernel.n_state, self.B), dtype=self.m.real)
+        self.d_y.download(y, self.stream)
+        if self.stream is not None:
+            self.stream.synchronize() if hasattr(self.stream, "synchronize") else rt.synchronize()
+        return y
+
+    def free(self):
+        for n in ("d_y", "d_out", "d_params", "d_slots", "d_rings", "d_tables"):
+            b = getattr(self, n, None)
+            if b is not None:
+                b.free()

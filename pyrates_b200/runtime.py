@@ -1,0 +1,367 @@
+"""ctypes binding of libprb (include/prb.h) — the only way the Python host side touches the GPU.
+
+No CPU execution path exists: if ``libprb.so`` is missing or the CUDA driver cannot be loaded, every
+compute call raises ``CudaBackendError``.  ``prb_compile`` (NVRTC) works without a GPU, which is what
+the CPU test-suite uses to check that every generated kernel builds for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import threading
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+__all__ = ["CudaBackendError", "lib", "Module", "DeviceBuffer", "compile_module", "KernelArgs", "RunDesc",
+           "device_info", "launch_count", "Stream", "Event", "synchronize", "PinnedBuffer", "set_device"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libprb.so")
+ARCH = "sm_100a"
+
+
+class CudaBackendError(RuntimeError):
+    """Raised for every libprb failure (mirrors PyRatesException of the reference,
+    pyrates/backend/__init__.py:42)."""
+
+
+class KernelArgs(C.Structure):
+    _fields_ = [("n_steps", C.c_int64), ("store_step", C.c_int64), ("step0", C.c_int64), ("t0", C.c_int64),
+                ("eval0", C.c_int64), ("n_inst", C.c_int64), ("sample0", C.c_int64), ("dt", C.c_double),
+                ("y", C.c_void_p), ("out", C.c_void_p), ("params", C.c_void_p), ("slots", C.c_void_p),
+                ("rings", C.c_void_p), ("tables", C.c_void_p), ("consts", C.c_void_p), ("iconsts", C.c_void_p),
+                ("work", C.c_void_p), ("sync", C.c_void_p)]
+
+
+class RunDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("cooperative", C.c_int32), ("grid_dim", C.c_uint32),
+                ("block_dim", C.c_uint32), ("smem_bytes", C.c_uint32), ("reserved", C.c_uint32),
+                ("stream", C.c_void_p), ("args", KernelArgs)]
+
+
+class DeviceInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 128), ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
+                ("sm_count", C.c_int32), ("max_smem_per_block_optin", C.c_int32), ("l2_bytes", C.c_int32),
+                ("clock_khz", C.c_int32), ("total_mem", C.c_int64)]
+
+
+class KernelInfo(C.Structure):
+    _fields_ = [("regs", C.c_int32), ("static_smem", C.c_int32), ("local_bytes", C.c_int32),
+                ("max_threads", C.c_int32), ("max_blocks_per_sm", C.c_int32)]
+
+
+# exported symbols of include/prb.h with (restype, argtypes); tests check that all of them resolve
+SYMBOLS = {
+    "prb_abi_version": (C.c_int, []),
+    "prb_last_error": (C.c_char_p, []),
+    "prb_launch_count": (C.c_int64, []),
+    "prb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "prb_set_device": (C.c_int, [C.c_int]),
+    "prb_get_device_info": (C.c_int, [C.POINTER(DeviceInfo)]),
+    "prb_device_synchronize": (C.c_int, []),
+    "prb_compile": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_void_p)]),
+    "prb_module_from_cubin": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "prb_module_cubin": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "prb_module_log": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p)]),
+    "prb_module_free": (C.c_int, [C.c_void_p]),
+    "prb_kernel_get_info": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(KernelInfo)]),
+    "prb_run": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(RunDesc)]),
+    "prb_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "prb_free": (C.c_int, [C.c_void_p]),
+    "prb_memset": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
+    "prb_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "prb_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "prb_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "prb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "prb_host_free": (C.c_int, [C.c_void_p]),
+    "prb_stream_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "prb_stream_destroy": (C.c_int, [C.c_void_p]),
+    "prb_stream_synchronize": (C.c_int, [C.c_void_p]),
+    "prb_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "prb_event_destroy": (C.c_int, [C.c_void_p]),
+    "prb_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "prb_event_synchronize": (C.c_int, [C.c_void_p]),
+    "prb_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def lib():
+    """Load libprb.so (built in-tree by ``__graft_entry__.build()`` / ``pyrates_b200.build``)."""
+    global _lib
+    if _lib is None:
+        with _lib_lock:
+            if _lib is None:
+                if not os.path.exists(_LIB_PATH):
+                    raise CudaBackendError(
+                        f"{_LIB_PATH} is missing — build it with `python -m pyrates_b200.build`; the CUDA backend "
+                        f"has no CPU fallback")
+                l = C.CDLL(_LIB_PATH)
+                for name, (res, args) in SYMBOLS.items():
+                    fn = getattr(l, name)
+                    fn.restype, fn.argtypes = res, args
+                if l.prb_abi_version() != 1:
+                    raise CudaBackendError("libprb ABI version mismatch; rebuild the library")
+                _lib = l
+    return _lib
+
+
+def _check(code: int):
+    if code != 0:
+        raise CudaBackendError(lib().prb_last_error().decode(errors="replace"))
+
+
+def set_device(ordinal: int):
+    _check(lib().prb_set_device(int(ordinal)))
+
+
+def device_info() -> dict:
+    info = DeviceInfo()
+    _check(lib().prb_get_device_info(C.byref(info)))
+    return {"name": info.name.decode(), "cc": (info.cc_major, info.cc_minor), "sm_count": info.sm_count,
+            "max_smem_optin": info.max_smem_per_block_optin, "l2_bytes": info.l2_bytes,
+            "clock_khz": info.clock_khz, "total_mem": info.total_mem}
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _check(lib().prb_device_count(C.byref(n)))
+    return n.value
+
+
+def launch_count() -> int:
+    return int(lib().prb_launch_count())
+
+
+def synchronize():
+    _check(lib().prb_device_synchronize())
+
+
+# ----------------------------------------------------------------------------- memory
+class DeviceBuffer:
+    """Caller-owned device allocation (the library never frees caller memory)."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        _check(lib().prb_malloc(C.byref(p), self.nbytes))
+        self.ptr = p.value
+
+    @classmethod
+    def from_host(cls, arr: np.ndarray, stream=None) -> "DeviceBuffer":
+        arr = np.ascontiguousarray(arr)
+        buf = cls(max(arr.nbytes, 1))
+        buf.upload(arr, stream)
+        return buf
+
+    def upload(self, arr: np.ndarray, stream=None, offset: int = 0):
+        arr = np.ascontiguousarray(arr)
+        if arr.nbytes + offset > self.nbytes:
+            raise ValueError("upload exceeds buffer size")
+        _check(lib().prb_memcpy_h2d(self.ptr + offset, arr.ctypes.data, arr.nbytes, _s(stream)))
+        if stream is None:
+            synchronize()
+
+    def download(self, out: np.ndarray, stream=None, offset: int = 0):
+        if not out.flags.c_contiguous or out.nbytes + offset > self.nbytes:
+            raise ValueError("download target must be contiguous and fit the buffer")
+        _check(lib().prb_memcpy_d2h(out.ctypes.data, self.ptr + offset, out.nbytes, _s(stream)))
+        if stream is None:
+            synchronize()
+        return out
+
+    def zero(self, stream=None):
+        _check(lib().prb_memset(self.ptr, 0, self.nbytes, _s(stream)))
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            try:
+                lib().prb_free(self.ptr)
+            finally:
+                self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """Pinned host memory exposed as a NumPy array (for async H2D/D2H in the end-to-end path)."""
+
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        _check(lib().prb_host_alloc(C.byref(p), max(self.nbytes, 1)))
+        self.ptr = p.value
+        self.array = np.frombuffer((C.c_char * max(self.nbytes, 1)).from_address(self.ptr), dtype=self.dtype,
+                                   count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            try:
+                lib().prb_host_free(self.ptr)
+            finally:
+                self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _s(stream):
+    return stream.handle if isinstance(stream, Stream) else stream
+
+
+class Stream:
+    def __init__(self):
+        p = C.c_void_p()
+        _check(lib().prb_stream_create(C.byref(p)))
+        self.handle = p.value
+
+    def synchronize(self):
+        _check(lib().prb_stream_synchronize(self.handle))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().prb_stream_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class Event:
+    def __init__(self):
+        p = C.c_void_p()
+        _check(lib().prb_event_create(C.byref(p)))
+        self.handle = p.value
+
+    def record(self, stream=None):
+        _check(lib().prb_event_record(self.handle, _s(stream)))
+
+    def synchronize(self):
+        _check(lib().prb_event_synchronize(self.handle))
+
+    def elapsed_ms(self, end: "Event") -> float:
+        ms = C.c_float()
+        _check(lib().prb_event_elapsed_ms(self.handle, end.handle, C.byref(ms)))
+        return float(ms.value)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().prb_event_destroy(self.handle)
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------- modules
+class Module:
+    """A JIT-compiled cubin (``prb_module``); kernels are loaded lazily on first launch."""
+
+    def __init__(self, handle: int, log: str = "", source: str = ""):
+        self.handle = handle
+        self.log = log
+        self.source = source
+
+    @property
+    def cubin(self) -> bytes:
+        data, size = C.c_void_p(), C.c_size_t()
+        _check(lib().prb_module_cubin(self.handle, C.byref(data), C.byref(size)))
+        return C.string_at(data.value, size.value)
+
+    def kernel_info(self, kernel: str, block: int = 0, smem: int = 0) -> dict:
+        info = KernelInfo()
+        _check(lib().prb_kernel_get_info(self.handle, kernel.encode(), block, smem, C.byref(info)))
+        return {"regs": info.regs, "static_smem": info.static_smem, "local_bytes": info.local_bytes,
+                "max_threads": info.max_threads, "max_blocks_per_sm": info.max_blocks_per_sm}
+
+    def run(self, kernel: str, args: KernelArgs, *, block: int, grid: int = 0, smem: int = 0,
+            cooperative: bool = False, stream=None):
+        d = RunDesc()
+        d.struct_size = C.sizeof(RunDesc)
+        d.cooperative = 1 if cooperative else 0
+        d.grid_dim, d.block_dim, d.smem_bytes = int(grid), int(block), int(smem)
+        d.stream = _s(stream)
+        d.args = args
+        _check(lib().prb_run(self.handle, kernel.encode(), C.byref(d)))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().prb_module_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+_module_cache: Dict[str, Module] = {}
+DEFAULT_OPTS = ("--std=c++17", "-lineinfo", "--extra-device-vectorization")
+
+
+def _cache_dir() -> Optional[str]:
+    d = os.environ.get("PRB_CACHE_DIR")
+    if d is None:
+        d = os.path.join(_HERE, "_jit_cache")
+    if d in ("", "0", "off"):
+        return None
+    try:
+        os.makedirs(d, exist_ok=True)
+        return d
+    except OSError:
+        return None
+
+
+def compile_module(source: str, name: str = "prb_kernel.cu", opts: Sequence[str] = (), *, fmad: bool = True,
+                   verbose_ptxas: bool = False) -> Module:
+    """NVRTC-compile ``source`` for sm_100a.  Cached in memory and on disk by source hash
+    (cf. the reference's SHA-256 module cache, base_backend.py:557)."""
+    all_opts = list(DEFAULT_OPTS) + list(opts) + [f"--fmad={'true' if fmad else 'false'}"]
+    if verbose_ptxas:
+        all_opts += ["--ptxas-options=-v"]
+    key = hashlib.sha256(("\0".join(all_opts) + "\0" + ARCH + "\0" + source).encode()).hexdigest()
+    m = _module_cache.get(key)
+    if m is not None:
+        return m
+    l = lib()
+    cdir = _cache_dir()
+    path = os.path.join(cdir, key + ".cubin") if cdir else None
+    handle = C.c_void_p()
+    if path and os.path.exists(path) and not verbose_ptxas:
+        with open(path, "rb") as f:
+            blob = f.read()
+        _check(l.prb_module_from_cubin(blob, len(blob), C.byref(handle)))
+        m = Module(handle.value, "", source)
+    else:
+        arr = (C.c_char_p * len(all_opts))(*[o.encode() for o in all_opts])
+        code = l.prb_compile(source.encode(), name.encode(), ARCH.encode(), arr, len(all_opts), C.byref(handle))
+        log = ""
+        if handle.value:
+            p = C.c_char_p()
+            l.prb_module_log(handle.value, C.byref(p))
+            log = (p.value or b"").decode(errors="replace")
+        if code != 0:
+            msg = l.prb_last_error().decode(errors="replace")
+            if handle.value:
+                l.prb_module_free(handle.value)
+            raise CudaBackendError(msg)
+        m = Module(handle.value, log, source)
+        if path:
+            try:
+                tmp = path + f".{os.getpid()}.tmp"
+                with open(tmp, "wb") as f:
+                    f.write(m.cubin)
+                os.replace(tmp, path)
+            except OSError:
+                pass
+    _module_cache[key] = m
+    return m

@@ -1,0 +1,50 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol include/prb.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from pyrates_b200 import runtime as rt
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "prb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(prb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported():
+    names = _declared_symbols()
+    assert len(names) >= 25
+    l = ctypes.CDLL(os.path.join(ROOT, "pyrates_b200", "libprb.so"))
+    missing = [n for n in names if not hasattr(l, n)]
+    assert not missing, missing
+    assert set(names) == set(rt.SYMBOLS), set(names) ^ set(rt.SYMBOLS)
+
+
+def test_struct_layout_matches_header():
+    assert ctypes.sizeof(rt.KernelArgs) == 8 * 8 + 10 * 8
+    assert ctypes.sizeof(rt.RunDesc) == 6 * 4 + 8 + ctypes.sizeof(rt.KernelArgs)
+    assert rt.lib().prb_abi_version() == 1
+
+
+def test_nvrtc_compiles_without_gpu_and_reports_errors():
+    os.environ["PRB_CACHE_DIR"] = "off"
+    m = rt.compile_module('extern "C" __global__ void k(float* x) { x[threadIdx.x] *= 2.f; }', "t.cu")
+    assert len(m.cubin) > 500 and m.cubin[:4] == b"\x7fELF"
+    with pytest.raises(rt.CudaBackendError, match="error"):
+        rt.compile_module('extern "C" __global__ void k(float* x) { x[0] = undefined_symbol; }', "bad.cu")
+
+
+def test_compute_calls_fail_loudly_without_device():
+    """No CPU fallback: on a box without the CUDA driver every compute entry point raises."""
+    try:
+        n = rt.device_count()
+    except rt.CudaBackendError as e:
+        assert "no CPU execution path" in str(e)
+        with pytest.raises(rt.CudaBackendError):
+            rt.DeviceBuffer(16)
+        return
+    assert n >= 1

@@ -1,0 +1,93 @@
+"""GPU parity (through the C ABI): fused rhs+solver instance kernels vs the golden trajectories of the
+reference NumPy backend (euler, aliased heun) and the oracle-defined heun_true / rk4.
+
+Tolerances are the north star's: rel 1e-9 in fp64, 1e-4 in fp32 (per-column scaled max error)."""
+import numpy as np
+import pytest
+
+from conftest import RTOL, golden_names, golden_path, traj_rel_err
+from oracle import numpy_oracle as orc
+from pyrates_b200 import runtime as rt
+from pyrates_b200.engine import InstanceModel, n_steps_for
+from pyrates_b200.program import Program
+
+pytestmark = pytest.mark.gpu
+
+SKIP = {"kuramoto_n128", "qsfa_both_n96", "wc_n128", "wc_n128_f32"}      # network-mode fixtures
+NAMES = [n for n in golden_names() if n not in SKIP]
+SOLVERS = ["euler", "heun", "heun_true", "rk4"]
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
+@pytest.mark.parametrize("name", NAMES)
+def test_instance_kernel_matches_golden(gpu, name, solver):
+    fx = orc.load_fixture(golden_path(name))
+    prog = Program.load(golden_path(name))
+    r = fx["run"]
+    before = rt.launch_count()
+    out, y_final = InstanceModel(prog, solver=solver).run(r["T"], r["dt"], r["dts"])
+    assert rt.launch_count() == before + 1          # one fused kernel launch for the whole simulation
+    ref = fx["extra"][f"rec_{solver}"]
+    got = out[:, :, 0]
+    assert got.shape == ref.shape
+    err = traj_rel_err(got, ref)
+    assert err <= RTOL[prog.float_precision], f"{name}/{solver}: rel err {err:.3e}"
+
+
+def test_state_writeback_and_chunked_launches(gpu):
+    """Two launches that continue from the device-resident state == one launch (step0/eval0/sample0
+    bookkeeping, ring-buffer heads included)."""
+    for name in ("qsfa_ring_n8", "net10", "qif_input"):
+        prog = Program.load(golden_path(name))
+        fx = orc.load_fixture(golden_path(name))
+        r = fx["run"]
+        steps, store_step, n_samples = n_steps_for(r["T"], r["dt"], r["dts"])
+        m = InstanceModel(prog, solver="heun")
+        s = m.session(1, n_samples)
+        s.reset()
+        cut = (steps // 3) | 1
+        s.launch(cut, r["dt"], store_step)
+        s.launch(steps - cut, r["dt"], store_step)
+        got = s.download()[:, :, 0]
+        s.free()
+        assert traj_rel_err(got, fx["extra"]["rec_heun"]) <= RTOL[prog.float_precision]
+
+
+@pytest.mark.parametrize("solver", ["heun", "rk4"])
+def test_jrc_sweep_batch_matches_per_instance_oracle(gpu, solver):
+    """grid_search-style batch: B instances with per-instance (C, u); spot-check instances against the oracle
+    run one instance at a time with the same parameters."""
+    prog = Program.load(golden_path("jrc"))
+    B = 1000
+    rng = np.random.default_rng(7)
+    C = rng.uniform(68.0, 1350.0, B)
+    u = rng.uniform(120.0, 320.0, B)
+    sweep = [("u", 0), ("weight_v2", 0), ("weight_v2", 1), ("weight", 0), ("weight_v1", 0)]
+    m = InstanceModel(prog, solver=solver, sweep=sweep, observers=[0, 2])
+    order = [(p.arg, p.elem) for p in m.rhs.params]
+    vals = {("u", 0): u, ("weight_v2", 0): C, ("weight_v2", 1): C / 4, ("weight", 0): 0.8 * C, ("weight_v1", 0): C / 4}
+    params = np.stack([vals[k] for k in order])
+    T, dt, dts = 0.05, 1e-4, 1e-3
+    out, _ = m.run(T, dt, dts, params=params)
+    assert out.shape == (50, 2, B)
+    f = orc.build_vector_field(prog.source())
+    for b in (0, 1, 499, 998, 999):
+        args = [np.array(a.value, copy=True) for a in prog.args]
+        names = [a.name for a in prog.args]
+        args[names.index("u")] = np.float64(u[b])
+        args[names.index("weight_v2")] = np.array([C[b], C[b] / 4])
+        args[names.index("weight")] = np.float64(0.8 * C[b])
+        args[names.index("weight_v1")] = np.float64(C[b] / 4)
+        rec, _ = orc.run(f, args, T, dt, dts, solver)
+        assert traj_rel_err(out[:, :, b], rec[:, [0, 2]]) <= 1e-9
+
+
+def test_missing_device_buffers_are_rejected(gpu):
+    a = rt.KernelArgs()
+    a.n_steps, a.store_step, a.n_inst = 1, 1, 1
+    m = InstanceModel(Program.load(golden_path("qif")), solver="euler")
+    with pytest.raises(rt.CudaBackendError, match="state pointer"):
+        m.module.run("prb_integrate", a, block=128)
+    a.y = 8
+    with pytest.raises(rt.CudaBackendError, match="not found"):
+        m.module.run("no_such_kernel", a, block=128)

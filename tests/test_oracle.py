@@ -1,0 +1,109 @@
+"""The oracle (oracle/numpy_oracle.py) pinned against the reference: golden trajectories produced by the
+real reference NumPy backend (bit-exact) and the reference's own hand-computed known-answer loops."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, golden_path
+from oracle import numpy_oracle as orc
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("solver", ["euler", "heun"])
+def test_oracle_reproduces_reference_bit_exact(name, solver):
+    fx = orc.load_fixture(golden_path(name))
+    rec, times = orc.run_fixture(fx, solver=solver)
+    ref = fx["extra"][f"rec_{solver}"]
+    assert rec.shape == ref.shape and rec.dtype == ref.dtype
+    assert np.array_equal(rec, ref, equal_nan=True), f"max abs diff {np.nanmax(np.abs(rec - ref))}"
+    r = fx["run"]
+    assert times.shape[0] == ref.shape[0] == round(r["T"] / (r["dts"] or r["dt"]))
+
+
+def test_reference_heun_is_aliased_not_textbook():
+    """SURVEY headline 4: `heun` == y + dt*f(y + dt*f(y)); textbook Heun differs measurably."""
+    fx = orc.load_fixture(golden_path("qif_dt2"))
+    ref = fx["extra"]["rec_heun"]
+    true_heun = fx["extra"]["rec_heun_true"]
+    f = orc.build_vector_field(fx["source"])
+    args = [np.array(a, copy=True) for a in fx["args"]]
+    y, dt = args[1].copy(), fx["run"]["dt"]
+    rec = []
+    ss = round(fx["run"]["dts"] / dt)
+    for i in range(round(fx["run"]["T"] / dt)):
+        if i % ss == 0:
+            rec.append(y.copy())
+        k1 = f(i, y, *args[2:]).copy()
+        k2 = f(i, y + dt * k1, *args[2:]).copy()
+        y = y + dt / 2 * (k2 + k2)
+    assert np.array_equal(np.array(rec), ref)
+    assert np.max(np.abs(true_heun - ref)) > 1e-4
+
+
+def test_ring_buffer_known_answer():
+    """reference tests/test_population_connectivity.py:361-415 (roll -> write -> read, d=4 steps)."""
+    fx = orc.load_fixture(golden_path("ring_kat"))
+    rec, _ = orc.run_fixture(fx, solver="euler")
+    N, d_steps, dt, tau_r = 2, 4, 1e-3, 0.1
+    W = np.array([[0., 0.5], [0.5, 0.]])
+    r, eta = np.array([1.0, 2.0]), np.array([5.0, 8.0])
+    buf = np.zeros((N, d_steps + 1))
+    ref = np.zeros((10, N))
+    for k in range(10):
+        ref[k] = r
+        buf = np.roll(buf, 1, axis=1)
+        buf[:, 0] = r
+        r = r + dt * ((-r + eta + W @ buf[:, d_steps]) / tau_r)
+    np.testing.assert_allclose(rec, ref, rtol=1e-12)
+    np.testing.assert_allclose(fx["extra"]["rec_euler"], ref, rtol=1e-5)   # the reference's own bar
+
+
+def test_gamma_cascade_known_answer():
+    """reference tests/test_population_connectivity.py:422-476 (n=6 stage ODE cascade)."""
+    fx = orc.load_fixture(golden_path("gamma_kat"))
+    rec, _ = orc.run_fixture(fx, solver="euler")
+    delay, spread, dt, tau_r = 5e-3, 2e-3, 1e-3, 0.1
+    n = max(1, int(round((delay / spread) ** 2)))
+    a = n / delay
+    W = np.array([[0., 0.5], [0.5, 0.]])
+    r, eta = np.array([1.0, 2.0]), np.array([5.0, 8.0])
+    z = np.zeros((n, 2))
+    ref = np.zeros((20, 2))
+    for k in range(20):
+        ref[k] = r
+        dz = np.zeros_like(z)
+        dz[0] = a * (r - z[0])
+        for j in range(1, n):
+            dz[j] = a * (z[j - 1] - z[j])
+        r, z = r + dt * ((-r + eta + W @ z[-1]) / tau_r), z + dt * dz
+    np.testing.assert_allclose(rec[:, :2], ref, rtol=1e-10)
+
+
+def test_kuramoto_first_euler_step_known_answer():
+    """reference tests/test_population_connectivity.py:238-283, restated through the oracle's op table."""
+    src = ("def vector_field(t,y,dy,K,s_ext,omega,weight):\n"
+           "\ttheta = y[0:2]\n"
+           "\ts_in = wsum(weight, -sin(broadcast_post(theta) - broadcast_pre(theta)))\n"
+           "\tdy[0:2] = K*s_in + omega + s_ext\n\treturn dy\n")
+    f = orc.build_vector_field(src)
+    y = np.array([0.0, np.pi / 2])
+    rec, _ = orc.run(f, [0, y, np.zeros(2), np.ones(2), 0.0, np.full(2, 10.0), np.array([[0., 1.], [1., 0.]])],
+                     2e-3, 1e-3, None, "euler")
+    np.testing.assert_allclose(rec[1], [0.011, np.pi / 2 + 0.009], rtol=1e-12)
+
+
+@pytest.mark.parametrize("solver,order", [("euler", 1), ("heun_true", 2), ("rk4", 4), ("heun", 1)])
+def test_solver_convergence_order(solver, order):
+    """RK4 / textbook Heun have no reference implementation: pin them on y' = -y + sin(t-free) problem
+    (analytic solution) by their convergence order.  The aliased reference `heun` is only 1st order."""
+    src = "def vector_field(t,y,dy,lam):\n\ta = y[0]\n\tdy[0] = lam*a - a**3\n\treturn dy\n"
+    f = orc.build_vector_field(src)
+    lam, y0, T = -1.5, 0.8, 1.0
+    # analytic solution of y' = lam*y - y^3 (Bernoulli): y^2 = lam / (1 - (1 - lam/y0^2) exp(-2 lam t))... use fine RK4 as truth
+    def final(dt, s):
+        y = np.array([y0])
+        n = round(T / dt)
+        rec, _ = orc.run(f, [0, y, np.zeros(1), lam], T + dt, dt, None, s)
+        return rec[n, 0]
+    truth = final(1e-4, "rk4")
+    e1, e2 = abs(final(2e-2, solver) - truth), abs(final(1e-2, solver) - truth)
+    assert abs(np.log2(e1 / e2) - order) < 0.35, (e1, e2)

@@ -1,0 +1,57 @@
+"""Front end on CPU: the scalarised DAG (what the instance kernels are printed from) evaluated with NumPy
+must reproduce the reference's Euler trajectories for every fixture small enough to unroll."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, golden_path, traj_rel_err
+from dag_eval import DagMachine
+from oracle import numpy_oracle as orc
+from pyrates_b200.program import Program
+from pyrates_b200.scalarize import UnsupportedModelError, scalarize
+
+LARGE = {"kuramoto_n128", "qsfa_both_n96"}
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n not in LARGE])
+def test_dag_matches_reference_euler(name):
+    fx = orc.load_fixture(golden_path(name))
+    prog = Program.load(golden_path(name))
+    rhs = scalarize(prog)
+    r = fx["run"]
+    ss = round((r["dts"] or r["dt"]) / r["dt"])
+    n_steps = min(round(r["T"] / r["dt"]), 40 * ss)
+    rec = DagMachine(rhs, prog.real_dtype).euler(prog.y0, int(prog.arg_by_kind("t").value), n_steps, r["dt"], ss)
+    ref = fx["extra"]["rec_euler"][: rec.shape[0]]
+    tol = 1e-12 if prog.float_precision == "float64" else 1e-5
+    assert traj_rel_err(rec, ref) <= tol
+
+
+@pytest.mark.parametrize("name", sorted(LARGE))
+def test_large_models_refuse_to_unroll(name):
+    with pytest.raises(UnsupportedModelError):
+        scalarize(Program.load(golden_path(name)))
+
+
+def test_program_roundtrip_and_source():
+    prog = Program.load(golden_path("net12"))
+    p2 = prog.clone()
+    assert p2.source() == prog.source()
+    assert [a.kind for a in prog.args][:3] == ["t", "y", "dy"]
+    assert prog.arg("a_buffer").kind == "var" and prog.arg("u").kind == "var"
+    p3 = Program.from_source(prog.source(), [(a.name, a.value) for a in prog.args], state_vars=prog.state_vars)
+    assert [s.text() for s in p3.stmts] == [s.text() for s in prog.stmts]
+
+
+def test_sweep_params_become_leaves():
+    prog = Program.load(golden_path("jrc"))
+    rhs = scalarize(prog, sweep=[("u", 0), ("weight", 0), ("weight_v2", 1)])
+    assert [(p.arg, p.elem) for p in rhs.params] == [("u", 0), ("weight_v2", 1), ("weight", 0)] or len(rhs.params) == 3
+    with pytest.raises(KeyError):
+        scalarize(prog, sweep=[("source_idx", 0)])
+
+
+def test_unsupported_ops_raise():
+    src = "def vector_field(t,y,dy,c):\n\ta = y[0]\n\tdy[0] = past(a, c)\n\treturn dy\n"
+    prog = Program.from_source(src, [("t", np.int32(0)), ("y", np.zeros(1)), ("dy", np.zeros(1)), ("c", np.float64(1))])
+    with pytest.raises(UnsupportedModelError):
+        scalarize(prog)
