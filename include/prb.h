@@ -152,6 +152,7 @@ int prb_host_free(void* hptr);
 int prb_stream_create(void** stream);
 int prb_stream_destroy(void* stream);
 int prb_stream_synchronize(void* stream);
+int prb_stream_wait_event(void* stream, void* event);   /* later work on `stream` waits for `event` */
 int prb_event_create(void** event);
 int prb_event_destroy(void* event);
 int prb_event_record(void* event, void* stream);

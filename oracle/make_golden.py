@@ -155,6 +155,31 @@ def _matrix_delay_test(kind):
     return build
 
 
+def _jrc_grid(n_c, n_u, T, dt, dts):
+    """reference grid_search over (C, u) like documentation/model_analysis/parameter_sweeps.py:44-90."""
+    def run(solver, precision):
+        from pyrates import grid_search
+        param_grid = {"C": np.linspace(68.0, 1350.0, n_c), "u": np.linspace(120.0, 320.0, n_u)}
+        param_map = {
+            "C": {"vars": ["weight"], "edges": [("pc/pro/m", "ein/rpo_e/m_in")]},
+            "C2": {"vars": ["weight"], "edges": [("ein/pro/m", "pc/rpo_e_in/m_in")]},
+            "C4": {"vars": ["weight"], "edges": [("pc/pro/m", "iin/rpo_e/m_in"), ("iin/pro/m", "pc/rpo_i/m_in")]},
+            "u": {"vars": ["rpo_e_in/u"], "nodes": ["pc"]},
+        }
+        import pandas as pd
+        from pyrates.utility import linearize_grid
+        grid = linearize_grid(param_grid, permute=True)
+        grid["C2"] = 0.8 * grid["C"]
+        grid["C4"] = 0.25 * grid["C"]
+        res, pmap = grid_search(NM + "jansenrit.JRC", grid, param_map, step_size=dt, simulation_time=T,
+                                outputs={"v": "pc/rpo_e_in/v"}, sampling_step_size=dts, solver=solver,
+                                backend="default", float_precision=precision, verbose=False, clear=True)
+        return {"grid_C": np.asarray(pmap["C"].values, dtype=np.float64), "grid_u": np.asarray(pmap["u"].values, dtype=np.float64),
+                f"frame_{solver}": np.asarray(res.values, dtype=np.float64),
+                "frame_columns": np.frombuffer(json.dumps([list(map(str, c)) for c in res.columns]).encode(), dtype=np.uint8)}
+    return run
+
+
 def _sin_input(n, cols=None):
     t = np.arange(n) * 1e-3
     if cols is None:
@@ -205,6 +230,9 @@ CASES = {
     "kuramoto_n8":       dict(build=_kuramoto(8), T=0.2, dt=1e-3, out="e/phase_op/theta"),
     "kuramoto_n128":     dict(build=_kuramoto(128), T=0.05, dt=1e-3, out="e/phase_op/theta"),
     "kuramoto_scalar_n128": dict(build=_kuramoto(128, dense=False), T=0.05, dt=1e-3, out="e/phase_op/theta"),
+    # reference grid_search (B deep copies vectorised into one circuit, pyrates/utility.py:189-275)
+    "jrc_grid_b16":   dict(run=_jrc_grid(4, 4, 0.05, 1e-4, 1e-3), T=0.05, dt=1e-4, dts=1e-3, out="pc/rpo_e_in/v"),
+    "jrc_grid_b1024": dict(run=_jrc_grid(32, 32, 2e-3, 1e-4, 1e-3), T=2e-3, dt=1e-4, dts=1e-3, out="pc/rpo_e_in/v"),
 }
 
 
@@ -217,16 +245,21 @@ def make_case(name: str, spec: dict, cap: Capture) -> str:
     prog = None
     first_args = None
     cwd = os.getcwd()
+    extra = {}
     for solver in ("euler", "heun"):
         clear_ir_caches()
-        circuit = spec["build"]()
-        inputs = spec["inputs"]() if "inputs" in spec else None
+        circuit = None
         with tempfile.TemporaryDirectory() as tmp:
             os.chdir(tmp)
             try:
-                circuit.run(simulation_time=T, step_size=dt, sampling_step_size=dts, solver=solver,
-                            outputs={"o": spec["out"]}, inputs=inputs, backend="default",
-                            float_precision=precision, verbose=False, clear=True)
+                if "run" in spec:
+                    extra.update(spec["run"](solver, precision))
+                else:
+                    circuit = spec["build"]()
+                    inputs = spec["inputs"]() if "inputs" in spec else None
+                    circuit.run(simulation_time=T, step_size=dt, sampling_step_size=dts, solver=solver,
+                                outputs={"o": spec["out"]}, inputs=inputs, backend="default",
+                                float_precision=precision, verbose=False, clear=True)
             finally:
                 os.chdir(cwd)
         recs[solver] = cap.rec
@@ -235,7 +268,8 @@ def make_case(name: str, spec: dict, cap: Capture) -> str:
             prog = Program.from_source(cap.source, list(zip(cap.names, cap.func_args)),
                                        state_vars=cap.state_vars, float_precision=precision)
         try:
-            clear(circuit)
+            if circuit is not None:
+                clear(circuit)
         except Exception:
             pass
     # oracle-defined solvers (no reference implementation): run around the reference-generated text
@@ -255,7 +289,7 @@ def make_case(name: str, spec: dict, cap: Capture) -> str:
                 "reference_version": "1.2.3", "out": spec["out"]}
     path = os.path.join(GOLDEN, f"{name}.npz")
     prog.save(path, __run__=np.frombuffer(json.dumps(run_meta).encode(), dtype=np.uint8),
-              **{f"rec_{k}": v for k, v in recs.items()})
+              **{f"rec_{k}": v for k, v in recs.items()}, **extra)
     return path
 
 

@@ -48,7 +48,7 @@ int fail(int code, const char* fmt, ...) {
     X(cuLaunchKernel) X(cuLaunchCooperativeKernel) X(cuMemAlloc_v2) X(cuMemFree_v2)               \
     X(cuMemsetD8Async) X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2) X(cuMemcpyDtoDAsync_v2)    \
     X(cuMemHostAlloc) X(cuMemFreeHost) X(cuStreamCreate) X(cuStreamDestroy_v2)                    \
-    X(cuStreamSynchronize) X(cuEventCreate) X(cuEventDestroy_v2) X(cuEventRecord)                 \
+    X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuEventCreate) X(cuEventDestroy_v2) X(cuEventRecord)                 \
     X(cuEventSynchronize) X(cuEventElapsedTime) X(cuGetErrorString) X(cuGetErrorName)
 
 struct Driver {
@@ -406,6 +406,11 @@ int prb_stream_destroy(void* stream) {
 int prb_stream_synchronize(void* stream) {
     if (int e = need_ctx()) return e;
     CU(cuStreamSynchronize((CUstream)stream));
+    return PRB_OK;
+}
+int prb_stream_wait_event(void* stream, void* event) {
+    if (int e = need_ctx()) return e;
+    CU(cuStreamWaitEvent((CUstream)stream, (CUevent)event, 0));
     return PRB_OK;
 }
 int prb_event_create(void** event) {

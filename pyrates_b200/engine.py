@@ -136,27 +136,38 @@ class InstanceSession:
         self.d_params.upload(params, self.stream)
 
     # -- launch
-    def launch(self, n_steps: int, dt: float, store_step: int = 1):
-        """Advance all instances by ``n_steps`` solver steps (asynchronous on the session's stream)."""
+    def samples_in(self, n_steps: int, store_step: int) -> int:
+        """Samples the next ``n_steps`` steps will record (sampling happens before a step when
+        step % store_step == 0, base_backend.py:730-733)."""
+        if n_steps <= 0:
+            return 0
+        first = (-self.steps_done) % store_step
+        return 0 if first >= n_steps else (n_steps - 1 - first) // store_step + 1
+
+    def launch(self, n_steps: int, dt: float, store_step: int = 1, out: Optional[rt.DeviceBuffer] = None,
+               out_capacity: Optional[int] = None):
+        """Advance all instances by ``n_steps`` solver steps (asynchronous on the session's stream).
+        With ``out`` the samples of this launch go to rows 0.. of that buffer (chunked/streamed runs)
+        instead of being appended to the session's own recording."""
         k = self.m.kernel
-        new_samples = 0
-        if n_steps > 0:
-            first = (-self.steps_done) % store_step
-            if first < n_steps:
-                new_samples = (n_steps - 1 - first) // store_step + 1
-        if self.samples_done + new_samples > self.n_samples:
+        new_samples = self.samples_in(n_steps, store_step)
+        if out is not None:
+            if new_samples > (out_capacity if out_capacity is not None else new_samples):
+                raise ValueError("chunk buffer too small for this launch")
+        elif self.samples_done + new_samples > self.n_samples:
             raise ValueError(f"launch would record {self.samples_done + new_samples} samples but the session "
                              f"holds only {self.n_samples}")
         a = rt.KernelArgs()
         a.n_steps, a.store_step, a.step0 = int(n_steps), int(store_step), int(self.steps_done)
         a.t0, a.eval0 = self.m.t0, int(self.steps_done) * k.evals_per_step
-        a.n_inst, a.sample0, a.dt = self.B, int(self.samples_done), float(dt)
-        a.y, a.out, a.params = self.d_y.ptr, self.d_out.ptr, self.d_params.ptr
+        a.n_inst, a.sample0, a.dt = self.B, (0 if out is not None else int(self.samples_done)), float(dt)
+        a.y, a.out, a.params = self.d_y.ptr, (out.ptr if out is not None else self.d_out.ptr), self.d_params.ptr
         a.slots, a.rings, a.tables = self.d_slots.ptr, self.d_rings.ptr, self.d_tables.ptr
         a.consts = a.iconsts = a.work = a.sync = None
         self.m.module.run(k.kernel_name, a, block=k.block, stream=self.stream)
         self.steps_done += int(n_steps)
         self.samples_done += new_samples
+        return new_samples
 
     # -- results
     def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:

@@ -79,6 +79,7 @@ SYMBOLS = {
     "prb_stream_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "prb_stream_destroy": (C.c_int, [C.c_void_p]),
     "prb_stream_synchronize": (C.c_int, [C.c_void_p]),
+    "prb_stream_wait_event": (C.c_int, [C.c_void_p, C.c_void_p]),
     "prb_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "prb_event_destroy": (C.c_int, [C.c_void_p]),
     "prb_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -230,6 +231,9 @@ class Stream:
 
     def synchronize(self):
         _check(lib().prb_stream_synchronize(self.handle))
+
+    def wait_event(self, event: "Event"):
+        _check(lib().prb_stream_wait_event(self.handle, event.handle))
 
     def __del__(self):
         try:

@@ -1,0 +1,155 @@
+"""Batched parameter sweeps: compile ONE instance of the model, integrate B parametrisations at once.
+
+Replaces the internals of ``pyrates.grid_search`` (pyrates/utility.py:189-275), which deep-copies the
+template once per grid point and vectorises the B copies into one circuit (build time superlinear in B,
+SURVEY.md headline 7).  Here the single-instance compute graph is lowered once; the swept parameters
+become per-instance kernel arguments laid out structure-of-arrays ``[n_param][B]``; one CUDA thread
+integrates one grid point with its state in registers.
+
+``BatchedSweep`` is the end-to-end engine (host parameters in -> host trajectories out):
+  * H2D of the parameter table and initial state from pinned staging buffers,
+  * the simulation is cut into time chunks; chunk c computes on the compute stream into one of two
+    device observer buffers while chunk c-1 is copied D2H on the copy stream straight into the
+    (pinned) result array — copies overlap compute, nothing is staged twice,
+  * instances shard contiguously across GPUs (one process per GPU); no data-path collective.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import runtime as rt
+from .engine import InstanceModel, n_steps_for
+from .program import Program
+
+__all__ = ["BatchedSweep", "shard_bounds"]
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous near-equal split of n sweep instances over `world` ranks (first n%world ranks get +1)."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class BatchedSweep:
+    """B parametrisations of one model, integrated on one GPU with streamed result read-back.
+
+    Parameters
+    ----------
+    prog : single-instance Program
+    sweep : ordered ``(arg_name, flat_element)`` targets; row k of the parameter table feeds target k
+    observers : state-vector indices to record
+    """
+
+    def __init__(self, prog: Program, sweep: Sequence[Tuple[str, int]], observers: Sequence[int], *,
+                 solver: str, T: float, dt: float, dts: Optional[float], n_inst: int,
+                 chunk_samples: int = 100, const_div_to_mul: bool = True, block: int = 128,
+                 pinned_result: bool = True):
+        self.model = InstanceModel(prog, solver=solver, sweep=sweep, observers=observers, block=block,
+                                   const_div_to_mul=const_div_to_mul)
+        order = [(p.arg, p.elem) for p in self.model.rhs.params]
+        self._perm = [order.index((a, int(e))) for a, e in sweep]      # user row k -> kernel param row
+        self.sweep = list(sweep)
+        self.B = int(n_inst)
+        self.dt = float(dt)
+        self.steps, self.store_step, self.n_samples = n_steps_for(T, dt, dts)
+        self.n_obs = len(self.model.observers)
+        self.real = self.model.real
+        self.chunk_samples = max(1, min(int(chunk_samples), max(self.n_samples, 1)))
+        self.compute = rt.Stream()
+        self.copy = rt.Stream()
+        self.sess = self.model.session(self.B, 0, stream=self.compute)
+        item = np.dtype(self.real).itemsize
+        self._chunk_bytes = self.chunk_samples * self.n_obs * self.B * item
+        self.d_chunks = [rt.DeviceBuffer(max(self._chunk_bytes, 8)) for _ in range(2)]
+        self.ev_done = [rt.Event() for _ in range(2)]      # compute finished writing buffer i
+        self.ev_free = [rt.Event() for _ in range(2)]      # copy finished reading buffer i
+        k = self.model.kernel
+        self.h_params = rt.PinnedBuffer((max(k.n_params, 1), self.B), self.real)
+        self.h_y0 = rt.PinnedBuffer((k.n_state, self.B), self.real)
+        self.h_y0.array[:] = np.asarray(prog.y0, dtype=self.real)[:, None]
+        self._pinned_result = pinned_result
+        self.h_out = rt.PinnedBuffer((max(self.n_samples, 1), self.n_obs, self.B), self.real) if pinned_result else None
+        self.h2d_bytes = self.h_params.nbytes + self.h_y0.nbytes
+        self.d2h_bytes = self.n_samples * self.n_obs * self.B * item
+        self.launches_per_run = 0
+        self._static_ready = False
+
+    # ------------------------------------------------------------------ pieces
+    def stage_params(self, table: np.ndarray):
+        """Copy the user's ``[len(sweep), B]`` parameter table into pinned staging (kernel row order)."""
+        table = np.asarray(table)
+        if table.shape != (len(self.sweep), self.B):
+            raise ValueError(f"parameter table must have shape ({len(self.sweep)}, {self.B}), got {table.shape}")
+        for k, row in enumerate(self._perm):
+            self.h_params.array[row, :] = table[k]
+
+    def upload(self):
+        """H2D: parameters + initial state (+ slots / ring buffers once) on the compute stream."""
+        s, k = self.sess, self.model.kernel
+        if k.n_params:
+            rt._check(rt.lib().prb_memcpy_h2d(s.d_params.ptr, self.h_params.ptr, self.h_params.nbytes, self.compute.handle))
+        rt._check(rt.lib().prb_memcpy_h2d(s.d_y.ptr, self.h_y0.ptr, self.h_y0.nbytes, self.compute.handle))
+        if k.n_slots:
+            s.d_slots.upload(np.repeat(k.slot_init.astype(self.real)[:, None], self.B, axis=1), self.compute)
+        if k.ring_elems:
+            s.d_rings.upload(np.repeat(k.ring_init.astype(self.real)[:, None], self.B, axis=1), self.compute)
+        s.steps_done = 0
+        s.samples_done = 0
+
+    def integrate(self, read_back: bool = True):
+        """Launch all time chunks; with ``read_back`` stream each chunk D2H into the result array."""
+        s = self.sess
+        steps_per_chunk = self.chunk_samples * self.store_step
+        done, sample, c = 0, 0, 0
+        item = np.dtype(self.real).itemsize
+        n_launch = 0
+        while done < self.steps:
+            n = min(steps_per_chunk, self.steps - done)
+            i = c & 1
+            if read_back and c >= 2:
+                self.compute.wait_event(self.ev_free[i])
+            ns = s.launch(n, self.dt, self.store_step, out=self.d_chunks[i], out_capacity=self.chunk_samples)
+            n_launch += 1
+            if read_back and ns:
+                self.ev_done[i].record(self.compute)
+                self.copy.wait_event(self.ev_done[i])
+                nbytes = ns * self.n_obs * self.B * item
+                dst = self.h_out.ptr + sample * self.n_obs * self.B * item
+                rt._check(rt.lib().prb_memcpy_d2h(dst, self.d_chunks[i].ptr, nbytes, self.copy.handle))
+                self.ev_free[i].record(self.copy)
+            done += n
+            sample += ns
+            c += 1
+        self.launches_per_run = n_launch
+        return n_launch
+
+    def wait(self):
+        self.compute.synchronize()
+        self.copy.synchronize()
+
+    # ------------------------------------------------------------------ public end-to-end call
+    def run(self, table: np.ndarray) -> np.ndarray:
+        """Host parameter table in, host trajectories ``[n_samples, n_obs, B]`` out (view of the pinned
+        result buffer, overwritten by the next call)."""
+        if self.h_out is None:
+            raise rt.CudaBackendError("BatchedSweep was created with pinned_result=False")
+        self.stage_params(table)
+        self.upload()
+        self.integrate(read_back=True)
+        self.wait()
+        return self.h_out.array[: self.n_samples]
+
+    def final_state(self) -> np.ndarray:
+        return self.sess.download_state()
+
+    def free(self):
+        self.wait()
+        self.sess.free()
+        for b in self.d_chunks:
+            b.free()
+        for b in (self.h_params, self.h_y0, self.h_out):
+            if b is not None:
+                b.free()
