@@ -1,0 +1,332 @@
+"""``CudaBackend`` — the object PyRates' ``ComputeGraph`` drives when ``backend='cuda'``.
+
+It mirrors, name for name, the interface the reference's compute graph calls on a backend object
+(reference implementation: ``BaseBackend``, pyrates/backend/base/base_backend.py:229-812):
+
+  ctor kwargs ............ float_precision / int_precision / file_name / add_hist_arg   (:271-324)
+  get_var ................ argument arrays in the backend's precision                    (:326-340)
+  get_op ................. op table used while the graph is built / constant-folded       (:342-384)
+  add_var_update ......... one assignment of the generated vector field                  (:386-393)
+  generate_func_head/tail, generate_func, create_index_str, finalize_idx_str, expr_to_str,
+  register_vars, add_var_hist, get_hist_func, clear, CodeGen line helpers               (:180-222, 437-660)
+  run .................... fixed-step integration + state recording                      (:596-611, 693-769)
+
+Instead of printing Python source and exec'ing it, the assignment stream is recorded into a
+``pyrates_b200.Program``; ``run`` lowers that program to CUDA C for sm_100a (instance model:
+``engine.InstanceModel``; network model: ``netengine.NetworkModel``), JIT-builds it through the C ABI and
+integrates on the GPU.  It does not import the reference, so it also works from recorded programs
+(tests/golden) on machines without PyRates.
+
+There is no CPU fallback: unsupported ops / solvers raise, a missing GPU raises.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+
+from . import runtime as rt
+from .engine import FIXED_STEP_SOLVERS, InstanceModel, n_steps_for
+from .program import Arg, Program, Stmt
+from .scalarize import UnsupportedModelError
+
+__all__ = ["CudaBackend", "CudaVectorField"]
+
+
+def _backend_error(msg: str) -> Exception:
+    """PyRatesException when the reference is importable (same error type users see from other backends)."""
+    try:
+        from pyrates.backend import PyRatesException      # pyrates/backend/__init__.py:42
+        return PyRatesException(msg)
+    except Exception:
+        return rt.CudaBackendError(msg)
+
+
+# ----------------------------------------------------------------------------- build-time op table
+# Used only while the reference's parser builds / constant-folds the compute graph on the host
+# (ComputeGraph.eval_node, computegraph.py:297-312) — never during integration.  Same names and call
+# strings as pyrates/backend/base/base_funcs.py:135-177 so the generated text is identical.
+def _sig(x):
+    return 1. / (1. + np.exp(-x))
+
+
+_OPS: Dict[str, Tuple[str, Callable]] = {
+    'maxi': ('maximum', np.maximum), 'mini': ('minimum', np.minimum), 'round': ('round', np.round),
+    'vsum': ('sum', np.sum), 'mean': ('mean', np.mean), 'matmul': ('dot', np.dot), 'matvec': ('dot', np.dot),
+    'roll': ('roll', np.roll), 'tanh': ('tanh', np.tanh), 'sinh': ('sinh', np.sinh), 'cosh': ('cosh', np.cosh),
+    'arctan': ('arctan', np.arctan), 'arcsin': ('arcsin', np.arcsin), 'arccos': ('arccos', np.arccos),
+    'sin': ('sin', np.sin), 'cos': ('cos', np.cos), 'tan': ('tan', np.tan), 'exp': ('exp', np.exp),
+    'sigmoid': ('sigmoid', _sig), 'broadcast_pre': ('broadcast_pre', lambda x: x[None, :]),
+    'broadcast_post': ('broadcast_post', lambda x: x[:, None]),
+    'wsum': ('wsum', lambda w, c: np.einsum('ij,ij->i', w, c)),
+    'reshape2d': ('reshape2d', lambda x, n, m: x.reshape(n, m)), 'flatten1d': ('flatten1d', lambda x: x.reshape(-1)),
+    'no_op': ('identity', lambda x: x), 'index': ('index_1d', lambda x, i: x[i]),
+    'index_range': ('index_range', lambda x, a, b: x[a:b]), 'index_2d': ('index_2d', lambda x, i, j: x[i, j]),
+    'index_axis': ('index_axis', lambda x, idx=None, axis=0: (x[idx] if axis == 0 else x[:, idx]) if idx is not None else x[:]),
+    'absv': ('abs', np.abs), 'sign': ('sign', np.sign), 'log': ('log', np.log),
+    'interp': ('interp', np.interp),
+    'interp_rows': ('interp_rows', lambda t, time, inp: np.array([np.interp(t, time, inp[:, k]) for k in range(inp.shape[1])])),
+    'past': ('past', lambda x, tau: x), 'concatenate': ('concatenate', np.concatenate),
+    'real': ('real', np.real), 'imag': ('imag', np.imag), 'conj': ('conjugate', np.conjugate),
+    'randn': ('randn', np.random.randn),
+}
+
+
+class CudaVectorField:
+    """Handle returned by ``generate_func``: the recorded vector field.  Calling it evaluates the rhs ONCE
+    on the GPU (``func(t, y, *args) -> dy``), matching what ``get_run_func`` hands to users
+    (pyrates/frontend/template/circuit.py:552-650)."""
+
+    def __init__(self, backend: "CudaBackend", func_name: str, arg_names: List[str], stmts: List[Stmt],
+                 state_var: str, return_var: str):
+        self.backend = backend
+        self.__name__ = func_name
+        self.arg_names = list(arg_names)
+        self.stmts = list(stmts)
+        self.state_var, self.return_var = state_var, return_var
+
+    def program(self, func_args) -> Program:
+        if len(func_args) != len(self.arg_names):
+            raise ValueError(f"vector field takes {len(self.arg_names)} arguments, got {len(func_args)}")
+        assigned = {s.lhs for s in self.stmts}
+        args = []
+        for i, (name, val) in enumerate(zip(self.arg_names, func_args)):
+            if name == "hist" or callable(val):
+                raise UnsupportedModelError("delay-differential models (`past`) are not supported by the CUDA backend")
+            kind = "t" if i == 0 else ("y" if name == self.state_var else ("dy" if name == self.return_var else
+                                                                           ("var" if name in assigned else "const")))
+            args.append(Arg(name, kind, np.array(val, copy=True)))
+        return Program(args, self.stmts, {}, self.backend._float_precision, self.__name__)
+
+    def source(self) -> str:
+        return Program([Arg(n, "const", np.zeros(())) for n in self.arg_names], self.stmts,
+                       func_name=self.__name__).source().replace("return t", f"return {self.return_var}")
+
+    def __call__(self, t, y, *args):
+        names = self.arg_names
+        dy = np.zeros_like(np.asarray(y))
+        full = [np.asarray(t), np.asarray(y)] + list(args)
+        if len(full) == len(names) - 1:              # dy omitted by the caller
+            full.insert(2, dy)
+        prog = self.program(full)
+        from .engine import evaluate_rhs
+        return evaluate_rhs(prog)
+
+
+class CudaBackend:
+    """Code generator + runner with the reference backend interface, targeting B200 CUDA kernels."""
+
+    SUPPORTED_SOLVERS: Tuple[str, ...] = FIXED_STEP_SOLVERS
+    SUPPORTS_SPARSE_JACOBIAN: bool = False
+    SUPPORTS_EDGE_DELAY_BUFFER: bool = True
+    _no_funcs: Tuple[str, ...] = ("identity", "index_1d", "index_2d", "index_range", "index_axis")
+
+    def __init__(self, ops: Optional[Dict[str, str]] = None, imports: Optional[List[str]] = None, **kwargs) -> None:
+        self.code: List[str] = []
+        self.lvl = 0
+        self._stmts: List[Stmt] = []
+        self._imports: List[str] = []
+        self._helper_funcs: List[str] = []
+        self.add_hist_arg = kwargs.pop('add_hist_arg', False)
+        self.lags = {}
+        self.idx_dummy_var = "temporary_pyrates_var_index"
+        self._float_precision = kwargs.pop('float_precision', 'float32')      # reference default (:300)
+        self._int_precision = kwargs.pop('int_precision', 'int32')
+        if self._float_precision not in ('float32', 'float64'):
+            raise _backend_error(f"CudaBackend supports float_precision 'float32' or 'float64', got "
+                                 f"`{self._float_precision}`")
+        self._idx_left, self._idx_right = '[', ']'
+        self._start_idx = 0
+        kwargs.pop('idx_left', None), kwargs.pop('idx_right', None), kwargs.pop('start_idx', None)
+        fname = kwargs.pop('file_name', 'pyrates_run')
+        self.fdir = ""
+        self._fname = os.path.basename(fname).split('.')[0]
+        self._fend = ".cu"
+        # CUDA-specific options, popped so they never leak into solver kwargs (SURVEY §5 "config / flags")
+        self.device = kwargs.pop('device', None)
+        self.fmad = kwargs.pop('fmad', True)
+        self.const_div_to_mul = kwargs.pop('const_div_to_mul', False)
+        self.exec_model = kwargs.pop('exec_model', 'auto')        # 'auto' | 'instance' | 'network'
+        self.last_model = None
+        self._head: Optional[Tuple[str, str, str, List[str]]] = None
+
+    # ------------------------------------------------------------------ CodeGen line helpers (:180-222)
+    def generate(self) -> str:
+        return '\n'.join(self.code)
+
+    def add_code_line(self, code_str: str):
+        for code in code_str.split('\n'):
+            self.code.append("\t" * self.lvl + code)
+
+    def add_linebreak(self):
+        self.code.append("")
+
+    def add_indent(self):
+        self.lvl += 1
+
+    def remove_indent(self):
+        if self.lvl == 0:
+            raise SyntaxError("Error in generation of network function file: A net negative indentation was requested.")
+        self.lvl -= 1
+
+    # ------------------------------------------------------------------ variables and ops
+    def get_var(self, v):
+        """base_backend.py:326-340: value in backend precision; (1,) constants squeezed to 0-d."""
+        if v.is_float or v.is_complex:
+            if v.is_complex:
+                raise UnsupportedModelError("complex-valued models are not supported by the CUDA backend")
+            dtype = self._float_precision
+        else:
+            dtype = self._int_precision
+        result = np.asarray(v.value, dtype=dtype)
+        if result.shape == (1,) and v.vtype == 'constant':
+            result = result.squeeze()
+        return result
+
+    def get_op(self, name: str, **kwargs) -> dict:
+        call, func = _OPS[name]              # KeyError for unknown ops, like the reference's table lookup
+        return {'func': func, 'call': call}
+
+    @staticmethod
+    def register_vars(variables: list):
+        pass
+
+    # ------------------------------------------------------------------ index strings (:453-475, 643-660)
+    def create_index_str(self, idx, separator: str = ',', apply: bool = True, **kwargs) -> Tuple[str, dict]:
+        if type(idx) is str and separator in idx:
+            idx = tuple(idx.split(separator))
+        if type(idx) is tuple:
+            parts = tuple(f"{self._process_idx(i)}" for i in idx)
+            body = separator.join(parts)
+            return (f"[{body}]" if apply else body), dict()
+        body = self._process_idx(idx)
+        return (f"[{body}]" if apply else body), dict()
+
+    def _process_idx(self, idx) -> str:
+        if hasattr(idx, "vtype") and hasattr(idx, "name"):        # ComputeVar holding an index array
+            return idx.name
+        if type(idx) is tuple:
+            return f"{idx[0]}:{idx[1]}"
+        if type(idx) is int:
+            return f"{idx}"
+        try:
+            return f"{int(idx)}"
+        except (TypeError, ValueError):
+            return idx
+
+    @staticmethod
+    def finalize_idx_str(var, idx: str):
+        return f"{var.name}{idx}"
+
+    @staticmethod
+    def expr_to_str(expr: str, args: tuple):
+        return expr
+
+    # ------------------------------------------------------------------ assignment stream
+    def add_var_update(self, lhs, rhs: str, lhs_idx: Optional[str] = None, rhs_shape: Optional[tuple] = ()):
+        idx_str = None
+        if lhs_idx:
+            idx_str, _ = self.create_index_str(lhs_idx, apply=False)
+        self._stmts.append(Stmt(lhs.name, rhs, idx_str))
+        self.add_code_line(f"{lhs.name}[{idx_str}] = {rhs}" if idx_str is not None else f"{lhs.name} = {rhs}")
+
+    def add_var_hist(self, lhs: str, delay, state_idx: str, **kwargs):
+        raise UnsupportedModelError("delay-differential models (`past` / history functions) are not supported by the "
+                                    "CUDA backend; use discrete or gamma-kernel edge delays")
+
+    def add_import(self, line: str):
+        if line not in self._imports:
+            self._imports.append(line)
+
+    def generate_func_head(self, func_name: str, state_var: str = 'y', return_var: str = 'dy', func_args: list = None,
+                           add_hist_func: Optional[bool] = None):
+        """base_backend.py:483-528: signature order = t, y, [hist], then unique args in first-seen order."""
+        if add_hist_func:
+            raise UnsupportedModelError("delay-differential models (`past`) are not supported by the CUDA backend")
+        names = [a.name for a in func_args] if func_args else []
+        seen, uniq = set(), []
+        for n in names:
+            if n not in seen:
+                seen.add(n)
+                uniq.append(n)
+        args = ['t', state_var] + uniq
+        self._head = (func_name, state_var, return_var, args)
+        self.add_linebreak()
+        self.add_code_line(f"def {func_name}({','.join(args)}):")
+        self.add_indent()
+        return args
+
+    def generate_func_tail(self, rhs_var: str = 'dy'):
+        self.add_code_line(f"return {rhs_var}")
+        self.remove_indent()
+
+    def generate_func(self, func_name: str, to_file: bool = True, **kwargs):
+        if self._head is None:
+            raise _backend_error("generate_func called before generate_func_head")
+        _, state_var, return_var, args = self._head
+        func = CudaVectorField(self, func_name, args, self._stmts, state_var, return_var)
+        decorator = kwargs.pop('decorator', None)
+        if decorator:
+            raise _backend_error("CudaBackend does not support python decorators on the vector field")
+        return func
+
+    @staticmethod
+    def get_hist_func(y: np.ndarray, t0: float = 0.0):
+        raise UnsupportedModelError("delay-differential models (`past`) are not supported by the CUDA backend")
+
+    @staticmethod
+    def to_file(fn: str, **kwargs):
+        np.savez(fn, **kwargs)
+
+    def clear(self):
+        self.code.clear()
+        self._stmts = []
+        self._head = None
+
+    # ------------------------------------------------------------------ integration
+    def _validate_solver(self, solver: str) -> None:
+        if solver not in self.SUPPORTED_SOLVERS:
+            raise _backend_error(f"Backend `{type(self).__name__}` does not support solver `{solver}`. "
+                                 f"Supported solvers: {list(self.SUPPORTED_SOLVERS)}.")
+
+    def run(self, func: CudaVectorField, func_args: tuple, T: float, dt: float, dts: float, solver: str,
+            **kwargs) -> tuple:
+        """Counterpart of BaseBackend.run (:596-611): returns ``(state_rec[round(T/dts), n_state], times)``
+        with row k = state at step k*store_step sampled before the update."""
+        self._validate_solver(solver)
+        if not isinstance(func, CudaVectorField):
+            raise _backend_error("CudaBackend.run needs the vector-field handle returned by its own generate_func")
+        if self.device is not None:
+            rt.set_device(int(self.device))
+        prog = func.program(func_args)
+        step = dts if dts else dt
+        times = np.linspace(0.0, T, num=round(T / step), endpoint=False)
+        model = build_model(prog, solver=solver, exec_model=self.exec_model, fmad=self.fmad,
+                            const_div_to_mul=self.const_div_to_mul)
+        self.last_model = model
+        out, y_final = model.run(T, dt, dts)
+        rec = np.ascontiguousarray(out[:, :, 0])
+        # mirror the reference's in-place semantics: y0 (func_args[1]) ends up holding the final state
+        try:
+            np.asarray(func_args[1])[...] = y_final[:, 0]
+        except (ValueError, TypeError):
+            pass
+        return rec, times
+
+
+def build_model(prog: Program, *, solver: str, exec_model: str = "auto", **kw):
+    """Pick the execution model: 'instance' (whole state in one thread's registers — small circuits and
+    parameter sweeps) or 'network' (persistent cooperative grid, one thread per node — large populations)."""
+    if exec_model not in ("auto", "instance", "network"):
+        raise ValueError("exec_model must be 'auto', 'instance' or 'network'")
+    if exec_model in ("auto", "instance"):
+        try:
+            limit = 4000 if exec_model == "auto" else 60000
+            return InstanceModel(prog, solver=solver, max_nodes=limit, **kw)
+        except UnsupportedModelError as e:
+            if exec_model == "instance" or "too large" not in str(e):
+                raise
+    from .netengine import NetworkModel
+    kw.pop("const_div_to_mul", None)
+    return NetworkModel(prog, solver=solver, **kw)

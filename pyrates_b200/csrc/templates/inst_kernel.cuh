@@ -100,3 +100,22 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
     for (int j = 0; j < PRB_NS; ++j) Y[(long long)j * B + b] = y[j];
     prb_thread_exit(T, A, b);
 }
+
+// Single rhs evaluation dy = f(t, y) for every instance (the callable handed out by get_run_func).
+extern "C" __global__ void __launch_bounds__(PRB_BLOCK)
+prb_rhs_eval(const __grid_constant__ prb_kernel_args A)
+{
+    const long long B = A.n_inst;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    PrbThread T;
+    prb_thread_init(T, A, b);
+    const real* __restrict__ Y = (const real*)A.y;
+    real y[PRB_NS], k[PRB_NS];
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) y[j] = Y[(long long)j * B + b];
+    prb_rhs(A.step0 + A.t0, y, k, T);
+    real* __restrict__ out = (real*)A.out;
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) out[(long long)j * B + b] = k[j];
+}

@@ -16,7 +16,7 @@ from .emit_inst import InstKernel, emit_inst_kernel
 from .program import Program
 from .scalarize import ScalarRhs, scalarize
 
-__all__ = ["InstanceModel", "InstanceSession", "n_steps_for", "FIXED_STEP_SOLVERS"]
+__all__ = ["InstanceModel", "InstanceSession", "n_steps_for", "FIXED_STEP_SOLVERS", "evaluate_rhs"]
 
 FIXED_STEP_SOLVERS = ("euler", "heun", "heun_true", "rk4")
 
@@ -194,3 +194,23 @@ class InstanceSession:
             b = getattr(self, n, None)
             if b is not None:
                 b.free()
+
+
+def evaluate_rhs(prog: Program) -> np.ndarray:
+    """One evaluation ``dy = f(t, y, *args)`` of the vector field on the GPU (kernel ``prb_rhs_eval``)."""
+    m = InstanceModel(prog, solver="euler")
+    s = m.session(1, 0)
+    d_dy = rt.DeviceBuffer(max(m.n_state, 1) * np.dtype(m.real).itemsize)
+    try:
+        s.reset()
+        a = rt.KernelArgs()
+        a.n_steps, a.store_step, a.step0, a.t0, a.eval0, a.n_inst, a.sample0, a.dt = 0, 1, 0, m.t0, 0, 1, 0, 0.0
+        a.y, a.out, a.params = s.d_y.ptr, d_dy.ptr, s.d_params.ptr
+        a.slots, a.rings, a.tables = s.d_slots.ptr, s.d_rings.ptr, s.d_tables.ptr
+        m.module.run("prb_rhs_eval", a, block=m.kernel.block)
+        dy = np.empty(m.n_state, dtype=m.real)
+        d_dy.download(dy)
+        return dy
+    finally:
+        d_dy.free()
+        s.free()

@@ -1,0 +1,218 @@
+"""Hook ``backend='cuda'`` into an installed PyRates and provide the batched ``grid_search``.
+
+The reference has no backend registry: ``ComputeGraph.__init__`` maps strings to classes with an if/elif
+chain and silently falls back to NumPy for unknown names (pyrates/backend/computegraph.py:228-253).
+``register()`` therefore patches, at import time of the user's choosing,
+
+* ``ComputeGraph.__init__`` so that ``backend in ('cuda', 'b200')`` instantiates ``CudaBackend(**kwargs)``,
+* ``ComputeGraph.__new__`` (networkx >= 3.6 treats a ``backend=`` keyword as its own dispatch argument),
+* ``is_integration_adaptive`` (pyrates/frontend/template/circuit.py:1652) so the new fixed-step solver
+  names 'rk4' / 'heun_true' get integer step counters, ring buffers and indexed inputs like 'euler'/'heun',
+* ``pyrates.grid_search`` / ``pyrates.utility.grid_search``: calls with ``backend='cuda'`` go to the
+  compile-once batched implementation below, everything else to the original.
+
+See INTEGRATION.md for the three-line upstream patch that would replace the monkey-patching.
+"""
+from __future__ import annotations
+
+import functools
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from .backend import CudaBackend
+from .engine import FIXED_STEP_SOLVERS
+from .program import Program
+
+CUDA_NAMES = ("cuda", "b200")
+_registered = False
+
+
+def register() -> bool:
+    """Idempotently install the hooks.  Returns False when PyRates is not importable."""
+    global _registered
+    if _registered:
+        return True
+    try:
+        import pyrates
+        import pyrates.backend.computegraph as cg
+        import pyrates.frontend.template.circuit as fc
+        import pyrates.utility as util
+    except ImportError:
+        return False
+
+    orig_init = cg.ComputeGraph.__init__
+
+    @functools.wraps(orig_init)
+    def __init__(self, backend=None, **kwargs):
+        if backend in CUDA_NAMES:
+            cuda_backend = CudaBackend(**dict(kwargs))
+            orig_init(self, "default", **kwargs)          # graph attributes; its NumPy backend is discarded
+            self.backend = cuda_backend
+        else:
+            orig_init(self, backend, **kwargs)
+
+    cg.ComputeGraph.__init__ = __init__
+    cg.ComputeGraph.__new__ = lambda cls, *a, **k: object.__new__(cls)
+
+    orig_adaptive = fc.is_integration_adaptive
+
+    def is_integration_adaptive(solver: str, **solver_kwargs):
+        if solver in FIXED_STEP_SOLVERS:
+            return False
+        return orig_adaptive(solver, **solver_kwargs)
+
+    fc.is_integration_adaptive = is_integration_adaptive
+
+    orig_grid_search = util.grid_search
+
+    @functools.wraps(orig_grid_search)
+    def grid_search_dispatch(*args, **kwargs):
+        if kwargs.get("backend") in CUDA_NAMES:
+            return grid_search(*args, **kwargs)
+        return orig_grid_search(*args, **kwargs)
+
+    util.grid_search = grid_search_dispatch
+    pyrates.grid_search = grid_search_dispatch
+    _registered = True
+    return True
+
+
+# ----------------------------------------------------------------------------- batched grid_search
+def _probe_positions(template, keys: List[str], param_map: dict, build, sentinels=(1009.0, 2003.0)):
+    """Find where each grid key lands in the single-instance argument tuple by building the instance with
+    two distinct sentinel values per key and diffing the arguments.  Only identity
+    dependence (the value appears verbatim) is accepted — anything else raises instead of guessing."""
+    from pyrates.utility import adapt_circuit
+    builds = []
+    for base in sentinels:
+        vals = {k: base + 7.0 * i for i, k in enumerate(keys)}
+        builds.append((vals, build(adapt_circuit(template, vals, param_map))))
+    (vals_a, a), (vals_b, b) = builds
+    prog_a, prog_b = a["program"], b["program"]
+    targets: Dict[str, List[Tuple[str, int]]] = {k: [] for k in keys}
+    for arg_a, arg_b in zip(prog_a.args, prog_b.args):
+        va, vb = np.asarray(arg_a.value).reshape(-1), np.asarray(arg_b.value).reshape(-1)
+        if va.shape != vb.shape:
+            raise NotImplementedError(f"grid parameter changes the shape of `{arg_a.name}`; cannot batch this sweep")
+        if arg_a.is_int or va.size == 0:
+            if not np.array_equal(va, vb):
+                raise NotImplementedError(f"grid parameter changes integer/index array `{arg_a.name}`")
+            continue
+        for e in np.nonzero(va != vb)[0]:
+            hit = [k for k in keys if va[e] == np.asarray(vals_a[k], dtype=va.dtype) and
+                   vb[e] == np.asarray(vals_b[k], dtype=vb.dtype)]
+            if len(hit) != 1:
+                raise NotImplementedError(
+                    f"`{arg_a.name}[{e}]` depends on the swept parameters in a non-identity way (constant folding of a "
+                    f"derived quantity); this sweep cannot be batched by the CUDA backend")
+            targets[hit[0]].append((arg_a.name, int(e)))
+    missing = [k for k, t in targets.items() if not t]
+    if missing:
+        raise NotImplementedError(f"swept parameter(s) {missing} do not reach the compiled vector field")
+    return a, targets
+
+
+def grid_search(circuit_template, param_grid, param_map: dict, step_size: float, simulation_time: float,
+                outputs: dict, inputs: Optional[dict] = None, sampling_step_size: Optional[float] = None,
+                permute_grid: bool = False, **kwargs) -> tuple:
+    """Drop-in for ``pyrates.grid_search`` (pyrates/utility.py:189-275) on the CUDA backend.
+
+    Same signature and return value — ``(DataFrame[time, (out_key, '<name>_<i>', node.., 'op/var')],
+    param_grid DataFrame re-indexed '<name>_<i>')`` — but the circuit is compiled ONCE as a single instance
+    and all grid points are integrated as one batch (one CUDA thread per grid point).  Extra keywords:
+    ``as_arrays=True`` returns ``(ndarray[n_samples, n_out, B], param_grid)`` without building the frame;
+    ``shard=(rank, world)`` integrates only that contiguous slice of the grid (one process per GPU).
+    """
+    import pandas as pd
+    from pyrates import CircuitTemplate
+    from pyrates.utility import linearize_grid
+    from .sweep import BatchedSweep, shard_bounds
+
+    register()
+    kwargs.pop("vectorize", None)
+    backend = kwargs.pop("backend", "cuda")
+    if backend not in CUDA_NAMES:
+        raise ValueError("pyrates_b200.grid_search only serves backend='cuda'")
+    solver = kwargs.pop("solver", "euler")
+    cutoff = kwargs.pop("cutoff", 0.0)
+    as_arrays = kwargs.pop("as_arrays", False)
+    shard = kwargs.pop("shard", None)
+    verbose = kwargs.pop("verbose", False)
+    kwargs.pop("clear", None)
+    chunk_samples = kwargs.pop("chunk_samples", 100)
+    const_div_to_mul = kwargs.pop("const_div_to_mul", False)
+    float_precision = kwargs.pop("float_precision", "float32")
+
+    if type(param_grid) is dict:
+        param_grid = linearize_grid(param_grid, permute_grid)
+    keys = list(param_grid.keys())
+    template = CircuitTemplate.from_yaml(circuit_template) if type(circuit_template) is str else circuit_template
+    name = template.name
+
+    def build(circuit):
+        func, args, _, _ = circuit.get_run_func("vector_field", step_size=step_size, inputs=dict(inputs) if inputs else None,
+                                                backend="cuda", solver=solver, verbose=verbose, clear=False,
+                                                float_precision=float_precision, **kwargs)
+        prog = func.program(args)
+        out_map, out_vars = circuit.get_variable_positions(outputs)
+        obs, cols = [], []
+        sv = circuit._ir.graph._state_var_indices
+        for key, info in out_map.items():
+            items = info.items() if type(info) is dict else [(None, info)]
+            for var_key, idx in items:
+                backend_var = circuit._ir.get_var(out_vars[var_key if var_key is not None else key], get_key=True)
+                pos = sv[backend_var]
+                start = pos[0] if isinstance(pos, tuple) else pos
+                for j in np.atleast_1d(idx):
+                    obs.append(int(start + j))
+                    full = var_key if var_key is not None else outputs[key]
+                    *nodes, op, var = full.split("/")
+                    cols.append((key, tuple(nodes), f"{op}/{var}"))
+        try:
+            circuit.clear()
+        except Exception:
+            pass
+        return {"program": prog, "observers": obs, "columns": cols}
+
+    base, targets = _probe_positions(template, keys, param_map, build)
+    prog: Program = base["program"]
+    y_name = prog.arg_by_kind("y").name
+    sweep, rows, y0_rows = [], [], []
+    for k in keys:
+        for arg, elem in targets[k]:
+            if arg == y_name:
+                y0_rows.append((elem, k))
+            else:
+                sweep.append((arg, elem))
+                rows.append(k)
+    B_total = len(param_grid.index)
+    lo, hi = (0, B_total) if shard is None else shard_bounds(B_total, shard[1], shard[0])
+    B = hi - lo
+    grid_vals = {k: np.asarray(param_grid[k].values[lo:hi], dtype=np.float64) for k in keys}
+    table = np.stack([grid_vals[k] for k in rows]) if rows else np.zeros((0, B))
+
+    sw = BatchedSweep(prog, sweep, base["observers"], solver=solver, T=simulation_time, dt=step_size,
+                      dts=sampling_step_size, n_inst=B, chunk_samples=chunk_samples, const_div_to_mul=const_div_to_mul)
+    try:
+        for elem, k in y0_rows:
+            sw.h_y0.array[elem, :] = grid_vals[k]
+        res = np.array(sw.run(table), copy=True)           # [n_samples, n_obs, B]
+    finally:
+        sw.free()
+
+    circuit_names = [f"{name}_{idx}" for idx in param_grid.index]
+    param_grid = param_grid.copy()
+    param_grid.index = circuit_names
+    step = sampling_step_size if sampling_step_size else step_size
+    times = np.linspace(0.0, simulation_time, num=round(simulation_time / step), endpoint=False)
+    if as_arrays:
+        return res[times >= cutoff], param_grid
+    columns, data = [], []
+    for o, (key, nodes, opvar) in enumerate(base["columns"]):
+        for i in range(B):
+            columns.append((key, circuit_names[lo + i]) + nodes + (opvar,))
+        data.append(res[:, o, :])
+    frame = pd.DataFrame(np.concatenate(data, axis=1) if data else np.zeros((len(times), 0)),
+                         columns=pd.MultiIndex.from_tuples(columns), index=times)
+    return frame.loc[cutoff:, :], param_grid

@@ -1,0 +1,141 @@
+"""Drop-in boundary: with the reference importable, `backend='cuda'` makes PyRates' own compute graph drive
+CudaBackend, which must record exactly the program the NumPy backend would have printed (same statements,
+same argument arrays).  CPU part: capture only.  GPU part (needs baseline/_ref on the box): the public
+CircuitTemplate.run / grid_search calls end to end against the reference NumPy backend."""
+import ast
+import json
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import RTOL, golden_path, traj_rel_err
+from oracle import numpy_oracle as orc
+from oracle.ref_env import import_reference
+from pyrates_b200 import runtime as rt
+from pyrates_b200.program import Program
+
+pyrates = import_reference()
+needs_ref = pytest.mark.skipif(pyrates is None, reason="reference PyRates not importable on this machine")
+warnings.filterwarnings("ignore")
+
+
+def _norm(stmts):
+    return [ast.dump(ast.parse(s.text())) for s in stmts]
+
+
+@pytest.fixture()
+def registered(tmp_path, monkeypatch):
+    import pyrates_b200.register as reg
+    assert reg.register()
+    monkeypatch.chdir(tmp_path)
+    yield reg
+    from pyrates.ir.node import clear_ir_caches
+    clear_ir_caches()
+
+
+@needs_ref
+@pytest.mark.parametrize("name,path,solver", [
+    ("jrc", "model_templates.neural_mass_models.jansenrit.JRC", "rk4"),
+    ("qif", "model_templates.neural_mass_models.qif.qif", "euler"),
+    ("net10", "model_templates.test_resources.test_backend.net10", "heun"),
+    ("net13", "model_templates.test_resources.test_backend.net13", "heun_true"),
+    ("jrc_2delay", "model_templates.neural_mass_models.jansenrit.JRC_2delaycoupled", "euler"),
+])
+def test_cuda_backend_records_same_program_as_numpy_backend(registered, name, path, solver):
+    from pyrates import CircuitTemplate, clear
+    c = CircuitTemplate.from_yaml(path)
+    fx = orc.load_fixture(golden_path(name))
+    func, args, names, svmap = c.get_run_func("vector_field", step_size=fx["run"]["dt"], backend="cuda", solver=solver,
+                                              float_precision="float64", verbose=False)
+    prog = func.program(args)
+    gold = Program.load(golden_path(name))
+    assert _norm(prog.stmts) == _norm(gold.stmts)
+    assert [(a.name, a.kind) for a in prog.args] == [(a.name, a.kind) for a in gold.args]
+    for a, b in zip(prog.args, gold.args):
+        assert a.value.dtype == b.value.dtype and np.array_equal(a.value, b.value), a.name
+    clear(c)
+
+
+@needs_ref
+def test_new_solver_names_are_fixed_step(registered):
+    import pyrates.frontend.template.circuit as fc
+    assert not fc.is_integration_adaptive("rk4") and not fc.is_integration_adaptive("heun_true")
+    assert not fc.is_integration_adaptive("euler") and fc.is_integration_adaptive("scipy")
+
+
+@needs_ref
+def test_unsupported_solver_and_no_device_raise(registered):
+    from pyrates import CircuitTemplate
+    c = CircuitTemplate.from_yaml("model_templates.neural_mass_models.qif.qif")
+    with pytest.raises(Exception, match="does not support solver"):
+        c.run(simulation_time=0.01, step_size=1e-3, solver="scipy", outputs={"r": "p/qif_op/r"}, backend="cuda",
+              verbose=False, in_place=False)
+    try:
+        rt.device_count()
+    except rt.CudaBackendError:
+        c = CircuitTemplate.from_yaml("model_templates.neural_mass_models.qif.qif")
+        with pytest.raises(rt.CudaBackendError, match="no CPU execution path"):
+            c.run(simulation_time=0.01, step_size=1e-3, solver="euler", outputs={"r": "p/qif_op/r"}, backend="cuda",
+                  verbose=False)
+
+
+# ------------------------------------------------------------------------------------------- GPU end to end
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("path,out,solver,T,dt,precision", [
+    ("model_templates.neural_mass_models.qif.qif", "p/qif_op/r", "euler", 1.0, 1e-3, "float64"),
+    ("model_templates.neural_mass_models.qif.qif", "p/qif_op/v", "heun", 1.0, 1e-3, "float32"),
+    ("model_templates.neural_mass_models.jansenrit.JRC", "pc/rpo_e_in/v", "heun", 0.2, 1e-4, "float64"),
+    ("model_templates.test_resources.test_backend.net10", "pop0/op8/a", "euler", 1.5, 1e-3, "float64"),
+    ("model_templates.neural_mass_models.qif.qif_sfa", "p/qif_sfa_op/r", "euler", 1.0, 1e-3, "float64"),
+])
+def test_circuit_run_cuda_matches_numpy_backend(gpu, registered, path, out, solver, T, dt, precision):
+    """tests/test_backend_simulations.py:527 pattern (cross-backend parity) with the north-star tolerance."""
+    from pyrates import CircuitTemplate
+    kw = dict(simulation_time=T, step_size=dt, sampling_step_size=dt * 5, solver=solver, outputs={"o": out},
+              verbose=False, float_precision=precision, clear=True)
+    ref = CircuitTemplate.from_yaml(path).run(backend="default", **kw)
+    got = CircuitTemplate.from_yaml(path).run(backend="cuda", **kw)
+    assert list(got.columns) == list(ref.columns) and np.allclose(got.index, ref.index)
+    assert traj_rel_err(got.values, ref.values) <= RTOL[precision]
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_circuit_run_with_inputs_and_state_writeback(gpu, registered):
+    from pyrates import CircuitTemplate
+    inp = np.sin(np.arange(500) * 0.02) * 3.0
+    kw = dict(simulation_time=0.5, step_size=1e-3, solver="heun", outputs={"r": "p/qif_op/r", "v": "p/qif_op/v"},
+              inputs={"p/qif_op/I_ext": inp}, verbose=False, float_precision="float64", clear=True)
+    c_ref, c_gpu = (CircuitTemplate.from_yaml("model_templates.neural_mass_models.qif.qif") for _ in range(2))
+    ref = c_ref.run(backend="default", **kw)
+    got = c_gpu.run(backend="cuda", **kw)
+    assert traj_rel_err(got.values, ref.values) <= 1e-9
+    for key, val in c_ref.state.items():                       # final stored sample written back (computegraph.py:503-507)
+        np.testing.assert_allclose(np.asarray(c_gpu.state[key], dtype=float), np.asarray(val, dtype=float), rtol=1e-9)
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("solver", ["euler", "heun"])
+def test_grid_search_cuda_matches_reference_grid_search(gpu, registered, solver):
+    """New compile-once grid_search vs the frames the reference's own grid_search produced (golden)."""
+    import pyrates
+    from pyrates.utility import linearize_grid
+    fx = orc.load_fixture(golden_path("jrc_grid_b16"))
+    grid = linearize_grid({"C": np.linspace(68.0, 1350.0, 4), "u": np.linspace(120.0, 320.0, 4)}, permute=True)
+    grid["C2"], grid["C4"] = 0.8 * grid["C"], 0.25 * grid["C"]
+    param_map = {"C": {"vars": ["weight"], "edges": [("pc/pro/m", "ein/rpo_e/m_in")]},
+                 "C2": {"vars": ["weight"], "edges": [("ein/pro/m", "pc/rpo_e_in/m_in")]},
+                 "C4": {"vars": ["weight"], "edges": [("pc/pro/m", "iin/rpo_e/m_in"), ("iin/pro/m", "pc/rpo_i/m_in")]},
+                 "u": {"vars": ["rpo_e_in/u"], "nodes": ["pc"]}}
+    res, pmap = pyrates.grid_search("model_templates.neural_mass_models.jansenrit.JRC", grid, param_map, step_size=1e-4,
+                                    simulation_time=0.05, outputs={"v": "pc/rpo_e_in/v"}, sampling_step_size=1e-3,
+                                    solver=solver, backend="cuda", float_precision="float64", verbose=False)
+    ref_cols = [tuple(c) for c in json.loads(bytes(fx["extra"]["frame_columns"]).decode())]
+    assert [tuple(map(str, c)) for c in res.columns] == ref_cols
+    assert list(pmap.index) == [f"JRC_{i}" for i in range(16)]
+    np.testing.assert_array_equal(pmap["C"].values, fx["extra"]["grid_C"])
+    assert traj_rel_err(res.values, fx["extra"][f"frame_{solver}"]) <= 1e-9
