@@ -322,7 +322,7 @@ def build_model(prog: Program, *, solver: str, exec_model: str = "auto", **kw):
         raise ValueError("exec_model must be 'auto', 'instance' or 'network'")
     if exec_model in ("auto", "instance"):
         try:
-            limit = 4000 if exec_model == "auto" else 60000
+            limit = 4000 if exec_model == "auto" else 20000
             return InstanceModel(prog, solver=solver, max_nodes=limit, **kw)
         except UnsupportedModelError as e:
             if exec_model == "instance" or "too large" not in str(e):

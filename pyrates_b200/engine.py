@@ -35,7 +35,7 @@ class InstanceModel:
 
     def __init__(self, prog: Program, *, solver: str = "euler", sweep: Sequence[Tuple[str, int]] = (),
                  observers: Optional[Sequence[int]] = None, block: int = 128, fmad: bool = True,
-                 const_div_to_mul: bool = False, max_nodes: int = 60000):
+                 const_div_to_mul: bool = False, max_nodes: int = 6000):
         if solver not in FIXED_STEP_SOLVERS:
             raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
                                       f"Supported solvers: {list(FIXED_STEP_SOLVERS)}.")

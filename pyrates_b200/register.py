@@ -155,7 +155,13 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
                                                 backend="cuda", solver=solver, verbose=verbose, clear=False,
                                                 float_precision=float_precision, **kwargs)
         prog = func.program(args)
-        out_map, out_vars = circuit.get_variable_positions(outputs)
+        # CircuitTemplate.run resolves outputs BEFORE _state_var_indices is filled (circuit.py:474-482); with it
+        # filled, _get_var_idx (circuit.py:1229-1235) would index by the ambiguous short variable name.
+        saved, circuit._state_var_indices = circuit._state_var_indices, {}
+        try:
+            out_map, out_vars = circuit.get_variable_positions(outputs)
+        finally:
+            circuit._state_var_indices = saved
         obs, cols = [], []
         sv = circuit._ir.graph._state_var_indices
         for key, info in out_map.items():

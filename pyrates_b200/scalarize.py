@@ -760,7 +760,7 @@ class _Interp:
         return out
 
 
-def scalarize(prog: Program, sweep: Sequence[Tuple[str, int]] = (), max_nodes: int = 60000) -> ScalarRhs:
+def scalarize(prog: Program, sweep: Sequence[Tuple[str, int]] = (), max_nodes: int = 6000) -> ScalarRhs:
     """Lower ``prog`` to a scalar DAG.  ``sweep`` lists ``(arg_name, flat_element)`` pairs that vary
     per sweep instance (they become runtime 'param' leaves instead of baked constants)."""
     return _Interp(prog, sweep, max_nodes).run()

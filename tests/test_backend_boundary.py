@@ -21,6 +21,13 @@ needs_ref = pytest.mark.skipif(pyrates is None, reason="reference PyRates not im
 warnings.filterwarnings("ignore")
 
 
+def _fresh(path):
+    """from_yaml returns a cached template object that run() mutates in place: work on private copies."""
+    from copy import deepcopy
+    from pyrates import CircuitTemplate
+    return deepcopy(CircuitTemplate.from_yaml(path))
+
+
 def _norm(stmts):
     return [ast.dump(ast.parse(s.text())) for s in stmts]
 
@@ -44,8 +51,8 @@ def registered(tmp_path, monkeypatch):
     ("jrc_2delay", "model_templates.neural_mass_models.jansenrit.JRC_2delaycoupled", "euler"),
 ])
 def test_cuda_backend_records_same_program_as_numpy_backend(registered, name, path, solver):
-    from pyrates import CircuitTemplate, clear
-    c = CircuitTemplate.from_yaml(path)
+    from pyrates import clear
+    c = _fresh(path)
     fx = orc.load_fixture(golden_path(name))
     func, args, names, svmap = c.get_run_func("vector_field", step_size=fx["run"]["dt"], backend="cuda", solver=solver,
                                               float_precision="float64", verbose=False)
@@ -68,14 +75,14 @@ def test_new_solver_names_are_fixed_step(registered):
 @needs_ref
 def test_unsupported_solver_and_no_device_raise(registered):
     from pyrates import CircuitTemplate
-    c = CircuitTemplate.from_yaml("model_templates.neural_mass_models.qif.qif")
+    c = _fresh("model_templates.neural_mass_models.qif.qif")
     with pytest.raises(Exception, match="does not support solver"):
         c.run(simulation_time=0.01, step_size=1e-3, solver="scipy", outputs={"r": "p/qif_op/r"}, backend="cuda",
               verbose=False, in_place=False)
     try:
         rt.device_count()
     except rt.CudaBackendError:
-        c = CircuitTemplate.from_yaml("model_templates.neural_mass_models.qif.qif")
+        c = _fresh("model_templates.neural_mass_models.qif.qif")
         with pytest.raises(rt.CudaBackendError, match="no CPU execution path"):
             c.run(simulation_time=0.01, step_size=1e-3, solver="euler", outputs={"r": "p/qif_op/r"}, backend="cuda",
                   verbose=False)
@@ -96,8 +103,8 @@ def test_circuit_run_cuda_matches_numpy_backend(gpu, registered, path, out, solv
     from pyrates import CircuitTemplate
     kw = dict(simulation_time=T, step_size=dt, sampling_step_size=dt * 5, solver=solver, outputs={"o": out},
               verbose=False, float_precision=precision, clear=True)
-    ref = CircuitTemplate.from_yaml(path).run(backend="default", **kw)
-    got = CircuitTemplate.from_yaml(path).run(backend="cuda", **kw)
+    ref = _fresh(path).run(backend="default", **kw)
+    got = _fresh(path).run(backend="cuda", **kw)
     assert list(got.columns) == list(ref.columns) and np.allclose(got.index, ref.index)
     assert traj_rel_err(got.values, ref.values) <= RTOL[precision]
 
@@ -109,7 +116,7 @@ def test_circuit_run_with_inputs_and_state_writeback(gpu, registered):
     inp = np.sin(np.arange(500) * 0.02) * 3.0
     kw = dict(simulation_time=0.5, step_size=1e-3, solver="heun", outputs={"r": "p/qif_op/r", "v": "p/qif_op/v"},
               inputs={"p/qif_op/I_ext": inp}, verbose=False, float_precision="float64", clear=True)
-    c_ref, c_gpu = (CircuitTemplate.from_yaml("model_templates.neural_mass_models.qif.qif") for _ in range(2))
+    c_ref, c_gpu = (_fresh("model_templates.neural_mass_models.qif.qif") for _ in range(2))
     ref = c_ref.run(backend="default", **kw)
     got = c_gpu.run(backend="cuda", **kw)
     assert traj_rel_err(got.values, ref.values) <= 1e-9
