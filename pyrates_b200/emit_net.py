@@ -1,0 +1,372 @@
+"""CUDA C emitter for the *network* execution model: phased kernel IR (netcompile.NetIR) -> source.
+
+Generates ``prb_eval<STAGE>()`` — one rhs evaluation as a sequence of phases (full reductions, warp-per-row
+reductions with the element-wise tail fused behind them, thread-per-element loops, grid barriers in
+between) — and splices it into the hand-written solver template ``csrc/templates/net_kernel.cuh``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Set, Tuple
+
+import numpy as np
+
+from .emit_inst import SOLVER_IDS, _FUNC, _lit, read_template
+from .netcompile import MemArray, NetIR, Reduction, Store
+
+__all__ = ["NetKernel", "emit_net_kernel"]
+
+
+@dataclass
+class NetKernel:
+    source: str
+    n_state: int
+    n_obs: int
+    work_elems: int            # total `work` buffer elements (user arrays + 6 solver vectors)
+    work_user: int
+    work_init: np.ndarray
+    const_init: np.ndarray
+    iconst_init: np.ndarray
+    ring_init: np.ndarray
+    table_init: np.ndarray
+    block: int
+    solver: str
+    precision: str
+    evals_per_step: int
+    n_phases: int
+    kernel_name: str = "prb_integrate_net"
+
+
+class _Emitter:
+    def __init__(self, ir: NetIR, f32: bool, obs_off: int):
+        self.ir, self.g, self.f32 = ir, ir.graph, f32
+        self.roles: Dict[int, frozenset] = {}
+        self.red_work: Dict[int, MemArray] = {}
+        self.ring_index = {name: k for k, name in enumerate(a.name for a in ir.arrays.values() if a.space == "ring")}
+
+    # ---- role analysis: which loop indices a node depends on
+    def role(self, i: int) -> frozenset:
+        r = self.roles.get(i)
+        if r is not None:
+            return r
+        g = self.g
+        op, pl = g.ops[i], g.payload[i]
+        if op == "ld":
+            r = frozenset(pl[2])
+        elif op == "gather":
+            r = frozenset(pl[3])
+        elif op == "ldring":
+            r = frozenset(pl[2])
+        elif op == "ldm":
+            r = frozenset("ij")
+        elif op == "red":
+            r = frozenset("i") if pl[1] == "i" else frozenset()
+        elif op == "table":
+            r = frozenset("i") if pl[2] == "i" else frozenset()
+        else:
+            r = frozenset()
+            for a in g.args[i]:
+                r = r | self.role(a)
+        self.roles[i] = r
+        return r
+
+    # ---- addressing
+    def _ptr(self, arr: MemArray) -> str:
+        return {"y": "C.yin", "const": "C.consts", "work": "C.work", "iconst": "C.iconsts", "table": "C.tables",
+                "ring": "C.rings"}[arr.space]
+
+    def _load(self, arr: MemArray, index: str) -> str:
+        base = self._ptr(arr)
+        off = f"{arr.offset}LL + " if arr.space != "y" else ""
+        if arr.space in ("const", "iconst", "table"):
+            return f"__ldg({base} + {off}{index})"
+        return f"{base}[{off}{index}]"
+
+    def ref(self, i: int, cur: Tuple[int, int, bool], want_real=True) -> str:
+        g = self.g
+        op = g.ops[i]
+        if op == "const":
+            v = g.const_value(i)
+            if g.isint[i] and not want_real:
+                return f"({int(v)}LL)"
+            return _lit(float(v), self.f32)
+        if op == "t":
+            return "((real)C.t)" if want_real else "C.t"
+        if op == "red":
+            rid, kind = g.payload[i]
+            red = self.ir.reductions[rid]
+            if kind == "s":
+                return f"red{rid}"
+            if cur == (red.phase, red.n, True):
+                return f"red{rid}"
+            arr = self.red_work[rid]
+            return f"C.work[{arr.offset}LL + i]"
+        name = f"v{i}"
+        if g.isint[i] and want_real:
+            return f"((real){name})"
+        return name
+
+    def expr(self, i: int, cur) -> Optional[str]:
+        """C expression computing node i from its operands (None for leaf refs that need no temp)."""
+        g, ir = self.g, self.ir
+        op, a, pl = g.ops[i], g.args[i], g.payload[i]
+        r = lambda k, real=True: self.ref(k, cur, real)
+        if op in ("const", "t", "red"):
+            return None
+        if op == "ld":
+            arr = ir.arrays[pl[0]]
+            return self._load(arr, f"{pl[1]}LL + {pl[2]}")
+        if op == "lds":
+            arr = ir.arrays[pl[0]]
+            return self._load(arr, f"{pl[1]}LL")
+        if op == "ldm":
+            arr = ir.arrays[pl[0]]
+            return self._load(arr, f"i * {pl[2]}LL + j")
+        if op == "gather":
+            arr, iarr = ir.arrays[pl[0]], ir.arrays[pl[2]]
+            return self._load(arr, f"{pl[1]}LL + (long long){self._load(iarr, pl[3])}")
+        if op == "ldring":
+            arr = ir.arrays[pl[0]]
+            rows, L = arr.shape
+            k = self.ring_index[pl[0]]
+            return (f"C.rings[{arr.offset}LL + prb_ring_pos(C.head[{k}], {pl[1] - arr.rolls}, {L}) * {rows}LL + {pl[2]}]")
+        if op == "table":
+            arr = ir.arrays[pl[0]]
+            col = "i" if pl[2] == "i" else f"{pl[2]}LL"
+            return self._load(arr, f"{r(pl[1], False)} * {pl[3]}LL + {col}")
+        if g.isint[i]:
+            x = r(a[0], False)
+            y = r(a[1], False) if len(a) > 1 else None
+            return {"add": f"{x} + {y}", "sub": f"{x} - {y}", "mul": f"{x} * {y}", "neg": f"-{x}"}[op]
+        if op == "add":
+            return f"{r(a[0])} + {r(a[1])}"
+        if op == "sub":
+            return f"{r(a[0])} - {r(a[1])}"
+        if op == "mul":
+            return f"{r(a[0])} * {r(a[1])}"
+        if op == "div":
+            return f"{r(a[0])} / {r(a[1])}"
+        if op == "neg":
+            return f"-{r(a[0])}"
+        if op == "pow":
+            return f"pow({r(a[0])}, {r(a[1])})"
+        if op == "maximum":
+            return f"prb_max({r(a[0])}, {r(a[1])})"
+        if op == "minimum":
+            return f"prb_min({r(a[0])}, {r(a[1])})"
+        if op == "sign":
+            return f"prb_sign({r(a[0])})"
+        if op in _FUNC:
+            return f"{_FUNC[op]}({r(a[0])})"
+        raise NotImplementedError(f"no CUDA lowering for op `{op}`")
+
+    def order(self, roots: Sequence[int]) -> List[int]:
+        g = self.g
+        seen: Set[int] = set()
+        stack = list(roots)
+        while stack:
+            i = stack.pop()
+            if i in seen:
+                continue
+            seen.add(i)
+            stack.extend(g.args[i])
+            if g.ops[i] == "table":
+                stack.append(g.payload[i][1])
+        return sorted(seen)
+
+    def emit_nodes(self, nodes: Sequence[int], cur, emitted: Set[int], indent: str, only_roles=None) -> List[str]:
+        out = []
+        for i in nodes:
+            if i in emitted:
+                continue
+            if only_roles is not None and not (self.role(i) <= only_roles):
+                continue
+            e = self.expr(i, cur)
+            emitted.add(i)
+            if e is None:
+                continue
+            ty = "long long" if self.g.isint[i] else "real"
+            out.append(f"{indent}const {ty} v{i} = {e};")
+        return out
+
+    # ---- stores
+    def store_stmt(self, st: Store, cur, stage_tpl: str) -> str:
+        val = self.ref(st.node, cur)
+        t = st.target
+        if t[0] == "dy":
+            return f"prb_emit_k<STAGE>(C, {t[1]}LL + i, {val});"
+        if t[0] == "work":
+            arr = self.ir.arrays[t[1]]
+            return f"C.work[{arr.offset}LL + i] = {val};"
+        if t[0] == "work_at":
+            arr = self.ir.arrays[t[1]]
+            return f"C.work[{arr.offset + t[2]}LL] = {val};"
+        if t[0] == "scatter":
+            arr, iarr = self.ir.arrays[t[1]], self.ir.arrays[t[2]]
+            return f"C.work[{arr.offset}LL + (long long){self._load(iarr, 'i')}] = {val};"
+        if t[0] == "ring":
+            arr = self.ir.arrays[t[1]]
+            rows, L = arr.shape
+            k = self.ring_index[t[1]]
+            return f"C.rings[{arr.offset}LL + prb_ring_pos(C.head[{k}], {t[2] - arr.rolls}, {L}) * {rows}LL + i] = {val};"
+        raise NotImplementedError(t[0])
+
+
+def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequence[int], block: int = 512) -> NetKernel:
+    if solver not in SOLVER_IDS:
+        raise ValueError(f"unknown solver `{solver}`")
+    f32 = precision == "float32"
+    g = ir.graph
+    ns = ir.n_state
+    # reduction results get a work array so that consumers outside the fused row task can read them
+    work_size = ir.work_size
+    em = _Emitter(ir, f32, 0)
+    for red in ir.reductions:
+        if red.kind == "row":
+            arr = MemArray(f"__red{red.id}", "work", (red.n,), work_size, np.zeros(red.n))
+            work_size += ((red.n + 31) // 32) * 32
+            ir.arrays[arr.name] = arr
+            em.red_work[red.id] = arr
+    # observer index table goes to the end of iconsts
+    obs = np.asarray(list(observers), dtype=np.int32)
+    all_state = obs.size == ns and np.array_equal(obs, np.arange(ns))
+    obs_off = ir.iconst_size
+    iconst_size = ir.iconst_size + (0 if all_state else ((obs.size + 31) // 32) * 32)
+
+    body: List[str] = []
+    full_reds = [r for r in ir.reductions if r.kind == "full"]
+    for r in full_reds:
+        body.append(f"    real red{r.id} = (real)0;")
+    n_phases = ir.n_phases
+    for p in range(n_phases):
+        body.append(f"    // ---------------- phase {p}")
+        # (1) full reductions, block-redundant
+        for r in [r for r in full_reds if r.phase == p]:
+            cur = (p, -1, False)
+            emitted: Set[int] = set()
+            nodes = em.order([r.node])
+            body.append("    {")
+            body.extend(em.emit_nodes(nodes, cur, emitted, "        ", only_roles=frozenset()))
+            body.append("        real acc = (real)0;")
+            body.append(f"        for (long long j = threadIdx.x; j < {r.m}LL; j += blockDim.x) {{")
+            body.extend(em.emit_nodes(nodes, cur, emitted, "            "))
+            body.append(f"            acc += {em.ref(r.node, cur)};")
+            body.append("        }")
+            body.append(f"        red{r.id} = prb_block_sum(acc);")
+            body.append("    }")
+        # (2) groups by length
+        stores_p = [s for s in ir.stores if s.phase == p]
+        rows_p = [r for r in ir.reductions if r.kind == "row" and r.phase == p]
+        lengths = sorted({s.n for s in stores_p} | {r.n for r in rows_p})
+        for n in lengths:
+            reds = [r for r in rows_p if r.n == n]
+            sts = [s for s in stores_p if s.n == n]
+            if reds:
+                cur = (p, n, True)
+                body.append(f"    for (long long i = C.gwarp; i < {n}LL; i += C.nwarps) {{      // warp per row, n = {n}")
+                emitted = set()
+                for r in reds:
+                    if r.simple is not None:
+                        W, X, xoff = r.simple
+                        warr, xarr = ir.arrays[W], ir.arrays[X]
+                        xptr = f"{em._ptr(xarr)} + {('%dLL' % (xarr.offset + xoff)) if xarr.space != 'y' else ('%dLL' % xoff)}"
+                        body.append(f"        const real red{r.id} = prb_row_dot(C.consts + {warr.offset}LL + i * {r.m}LL, "
+                                    f"{xptr}, {r.m}, C.lane);")
+                    else:
+                        nodes = em.order([r.node])
+                        body.extend(em.emit_nodes(nodes, cur, emitted, "        ", only_roles=frozenset("i")))
+                        body.append(f"        real acc{r.id}a = (real)0, acc{r.id}b = (real)0;")
+                        inner: Set[int] = set(emitted)
+                        body.append(f"        for (long long j = C.lane; j < {r.m}LL; j += 64) {{")
+                        body.extend(em.emit_nodes(nodes, cur, inner, "            "))
+                        body.append(f"            acc{r.id}a += {em.ref(r.node, cur)};")
+                        body.append(f"            const long long jb = j + 32;")
+                        body.append(f"            if (jb < {r.m}LL) {{")
+                        body.append(f"                const long long j = jb;")
+                        inner2: Set[int] = set(emitted)
+                        body.extend(em.emit_nodes(nodes, cur, inner2, "                "))
+                        body.append(f"                acc{r.id}b += {em.ref(r.node, cur)};")
+                        body.append("            }")
+                        body.append("        }")
+                        body.append(f"        const real red{r.id} = prb_warp_sum(acc{r.id}a + acc{r.id}b);")
+                    need_store = any(_uses_red(g, em, s.node, r.id) and (s.phase, s.n) != (p, n) for s in ir.stores) or \
+                        any(_uses_red(g, em, q.node, r.id) for q in ir.reductions)
+                    if need_store:
+                        body.append(f"        if (C.lane == 0) C.work[{em.red_work[r.id].offset}LL + i] = red{r.id};")
+                roots = [s.node for s in sts]
+                nodes = em.order(roots)
+                body.extend(em.emit_nodes(nodes, cur, emitted, "        "))
+                if sts:
+                    body.append("        if (C.lane == 0) {")
+                    for s in sts:
+                        body.append("            " + em.store_stmt(s, cur, "STAGE"))
+                    body.append("        }")
+                body.append("    }")
+            elif sts:
+                cur = (p, n, False)
+                roots = [s.node for s in sts]
+                nodes = em.order(roots)
+                emitted = set()
+                body.append(f"    for (long long i = C.gtid; i < {n}LL; i += C.gsize) {{        // thread per element, n = {n}")
+                body.extend(em.emit_nodes(nodes, cur, emitted, "        "))
+                for s in sts:
+                    body.append("        " + em.store_stmt(s, cur, "STAGE"))
+                body.append("    }")
+        if p < n_phases - 1:
+            body.append("    prb_grid_barrier(C);")
+
+    rings = [a for a in ir.arrays.values() if a.space == "ring"]
+    src: List[str] = []
+    src.append("// Generated by pyrates_b200.emit_net — do not edit.  Network execution model (persistent cooperative grid).")
+    src.append(read_template("prb_kernel_abi.cuh"))
+    src.append(f"typedef {'float' if f32 else 'double'} real;")
+    src.append(f"#define PRB_NS {ns}LL")
+    src.append(f"#define PRB_NOBS {obs.size}LL")
+    src.append(f"#define PRB_NRINGS {len(rings)}")
+    src.append(f"#define PRB_SOLVER {SOLVER_IDS[solver]}")
+    src.append(f"#define PRB_BLOCK {block}")
+    src.append(f"#define PRB_WORK_USER {work_size}LL")
+    src.append("#define PRB_OBS_INDEX(o) (o)" if all_state else f"#define PRB_OBS_INDEX(o) ((long long)A.iconsts[{obs_off}LL + (o)])")
+    src.append("struct PrbNet;")
+    src.append("__device__ __forceinline__ void prb_net_init_heads(PrbNet& C, long long eval0);")
+    src.append("__device__ __forceinline__ void prb_net_advance_heads(PrbNet& C);")
+    src.append(read_template("net_kernel.cuh"))
+    heads_i, heads_a = [], []
+    for k, a in enumerate(rings):
+        L = a.shape[1]
+        heads_i.append(f"    C.head[{k}] = (int)((eval0 * {a.rolls}LL) % {L}LL);")
+        if a.rolls:
+            heads_a.append(f"    C.head[{k}] = (C.head[{k}] + {a.rolls % L}) % {L};")
+    src.append("__device__ __forceinline__ void prb_net_init_heads(PrbNet& C, long long eval0) {\n" + "\n".join(heads_i) + "\n}")
+    src.append("__device__ __forceinline__ void prb_net_advance_heads(PrbNet& C) {\n" + "\n".join(heads_a) + "\n}")
+    src.append("template <int STAGE> __device__ void prb_eval(PrbNet& C) {")
+    src.extend(body)
+    src.append("}")
+
+    real = np.float32 if f32 else np.float64
+
+    def pack(space, size, dtype):
+        buf = np.zeros(max(size, 1), dtype=dtype)
+        for a in ir.arrays.values():
+            if a.space == space and a.init is not None:
+                v = np.asarray(a.init)
+                if space == "ring":
+                    v = v.T                        # device layout [L][rows]: a delay column is contiguous
+                buf[a.offset:a.offset + a.size] = v.reshape(-1).astype(dtype)
+        return buf
+
+    iconst = pack("iconst", iconst_size, np.int32)
+    if not all_state:
+        iconst[obs_off:obs_off + obs.size] = obs
+    evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4}[solver]
+    return NetKernel("\n".join(src) + "\n", ns, int(obs.size), work_size + 6 * ns, work_size,
+                     pack("work", work_size, real), pack("const", ir.const_size, real), iconst,
+                     pack("ring", ir.ring_size, real), pack("table", ir.table_size, real), block, solver, precision,
+                     evals, n_phases)
+
+
+def _uses_red(g, em: _Emitter, node: int, rid: int) -> bool:
+    for i in em.order([node]):
+        if g.ops[i] == "red" and g.payload[i][0] == rid:
+            return True
+    return False

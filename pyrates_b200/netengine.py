@@ -1,0 +1,169 @@
+"""Host-side driver of the network execution model (persistent cooperative kernel, one network instance).
+
+Counterpart of ``engine.InstanceModel`` for models whose state does not fit one thread: builds the phased
+kernel (``netcompile`` + ``emit_net``), owns the device buffers (packed constants incl. the connectivity
+matrices, work/stage vectors, ring buffers, grid-barrier word) and launches ``prb_integrate_net`` through
+the C ABI with ``cooperative=1``.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import runtime as rt
+from .emit_net import NetKernel, emit_net_kernel
+from .engine import FIXED_STEP_SOLVERS, n_steps_for
+from .netcompile import NetIR, netcompile
+from .program import Program
+
+__all__ = ["NetworkModel", "NetworkSession", "build_check", "smoke_check"]
+
+
+class NetworkModel:
+    def __init__(self, prog: Program, *, solver: str = "euler", observers: Optional[Sequence[int]] = None,
+                 block: int = 512, fmad: bool = True, blocks_per_sm: int = 1):
+        if solver not in FIXED_STEP_SOLVERS:
+            raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
+                                      f"Supported solvers: {list(FIXED_STEP_SOLVERS)}.")
+        self.prog = prog
+        self.solver = solver
+        self.precision = prog.float_precision
+        self.real = prog.real_dtype
+        self.ir: NetIR = netcompile(prog)
+        self.observers = list(range(prog.n_state)) if observers is None else [int(o) for o in observers]
+        self.kernel: NetKernel = emit_net_kernel(self.ir, solver=solver, precision=self.precision,
+                                                 observers=self.observers, block=block)
+        self.fmad = fmad
+        self.blocks_per_sm = blocks_per_sm
+        self._module: Optional[rt.Module] = None
+        self.t0 = int(np.asarray(prog.arg_by_kind("t").value))
+
+    @property
+    def module(self) -> rt.Module:
+        if self._module is None:
+            self._module = rt.compile_module(self.kernel.source, f"prb_net_{self.solver}.cu", fmad=self.fmad)
+        return self._module
+
+    @property
+    def n_state(self) -> int:
+        return self.kernel.n_state
+
+    def session(self, n_samples: int, stream=None) -> "NetworkSession":
+        return NetworkSession(self, n_samples, stream)
+
+    def run(self, T: float, dt: float, dts: Optional[float] = None, *, y0: Optional[np.ndarray] = None, **_):
+        steps, store_step, n_samples = n_steps_for(T, dt, dts)
+        s = self.session(n_samples)
+        try:
+            s.reset(y0)
+            s.launch(steps, dt, store_step)
+            out = s.download()
+            y_final = s.download_state()
+        finally:
+            s.free()
+        return out[:, :, None], y_final[:, None]
+
+
+class NetworkSession:
+    def __init__(self, model: NetworkModel, n_samples: int, stream=None):
+        self.m = model
+        k = model.kernel
+        real = model.real
+        self.stream = stream
+        self.n_samples = int(n_samples)
+        item = np.dtype(real).itemsize
+        self.d_y = rt.DeviceBuffer(max(k.n_state, 1) * item)
+        self.d_out = rt.DeviceBuffer(max(self.n_samples * k.n_obs, 1) * item)
+        self.d_consts = rt.DeviceBuffer.from_host(k.const_init.astype(real))
+        self.d_iconsts = rt.DeviceBuffer.from_host(k.iconst_init.astype(np.int32))
+        self.d_tables = rt.DeviceBuffer.from_host(k.table_init.astype(real))
+        self.d_work = rt.DeviceBuffer(max(k.work_elems, 1) * item)
+        self.d_rings = rt.DeviceBuffer(max(k.ring_init.size, 1) * item)
+        self.d_sync = rt.DeviceBuffer(64)
+        self.sm_count = rt.device_info()["sm_count"]
+        self.steps_done = 0
+        self.samples_done = 0
+
+    def reset(self, y0: Optional[np.ndarray] = None):
+        k, real = self.m.kernel, self.m.real
+        y0 = self.m.prog.y0 if y0 is None else np.asarray(y0).reshape(-1)
+        self.d_y.upload(np.ascontiguousarray(y0, dtype=real), self.stream)
+        work = np.zeros(max(k.work_elems, 1), dtype=real)
+        work[: k.work_init.size] = k.work_init
+        self.d_work.upload(work, self.stream)
+        self.d_rings.upload(np.ascontiguousarray(k.ring_init, dtype=real), self.stream)
+        self.steps_done = 0
+        self.samples_done = 0
+
+    def launch(self, n_steps: int, dt: float, store_step: int = 1):
+        k = self.m.kernel
+        new_samples = 0
+        if n_steps > 0:
+            first = (-self.steps_done) % store_step
+            if first < n_steps:
+                new_samples = (n_steps - 1 - first) // store_step + 1
+        if self.samples_done + new_samples > self.n_samples:
+            raise ValueError("launch would overflow the recording buffer")
+        self.d_sync.zero(self.stream)
+        a = rt.KernelArgs()
+        a.n_steps, a.store_step, a.step0 = int(n_steps), int(store_step), int(self.steps_done)
+        a.t0, a.eval0 = self.m.t0, int(self.steps_done) * k.evals_per_step
+        a.n_inst, a.sample0, a.dt = 1, int(self.samples_done), float(dt)
+        a.y, a.out = self.d_y.ptr, self.d_out.ptr
+        a.params = a.slots = None
+        a.rings, a.tables = self.d_rings.ptr, self.d_tables.ptr
+        a.consts, a.iconsts = self.d_consts.ptr, self.d_iconsts.ptr
+        a.work, a.sync = self.d_work.ptr, self.d_sync.ptr
+        self.m.module.run(k.kernel_name, a, block=k.block, grid=self.sm_count * self.m.blocks_per_sm,
+                          cooperative=True, stream=self.stream)
+        self.steps_done += int(n_steps)
+        self.samples_done += new_samples
+        return new_samples
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.n_samples, self.m.kernel.n_obs), dtype=self.m.real)
+        if out.size:
+            self.d_out.download(out, self.stream)
+        if self.stream is not None:
+            self.stream.synchronize()
+        return out
+
+    def download_state(self) -> np.ndarray:
+        y = np.empty(self.m.kernel.n_state, dtype=self.m.real)
+        self.d_y.download(y, self.stream)
+        if self.stream is not None:
+            self.stream.synchronize()
+        return y
+
+    def free(self):
+        for n in ("d_y", "d_out", "d_consts", "d_iconsts", "d_tables", "d_work", "d_rings", "d_sync"):
+            b = getattr(self, n, None)
+            if b is not None:
+                b.free()
+
+
+# ----------------------------------------------------------------------------- driver hooks
+_CHECK = [("wc_n128", "rk4"), ("qsfa_both_n96", "heun"), ("kuramoto_n128", "euler"), ("jrc_grid_b1024", "heun")]
+
+
+def build_check(golden_dir: str) -> None:
+    """NVRTC-compile (sm_100a) one network kernel per coupling family; used by __graft_entry__.build()."""
+    for name, solver in _CHECK:
+        m = NetworkModel(Program.load(os.path.join(golden_dir, name + ".npz")), solver=solver)
+        cubin = m.module.cubin
+        assert cubin[:4] == b"\x7fELF", name
+        print(f"[build] net {name}/{solver}: {m.kernel.n_phases} phase(s), cubin {len(cubin)} bytes")
+
+
+def smoke_check(golden_dir: str) -> None:
+    from oracle import numpy_oracle as orc
+    path = os.path.join(golden_dir, "wc_n128.npz")
+    fx = orc.load_fixture(path)
+    r = fx["run"]
+    out, _ = NetworkModel(Program.load(path), solver="rk4").run(r["T"], r["dt"], r["dts"])
+    ref = fx["extra"]["rec_rk4"]
+    err = float(np.max(np.abs(out[:, :, 0] - ref)) / np.max(np.abs(ref)))
+    print(f"[smoke] WC N=128 dense, rk4 (network kernel): max scaled error vs oracle {err:.3e}")
+    assert err < 1e-9, err

@@ -1,0 +1,59 @@
+"""GPU parity of the network execution model (persistent cooperative kernel): dense dot coupling (WC, QIF-SFA),
+gamma-kernel cascades, delay ring buffers, pair-space wsum(sin) (Kuramoto), global vsum, gather/scatter edges of
+vectorised circuits — vs golden trajectories of the reference NumPy backend / oracle-defined rk4 + heun_true."""
+import numpy as np
+import pytest
+
+from conftest import RTOL, golden_path, traj_rel_err
+from oracle import numpy_oracle as orc
+from pyrates_b200 import runtime as rt
+from pyrates_b200.netengine import NetworkModel
+from pyrates_b200.program import Program
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
+
+NAMES = ["wc_n8", "wc_n128", "wc_n128_f32", "qsfa_cascade_n8", "qsfa_ring_n8", "qsfa_both_n8", "qsfa_both_n96",
+         "kuramoto_n8", "kuramoto_n128", "kuramoto_scalar_n128", "jrc_grid_b16", "jrc_grid_b1024", "jrc", "net8", "net9",
+         "net13", "jrc_2delay", "qif_input", "ring_kat", "gamma_kat"]
+SOLVERS = ["euler", "heun", "heun_true", "rk4"]
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
+@pytest.mark.parametrize("name", NAMES)
+def test_network_kernel_matches_golden(gpu, name, solver):
+    fx = orc.load_fixture(golden_path(name))
+    prog = Program.load(golden_path(name))
+    r = fx["run"]
+    before = rt.launch_count()
+    out, y_final = NetworkModel(prog, solver=solver).run(r["T"], r["dt"], r["dts"])
+    assert rt.launch_count() == before + 1          # the whole simulation is one persistent launch
+    ref = fx["extra"][f"rec_{solver}"]
+    got = out[:, :, 0]
+    assert got.shape == ref.shape
+    err = traj_rel_err(got, ref)
+    assert err <= RTOL[prog.float_precision], f"{name}/{solver}: rel err {err:.3e}"
+
+
+def test_network_chunked_launches_continue(gpu):
+    for name in ("qsfa_both_n96", "wc_n128"):
+        fx = orc.load_fixture(golden_path(name))
+        prog = Program.load(golden_path(name))
+        r = fx["run"]
+        from pyrates_b200.engine import n_steps_for
+        steps, ss, ns = n_steps_for(r["T"], r["dt"], r["dts"])
+        m = NetworkModel(prog, solver="heun")
+        s = m.session(ns)
+        s.reset()
+        cut = steps // 2 + 1
+        s.launch(cut, r["dt"], ss)
+        s.launch(steps - cut, r["dt"], ss)
+        got = s.download()
+        s.free()
+        assert traj_rel_err(got, fx["extra"]["rec_heun"]) <= RTOL[prog.float_precision]
+
+
+def test_backend_auto_picks_network_model_for_large_programs(gpu):
+    from pyrates_b200.backend import build_model
+    from pyrates_b200.engine import InstanceModel
+    assert isinstance(build_model(Program.load(golden_path("qif")), solver="euler"), InstanceModel)
+    assert isinstance(build_model(Program.load(golden_path("wc_n128")), solver="euler"), NetworkModel)
