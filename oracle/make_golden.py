@@ -93,7 +93,11 @@ def _wc_pop(N, seed=42):
         W = rng.normal(0.0, 1.0 / np.sqrt(N), (N, N))
         np.fill_diagonal(W, 15.0)
         exc = NodeTemplate.from_yaml("model_templates.neural_mass_models.wilsoncowan.exc_pop")
-        pop = PopulationTemplate(name="e", node=exc, n=N)
+        # the template's defaults (r=0, r_ext=0) sit exactly on a fixed point: start from random rates and
+        # heterogeneous thresholds so the trajectory actually exercises the coupling
+        pop = PopulationTemplate(name="e", node=exc, n=N,
+                                 params={"rate_op/r": list(rng.uniform(0.05, 0.6, N)),
+                                         "se_op/theta": list(rng.normal(2.0, 0.5, N))})
         conn = Connectivity(source="e/rate_op/r", target="e/se_op/r_in", weights=W)
         return CircuitTemplate(name=f"wc_n{N}", populations={"e": pop}, connections=[conn])
     return build
