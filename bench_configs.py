@@ -1,0 +1,176 @@
+#!/usr/bin/env python
+"""Secondary benchmark: the coupled-network configs of BASELINE.json (C3 WC dense, C4 QIF-SFA delays, C5 Kuramoto)
+on the network execution model, each next to the NumPy oracle port on the host CPU.
+
+Programs at the named sizes are obtained by *resizing* the golden fixture programs (tests/golden/*_n8.npz, captured
+from the reference at N=8): the generated statements do not depend on N except through slice bounds and array
+shapes, so every dimension equal to the fixture's N is mapped to the requested N and the arrays are re-drawn from
+the seeded distributions SURVEY.md §8d prescribes.  (The reference itself is not available on the GPU box.)
+
+    python bench_configs.py --config c3 --n 8192 --solver euler --steps 200
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from pyrates_b200.program import Arg, Program, Stmt   # noqa: E402
+
+
+def resize_program(prog: Program, n_old: int, n_new: int, fill) -> Program:
+    """Map every array dimension == n_old to n_new and rescale the y/dy slice bounds accordingly.
+    ``fill(name, shape, old_value)`` returns the new array for argument `name`."""
+    f = n_new // n_old
+    assert n_new % n_old == 0
+
+    def scale_slices(text):
+        return re.sub(r"\b(y|dy)\[(\d+):(\d+)\]", lambda m: f"{m.group(1)}[{int(m.group(2)) * f}:{int(m.group(3)) * f}]", text)
+
+    stmts = [Stmt(s.lhs, scale_slices(s.rhs), None if s.lhs_idx is None else
+                  re.sub(r"^(\d+):(\d+)$", lambda m: f"{int(m.group(1)) * f}:{int(m.group(2)) * f}", s.lhs_idx))
+             for s in prog.stmts]
+    args = []
+    for a in prog.args:
+        v = np.asarray(a.value)
+        if a.kind in ("y", "dy"):
+            shape = (v.size * f,)
+        else:
+            shape = tuple(n_new if d == n_old else d for d in v.shape)
+        args.append(Arg(a.name, a.kind, np.asarray(fill(a.name, shape, v), dtype=v.dtype).reshape(shape), a.label))
+    return Program(args, stmts, {}, prog.float_precision, prog.func_name)
+
+
+def _tile(old, shape):
+    old = np.asarray(old)
+    if old.shape == tuple(shape):
+        return old
+    if old.ndim == 0:
+        return np.full(shape, old)
+    reps = [int(np.ceil(s / o)) for s, o in zip(shape, old.shape)]
+    return np.tile(old, reps)[tuple(slice(0, s) for s in shape)]
+
+
+def make_c3(n: int) -> Program:
+    """WC N-node dense network: W diag 15, off-diag N(0, 1/sqrt(N)), seed 42 (examples/benchmark_population_connectivity.py:31-39)."""
+    base = Program.load(os.path.join(ROOT, "tests", "golden", "wc_n8.npz"))
+    rng = np.random.default_rng(42)
+
+    def fill(name, shape, old):
+        if name == "weight":
+            W = rng.normal(0.0, 1.0 / np.sqrt(n), shape)
+            np.fill_diagonal(W, 15.0)
+            return W
+        if name == "y":
+            return rng.uniform(0.05, 0.6, shape)
+        if name == "theta":
+            return rng.normal(2.0, 0.5, shape)
+        return _tile(old, shape)
+    return resize_program(base, 8, n, fill)
+
+
+def make_c4(n: int) -> Program:
+    """QIF-SFA, two populations of n units: p1->p2 gamma-kernel delay (cascade n=4), p2->p1 ring-buffer delay of 3 steps
+    (SURVEY §8d C4 (iii)); eta ~ N(-5,1), W ~ N(0, 1/sqrt(n)), seed 42."""
+    base = Program.load(os.path.join(ROOT, "tests", "golden", "qsfa_both_n8.npz"))
+    rng = np.random.default_rng(42)
+
+    def fill(name, shape, old):
+        if name.startswith("weight"):
+            return rng.normal(0.0, 1.0 / np.sqrt(n), shape)
+        if name.startswith("eta"):
+            return rng.normal(-5.0, 1.0, shape)
+        if name == "r_buffer":
+            return np.zeros(shape)
+        return _tile(old, shape)
+    return resize_program(base, 8, n, fill)
+
+
+def make_c5(n: int) -> Program:
+    """Kuramoto, N phase oscillators, dense W ~ U(0, 2/N) with sin(theta_j - theta_i) pair coupling."""
+    base = Program.load(os.path.join(ROOT, "tests", "golden", "kuramoto_n8.npz"))
+
+    def fill(name, shape, old):
+        if name == "weight":
+            return np.random.default_rng(2).uniform(0.0, 2.0 / n, shape)
+        if name == "y":
+            return np.random.default_rng(1).uniform(0, 2 * np.pi, shape)
+        if name == "omega":
+            return np.random.default_rng(1).normal(10, 1, shape)
+        return _tile(old, shape)
+    return resize_program(base, 8, n, fill)
+
+
+CONFIGS = {"c3": (make_c3, 1, 1), "c4": (make_c4, 12, 2), "c5": (make_c5, 1, 1)}   # (builder, n_sv per unit, populations)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", required=True, choices=sorted(CONFIGS))
+    ap.add_argument("--n", type=int, required=True)
+    ap.add_argument("--solver", default="euler")
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--block", type=int, default=512)
+    ap.add_argument("--check", action="store_true", help="compare the first cpu-steps against the oracle")
+    a = ap.parse_args()
+    from pyrates_b200 import runtime as rt
+    from pyrates_b200.netengine import NetworkModel
+    build, _, pops = CONFIGS[a.config]
+    prog = build(a.n)
+    dt = 1e-3
+    m = NetworkModel(prog, solver=a.solver, observers=[0], block=a.block)
+    t0 = time.perf_counter()
+    m.module
+    jit_s = time.perf_counter() - t0
+    s = m.session(a.steps)
+    s.reset()
+    s.launch(min(a.steps, 20), dt, 1)
+    rt.synchronize()
+    s.reset()
+    e0, e1 = rt.Event(), rt.Event()
+    e0.record()
+    s.launch(a.steps, dt, 1)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_ms(e1)
+    evals = m.kernel.evals_per_step
+    nodes = a.n * pops
+    wbytes = sum(arr.size for arr in m.ir.arrays.values() if arr.space == "const" and len(arr.shape) == 2) * np.dtype(m.real).itemsize
+    hbm = 6548.2
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        hbm = float(json.load(open(p))["hbm_gbs"])
+    achieved = wbytes * evals * a.steps / (ms * 1e-3) / 1e9
+    line = {"config": a.config, "n": a.n, "solver": a.solver, "steps": a.steps, "ms_per_step": ms / a.steps,
+            "node_steps_per_s": nodes * a.steps / (ms * 1e-3), "evals_per_step": evals, "W_bytes": wbytes,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         "model": "W bytes x evaluations per step (state vectors negligible)"},
+            "jit_s": jit_s, "phases": m.kernel.n_phases, "block": a.block}
+    if a.cpu_steps:
+        from oracle import numpy_oracle as orc
+        f = orc.build_vector_field(prog.source())
+        args = [np.array(x.value, copy=True) for x in prog.args]
+        args[0] = args[0][()]
+        t0 = time.perf_counter()
+        rec, _ = orc.run(f, args, a.cpu_steps * dt, dt, None, a.solver if a.solver != "heun" else "heun")
+        cpu_s = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": nodes * a.cpu_steps / cpu_s, "unit": "node-steps/s", "kind": "port",
+                                "cores": os.cpu_count(), "sample": f"{a.cpu_steps} steps, NumPy/OpenBLAS default threads"}
+        if a.check:
+            out = s.download()[: a.cpu_steps, 0]
+            line["max_abs_diff_vs_oracle_obs0"] = float(np.max(np.abs(out - rec[:, 0])))
+    print(json.dumps(line))
+    s.free()
+
+
+if __name__ == "__main__":
+    main()
