@@ -124,10 +124,19 @@ def main():
     a = ap.parse_args()
     from pyrates_b200 import runtime as rt
     from pyrates_b200.netengine import NetworkModel
+    rank, world, local_rank = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    dist = None
+    if world > 1:
+        # one process per GPU; rows of W are sharded, stage vectors are all-gathered INSIDE the kernel over NVLink
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rt.set_device(local_rank)
     build, _, pops = CONFIGS[a.config]
     prog = build(a.n)
     dt = 1e-3
-    m = NetworkModel(prog, solver=a.solver, observers=[0], block=a.block)
+    m = NetworkModel(prog, solver=a.solver, observers=[0], block=a.block, rank=rank, world=world)
     t0 = time.perf_counter()
     m.module
     jit_s = time.perf_counter() - t0
@@ -142,6 +151,12 @@ def main():
     e1.record()
     e1.synchronize()
     ms = e0.elapsed_ms(e1)
+    s.check()
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     evals = m.kernel.evals_per_step
     nodes = a.n * pops
     wbytes = sum(arr.size for arr in m.ir.arrays.values() if arr.space == "const" and len(arr.shape) == 2) * np.dtype(m.real).itemsize
@@ -150,10 +165,14 @@ def main():
     if os.path.exists(p):
         hbm = float(json.load(open(p))["hbm_gbs"])
     achieved = wbytes * evals * a.steps / (ms * 1e-3) / 1e9
-    line = {"config": a.config, "n": a.n, "solver": a.solver, "steps": a.steps, "ms_per_step": ms / a.steps,
+    if rank != 0:
+        s.free()
+        dist.destroy_process_group()
+        return
+    line = {"config": a.config, "n": a.n, "solver": a.solver, "n_gpus": world, "steps": a.steps, "ms_per_step": ms / a.steps,
             "node_steps_per_s": nodes * a.steps / (ms * 1e-3), "evals_per_step": evals, "W_bytes": wbytes,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "model": "W bytes x evaluations per step (state vectors negligible)"},
+                         "model": "this rank's W shard bytes x evaluations per step (state vectors negligible); per GPU"},
             "jit_s": jit_s, "phases": m.kernel.n_phases, "block": a.block}
     if a.cpu_steps:
         from oracle import numpy_oracle as orc
@@ -170,6 +189,8 @@ def main():
             line["max_abs_diff_vs_oracle_obs0"] = float(np.max(np.abs(out - rec[:, 0])))
     print(json.dumps(line))
     s.free()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

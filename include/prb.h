@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PRB_ABI_VERSION 1
+#define PRB_ABI_VERSION 2
 
 typedef enum prb_status {
     PRB_OK = 0,
@@ -57,7 +57,10 @@ enum { PRB_SOLVER_EULER = 0, PRB_SOLVER_HEUN_REF = 1, PRB_SOLVER_HEUN = 2, PRB_S
  *   tables [..]                    timed-input tables u[t] shared by all instances (circuit.py:1711-1719)
  *   consts / iconsts               packed real / int32 constant arrays of network-mode kernels (W, idx)
  *   work                           network-mode scratch (stage vectors, materialised intermediates)
- *   sync                           network-mode grid-barrier words (zero-initialised by the caller)
+ *   sync                           network-mode barrier words, 64-bit each (zero-initialised by the caller):
+ *                                  [0] local CTA arrivals, [1] release epoch, [2] error flag, [8+q] arrival epoch of rank q
+ *   peers                          multi-GPU network mode: device array of 3*world pointers
+ *                                  {work[0..world), rings[0..world), sync[0..world)} of all ranks (IPC-mapped)
  */
 typedef struct prb_kernel_args {
     int64_t n_steps;      /* solver steps to perform in this launch */
@@ -78,6 +81,9 @@ typedef struct prb_kernel_args {
     const int32_t* iconsts;
     void*       work;
     unsigned int* sync;
+    void* const* peers;   /* NULL unless world > 1 */
+    int32_t     rank;
+    int32_t     world;
 } prb_kernel_args;
 
 /* Launch descriptor for prb_run. */
@@ -147,6 +153,12 @@ int prb_memset(void* dptr, int byte, size_t bytes, void* stream);
 int prb_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
 int prb_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
 int prb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+/* CUDA IPC: share a prb_malloc'ed buffer with the other ranks of a multi-GPU network run (one process per GPU);
+ * the opening process gets a peer pointer that kernels may load/store over NVLink. */
+#define PRB_IPC_HANDLE_BYTES 64
+int prb_ipc_get_handle(void* dptr, unsigned char* handle /* [PRB_IPC_HANDLE_BYTES] */);
+int prb_ipc_open_handle(const unsigned char* handle, void** dptr);
+int prb_ipc_close_handle(void* dptr);
 int prb_host_alloc(void** hptr, size_t bytes);       /* pinned host memory */
 int prb_host_free(void* hptr);
 int prb_stream_create(void** stream);

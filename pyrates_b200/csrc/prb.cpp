@@ -49,7 +49,8 @@ int fail(int code, const char* fmt, ...) {
     X(cuMemsetD8Async) X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2) X(cuMemcpyDtoDAsync_v2)    \
     X(cuMemHostAlloc) X(cuMemFreeHost) X(cuStreamCreate) X(cuStreamDestroy_v2)                    \
     X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuEventCreate) X(cuEventDestroy_v2) X(cuEventRecord)                 \
-    X(cuEventSynchronize) X(cuEventElapsedTime) X(cuGetErrorString) X(cuGetErrorName)
+    X(cuEventSynchronize) X(cuEventElapsedTime) X(cuGetErrorString) X(cuGetErrorName)             \
+    X(cuIpcGetMemHandle) X(cuIpcOpenMemHandle_v2) X(cuIpcCloseMemHandle)
 
 struct Driver {
     void* lib = nullptr;
@@ -328,6 +329,7 @@ int prb_run(prb_module* m, const char* kernel, const prb_run_desc* d) {
         if (grid > max_grid)
             return fail(PRB_ERR_LAUNCH, "cooperative grid %u exceeds co-resident capacity %u", grid, max_grid);
         if (!a.sync) return fail(PRB_ERR_INVALID, "cooperative kernels need args.sync (grid barrier words)");
+        if (a.world > 1 && !a.peers) return fail(PRB_ERR_INVALID, "multi-GPU network kernels need args.peers");
     } else if (grid == 0) {
         grid = (unsigned)((a.n_inst + d->block_dim - 1) / d->block_dim);
     }
@@ -376,6 +378,31 @@ int prb_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
 int prb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
     if (int e = need_ctx()) return e;
     if (bytes) CU(cuMemcpyDtoDAsync_v2((CUdeviceptr)dst, (CUdeviceptr)src, bytes, (CUstream)stream));
+    return PRB_OK;
+}
+int prb_ipc_get_handle(void* dptr, unsigned char* handle) {
+    if (!dptr || !handle) return fail(PRB_ERR_INVALID, "NULL argument");
+    if (int e = need_ctx()) return e;
+    static_assert(sizeof(CUipcMemHandle) == PRB_IPC_HANDLE_BYTES, "IPC handle size");
+    CUipcMemHandle h;
+    CU(cuIpcGetMemHandle(&h, (CUdeviceptr)dptr));
+    memcpy(handle, &h, sizeof h);
+    return PRB_OK;
+}
+int prb_ipc_open_handle(const unsigned char* handle, void** dptr) {
+    if (!dptr || !handle) return fail(PRB_ERR_INVALID, "NULL argument");
+    if (int e = need_ctx()) return e;
+    CUipcMemHandle h;
+    memcpy(&h, handle, sizeof h);
+    CUdeviceptr p = 0;
+    CU(cuIpcOpenMemHandle_v2(&p, h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS));
+    *dptr = (void*)p;
+    return PRB_OK;
+}
+int prb_ipc_close_handle(void* dptr) {
+    if (!dptr) return PRB_OK;
+    if (int e = need_ctx()) return e;
+    CU(cuIpcCloseMemHandle((CUdeviceptr)dptr));
     return PRB_OK;
 }
 int prb_host_alloc(void** hptr, size_t bytes) {

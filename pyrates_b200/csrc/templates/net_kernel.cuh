@@ -16,7 +16,7 @@
 // non-allocating loads; the source vector stays L1/L2 resident.
 //
 // Expects from the generated prologue: real, PRB_NS, PRB_NOBS, PRB_SOLVER, PRB_BLOCK, PRB_NRINGS,
-// PRB_WORK_USER (element offset of the solver buffers inside `work`), prb_net_init_heads(),
+// PRB_WORK_USER (element offset of the solver buffers inside `work`), PRB_RANK, PRB_WORLD, prb_net_init_heads(),
 // prb_net_advance_heads(), prb_eval<STAGE>() and PRB_OBS_OFF.
 
 struct PrbNet {
@@ -26,28 +26,99 @@ struct PrbNet {
     const real* __restrict__ consts;
     const int* __restrict__ iconsts;
     const real* __restrict__ tables;
-    real *Y, *YN, *S1, *S2, *S3, *ACC;
+    long long oY, oYN, oS1, oS2, oS3, oACC;     // element offsets of the solver vectors inside `work`
     real dt, hdt, dt6;
     long long t;
     int head[PRB_NRINGS > 0 ? PRB_NRINGS : 1];
-    unsigned long long* bar;
+    unsigned long long* bar;     // [0] local arrivals, [1] release epoch, [2] error flag, [8+q] epoch of rank q
     unsigned long long bar_target;
+    unsigned long long epoch;
+#if PRB_WORLD > 1
+    real* peer_work[PRB_WORLD];
+    real* peer_rings[PRB_WORLD];
+    unsigned long long* peer_sync[PRB_WORLD];
+#endif
     long long gtid, gsize, gwarp, nwarps;
     int lane;
 };
 
-// ---- grid-wide barrier: monotonic counter, one arrival per CTA (host zeroes the counter before launch)
+// ---- shared stores: values other CTAs (and, with PRB_WORLD > 1, other GPUs) will read.  In a multi-GPU run every
+// rank owns a contiguous row shard; the owner writes its elements into the replica of every peer over NVLink
+// (P2P stores on IPC-mapped pointers), so the all-gather of the stage vector is fused into the producing kernel.
+__device__ __forceinline__ void prb_st_work(const PrbNet& C, const long long off, const real v) {
+    C.work[off] = v;
+#if PRB_WORLD > 1
+#pragma unroll
+    for (int p = 0; p < PRB_WORLD; ++p)
+        if (p != PRB_RANK) C.peer_work[p][off] = v;
+#endif
+}
+__device__ __forceinline__ void prb_st_ring(const PrbNet& C, const long long off, const real v) {
+    C.rings[off] = v;
+#if PRB_WORLD > 1
+#pragma unroll
+    for (int p = 0; p < PRB_WORLD; ++p)
+        if (p != PRB_RANK) C.peer_rings[p][off] = v;
+#endif
+}
+
+// ---- barriers.  Single GPU: monotonic counter, one arrival per CTA (host zeroes the words before launch).
+// Multi GPU: CTA 0 additionally exchanges an epoch flag with every peer (release/acquire at system scope) before
+// it releases the local CTAs.  Spins are bounded (~4e9 cycles): on timeout the error word is set and every
+// later barrier falls through, so a lost peer can never hang the GPU.
+#define PRB_SPIN_LIMIT 4000000000LL
+
+template <bool SYS>
+__device__ __forceinline__ unsigned long long prb_ld_acquire(const unsigned long long* p) {
+    unsigned long long v;
+    if (SYS) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    else     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool SYS>
+__device__ __forceinline__ bool prb_spin_until(PrbNet& C, const unsigned long long* p, const unsigned long long target) {
+    const long long t0 = clock64();
+    unsigned int it = 0;
+    while (prb_ld_acquire<SYS>(p) < target) {
+        if ((++it & 1023u) == 0) {
+            if (prb_ld_acquire<false>(C.bar + 2) != 0ULL) return false;
+            if (clock64() - t0 > PRB_SPIN_LIMIT) { atomicExch(C.bar + 2, 1ULL); return false; }
+        }
+    }
+    return true;
+}
+
 __device__ __forceinline__ void prb_grid_barrier(PrbNet& C) {
     __syncthreads();
     if (threadIdx.x == 0) {
         C.bar_target += gridDim.x;
+        C.epoch += 1ULL;
+#if PRB_WORLD > 1
+        __threadfence_system();
+        atomicAdd(C.bar, 1ULL);
+        if (blockIdx.x == 0) {
+            bool ok = prb_spin_until<false>(C, C.bar, C.bar_target);      // all local CTAs arrived (stores fenced)
+            if (ok) {
+#pragma unroll
+                for (int p = 0; p < PRB_WORLD; ++p)
+                    if (p != PRB_RANK)
+                        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(C.peer_sync[p] + 8 + PRB_RANK), "l"(C.epoch) : "memory");
+#pragma unroll
+                for (int q = 0; q < PRB_WORLD; ++q)
+                    if (q != PRB_RANK) ok = ok && prb_spin_until<true>(C, C.bar + 8 + q, C.epoch);
+            }
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(C.bar + 1), "l"(C.epoch) : "memory");
+        } else {
+            prb_spin_until<false>(C, C.bar + 1, C.epoch);
+        }
+        __threadfence_system();
+#else
         __threadfence();
         atomicAdd(C.bar, 1ULL);
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(C.bar) : "memory");
-        } while (v < C.bar_target);
+        prb_spin_until<false>(C, C.bar, C.bar_target);
         __threadfence();
+#endif
     }
     __syncthreads();
 }
@@ -157,27 +228,28 @@ __device__ __forceinline__ float prb_row_dot(const float* __restrict__ w, const 
 // HEUN_REF reproduces the reference's aliased `heun` (y += dt/2*(k2+k2), base_backend.py:763-765).
 template <int STAGE>
 __device__ __forceinline__ void prb_emit_k(const PrbNet& C, const long long e, const real k) {
+    const real y = C.work[C.oY + e];
 #if PRB_SOLVER == PRB_SOLVER_EULER
-    C.YN[e] = C.Y[e] + C.dt * k;
+    prb_st_work(C, C.oYN + e, y + C.dt * k);
 #elif PRB_SOLVER == PRB_SOLVER_HEUN_REF
-    if (STAGE == 0) C.S1[e] = C.Y[e] + C.dt * k;
-    else            C.YN[e] = C.Y[e] + C.hdt * (k + k);
+    if (STAGE == 0) prb_st_work(C, C.oS1 + e, y + C.dt * k);
+    else            prb_st_work(C, C.oYN + e, y + C.hdt * (k + k));
 #elif PRB_SOLVER == PRB_SOLVER_HEUN
-    if (STAGE == 0) { C.ACC[e] = k; C.S1[e] = C.Y[e] + C.dt * k; }
-    else            C.YN[e] = C.Y[e] + C.hdt * (C.ACC[e] + k);
+    if (STAGE == 0) { C.work[C.oACC + e] = k; prb_st_work(C, C.oS1 + e, y + C.dt * k); }
+    else            prb_st_work(C, C.oYN + e, y + C.hdt * (C.work[C.oACC + e] + k));
 #elif PRB_SOLVER == PRB_SOLVER_RK4
-    if (STAGE == 0)      { C.ACC[e] = k;                           C.S1[e] = C.Y[e] + C.hdt * k; }
-    else if (STAGE == 1) { C.ACC[e] = C.ACC[e] + (real)2 * k;      C.S2[e] = C.Y[e] + C.hdt * k; }
-    else if (STAGE == 2) { C.ACC[e] = C.ACC[e] + (real)2 * k;      C.S3[e] = C.Y[e] + C.dt * k; }
-    else                 C.YN[e] = C.Y[e] + C.dt6 * (C.ACC[e] + k);
+    if (STAGE == 0)      { C.work[C.oACC + e] = k;                                   prb_st_work(C, C.oS1 + e, y + C.hdt * k); }
+    else if (STAGE == 1) { C.work[C.oACC + e] = C.work[C.oACC + e] + (real)2 * k;    prb_st_work(C, C.oS2 + e, y + C.hdt * k); }
+    else if (STAGE == 2) { C.work[C.oACC + e] = C.work[C.oACC + e] + (real)2 * k;    prb_st_work(C, C.oS3 + e, y + C.dt * k); }
+    else                 prb_st_work(C, C.oYN + e, y + C.dt6 * (C.work[C.oACC + e] + k));
 #endif
 }
 
 template <int STAGE> __device__ void prb_eval(PrbNet& C);     // generated
 
 template <int STAGE>
-__device__ __forceinline__ void prb_stage(PrbNet& C, const real* yin) {
-    C.yin = yin;
+__device__ __forceinline__ void prb_stage(PrbNet& C, const long long oyin) {
+    C.yin = C.work + oyin;
     prb_eval<STAGE>(C);
     prb_net_advance_heads(C);
     prb_grid_barrier(C);
@@ -192,12 +264,20 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
     C.consts = (const real*)A.consts;
     C.iconsts = A.iconsts;
     C.tables = (const real*)A.tables;
-    real* sol = C.work + (long long)PRB_WORK_USER;
-    C.Y = sol; C.YN = sol + (long long)PRB_NS; C.S1 = sol + 2LL * PRB_NS; C.S2 = sol + 3LL * PRB_NS;
-    C.S3 = sol + 4LL * PRB_NS; C.ACC = sol + 5LL * PRB_NS;
+    C.oY = (long long)PRB_WORK_USER; C.oYN = C.oY + PRB_NS; C.oS1 = C.oY + 2LL * PRB_NS; C.oS2 = C.oY + 3LL * PRB_NS;
+    C.oS3 = C.oY + 4LL * PRB_NS; C.oACC = C.oY + 5LL * PRB_NS;
     C.dt = (real)A.dt; C.hdt = (real)(A.dt / 2); C.dt6 = (real)(A.dt / 6);
     C.bar = (unsigned long long*)A.sync;
     C.bar_target = 0;
+    C.epoch = 0;
+#if PRB_WORLD > 1
+#pragma unroll
+    for (int p = 0; p < PRB_WORLD; ++p) {
+        C.peer_work[p] = (real*)A.peers[p];
+        C.peer_rings[p] = (real*)A.peers[PRB_WORLD + p];
+        C.peer_sync[p] = (unsigned long long*)A.peers[2 * PRB_WORLD + p];
+    }
+#endif
     C.gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     C.gsize = (long long)gridDim.x * blockDim.x;
     C.lane = threadIdx.x & 31;
@@ -206,7 +286,7 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
     prb_net_init_heads(C, A.eval0);
 
     real* extY = (real*)A.y;
-    for (long long e = C.gtid; e < PRB_NS; e += C.gsize) C.Y[e] = extY[e];
+    for (long long e = C.gtid; e < PRB_NS; e += C.gsize) C.work[C.oY + e] = extY[e];   // every rank holds a full replica
     prb_grid_barrier(C);
 
     real* out = (real*)A.out;
@@ -218,23 +298,23 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
     for (long long i = 0; i < A.n_steps; ++i, ++C.t) {
         if (until_store == 0) {
             for (long long o = C.gtid; o < PRB_NOBS; o += C.gsize)
-                out[sample * (long long)PRB_NOBS + o] = C.Y[PRB_OBS_INDEX(o)];
+                out[sample * (long long)PRB_NOBS + o] = C.work[C.oY + PRB_OBS_INDEX(o)];
             ++sample;
             until_store = store_step;
         }
         --until_store;
 #if PRB_SOLVER == PRB_SOLVER_EULER
-        prb_stage<0>(C, C.Y);
+        prb_stage<0>(C, C.oY);
 #elif PRB_SOLVER == PRB_SOLVER_HEUN_REF || PRB_SOLVER == PRB_SOLVER_HEUN
-        prb_stage<0>(C, C.Y);
-        prb_stage<1>(C, C.S1);
+        prb_stage<0>(C, C.oY);
+        prb_stage<1>(C, C.oS1);
 #elif PRB_SOLVER == PRB_SOLVER_RK4
-        prb_stage<0>(C, C.Y);
-        prb_stage<1>(C, C.S1);
-        prb_stage<2>(C, C.S2);
-        prb_stage<3>(C, C.S3);
+        prb_stage<0>(C, C.oY);
+        prb_stage<1>(C, C.oS1);
+        prb_stage<2>(C, C.oS2);
+        prb_stage<3>(C, C.oS3);
 #endif
-        real* tmp = C.Y; C.Y = C.YN; C.YN = tmp;
+        const long long tmp = C.oY; C.oY = C.oYN; C.oYN = tmp;
     }
-    for (long long e = C.gtid; e < PRB_NS; e += C.gsize) extY[e] = C.Y[e];
+    for (long long e = C.gtid; e < PRB_NS; e += C.gsize) extY[e] = C.work[C.oY + e];
 }

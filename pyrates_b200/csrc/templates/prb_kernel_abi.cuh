@@ -21,9 +21,12 @@ struct prb_kernel_args {
     const int*  iconsts;
     void*       work;
     unsigned int* sync;
+    void* const* peers;
+    int         rank;
+    int         world;
 };
 static_assert(sizeof(long long) == 8 && sizeof(int) == 4 && sizeof(void*) == 8, "LP64 expected");
-static_assert(sizeof(prb_kernel_args) == 8 * 8 + 10 * 8, "prb_kernel_args layout drifted from include/prb.h");
+static_assert(sizeof(prb_kernel_args) == 8 * 8 + 10 * 8 + 16, "prb_kernel_args layout drifted from include/prb.h");
 
 #define PRB_SOLVER_EULER    0
 #define PRB_SOLVER_HEUN_REF 1

@@ -38,11 +38,18 @@ class NetKernel:
 
 
 class _Emitter:
-    def __init__(self, ir: NetIR, f32: bool, obs_off: int):
+    def __init__(self, ir: NetIR, f32: bool, rank: int = 0, world: int = 1):
         self.ir, self.g, self.f32 = ir, ir.graph, f32
+        self.rank, self.world = rank, world
         self.roles: Dict[int, frozenset] = {}
         self.red_work: Dict[int, MemArray] = {}
         self.ring_index = {name: k for k, name in enumerate(a.name for a in ir.arrays.values() if a.space == "ring")}
+
+    def bounds(self, n: int) -> Tuple[int, int]:
+        """Rows [lo, hi) of an index space of length n owned by this rank (== sweep.shard_bounds)."""
+        base, rem = divmod(int(n), self.world)
+        lo = self.rank * base + min(self.rank, rem)
+        return lo, lo + base + (1 if self.rank < rem else 0)
 
     # ---- role analysis: which loop indices a node depends on
     def role(self, i: int) -> frozenset:
@@ -121,7 +128,7 @@ class _Emitter:
             return self._load(arr, f"{pl[1]}LL")
         if op == "ldm":
             arr = ir.arrays[pl[0]]
-            return self._load(arr, f"i * {pl[2]}LL + j")
+            return self._load(arr, f"(i - {self.bounds(arr.shape[0])[0]}LL) * {pl[2]}LL + j")
         if op == "gather":
             arr, iarr = ir.arrays[pl[0]], ir.arrays[pl[2]]
             return self._load(arr, f"{pl[1]}LL + (long long){self._load(iarr, pl[3])}")
@@ -197,22 +204,24 @@ class _Emitter:
             return f"prb_emit_k<STAGE>(C, {t[1]}LL + i, {val});"
         if t[0] == "work":
             arr = self.ir.arrays[t[1]]
-            return f"C.work[{arr.offset}LL + i] = {val};"
+            return f"prb_st_work(C, {arr.offset}LL + i, {val});"
         if t[0] == "work_at":
             arr = self.ir.arrays[t[1]]
-            return f"C.work[{arr.offset + t[2]}LL] = {val};"
+            return f"prb_st_work(C, {arr.offset + t[2]}LL, {val});"
         if t[0] == "scatter":
             arr, iarr = self.ir.arrays[t[1]], self.ir.arrays[t[2]]
-            return f"C.work[{arr.offset}LL + (long long){self._load(iarr, 'i')}] = {val};"
+            return f"prb_st_work(C, {arr.offset}LL + (long long){self._load(iarr, 'i')}, {val});"
         if t[0] == "ring":
             arr = self.ir.arrays[t[1]]
             rows, L = arr.shape
             k = self.ring_index[t[1]]
-            return f"C.rings[{arr.offset}LL + prb_ring_pos(C.head[{k}], {t[2] - arr.rolls}, {L}) * {rows}LL + i] = {val};"
+            return (f"prb_st_ring(C, {arr.offset}LL + prb_ring_pos(C.head[{k}], {t[2] - arr.rolls}, {L}) * {rows}LL + i, "
+                    f"{val});")
         raise NotImplementedError(t[0])
 
 
-def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequence[int], block: int = 512) -> NetKernel:
+def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequence[int], block: int = 512,
+                    rank: int = 0, world: int = 1) -> NetKernel:
     if solver not in SOLVER_IDS:
         raise ValueError(f"unknown solver `{solver}`")
     f32 = precision == "float32"
@@ -220,7 +229,18 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     ns = ir.n_state
     # reduction results get a work array so that consumers outside the fused row task can read them
     work_size = ir.work_size
-    em = _Emitter(ir, f32, 0)
+    em = _Emitter(ir, f32, rank, world)
+    # multi-GPU: 2-d constants (connectivity) are row-sharded -> re-pack the constant space with shard sizes
+    const_size = ir.const_size
+    if world > 1:
+        const_size = 0
+        for a in ir.arrays.values():
+            if a.space == "const":
+                rows = a.shape[0]
+                lo, hi = em.bounds(rows) if len(a.shape) == 2 else (0, rows)
+                size = (hi - lo) * (a.shape[1] if len(a.shape) == 2 else 1) if a.shape else 1
+                a.offset = const_size
+                const_size += ((max(size, 1) + 31) // 32) * 32
     for red in ir.reductions:
         if red.kind == "row":
             arr = MemArray(f"__red{red.id}", "work", (red.n,), work_size, np.zeros(red.n))
@@ -263,14 +283,15 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
             sts = [s for s in stores_p if s.n == n]
             if reds:
                 cur = (p, n, True)
-                body.append(f"    for (long long i = C.gwarp; i < {n}LL; i += C.nwarps) {{      // warp per row, n = {n}")
+                lo, hi = em.bounds(n)
+                body.append(f"    for (long long i = {lo}LL + C.gwarp; i < {hi}LL; i += C.nwarps) {{      // warp per row, n = {n}")
                 emitted = set()
                 for r in reds:
                     if r.simple is not None:
                         W, X, xoff = r.simple
                         warr, xarr = ir.arrays[W], ir.arrays[X]
                         xptr = f"{em._ptr(xarr)} + {('%dLL' % (xarr.offset + xoff)) if xarr.space != 'y' else ('%dLL' % xoff)}"
-                        body.append(f"        const real red{r.id} = prb_row_dot(C.consts + {warr.offset}LL + i * {r.m}LL, "
+                        body.append(f"        const real red{r.id} = prb_row_dot(C.consts + {warr.offset}LL + (i - {lo}LL) * {r.m}LL, "
                                     f"{xptr}, {r.m}, C.lane);")
                     else:
                         nodes = em.order([r.node])
@@ -292,7 +313,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                     need_store = any(_uses_red(g, em, s.node, r.id) and (s.phase, s.n) != (p, n) for s in ir.stores) or \
                         any(_uses_red(g, em, q.node, r.id) for q in ir.reductions)
                     if need_store:
-                        body.append(f"        if (C.lane == 0) C.work[{em.red_work[r.id].offset}LL + i] = red{r.id};")
+                        body.append(f"        if (C.lane == 0) prb_st_work(C, {em.red_work[r.id].offset}LL + i, red{r.id});")
                 roots = [s.node for s in sts]
                 nodes = em.order(roots)
                 body.extend(em.emit_nodes(nodes, cur, emitted, "        "))
@@ -307,7 +328,8 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 roots = [s.node for s in sts]
                 nodes = em.order(roots)
                 emitted = set()
-                body.append(f"    for (long long i = C.gtid; i < {n}LL; i += C.gsize) {{        // thread per element, n = {n}")
+                lo, hi = em.bounds(n)
+                body.append(f"    for (long long i = {lo}LL + C.gtid; i < {hi}LL; i += C.gsize) {{        // thread per element, n = {n}")
                 body.extend(em.emit_nodes(nodes, cur, emitted, "        "))
                 for s in sts:
                     body.append("        " + em.store_stmt(s, cur, "STAGE"))
@@ -326,6 +348,8 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     src.append(f"#define PRB_SOLVER {SOLVER_IDS[solver]}")
     src.append(f"#define PRB_BLOCK {block}")
     src.append(f"#define PRB_WORK_USER {work_size}LL")
+    src.append(f"#define PRB_RANK {rank}")
+    src.append(f"#define PRB_WORLD {world}")
     src.append("#define PRB_OBS_INDEX(o) (o)" if all_state else f"#define PRB_OBS_INDEX(o) ((long long)A.iconsts[{obs_off}LL + (o)])")
     src.append("struct PrbNet;")
     src.append("__device__ __forceinline__ void prb_net_init_heads(PrbNet& C, long long eval0);")
@@ -352,7 +376,10 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 v = np.asarray(a.init)
                 if space == "ring":
                     v = v.T                        # device layout [L][rows]: a delay column is contiguous
-                buf[a.offset:a.offset + a.size] = v.reshape(-1).astype(dtype)
+                if space == "const" and world > 1 and v.ndim == 2:
+                    lo, hi = em.bounds(v.shape[0])
+                    v = v[lo:hi]                   # this rank's row shard of the connectivity
+                buf[a.offset:a.offset + v.size] = v.reshape(-1).astype(dtype)
         return buf
 
     iconst = pack("iconst", iconst_size, np.int32)
@@ -360,7 +387,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
         iconst[obs_off:obs_off + obs.size] = obs
     evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4}[solver]
     return NetKernel("\n".join(src) + "\n", ns, int(obs.size), work_size + 6 * ns, work_size,
-                     pack("work", work_size, real), pack("const", ir.const_size, real), iconst,
+                     pack("work", work_size, real), pack("const", const_size, real), iconst,
                      pack("ring", ir.ring_size, real), pack("table", ir.table_size, real), block, solver, precision,
                      evals, n_phases)
 

@@ -23,7 +23,7 @@ __all__ = ["NetworkModel", "NetworkSession", "build_check", "smoke_check"]
 
 class NetworkModel:
     def __init__(self, prog: Program, *, solver: str = "euler", observers: Optional[Sequence[int]] = None,
-                 block: int = 512, fmad: bool = True, blocks_per_sm: int = 1):
+                 block: int = 512, fmad: bool = True, blocks_per_sm: int = 1, rank: int = 0, world: int = 1):
         if solver not in FIXED_STEP_SOLVERS:
             raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
                                       f"Supported solvers: {list(FIXED_STEP_SOLVERS)}.")
@@ -33,8 +33,9 @@ class NetworkModel:
         self.real = prog.real_dtype
         self.ir: NetIR = netcompile(prog)
         self.observers = list(range(prog.n_state)) if observers is None else [int(o) for o in observers]
+        self.rank, self.world = int(rank), int(world)
         self.kernel: NetKernel = emit_net_kernel(self.ir, solver=solver, precision=self.precision,
-                                                 observers=self.observers, block=block)
+                                                 observers=self.observers, block=block, rank=self.rank, world=self.world)
         self.fmad = fmad
         self.blocks_per_sm = blocks_per_sm
         self._module: Optional[rt.Module] = None
@@ -81,10 +82,37 @@ class NetworkSession:
         self.d_tables = rt.DeviceBuffer.from_host(k.table_init.astype(real))
         self.d_work = rt.DeviceBuffer(max(k.work_elems, 1) * item)
         self.d_rings = rt.DeviceBuffer(max(k.ring_init.size, 1) * item)
-        self.d_sync = rt.DeviceBuffer(64)
+        self.d_sync = rt.DeviceBuffer(8 * (8 + max(model.world, 8)))
         self.sm_count = rt.device_info()["sm_count"]
         self.steps_done = 0
         self.samples_done = 0
+        self.d_peers = None
+        self._peer_ptrs = []
+        if model.world > 1:
+            self._connect_peers()
+
+    def _connect_peers(self):
+        """Exchange CUDA IPC handles of (work, rings, sync) with the other ranks (one process per GPU) and build the
+        device table kernels use for NVLink peer stores.  torch.distributed is only the control plane here."""
+        import torch.distributed as dist
+        m = self.m
+        if not dist.is_initialized() or dist.get_world_size() != m.world or dist.get_rank() != m.rank:
+            raise rt.CudaBackendError("multi-GPU network runs need an initialised torch.distributed group matching rank/world")
+        mine = [rt.ipc_handle(b) for b in (self.d_work, self.d_rings, self.d_sync)]
+        everyone = [None] * m.world
+        dist.all_gather_object(everyone, mine)
+        table = np.zeros(3 * m.world, dtype=np.uint64)
+        own = (self.d_work.ptr, self.d_rings.ptr, self.d_sync.ptr)
+        for p in range(m.world):
+            for k in range(3):
+                if p == m.rank:
+                    ptr = own[k]
+                else:
+                    ptr = rt.ipc_open(everyone[p][k])
+                    self._peer_ptrs.append(ptr)
+                table[k * m.world + p] = ptr
+        self.d_peers = rt.DeviceBuffer.from_host(table)
+        dist.barrier()
 
     def reset(self, y0: Optional[np.ndarray] = None):
         k, real = self.m.kernel, self.m.real
@@ -107,6 +135,12 @@ class NetworkSession:
         if self.samples_done + new_samples > self.n_samples:
             raise ValueError("launch would overflow the recording buffer")
         self.d_sync.zero(self.stream)
+        if self.m.world > 1:
+            import torch.distributed as dist
+            if self.stream is not None:
+                self.stream.synchronize()
+            rt.synchronize()
+            dist.barrier()                      # every rank's barrier words are zero before any kernel signals
         a = rt.KernelArgs()
         a.n_steps, a.store_step, a.step0 = int(n_steps), int(store_step), int(self.steps_done)
         a.t0, a.eval0 = self.m.t0, int(self.steps_done) * k.evals_per_step
@@ -116,11 +150,22 @@ class NetworkSession:
         a.rings, a.tables = self.d_rings.ptr, self.d_tables.ptr
         a.consts, a.iconsts = self.d_consts.ptr, self.d_iconsts.ptr
         a.work, a.sync = self.d_work.ptr, self.d_sync.ptr
+        a.peers = self.d_peers.ptr if self.d_peers is not None else None
+        a.rank, a.world = self.m.rank, self.m.world
         self.m.module.run(k.kernel_name, a, block=k.block, grid=self.sm_count * self.m.blocks_per_sm,
                           cooperative=True, stream=self.stream)
         self.steps_done += int(n_steps)
         self.samples_done += new_samples
         return new_samples
+
+    def check(self):
+        """Raise if a barrier timed out inside the kernel (lost peer / launch failure on another rank)."""
+        words = np.zeros(8, dtype=np.uint64)
+        self.d_sync.download(words, self.stream)
+        if self.stream is not None:
+            self.stream.synchronize()
+        if words[2] != 0:
+            raise rt.CudaBackendError("network kernel barrier timed out (a peer rank did not arrive)")
 
     def download(self) -> np.ndarray:
         out = np.empty((self.n_samples, self.m.kernel.n_obs), dtype=self.m.real)
@@ -128,6 +173,7 @@ class NetworkSession:
             self.d_out.download(out, self.stream)
         if self.stream is not None:
             self.stream.synchronize()
+        self.check()
         return out
 
     def download_state(self) -> np.ndarray:
@@ -138,7 +184,15 @@ class NetworkSession:
         return y
 
     def free(self):
-        for n in ("d_y", "d_out", "d_consts", "d_iconsts", "d_tables", "d_work", "d_rings", "d_sync"):
+        if self.m.world > 1:
+            import torch.distributed as dist
+            rt.synchronize()
+            for p in self._peer_ptrs:
+                rt.ipc_close(p)
+            self._peer_ptrs = []
+            if dist.is_initialized():
+                dist.barrier()                  # nobody frees memory a peer may still have mapped
+        for n in ("d_y", "d_out", "d_consts", "d_iconsts", "d_tables", "d_work", "d_rings", "d_sync", "d_peers"):
             b = getattr(self, n, None)
             if b is not None:
                 b.free()

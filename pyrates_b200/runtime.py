@@ -32,7 +32,8 @@ class KernelArgs(C.Structure):
                 ("eval0", C.c_int64), ("n_inst", C.c_int64), ("sample0", C.c_int64), ("dt", C.c_double),
                 ("y", C.c_void_p), ("out", C.c_void_p), ("params", C.c_void_p), ("slots", C.c_void_p),
                 ("rings", C.c_void_p), ("tables", C.c_void_p), ("consts", C.c_void_p), ("iconsts", C.c_void_p),
-                ("work", C.c_void_p), ("sync", C.c_void_p)]
+                ("work", C.c_void_p), ("sync", C.c_void_p), ("peers", C.c_void_p), ("rank", C.c_int32),
+                ("world", C.c_int32)]
 
 
 class RunDesc(C.Structure):
@@ -74,6 +75,9 @@ SYMBOLS = {
     "prb_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "prb_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "prb_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "prb_ipc_get_handle": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "prb_ipc_open_handle": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "prb_ipc_close_handle": (C.c_int, [C.c_void_p]),
     "prb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "prb_host_free": (C.c_int, [C.c_void_p]),
     "prb_stream_create": (C.c_int, [C.POINTER(C.c_void_p)]),
@@ -105,7 +109,7 @@ def lib():
                 for name, (res, args) in SYMBOLS.items():
                     fn = getattr(l, name)
                     fn.restype, fn.argtypes = res, args
-                if l.prb_abi_version() != 1:
+                if l.prb_abi_version() != 2:
                     raise CudaBackendError("libprb ABI version mismatch; rebuild the library")
                 _lib = l
     return _lib
@@ -190,6 +194,22 @@ class DeviceBuffer:
             self.free()
         except Exception:
             pass
+
+
+def ipc_handle(buf: "DeviceBuffer") -> bytes:
+    h = C.create_string_buffer(64)
+    _check(lib().prb_ipc_get_handle(buf.ptr, h))
+    return h.raw
+
+
+def ipc_open(handle: bytes) -> int:
+    p = C.c_void_p()
+    _check(lib().prb_ipc_open_handle(handle, C.byref(p)))
+    return p.value
+
+
+def ipc_close(ptr: int):
+    _check(lib().prb_ipc_close_handle(ptr))
 
 
 class PinnedBuffer:

@@ -25,9 +25,9 @@ def test_header_symbols_all_exported():
 
 
 def test_struct_layout_matches_header():
-    assert ctypes.sizeof(rt.KernelArgs) == 8 * 8 + 10 * 8
+    assert ctypes.sizeof(rt.KernelArgs) == 8 * 8 + 10 * 8 + 16
     assert ctypes.sizeof(rt.RunDesc) == 6 * 4 + 8 + ctypes.sizeof(rt.KernelArgs)
-    assert rt.lib().prb_abi_version() == 1
+    assert rt.lib().prb_abi_version() == 2
 
 
 def test_nvrtc_compiles_without_gpu_and_reports_errors():
