@@ -7,7 +7,7 @@ from the reference at N=8): the generated statements do not depend on N except t
 shapes, so every dimension equal to the fixture's N is mapped to the requested N and the arrays are re-drawn from
 the seeded distributions SURVEY.md §8d prescribes.  (The reference itself is not available on the GPU box.)
 
-    python bench_configs.py --config c3 --n 8192 --solver euler --steps 200
+    python bench_configs.py --config c3 --size 8192 --solver euler --steps 200
 """
 from __future__ import annotations
 
@@ -115,7 +115,7 @@ CONFIGS = {"c3": (make_c3, 1, 1), "c4": (make_c4, 12, 2), "c5": (make_c5, 1, 1)}
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", required=True, choices=sorted(CONFIGS))
-    ap.add_argument("--n", type=int, required=True)
+    ap.add_argument("--size", dest="n", type=int, required=True)
     ap.add_argument("--solver", default="euler")
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--cpu-steps", type=int, default=20)
