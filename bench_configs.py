@@ -164,7 +164,8 @@ def main():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         hbm = float(json.load(open(p))["hbm_gbs"])
-    achieved = wbytes * evals * a.steps / (ms * 1e-3) / 1e9
+    wbytes_rank = wbytes / world
+    achieved = wbytes_rank * evals * a.steps / (ms * 1e-3) / 1e9
     if rank != 0:
         s.free()
         dist.destroy_process_group()

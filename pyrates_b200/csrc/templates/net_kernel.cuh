@@ -63,8 +63,8 @@ __device__ __forceinline__ void prb_st_ring(const PrbNet& C, const long long off
 }
 
 // ---- barriers.  Single GPU: monotonic counter, one arrival per CTA (host zeroes the words before launch).
-// Multi GPU: CTA 0 additionally exchanges an epoch flag with every peer (release/acquire at system scope) before
-// it releases the local CTAs.  Spins are bounded (~4e9 cycles): on timeout the error word is set and every
+// Multi GPU: every CTA increments the arrival counter of every rank (system-scope atomics over NVLink) and waits
+// for world x gridDim arrivals on its own counter.  Spins are bounded (~4e9 cycles): on timeout the error word is set and every
 // later barrier falls through, so a lost peer can never hang the GPU.
 #define PRB_SPIN_LIMIT 4000000000LL
 
@@ -95,23 +95,13 @@ __device__ __forceinline__ void prb_grid_barrier(PrbNet& C) {
         C.bar_target += gridDim.x;
         C.epoch += 1ULL;
 #if PRB_WORLD > 1
+        // one-hop multi-GPU barrier: after making this CTA's (remote) stores visible system-wide, announce the arrival
+        // on EVERY rank's counter (NVLink atomics on IPC-mapped peers), then wait for world x gridDim arrivals locally.
         __threadfence_system();
-        atomicAdd(C.bar, 1ULL);
-        if (blockIdx.x == 0) {
-            bool ok = prb_spin_until<false>(C, C.bar, C.bar_target);      // all local CTAs arrived (stores fenced)
-            if (ok) {
 #pragma unroll
-                for (int p = 0; p < PRB_WORLD; ++p)
-                    if (p != PRB_RANK)
-                        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(C.peer_sync[p] + 8 + PRB_RANK), "l"(C.epoch) : "memory");
-#pragma unroll
-                for (int q = 0; q < PRB_WORLD; ++q)
-                    if (q != PRB_RANK) ok = ok && prb_spin_until<true>(C, C.bar + 8 + q, C.epoch);
-            }
-            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(C.bar + 1), "l"(C.epoch) : "memory");
-        } else {
-            prb_spin_until<false>(C, C.bar + 1, C.epoch);
-        }
+        for (int p = 0; p < PRB_WORLD; ++p)
+            atomicAdd_system(C.peer_sync[p], 1ULL);
+        prb_spin_until<true>(C, C.bar, C.bar_target * (unsigned long long)PRB_WORLD);
         __threadfence_system();
 #else
         __threadfence();
