@@ -1,0 +1,53 @@
+"""Network-model kernels build for sm_100a without a GPU (NVRTC): one per coupling family, plus the multi-GPU
+variants (row shards, peer stores, cross-GPU barrier) for world sizes 2 and 3."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_path
+from pyrates_b200 import runtime as rt
+from pyrates_b200.netcompile import netcompile
+from pyrates_b200.netengine import NetworkModel
+from pyrates_b200.program import Program
+from pyrates_b200.scalarize import UnsupportedModelError
+
+CASES = [("wc_n128", "rk4"), ("wc_n128_f32", "euler"), ("qsfa_both_n96", "heun"), ("kuramoto_n128", "heun_true"),
+         ("kuramoto_scalar_n128", "euler"), ("jrc_grid_b1024", "rk4"), ("jrc_2delay", "heun"), ("net13", "euler")]
+
+
+@pytest.mark.parametrize("name,solver", CASES)
+def test_network_kernel_compiles(name, solver):
+    os.environ["PRB_CACHE_DIR"] = "off"
+    m = NetworkModel(Program.load(golden_path(name)), solver=solver)
+    assert "prb_integrate_net" in m.kernel.source and "prb_eval" in m.kernel.source
+    mod = rt.compile_module(m.kernel.source, f"{name}.cu", verbose_ptxas=True)
+    assert mod.cubin[:4] == b"\x7fELF"
+
+
+def test_phase_structure():
+    """State-sourced dense coupling needs no intra-evaluation barrier; gather edges over a computed vector need one;
+    read-before-write persistent buffers (WAR) force an extra phase."""
+    assert netcompile(Program.load(golden_path("wc_n128"))).n_phases == 1
+    assert netcompile(Program.load(golden_path("kuramoto_n128"))).n_phases == 1
+    assert netcompile(Program.load(golden_path("jrc_grid_b16"))).n_phases == 2
+    assert netcompile(Program.load(golden_path("jrc_2delay"))).n_phases == 3
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_gpu_variants_compile_and_shard_constants(world):
+    os.environ["PRB_CACHE_DIR"] = "off"
+    prog = Program.load(golden_path("qsfa_both_n96"))
+    sizes = []
+    for rank in range(world):
+        m = NetworkModel(prog, solver="rk4", rank=rank, world=world)
+        assert f"#define PRB_WORLD {world}" in m.kernel.source and "atomicAdd_system" in m.kernel.source
+        rt.compile_module(m.kernel.source, f"mg{rank}.cu")
+        sizes.append(m.kernel.const_init.size)
+    full = NetworkModel(prog, solver="rk4").kernel.const_init.size
+    assert max(sizes) < 0.6 * full if world == 2 else max(sizes) < 0.45 * full      # W rows are sharded
+
+
+def test_legacy_ring_gather_is_rejected_by_network_model():
+    with pytest.raises(UnsupportedModelError):
+        netcompile(Program.load(golden_path("net10")))
