@@ -214,6 +214,41 @@ __device__ __forceinline__ float prb_row_dot(const float* __restrict__ w, const 
     return prb_warp_sum((a0 + a1) + (a2 + a3));
 }
 
+// two right-hand sides over ONE pass of the row (separable pair-space couplings: W.sin(theta) and W.cos(theta))
+__device__ __forceinline__ void prb_row_dot2(const double* __restrict__ w, const double* x, const double* z, int m, int lane,
+                                             double& rx, double& rz) {
+    double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+    if ((m & 1) == 0 && ((((unsigned long long)w) | ((unsigned long long)x) | ((unsigned long long)z)) & 15ULL) == 0) {
+        const double2* w2 = (const double2*)w;
+        const double2* x2 = (const double2*)x;
+        const double2* z2 = (const double2*)z;
+        const int m2 = m >> 1;
+        int j = lane;
+        for (; j + 32 < m2; j += 64) {
+            const double2 wa = prb_ld_stream(w2 + j), wb = prb_ld_stream(w2 + j + 32);
+            const double2 xa = x2[j], xb = x2[j + 32], za = z2[j], zb = z2[j + 32];
+            a0 = fma(wa.x, xa.x, a0); a0 = fma(wa.y, xa.y, a0); b0 = fma(wa.x, za.x, b0); b0 = fma(wa.y, za.y, b0);
+            a1 = fma(wb.x, xb.x, a1); a1 = fma(wb.y, xb.y, a1); b1 = fma(wb.x, zb.x, b1); b1 = fma(wb.y, zb.y, b1);
+        }
+        for (; j < m2; j += 32) {
+            const double2 wa = prb_ld_stream(w2 + j);
+            const double2 xa = x2[j], za = z2[j];
+            a0 = fma(wa.x, xa.x, a0); a0 = fma(wa.y, xa.y, a0); b0 = fma(wa.x, za.x, b0); b0 = fma(wa.y, za.y, b0);
+        }
+    } else {
+        for (int j = lane; j < m; j += 32) { const double wv = __ldg(w + j); a0 = fma(wv, x[j], a0); b0 = fma(wv, z[j], b0); }
+    }
+    rx = prb_warp_sum(a0 + a1);
+    rz = prb_warp_sum(b0 + b1);
+}
+__device__ __forceinline__ void prb_row_dot2(const float* __restrict__ w, const float* x, const float* z, int m, int lane,
+                                             float& rx, float& rz) {
+    float a0 = 0, b0 = 0;
+    for (int j = lane; j < m; j += 32) { const float wv = __ldg(w + j); a0 = fmaf(wv, x[j], a0); b0 = fmaf(wv, z[j], b0); }
+    rx = prb_warp_sum(a0);
+    rz = prb_warp_sum(b0);
+}
+
 // ---- solver stage logic: what happens to the derivative k of state element e in stage STAGE.
 // HEUN_REF reproduces the reference's aliased `heun` (y += dt/2*(k2+k2), base_backend.py:763-765).
 template <int STAGE>

@@ -286,13 +286,31 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 lo, hi = em.bounds(n)
                 body.append(f"    for (long long i = {lo}LL + C.gwarp; i < {hi}LL; i += C.nwarps) {{      // warp per row, n = {n}")
                 emitted = set()
+                def xptr_of(r):
+                    xarr = ir.arrays[r.simple[1]]
+                    off = r.simple[2] + (xarr.offset if xarr.space != "y" else 0)
+                    return f"{em._ptr(xarr)} + {off}LL"
+                fused_done: Set[int] = set()
                 for r in reds:
+                    if r.id in fused_done:
+                        continue
                     if r.simple is not None:
-                        W, X, xoff = r.simple
-                        warr, xarr = ir.arrays[W], ir.arrays[X]
-                        xptr = f"{em._ptr(xarr)} + {('%dLL' % (xarr.offset + xoff)) if xarr.space != 'y' else ('%dLL' % xoff)}"
-                        body.append(f"        const real red{r.id} = prb_row_dot(C.consts + {warr.offset}LL + (i - {lo}LL) * {r.m}LL, "
-                                    f"{xptr}, {r.m}, C.lane);")
+                        warr = ir.arrays[r.simple[0]]
+                        wptr = f"C.consts + {warr.offset}LL + (i - {lo}LL) * {r.m}LL"
+                        mate = next((q for q in reds if q.id != r.id and q.id not in fused_done and q.simple is not None
+                                     and q.simple[0] == r.simple[0] and q.m == r.m), None)
+                        if mate is not None:        # same W: both dot products share one pass over the row
+                            fused_done.add(mate.id)
+                            body.append(f"        real red{r.id}, red{mate.id};")
+                            body.append(f"        prb_row_dot2({wptr}, {xptr_of(r)}, {xptr_of(mate)}, {r.m}, C.lane, red{r.id}, red{mate.id});")
+                        else:
+                            body.append(f"        const real red{r.id} = prb_row_dot({wptr}, {xptr_of(r)}, {r.m}, C.lane);")
+                        for q in ([r] if mate is None else [r, mate]):
+                            need = any(_uses_red(g, em, s.node, q.id) and (s.phase, s.n) != (p, n) for s in ir.stores) or \
+                                any(_uses_red(g, em, x.node, q.id) for x in ir.reductions)
+                            if need:
+                                body.append(f"        if (C.lane == 0) prb_st_work(C, {em.red_work[q.id].offset}LL + i, red{q.id});")
+                        continue
                     else:
                         nodes = em.order([r.node])
                         body.extend(em.emit_nodes(nodes, cur, emitted, "        ", only_roles=frozenset("i")))

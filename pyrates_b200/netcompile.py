@@ -96,8 +96,10 @@ class _V:
 
 
 class _NetInterp:
-    def __init__(self, prog: Program):
+    def __init__(self, prog: Program, separable: bool = True):
         self.p = prog
+        self.separable = separable
+        self._role_memo: Dict[int, frozenset] = {}
         self.g = Graph(prog.real_dtype)
         self.arrays: Dict[str, MemArray] = {}
         self.env: Dict[str, object] = {}
@@ -419,6 +421,10 @@ class _NetInterp:
             if w.kind != PAIR or c.kind != PAIR:
                 raise UnsupportedModelError("wsum expects 2-d operands")
             nrow, ncol = max(w.n, c.n), max(w.m, c.m)
+            if self.separable and g.ops[w.sym.id] == "ldm" and (w.n, w.m) == (nrow, ncol):
+                terms = self._separate(c.sym.id)
+                if terms is not None and 0 < len(terms) <= 4:
+                    return self._wsum_separated(w, terms, nrow, ncol)
             return self._reduce_rows(g.binop("mul", w.sym, c.sym), nrow, ncol, None)
         if fname in ("sum", "mean"):
             v = self.as_val(args[0])
@@ -441,6 +447,91 @@ class _NetInterp:
         if fname in ("interp", "interp_rows"):
             raise UnsupportedModelError("interpolated (adaptive-step) inputs are not supported; use a fixed-step solver")
         raise UnsupportedModelError(f"function `{fname}` is not supported by the CUDA network model")
+
+    # ------------------------------------------------------------------ separable pair expressions
+    def _roles(self, i: int, memo=None) -> frozenset:
+        g = self.g
+        memo = self._role_memo
+        r = memo.get(i)
+        if r is None:
+            op, pl = g.ops[i], g.payload[i]
+            if op in ("ld", "ldring"):
+                r = frozenset(pl[2])
+            elif op == "gather":
+                r = frozenset(pl[3])
+            elif op == "ldm":
+                r = frozenset("ij")
+            elif op == "red":
+                r = frozenset("i") if pl[1] == "i" else frozenset()
+            elif op == "table":
+                r = frozenset("i") if pl[2] == "i" else frozenset()
+            else:
+                r = frozenset()
+                for a in g.args[i]:
+                    r = r | self._roles(a)
+            memo[i] = r
+        return r
+
+    def _separate(self, i: int):
+        """Try to write pair expression i as sum_k f_k(i) * g_k(j); returns [(f_k | None, g_k | None)] or None.
+        Rules: linearity, products, and the angle-addition / exponential identities
+        sin(u+v) = sin u cos v + cos u sin v,  cos(u+v) = cos u cos v - sin u sin v,  exp(u+v) = exp u exp v,
+        which turn e.g. the Kuramoto coupling W_ij sin(theta_j - theta_i) into two GEMVs over one pass of W."""
+        g = self.g
+        role = self._roles(i)
+        if "j" not in role:
+            return [(Sym(g, i), None)]
+        if "i" not in role:
+            return [(None, Sym(g, i))]
+        op, a = g.ops[i], g.args[i]
+        neg = lambda ts: [(g.unop("neg", f), gj) if f is not None else (None, g.unop("neg", gj)) for f, gj in ts]
+        if op in ("add", "sub"):
+            l, r = self._separate(a[0]), self._separate(a[1])
+            if l is None or r is None:
+                return None
+            return l + (neg(r) if op == "sub" else r)
+        if op == "neg":
+            t = self._separate(a[0])
+            return None if t is None else neg(t)
+        if op == "mul":
+            l, r = self._separate(a[0]), self._separate(a[1])
+            if l is None or r is None or len(l) * len(r) > 4:
+                return None
+            mul = lambda x, y: y if x is None else (x if y is None else g.binop("mul", x, y))
+            return [(mul(f1, f2), mul(g1, g2)) for f1, g1 in l for f2, g2 in r]
+        if op in ("sin", "cos", "exp"):
+            t = self._separate(a[0])
+            if t is None or any(f is not None and gj is not None for f, gj in t):
+                return None
+            one = g.const(1.0, weak=True)
+            u = v = None
+            for f, gj in t:
+                if gj is None:
+                    u = f if u is None else g.binop("add", u, f)
+                else:
+                    v = gj if v is None else g.binop("add", v, gj)
+            if u is None or v is None:
+                return None
+            if op == "exp":
+                return [(g.unop("exp", u), g.unop("exp", v))]
+            su, cu, sv, cv = g.unop("sin", u), g.unop("cos", u), g.unop("sin", v), g.unop("cos", v)
+            if op == "sin":
+                return [(su, cv), (cu, sv)]
+            return [(cu, cv), (g.unop("neg", su), sv)]
+        return None
+
+    def _wsum_separated(self, w: _V, terms, nrow: int, ncol: int) -> _V:
+        g = self.g
+        out = None
+        wname = g.payload[w.sym.id][0]
+        for f, gj in terms:
+            src = _V(VEC, self._role_swap(gj.id, "j", "i") if gj is not None else g.const(1.0), n=ncol)
+            name, off = self._materialize(src, "sep")
+            summand = g.binop("mul", w.sym, self._leaf("ld", (name, off, "j")))
+            red = self._reduce_rows(summand, nrow, ncol, (wname, name, off))
+            term = red if f is None else self._shape_of(g.binop("mul", f, red.sym), _V(VEC, f, n=nrow), red)
+            out = term if out is None else self._shape_of(g.binop("add", out.sym, term.sym), out, term)
+        return out
 
     def _as_source(self, v: _V) -> Sym:
         """Vector value as a j-indexed summand source.  Cheap expressions are inlined (recomputed at j),
@@ -600,5 +691,7 @@ class _NetInterp:
                      self.uses_t)
 
 
-def netcompile(prog: Program) -> NetIR:
-    return _NetInterp(prog).run()
+def netcompile(prog: Program, separable: bool = True) -> NetIR:
+    """``separable``: rewrite pair-space couplings that factor as sum_k f_k(i) g_k(j) (e.g. sin(theta_j - theta_i))
+    into GEMVs over materialised source vectors — algebraically equal, not bit-equal, to the direct evaluation."""
+    return _NetInterp(prog, separable).run()

@@ -23,7 +23,8 @@ __all__ = ["NetworkModel", "NetworkSession", "build_check", "smoke_check"]
 
 class NetworkModel:
     def __init__(self, prog: Program, *, solver: str = "euler", observers: Optional[Sequence[int]] = None,
-                 block: int = 512, fmad: bool = True, blocks_per_sm: int = 1, rank: int = 0, world: int = 1):
+                 block: int = 512, fmad: bool = True, blocks_per_sm: int = 1, rank: int = 0, world: int = 1,
+                 separable: bool = True):
         if solver not in FIXED_STEP_SOLVERS:
             raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
                                       f"Supported solvers: {list(FIXED_STEP_SOLVERS)}.")
@@ -31,7 +32,7 @@ class NetworkModel:
         self.solver = solver
         self.precision = prog.float_precision
         self.real = prog.real_dtype
-        self.ir: NetIR = netcompile(prog)
+        self.ir: NetIR = netcompile(prog, separable=separable)
         self.observers = list(range(prog.n_state)) if observers is None else [int(o) for o in observers]
         self.rank, self.world = int(rank), int(world)
         self.kernel: NetKernel = emit_net_kernel(self.ir, solver=solver, precision=self.precision,
