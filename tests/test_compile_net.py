@@ -29,7 +29,10 @@ def test_phase_structure():
     """State-sourced dense coupling needs no intra-evaluation barrier; gather edges over a computed vector need one;
     read-before-write persistent buffers (WAR) force an extra phase."""
     assert netcompile(Program.load(golden_path("wc_n128"))).n_phases == 1
-    assert netcompile(Program.load(golden_path("kuramoto_n128"))).n_phases == 1
+    assert netcompile(Program.load(golden_path("kuramoto_n128")), separable=False).n_phases == 1
+    # separable rewrite: phase 0 materialises sin/cos(theta), phase 1 = two GEMVs sharing one W pass
+    ir = netcompile(Program.load(golden_path("kuramoto_n128")))
+    assert ir.n_phases == 2 and [r.simple[0] for r in ir.reductions] == ["weight", "weight"]
     assert netcompile(Program.load(golden_path("jrc_grid_b16"))).n_phases == 2
     assert netcompile(Program.load(golden_path("jrc_2delay"))).n_phases == 3
 
