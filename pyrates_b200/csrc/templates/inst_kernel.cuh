@@ -24,7 +24,11 @@ __device__ __forceinline__ void prb_axpy(real (&o)[N], const real (&y)[N], const
     for (int j = 0; j < N; ++j) o[j] = y[j] + a * k[j];
 }
 
-extern "C" __global__ void __launch_bounds__(PRB_BLOCK)
+#ifndef PRB_MIN_BLOCKS
+#define PRB_MIN_BLOCKS 1
+#endif
+
+extern "C" __global__ void __launch_bounds__(PRB_BLOCK, PRB_MIN_BLOCKS)
 prb_integrate(const __grid_constant__ prb_kernel_args A)
 {
     const long long B = A.n_inst;

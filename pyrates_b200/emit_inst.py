@@ -157,7 +157,7 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool) -> List[str
 
 
 def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: Sequence[int],
-                     block: int = 128, const_div_to_mul: bool = False) -> InstKernel:
+                     block: int = 128, const_div_to_mul: bool = False, min_blocks: int = 1) -> InstKernel:
     """Generate the full CUDA C source of the fused rhs+solver instance kernel."""
     if solver not in SOLVER_IDS:
         raise ValueError(f"unknown solver `{solver}`; supported: {sorted(SOLVER_IDS)}")
@@ -176,6 +176,7 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     src.append(f"#define PRB_NRINGS {nrings}")
     src.append(f"#define PRB_SOLVER {SOLVER_IDS[solver]}")
     src.append(f"#define PRB_BLOCK {block}")
+    src.append(f"#define PRB_MIN_BLOCKS {int(min_blocks)}")
     if ns > 64:
         src.append("#define PRB_UNROLL_NS")        # big states: keep loops rolled (state spills to local memory)
     src.append("""

@@ -46,9 +46,11 @@ class BatchedSweep:
     def __init__(self, prog: Program, sweep: Sequence[Tuple[str, int]], observers: Sequence[int], *,
                  solver: str, T: float, dt: float, dts: Optional[float], n_inst: int,
                  chunk_samples: int = 100, const_div_to_mul: bool = True, block: int = 128,
-                 pinned_result: bool = True):
+                 pinned_result: bool = True, min_blocks: int = 5):
+        # min_blocks=5 caps the kernel at 96 registers -> 20 warps/SM; measured +3.5 % on the JRC/RK4 sweep
+        # (scripts/tune_inst.py), the kernel being FP64-pipe bound either way
         self.model = InstanceModel(prog, solver=solver, sweep=sweep, observers=observers, block=block,
-                                   const_div_to_mul=const_div_to_mul)
+                                   const_div_to_mul=const_div_to_mul, min_blocks=min_blocks if block == 128 else 1)
         order = [(p.arg, p.elem) for p in self.model.rhs.params]
         self._perm = [order.index((a, int(e))) for a, e in sweep]      # user row k -> kernel param row
         self.sweep = list(sweep)
