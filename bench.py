@@ -156,6 +156,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rt.set_device(local_rank)
+    numa_node = None
+    if world > 1:
+        from pyrates_b200.distributed import bind_to_gpu_numa_node
+        numa_node = bind_to_gpu_numa_node(local_rank)      # pinned result buffers next to this GPU's PCIe root
 
     def barrier():
         if dist is not None:
@@ -244,7 +248,7 @@ def main():
                              "observer store; the true bound is the FP64 pipe (see DESIGN.md)"},
         "kernel": {"regs": info["regs"], "local_bytes": info["local_bytes"], "blocks_per_sm": info["max_blocks_per_sm"],
                    "block": sw.model.kernel.block, "const_div_to_mul": not a.strict_div},
-        "jit_s": jit_s,
+        "jit_s": jit_s, "numa_node_rank0": numa_node,
         "clocks": clocks.stop(wall0, wall1) if clocks else None,
     }
     if world == 1 and not a.no_cpu_baseline:

@@ -63,3 +63,30 @@ def gather_instances(local: np.ndarray, n_instances: int, dst: int = 0, device: 
     for r, (lo, hi) in enumerate(bounds):
         out[..., lo:hi] = bufs[r].cpu().numpy()[..., : hi - lo]
     return out
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers allocated
+    afterwards (first touch) sit next to the GPU's PCIe root.  With 8 ranks streaming 8.4 GB each per sweep the
+    D2H path is otherwise limited by cross-socket traffic.  Best effort: returns the node or None."""
+    import subprocess
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = set(os.sched_getaffinity(0)) & set(cpus)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None

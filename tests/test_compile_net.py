@@ -44,7 +44,7 @@ def test_multi_gpu_variants_compile_and_shard_constants(world):
     sizes = []
     for rank in range(world):
         m = NetworkModel(prog, solver="rk4", rank=rank, world=world)
-        assert f"#define PRB_WORLD {world}" in m.kernel.source and "st.release.sys" in m.kernel.source
+        assert f"#define PRB_WORLD {world}" in m.kernel.source and "st.relaxed.sys" in m.kernel.source
         rt.compile_module(m.kernel.source, f"mg{rank}.cu")
         sizes.append(m.kernel.const_init.size)
     full = NetworkModel(prog, solver="rk4").kernel.const_init.size
