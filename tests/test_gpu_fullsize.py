@@ -1,0 +1,91 @@
+"""Parity at the BASELINE.json sizes through size-independent checks (the oracle cannot run 2^20 instances):
+
+* C2 — 2^20-instance JRC sweep through the end-to-end engine (BatchedSweep): random instances of the grid against the
+  oracle integrating that single parameter set; duplicated parameter columns give bit-identical trajectories; the
+  streamed (chunked, overlapped D2H) result is bit-identical to a single-launch run.
+* C3 / C4 / C5 — networks at N in the thousands (programs resized from the N=8 goldens, bench_configs.py) against the
+  oracle on the full state vector for a few steps."""
+import numpy as np
+import pytest
+
+import bench
+import bench_configs as bc
+from conftest import golden_path, traj_rel_err
+from oracle import numpy_oracle as orc
+from pyrates_b200.engine import InstanceModel
+from pyrates_b200.netengine import NetworkModel
+from pyrates_b200.program import Program
+from pyrates_b200.sweep import BatchedSweep
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+def test_c2_full_grid_sweep_spot_checks(gpu):
+    prog = Program.load(golden_path("jrc"))
+    grid = 1024
+    B = grid * grid
+    table = bench.param_table(grid, grid, 0, B)
+    rng = np.random.default_rng(11)
+    picks = sorted(rng.choice(B, 6, replace=False).tolist()) + [0, B - 1]
+    dup_src, dup_dst = picks[0], picks[1] + 1
+    table[:, dup_dst] = table[:, dup_src]
+    T, dt, dts = 0.05, 1e-4, 1e-3
+    sw = BatchedSweep(prog, bench.SWEEP, observers=[0, 2], solver="rk4", T=T, dt=dt, dts=dts, n_inst=B,
+                      chunk_samples=16, const_div_to_mul=False)
+    try:
+        out = np.array(sw.run(table), copy=True)                    # [50, 2, 2^20], 4 chunks streamed
+        assert out.shape == (50, 2, B) and np.all(np.isfinite(out))
+        assert np.array_equal(out[:, :, dup_src], out[:, :, dup_dst])
+        f = orc.build_vector_field(prog.source())
+        names = [a.name for a in prog.args]
+        for b in picks:
+            u, C, C4, C08, _ = table[:, b]
+            args = [np.array(a.value, copy=True) for a in prog.args]
+            args[names.index("u")] = np.float64(u)
+            args[names.index("weight_v2")] = np.array([C, C4])
+            args[names.index("weight")] = np.float64(C08)
+            args[names.index("weight_v1")] = np.float64(C4)
+            rec, _ = orc.run(f, args, T, dt, dts, "rk4")
+            assert traj_rel_err(out[:, :, b], rec[:, [0, 2]]) <= 1e-9, b
+        # one un-chunked launch of a 2^16 slice must reproduce the streamed result bit for bit
+        m = InstanceModel(prog, solver="rk4", sweep=bench.SWEEP, observers=[0, 2], min_blocks=5)
+        order = [(p.arg, p.elem) for p in m.rhs.params]
+        sl = slice(3 * 2 ** 16, 4 * 2 ** 16)
+        params = np.stack([table[bench.SWEEP.index(k), sl] for k in order])
+        single, _ = m.run(T, dt, dts, params=params)
+        assert np.array_equal(single, out[:, :, sl])
+    finally:
+        sw.free()
+
+
+@pytest.mark.parametrize("solver", ["euler", "rk4"])
+def test_c3_wc_dense_n2048_full_state(gpu, solver):
+    prog = bc.make_c3(2048)
+    f = orc.build_vector_field(prog.source())
+    args = [np.array(a.value, copy=True) for a in prog.args]
+    args[0] = args[0][()]
+    ref, _ = orc.run(f, args, 12e-3, 1e-3, None, solver)
+    out, y_final = NetworkModel(prog, solver=solver).run(12e-3, 1e-3, None)
+    assert traj_rel_err(out[:, :, 0], ref) <= 1e-9
+    np.testing.assert_allclose(y_final[:, 0], args[1], rtol=1e-9, atol=1e-12)     # oracle mutated y0 in place to y(T)
+
+
+def test_c4_qif_sfa_two_populations_n1024_full_state(gpu):
+    prog = bc.make_c4(1024)
+    f = orc.build_vector_field(prog.source())
+    args = [np.array(a.value, copy=True) for a in prog.args]
+    args[0] = args[0][()]
+    ref, _ = orc.run(f, args, 10e-3, 1e-3, None, "heun")
+    out, _ = NetworkModel(prog, solver="heun").run(10e-3, 1e-3, None)
+    assert out.shape[1] == 12 * 1024
+    assert traj_rel_err(out[:, :, 0], ref) <= 1e-9
+
+
+def test_c5_kuramoto_n1024_separable_full_state(gpu):
+    prog = bc.make_c5(1024)
+    f = orc.build_vector_field(prog.source())
+    args = [np.array(a.value, copy=True) for a in prog.args]
+    args[0] = args[0][()]
+    ref, _ = orc.run(f, args, 8e-3, 1e-3, None, "rk4")
+    out, _ = NetworkModel(prog, solver="rk4").run(8e-3, 1e-3, None)
+    assert traj_rel_err(out[:, :, 0], ref) <= 1e-9
