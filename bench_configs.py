@@ -186,7 +186,7 @@ def main():
         line["cpu_baseline"] = {"value": nodes * a.cpu_steps / cpu_s, "unit": "node-steps/s", "kind": "port",
                                 "cores": os.cpu_count(), "sample": f"{a.cpu_steps} steps, NumPy/OpenBLAS default threads"}
         if a.check:
-            out = s.download()[: a.cpu_steps, 0]
+            out = s.download()[: a.cpu_steps, 0, 0]
             line["max_abs_diff_vs_oracle_obs0"] = float(np.max(np.abs(out - rec[:, 0])))
     print(json.dumps(line))
     s.free()

@@ -19,8 +19,13 @@
 // PRB_WORK_USER (element offset of the solver buffers inside `work`), PRB_RANK, PRB_WORLD, prb_net_init_heads(),
 // prb_net_advance_heads(), prb_eval<STAGE>() and PRB_OBS_OFF.
 
+#ifndef PRB_NB
+#define PRB_NB 1                 // sweep instances integrated together (batch index b is the fastest-varying dimension)
+#endif
+
 struct PrbNet {
     const real* yin;             // stage input of the current evaluation (written in-kernel: plain loads only)
+    const real* __restrict__ params;   // [n_params][PRB_NB] per-instance (swept) scalars
     real* work;
     real* rings;
     const real* __restrict__ consts;
@@ -260,6 +265,44 @@ __device__ __forceinline__ void prb_row_dot2(const float* __restrict__ w, const 
     rz = prb_warp_sum(b0);
 }
 
+// ---- batched rows: acc[r][bb] = sum_j w[r][j] * x[j][b0+bb] for R rows and BT sweep instances per warp task.
+// The connectivity is shared by all instances of a sweep, so one pass over a W row serves BT instances (and one load
+// of x[j][b0..b0+BT) serves R rows): the GEMM-shaped reuse of a grid_search over a network, in fp64 FMA.
+template <int R, int BT>
+__device__ __forceinline__ void prb_rows_dot_batch(const real* __restrict__ w, const long long ldw, const int rows,
+                                                   const real* x, const int m, const int lane, real (&acc)[R][BT]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int bb = 0; bb < BT; ++bb) acc[r][bb] = (real)0;
+    for (int j = lane; j < m; j += 32) {
+        real xv[BT];
+        const real* xp = x + (long long)j * PRB_NB;
+#pragma unroll
+        for (int bb = 0; bb < BT; ++bb) xv[bb] = xp[bb];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const real wv = (r < rows) ? __ldg(w + r * ldw + j) : (real)0;
+#pragma unroll
+            for (int bb = 0; bb < BT; ++bb) acc[r][bb] = fma(wv, xv[bb], acc[r][bb]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int bb = 0; bb < BT; ++bb) acc[r][bb] = prb_warp_sum(acc[r][bb]);
+}
+
+// lane l of a batched row task owns (row r = l / BT, instance bb = l % BT): pick its sum out of the register tile
+template <int R, int BT>
+__device__ __forceinline__ real prb_tile_pick(const real (&acc)[R][BT], const int lane) {
+    real v = (real)0;
+#pragma unroll
+    for (int q = 0; q < R * BT; ++q)
+        if (lane == q) v = acc[q / BT][q % BT];
+    return v;
+}
+
 // ---- solver stage logic: what happens to the derivative k of state element e in stage STAGE.
 // HEUN_REF reproduces the reference's aliased `heun` (y += dt/2*(k2+k2), base_backend.py:763-765).
 template <int STAGE>
@@ -300,8 +343,10 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
     C.consts = (const real*)A.consts;
     C.iconsts = A.iconsts;
     C.tables = (const real*)A.tables;
-    C.oY = (long long)PRB_WORK_USER; C.oYN = C.oY + PRB_NS; C.oS1 = C.oY + 2LL * PRB_NS; C.oS2 = C.oY + 3LL * PRB_NS;
-    C.oS3 = C.oY + 4LL * PRB_NS; C.oACC = C.oY + 5LL * PRB_NS;
+    const long long nsb = (long long)PRB_NS * PRB_NB;        // every state / work / ring array carries the batch dimension
+    C.oY = (long long)PRB_WORK_USER * PRB_NB; C.oYN = C.oY + nsb; C.oS1 = C.oY + 2LL * nsb; C.oS2 = C.oY + 3LL * nsb;
+    C.oS3 = C.oY + 4LL * nsb; C.oACC = C.oY + 5LL * nsb;
+    C.params = (const real*)A.params;
     C.dt = (real)A.dt; C.hdt = (real)(A.dt / 2); C.dt6 = (real)(A.dt / 6);
     C.bar = (unsigned long long*)A.sync;
     C.bar_target = 0;
@@ -322,7 +367,7 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
     prb_net_init_heads(C, A.eval0);
 
     real* extY = (real*)A.y;
-    for (long long e = C.gtid; e < PRB_NS; e += C.gsize) C.work[C.oY + e] = extY[e];   // every rank holds a full replica
+    for (long long e = C.gtid; e < nsb; e += C.gsize) C.work[C.oY + e] = extY[e];   // every rank holds a full replica
     prb_grid_barrier(C);
 
     real* out = (real*)A.out;
@@ -333,8 +378,10 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
 
     for (long long i = 0; i < A.n_steps; ++i, ++C.t) {
         if (until_store == 0) {
-            for (long long o = C.gtid; o < PRB_NOBS; o += C.gsize)
-                out[sample * (long long)PRB_NOBS + o] = C.work[C.oY + PRB_OBS_INDEX(o)];
+            for (long long q = C.gtid; q < PRB_NOBS * PRB_NB; q += C.gsize) {
+                const long long o = q / PRB_NB, b = q - o * PRB_NB;
+                out[sample * (long long)PRB_NOBS * PRB_NB + q] = C.work[C.oY + PRB_OBS_INDEX(o) * PRB_NB + b];
+            }
             ++sample;
             until_store = store_step;
         }
@@ -352,5 +399,5 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
 #endif
         const long long tmp = C.oY; C.oY = C.oYN; C.oYN = tmp;
     }
-    for (long long e = C.gtid; e < PRB_NS; e += C.gsize) extY[e] = C.work[C.oY + e];
+    for (long long e = C.gtid; e < nsb; e += C.gsize) extY[e] = C.work[C.oY + e];
 }

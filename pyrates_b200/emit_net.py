@@ -13,6 +13,7 @@ import numpy as np
 
 from .emit_inst import SOLVER_IDS, _FUNC, _lit, read_template
 from .netcompile import MemArray, NetIR, Reduction, Store
+from .scalarize import UnsupportedModelError
 
 __all__ = ["NetKernel", "emit_net_kernel"]
 
@@ -38,12 +39,28 @@ class NetKernel:
 
 
 class _Emitter:
-    def __init__(self, ir: NetIR, f32: bool, rank: int = 0, world: int = 1):
+    def __init__(self, ir: NetIR, f32: bool, rank: int = 0, world: int = 1, nb: int = 1):
         self.ir, self.g, self.f32 = ir, ir.graph, f32
-        self.rank, self.world = rank, world
+        self.rank, self.world, self.nb = rank, world, nb
         self.roles: Dict[int, frozenset] = {}
         self.red_work: Dict[int, MemArray] = {}
         self.ring_index = {name: k for k, name in enumerate(a.name for a in ir.arrays.values() if a.space == "ring")}
+
+    def source_ptr(self, r: Reduction) -> str:
+        """Pointer to element j = 0 (instance 0) of the source vector of a simple dot reduction."""
+        xarr = self.ir.arrays[r.simple[1]]
+        scale = f" * {self.nb}LL" if self.nb > 1 else ""
+        if xarr.space == "ring":
+            rows, L = xarr.shape
+            k = self.ring_index[xarr.name]
+            col = r.simple[2][1]
+            return f"C.rings + ({xarr.offset}LL + prb_ring_pos(C.head[{k}], {col - xarr.rolls}, {L}) * {rows}LL){scale}"
+        off = r.simple[2] + (xarr.offset if xarr.space != "y" else 0)
+        return f"{self._ptr(xarr)} + {off}LL{scale}"
+
+    def bidx(self, index: str) -> str:
+        """Element index -> address inside a batched array ([element][instance], instance fastest)."""
+        return f"({index}) * {self.nb}LL + b" if self.nb > 1 else index
 
     def bounds(self, n: int) -> Tuple[int, int]:
         """Rows [lo, hi) of an index space of length n owned by this rank (== sweep.shard_bounds)."""
@@ -87,7 +104,7 @@ class _Emitter:
         off = f"{arr.offset}LL + " if arr.space != "y" else ""
         if arr.space in ("const", "iconst", "table"):
             return f"__ldg({base} + {off}{index})"
-        return f"{base}[{off}{index}]"
+        return f"{base}[{self.bidx(off + index)}]"
 
     def ref(self, i: int, cur: Tuple[int, int, bool], want_real=True) -> str:
         g = self.g
@@ -103,11 +120,11 @@ class _Emitter:
             rid, kind = g.payload[i]
             red = self.ir.reductions[rid]
             if kind == "s":
-                return f"red{rid}"
+                return f"sfull{rid}[b]" if self.nb > 1 else f"red{rid}"
             if cur == (red.phase, red.n, True):
                 return f"red{rid}"
             arr = self.red_work[rid]
-            return f"C.work[{arr.offset}LL + i]"
+            return f"C.work[{self.bidx(f'{arr.offset}LL + i')}]"
         name = f"v{i}"
         if g.isint[i] and want_real:
             return f"((real){name})"
@@ -120,6 +137,8 @@ class _Emitter:
         r = lambda k, real=True: self.ref(k, cur, real)
         if op in ("const", "t", "red"):
             return None
+        if op == "param":
+            return f"__ldg(C.params + {pl}LL * {self.nb}LL + b)"
         if op == "ld":
             arr = ir.arrays[pl[0]]
             return self._load(arr, f"{pl[1]}LL + {pl[2]}")
@@ -136,7 +155,7 @@ class _Emitter:
             arr = ir.arrays[pl[0]]
             rows, L = arr.shape
             k = self.ring_index[pl[0]]
-            return (f"C.rings[{arr.offset}LL + prb_ring_pos(C.head[{k}], {pl[1] - arr.rolls}, {L}) * {rows}LL + {pl[2]}]")
+            return ("C.rings[" + self.bidx(f"{arr.offset}LL + prb_ring_pos(C.head[{k}], {pl[1] - arr.rolls}, {L}) * {rows}LL + {pl[2]}") + "]")
         if op == "table":
             arr = ir.arrays[pl[0]]
             col = "i" if pl[2] == "i" else f"{pl[2]}LL"
@@ -200,28 +219,29 @@ class _Emitter:
     def store_stmt(self, st: Store, cur, stage_tpl: str) -> str:
         val = self.ref(st.node, cur)
         t = st.target
+        B = self.bidx
         if t[0] == "dy":
-            return f"prb_emit_k<STAGE>(C, {t[1]}LL + i, {val});"
+            return f"prb_emit_k<STAGE>(C, {B(f'{t[1]}LL + i')}, {val});"
         if t[0] == "work":
             arr = self.ir.arrays[t[1]]
-            return f"prb_st_work(C, {arr.offset}LL + i, {val});"
+            return f"prb_st_work(C, {B(f'{arr.offset}LL + i')}, {val});"
         if t[0] == "work_at":
             arr = self.ir.arrays[t[1]]
-            return f"prb_st_work(C, {arr.offset + t[2]}LL, {val});"
+            return f"prb_st_work(C, {B(f'{arr.offset + t[2]}LL')}, {val});"
         if t[0] == "scatter":
             arr, iarr = self.ir.arrays[t[1]], self.ir.arrays[t[2]]
-            return f"prb_st_work(C, {arr.offset}LL + (long long){self._load(iarr, 'i')}, {val});"
+            return f"prb_st_work(C, {B(f'{arr.offset}LL + (long long){self._load(iarr, chr(105))}')}, {val});"
         if t[0] == "ring":
             arr = self.ir.arrays[t[1]]
             rows, L = arr.shape
             k = self.ring_index[t[1]]
-            return (f"prb_st_ring(C, {arr.offset}LL + prb_ring_pos(C.head[{k}], {t[2] - arr.rolls}, {L}) * {rows}LL + i, "
-                    f"{val});")
+            pos = f"{arr.offset}LL + prb_ring_pos(C.head[{k}], {t[2] - arr.rolls}, {L}) * {rows}LL + i"
+            return f"prb_st_ring(C, {B(pos)}, {val});"
         raise NotImplementedError(t[0])
 
 
 def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequence[int], block: int = 512,
-                    rank: int = 0, world: int = 1) -> NetKernel:
+                    rank: int = 0, world: int = 1, n_batch: int = 1) -> NetKernel:
     if solver not in SOLVER_IDS:
         raise ValueError(f"unknown solver `{solver}`")
     f32 = precision == "float32"
@@ -229,7 +249,11 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     ns = ir.n_state
     # reduction results get a work array so that consumers outside the fused row task can read them
     work_size = ir.work_size
-    em = _Emitter(ir, f32, rank, world)
+    nb = int(n_batch)
+    R_T, B_T = 2, 8                       # batched row task: 2 rows x 8 instances per warp
+    if nb > 1 and nb % B_T:
+        raise ValueError(f"batched network kernels need a multiple of {B_T} instances (pad the sweep), got {nb}")
+    em = _Emitter(ir, f32, rank, world, nb)
     # multi-GPU: 2-d constants (connectivity) are row-sharded -> re-pack the constant space with shard sizes
     const_size = ir.const_size
     if world > 1:
@@ -256,7 +280,9 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     body: List[str] = []
     full_reds = [r for r in ir.reductions if r.kind == "full"]
     for r in full_reds:
-        body.append(f"    real red{r.id} = (real)0;")
+        body.append(f"    __shared__ real sfull{r.id}[{nb}];" if nb > 1 else f"    real red{r.id} = (real)0;")
+    if nb == 1:
+        body.append("    const int b = 0; (void)b;")
     n_phases = ir.n_phases
     for p in range(n_phases):
         body.append(f"    // ---------------- phase {p}")
@@ -265,15 +291,20 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
             cur = (p, -1, False)
             emitted: Set[int] = set()
             nodes = em.order([r.node])
-            body.append("    {")
-            body.extend(em.emit_nodes(nodes, cur, emitted, "        ", only_roles=frozenset()))
+            body.append(f"    for (int b = 0; b < {nb}; ++b) {{" if nb > 1 else "    {")
             body.append("        real acc = (real)0;")
             body.append(f"        for (long long j = threadIdx.x; j < {r.m}LL; j += blockDim.x) {{")
             body.extend(em.emit_nodes(nodes, cur, emitted, "            "))
             body.append(f"            acc += {em.ref(r.node, cur)};")
             body.append("        }")
-            body.append(f"        red{r.id} = prb_block_sum(acc);")
-            body.append("    }")
+            if nb > 1:
+                body.append("        acc = prb_block_sum(acc);")
+                body.append(f"        if (threadIdx.x == 0) sfull{r.id}[b] = acc;")
+                body.append("    }")
+                body.append("    __syncthreads();")
+            else:
+                body.append(f"        red{r.id} = prb_block_sum(acc);")
+                body.append("    }")
         # (2) groups by length
         stores_p = [s for s in ir.stores if s.phase == p]
         rows_p = [r for r in ir.reductions if r.kind == "row" and r.phase == p]
@@ -281,15 +312,48 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
         for n in lengths:
             reds = [r for r in rows_p if r.n == n]
             sts = [s for s in stores_p if s.n == n]
-            if reds:
+            if reds and nb > 1:
+                # batched sweep: one warp task = R_T rows x B_T instances; W rows are read once per B_T instances
+                cur = (p, n, True)
+                lo, hi = em.bounds(n)
+                if any(r.simple is None for r in reds):
+                    raise UnsupportedModelError("batched network sweeps support dense dot couplings (and pair-space "
+                                                "couplings that separate into them) only")
+                n_bt = nb // B_T
+                body.append(f"    for (long long task = C.gwarp; task < {((hi - lo + R_T - 1) // R_T) * n_bt}LL; task += C.nwarps) {{"
+                            f"   // {R_T} rows x {B_T} instances per warp, n = {n}")
+                body.append(f"        const long long i0 = {lo}LL + (task / {n_bt}) * {R_T};")
+                body.append(f"        const int b0 = (int)(task % {n_bt}) * {B_T};")
+                body.append(f"        const int rows = (int)(({hi}LL - i0) < {R_T} ? ({hi}LL - i0) : {R_T});")
+                for r in reds:
+                    warr = ir.arrays[r.simple[0]]
+                    body.append(f"        real acc{r.id}[{R_T}][{B_T}];")
+                    body.append(f"        prb_rows_dot_batch<{R_T}, {B_T}>(C.consts + {warr.offset}LL + (i0 - {lo}LL) * {r.m}LL, {r.m}LL, rows, "
+                                f"{em.source_ptr(r)} + b0, {r.m}, C.lane, acc{r.id});")
+                body.append(f"        const long long i = i0 + (C.lane / {B_T});")
+                body.append(f"        const int b = b0 + (C.lane % {B_T});")
+                for r in reds:
+                    body.append(f"        const real red{r.id} = prb_tile_pick<{R_T}, {B_T}>(acc{r.id}, C.lane);")
+                body.append(f"        if (C.lane < {R_T * B_T} && i < {hi}LL) {{")
+                emitted = set()
+                for r in reds:
+                    need = any(_uses_red(g, em, s_.node, r.id) and (s_.phase, s_.n) != (p, n) for s_ in ir.stores) or \
+                        any(_uses_red(g, em, x.node, r.id) for x in ir.reductions)
+                    if need:
+                        body.append(f"            prb_st_work(C, {em.bidx(f'{em.red_work[r.id].offset}LL + i')}, red{r.id});")
+                nodes = em.order([s_.node for s_ in sts])
+                body.extend(em.emit_nodes(nodes, cur, emitted, "            "))
+                for s_ in sts:
+                    body.append("            " + em.store_stmt(s_, cur, "STAGE"))
+                body.append("        }")
+                body.append("    }")
+            elif reds:
                 cur = (p, n, True)
                 lo, hi = em.bounds(n)
                 body.append(f"    for (long long i = {lo}LL + C.gwarp; i < {hi}LL; i += C.nwarps) {{      // warp per row, n = {n}")
                 emitted = set()
                 def xptr_of(r):
-                    xarr = ir.arrays[r.simple[1]]
-                    off = r.simple[2] + (xarr.offset if xarr.space != "y" else 0)
-                    return f"{em._ptr(xarr)} + {off}LL"
+                    return em.source_ptr(r)
                 fused_done: Set[int] = set()
                 for r in reds:
                     if r.id in fused_done:
@@ -347,7 +411,11 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 nodes = em.order(roots)
                 emitted = set()
                 lo, hi = em.bounds(n)
-                body.append(f"    for (long long i = {lo}LL + C.gtid; i < {hi}LL; i += C.gsize) {{        // thread per element, n = {n}")
+                if nb > 1:
+                    body.append(f"    for (long long q = {lo * nb}LL + C.gtid; q < {hi * nb}LL; q += C.gsize) {{   // thread per (element, instance), n = {n}")
+                    body.append(f"        const long long i = q / {nb}; const int b = (int)(q - i * {nb});")
+                else:
+                    body.append(f"    for (long long i = {lo}LL + C.gtid; i < {hi}LL; i += C.gsize) {{        // thread per element, n = {n}")
                 body.extend(em.emit_nodes(nodes, cur, emitted, "        "))
                 for s in sts:
                     body.append("        " + em.store_stmt(s, cur, "STAGE"))
@@ -366,6 +434,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     src.append(f"#define PRB_SOLVER {SOLVER_IDS[solver]}")
     src.append(f"#define PRB_BLOCK {block}")
     src.append(f"#define PRB_WORK_USER {work_size}LL")
+    src.append(f"#define PRB_NB {nb}")
     src.append(f"#define PRB_RANK {rank}")
     src.append(f"#define PRB_WORLD {world}")
     src.append("#define PRB_OBS_INDEX(o) (o)" if all_state else f"#define PRB_OBS_INDEX(o) ((long long)A.iconsts[{obs_off}LL + (o)])")
@@ -404,7 +473,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     if not all_state:
         iconst[obs_off:obs_off + obs.size] = obs
     evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4}[solver]
-    return NetKernel("\n".join(src) + "\n", ns, int(obs.size), work_size + 6 * ns, work_size,
+    return NetKernel("\n".join(src) + "\n", ns, int(obs.size), (work_size + 6 * ns) * nb, work_size,
                      pack("work", work_size, real), pack("const", const_size, real), iconst,
                      pack("ring", ir.ring_size, real), pack("table", ir.table_size, real), block, solver, precision,
                      evals, n_phases)

@@ -85,6 +85,7 @@ class NetIR:
     ring_size: int
     table_size: int
     uses_t: bool
+    params: List[Tuple[str, float]] = field(default_factory=list)    # swept per-instance scalars (arg name, default)
 
 
 class _V:
@@ -96,9 +97,11 @@ class _V:
 
 
 class _NetInterp:
-    def __init__(self, prog: Program, separable: bool = True):
+    def __init__(self, prog: Program, separable: bool = True, sweep: Sequence[str] = ()):
         self.p = prog
         self.separable = separable
+        self.params: List[Tuple[str, float]] = []
+        sweep = list(sweep)
         self._role_memo: Dict[int, frozenset] = {}
         self.g = Graph(prog.real_dtype)
         self.arrays: Dict[str, MemArray] = {}
@@ -129,6 +132,9 @@ class _NetInterp:
                 if isinstance(node, ast.Call) and getattr(node.func, "id", None) == "roll" and node.args \
                         and isinstance(node.args[0], ast.Name):
                     rolled.add(node.args[0].id)
+        unknown = [n for n in sweep if n not in {a.name for a in prog.args}]
+        if unknown:
+            raise KeyError(f"sweep targets {unknown} are not arguments of the program")
         for a in prog.args:
             v = np.asarray(a.value)
             if a.kind == "t":
@@ -154,6 +160,13 @@ class _NetInterp:
                     self.env[a.name] = ("index", a.name)
             elif np.iscomplexobj(v):
                 raise UnsupportedModelError("complex-valued models are not supported by the CUDA backend")
+            elif a.name in sweep:
+                # per-instance scalar of a batched sweep (a 0-d parameter, or a uniform per-node vector swept as a whole)
+                if a.kind != "const" or not (v.ndim == 0 or (v.ndim == 1 and np.all(v == v.reshape(-1)[0]))):
+                    raise UnsupportedModelError(f"swept argument `{a.name}` must be a scalar or a uniform per-node vector")
+                leaf = self.g.leaf("param", len(self.params))
+                self.params.append((a.name, float(v.reshape(-1)[0])))
+                self.env[a.name] = _V(SCALAR, leaf) if v.ndim == 0 else _V(VEC, leaf, n=v.size)
             elif a.kind == "var":
                 arr = self._add_array(a.name, "work", v.shape, v)
                 arr.persistent = True
@@ -415,6 +428,8 @@ class _NetInterp:
             simple = None
             if g.ops[src.id] == "ld":
                 simple = (g.payload[w.sym.id][0], g.payload[src.id][0], g.payload[src.id][1])
+            elif g.ops[src.id] == "ldring":          # delayed source: one contiguous column of the ring buffer
+                simple = (g.payload[w.sym.id][0], g.payload[src.id][0], ("ring", g.payload[src.id][1]))
             return self._reduce_rows(summand, w.n, w.m, simple)
         if fname == "wsum":
             w, c = self.as_val(args[0]), self.as_val(args[1])
@@ -688,10 +703,10 @@ class _NetInterp:
         n_phases = 1 + max([s.phase for s in self.stores] + [r.phase for r in self.reductions] + [0])
         return NetIR(g, self.n_state, self.arrays, self.reductions, self.stores, n_phases,
                      self.off["const"], self.off["iconst"], self.off["work"], self.off["ring"], self.off["table"],
-                     self.uses_t)
+                     self.uses_t, self.params)
 
 
-def netcompile(prog: Program, separable: bool = True) -> NetIR:
+def netcompile(prog: Program, separable: bool = True, sweep: Sequence[str] = ()) -> NetIR:
     """``separable``: rewrite pair-space couplings that factor as sum_k f_k(i) g_k(j) (e.g. sin(theta_j - theta_i))
     into GEMVs over materialised source vectors — algebraically equal, not bit-equal, to the direct evaluation."""
-    return _NetInterp(prog, separable).run()
+    return _NetInterp(prog, separable, sweep).run()

@@ -24,7 +24,9 @@ __all__ = ["NetworkModel", "NetworkSession", "build_check", "smoke_check"]
 class NetworkModel:
     def __init__(self, prog: Program, *, solver: str = "euler", observers: Optional[Sequence[int]] = None,
                  block: int = 512, fmad: bool = True, blocks_per_sm: int = 1, rank: int = 0, world: int = 1,
-                 separable: bool = True):
+                 separable: bool = True, n_batch: int = 1, sweep: Sequence[str] = ()):
+        """``n_batch`` > 1 integrates that many sweep instances of the network together (shared connectivity, one
+        pass over W per 8 instances); ``sweep`` names the scalar / uniform-vector arguments that vary per instance."""
         if solver not in FIXED_STEP_SOLVERS:
             raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
                                       f"Supported solvers: {list(FIXED_STEP_SOLVERS)}.")
@@ -32,11 +34,15 @@ class NetworkModel:
         self.solver = solver
         self.precision = prog.float_precision
         self.real = prog.real_dtype
-        self.ir: NetIR = netcompile(prog, separable=separable)
+        self.n_batch = int(n_batch)
+        self.ir: NetIR = netcompile(prog, separable=separable, sweep=sweep)
+        self.param_names = [n for n, _ in self.ir.params]
+        self.param_defaults = np.array([d for _, d in self.ir.params], dtype=np.float64)
         self.observers = list(range(prog.n_state)) if observers is None else [int(o) for o in observers]
         self.rank, self.world = int(rank), int(world)
         self.kernel: NetKernel = emit_net_kernel(self.ir, solver=solver, precision=self.precision,
-                                                 observers=self.observers, block=block, rank=self.rank, world=self.world)
+                                                 observers=self.observers, block=block, rank=self.rank, world=self.world,
+                                                 n_batch=self.n_batch)
         self.fmad = fmad
         self.blocks_per_sm = blocks_per_sm
         self._module: Optional[rt.Module] = None
@@ -55,17 +61,19 @@ class NetworkModel:
     def session(self, n_samples: int, stream=None) -> "NetworkSession":
         return NetworkSession(self, n_samples, stream)
 
-    def run(self, T: float, dt: float, dts: Optional[float] = None, *, y0: Optional[np.ndarray] = None, **_):
+    def run(self, T: float, dt: float, dts: Optional[float] = None, *, y0: Optional[np.ndarray] = None,
+            params: Optional[np.ndarray] = None, **_):
+        """Returns ``(out[n_samples, n_obs, n_batch], y_final[n_state, n_batch])``."""
         steps, store_step, n_samples = n_steps_for(T, dt, dts)
         s = self.session(n_samples)
         try:
-            s.reset(y0)
+            s.reset(y0, params)
             s.launch(steps, dt, store_step)
             out = s.download()
             y_final = s.download_state()
         finally:
             s.free()
-        return out[:, :, None], y_final[:, None]
+        return out, y_final
 
 
 class NetworkSession:
@@ -76,13 +84,15 @@ class NetworkSession:
         self.stream = stream
         self.n_samples = int(n_samples)
         item = np.dtype(real).itemsize
-        self.d_y = rt.DeviceBuffer(max(k.n_state, 1) * item)
-        self.d_out = rt.DeviceBuffer(max(self.n_samples * k.n_obs, 1) * item)
+        self.B = B = model.n_batch
+        self.d_y = rt.DeviceBuffer(max(k.n_state * B, 1) * item)
+        self.d_out = rt.DeviceBuffer(max(self.n_samples * k.n_obs * B, 1) * item)
+        self.d_params = rt.DeviceBuffer(max(len(model.param_names) * B, 1) * item)
         self.d_consts = rt.DeviceBuffer.from_host(k.const_init.astype(real))
         self.d_iconsts = rt.DeviceBuffer.from_host(k.iconst_init.astype(np.int32))
         self.d_tables = rt.DeviceBuffer.from_host(k.table_init.astype(real))
         self.d_work = rt.DeviceBuffer(max(k.work_elems, 1) * item)
-        self.d_rings = rt.DeviceBuffer(max(k.ring_init.size, 1) * item)
+        self.d_rings = rt.DeviceBuffer(max(k.ring_init.size * B, 1) * item)
         self.d_sync = rt.DeviceBuffer(8 * (8 + max(model.world, 8)))
         self.sm_count = rt.device_info()["sm_count"]
         self.steps_done = 0
@@ -115,14 +125,28 @@ class NetworkSession:
         self.d_peers = rt.DeviceBuffer.from_host(table)
         dist.barrier()
 
-    def reset(self, y0: Optional[np.ndarray] = None):
-        k, real = self.m.kernel, self.m.real
-        y0 = self.m.prog.y0 if y0 is None else np.asarray(y0).reshape(-1)
+    def reset(self, y0: Optional[np.ndarray] = None, params: Optional[np.ndarray] = None):
+        """Upload initial state ([n_state] or [n_state, B]), swept parameters ([n_params, B]) and buffer images;
+        every batched array is laid out [element][instance]."""
+        k, real, B = self.m.kernel, self.m.real, self.B
+        y0 = self.m.prog.y0 if y0 is None else np.asarray(y0)
+        if y0.ndim == 1:
+            y0 = np.repeat(y0[:, None], B, axis=1)
+        if y0.shape != (k.n_state, B):
+            raise ValueError(f"y0 must have shape ({k.n_state},) or ({k.n_state}, {B})")
         self.d_y.upload(np.ascontiguousarray(y0, dtype=real), self.stream)
+        n_par = len(self.m.param_names)
+        if n_par:
+            if params is None:
+                params = np.repeat(self.m.param_defaults[:, None], B, axis=1)
+            params = np.ascontiguousarray(params, dtype=real)
+            if params.shape != (n_par, B):
+                raise ValueError(f"params must have shape ({n_par}, {B}) in the order {self.m.param_names}")
+            self.d_params.upload(params, self.stream)
         work = np.zeros(max(k.work_elems, 1), dtype=real)
-        work[: k.work_init.size] = k.work_init
+        work[: k.work_init.size * B] = np.repeat(k.work_init, B)
         self.d_work.upload(work, self.stream)
-        self.d_rings.upload(np.ascontiguousarray(k.ring_init, dtype=real), self.stream)
+        self.d_rings.upload(np.ascontiguousarray(np.repeat(k.ring_init, B), dtype=real), self.stream)
         self.steps_done = 0
         self.samples_done = 0
 
@@ -145,9 +169,9 @@ class NetworkSession:
         a = rt.KernelArgs()
         a.n_steps, a.store_step, a.step0 = int(n_steps), int(store_step), int(self.steps_done)
         a.t0, a.eval0 = self.m.t0, int(self.steps_done) * k.evals_per_step
-        a.n_inst, a.sample0, a.dt = 1, int(self.samples_done), float(dt)
+        a.n_inst, a.sample0, a.dt = self.B, int(self.samples_done), float(dt)
         a.y, a.out = self.d_y.ptr, self.d_out.ptr
-        a.params = a.slots = None
+        a.params, a.slots = self.d_params.ptr, None
         a.rings, a.tables = self.d_rings.ptr, self.d_tables.ptr
         a.consts, a.iconsts = self.d_consts.ptr, self.d_iconsts.ptr
         a.work, a.sync = self.d_work.ptr, self.d_sync.ptr
@@ -169,7 +193,7 @@ class NetworkSession:
             raise rt.CudaBackendError("network kernel barrier timed out (a peer rank did not arrive)")
 
     def download(self) -> np.ndarray:
-        out = np.empty((self.n_samples, self.m.kernel.n_obs), dtype=self.m.real)
+        out = np.empty((self.n_samples, self.m.kernel.n_obs, self.B), dtype=self.m.real)
         if out.size:
             self.d_out.download(out, self.stream)
         if self.stream is not None:
@@ -178,7 +202,7 @@ class NetworkSession:
         return out
 
     def download_state(self) -> np.ndarray:
-        y = np.empty(self.m.kernel.n_state, dtype=self.m.real)
+        y = np.empty((self.m.kernel.n_state, self.B), dtype=self.m.real)
         self.d_y.download(y, self.stream)
         if self.stream is not None:
             self.stream.synchronize()
@@ -193,7 +217,7 @@ class NetworkSession:
             self._peer_ptrs = []
             if dist.is_initialized():
                 dist.barrier()                  # nobody frees memory a peer may still have mapped
-        for n in ("d_y", "d_out", "d_consts", "d_iconsts", "d_tables", "d_work", "d_rings", "d_sync", "d_peers"):
+        for n in ("d_y", "d_out", "d_consts", "d_iconsts", "d_tables", "d_work", "d_rings", "d_sync", "d_peers", "d_params"):
             b = getattr(self, n, None)
             if b is not None:
                 b.free()
