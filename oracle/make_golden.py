@@ -227,6 +227,10 @@ CASES = {
     "wc_n8":       dict(build=_wc_pop(8), T=0.2, dt=1e-3, out="e/rate_op/r"),
     "wc_n128":     dict(build=_wc_pop(128), T=0.1, dt=1e-3, dts=2e-3, out="e/rate_op/r"),
     "wc_n128_f32": dict(build=_wc_pop(128), T=0.1, dt=1e-3, dts=2e-3, out="e/rate_op/r", precision="float32"),
+    # float32 networks for the tcgen05 (3xTF32) sweep-batched coupling: padded rows / K, several K chunks, two matrices
+    "wc_n300_f32": dict(build=_wc_pop(300), T=0.05, dt=1e-3, dts=2e-3, out="e/rate_op/r", precision="float32"),
+    "qsfa_both_n96_f32": dict(build=_qif_sfa_pop(96, "both"), T=0.05, dt=1e-3, out="p1/qif_sfa_op/r", precision="float32"),
+    "kuramoto_n128_f32": dict(build=_kuramoto(128), T=0.05, dt=1e-3, out="e/phase_op/theta", precision="float32"),
     "qsfa_cascade_n8":   dict(build=_qif_sfa_pop(8, "cascade"), T=0.1, dt=1e-3, out="p/qif_sfa_op/r"),
     "qsfa_ring_n8":      dict(build=_qif_sfa_pop(8, "ring"), T=0.1, dt=1e-3, out="p/qif_sfa_op/r"),
     "qsfa_both_n8":      dict(build=_qif_sfa_pop(8, "both"), T=0.1, dt=1e-3, out="p1/qif_sfa_op/r"),

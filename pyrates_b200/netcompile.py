@@ -100,8 +100,8 @@ class _NetInterp:
     def __init__(self, prog: Program, separable: bool = True, sweep: Sequence[str] = ()):
         self.p = prog
         self.separable = separable
-        self.params: List[Tuple[str, float]] = []
         sweep = list(sweep)
+        self.params: List[Tuple[str, float]] = [(n, 0.0) for n in sweep]   # rows of the params array, caller's order
         self._role_memo: Dict[int, frozenset] = {}
         self.g = Graph(prog.real_dtype)
         self.arrays: Dict[str, MemArray] = {}
@@ -135,6 +135,7 @@ class _NetInterp:
         unknown = [n for n in sweep if n not in {a.name for a in prog.args}]
         if unknown:
             raise KeyError(f"sweep targets {unknown} are not arguments of the program")
+        bound = set()
         for a in prog.args:
             v = np.asarray(a.value)
             if a.kind == "t":
@@ -164,8 +165,9 @@ class _NetInterp:
                 # per-instance scalar of a batched sweep (a 0-d parameter, or a uniform per-node vector swept as a whole)
                 if a.kind != "const" or not (v.ndim == 0 or (v.ndim == 1 and np.all(v == v.reshape(-1)[0]))):
                     raise UnsupportedModelError(f"swept argument `{a.name}` must be a scalar or a uniform per-node vector")
-                leaf = self.g.leaf("param", len(self.params))
-                self.params.append((a.name, float(v.reshape(-1)[0])))
+                leaf = self.g.leaf("param", sweep.index(a.name))
+                self.params[sweep.index(a.name)] = (a.name, float(v.reshape(-1)[0]))
+                bound.add(a.name)
                 self.env[a.name] = _V(SCALAR, leaf) if v.ndim == 0 else _V(VEC, leaf, n=v.size)
             elif a.kind == "var":
                 arr = self._add_array(a.name, "work", v.shape, v)
@@ -179,6 +181,9 @@ class _NetInterp:
             else:
                 self._add_array(a.name, "const", v.shape, v)
                 self.env[a.name] = ("array", a.name)
+        unbound = [n for n in sweep if n not in bound]
+        if unbound:
+            raise UnsupportedModelError(f"swept arguments {unbound} are not real-valued constants of the program")
 
     # ------------------------------------------------------------------ arrays
     def _add_array(self, name, space, shape, init) -> MemArray:
