@@ -109,6 +109,13 @@ def make_c5(n: int) -> Program:
     return resize_program(base, 8, n, fill)
 
 
+def to_float32(prog: Program) -> Program:
+    """The same program at the reference's default float_precision='float32' (real arguments cast, text unchanged)."""
+    args = [Arg(a.name, a.kind, np.asarray(a.value).astype(np.float32) if np.asarray(a.value).dtype == np.float64
+                else np.asarray(a.value), a.label) for a in prog.args]
+    return Program(args, list(prog.stmts), {}, "float32", prog.func_name)
+
+
 CONFIGS = {"c3": (make_c3, 1, 1), "c4": (make_c4, 12, 2), "c5": (make_c5, 1, 1)}   # (builder, n_sv per unit, populations)
 
 
@@ -121,6 +128,10 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--block", type=int, default=512)
     ap.add_argument("--check", action="store_true", help="compare the first cpu-steps against the oracle")
+    ap.add_argument("--batch", type=int, default=1, help="sweep instances sharing the connectivity (grid_search over a network)")
+    ap.add_argument("--sweep", default="", help="comma-separated swept scalar arguments (batch > 1)")
+    ap.add_argument("--precision", default="float64", choices=["float64", "float32"])
+    ap.add_argument("--tensor-core", default="auto", choices=["auto", "off"])
     a = ap.parse_args()
     from pyrates_b200 import runtime as rt
     from pyrates_b200.netengine import NetworkModel
@@ -135,16 +146,25 @@ def main():
     rt.set_device(local_rank)
     build, _, pops = CONFIGS[a.config]
     prog = build(a.n)
+    if a.precision == "float32":
+        prog = to_float32(prog)
     dt = 1e-3
-    m = NetworkModel(prog, solver=a.solver, observers=[0], block=a.block, rank=rank, world=world)
+    sweep = [x for x in a.sweep.split(",") if x]
+    m = NetworkModel(prog, solver=a.solver, observers=[0], block=a.block, rank=rank, world=world, n_batch=a.batch,
+                     sweep=sweep, tensor_core="auto" if a.tensor_core == "auto" else False)
+    params = None
+    if sweep:
+        params = m.param_defaults[:, None] * (1.0 + 0.1 * np.random.default_rng(3).uniform(-1, 1, (len(sweep), a.batch))) \
+            + 0.05 * np.random.default_rng(4).uniform(0, 1, (len(sweep), a.batch))
     t0 = time.perf_counter()
     m.module
     jit_s = time.perf_counter() - t0
     s = m.session(a.steps)
-    s.reset()
+    s.reset(params=params)
     s.launch(min(a.steps, 20), dt, 1)
     rt.synchronize()
-    s.reset()
+    s.check()
+    s.reset(params=params)
     e0, e1 = rt.Event(), rt.Event()
     e0.record()
     s.launch(a.steps, dt, 1)
@@ -171,11 +191,28 @@ def main():
         dist.destroy_process_group()
         return
     line = {"config": a.config, "n": a.n, "solver": a.solver, "n_gpus": world, "steps": a.steps, "ms_per_step": ms / a.steps,
-            "node_steps_per_s": nodes * a.steps / (ms * 1e-3), "evals_per_step": evals, "W_bytes": wbytes,
+            "node_steps_per_s": nodes * a.batch * a.steps / (ms * 1e-3), "evals_per_step": evals, "W_bytes": wbytes,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "model": "this rank's W shard bytes x evaluations per step (state vectors negligible); per GPU"},
-            "jit_s": jit_s, "phases": m.kernel.n_phases, "block": a.block}
-    if a.cpu_steps:
+            "jit_s": jit_s, "phases": m.kernel.n_phases, "block": m.kernel.block, "batch": a.batch, "precision": a.precision}
+    if a.batch > 1:
+        # sweep-batched coupling is GEMM-shaped: 2 flops per (target, source, instance) and evaluation
+        flops = sum(2.0 * r.n * r.m for r in m.ir.reductions if r.kind == "row") * a.batch * evals * a.steps
+        tf = flops / (ms * 1e-3) / 1e12
+        if m.kernel.tc is not None:
+            peak = 1388.2
+            if os.path.exists(p):
+                peak = float(json.load(open(p)).get("bf16_tflops_sustained", peak))
+            line["roofline"] = {"bound": "tensor", "achieved": 3 * tf, "peak": peak / 2, "unit": "TFLOP/s", "frac": 3 * tf / (peak / 2),
+                                "model": "tf32 tensor-pipe flops = 3 x (2 N_t N_s B) per evaluation (3xTF32 error-compensated "
+                                         "products); peak = measured sustained bf16 dense / 2 (tf32 runs at half the bf16 rate)",
+                                "fp32_equivalent_tflops": tf}
+            line["tc"] = m.kernel.tc
+        else:
+            fma_peak = 148 * 128 * 2 * 1.965e9 / 1e12 / (1 if a.precision == "float32" else 2)
+            line["roofline"] = {"bound": "fma", "achieved": tf, "peak": fma_peak, "unit": "TFLOP/s", "frac": tf / fma_peak,
+                                "model": "2 N_t N_s B flops per evaluation on the FMA pipe (nominal 148 SMs x 128 (64 fp64) FMA/clk x 1.965 GHz)"}
+    if a.cpu_steps and a.batch == 1:
         from oracle import numpy_oracle as orc
         f = orc.build_vector_field(prog.source())
         args = [np.array(x.value, copy=True) for x in prog.args]

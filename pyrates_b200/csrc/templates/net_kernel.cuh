@@ -45,6 +45,9 @@ struct PrbNet {
 #endif
     long long gtid, gsize, gwarp, nwarps;
     int lane;
+#ifdef PRB_TC
+    PrbTc tc;                    // tcgen05 coupling-GEMM pipeline state (tc_gemm.cuh)
+#endif
 };
 
 // ---- shared stores: values other CTAs (and, with PRB_WORLD > 1, other GPUs) will read.  In a multi-GPU run every
@@ -365,6 +368,9 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
     C.gwarp = C.gtid >> 5;
     C.nwarps = C.gsize >> 5;
     prb_net_init_heads(C, A.eval0);
+#ifdef PRB_TC
+    prb_tc_setup(C.tc, C.bar + 2);
+#endif
 
     real* extY = (real*)A.y;
     for (long long e = C.gtid; e < nsb; e += C.gsize) C.work[C.oY + e] = extY[e];   // every rank holds a full replica
@@ -400,4 +406,7 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
         const long long tmp = C.oY; C.oY = C.oYN; C.oYN = tmp;
     }
     for (long long e = C.gtid; e < nsb; e += C.gsize) extY[e] = C.work[C.oY + e];
+#ifdef PRB_TC
+    prb_tc_teardown(C.tc);
+#endif
 }

@@ -122,4 +122,168 @@ __device__ __forceinline__ void prb_tf32_split(const float x, float& hi, float& 
 __host__ __device__ constexpr long long prb_tc_tile_off(int rows, int r, int k) {
     return ((long long)(k >> 2) * (rows >> 3) + (r >> 3)) * 32 + (r & 7) * 4 + (k & 3);
 }
+// =====================================================================================================================
+// Pipeline used inside the persistent network kernel (net_kernel.cuh) when the emitter defines PRB_TC:
+//   PRB_TC_BT      sweep instances per tile (UMMA N; 32 / 64 / 128)
+//   PRB_TC_E       epilogue column groups: 4*E epilogue warps (warps 4 .. 4+4E), PRB_TC_BT/E accumulator columns per thread
+//   PRB_TC_NSTAGE  shared-memory ring depth (K slabs in flight)
+//   PRB_TC_KC      K slabs accumulated inside TMEM before the partial sum is promoted to fp32 registers.  The tensor
+//                  core adds into its fp32 accumulator with truncation (measured on B200: K = 8192 gives a relative
+//                  bias of -1.7e-4), so partial sums of KC*32 products are added up by the CUDA cores (round-to-nearest).
+// Roles: warp 0 lane 0 = bulk-copy producer, warp 1 lane 0 = MMA issuer (warp 1 owns the TMEM allocation),
+// warps >= 4 = epilogue (TMEM -> register accumulators -> generated element-wise tail + solver update).
+// Two TMEM accumulator buffers of BT columns alternate between the MMA issuer and the epilogue warps.
+#ifdef PRB_TC
+#define PRB_TC_A_BYTES (128 * PRB_TC_BK * 4)
+#define PRB_TC_B_BYTES (PRB_TC_BT * PRB_TC_BK * 4)
+#define PRB_TC_STAGE_BYTES (2 * PRB_TC_A_BYTES + 2 * PRB_TC_B_BYTES)
+#define PRB_TC_SMEM_BYTES (PRB_TC_NSTAGE * PRB_TC_STAGE_BYTES)
+#define PRB_TC_NCOLS (2 * PRB_TC_BT)
+#define PRB_TC_EPI_WARPS (4 * PRB_TC_E)
+#define PRB_TC_CPT (PRB_TC_BT / PRB_TC_E)
+static_assert(PRB_TC_NCOLS >= 32 && PRB_TC_NCOLS <= 512 && (PRB_TC_NCOLS & (PRB_TC_NCOLS - 1)) == 0, "TMEM columns: power of two in [32, 512]");
+static_assert(PRB_TC_BT % 16 == 0 && PRB_TC_CPT % 8 == 0, "tile shape");
+
+struct PrbTc {
+    unsigned int smem0, bar0, tmem;
+    int s; unsigned int ph;          // shared-memory ring position (producer thread / MMA thread: one copy each)
+    unsigned int buf, uph;           // TMEM accumulator buffer position (MMA thread / epilogue threads)
+    unsigned long long* err;
+    bool ok;
+};
+#define PRB_TC_FULL(T, s)   ((T).bar0 + 8u * (s))
+#define PRB_TC_EMPTY(T, s)  ((T).bar0 + 8u * (PRB_TC_NSTAGE + (s)))
+#define PRB_TC_TFULL(T, b)  ((T).bar0 + 8u * (2 * PRB_TC_NSTAGE + (b)))
+#define PRB_TC_TEMPTY(T, b) ((T).bar0 + 8u * (2 * PRB_TC_NSTAGE + 2 + (b)))
+
+// all threads of the CTA, once, at kernel start
+__device__ __forceinline__ void prb_tc_setup(PrbTc& T, unsigned long long* err) {
+    extern __shared__ __align__(1024) unsigned char prb_tc_smem[];
+    __shared__ __align__(8) unsigned long long bars[2 * PRB_TC_NSTAGE + 4];
+    __shared__ unsigned int tmem_slot;
+    T.smem0 = prb_smem_u32(prb_tc_smem);
+    T.bar0 = prb_smem_u32(bars);
+    T.s = 0; T.ph = 0; T.buf = 0; T.uph = 0; T.err = err; T.ok = true;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PRB_TC_NSTAGE; ++s) { prb_mbar_init(PRB_TC_FULL(T, s), 1); prb_mbar_init(PRB_TC_EMPTY(T, s), 1); }
+        for (int b = 0; b < 2; ++b) { prb_mbar_init(PRB_TC_TFULL(T, b), 1); prb_mbar_init(PRB_TC_TEMPTY(T, b), PRB_TC_EPI_WARPS); }
+        prb_mbar_fence_init();
+    }
+    if (warp == 1) prb_tmem_alloc(prb_smem_u32(&tmem_slot), PRB_TC_NCOLS);
+    prb_tc_fence_before();
+    __syncthreads();
+    prb_tc_fence_after();
+    T.tmem = tmem_slot;
+}
+// all threads, once, at kernel end
+__device__ __forceinline__ void prb_tc_teardown(PrbTc& T) {
+    prb_tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 1) prb_tmem_dealloc(T.tmem, PRB_TC_NCOLS);
+}
+
+// generic-proxy global stores -> visible to later bulk copies (async proxy)
+__device__ __forceinline__ void prb_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---- operand preparation: source vector x[j][NB] (element-major, instance fastest) -> hi / lo K-major tiles
+// [NB/BT][KS][BT x 32] in the canonical layout.  One thread handles 4 consecutive j of one instance: coalesced
+// reads along the instances, one 16-byte store per piece.  Rows j >= m stay zero (buffers are zero-initialised).
+__device__ __forceinline__ void prb_tc_prep(const long long gtid, const long long gsize, const float* x, const int m,
+                                            float* xt_hi, float* xt_lo, const int KS) {
+    const long long total = (long long)((m + 3) >> 2) * PRB_NB;
+    for (long long q = gtid; q < total; q += gsize) {
+        const int j4 = (int)(q / PRB_NB), b = (int)(q - (long long)j4 * PRB_NB);
+        float v[4], h[4], l[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = 4 * j4 + c;
+            v[c] = (j < m) ? x[(long long)j * PRB_NB + b] : 0.0f;
+            prb_tf32_split(v[c], h[c], l[c]);
+        }
+        const int nbk = b / PRB_TC_BT, r = b - nbk * PRB_TC_BT, ks = j4 >> 3, kc = j4 & 7;
+        const long long off = ((long long)nbk * KS + ks) * (PRB_TC_BT * PRB_TC_BK) + (kc * (PRB_TC_BT / 8) + (r >> 3)) * 32 + (r & 7) * 4;
+        *(float4*)(xt_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+        *(float4*)(xt_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+    prb_fence_proxy_async();
+}
+
+// ---- producer (one thread): stream the K slabs of one (row block, instance block) pair through the smem ring.
+// a_* / b_* point at the first slab tile; consecutive slabs are one tile apart.
+__device__ __forceinline__ void prb_tc_produce(PrbTc& T, const float* a_hi, const float* a_lo, const float* b_hi,
+                                               const float* b_lo, const int KS) {
+    for (int ks = 0; ks < KS && T.ok; ++ks) {
+        T.ok = prb_mbar_wait(PRB_TC_EMPTY(T, T.s), T.ph ^ 1u, T.err, 101);
+        if (!T.ok) break;
+        const unsigned int full = PRB_TC_FULL(T, T.s);
+        prb_mbar_expect_tx(full, PRB_TC_STAGE_BYTES);
+        const unsigned int base = T.smem0 + T.s * PRB_TC_STAGE_BYTES;
+        prb_bulk_g2s(base, a_hi + (long long)ks * (128 * PRB_TC_BK), PRB_TC_A_BYTES, full);
+        prb_bulk_g2s(base + PRB_TC_A_BYTES, a_lo + (long long)ks * (128 * PRB_TC_BK), PRB_TC_A_BYTES, full);
+        prb_bulk_g2s(base + 2 * PRB_TC_A_BYTES, b_hi + (long long)ks * (PRB_TC_BT * PRB_TC_BK), PRB_TC_B_BYTES, full);
+        prb_bulk_g2s(base + 2 * PRB_TC_A_BYTES + PRB_TC_B_BYTES, b_lo + (long long)ks * (PRB_TC_BT * PRB_TC_BK), PRB_TC_B_BYTES, full);
+        if (++T.s == PRB_TC_NSTAGE) { T.s = 0; T.ph ^= 1u; }
+    }
+}
+
+// ---- MMA issuer (one thread): KS slabs, promoted every PRB_TC_KC slabs through alternating TMEM buffers
+__device__ __forceinline__ void prb_tc_mma(PrbTc& T, const int KS) {
+    constexpr unsigned int idesc = prb_umma_idesc_tf32(128, PRB_TC_BT);
+    constexpr unsigned int lboA = 128 * 16, lboB = PRB_TC_BT * 16, sbo = 128;
+    for (int ks0 = 0; ks0 < KS && T.ok; ks0 += PRB_TC_KC) {
+        T.ok = prb_mbar_wait(PRB_TC_TEMPTY(T, T.buf), T.uph ^ 1u, T.err, 104);
+        if (!T.ok) break;
+        prb_tc_fence_after();
+        const unsigned int tmem_d = T.tmem + T.buf * PRB_TC_BT;
+        const int ks1 = (ks0 + PRB_TC_KC < KS) ? ks0 + PRB_TC_KC : KS;
+        for (int ks = ks0; ks < ks1; ++ks) {
+            T.ok = prb_mbar_wait(PRB_TC_FULL(T, T.s), T.ph, T.err, 102);
+            if (!T.ok) break;
+            prb_tc_fence_after();
+            const unsigned int base = T.smem0 + T.s * PRB_TC_STAGE_BYTES;
+            const unsigned int sa_hi = base, sa_lo = base + PRB_TC_A_BYTES;
+            const unsigned int sb_hi = base + 2 * PRB_TC_A_BYTES, sb_lo = sb_hi + PRB_TC_B_BYTES;
+#pragma unroll
+            for (int k = 0; k < PRB_TC_BK / 8; ++k) {
+                const unsigned long long dah = prb_umma_smem_desc(sa_hi + k * 2 * lboA, lboA, sbo);
+                const unsigned long long dal = prb_umma_smem_desc(sa_lo + k * 2 * lboA, lboA, sbo);
+                const unsigned long long dbh = prb_umma_smem_desc(sb_hi + k * 2 * lboB, lboB, sbo);
+                const unsigned long long dbl = prb_umma_smem_desc(sb_lo + k * 2 * lboB, lboB, sbo);
+                prb_umma_tf32(tmem_d, dal, dbh, idesc, (ks != ks0 || k != 0) ? 1u : 0u);     // small terms first
+                prb_umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                prb_umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+            }
+            prb_umma_commit(PRB_TC_EMPTY(T, T.s));          // smem slot free once these MMAs have read it
+            if (++T.s == PRB_TC_NSTAGE) { T.s = 0; T.ph ^= 1u; }
+        }
+        prb_umma_commit(PRB_TC_TFULL(T, T.buf));            // partial sum complete -> epilogue
+        T.buf ^= 1u; if (T.buf == 0) T.uph ^= 1u;
+    }
+}
+
+// ---- epilogue warps: add the partial sums of one reduction into this thread's PRB_TC_CPT accumulator columns
+// (row = TMEM lane = 32*q + lane, columns cg*CPT .. +CPT of the instance block)
+__device__ __forceinline__ void prb_tc_accumulate(PrbTc& T, const int KS, float (&acc)[PRB_TC_CPT], const int q, const int cg) {
+    for (int ks0 = 0; ks0 < KS; ks0 += PRB_TC_KC) {
+        bool ok = T.ok && prb_mbar_wait(PRB_TC_TFULL(T, T.buf), T.uph, T.err, 103);
+        ok = __all_sync(0xffffffffu, ok);
+        T.ok = ok;
+        if (!ok) return;
+        prb_tc_fence_after();
+        const unsigned int taddr = T.tmem + ((unsigned int)(q * 32) << 16) + T.buf * PRB_TC_BT + cg * PRB_TC_CPT;
+#pragma unroll
+        for (int c = 0; c < PRB_TC_CPT; c += 8) {
+            float v[8];
+            prb_tmem_ld8(taddr + c, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[c + e] += v[e];
+        }
+        prb_tc_fence_before();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) prb_mbar_arrive(PRB_TC_TEMPTY(T, T.buf));
+        T.buf ^= 1u; if (T.buf == 0) T.uph ^= 1u;
+    }
+}
+#endif  // PRB_TC
 #endif

@@ -36,6 +36,8 @@ class NetKernel:
     evals_per_step: int
     n_phases: int
     kernel_name: str = "prb_integrate_net"
+    smem_bytes: int = 0        # dynamic shared memory (tcgen05 operand ring)
+    tc: Optional[dict] = None  # tcgen05 coupling-GEMM configuration, None = SIMT row reductions
 
 
 class _Emitter:
@@ -240,8 +242,24 @@ class _Emitter:
         raise NotImplementedError(t[0])
 
 
+def tc_config(ir: NetIR, precision: str, n_batch: int, world: int) -> Optional[dict]:
+    """tcgen05 (3xTF32) configuration for the sweep-batched dense couplings of ``ir``, or None when the tensor-core
+    path does not apply: it needs float32, a batch that is a multiple of 32 instances, one GPU and row reductions that
+    are all plain ``dot(W, x)`` contractions."""
+    rows = [r for r in ir.reductions if r.kind == "row"]
+    if precision != "float32" or world != 1 or not rows or any(r.simple is None for r in rows):
+        return None
+    per_group = max(sum(1 for r in rows if (r.phase, r.n) == key) for key in {(r.phase, r.n) for r in rows})
+    e = 2                                               # 8 epilogue warps; <= 64 fp32 accumulator registers per thread
+    bt = next((c for c in (128, 64, 32) if n_batch % c == 0 and per_group * c // e <= 64), None)
+    if bt is None:
+        return None
+    stage = 2 * 128 * 32 * 4 + 2 * bt * 32 * 4
+    return {"bt": bt, "e": e, "nstage": max(2, min(4, (200 * 1024) // stage)), "kc": 8, "block": 128 * (1 + e)}
+
+
 def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequence[int], block: int = 512,
-                    rank: int = 0, world: int = 1, n_batch: int = 1) -> NetKernel:
+                    rank: int = 0, world: int = 1, n_batch: int = 1, tensor_core: bool = False) -> NetKernel:
     if solver not in SOLVER_IDS:
         raise ValueError(f"unknown solver `{solver}`")
     f32 = precision == "float32"
@@ -254,6 +272,16 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     if nb > 1 and nb % B_T:
         raise ValueError(f"batched network kernels need a multiple of {B_T} instances (pad the sweep), got {nb}")
     em = _Emitter(ir, f32, rank, world, nb)
+    tc = tc_config(ir, precision, nb, world) if (tensor_core and nb > 1) else None
+    if tensor_core and tc is None:
+        raise UnsupportedModelError("the tcgen05 coupling path needs a float32 model, a batch that is a multiple of 32 "
+                                    "instances, one GPU and dense dot(W, x) couplings only")
+    if tc is not None:
+        block = tc["block"]
+    tc_consts: Dict[str, Tuple[int, int, int]] = {}     # W array -> (hi offset, lo offset, K slabs) inside consts
+    tc_xt: Dict[str, Tuple[int, int]] = {}              # source pointer expr -> (hi, lo) element offsets inside work
+    tc_work = 0
+    tc_extra: List[Tuple[int, np.ndarray]] = []         # (const offset, tiled hi / lo image)
     # multi-GPU: 2-d constants (connectivity) are row-sharded -> re-pack the constant space with shard sizes
     const_size = ir.const_size
     if world > 1:
@@ -312,7 +340,84 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
         for n in lengths:
             reds = [r for r in rows_p if r.n == n]
             sts = [s for s in stores_p if s.n == n]
-            if reds and nb > 1:
+            if reds and nb > 1 and tc is not None:
+                # sweep-batched dense coupling on the tensor cores: R[i, b] = sum_j W[i, j] x[j, b] as 128 x BT tiles of
+                # tcgen05.mma kind::tf32 (3xTF32), element-wise tail + solver update fused into the TMEM epilogue
+                cur = (p, n, True)
+                BT, CPT = tc["bt"], tc["bt"] // tc["e"]
+                n_mb, n_nbk = (n + 127) // 128, nb // BT
+                tc_base = (work_size + 6 * ns) * nb
+                plan = []
+                for r in reds:
+                    wname = r.simple[0]
+                    KS = (r.m + 31) // 32
+                    if wname not in tc_consts:
+                        from .tcgemm import split_tf32, tile_operand
+                        w_hi, w_lo = split_tf32(np.asarray(ir.arrays[wname].init, dtype=np.float32).reshape(r.n, r.m))
+                        t_hi, t_lo = tile_operand(w_hi, 128), tile_operand(w_lo, 128)
+                        tc_consts[wname] = (const_size, const_size + t_hi.size, KS)
+                        tc_extra.append((const_size, t_hi))
+                        tc_extra.append((const_size + t_hi.size, t_lo))
+                        const_size += t_hi.size + t_lo.size
+                    xp = em.source_ptr(r)
+                    if xp not in tc_xt:
+                        sz = nb * KS * 32
+                        tc_xt[xp] = (tc_base + tc_work, tc_base + tc_work + sz, r.m, KS)
+                        tc_work += 2 * sz
+                    plan.append((r, tc_consts[wname], tc_xt[xp], KS))
+                body.append(f"    // tcgen05 coupling GEMM: {len(reds)} reduction(s), {n_mb} row block(s) x {n_nbk} instance block(s) of {BT}, n = {n}")
+                for xp, (o_hi, o_lo, m_src, KS) in tc_xt.items():
+                    if any(pl[2][0] == o_hi for pl in plan):
+                        body.append(f"    prb_tc_prep(C.gtid, C.gsize, {xp}, {m_src}, C.work + {o_hi}LL, C.work + {o_lo}LL, {KS});")
+                body.append("    prb_grid_barrier(C);")
+                body.append("    {")
+                body.append("        const int warp = (int)(threadIdx.x >> 5);")
+                body.append(f"        for (int tile = (int)blockIdx.x; tile < {n_mb * n_nbk}; tile += (int)gridDim.x) {{")
+                body.append(f"            const int mbk = tile / {n_nbk}, nbk = tile - mbk * {n_nbk};")
+                body.append("            if (warp == 0) {")
+                body.append("                if (C.lane == 0) {")
+                body.append("                    prb_fence_proxy_async();")
+                for r, (a_hi, a_lo, _), (x_hi, x_lo, _, _), KS in plan:
+                    body.append(f"                    prb_tc_produce(C.tc, C.consts + {a_hi}LL + (long long)mbk * {KS * 4096}LL, "
+                                f"C.consts + {a_lo}LL + (long long)mbk * {KS * 4096}LL, "
+                                f"C.work + {x_hi}LL + (long long)nbk * {KS * BT * 32}LL, "
+                                f"C.work + {x_lo}LL + (long long)nbk * {KS * BT * 32}LL, {KS});")
+                body.append("                }")
+                body.append("            } else if (warp == 1) {")
+                body.append("                if (C.lane == 0) {")
+                for r, _, _, KS in plan:
+                    body.append(f"                    prb_tc_mma(C.tc, {KS});")
+                body.append("                }")
+                body.append("            } else if (warp >= 4) {")
+                body.append("                const int q = warp & 3, cg = (warp - 4) >> 2;")
+                for r, _, _, KS in plan:
+                    body.append(f"                float acc{r.id}[{CPT}];")
+                    body.append("#pragma unroll")
+                    body.append(f"                for (int e = 0; e < {CPT}; ++e) acc{r.id}[e] = 0.0f;")
+                    body.append(f"                prb_tc_accumulate(C.tc, {KS}, acc{r.id}, q, cg);")
+                body.append(f"                const long long i = (long long)mbk * 128 + q * 32 + C.lane;")
+                body.append(f"                if (i < {n}LL) {{")
+                body.append("#pragma unroll")
+                body.append(f"                    for (int e = 0; e < {CPT}; ++e) {{")
+                body.append(f"                        const int b = nbk * {BT} + cg * {CPT} + e;")
+                for r, _, _, _ in plan:
+                    body.append(f"                        const real red{r.id} = acc{r.id}[e];")
+                emitted = set()
+                for r in reds:
+                    need = any(_uses_red(g, em, s_.node, r.id) and (s_.phase, s_.n) != (p, n) for s_ in ir.stores) or \
+                        any(_uses_red(g, em, x.node, r.id) for x in ir.reductions)
+                    if need:
+                        body.append(f"                        prb_st_work(C, {em.bidx(f'{em.red_work[r.id].offset}LL + i')}, red{r.id});")
+                nodes = em.order([s_.node for s_ in sts])
+                body.extend(em.emit_nodes(nodes, cur, emitted, "                        "))
+                for s_ in sts:
+                    body.append("                        " + em.store_stmt(s_, cur, "STAGE"))
+                body.append("                    }")
+                body.append("                }")
+                body.append("            }")
+                body.append("        }")
+                body.append("    }")
+            elif reds and nb > 1:
                 # batched sweep: one warp task = R_T rows x B_T instances; W rows are read once per B_T instances
                 cur = (p, n, True)
                 lo, hi = em.bounds(n)
@@ -441,6 +546,13 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     src.append("struct PrbNet;")
     src.append("__device__ __forceinline__ void prb_net_init_heads(PrbNet& C, long long eval0);")
     src.append("__device__ __forceinline__ void prb_net_advance_heads(PrbNet& C);")
+    if tc is not None:
+        src.append("#define PRB_TC 1")
+        src.append(f"#define PRB_TC_BT {tc['bt']}")
+        src.append(f"#define PRB_TC_E {tc['e']}")
+        src.append(f"#define PRB_TC_NSTAGE {tc['nstage']}")
+        src.append(f"#define PRB_TC_KC {tc['kc']}")
+        src.append(read_template("tc_gemm.cuh"))
     src.append(read_template("net_kernel.cuh"))
     heads_i, heads_a = [], []
     for k, a in enumerate(rings):
@@ -469,14 +581,21 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 buf[a.offset:a.offset + v.size] = v.reshape(-1).astype(dtype)
         return buf
 
+    const_buf = pack("const", const_size, real)
+    for off, img in tc_extra:
+        const_buf[off:off + img.size] = img
     iconst = pack("iconst", iconst_size, np.int32)
     if not all_state:
         iconst[obs_off:obs_off + obs.size] = obs
     evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4}[solver]
-    return NetKernel("\n".join(src) + "\n", ns, int(obs.size), (work_size + 6 * ns) * nb, work_size,
-                     pack("work", work_size, real), pack("const", const_size, real), iconst,
+    smem = 0
+    if tc is not None:
+        smem = tc["nstage"] * (2 * 128 * 32 * 4 + 2 * tc["bt"] * 32 * 4)
+        tc = dict(tc, smem=smem, xt_elems=tc_work)
+    return NetKernel("\n".join(src) + "\n", ns, int(obs.size), (work_size + 6 * ns) * nb + tc_work, work_size,
+                     pack("work", work_size, real), const_buf, iconst,
                      pack("ring", ir.ring_size, real), pack("table", ir.table_size, real), block, solver, precision,
-                     evals, n_phases)
+                     evals, n_phases, smem_bytes=smem, tc=tc)
 
 
 def _uses_red(g, em: _Emitter, node: int, rid: int) -> bool:

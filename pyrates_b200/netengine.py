@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import runtime as rt
-from .emit_net import NetKernel, emit_net_kernel
+from .emit_net import NetKernel, emit_net_kernel, tc_config
 from .engine import FIXED_STEP_SOLVERS, n_steps_for
 from .netcompile import NetIR, netcompile
 from .program import Program
@@ -24,9 +24,11 @@ __all__ = ["NetworkModel", "NetworkSession", "build_check", "smoke_check"]
 class NetworkModel:
     def __init__(self, prog: Program, *, solver: str = "euler", observers: Optional[Sequence[int]] = None,
                  block: int = 512, fmad: bool = True, blocks_per_sm: int = 1, rank: int = 0, world: int = 1,
-                 separable: bool = True, n_batch: int = 1, sweep: Sequence[str] = ()):
-        """``n_batch`` > 1 integrates that many sweep instances of the network together (shared connectivity, one
-        pass over W per 8 instances); ``sweep`` names the scalar / uniform-vector arguments that vary per instance."""
+                 separable: bool = True, n_batch: int = 1, sweep: Sequence[str] = (), tensor_core="auto"):
+        """``n_batch`` > 1 integrates that many sweep instances of the network together (shared connectivity);
+        ``sweep`` names the scalar / uniform-vector arguments that vary per instance.  ``tensor_core``: run the batched
+        dense couplings as tcgen05 3xTF32 GEMMs (float32 models, batch a multiple of 32; "auto" = whenever that
+        applies), otherwise as fp32/fp64 FMA register tiles (one pass over W per 8 instances)."""
         if solver not in FIXED_STEP_SOLVERS:
             raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
                                       f"Supported solvers: {list(FIXED_STEP_SOLVERS)}.")
@@ -40,9 +42,11 @@ class NetworkModel:
         self.param_defaults = np.array([d for _, d in self.ir.params], dtype=np.float64)
         self.observers = list(range(prog.n_state)) if observers is None else [int(o) for o in observers]
         self.rank, self.world = int(rank), int(world)
+        if tensor_core == "auto":
+            tensor_core = self.n_batch > 1 and tc_config(self.ir, self.precision, self.n_batch, self.world) is not None
         self.kernel: NetKernel = emit_net_kernel(self.ir, solver=solver, precision=self.precision,
                                                  observers=self.observers, block=block, rank=self.rank, world=self.world,
-                                                 n_batch=self.n_batch)
+                                                 n_batch=self.n_batch, tensor_core=bool(tensor_core))
         self.fmad = fmad
         self.blocks_per_sm = blocks_per_sm
         self._module: Optional[rt.Module] = None
@@ -178,7 +182,7 @@ class NetworkSession:
         a.peers = self.d_peers.ptr if self.d_peers is not None else None
         a.rank, a.world = self.m.rank, self.m.world
         self.m.module.run(k.kernel_name, a, block=k.block, grid=self.sm_count * self.m.blocks_per_sm,
-                          cooperative=True, stream=self.stream)
+                          smem=k.smem_bytes, cooperative=True, stream=self.stream)
         self.steps_done += int(n_steps)
         self.samples_done += new_samples
         return new_samples
@@ -190,7 +194,10 @@ class NetworkSession:
         if self.stream is not None:
             self.stream.synchronize()
         if words[2] != 0:
-            raise rt.CudaBackendError("network kernel barrier timed out (a peer rank did not arrive)")
+            what = {101: "tcgen05 producer (smem slot never freed)", 102: "tcgen05 MMA issuer (operand tile never arrived)",
+                    103: "tcgen05 epilogue (accumulator never completed)", 104: "tcgen05 MMA issuer (TMEM buffer never drained)"
+                    }.get(int(words[2]), "grid barrier (a CTA or peer rank did not arrive)")
+            raise rt.CudaBackendError(f"network kernel wait timed out: {what}")
 
     def download(self) -> np.ndarray:
         out = np.empty((self.n_samples, self.m.kernel.n_obs, self.B), dtype=self.m.real)

@@ -54,3 +54,45 @@ def test_multi_gpu_variants_compile_and_shard_constants(world):
 def test_legacy_ring_gather_is_rejected_by_network_model():
     with pytest.raises(UnsupportedModelError):
         netcompile(Program.load(golden_path("net10")))
+
+
+@pytest.mark.parametrize("name,sweep,nb,bt", [("wc_n300_f32", ["r_ext"], 256, 128), ("qsfa_both_n96_f32", ["I_ext"], 128, 64),
+                                              ("kuramoto_n128_f32", ["s_ext"], 96, 32)])
+def test_tensor_core_sweep_kernels_compile(name, sweep, nb, bt):
+    """float32 sweep-batched networks take the tcgen05 path: the cubin holds UTC*MMA / LDTM / UBLKCP (checked in SASS
+    when cuobjdump is available) and the connectivity is packed as hi / lo K-major tiles."""
+    os.environ["PRB_CACHE_DIR"] = "off"
+    m = NetworkModel(Program.load(golden_path(name)), solver="heun", n_batch=nb, sweep=sweep)
+    k = m.kernel
+    assert k.tc is not None and k.tc["bt"] == bt and k.smem_bytes == k.tc["smem"] > 48 * 1024
+    assert "tcgen05.mma.cta_group::1.kind::tf32" in k.source and "prb_tc_accumulate" in k.source
+    mod = rt.compile_module(k.source, f"{name}_tc.cu")
+    assert mod.cubin[:4] == b"\x7fELF"
+    import shutil, subprocess, tempfile
+    if shutil.which("cuobjdump"):
+        with tempfile.NamedTemporaryFile(suffix=".cubin") as f:
+            f.write(mod.cubin)
+            f.flush()
+            sass = subprocess.run(["cuobjdump", "-sass", f.name], capture_output=True, text=True).stdout
+        assert "UTCHMMA" in sass and "LDTM" in sass and "UBLKCP" in sass
+
+
+def test_tensor_core_path_is_float32_only():
+    prog = Program.load(golden_path("wc_n128"))
+    assert NetworkModel(prog, solver="euler", n_batch=128, sweep=["r_ext"]).kernel.tc is None      # fp64 -> FMA tiles
+    with pytest.raises(UnsupportedModelError):
+        NetworkModel(prog, solver="euler", n_batch=128, sweep=["r_ext"], tensor_core=True)
+
+
+def test_operand_tiling_roundtrip_and_split():
+    from pyrates_b200 import tcgemm
+    rng = np.random.default_rng(0)
+    m = rng.normal(size=(300, 70)).astype(np.float32)
+    t = tcgemm.tile_operand(m, 128)
+    assert t.size == 3 * 3 * 128 * 32
+    assert np.array_equal(tcgemm.untile_operand(t, 300, 70, 128), m)
+    r, k = 37, 21                                              # documented offset formula (tc_gemm.cuh)
+    assert t[((k // 4) * 16 + r // 8) * 32 + (r % 8) * 4 + k % 4] == m[r, k]
+    hi, lo = tcgemm.split_tf32(m)
+    assert np.array_equal(hi + lo, m) and not np.any(hi.view(np.uint32) & 0x1FFF)
+    assert np.max(np.abs(lo)) <= np.max(np.abs(m)) * 2.0 ** -10

@@ -102,3 +102,38 @@ def test_batched_network_sweep_matches_per_instance_oracle(gpu, name, sweep, sol
             args[names.index(nme)] = np.full(v.shape, params[k, b], dtype=v.dtype) if v.ndim else np.asarray(params[k, b], dtype=v.dtype)[()]
         rec, _ = orc.run(f, args, r["T"], r["dt"], r["dts"], solver)
         assert traj_rel_err(out[:, :, b], rec) <= RTOL[prog.float_precision], (name, b)
+
+
+@pytest.mark.parametrize("name,sweep,solver,B", [
+    ("wc_n128_f32", ["r_ext", "k"], "rk4", 128),             # one tile, one K chunk
+    ("wc_n300_f32", ["r_ext"], "heun", 256),                 # 3 row blocks (padded), 2 instance blocks, 2 K chunks
+    ("qsfa_both_n96_f32", ["I_ext", "I_ext_v1"], "heun", 128),   # two matrices, ring + cascade sources, BT = 64
+    ("kuramoto_n128_f32", ["s_ext"], "euler", 64),           # separable pair coupling: two GEMMs over one W
+    ("wc_n300_f32", ["r_ext"], "euler", 32),
+])
+def test_tensor_core_network_sweep_matches_per_instance_oracle(gpu, name, sweep, solver, B):
+    """float32 grid_search over a network on the tcgen05 path (3xTF32 coupling GEMM, fused tail): every sampled
+    instance matches the oracle integrating that parameter set alone, and the FMA-tile path, within rel 1e-4."""
+    fx = orc.load_fixture(golden_path(name))
+    prog = Program.load(golden_path(name))
+    r = fx["run"]
+    rng = np.random.default_rng(7)
+    m = NetworkModel(prog, solver=solver, n_batch=B, sweep=sweep)
+    assert m.kernel.tc is not None
+    params = m.param_defaults[:, None] + rng.uniform(-0.3, 0.6, (len(sweep), B))
+    before = rt.launch_count()
+    out, y_final = m.run(r["T"], r["dt"], r["dts"], params=params)
+    assert rt.launch_count() == before + 1
+    assert np.all(np.isfinite(out))
+    simt, _ = NetworkModel(prog, solver=solver, n_batch=B, sweep=sweep, tensor_core=False).run(r["T"], r["dt"], r["dts"], params=params)
+    f = orc.build_vector_field(prog.source())
+    names = [a.name for a in prog.args]
+    for b in sorted({0, 1, B // 2 - 1, B // 2, B - 1}):
+        args = [np.array(a.value, copy=True) for a in prog.args]
+        args[0] = args[0][()]
+        for k, nme in enumerate(sweep):
+            v = args[names.index(nme)]
+            args[names.index(nme)] = np.full(v.shape, params[k, b], dtype=v.dtype) if v.ndim else np.asarray(params[k, b], dtype=v.dtype)[()]
+        rec, _ = orc.run(f, args, r["T"], r["dt"], r["dts"], solver)
+        assert traj_rel_err(out[:, :, b], rec) <= RTOL["float32"], (name, b)
+        assert traj_rel_err(out[:, :, b], simt[:, :, b]) <= RTOL["float32"], (name, b)
