@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--sweep", default="", help="comma-separated swept scalar arguments (batch > 1)")
     ap.add_argument("--precision", default="float64", choices=["float64", "float32"])
     ap.add_argument("--tensor-core", default="auto", choices=["auto", "off"])
+    ap.add_argument("--tc-max-acc", type=int, default=128, help="fp32 accumulator registers per epilogue thread (128 -> 256-wide tiles)")
     a = ap.parse_args()
     from pyrates_b200 import runtime as rt
     from pyrates_b200.netengine import NetworkModel
@@ -151,7 +152,7 @@ def main():
     dt = 1e-3
     sweep = [x for x in a.sweep.split(",") if x]
     m = NetworkModel(prog, solver=a.solver, observers=[0], block=a.block, rank=rank, world=world, n_batch=a.batch,
-                     sweep=sweep, tensor_core="auto" if a.tensor_core == "auto" else False)
+                     sweep=sweep, tensor_core="auto" if a.tensor_core == "auto" else False, tc_max_acc=a.tc_max_acc)
     params = None
     if sweep:
         params = m.param_defaults[:, None] * (1.0 + 0.1 * np.random.default_rng(3).uniform(-1, 1, (len(sweep), a.batch))) \

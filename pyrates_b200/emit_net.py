@@ -242,7 +242,7 @@ class _Emitter:
         raise NotImplementedError(t[0])
 
 
-def tc_config(ir: NetIR, precision: str, n_batch: int, world: int) -> Optional[dict]:
+def tc_config(ir: NetIR, precision: str, n_batch: int, world: int, tc_max_acc: int = 128) -> Optional[dict]:
     """tcgen05 (3xTF32) configuration for the sweep-batched dense couplings of ``ir``, or None when the tensor-core
     path does not apply: it needs float32, a batch that is a multiple of 32 instances, one GPU and row reductions that
     are all plain ``dot(W, x)`` contractions."""
@@ -251,7 +251,8 @@ def tc_config(ir: NetIR, precision: str, n_batch: int, world: int) -> Optional[d
         return None
     per_group = max(sum(1 for r in rows if (r.phase, r.n) == key) for key in {(r.phase, r.n) for r in rows})
     e = 2                                               # 8 epilogue warps; <= 64 fp32 accumulator registers per thread
-    bt = next((c for c in (128, 64, 32) if n_batch % c == 0 and per_group * c // e <= 64), None)
+    limit = tc_max_acc if per_group == 1 else min(tc_max_acc, 64)     # several live accumulator sets: keep the tail spill-free
+    bt = next((c for c in (256, 128, 64, 32) if n_batch % c == 0 and per_group * c // e <= limit), None)
     if bt is None:
         return None
     stage = 2 * 128 * 32 * 4 + 2 * bt * 32 * 4
@@ -259,7 +260,8 @@ def tc_config(ir: NetIR, precision: str, n_batch: int, world: int) -> Optional[d
 
 
 def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequence[int], block: int = 512,
-                    rank: int = 0, world: int = 1, n_batch: int = 1, tensor_core: bool = False) -> NetKernel:
+                    rank: int = 0, world: int = 1, n_batch: int = 1, tensor_core: bool = False,
+                    tc_max_acc: int = 128) -> NetKernel:
     if solver not in SOLVER_IDS:
         raise ValueError(f"unknown solver `{solver}`")
     f32 = precision == "float32"
@@ -272,7 +274,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     if nb > 1 and nb % B_T:
         raise ValueError(f"batched network kernels need a multiple of {B_T} instances (pad the sweep), got {nb}")
     em = _Emitter(ir, f32, rank, world, nb)
-    tc = tc_config(ir, precision, nb, world) if (tensor_core and nb > 1) else None
+    tc = tc_config(ir, precision, nb, world, tc_max_acc) if (tensor_core and nb > 1) else None
     if tensor_core and tc is None:
         raise UnsupportedModelError("the tcgen05 coupling path needs a float32 model, a batch that is a multiple of 32 "
                                     "instances, one GPU and dense dot(W, x) couplings only")
@@ -369,6 +371,20 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 for xp, (o_hi, o_lo, m_src, KS) in tc_xt.items():
                     if any(pl[2][0] == o_hi for pl in plan):
                         body.append(f"    prb_tc_prep(C.gtid, C.gsize, {xp}, {m_src}, C.work + {o_hi}LL, C.work + {o_lo}LL, {KS});")
+                # stores that do not consume a coupling sum of this group run thread-per-(element, instance) on the
+                # whole grid (coalesced along the instances); only the dependent tail is fused into the TMEM epilogue
+                rids = {r.id for r in reds}
+                free_sts = [s_ for s_ in sts if not any(_uses_red(g, em, s_.node, rid) for rid in rids)]
+                sts = [s_ for s_ in sts if s_ not in free_sts]
+                if free_sts:
+                    cur_e = (p, n, False)
+                    emitted_e: Set[int] = set()
+                    body.append(f"    for (long long q = C.gtid; q < {n * nb}LL; q += C.gsize) {{   // stores independent of the coupling, n = {n}")
+                    body.append(f"        const long long i = q / {nb}; const int b = (int)(q - i * {nb});")
+                    body.extend(em.emit_nodes(em.order([s_.node for s_ in free_sts]), cur_e, emitted_e, "        "))
+                    for s_ in free_sts:
+                        body.append("        " + em.store_stmt(s_, cur_e, "STAGE"))
+                    body.append("    }")
                 body.append("    prb_grid_barrier(C);")
                 body.append("    {")
                 body.append("        const int warp = (int)(threadIdx.x >> 5);")

@@ -56,7 +56,7 @@ def test_legacy_ring_gather_is_rejected_by_network_model():
         netcompile(Program.load(golden_path("net10")))
 
 
-@pytest.mark.parametrize("name,sweep,nb,bt", [("wc_n300_f32", ["r_ext"], 256, 128), ("qsfa_both_n96_f32", ["I_ext"], 128, 64),
+@pytest.mark.parametrize("name,sweep,nb,bt", [("wc_n300_f32", ["r_ext"], 256, 256), ("wc_n300_f32", ["r_ext"], 384, 128), ("qsfa_both_n96_f32", ["I_ext"], 128, 64),
                                               ("kuramoto_n128_f32", ["s_ext"], 96, 32)])
 def test_tensor_core_sweep_kernels_compile(name, sweep, nb, bt):
     """float32 sweep-batched networks take the tcgen05 path: the cubin holds UTC*MMA / LDTM / UBLKCP (checked in SASS

@@ -13,7 +13,8 @@ from pyrates_b200.program import Program
 
 pytestmark = pytest.mark.gpu
 
-SKIP = {"kuramoto_n128", "qsfa_both_n96", "wc_n128", "wc_n128_f32", "jrc_grid_b1024"}      # network-mode fixtures
+SKIP = {"kuramoto_n128", "qsfa_both_n96", "wc_n128", "wc_n128_f32", "jrc_grid_b1024", "wc_n300_f32",
+        "qsfa_both_n96_f32", "kuramoto_n128_f32"}                                             # network-mode fixtures
 NAMES = [n for n in golden_names() if n not in SKIP]
 SOLVERS = ["euler", "heun", "heun_true", "rk4"]
 

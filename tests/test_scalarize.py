@@ -9,7 +9,8 @@ from oracle import numpy_oracle as orc
 from pyrates_b200.program import Program
 from pyrates_b200.scalarize import UnsupportedModelError, scalarize
 
-LARGE = {"kuramoto_n128", "qsfa_both_n96", "wc_n128", "wc_n128_f32", "jrc_grid_b1024"}
+LARGE = {"kuramoto_n128", "qsfa_both_n96", "wc_n128", "wc_n128_f32", "jrc_grid_b1024", "wc_n300_f32", "qsfa_both_n96_f32",
+         "kuramoto_n128_f32"}
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names() if n not in LARGE])
