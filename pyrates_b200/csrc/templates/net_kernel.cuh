@@ -306,6 +306,194 @@ __device__ __forceinline__ real prb_tile_pick(const real (&acc)[R][BT], const in
     return v;
 }
 
+// ---- sweep-batched dense coupling on the FMA pipes (fp64 models, and fp32 batches the tcgen05 path does not take):
+// R[i][b] = sum_j W[i][j] * x[j][b] for all sweep instances b that share the connectivity — a GEMM [n x m] x [m x NB].
+// CTA tile = 128 rows x TN instances (TN = 32 * CB), K slabs of 16 double-buffered in shared memory (global -> registers
+// -> smem prefetch of slab s+1 overlaps the FMAs of slab s, one __syncthreads per slab).  16 warps as 4 (rows) x 4
+// (instances); each thread owns an 8 x CB register tile whose rows / instances are INTERLEAVED across the lanes
+// (row = 4 r + lane/8, instance = 8 c + lane%8): every shared-memory read is a scalar load of 4 (8) consecutive words
+// broadcast inside ONE wavefront — ncu showed the contiguous-tile version bound by 128-bit LDS wavefronts
+// (4 per quarter-warp, 537 M bank conflicts) at 42 % of the fp64 pipe.
+// Results go to the reduction's work array [i][NB]; the element-wise tail runs as a thread-per-(element, instance)
+// phase behind a grid barrier.  Needs blockDim.x == 512.
+#define PRB_GT_M 128
+#define PRB_GT_K 16
+#define PRB_GT_PAD (sizeof(real) == 8 ? 1 : 2)      // As row padding: conflict-free transposing stores
+// fp64 variant on the tensor cores: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) runs at the full fp64 rate on B200 (measured
+// 36.8 TFLOP/s vs 34.1 for a pure DFMA loop, scripts/dmma_probe.py) with 8x fewer math instructions and 6x fewer
+// shared-memory reads per FMA than 8 x 4 register tiles.  (tcgen05 has no fp64 kind: this is the only tensor path for
+// the parity precision.)  Warp tile 32 rows x 8*CB instances = 4 x CB fragments; smem: A [row][k] (row stride 20) and
+// x [k][inst] (row stride TN + 4) make every fragment load conflict-free.
+#define PRB_GD_LDA 20
+template <int CB>
+__device__ __forceinline__ void prb_gemm_batch_dmma(const PrbNet& C, const double* __restrict__ W, const long long row0, const int n_rows,
+                                                    const int m, const double* x, const long long out_off) {
+    constexpr int TN = 32 * CB, LDX = TN + 4;
+    extern __shared__ __align__(16) unsigned char prb_dyn_smem[];
+    double (*As)[PRB_GT_M][PRB_GD_LDA] = (double (*)[PRB_GT_M][PRB_GD_LDA])prb_dyn_smem;                                     // [2][row][k]
+    double (*Xs)[PRB_GT_K][LDX] = (double (*)[PRB_GT_K][LDX])(prb_dyn_smem + 2 * PRB_GT_M * PRB_GD_LDA * sizeof(double));   // [2][k][inst]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;                      // fragment coordinates: group id, thread in group
+    const int wr0 = (warp >> 2) * 32, wc0 = (warp & 3) * (TN / 4);
+    const int a_row = tid >> 2, a_k = (tid & 3) * 4;
+    const int x_k = tid >> 5;
+    const int n_mb = (n_rows + PRB_GT_M - 1) / PRB_GT_M, n_nb = PRB_NB / TN, KS = (m + PRB_GT_K - 1) / PRB_GT_K;
+    const bool w_vec = (m & 3) == 0 && (((unsigned long long)W) & 15ULL) == 0;
+    for (int tile = blockIdx.x; tile < n_mb * n_nb; tile += gridDim.x) {
+        const int mb = tile / n_nb, nbk = tile - mb * n_nb;
+        const int i0 = mb * PRB_GT_M, b0 = nbk * TN;
+        double acc[4][CB][2];
+#pragma unroll
+        for (int fr = 0; fr < 4; ++fr)
+#pragma unroll
+            for (int fc = 0; fc < CB; ++fc) acc[fr][fc][0] = acc[fr][fc][1] = 0.0;
+        double pa[4], px[CB];
+        auto load_global = [&](const int s) {
+            const int k0 = s * PRB_GT_K;
+            const bool row_ok = (i0 + a_row) < n_rows;
+            const double* wp = W + (long long)(i0 + a_row) * m + k0 + a_k;
+            if (row_ok && w_vec && k0 + a_k + 3 < m) {
+                const double2 u = prb_ld_stream((const double2*)wp), v = prb_ld_stream((const double2*)wp + 1);
+                pa[0] = u.x; pa[1] = u.y; pa[2] = v.x; pa[3] = v.y;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) pa[c] = (row_ok && k0 + a_k + c < m) ? __ldg(wp + c) : 0.0;
+            }
+            const bool k_ok = (k0 + x_k) < m;
+            const double* xp = x + (long long)(k0 + x_k) * PRB_NB + b0 + lane;
+#pragma unroll
+            for (int c = 0; c < CB; ++c) px[c] = k_ok ? xp[32 * c] : 0.0;
+        };
+        auto store_smem = [&](const int buf) {
+            *(double2*)&As[buf][a_row][a_k] = make_double2(pa[0], pa[1]);
+            *(double2*)&As[buf][a_row][a_k + 2] = make_double2(pa[2], pa[3]);
+#pragma unroll
+            for (int c = 0; c < CB; ++c) Xs[buf][x_k][lane + 32 * c] = px[c];
+        };
+        load_global(0);
+        __syncthreads();
+        store_smem(0);
+        __syncthreads();
+        for (int s = 0; s < KS; ++s) {
+            const int buf = s & 1;
+            if (s + 1 < KS) load_global(s + 1);
+#pragma unroll
+            for (int kq = 0; kq < PRB_GT_K / 4; ++kq) {
+                double a[4], bq[CB];
+#pragma unroll
+                for (int fr = 0; fr < 4; ++fr) a[fr] = As[buf][wr0 + 8 * fr + g][4 * kq + t4];
+#pragma unroll
+                for (int fc = 0; fc < CB; ++fc) bq[fc] = Xs[buf][4 * kq + t4][wc0 + 8 * fc + g];
+#pragma unroll
+                for (int fr = 0; fr < 4; ++fr)
+#pragma unroll
+                    for (int fc = 0; fc < CB; ++fc)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                     : "+d"(acc[fr][fc][0]), "+d"(acc[fr][fc][1]) : "d"(a[fr]), "d"(bq[fc]));
+            }
+            if (s + 1 < KS) store_smem(buf ^ 1);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int fr = 0; fr < 4; ++fr) {
+            const int ir = i0 + wr0 + 8 * fr + g;
+            if (ir < n_rows) {
+#pragma unroll
+                for (int fc = 0; fc < CB; ++fc) {
+                    const long long o = (out_off + row0 + ir) * PRB_NB + b0 + wc0 + 8 * fc + 2 * t4;
+                    prb_st_work(C, o, acc[fr][fc][0]);
+                    prb_st_work(C, o + 1, acc[fr][fc][1]);
+                }
+            }
+        }
+    }
+}
+
+template <int CB>
+__device__ __forceinline__ void prb_gemm_batch(const PrbNet& C, const real* __restrict__ W, const long long row0, const int n_rows,
+                                               const int m, const real* x, const long long out_off) {
+    constexpr int TN = 32 * CB;
+    constexpr int LDA = PRB_GT_M + PRB_GT_PAD;
+    if constexpr (sizeof(real) == 8) { prb_gemm_batch_dmma<CB>(C, (const double*)W, row0, n_rows, m, (const double*)x, out_off); return; }
+    extern __shared__ __align__(16) unsigned char prb_dyn_smem[];
+    real (*As)[PRB_GT_K][LDA] = (real (*)[PRB_GT_K][LDA])prb_dyn_smem;                                    // [2][k][row]
+    real (*Xs)[PRB_GT_K][TN] = (real (*)[PRB_GT_K][TN])(prb_dyn_smem + 2 * PRB_GT_K * LDA * sizeof(real));   // [2][k][inst]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ri0 = (warp >> 2) * 32 + (lane >> 3);              // this thread's rows inside the tile: ri0 + 4 r
+    const int cb0 = (warp & 3) * (TN / 4) + (lane & 7);          // its instances: cb0 + 8 c
+    const int a_row = tid >> 2, a_k = (tid & 3) * 4;             // global -> smem: 4 consecutive k of one W row
+    const int x_k = tid >> 5;                                    //                 instances lane, lane + 32, .. of one source
+    const int n_mb = (n_rows + PRB_GT_M - 1) / PRB_GT_M, n_nb = PRB_NB / TN, KS = (m + PRB_GT_K - 1) / PRB_GT_K;
+    const bool w_vec = (m & 3) == 0 && (((unsigned long long)W) & 15ULL) == 0;
+    for (int tile = blockIdx.x; tile < n_mb * n_nb; tile += gridDim.x) {
+        const int mb = tile / n_nb, nbk = tile - mb * n_nb;
+        const int i0 = mb * PRB_GT_M, b0 = nbk * TN;
+        real acc[8][CB];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < CB; ++c) acc[r][c] = (real)0;
+        real pa[4], px[CB];
+        auto load_global = [&](const int s) {
+            const int k0 = s * PRB_GT_K;
+            const bool row_ok = (i0 + a_row) < n_rows;
+            const real* wp = W + (long long)(i0 + a_row) * m + k0 + a_k;
+            if (row_ok && w_vec && k0 + a_k + 3 < m) {
+                if (sizeof(real) == 8) {
+                    const double2 u = prb_ld_stream((const double2*)wp), v = prb_ld_stream((const double2*)wp + 1);
+                    pa[0] = (real)u.x; pa[1] = (real)u.y; pa[2] = (real)v.x; pa[3] = (real)v.y;
+                } else {
+                    const float4 u = prb_ld_stream((const float4*)wp);
+                    pa[0] = (real)u.x; pa[1] = (real)u.y; pa[2] = (real)u.z; pa[3] = (real)u.w;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) pa[c] = (row_ok && k0 + a_k + c < m) ? __ldg(wp + c) : (real)0;
+            }
+            const bool k_ok = (k0 + x_k) < m;
+            const real* xp = x + (long long)(k0 + x_k) * PRB_NB + b0 + lane;
+#pragma unroll
+            for (int c = 0; c < CB; ++c) px[c] = k_ok ? xp[32 * c] : (real)0;
+        };
+        auto store_smem = [&](const int buf) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) As[buf][a_k + c][a_row] = pa[c];
+#pragma unroll
+            for (int c = 0; c < CB; ++c) Xs[buf][x_k][lane + 32 * c] = px[c];
+        };
+        load_global(0);
+        __syncthreads();                    // previous tile's readers are done with both buffers
+        store_smem(0);
+        __syncthreads();
+        for (int s = 0; s < KS; ++s) {
+            const int buf = s & 1;
+            if (s + 1 < KS) load_global(s + 1);
+#pragma unroll
+            for (int kk = 0; kk < PRB_GT_K; ++kk) {
+                real a[8], xv[CB];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) a[r] = As[buf][kk][ri0 + 4 * r];
+#pragma unroll
+                for (int c = 0; c < CB; ++c) xv[c] = Xs[buf][kk][cb0 + 8 * c];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < CB; ++c) acc[r][c] = fma(a[r], xv[c], acc[r][c]);
+            }
+            if (s + 1 < KS) store_smem(buf ^ 1);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int ir = i0 + ri0 + 4 * r;
+            if (ir < n_rows) {
+#pragma unroll
+                for (int c = 0; c < CB; ++c) prb_st_work(C, (out_off + row0 + ir) * PRB_NB + b0 + cb0 + 8 * c, acc[r][c]);
+            }
+        }
+    }
+}
+
 // ---- solver stage logic: what happens to the derivative k of state element e in stage STAGE.
 // HEUN_REF reproduces the reference's aliased `heun` (y += dt/2*(k2+k2), base_backend.py:763-765).
 template <int STAGE>

@@ -283,6 +283,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     tc_consts: Dict[str, Tuple[int, int, int]] = {}     # W array -> (hi offset, lo offset, K slabs) inside consts
     tc_xt: Dict[str, Tuple[int, int]] = {}              # source pointer expr -> (hi, lo) element offsets inside work
     tc_work = 0
+    gemm_smem = 0
     tc_extra: List[Tuple[int, np.ndarray]] = []         # (const offset, tiled hi / lo image)
     # multi-GPU: 2-d constants (connectivity) are row-sharded -> re-pack the constant space with shard sizes
     const_size = ir.const_size
@@ -433,6 +434,30 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 body.append("            }")
                 body.append("        }")
                 body.append("    }")
+            elif reds and nb > 1 and nb % 32 == 0 and block == 512 and all(r.simple is not None for r in reds):
+                # sweep-batched dense coupling as a shared-memory tiled GEMM on the FMA pipes (prb_gemm_batch), results to
+                # the reductions' work arrays; the element-wise tail follows behind a grid barrier, thread per (element, instance)
+                lo, hi = em.bounds(n)
+                # instances per tile = 32 * cb: the widest tile that still gives every SM a tile, else the narrowest
+                cands = [c for c in (4, 2, 1) if nb % (32 * c) == 0]
+                n_tiles = lambda c: ((hi - lo + 127) // 128) * (nb // (32 * c))
+                cb = next((c for c in cands if n_tiles(c) >= 120), cands[-1])
+                item = 4 if f32 else 8
+                gemm_smem = max(gemm_smem, 2 * 16 * (128 + 2 + 32 * cb) * 4 if f32 else 2 * (128 * 20 + 16 * (32 * cb + 4)) * 8)
+                for r in reds:
+                    warr = ir.arrays[r.simple[0]]
+                    body.append(f"    prb_gemm_batch<{cb}>(C, C.consts + {warr.offset}LL, {lo}LL, {hi - lo}, {r.m}, {em.source_ptr(r)}, "
+                                f"{em.red_work[r.id].offset}LL);      // n = {n}")
+                body.append("    prb_grid_barrier(C);")
+                if sts:
+                    cur = (p, n, False)
+                    emitted = set()
+                    body.append(f"    for (long long q = {lo * nb}LL + C.gtid; q < {hi * nb}LL; q += C.gsize) {{   // tail, thread per (element, instance), n = {n}")
+                    body.append(f"        const long long i = q / {nb}; const int b = (int)(q - i * {nb});")
+                    body.extend(em.emit_nodes(em.order([s_.node for s_ in sts]), cur, emitted, "        "))
+                    for s_ in sts:
+                        body.append("        " + em.store_stmt(s_, cur, "STAGE"))
+                    body.append("    }")
             elif reds and nb > 1:
                 # batched sweep: one warp task = R_T rows x B_T instances; W rows are read once per B_T instances
                 cur = (p, n, True)
@@ -604,7 +629,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     if not all_state:
         iconst[obs_off:obs_off + obs.size] = obs
     evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4}[solver]
-    smem = 0
+    smem = gemm_smem
     if tc is not None:
         smem = tc["nstage"] * (2 * 128 * 32 * 4 + 2 * tc["bt"] * 32 * 4)
         tc = dict(tc, smem=smem, xt_elems=tc_work)

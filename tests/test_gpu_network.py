@@ -72,21 +72,26 @@ def test_kuramoto_separable_rewrite_agrees_with_direct_pair_evaluation(gpu):
     assert traj_rel_err(a[:, :, 0], b[:, :, 0]) <= 1e-11
 
 
-@pytest.mark.parametrize("name,sweep,solver", [
-    ("wc_n128", ["r_ext", "k"], "rk4"),            # 0-d parameter + uniform per-node vector swept as a whole
-    ("qsfa_both_n96", ["I_ext", "I_ext_v1"], "heun"),
-    ("kuramoto_n128", ["s_ext"], "euler"),          # separable pair coupling -> batched two-RHS dots
-    ("wc_n128_f32", ["r_ext"], "heun_true"),
+@pytest.mark.parametrize("name,sweep,solver,B", [
+    ("wc_n128", ["r_ext", "k"], "rk4", 16),         # 0-d parameter + uniform per-node vector swept as a whole
+    ("qsfa_both_n96", ["I_ext", "I_ext_v1"], "heun", 16),
+    ("kuramoto_n128", ["s_ext"], "euler", 16),      # separable pair coupling -> batched two-RHS dots
+    ("wc_n128_f32", ["r_ext"], "heun_true", 16),
+    # B a multiple of 32: shared-memory tiled GEMM on the FMA pipes (prb_gemm_batch), 8 x CB register tiles
+    ("wc_n128", ["r_ext", "k"], "rk4", 128),        # CB = 4
+    ("qsfa_both_n96", ["I_ext", "I_ext_v1"], "heun", 64),     # CB = 2, padded rows (96 < 128), two matrices, ring source
+    ("kuramoto_n128", ["s_ext"], "heun_true", 32),  # CB = 1
+    ("wc_n300_f32", ["r_ext"], "euler", 96),        # fp32 on the FMA pipes (96 is not a tcgen05 batch), K = 300 (scalar W loads... m % 4 == 0 -> vector)
 ])
-def test_batched_network_sweep_matches_per_instance_oracle(gpu, name, sweep, solver):
-    """grid_search over a *network*: B instances share the connectivity, W rows are read once per 8 instances.  Every
-    instance must match the oracle integrating that parameter set alone."""
+def test_batched_network_sweep_matches_per_instance_oracle(gpu, name, sweep, solver, B):
+    """grid_search over a *network*: B instances share the connectivity (register tiles over W rows; a tiled GEMM when
+    B is a multiple of 32).  Every sampled instance must match the oracle integrating that parameter set alone."""
     fx = orc.load_fixture(golden_path(name))
     prog = Program.load(golden_path(name))
     r = fx["run"]
-    B = 16
     rng = np.random.default_rng(5)
-    m = NetworkModel(prog, solver=solver, n_batch=B, sweep=sweep)
+    m = NetworkModel(prog, solver=solver, n_batch=B, sweep=sweep, tensor_core=False)
+    assert ("prb_gemm_batch<" in m.kernel.source.split("prb_eval(PrbNet& C) {")[1]) == (B % 32 == 0)
     assert m.param_names == sweep
     base = m.param_defaults
     params = base[:, None] + rng.uniform(-0.3, 0.6, (len(sweep), B))
@@ -94,7 +99,7 @@ def test_batched_network_sweep_matches_per_instance_oracle(gpu, name, sweep, sol
     assert out.shape[2] == B and y_final.shape == (prog.n_state, B)
     f = orc.build_vector_field(prog.source())
     names = [a.name for a in prog.args]
-    for b in (0, 3, 8, 15):
+    for b in sorted({0, 3, B // 2, B - 1}):
         args = [np.array(a.value, copy=True) for a in prog.args]
         args[0] = args[0][()]
         for k, nme in enumerate(sweep):
