@@ -79,15 +79,29 @@ def register() -> bool:
 
 
 # ----------------------------------------------------------------------------- batched grid_search
+def _adapt(template, vals: dict, param_map: dict):
+    """``pyrates.utility.adapt_circuit`` (utility.py:138-186) plus population parameters: a ``nodes`` entry naming a
+    ``PopulationTemplate`` of the circuit (frontend/template/population.py:40) sets that population's ``params['op/var']``
+    for all of its units — the reference's ``update_var`` only reaches classic node templates."""
+    from pyrates.utility import adapt_circuit
+    pops = getattr(template, "populations", None) or {}
+    pop_keys = [k for k in vals if "nodes" in param_map[k] and all(n in pops for n in param_map[k]["nodes"])]
+    circuit = adapt_circuit(template, {k: v for k, v in vals.items() if k not in pop_keys}, param_map)
+    for k in pop_keys:
+        for n in param_map[k]["nodes"]:
+            for v in param_map[k]["vars"]:
+                circuit.populations[n].params[v] = vals[k]
+    return circuit
+
+
 def _probe_positions(template, keys: List[str], param_map: dict, build, sentinels=(1009.0, 2003.0)):
     """Find where each grid key lands in the single-instance argument tuple by building the instance with
     two distinct sentinel values per key and diffing the arguments.  Only identity
     dependence (the value appears verbatim) is accepted — anything else raises instead of guessing."""
-    from pyrates.utility import adapt_circuit
     builds = []
     for base in sentinels:
         vals = {k: base + 7.0 * i for i, k in enumerate(keys)}
-        builds.append((vals, build(adapt_circuit(template, vals, param_map))))
+        builds.append((vals, build(_adapt(template, vals, param_map))))
     (vals_a, a), (vals_b, b) = builds
     prog_a, prog_b = a["program"], b["program"]
     targets: Dict[str, List[Tuple[str, int]]] = {k: [] for k in keys}
@@ -127,7 +141,8 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     import pandas as pd
     from pyrates import CircuitTemplate
     from pyrates.utility import linearize_grid
-    from .sweep import BatchedSweep, shard_bounds
+    from .scalarize import UnsupportedModelError
+    from .sweep import BatchedSweep, NetworkSweep, shard_bounds
 
     register()
     kwargs.pop("vectorize", None)
@@ -198,14 +213,31 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     grid_vals = {k: np.asarray(param_grid[k].values[lo:hi], dtype=np.float64) for k in keys}
     table = np.stack([grid_vals[k] for k in rows]) if rows else np.zeros((0, B))
 
-    sw = BatchedSweep(prog, sweep, base["observers"], solver=solver, T=simulation_time, dt=step_size,
-                      dts=sampling_step_size, n_inst=B, chunk_samples=chunk_samples, const_div_to_mul=const_div_to_mul)
-    try:
+    exec_model = kwargs.pop("exec_model", "auto")
+    sw = None
+    if exec_model in ("auto", "instance"):
+        try:
+            sw = BatchedSweep(prog, sweep, base["observers"], solver=solver, T=simulation_time, dt=step_size,
+                              dts=sampling_step_size, n_inst=B, chunk_samples=chunk_samples,
+                              const_div_to_mul=const_div_to_mul)
+        except UnsupportedModelError as e:
+            if exec_model == "instance" or "too large" not in str(e):
+                raise
+    if sw is not None:
+        try:
+            for elem, k in y0_rows:
+                sw.h_y0.array[elem, :] = grid_vals[k]
+            res = np.array(sw.run(table), copy=True)           # [n_samples, n_obs, B]
+        finally:
+            sw.free()
+    else:
+        # the circuit is a network (populations, dense coupling): all grid points share the connectivity and step
+        # together in the persistent network kernel, their couplings as one GEMM per evaluation
+        ns = NetworkSweep(prog, sweep, base["observers"], solver=solver, T=simulation_time, dt=step_size,
+                          dts=sampling_step_size, n_inst=B, tensor_core=kwargs.pop("tensor_core", "auto"))
         for elem, k in y0_rows:
-            sw.h_y0.array[elem, :] = grid_vals[k]
-        res = np.array(sw.run(table), copy=True)           # [n_samples, n_obs, B]
-    finally:
-        sw.free()
+            ns.set_y0(elem, grid_vals[k])
+        res = ns.run(table)
 
     circuit_names = [f"{name}_{idx}" for idx in param_grid.index]
     param_grid = param_grid.copy()

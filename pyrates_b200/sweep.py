@@ -23,7 +23,7 @@ from . import runtime as rt
 from .engine import InstanceModel, n_steps_for
 from .program import Program
 
-__all__ = ["BatchedSweep", "shard_bounds"]
+__all__ = ["BatchedSweep", "NetworkSweep", "shard_bounds"]
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -155,3 +155,60 @@ class BatchedSweep:
         for b in (self.h_params, self.h_y0, self.h_out):
             if b is not None:
                 b.free()
+
+
+class NetworkSweep:
+    """grid_search over a model that does not fit one thread (populations / dense coupling): all grid points share
+    the connectivity and are integrated together by the persistent network kernel (``NetworkModel(n_batch=B)``) — the
+    dense couplings of the B instances become ONE GEMM per evaluation (tcgen05 3xTF32 in float32, DMMA in float64).
+
+    ``sweep`` entries are ``(arg_name, flat_element)`` targets like ``BatchedSweep``'s; a swept argument must be a scalar
+    or a uniform per-node vector that the grid key fills entirely.  The batch is padded to a multiple of 32 instances
+    (copies of the last grid point) so that the GEMM tiles are full; padded trajectories are dropped on return."""
+
+    PAD = 32
+
+    def __init__(self, prog: Program, sweep: Sequence[Tuple[str, int]], observers: Sequence[int], *, solver: str,
+                 T: float, dt: float, dts: Optional[float], n_inst: int, tensor_core="auto"):
+        from .netengine import NetworkModel
+        self.B = int(n_inst)
+        self.Bp = -(-self.B // self.PAD) * self.PAD if self.B > 8 else 8
+        per_arg: Dict[str, List[int]] = {}
+        self.rows: Dict[str, int] = {}
+        for k, (arg, elem) in enumerate(sweep):
+            per_arg.setdefault(arg, []).append(int(elem))
+            self.rows.setdefault(arg, k)
+        for arg, elems in per_arg.items():
+            size = int(np.asarray(prog.arg(arg).value).size)
+            if sorted(elems) != list(range(size)):
+                raise NotImplementedError(f"network sweeps vary whole arguments only: `{arg}` is hit at elements {elems[:4]}.. "
+                                          f"of {size}")
+        self.names = list(per_arg)
+        self.sweep = list(sweep)
+        self.T, self.dt, self.dts = T, dt, dts
+        self.model = NetworkModel(prog, solver=solver, observers=observers, n_batch=self.Bp, sweep=self.names,
+                                  tensor_core=tensor_core)
+        self.y0 = np.repeat(np.asarray(prog.y0, dtype=self.model.real)[:, None], self.Bp, axis=1)
+        self.n_obs = len(self.model.observers)
+        self._y_final = None
+
+    def set_y0(self, elem: int, values: np.ndarray):
+        self.y0[elem, : self.B] = values
+        self.y0[elem, self.B:] = values[-1]
+
+    def run(self, table: np.ndarray) -> np.ndarray:
+        table = np.asarray(table, dtype=np.float64)
+        if table.shape != (len(self.sweep), self.B):
+            raise ValueError(f"parameter table must have shape ({len(self.sweep)}, {self.B}), got {table.shape}")
+        params = np.empty((len(self.names), self.Bp))
+        for r, arg in enumerate(self.names):
+            params[r, : self.B] = table[self.rows[arg]]
+            params[r, self.B:] = table[self.rows[arg], -1]
+        out, self._y_final = self.model.run(self.T, self.dt, self.dts, y0=self.y0, params=params)
+        return out[:, :, : self.B]
+
+    def final_state(self) -> np.ndarray:
+        return self._y_final[:, : self.B]
+
+    def free(self):
+        pass

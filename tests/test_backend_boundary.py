@@ -146,3 +146,33 @@ def test_grid_search_cuda_matches_reference_grid_search(gpu, registered, solver)
     assert list(pmap.index) == [f"JRC_{i}" for i in range(16)]
     np.testing.assert_array_equal(pmap["C"].values, fx["extra"]["grid_C"])
     assert traj_rel_err(res.values, fx["extra"][f"frame_{solver}"]) <= 1e-9
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("precision,solver", [("float64", "heun"), ("float32", "euler")])
+def test_grid_search_over_population_network_matches_reference_runs(gpu, registered, precision, solver):
+    """grid_search over a *network* (WC population, dense Connectivity shared by all grid points): the grid steps as one
+    batch in the persistent network kernel, couplings as one GEMM per evaluation (DMMA in fp64, tcgen05 3xTF32 in
+    fp32).  Checked against the reference NumPy backend run once per sampled grid point."""
+    import pyrates
+    from copy import deepcopy
+    from pyrates.utility import linearize_grid
+    from oracle.make_golden import _wc_pop
+    tpl = _wc_pop(96)()
+    grid = linearize_grid({"tau": np.linspace(8.0, 12.0, 8), "k": np.linspace(0.8, 1.2, 5)}, permute=True)     # 40 points
+    pm = {"tau": {"vars": ["rate_op/tau"], "nodes": ["e"]}, "k": {"vars": ["rate_op/k"], "nodes": ["e"]}}
+    kw = dict(step_size=1e-3, simulation_time=0.05, sampling_step_size=2e-3, solver=solver, float_precision=precision)
+    before = rt.launch_count()
+    res, pmap = pyrates.grid_search(deepcopy(tpl), grid, pm, outputs={"r": "e/rate_op/r"}, backend="cuda",
+                                    exec_model="network", verbose=False, **kw)
+    assert rt.launch_count() == before + 1                      # the whole grid, the whole simulation: one launch
+    assert res.shape == (25, 40 * 96) and list(pmap.index)[:2] == ["wc_n96_0", "wc_n96_1"]
+    for i in (0, 17, 39):
+        c = deepcopy(tpl)
+        c.populations["e"].params["rate_op/tau"] = float(grid["tau"].values[i])
+        c.populations["e"].params["rate_op/k"] = float(grid["k"].values[i])
+        ref = c.run(outputs={"r": "e/rate_op/r"}, backend="default", verbose=False, clear=True, **kw)
+        got = res.xs(f"wc_n96_{i}", axis=1, level=1)
+        assert got.shape == ref.shape
+        assert traj_rel_err(got.values, ref.values) <= RTOL[precision], (precision, i)
