@@ -43,7 +43,11 @@ typedef enum prb_status {
 /* Solver ids.  HEUN_REF is the reference's `solver='heun'`, whose in-place rhs buffer aliasing makes
  * the update y <- y + dt*f(y + dt*f(y))  (base_backend.py:763-765; SURVEY.md headline 4).
  * HEUN is the textbook explicit trapezoid; RK4 the classic 4-stage scheme (no reference counterpart). */
-enum { PRB_SOLVER_EULER = 0, PRB_SOLVER_HEUN_REF = 1, PRB_SOLVER_HEUN = 2, PRB_SOLVER_RK4 = 3 };
+enum { PRB_SOLVER_EULER = 0, PRB_SOLVER_HEUN_REF = 1, PRB_SOLVER_HEUN = 2, PRB_SOLVER_RK4 = 3,
+       /* the reference's solver='scipy': solve_ivp(method='RK45', first_step=dt, t_eval=times), base_backend.py:802-812;
+        * options (rtol, atol, t_start, t_bound, first_step, sample spacing, max_step, max attempts) are 8 doubles behind
+        * args.consts, args.n_steps = samples, per-instance status words behind args.sync */
+       PRB_SOLVER_RK45 = 4 };
 
 /* Kernel argument block.  Passed BY VALUE as the single __grid_constant__ parameter of every generated
  * kernel; the generated CUDA source embeds the identical definition (pyrates_b200/csrc/prb_kernel_abi.h).

@@ -301,16 +301,66 @@ def make_case(name: str, spec: dict, cap: Capture) -> str:
     return path
 
 
+# adaptive cases: the reference's solver='scipy' (solve_ivp RK45, base_backend.py:802-812); float t, no ring buffers
+ADAPTIVE_CASES = {
+    "qif_rk45":     dict(build=_yaml(NM + "qif.qif"), T=2.0, dt=1e-3, dts=1e-2, out="p/qif_op/r"),
+    "qif_rk45_tight": dict(build=_yaml(NM + "qif.qif"), T=2.0, dt=1e-3, dts=1e-2, out="p/qif_op/r",
+                           kw=dict(rtol=1e-8, atol=1e-10)),
+    "jrc_rk45":     dict(build=_yaml(NM + "jansenrit.JRC"), T=0.5, dt=1e-4, dts=1e-3, out="pc/rpo_e_in/v"),
+    "jrc_rk45_tight": dict(build=_yaml(NM + "jansenrit.JRC"), T=0.5, dt=1e-4, dts=1e-3, out="pc/rpo_e_in/v",
+                           kw=dict(rtol=1e-7, atol=1e-9)),
+    "qif_sfa_rk45": dict(build=_yaml(NM + "qif.qif_sfa"), T=2.0, dt=1e-3, dts=5e-3, out="p/qif_sfa_op/r",
+                         kw=dict(rtol=1e-6, atol=1e-8)),
+    "wc_n8_rk45":   dict(build=_wc_pop(8), T=0.5, dt=1e-3, dts=5e-3, out="e/rate_op/r", kw=dict(rtol=1e-6, atol=1e-9)),
+}
+
+
+def make_adaptive_case(name: str, spec: dict, cap: Capture) -> str:
+    from pyrates import clear
+    from pyrates.ir.node import clear_ir_caches
+    T, dt, dts, kw = spec["T"], spec["dt"], spec.get("dts"), spec.get("kw", {})
+    clear_ir_caches()
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            circuit = spec["build"]()
+            circuit.run(simulation_time=T, step_size=dt, sampling_step_size=dts, solver="scipy", outputs={"o": spec["out"]},
+                        backend="default", float_precision="float64", verbose=False, clear=True, **kw)
+        finally:
+            os.chdir(cwd)
+    prog = Program.from_source(cap.source, list(zip(cap.names, cap.func_args)), state_vars=cap.state_vars,
+                               float_precision="float64")
+    rec = cap.rec
+    # the restatement (oracle.solve_rk45) must reproduce reference + SciPy bit for bit
+    func = orc.build_vector_field(prog.source())
+    args = [np.array(a, copy=True) for a in cap.func_args]
+    args[0] = args[0][()]
+    mine, _ = orc.run_adaptive(func, args, T, dt, dts, **kw)
+    diff = float(np.max(np.abs(mine - rec)))
+    assert mine.shape == rec.shape and diff == 0.0, f"{name}: oracle RK45 != reference+scipy (max abs diff {diff})"
+    try:
+        clear(circuit)
+    except Exception:
+        pass
+    run_meta = {"T": T, "dt": dt, "dts": dts, "solver": "scipy", "method": "RK45", "precision": "float64",
+                "rtol": kw.get("rtol", 1e-3), "atol": kw.get("atol", 1e-6), "reference_solvers": ["scipy"],
+                "reference_version": "1.2.3", "scipy_version": __import__("scipy").__version__, "out": spec["out"]}
+    path = os.path.join(GOLDEN, f"{name}.npz")
+    prog.save(path, __run__=np.frombuffer(json.dumps(run_meta).encode(), dtype=np.uint8), rec_scipy=rec)
+    return path
+
+
 def main(argv):
     warnings.filterwarnings("ignore")
     if import_reference() is None:
         raise SystemExit("reference PyRates not importable here; fixtures can only be regenerated in the build container")
     os.makedirs(GOLDEN, exist_ok=True)
-    names = argv or list(CASES)
+    names = argv or (list(CASES) + list(ADAPTIVE_CASES))
     cap = Capture()
     try:
         for n in names:
-            p = make_case(n, CASES[n], cap)
+            p = make_adaptive_case(n, ADAPTIVE_CASES[n], cap) if n in ADAPTIVE_CASES else make_case(n, CASES[n], cap)
             print(f"{n:24s} -> {os.path.relpath(p, _ROOT)}  ({os.path.getsize(p) / 1024:.1f} KiB)")
     finally:
         cap.close()

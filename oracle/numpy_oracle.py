@@ -148,6 +148,99 @@ def solve_rk4(func, args, T, dt, dts, y, t0):
 SOLVERS = {"euler": solve_euler, "heun": solve_heun, "heun_true": solve_heun_true, "rk4": solve_rk4}
 
 
+# ----------------------------------------------------------------------------- adaptive: solver='scipy' (RK45)
+# Restatement of what BaseBackend._solve_scipy (base_backend.py:802-812) executes:
+#   solve_ivp(fun=func, t_span=(t0, T), y0=y, first_step=dt, args=args, t_eval=times, **kwargs)
+# with SciPy's default method RK45 (Dormand-Prince 5(4), scipy/integrate/_ivp/rk.py: RungeKutta._step_impl, rk_step,
+# RkDenseOutput; scipy/integrate/_ivp/ivp.py: the t_eval loop).  SciPy is a third-party dependency of the reference
+# (setup.py: 'scipy', unpinned; 1.18.1 installed here); its published algorithm is restated below and pinned bit-exact
+# against the real reference + SciPy in tests/golden/*_rk45.npz.
+# One reference-specific effect is part of the semantics: the generated rhs returns its in-place ``dy`` buffer
+# (computegraph.py:1220-1228) and SciPy keeps ``self.f = f_new`` by reference, so ``K[0]`` of every attempt is simply
+# the MOST RECENT rhs evaluation — after a rejected attempt that is f(t + h_rejected, y_rejected), not f(t, y).
+RK45_C = np.array([0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1])
+RK45_A = np.array([[0, 0, 0, 0, 0], [1 / 5, 0, 0, 0, 0], [3 / 40, 9 / 40, 0, 0, 0], [44 / 45, -56 / 15, 32 / 9, 0, 0],
+                   [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729, 0],
+                   [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656]])
+RK45_B = np.array([35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84])
+RK45_E = np.array([-71 / 57600, 0, 71 / 16695, -71 / 1920, 17253 / 339200, -22 / 525, 1 / 40])
+RK45_P = np.array([[1, -8048581381 / 2820520608, 8663915743 / 2820520608, -12715105075 / 11282082432], [0, 0, 0, 0],
+                   [0, 131558114200 / 32700410799, -68118460800 / 10900136933, 87487479700 / 32700410799],
+                   [0, -1754552775 / 470086768, 14199869525 / 1410260304, -10690763975 / 1880347072],
+                   [0, 127303824393 / 49829197408, -318862633887 / 49829197408, 701980252875 / 199316789632],
+                   [0, -282668133 / 205662961, 2019193451 / 616988883, -1453857185 / 822651844],
+                   [0, 40617522 / 29380423, -110615467 / 29380423, 69997945 / 29380423]])
+
+
+def solve_rk45(func, args, T, dt, y0, t0, times, rtol=1e-3, atol=1e-6, max_step=np.inf, aliased=True):
+    """solve_ivp(method='RK45', first_step=dt, t_eval=times) around the reference rhs; returns state_rec[len(times), n].
+    The state is integrated in float64 whatever the model precision (scipy/integrate/_ivp/base.py: check_arguments).
+    ``aliased=True`` is the reference's behaviour (rhs returns its in-place buffer, see above); ``aliased=False`` is plain
+    SciPy around a function that returns fresh arrays (a rejected attempt restarts from the true f(t, y))."""
+    y = np.asarray(y0).astype(float, copy=False)
+    n = y.size
+    t, t_bound = float(t0), float(T)
+    f = np.asarray(func(t, y, *args), dtype=float)           # alias of the rhs buffer
+    h_abs = float(dt)
+    K = np.empty((7, n))
+    rec = np.empty((len(times), n))
+    i_eval = 0
+    while t != t_bound:
+        min_step = 10 * np.abs(np.nextafter(t, np.inf) - t)
+        if h_abs > max_step:
+            h_abs = max_step
+        elif h_abs < min_step:
+            h_abs = min_step
+        rejected = False
+        while True:
+            if h_abs < min_step:
+                raise RuntimeError("Required step size is less than spacing between numbers.")
+            t_new = t + h_abs
+            if t_new - t_bound > 0:
+                t_new = t_bound
+            h = t_new - t
+            h_abs = np.abs(h)
+            K[0] = f
+            for s in range(1, 6):
+                dy = np.dot(K[:s].T, RK45_A[s, :s]) * h
+                K[s] = func(t + RK45_C[s] * h, y + dy, *args)
+            y_new = y + h * np.dot(K[:-1].T, RK45_B)
+            f_new = np.asarray(func(t + h, y_new, *args), dtype=float)
+            K[-1] = f_new
+            if aliased:
+                f = f_new
+            scale = atol + np.maximum(np.abs(y), np.abs(y_new)) * rtol
+            err = np.dot(K.T, RK45_E) * h / scale
+            error_norm = np.linalg.norm(err) / err.size ** 0.5
+            if error_norm < 1:
+                factor = 10.0 if error_norm == 0 else min(10.0, 0.9 * error_norm ** -0.2)
+                if rejected:
+                    factor = min(1, factor)
+                h_abs *= factor
+                f = f_new
+                break
+            h_abs *= max(0.2, 0.9 * error_norm ** -0.2)
+            rejected = True
+        t_old, y_old = t, y
+        t, y = t_new, y_new
+        i_new = int(np.searchsorted(times, t, side="right"))
+        if i_new > i_eval:
+            Q = K.T.dot(RK45_P)
+            x = (times[i_eval:i_new] - t_old) / h
+            p = np.cumprod(np.tile(x, (4, 1)), axis=0)
+            rec[i_eval:i_new] = (h * np.dot(Q, p) + y_old[:, None]).T
+            i_eval = i_new
+    return rec[:i_eval]
+
+
+def run_adaptive(func, func_args: Sequence, T: float, dt: float, dts: float = None, **kw):
+    """base_backend.py:596-611 with solver='scipy' (method RK45)."""
+    t0, y0 = func_args[0], func_args[1]
+    step = dts if dts else dt
+    times = np.linspace(0.0, T, num=round(T / step), endpoint=False)
+    return solve_rk45(func, tuple(func_args[2:]), T, dt, y0, t0, times, **kw), times
+
+
 def run(func, func_args: Sequence, T: float, dt: float, dts: float = None, solver: str = "euler"):
     """base_backend.py:596-611: returns ``(state_rec[round(T/dts), n_state], times)``.
     ``func_args = (t0, y0, dy, *consts)``; ``y0`` and mutable buffers are modified in place like

@@ -27,7 +27,7 @@ from typing import Callable, Dict, List, Optional, Tuple, Union
 import numpy as np
 
 from . import runtime as rt
-from .engine import FIXED_STEP_SOLVERS, InstanceModel, n_steps_for
+from .engine import ADAPTIVE_SOLVERS, FIXED_STEP_SOLVERS, InstanceModel, n_steps_for
 from .program import Arg, Program, Stmt
 from .scalarize import UnsupportedModelError
 
@@ -117,7 +117,7 @@ class CudaVectorField:
 class CudaBackend:
     """Code generator + runner with the reference backend interface, targeting B200 CUDA kernels."""
 
-    SUPPORTED_SOLVERS: Tuple[str, ...] = FIXED_STEP_SOLVERS
+    SUPPORTED_SOLVERS: Tuple[str, ...] = FIXED_STEP_SOLVERS + ('scipy',)   # 'scipy' = solve_ivp RK45 semantics on device
     SUPPORTS_SPARSE_JACOBIAN: bool = False
     SUPPORTS_EDGE_DELAY_BUFFER: bool = True
     _no_funcs: Tuple[str, ...] = ("identity", "index_1d", "index_2d", "index_range", "index_axis")
@@ -302,10 +302,17 @@ class CudaBackend:
         prog = func.program(func_args)
         step = dts if dts else dt
         times = np.linspace(0.0, T, num=round(T / step), endpoint=False)
-        model = build_model(prog, solver=solver, exec_model=self.exec_model, fmad=self.fmad,
-                            const_div_to_mul=self.const_div_to_mul)
-        self.last_model = model
-        out, y_final = model.run(T, dt, dts)
+        if solver in ADAPTIVE_SOLVERS:
+            # BaseBackend._solve_scipy (:802-812): solve_ivp(first_step=dt, t_eval=times, **kwargs); one thread integrates the
+            # circuit with SciPy's RK45 step controller and dense output (csrc/templates/inst_kernel.cuh)
+            model = InstanceModel(prog, solver=solver, fmad=self.fmad, max_nodes=20000)
+            self.last_model = model
+            out, y_final = model.run(T, dt, dts, **kwargs)
+        else:
+            model = build_model(prog, solver=solver, exec_model=self.exec_model, fmad=self.fmad,
+                                const_div_to_mul=self.const_div_to_mul)
+            self.last_model = model
+            out, y_final = model.run(T, dt, dts)
         rec = np.ascontiguousarray(out[:, :, 0])
         # mirror the reference's in-place semantics: y0 (func_args[1]) ends up holding the final state
         try:

@@ -28,6 +28,137 @@ __device__ __forceinline__ void prb_axpy(real (&o)[N], const real (&y)[N], const
 #define PRB_MIN_BLOCKS 1
 #endif
 
+#if PRB_SOLVER == PRB_SOLVER_RK45
+// ---- adaptive solver: the reference's solver='scipy' == scipy.integrate.solve_ivp(method='RK45', first_step=dt,
+// t_eval=times) (BaseBackend._solve_scipy, pyrates/backend/base/base_backend.py:802-812).  Dormand-Prince 5(4) with
+// SciPy's step controller (safety 0.9, factors in [0.2, 10], RMS error norm against atol + rtol*max(|y|,|y_new|)) and
+// its 4th-order dense output evaluated at the sample times (scipy/integrate/_ivp/rk.py: rk_step, _step_impl,
+// RkDenseOutput; ivp.py: t_eval loop).  One thread integrates one instance with its OWN step sequence; the seven
+// stage vectors K live in registers.  Reference-specific: the generated rhs returns its in-place buffer and SciPy keeps
+// f by reference, so K[0] of every attempt is the most recent rhs evaluation (after a rejected attempt:
+// f(t + h_rej, y_rej)) — reproduced here because `f` below is exactly that buffer.  The state is integrated in double
+// whatever the model precision (scipy/integrate/_ivp/base.py: check_arguments).
+// Options (A.consts, doubles): [0] rtol [1] atol [2] t_start [3] t_bound [4] first_step [5] sample spacing
+// [6] max_step [7] max attempts.  A.n_steps = number of samples; per-instance status (0 ok, 1 step too small,
+// 2 attempt budget exhausted) goes to ((unsigned*)A.sync)[b].
+extern "C" __global__ void __launch_bounds__(PRB_BLOCK, PRB_MIN_BLOCKS)
+prb_integrate(const __grid_constant__ prb_kernel_args A)
+{
+    constexpr double C_[6] = PRB_RK45_C_INIT;            // Dormand-Prince tableau, emitted by pyrates_b200/rk45.py
+    constexpr double A_[6][5] = PRB_RK45_A_INIT;
+    constexpr double B_[6] = PRB_RK45_B_INIT;
+    constexpr double E_[7] = PRB_RK45_E_INIT;
+    constexpr double P_[7][4] = PRB_RK45_P_INIT;         // dense output: y(t_old + x h) = y_old + h * sum_c Q[:, c] x^(c+1), Q = K^T P
+    const long long B = A.n_inst;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    PrbThread T;
+    prb_thread_init(T, A, b);
+    const double* __restrict__ opt = (const double*)A.consts;
+    const double rtol = opt[0], atol = opt[1], t_bound = opt[3], te_step = opt[5], max_step = opt[6];
+    const long long max_attempts = (long long)opt[7];
+    double t = opt[2], h_abs = opt[4];
+
+    real* __restrict__ Y = (real*)A.y;
+    double y[PRB_NS], f[PRB_NS];
+    real yr[PRB_NS], kr[PRB_NS];
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) { yr[j] = Y[(long long)j * B + b]; y[j] = (double)yr[j]; }
+    prb_rhs((prb_time)t, yr, kr, T);                                   // self.f = fun(t0, y0)
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) f[j] = (double)kr[j];
+
+    real* __restrict__ out = (real*)A.out;
+    long long sample = A.sample0;
+    const long long n_samples = A.sample0 + A.n_steps;
+    long long attempts = 0;
+    unsigned int status = 0;
+
+    while (t != t_bound && status == 0) {
+        const double min_step = 10.0 * fabs(nextafter(t, __longlong_as_double(0x7ff0000000000000LL)) - t);
+        if (h_abs > max_step) h_abs = max_step;
+        else if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false;
+        double K[7][PRB_NS], y_new[PRB_NS];
+        double h = 0.0, t_new = t;
+        for (;;) {
+            if (h_abs < min_step) { status = 1; break; }
+            if (++attempts > max_attempts) { status = 2; break; }
+            t_new = t + h_abs;
+            if (t_new - t_bound > 0.0) t_new = t_bound;
+            h = t_new - t;
+            h_abs = fabs(h);
+            PRB_UNROLL_NS
+            for (int j = 0; j < PRB_NS; ++j) K[0][j] = f[j];
+#pragma unroll
+            for (int s = 1; s < 6; ++s) {
+                PRB_UNROLL_NS
+                for (int j = 0; j < PRB_NS; ++j) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int q = 0; q < s; ++q) d += K[q][j] * A_[s][q];
+                    yr[j] = (real)(y[j] + d * h);
+                }
+                prb_rhs((prb_time)(t + C_[s] * h), yr, kr, T);
+                PRB_UNROLL_NS
+                for (int j = 0; j < PRB_NS; ++j) K[s][j] = (double)kr[j];
+            }
+            PRB_UNROLL_NS
+            for (int j = 0; j < PRB_NS; ++j) {
+                double d = 0.0;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) d += K[q][j] * B_[q];
+                y_new[j] = y[j] + h * d;
+                yr[j] = (real)y_new[j];
+            }
+            prb_rhs((prb_time)(t + h), yr, kr, T);
+            double sq = 0.0;
+            PRB_UNROLL_NS
+            for (int j = 0; j < PRB_NS; ++j) {
+                f[j] = (double)kr[j];                                  // the aliased buffer: newest evaluation
+                K[6][j] = f[j];
+                double e = 0.0;
+#pragma unroll
+                for (int q = 0; q < 7; ++q) e += K[q][j] * E_[q];
+                const double scale = atol + fmax(fabs(y[j]), fabs(y_new[j])) * rtol;
+                const double r = e * h / scale;
+                sq += r * r;
+            }
+            const double error_norm = sqrt(sq) / sqrt((double)PRB_NS);
+            if (error_norm < 1.0) {
+                double factor = (error_norm == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -0.2));
+                if (rejected) factor = fmin(1.0, factor);
+                h_abs *= factor;
+                break;
+            }
+            h_abs *= fmax(0.2, 0.9 * pow(error_norm, -0.2));
+            rejected = true;
+        }
+        if (status != 0) break;
+        // samples inside (t_old, t_new]: dense output  y_old + h * Q . (x, x^2, x^3, x^4),  Q = K^T P
+        while (sample < n_samples && (double)(sample - A.sample0) * te_step <= t_new) {
+            const double x = ((double)(sample - A.sample0) * te_step - t) / h;
+            const double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x;
+            PRB_UNROLL_NS
+            for (int j = 0; j < PRB_NS; ++j) {
+                double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll
+                for (int s = 0; s < 7; ++s) { q0 += K[s][j] * P_[s][0]; q1 += K[s][j] * P_[s][1]; q2 += K[s][j] * P_[s][2]; q3 += K[s][j] * P_[s][3]; }
+                yr[j] = (real)(h * (((q0 * p1 + q1 * p2) + q2 * p3) + q3 * p4) + y[j]);
+            }
+            prb_record(yr, out + sample * (long long)PRB_NOBS * B, b, B);
+            ++sample;
+        }
+        t = t_new;
+        PRB_UNROLL_NS
+        for (int j = 0; j < PRB_NS; ++j) y[j] = y_new[j];
+    }
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) Y[(long long)j * B + b] = (real)y[j];
+    if (A.sync) A.sync[b] = status | ((unsigned int)(attempts > 0xFFFFFFF ? 0xFFFFFFF : attempts) << 4);   // low 4 bits: status, rest: rhs attempts
+    prb_thread_exit(T, A, b);
+}
+#else
 extern "C" __global__ void __launch_bounds__(PRB_BLOCK, PRB_MIN_BLOCKS)
 prb_integrate(const __grid_constant__ prb_kernel_args A)
 {
@@ -104,6 +235,8 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
     for (int j = 0; j < PRB_NS; ++j) Y[(long long)j * B + b] = y[j];
     prb_thread_exit(T, A, b);
 }
+
+#endif   // fixed-step solvers
 
 // Single rhs evaluation dy = f(t, y) for every instance (the callable handed out by get_run_func).
 extern "C" __global__ void __launch_bounds__(PRB_BLOCK)

@@ -14,11 +14,12 @@ from typing import List, Sequence
 
 import numpy as np
 
-from .scalarize import ScalarRhs
+from .scalarize import ScalarRhs, UnsupportedModelError
 
 _TPL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "templates")
 
-SOLVER_IDS = {"euler": 0, "heun": 1, "heun_ref": 1, "heun_true": 2, "rk4": 3}
+SOLVER_IDS = {"euler": 0, "heun": 1, "heun_ref": 1, "heun_true": 2, "rk4": 3, "scipy": 4, "rk45": 4}
+ADAPTIVE_SOLVERS = ("scipy", "rk45")
 
 _FUNC = {"exp": "exp", "log": "log", "sin": "sin", "cos": "cos", "tan": "tan", "tanh": "tanh", "sinh": "sinh",
          "cosh": "cosh", "arctan": "atan", "arcsin": "asin", "arccos": "acos", "sqrt": "sqrt", "abs": "fabs",
@@ -69,7 +70,7 @@ def _lit(v: float, f32: bool) -> str:
     return f"({r})" if r.startswith("-") else r
 
 
-def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool) -> List[str]:
+def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time: bool = False) -> List[str]:
     """Straight-line statements computing dy[] (+ ring / slot stores) from y[], T."""
     g = rhs.graph
     ring_off = np.cumsum([0] + [r.rows * r.length for r in rhs.rings])
@@ -88,6 +89,8 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool) -> List[str
         if op == "param":
             return f"T.p[{g.payload[i]}]"
         if op == "t":
+            if not want_real and float_time:
+                raise UnsupportedModelError("the model indexes arrays with the time step; adaptive solvers pass a float time")
             return "((real)t)" if want_real else "t"
         name = f"v{i}"
         if g.isint[i] and want_real:
@@ -164,12 +167,17 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     f32 = precision == "float32"
     ns = rhs.n_state
     nrings = len(rhs.rings)
-    body = emit_rhs_body(rhs, f32, const_div_to_mul)
+    adaptive = solver in ADAPTIVE_SOLVERS
+    if adaptive and (rhs.rings or rhs.tables or rhs.slots):
+        raise UnsupportedModelError("adaptive integration (solver='scipy') needs a pure vector field: delay ring buffers, "
+                                    "step-indexed input tables and mutable buffers are fixed-step constructs")
+    body = emit_rhs_body(rhs, f32, const_div_to_mul, float_time=adaptive)
     np_ = len(rhs.params)
     src: List[str] = []
     src.append("// Generated by pyrates_b200.emit_inst — do not edit.  Instance execution model (1 thread = 1 instance).")
     src.append(read_template("prb_kernel_abi.cuh"))
     src.append(f"typedef {'float' if f32 else 'double'} real;")
+    src.append(f"typedef {'double' if adaptive else 'long long'} prb_time;     // adaptive solvers hand the rhs a float time")
     src.append(f"#define PRB_NS {ns}")
     src.append(f"#define PRB_NP {np_}")
     src.append(f"#define PRB_NOBS {len(observers)}")
@@ -177,6 +185,9 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     src.append(f"#define PRB_SOLVER {SOLVER_IDS[solver]}")
     src.append(f"#define PRB_BLOCK {block}")
     src.append(f"#define PRB_MIN_BLOCKS {int(min_blocks)}")
+    if adaptive:
+        from .rk45 import cuda_tables
+        src.append(cuda_tables())
     if ns > 64:
         src.append("#define PRB_UNROLL_NS")        # big states: keep loops rolled (state spills to local memory)
     src.append("""
@@ -210,7 +221,7 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
     init.append("}")
     init.append("__device__ __forceinline__ void prb_thread_exit(PrbThread&, const prb_kernel_args&, long long) {}")
     src.append("\n".join(init))
-    src.append("__device__ __forceinline__ void prb_rhs(const long long t, const real (&y)[PRB_NS], real (&dy)[PRB_NS], PrbThread& T) {")
+    src.append("__device__ __forceinline__ void prb_rhs(const prb_time t, const real (&y)[PRB_NS], real (&dy)[PRB_NS], PrbThread& T) {")
     src.extend("    " + l for l in body)
     src.append("}")
     rec = ["__device__ __forceinline__ void prb_record(const real (&y)[PRB_NS], real* __restrict__ row, long long b, long long B) {"]
@@ -224,7 +235,7 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
 
     ring_init = np.concatenate([r.init.reshape(-1) for r in rhs.rings]) if rhs.rings else np.zeros(0)
     tabs = np.concatenate([np.asarray(t.value, dtype=np.float64).reshape(-1) for t in rhs.tables]) if rhs.tables else np.zeros(0)
-    evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4}[solver]
+    evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4, "scipy": 6, "rk45": 6}[solver]
     return InstKernel("\n".join(src) + "\n", ns, np_, len(rhs.slots), len(observers), int(ring_init.size), ring_init,
                       [r.rolls_per_eval for r in rhs.rings], [r.length for r in rhs.rings], tabs,
                       np.array([s[2] for s in rhs.slots], dtype=np.float64),

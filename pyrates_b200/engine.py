@@ -16,9 +16,10 @@ from .emit_inst import InstKernel, emit_inst_kernel
 from .program import Program
 from .scalarize import ScalarRhs, scalarize
 
-__all__ = ["InstanceModel", "InstanceSession", "n_steps_for", "FIXED_STEP_SOLVERS", "evaluate_rhs"]
+__all__ = ["InstanceModel", "InstanceSession", "n_steps_for", "FIXED_STEP_SOLVERS", "ADAPTIVE_SOLVERS", "evaluate_rhs"]
 
 FIXED_STEP_SOLVERS = ("euler", "heun", "heun_true", "rk4")
+ADAPTIVE_SOLVERS = ("scipy", "rk45")        # the reference's solver='scipy' with SciPy's default method RK45
 
 
 def n_steps_for(T: float, dt: float, dts: Optional[float]) -> Tuple[int, int, int]:
@@ -36,11 +37,12 @@ class InstanceModel:
     def __init__(self, prog: Program, *, solver: str = "euler", sweep: Sequence[Tuple[str, int]] = (),
                  observers: Optional[Sequence[int]] = None, block: int = 128, fmad: bool = True,
                  const_div_to_mul: bool = False, max_nodes: int = 6000, min_blocks: int = 1):
-        if solver not in FIXED_STEP_SOLVERS:
+        if solver not in FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS:
             raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
-                                      f"Supported solvers: {list(FIXED_STEP_SOLVERS)}.")
+                                      f"Supported solvers: {list(FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS)}.")
         self.prog = prog
         self.solver = solver
+        self.adaptive = solver in ADAPTIVE_SOLVERS
         self.precision = prog.float_precision
         self.real = prog.real_dtype
         self.rhs: ScalarRhs = scalarize(prog, sweep, max_nodes=max_nodes)
@@ -50,7 +52,8 @@ class InstanceModel:
                                                    const_div_to_mul=const_div_to_mul, min_blocks=min_blocks)
         self.fmad = fmad
         self._module: Optional[rt.Module] = None
-        self.t0 = int(np.asarray(prog.arg_by_kind("t").value))
+        t0 = np.asarray(prog.arg_by_kind("t").value)
+        self.t0 = float(t0) if self.adaptive else int(t0)
 
     @property
     def module(self) -> rt.Module:
@@ -71,14 +74,23 @@ class InstanceModel:
 
     # convenience: the drop-in path of BaseBackend.run for a single instance
     def run(self, T: float, dt: float, dts: Optional[float] = None, *, params: Optional[np.ndarray] = None,
-            y0: Optional[np.ndarray] = None, n_inst: Optional[int] = None):
+            y0: Optional[np.ndarray] = None, n_inst: Optional[int] = None, **solver_kwargs):
+        """Fixed-step solvers: ``(out[n_samples, n_obs, B], y_final)``.  ``solver='scipy'`` accepts SciPy's ``rtol``,
+        ``atol``, ``max_step`` and ``method='RK45'`` keywords (base_backend.py:802-812 forwards them to solve_ivp)."""
         steps, store_step, n_samples = n_steps_for(T, dt, dts)
         if n_inst is None:
             n_inst = 1 if params is None else int(np.asarray(params).shape[-1])
+        if self.adaptive:
+            n_samples = int(round(T / (dts if dts else dt)))
         s = self.session(n_inst, n_samples)
         try:
             s.reset(y0=y0, params=params)
-            s.launch(steps, dt, store_step)
+            if self.adaptive:
+                s.launch_adaptive(T, dt, dts, **solver_kwargs)
+            else:
+                if solver_kwargs:
+                    raise TypeError(f"unexpected solver keywords for a fixed-step solver: {sorted(solver_kwargs)}")
+                s.launch(steps, dt, store_step)
             out = s.download()
             y_final = s.download_state()
         finally:
@@ -169,6 +181,51 @@ class InstanceSession:
         self.samples_done += new_samples
         return new_samples
 
+    def launch_adaptive(self, T: float, dt: float, dts: Optional[float] = None, *, rtol: float = 1e-3, atol: float = 1e-6,
+                        max_step: float = np.inf, method: str = "RK45", max_attempts: int = 50_000_000, **unknown):
+        """The whole adaptive integration of every instance in one launch: solve_ivp(method='RK45', first_step=dt,
+        t_eval=linspace(0, T, round(T/dts), endpoint=False)) per instance, each thread with its own step sequence.
+        Raises when an instance fails (step size underflow), like a failed solve_ivp would break the reference's run."""
+        if method not in (None, "RK45"):
+            raise rt.CudaBackendError(f"solver='scipy' on the CUDA backend implements method='RK45' (SciPy's default); "
+                                      f"got method={method!r}")
+        if unknown:
+            raise TypeError(f"unsupported solve_ivp options on the CUDA backend: {sorted(unknown)}")
+        if np.ndim(atol) or np.ndim(rtol):
+            raise rt.CudaBackendError("per-component tolerances are not supported; pass scalar rtol / atol")
+        k = self.m.kernel
+        step = dts if dts else dt
+        n_samples = int(round(T / step))
+        if n_samples > self.n_samples:
+            raise ValueError(f"session holds {self.n_samples} samples, the run records {n_samples}")
+        rtol = max(float(rtol), 100 * np.finfo(float).eps)          # validate_tol, scipy/integrate/_ivp/common.py
+        te_step = (float(T) - 0.0) / n_samples if n_samples else 0.0   # numpy.linspace: step = delta / div
+        opts = np.array([rtol, float(atol), self.m.t0, float(T), float(dt), te_step, float(max_step), float(max_attempts)])
+        self.d_opts = rt.DeviceBuffer.from_host(opts)
+        self.d_status = rt.DeviceBuffer(4 * self.B)
+        self.d_status.zero(self.stream)
+        a = rt.KernelArgs()
+        a.n_steps, a.store_step, a.step0, a.t0, a.eval0 = n_samples, 1, 0, 0, 0
+        a.n_inst, a.sample0, a.dt = self.B, 0, float(dt)
+        a.y, a.out, a.params = self.d_y.ptr, self.d_out.ptr, self.d_params.ptr
+        a.slots, a.rings, a.tables = self.d_slots.ptr, self.d_rings.ptr, self.d_tables.ptr
+        a.consts, a.sync = self.d_opts.ptr, self.d_status.ptr
+        a.iconsts = a.work = None
+        self.m.module.run(k.kernel_name, a, block=k.block, stream=self.stream)
+        status = np.zeros(self.B, dtype=np.uint32)
+        self.d_status.download(status, self.stream)
+        if self.stream is not None:
+            self.stream.synchronize()
+        self.samples_done = n_samples
+        self.attempts = (status >> 4).astype(np.int64)        # RK45 step attempts per instance (6 rhs evaluations each)
+        status = status & 15
+        if status.any():
+            bad = np.nonzero(status)[0]
+            why = {1: "Required step size is less than spacing between numbers.", 2: "attempt budget exhausted"}
+            raise rt.CudaBackendError(f"adaptive integration failed for {bad.size} instance(s), first {int(bad[0])}: "
+                                      f"{why.get(int(status[bad[0]]), 'unknown')}")
+        return n_samples
+
     # -- results
     def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Recorded observers as ``[n_samples, n_obs, B]`` (row k = state at step k*store_step)."""
@@ -190,7 +247,7 @@ class InstanceSession:
         return y
 
     def free(self):
-        for n in ("d_y", "d_out", "d_params", "d_slots", "d_rings", "d_tables"):
+        for n in ("d_y", "d_out", "d_params", "d_slots", "d_rings", "d_tables", "d_opts", "d_status"):
             b = getattr(self, n, None)
             if b is not None:
                 b.free()

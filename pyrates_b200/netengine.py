@@ -244,6 +244,45 @@ def build_check(golden_dir: str) -> None:
         print(f"[build] net {name}/{solver}: {m.kernel.n_phases} phase(s), cubin {len(cubin)} bytes")
 
 
+_CHECK_SWEEP = [("wc_n300_f32", "heun", 256, ["r_ext"]),        # float32 sweep -> tcgen05 3xTF32 coupling GEMM
+                ("wc_n128", "rk4", 128, ["r_ext"])]            # float64 sweep -> DMMA coupling GEMM
+
+
+def build_check_sweeps(golden_dir: str) -> None:
+    for name, solver, nb, sweep in _CHECK_SWEEP:
+        m = NetworkModel(Program.load(os.path.join(golden_dir, name + ".npz")), solver=solver, n_batch=nb, sweep=sweep)
+        cubin = m.module.cubin
+        assert cubin[:4] == b"\x7fELF", name
+        kind = f"tcgen05 tiles 128x{m.kernel.tc['bt']}" if m.kernel.tc else "DMMA / FMA tiles"
+        print(f"[build] net sweep {name}/{solver} x{nb}: {kind}, cubin {len(cubin)} bytes")
+
+
+def smoke_check_sweep(golden_dir: str) -> None:
+    """One small float32 network sweep on the tcgen05 path, two instances checked against the oracle."""
+    from oracle import numpy_oracle as orc
+    name, solver, nb, sweep = _CHECK_SWEEP[0]
+    path = os.path.join(golden_dir, name + ".npz")
+    fx = orc.load_fixture(path)
+    prog = Program.load(path)
+    r = fx["run"]
+    m = NetworkModel(prog, solver=solver, n_batch=nb, sweep=sweep)
+    assert m.kernel.tc is not None
+    params = m.param_defaults[:, None] + np.linspace(-0.2, 0.5, nb)[None, :]
+    out, _ = m.run(r["T"], r["dt"], r["dts"], params=params)
+    f = orc.build_vector_field(prog.source())
+    names = [a.name for a in prog.args]
+    worst = 0.0
+    for b in (0, nb - 1):
+        args = [np.array(a.value, copy=True) for a in prog.args]
+        args[0] = args[0][()]
+        v = args[names.index(sweep[0])]
+        args[names.index(sweep[0])] = np.asarray(params[0, b], dtype=v.dtype)[()]
+        rec, _ = orc.run(f, args, r["T"], r["dt"], r["dts"], solver)
+        worst = max(worst, float(np.max(np.abs(out[:, :, b] - rec)) / np.max(np.abs(rec))))
+    print(f"[smoke] WC N=300 float32 sweep x{nb} (tcgen05 3xTF32 coupling GEMM): max scaled error vs oracle {worst:.3e}")
+    assert worst < 1e-4, worst
+
+
 def smoke_check(golden_dir: str) -> None:
     from oracle import numpy_oracle as orc
     path = os.path.join(golden_dir, "wc_n128.npz")

@@ -373,7 +373,7 @@ class _Interp:
         for a in prog.args:
             v = np.asarray(a.value)
             if a.kind == "t":
-                self.env[a.name] = _obj(self.g.leaf("t", None, isint=True))
+                self.env[a.name] = _obj(self.g.leaf("t", None, isint=bool(np.issubdtype(np.asarray(a.value).dtype, np.integer))))
             elif a.kind == "y":
                 arr = np.empty(v.size, dtype=object)
                 for k in range(v.size):

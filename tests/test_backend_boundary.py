@@ -77,7 +77,7 @@ def test_unsupported_solver_and_no_device_raise(registered):
     from pyrates import CircuitTemplate
     c = _fresh("model_templates.neural_mass_models.qif.qif")
     with pytest.raises(Exception, match="does not support solver"):
-        c.run(simulation_time=0.01, step_size=1e-3, solver="scipy", outputs={"r": "p/qif_op/r"}, backend="cuda",
+        c.run(simulation_time=0.01, step_size=1e-3, solver="julia_dp5", outputs={"r": "p/qif_op/r"}, backend="cuda",
               verbose=False, in_place=False)
     try:
         rt.device_count()
@@ -176,3 +176,21 @@ def test_grid_search_over_population_network_matches_reference_runs(gpu, registe
         got = res.xs(f"wc_n96_{i}", axis=1, level=1)
         assert got.shape == ref.shape
         assert traj_rel_err(got.values, ref.values) <= RTOL[precision], (precision, i)
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("path,out,T,dt,kw", [
+    ("model_templates.neural_mass_models.qif.qif", "p/qif_op/r", 2.0, 1e-3, {}),
+    ("model_templates.neural_mass_models.jansenrit.JRC", "pc/rpo_e_in/v", 0.5, 1e-4, dict(rtol=1e-7, atol=1e-9)),
+    ("model_templates.neural_mass_models.qif.qif_sfa", "p/qif_sfa_op/r", 2.0, 1e-3, dict(method="RK45", rtol=1e-6, atol=1e-8)),
+])
+def test_circuit_run_scipy_solver_on_cuda_matches_solve_ivp(gpu, registered, path, out, T, dt, kw):
+    """solver='scipy' end to end: the reference hands the vector field to scipy.solve_ivp (RK45); the CUDA backend runs
+    the same step controller and dense output on the device."""
+    run = dict(simulation_time=T, step_size=dt, sampling_step_size=dt * 10, solver="scipy", outputs={"o": out},
+               verbose=False, float_precision="float64", clear=True, **kw)
+    ref = _fresh(path).run(backend="default", **run)
+    got = _fresh(path).run(backend="cuda", **run)
+    assert got.shape == ref.shape and np.allclose(got.index, ref.index)
+    assert traj_rel_err(got.values, ref.values) <= 1e-9

@@ -35,4 +35,34 @@ def test_jrc_rk4_stays_in_registers():
 
 def test_unknown_solver_is_rejected():
     with pytest.raises(rt.CudaBackendError, match="does not support solver"):
-        InstanceModel(Program.load(golden_path("qif")), solver="scipy")
+        InstanceModel(Program.load(golden_path("qif")), solver="lsoda")
+
+
+@pytest.mark.parametrize("name", ["qif_rk45", "jrc_rk45", "wc_n8_rk45"])
+def test_adaptive_rk45_kernel_compiles_without_spills(name):
+    """solver='scipy' (solve_ivp RK45 semantics): seven stage vectors + dense output stay in registers."""
+    os.environ["PRB_CACHE_DIR"] = "off"
+    m = InstanceModel(Program.load(golden_path(name)), solver="scipy")
+    assert "typedef double prb_time" in m.kernel.source and "#define PRB_SOLVER 4" in m.kernel.source
+    mod = rt.compile_module(m.kernel.source, f"{name}.cu", verbose_ptxas=True)
+    assert all("0 bytes spill stores" in l for l in mod.log.splitlines() if "spill" in l), mod.log
+
+
+def test_adaptive_solver_rejects_fixed_step_constructs():
+    from pyrates_b200.scalarize import UnsupportedModelError
+    with pytest.raises(UnsupportedModelError, match="adaptive"):
+        InstanceModel(Program.load(golden_path("qsfa_ring_n8")), solver="scipy")        # delay ring buffer
+    with pytest.raises(UnsupportedModelError, match="adaptive"):
+        InstanceModel(Program.load(golden_path("qif_input")), solver="scipy")           # step-indexed input table
+
+
+def test_rk45_tableau_is_scipys_and_reaches_the_kernel_exactly():
+    import numpy as np
+    from oracle import numpy_oracle as orc
+    from pyrates_b200 import rk45
+    for mine, theirs in ((rk45.A, orc.RK45_A), (rk45.B, orc.RK45_B), (rk45.C, orc.RK45_C), (rk45.E, orc.RK45_E), (rk45.P, orc.RK45_P)):
+        assert np.array_equal(np.asarray(mine, dtype=float), theirs)
+    src = InstanceModel(Program.load(golden_path("qif_rk45")), solver="scipy").kernel.source
+    line = [l for l in src.splitlines() if l.startswith("#define PRB_RK45_P_INIT")][0]
+    vals = [float(x) for x in line.split("INIT", 1)[1].replace("{", " ").replace("}", " ").replace(",", " ").split()]
+    assert np.array_equal(np.array(vals).reshape(7, 4), orc.RK45_P)          # repr() literals round-trip bit for bit

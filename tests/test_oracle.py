@@ -7,7 +7,44 @@ from conftest import golden_names, golden_path
 from oracle import numpy_oracle as orc
 
 
-@pytest.mark.parametrize("name", golden_names())
+ADAPTIVE = [n for n in golden_names() if n.endswith("_rk45") or "_rk45_" in n]
+
+
+@pytest.mark.parametrize("name", ADAPTIVE)
+def test_oracle_rk45_reproduces_reference_plus_scipy_bit_exact(name):
+    """solver='scipy': the restated Dormand-Prince stepper, step controller, dense output and t_eval loop (plus the
+    aliased rhs buffer) give exactly what the real reference + SciPy produced in the build container."""
+    fx = orc.load_fixture(golden_path(name))
+    r = fx["run"]
+    f = orc.build_vector_field(fx["source"])
+    args = [np.array(a, copy=True) for a in fx["args"]]
+    args[0] = args[0][()]
+    rec, times = orc.run_adaptive(f, args, r["T"], r["dt"], r["dts"], rtol=r["rtol"], atol=r["atol"])
+    ref = fx["extra"]["rec_scipy"]
+    assert rec.shape == ref.shape and np.array_equal(rec, ref)
+
+
+def test_oracle_rk45_coefficients_are_scipys():
+    rk = pytest.importorskip("scipy.integrate._ivp.rk")
+    for mine, theirs in ((orc.RK45_A, rk.RK45.A), (orc.RK45_B, rk.RK45.B), (orc.RK45_C, rk.RK45.C), (orc.RK45_E, rk.RK45.E),
+                         (orc.RK45_P, rk.RK45.P)):
+        assert np.array_equal(mine, theirs)
+
+
+def test_oracle_rk45_matches_solve_ivp_on_a_plain_function():
+    """Without the aliased buffer (a function returning fresh arrays) the restatement is scipy.solve_ivp itself."""
+    integ = pytest.importorskip("scipy.integrate")
+    f = lambda t, y: np.array([y[1], -4.0 * y[0] - 0.1 * y[1] + np.sin(3 * t)])
+    times = np.linspace(0.0, 5.0, 100, endpoint=False)
+    ref = integ.solve_ivp(f, (0.0, 5.0), np.array([1.0, 0.0]), first_step=1e-3, t_eval=times, rtol=1e-6, atol=1e-9).y.T
+    rec = orc.solve_rk45(f, (), 5.0, 1e-3, np.array([1.0, 0.0]), 0.0, times, rtol=1e-6, atol=1e-9, aliased=False)
+    assert np.array_equal(rec, ref)
+    # the reference's in-place rhs buffer changes what a rejected attempt restarts from: measurably different numbers
+    quirk = orc.solve_rk45(f, (), 5.0, 1e-3, np.array([1.0, 0.0]), 0.0, times, rtol=1e-6, atol=1e-9, aliased=True)
+    assert 1e-6 < np.max(np.abs(quirk - ref)) < 1e-2
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n not in ADAPTIVE])
 @pytest.mark.parametrize("solver", ["euler", "heun"])
 def test_oracle_reproduces_reference_bit_exact(name, solver):
     fx = orc.load_fixture(golden_path(name))
