@@ -307,7 +307,9 @@ class CudaBackend:
             # circuit with SciPy's RK45 step controller and dense output (csrc/templates/inst_kernel.cuh)
             model = InstanceModel(prog, solver=solver, fmad=self.fmad, max_nodes=20000)
             self.last_model = model
-            out, y_final = model.run(T, dt, dts, **kwargs)
+            # like solve_ivp, ignore options that have no effect for RK45 (the reference forwards e.g. float_precision)
+            opts = {k: v for k, v in kwargs.items() if k in ("rtol", "atol", "max_step", "method")}
+            out, y_final = model.run(T, dt, dts, **opts)
         else:
             model = build_model(prog, solver=solver, exec_model=self.exec_model, fmad=self.fmad,
                                 const_div_to_mul=self.const_div_to_mul)

@@ -158,6 +158,10 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     chunk_samples = kwargs.pop("chunk_samples", 100)
     const_div_to_mul = kwargs.pop("const_div_to_mul", False)
     float_precision = kwargs.pop("float_precision", "float32")
+    # solve_ivp options of the adaptive solver (reference: forwarded through run() to BaseBackend._solve_scipy)
+    solver_kw = {k: kwargs.pop(k) for k in ("rtol", "atol", "max_step", "method") if k in kwargs}
+    exec_model = kwargs.pop("exec_model", "auto")
+    tensor_core = kwargs.pop("tensor_core", "auto")
 
     if type(param_grid) is dict:
         param_grid = linearize_grid(param_grid, permute_grid)
@@ -213,13 +217,12 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     grid_vals = {k: np.asarray(param_grid[k].values[lo:hi], dtype=np.float64) for k in keys}
     table = np.stack([grid_vals[k] for k in rows]) if rows else np.zeros((0, B))
 
-    exec_model = kwargs.pop("exec_model", "auto")
     sw = None
     if exec_model in ("auto", "instance"):
         try:
             sw = BatchedSweep(prog, sweep, base["observers"], solver=solver, T=simulation_time, dt=step_size,
                               dts=sampling_step_size, n_inst=B, chunk_samples=chunk_samples,
-                              const_div_to_mul=const_div_to_mul)
+                              const_div_to_mul=const_div_to_mul, solver_kwargs=solver_kw)
         except UnsupportedModelError as e:
             if exec_model == "instance" or "too large" not in str(e):
                 raise
@@ -234,7 +237,7 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
         # the circuit is a network (populations, dense coupling): all grid points share the connectivity and step
         # together in the persistent network kernel, their couplings as one GEMM per evaluation
         ns = NetworkSweep(prog, sweep, base["observers"], solver=solver, T=simulation_time, dt=step_size,
-                          dts=sampling_step_size, n_inst=B, tensor_core=kwargs.pop("tensor_core", "auto"))
+                          dts=sampling_step_size, n_inst=B, tensor_core=tensor_core)
         for elem, k in y0_rows:
             ns.set_y0(elem, grid_vals[k])
         res = ns.run(table)

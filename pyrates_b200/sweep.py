@@ -46,9 +46,15 @@ class BatchedSweep:
     def __init__(self, prog: Program, sweep: Sequence[Tuple[str, int]], observers: Sequence[int], *,
                  solver: str, T: float, dt: float, dts: Optional[float], n_inst: int,
                  chunk_samples: int = 100, const_div_to_mul: bool = True, block: int = 128,
-                 pinned_result: bool = True, min_blocks: int = 5):
+                 pinned_result: bool = True, min_blocks: int = 5, solver_kwargs: Optional[dict] = None):
         # min_blocks=5 caps the kernel at 96 registers -> 20 warps/SM; measured +3.5 % on the JRC/RK4 sweep
         # (scripts/tune_inst.py), the kernel being FP64-pipe bound either way
+        from .engine import ADAPTIVE_SOLVERS
+        self.adaptive = solver in ADAPTIVE_SOLVERS
+        self.solver_kwargs = dict(solver_kwargs or {})
+        self.T, self.dts = float(T), dts
+        if self.adaptive:
+            const_div_to_mul, min_blocks = False, 1          # RK45 keeps 7 stage vectors in registers: no occupancy cap
         self.model = InstanceModel(prog, solver=solver, sweep=sweep, observers=observers, block=block,
                                    const_div_to_mul=const_div_to_mul, min_blocks=min_blocks if block == 128 else 1)
         order = [(p.arg, p.elem) for p in self.model.rhs.params]
@@ -62,7 +68,9 @@ class BatchedSweep:
         self.chunk_samples = max(1, min(int(chunk_samples), max(self.n_samples, 1)))
         self.compute = rt.Stream()
         self.copy = rt.Stream()
-        self.sess = self.model.session(self.B, 0, stream=self.compute)
+        if self.adaptive:
+            self.n_samples = int(round(T / (dts if dts else dt)))
+        self.sess = self.model.session(self.B, self.n_samples if self.adaptive else 0, stream=self.compute)
         item = np.dtype(self.real).itemsize
         self._chunk_bytes = self.chunk_samples * self.n_obs * self.B * item
         self.d_chunks = [rt.DeviceBuffer(max(self._chunk_bytes, 8)) for _ in range(2)]
@@ -104,6 +112,15 @@ class BatchedSweep:
     def integrate(self, read_back: bool = True):
         """Launch all time chunks; with ``read_back`` stream each chunk D2H into the result array."""
         s = self.sess
+        if self.adaptive:
+            # every instance has its own step sequence: one launch for the whole horizon, then one D2H
+            s.launch_adaptive(self.T, self.dt, self.dts, **self.solver_kwargs)
+            if read_back and self.n_samples:
+                item = np.dtype(self.real).itemsize
+                rt._check(rt.lib().prb_memcpy_d2h(self.h_out.ptr, s.d_out.ptr, self.n_samples * self.n_obs * self.B * item,
+                                                  self.compute.handle))
+            self.launches_per_run = 1
+            return 1
         steps_per_chunk = self.chunk_samples * self.store_step
         done, sample, c = 0, 0, 0
         item = np.dtype(self.real).itemsize

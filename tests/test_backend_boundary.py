@@ -194,3 +194,23 @@ def test_circuit_run_scipy_solver_on_cuda_matches_solve_ivp(gpu, registered, pat
     got = _fresh(path).run(backend="cuda", **run)
     assert got.shape == ref.shape and np.allclose(got.index, ref.index)
     assert traj_rel_err(got.values, ref.values) <= 1e-9
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_grid_search_with_adaptive_solver_matches_reference_runs(gpu, registered):
+    """grid_search(solver='scipy'): every grid point runs its own RK45 step sequence in its own thread; checked against
+    the reference's solver='scipy' run (SciPy solve_ivp) of individual grid points."""
+    import pyrates
+    from pyrates.utility import linearize_grid, adapt_circuit
+    path = "model_templates.neural_mass_models.jansenrit.JRC"
+    grid = linearize_grid({"u": np.linspace(120.0, 320.0, 12)}, permute=True)
+    pm = {"u": {"vars": ["rpo_e_in/u"], "nodes": ["pc"]}}
+    kw = dict(step_size=1e-4, simulation_time=0.3, sampling_step_size=1e-3, solver="scipy", float_precision="float64",
+              rtol=1e-7, atol=1e-9)
+    res, pmap = pyrates.grid_search(path, grid, pm, outputs={"v": "pc/rpo_e_in/v"}, backend="cuda", verbose=False, **kw)
+    assert res.shape == (300, 12)
+    for i in (0, 7, 11):
+        c = adapt_circuit(path, {"u": float(grid["u"].values[i])}, pm)
+        ref = c.run(outputs={"v": "pc/rpo_e_in/v"}, backend="default", verbose=False, clear=True, **kw)
+        assert traj_rel_err(res.iloc[:, [i]].values, ref.values) <= 1e-7, i
