@@ -122,7 +122,8 @@ def main():
     ap.add_argument("--sim-time", type=float, default=1.0)
     ap.add_argument("--cpu-sim-time", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--strict-div", action="store_true", help="keep IEEE divisions by constants (default: multiply by reciprocal)")
+    ap.add_argument("--strict-div", action="store_true",
+                    help="keep IEEE divisions by constants (default: multiply by the reciprocal)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -247,7 +248,7 @@ def main():
                      "note": "state/stages are register-resident across the launch: real DRAM traffic is only the "
                              "observer store; the true bound is the FP64 pipe (see DESIGN.md)"},
         "kernel": {"regs": info["regs"], "local_bytes": info["local_bytes"], "blocks_per_sm": info["max_blocks_per_sm"],
-                   "block": sw.model.kernel.block, "const_div_to_mul": not a.strict_div},
+                   "block": sw.model.kernel.block, "const_div_to_mul": not a.strict_div, "fast_math": False},
         "jit_s": jit_s, "numa_node_rank0": numa_node,
         "clocks": clocks.stop(wall0, wall1) if clocks else None,
     }

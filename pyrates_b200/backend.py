@@ -147,6 +147,7 @@ class CudaBackend:
         self.device = kwargs.pop('device', None)
         self.fmad = kwargs.pop('fmad', True)
         self.const_div_to_mul = kwargs.pop('const_div_to_mul', False)
+        self.fast_math = kwargs.pop('fast_math', False)
         self.exec_model = kwargs.pop('exec_model', 'auto')        # 'auto' | 'instance' | 'network'
         self.last_model = None
         self._head: Optional[Tuple[str, str, str, List[str]]] = None
@@ -312,7 +313,7 @@ class CudaBackend:
             out, y_final = model.run(T, dt, dts, **opts)
         else:
             model = build_model(prog, solver=solver, exec_model=self.exec_model, fmad=self.fmad,
-                                const_div_to_mul=self.const_div_to_mul)
+                                const_div_to_mul=self.const_div_to_mul, fast_math=self.fast_math)
             self.last_model = model
             out, y_final = model.run(T, dt, dts)
         rec = np.ascontiguousarray(out[:, :, 0])
@@ -338,4 +339,5 @@ def build_model(prog: Program, *, solver: str, exec_model: str = "auto", **kw):
                 raise
     from .netengine import NetworkModel
     kw.pop("const_div_to_mul", None)
+    kw.pop("fast_math", None)
     return NetworkModel(prog, solver=solver, **kw)

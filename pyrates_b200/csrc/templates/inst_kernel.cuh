@@ -28,6 +28,17 @@ __device__ __forceinline__ void prb_axpy(real (&o)[N], const real (&y)[N], const
 #define PRB_MIN_BLOCKS 1
 #endif
 
+// fast_math kernels read 2^(j/64) from shared memory (divergent indices: a __constant__ read would serialise)
+#ifdef PRB_USE_ETAB
+#define PRB_STAGE_ETAB __shared__ double prb_etab[64]; \
+    for (int q = threadIdx.x; q < 64; q += blockDim.x) prb_etab[q] = PRB_EXP_TAB[q]; \
+    __syncthreads();
+#define PRB_SET_ETAB T.etab = prb_etab;
+#else
+#define PRB_STAGE_ETAB
+#define PRB_SET_ETAB
+#endif
+
 #if PRB_SOLVER == PRB_SOLVER_RK45
 // ---- adaptive solver: the reference's solver='scipy' == scipy.integrate.solve_ivp(method='RK45', first_step=dt,
 // t_eval=times) (BaseBackend._solve_scipy, pyrates/backend/base/base_backend.py:802-812).  Dormand-Prince 5(4) with
@@ -51,9 +62,11 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
     constexpr double P_[7][4] = PRB_RK45_P_INIT;         // dense output: y(t_old + x h) = y_old + h * sum_c Q[:, c] x^(c+1), Q = K^T P
     const long long B = A.n_inst;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    PRB_STAGE_ETAB
     if (b >= B) return;
     PrbThread T;
     prb_thread_init(T, A, b);
+    PRB_SET_ETAB
     const double* __restrict__ opt = (const double*)A.consts;
     const double rtol = opt[0], atol = opt[1], t_bound = opt[3], te_step = opt[5], max_step = opt[6];
     const long long max_attempts = (long long)opt[7];
@@ -164,10 +177,12 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
 {
     const long long B = A.n_inst;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    PRB_STAGE_ETAB
     if (b >= B) return;
 
     PrbThread T;
     prb_thread_init(T, A, b);
+    PRB_SET_ETAB
 
     real* __restrict__ Y = (real*)A.y;
     real y[PRB_NS];
@@ -244,9 +259,11 @@ prb_rhs_eval(const __grid_constant__ prb_kernel_args A)
 {
     const long long B = A.n_inst;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    PRB_STAGE_ETAB
     if (b >= B) return;
     PrbThread T;
     prb_thread_init(T, A, b);
+    PRB_SET_ETAB
     const real* __restrict__ Y = (const real*)A.y;
     real y[PRB_NS], k[PRB_NS];
     PRB_UNROLL_NS

@@ -70,7 +70,8 @@ def _lit(v: float, f32: bool) -> str:
     return f"({r})" if r.startswith("-") else r
 
 
-def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time: bool = False) -> List[str]:
+def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time: bool = False,
+                  fast_math: bool = False) -> List[str]:
     """Straight-line statements computing dy[] (+ ring / slot stores) from y[], T."""
     g = rhs.graph
     ring_off = np.cumsum([0] + [r.rows * r.length for r in rhs.rings])
@@ -127,6 +128,8 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
                 c = float(g.const_value(a[1]))
                 inv = float(np.float32(1.0) / np.float32(c)) if f32 else 1.0 / c
                 expr = f"{ref(a[0])} * {_lit(inv, f32)}"
+            elif fast_math and not f32:
+                expr = f"prb_fast_div({ref(a[0])}, {ref(a[1])})"
             else:
                 expr = f"{ref(a[0])} / {ref(a[1])}"
         elif op == "neg":
@@ -139,6 +142,8 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
             expr = f"prb_min({ref(a[0])}, {ref(a[1])})"
         elif op == "sign":
             expr = f"prb_sign({ref(a[0])})"
+        elif op == "exp" and fast_math and not f32:
+            expr = f"prb_fast_exp({ref(a[0])}, T.etab)"
         elif op in _FUNC:
             expr = f"{_FUNC[op]}({ref(a[0])})"
         else:
@@ -160,7 +165,8 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
 
 
 def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: Sequence[int],
-                     block: int = 128, const_div_to_mul: bool = False, min_blocks: int = 1) -> InstKernel:
+                     block: int = 128, const_div_to_mul: bool = False, min_blocks: int = 1,
+                     fast_math: bool = False) -> InstKernel:
     """Generate the full CUDA C source of the fused rhs+solver instance kernel."""
     if solver not in SOLVER_IDS:
         raise ValueError(f"unknown solver `{solver}`; supported: {sorted(SOLVER_IDS)}")
@@ -171,7 +177,8 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     if adaptive and (rhs.rings or rhs.tables or rhs.slots):
         raise UnsupportedModelError("adaptive integration (solver='scipy') needs a pure vector field: delay ring buffers, "
                                     "step-indexed input tables and mutable buffers are fixed-step constructs")
-    body = emit_rhs_body(rhs, f32, const_div_to_mul, float_time=adaptive)
+    body = emit_rhs_body(rhs, f32, const_div_to_mul, float_time=adaptive, fast_math=fast_math)
+    use_etab = any("prb_fast_exp(" in l for l in body)
     np_ = len(rhs.params)
     src: List[str] = []
     src.append("// Generated by pyrates_b200.emit_inst — do not edit.  Instance execution model (1 thread = 1 instance).")
@@ -198,7 +205,44 @@ struct PrbThread {
     real* __restrict__ slots;
     real* __restrict__ rings;
     const real* __restrict__ tables;
+    const double* etab;            // shared-memory copy of PRB_EXP_TAB (fast_math kernels)
 };
+// ---- fast_math (fp64): cheaper exp / division for FP64-pipe-bound kernels (the JRC sweep spends ~70 % of its fp64
+// instructions in 3 sigmoids per evaluation).  exp: x = (64 k + j) ln2/64 + r, |r| <= ln2/128,
+// e^x = 2^k * 2^(j/64) * (1 + r + .. + r^5/120): 10 fp64 instructions + one shared-memory table read instead of ~20;
+// <= 2.1 ulp for |x| <= 700 (validated against long-double exp on the host, tests/test_compile_inst.py), library exp
+// outside.  Division: rcp.approx.ftz.f64 + two Newton steps (5 fp64 instructions), IEEE division for zero / denormal /
+// huge / non-finite divisors.  Both stay far inside the 1e-9 trajectory tolerance; off by default in CudaBackend.run.
+__device__ __constant__ double PRB_EXP_TAB[64] = {1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, 1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199, 1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418, 1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812, 1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687, 1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783, 1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303, 1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112, 1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647, 1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384, 1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267, 1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364, 1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062, 1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989, 1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656, 1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+__device__ __noinline__ double prb_exp_slow(const double z) { return exp(z); }
+__device__ __noinline__ double prb_div_slow(const double a, const double b) { return a / b; }
+__device__ __forceinline__ double prb_fast_exp(const double z, const double* __restrict__ tab) {
+    if (!(fabs(z) <= 700.0)) return prb_exp_slow(z);
+    const double t = fma(z, 92.33248261689366, 6755399441055744.0);          // 64/ln2, 1.5 * 2^52
+    const int n = __double2loint(t);
+    const double nd = t - 6755399441055744.0;
+    double r = fma(nd, -0.010830424609594047, z);                            // ln2/64, high part (26 trailing zero bits)
+    r = fma(nd, -8.66550983900947e-11, r);                                   //         low part
+    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = q * r;
+    const double tj = tab[n & 63];
+    const double e = fma(tj, q, tj);
+    return __hiloint2double(__double2hiint(e) + ((n >> 6) << 20), __double2loint(e));   // * 2^k: |x| <= 700 keeps it normal
+}
+__device__ __forceinline__ double prb_fast_div(const double a, const double b) {
+    const double ab = fabs(b);
+    if (!(ab > 1e-290 && ab < 1e290)) return prb_div_slow(a, b);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    return a * r;
+}
 __device__ __forceinline__ real prb_max(real a, real b) { return (a != a || b != b) ? a + b : (a > b ? a : b); }
 __device__ __forceinline__ real prb_min(real a, real b) { return (a != a || b != b) ? a + b : (a < b ? a : b); }
 __device__ __forceinline__ real prb_sign(real a) { return (real)((a > (real)0) - (a < (real)0)); }
@@ -210,8 +254,10 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
     return (long long)p;
 }
 """)
+    if use_etab:
+        src.append("#define PRB_USE_ETAB 1")
     init = ["__device__ __forceinline__ void prb_thread_init(PrbThread& T, const prb_kernel_args& A, long long b) {",
-            "    T.b = b; T.B = A.n_inst;",
+            "    T.b = b; T.B = A.n_inst; T.etab = nullptr;",
             "    T.slots = (real*)A.slots; T.rings = (real*)A.rings; T.tables = (const real*)A.tables;"]
     if np_:
         init.append("    const real* __restrict__ P = (const real*)A.params;")

@@ -36,7 +36,7 @@ class InstanceModel:
 
     def __init__(self, prog: Program, *, solver: str = "euler", sweep: Sequence[Tuple[str, int]] = (),
                  observers: Optional[Sequence[int]] = None, block: int = 128, fmad: bool = True,
-                 const_div_to_mul: bool = False, max_nodes: int = 6000, min_blocks: int = 1):
+                 const_div_to_mul: bool = False, max_nodes: int = 6000, min_blocks: int = 1, fast_math: bool = False):
         if solver not in FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS:
             raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
                                       f"Supported solvers: {list(FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS)}.")
@@ -49,7 +49,8 @@ class InstanceModel:
         self.observers = list(range(prog.n_state)) if observers is None else [int(o) for o in observers]
         self.kernel: InstKernel = emit_inst_kernel(self.rhs, solver=solver, precision=self.precision,
                                                    observers=self.observers, block=block,
-                                                   const_div_to_mul=const_div_to_mul, min_blocks=min_blocks)
+                                                   const_div_to_mul=const_div_to_mul, min_blocks=min_blocks,
+                                                   fast_math=fast_math)
         self.fmad = fmad
         self._module: Optional[rt.Module] = None
         t0 = np.asarray(prog.arg_by_kind("t").value)

@@ -157,6 +157,7 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     kwargs.pop("clear", None)
     chunk_samples = kwargs.pop("chunk_samples", 100)
     const_div_to_mul = kwargs.pop("const_div_to_mul", False)
+    fast_math = kwargs.pop("fast_math", False)
     float_precision = kwargs.pop("float_precision", "float32")
     # solve_ivp options of the adaptive solver (reference: forwarded through run() to BaseBackend._solve_scipy)
     solver_kw = {k: kwargs.pop(k) for k in ("rtol", "atol", "max_step", "method") if k in kwargs}
@@ -222,7 +223,7 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
         try:
             sw = BatchedSweep(prog, sweep, base["observers"], solver=solver, T=simulation_time, dt=step_size,
                               dts=sampling_step_size, n_inst=B, chunk_samples=chunk_samples,
-                              const_div_to_mul=const_div_to_mul, solver_kwargs=solver_kw)
+                              const_div_to_mul=const_div_to_mul, solver_kwargs=solver_kw, fast_math=fast_math)
         except UnsupportedModelError as e:
             if exec_model == "instance" or "too large" not in str(e):
                 raise

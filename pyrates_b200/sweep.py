@@ -46,17 +46,21 @@ class BatchedSweep:
     def __init__(self, prog: Program, sweep: Sequence[Tuple[str, int]], observers: Sequence[int], *,
                  solver: str, T: float, dt: float, dts: Optional[float], n_inst: int,
                  chunk_samples: int = 100, const_div_to_mul: bool = True, block: int = 128,
-                 pinned_result: bool = True, min_blocks: int = 5, solver_kwargs: Optional[dict] = None):
+                 pinned_result: bool = True, min_blocks: int = 5, solver_kwargs: Optional[dict] = None,
+                 fast_math: Optional[bool] = None):
         # min_blocks=5 caps the kernel at 96 registers -> 20 warps/SM; measured +3.5 % on the JRC/RK4 sweep
         # (scripts/tune_inst.py), the kernel being FP64-pipe bound either way
         from .engine import ADAPTIVE_SOLVERS
         self.adaptive = solver in ADAPTIVE_SOLVERS
         self.solver_kwargs = dict(solver_kwargs or {})
         self.T, self.dts = float(T), dts
+        if fast_math is None:
+            fast_math = False        # measured +1.6 % on the JRC sweep (issue-bound once the fp64 count drops): opt-in only
         if self.adaptive:
-            const_div_to_mul, min_blocks = False, 1          # RK45 keeps 7 stage vectors in registers: no occupancy cap
+            const_div_to_mul, fast_math, min_blocks = False, False, 1   # RK45 keeps 7 stage vectors in registers: no occupancy cap
         self.model = InstanceModel(prog, solver=solver, sweep=sweep, observers=observers, block=block,
-                                   const_div_to_mul=const_div_to_mul, min_blocks=min_blocks if block == 128 else 1)
+                                   const_div_to_mul=const_div_to_mul, min_blocks=min_blocks if block == 128 else 1,
+                                   fast_math=fast_math)
         order = [(p.arg, p.elem) for p in self.model.rhs.params]
         self._perm = [order.index((a, int(e))) for a, e in sweep]      # user row k -> kernel param row
         self.sweep = list(sweep)

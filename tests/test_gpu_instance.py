@@ -130,3 +130,12 @@ def test_adaptive_rk45_batch_has_independent_step_sequences(gpu):
         # observed 0 .. 2e-9; the bound is 1e-7 = rtol / 10, three orders below the solver's own error
         assert traj_rel_err(out[:, :, b], rec) <= 1e-7, b
 
+
+
+@pytest.mark.parametrize("name,solver", [("jrc", "rk4"), ("jrc_2delay", "heun"), ("wc_n8", "euler"), ("qif_sfa", "heun_true")])
+def test_fast_math_variant_keeps_fp64_parity(gpu, name, solver):
+    """Opt-in fast_math (table exp, rcp + Newton division): same 1e-9 tolerance as the default kernels."""
+    fx = orc.load_fixture(golden_path(name))
+    r = fx["run"]
+    out, _ = InstanceModel(Program.load(golden_path(name)), solver=solver, fast_math=True, const_div_to_mul=True).run(r["T"], r["dt"], r["dts"])
+    assert traj_rel_err(out[:, :, 0], fx["extra"][f"rec_{solver}"]) <= 1e-9
