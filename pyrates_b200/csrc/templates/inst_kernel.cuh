@@ -33,7 +33,7 @@ __device__ __forceinline__ void prb_axpy(real (&o)[N], const real (&y)[N], const
 #define PRB_STAGE_ETAB __shared__ double prb_etab[64]; \
     for (int q = threadIdx.x; q < 64; q += blockDim.x) prb_etab[q] = PRB_EXP_TAB[q]; \
     __syncthreads();
-#define PRB_SET_ETAB T.etab = prb_etab;
+#define PRB_SET_ETAB T.etab = prb_etab; T.etab_s = (unsigned int)__cvta_generic_to_shared(prb_etab);
 #else
 #define PRB_STAGE_ETAB
 #define PRB_SET_ETAB

@@ -71,20 +71,31 @@ def _lit(v: float, f32: bool) -> str:
 
 
 def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time: bool = False,
-                  fast_math: bool = False) -> List[str]:
+                  fast_math: bool = False, spec: bool = False) -> List[str]:
     """Straight-line statements computing dy[] (+ ring / slot stores) from y[], T."""
     g = rhs.graph
     ring_off = np.cumsum([0] + [r.rows * r.length for r in rhs.rings])
     tab_off = np.cumsum([0] + [int(np.prod(t.shape)) for t in rhs.tables])
     lines: List[str] = []
+    lit_table: List[float] = []          # fast_math: doubles that do not fit an instruction immediate -> __constant__ table
+
+    def lit(v: float) -> str:
+        """fp64 instructions take a 32-bit immediate (the high word); any other double costs two UMOV / IMAD.MOV per use
+        when written as a literal (ncu: 35 % of the JRC loop's issue slots).  Read from a __constant__ table instead: the
+        compiler loads it once into uniform registers (LDCU) or uses the c[bank][offset] operand form."""
+        if not fast_math or f32 or not math.isfinite(v) or (np.float64(v).view(np.uint64) & np.uint64(0xFFFFFFFF)) == 0:
+            return _lit(v, f32)
+        if v not in lit_table:
+            lit_table.append(v)
+        return f"PRB_LIT[{lit_table.index(v)}]"
 
     def ref(i: int, want_real: bool = True) -> str:
         op = g.ops[i]
         if op == "const":
             v = g.const_value(i)
             if g.isint[i]:
-                return _lit(float(v), f32) if want_real else (f"({int(v)}LL)" if v < 0 else f"{int(v)}LL")
-            return _lit(float(v), f32)
+                return lit(float(v)) if want_real else (f"({int(v)}LL)" if v < 0 else f"{int(v)}LL")
+            return lit(float(v))
         if op == "state":
             return f"y[{g.payload[i]}]"
         if op == "param":
@@ -98,10 +109,51 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
             return f"((real){name})"
         return name
 
-    for i in rhs.live_nodes():
+    def const_chain(i: int):
+        """fast_math: (base node, factor) such that node i == base * factor through a chain of multiplications /
+        divisions by compile-time constants (x * c1 * c2, x / c1 * c2 ...): emitted as ONE multiply by the folded constant
+        (reassociation: <= 1 ulp per folded factor)."""
+        f = 1.0
+        while not g.isint[i] and g.ops[i] in ("mul", "div"):
+            x, y_ = g.args[i]
+            if g.ops[i] == "mul" and g.is_const(y_) and not g.is_const(x):
+                f, i = f * float(g.const_value(y_)), x
+            elif g.ops[i] == "mul" and g.is_const(x) and not g.is_const(y_):
+                f, i = f * float(g.const_value(x)), y_
+            elif g.ops[i] == "div" and g.is_const(y_) and not g.is_const(x) and float(g.const_value(y_)) != 0.0:
+                f, i = f / float(g.const_value(y_)), x
+            else:
+                break
+        return i, f
+
+    live = list(rhs.live_nodes())
+    if fast_math and not f32:
+        # nodes that only fed a folded chain are dead now: recompute liveness over the rewritten expressions
+        needed, stack = set(), [n for n in rhs.dy] + [n for *_, n in rhs.ring_writes] + [n for _, n in rhs.slot_writes]
+        while stack:
+            i = stack.pop()
+            if i in needed:
+                continue
+            needed.add(i)
+            if not g.isint[i] and g.ops[i] in ("mul", "div"):
+                base, f = const_chain(i)
+                if base != i and math.isfinite(f) and f != 0.0:
+                    stack.append(base)
+                    continue
+            stack.extend(g.args[i])
+            if g.ops[i] == "table":
+                stack.append(g.payload[i][1])
+        live = [i for i in live if i in needed]
+
+    for i in live:
         op, a = g.ops[i], g.args[i]
         if op in ("const", "state", "param", "t"):
             continue
+        if fast_math and not f32 and not g.isint[i] and op in ("mul", "div"):
+            base, f = const_chain(i)
+            if base != i and math.isfinite(f) and f != 0.0:
+                lines.append(f"const real v{i} = {ref(base)} * {lit(f)};")
+                continue
         if g.isint[i]:
             x, y_ = (ref(a[0], False), ref(a[1], False) if len(a) > 1 else None)
             expr = {"add": f"{x} + {y_}", "sub": f"{x} - {y_}", "mul": f"{x} * {y_}", "neg": f"-{x}"}[op]
@@ -127,9 +179,9 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
             if const_div_to_mul and g.is_const(a[1]) and float(g.const_value(a[1])) != 0.0:
                 c = float(g.const_value(a[1]))
                 inv = float(np.float32(1.0) / np.float32(c)) if f32 else 1.0 / c
-                expr = f"{ref(a[0])} * {_lit(inv, f32)}"
+                expr = f"{ref(a[0])} * {lit(inv)}"
             elif fast_math and not f32:
-                expr = f"prb_fast_div({ref(a[0])}, {ref(a[1])})"
+                expr = f"prb_spec_div({ref(a[0])}, {ref(a[1])}, bad)" if spec else f"prb_fast_div({ref(a[0])}, {ref(a[1])})"
             else:
                 expr = f"{ref(a[0])} / {ref(a[1])}"
         elif op == "neg":
@@ -143,7 +195,7 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
         elif op == "sign":
             expr = f"prb_sign({ref(a[0])})"
         elif op == "exp" and fast_math and not f32:
-            expr = f"prb_fast_exp({ref(a[0])}, T.etab)"
+            expr = f"prb_spec_exp({ref(a[0])}, T.etab_s, bad)" if spec else f"prb_fast_exp({ref(a[0])}, T.etab)"
         elif op in _FUNC:
             expr = f"{_FUNC[op]}({ref(a[0])})"
         else:
@@ -161,6 +213,8 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
     for k, r in enumerate(rhs.rings):
         if r.rolls_per_eval:
             lines.append(f"T.head[{k}] = (T.head[{k}] + {r.rolls_per_eval % r.length}) % {r.length};")
+    if lit_table:
+        lines.insert(0, "// PRB_LIT = {" + ", ".join(repr(v) for v in lit_table) + "}")
     return lines
 
 
@@ -177,8 +231,12 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     if adaptive and (rhs.rings or rhs.tables or rhs.slots):
         raise UnsupportedModelError("adaptive integration (solver='scipy') needs a pure vector field: delay ring buffers, "
                                     "step-indexed input tables and mutable buffers are fixed-step constructs")
-    body = emit_rhs_body(rhs, f32, const_div_to_mul, float_time=adaptive, fast_math=fast_math)
-    use_etab = any("prb_fast_exp(" in l for l in body)
+    pure = not (rhs.rings or rhs.slots or rhs.ring_writes or rhs.slot_writes)
+    spec = bool(fast_math and not f32 and pure)
+    body = emit_rhs_body(rhs, f32, const_div_to_mul, float_time=adaptive, fast_math=fast_math, spec=spec)
+    exact_body = emit_rhs_body(rhs, f32, const_div_to_mul, float_time=adaptive) if spec else None
+    spec = spec and any("prb_spec_" in l for l in body)
+    use_etab = any("prb_fast_exp(" in l or "prb_spec_exp(" in l for l in body)
     np_ = len(rhs.params)
     src: List[str] = []
     src.append("// Generated by pyrates_b200.emit_inst — do not edit.  Instance execution model (1 thread = 1 instance).")
@@ -206,6 +264,7 @@ struct PrbThread {
     real* __restrict__ rings;
     const real* __restrict__ tables;
     const double* etab;            // shared-memory copy of PRB_EXP_TAB (fast_math kernels)
+    unsigned int etab_s;           // the same as a 32-bit shared-window address (ld.shared without S2UR per use)
 };
 // ---- fast_math (fp64): cheaper exp / division for FP64-pipe-bound kernels (the JRC sweep spends ~70 % of its fp64
 // instructions in 3 sigmoids per evaluation).  exp: x = (64 k + j) ln2/64 + r, |r| <= ln2/128,
@@ -214,23 +273,53 @@ struct PrbThread {
 // outside.  Division: rcp.approx.ftz.f64 + two Newton steps (5 fp64 instructions), IEEE division for zero / denormal /
 // huge / non-finite divisors.  Both stay far inside the 1e-9 trajectory tolerance; off by default in CudaBackend.run.
 __device__ __constant__ double PRB_EXP_TAB[64] = {1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, 1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199, 1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418, 1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812, 1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687, 1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783, 1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303, 1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112, 1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647, 1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384, 1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267, 1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364, 1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062, 1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989, 1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656, 1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+__device__ __constant__ double PRB_EXP_K[6] = {92.33248261689366, -0.010830424609594047, -8.66550983900947e-11,
+                                               1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};      // uniform registers, loaded once
 __device__ __noinline__ double prb_exp_slow(const double z) { return exp(z); }
 __device__ __noinline__ double prb_div_slow(const double a, const double b) { return a / b; }
 __device__ __forceinline__ double prb_fast_exp(const double z, const double* __restrict__ tab) {
     if (!(fabs(z) <= 700.0)) return prb_exp_slow(z);
-    const double t = fma(z, 92.33248261689366, 6755399441055744.0);          // 64/ln2, 1.5 * 2^52
+    const double t = fma(z, PRB_EXP_K[0], 6755399441055744.0);               // 64/ln2, 1.5 * 2^52 (an immediate)
     const int n = __double2loint(t);
     const double nd = t - 6755399441055744.0;
-    double r = fma(nd, -0.010830424609594047, z);                            // ln2/64, high part (26 trailing zero bits)
-    r = fma(nd, -8.66550983900947e-11, r);                                   //         low part
-    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    q = fma(q, r, 1.0 / 6.0);
+    double r = fma(nd, PRB_EXP_K[1], z);                                     // -ln2/64, high part (26 trailing zero bits)
+    r = fma(nd, PRB_EXP_K[2], r);                                            //          low part
+    double q = fma(r, PRB_EXP_K[3], PRB_EXP_K[4]);                           // 1/120, 1/24
+    q = fma(q, r, PRB_EXP_K[5]);                                             // 1/6
     q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
     q = q * r;
     const double tj = tab[n & 63];
     const double e = fma(tj, q, tj);
     return __hiloint2double(__double2hiint(e) + ((n >> 6) << 20), __double2loint(e));   // * 2^k: |x| <= 700 keeps it normal
+}
+// speculative variants: no branch per call — the caller accumulates one `bad` flag per rhs evaluation and re-evaluates
+// the whole (pure) vector field with the library functions in the rare case an argument left the fast range
+__device__ __forceinline__ double prb_spec_exp(const double z, const unsigned int tab, bool& bad) {
+    bad |= !(fabs(z) <= 700.0);
+    const double t = fma(z, PRB_EXP_K[0], 6755399441055744.0);
+    const int n = __double2loint(t);
+    const double nd = t - 6755399441055744.0;
+    double r = fma(nd, PRB_EXP_K[1], z);
+    r = fma(nd, PRB_EXP_K[2], r);
+    double q = fma(r, PRB_EXP_K[3], PRB_EXP_K[4]);
+    q = fma(q, r, PRB_EXP_K[5]);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = q * r;
+    double tj;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab + ((unsigned int)(n & 63) << 3)));
+    const double e = fma(tj, q, tj);
+    return __hiloint2double(__double2hiint(e) + ((n >> 6) << 20), __double2loint(e));
+}
+__device__ __forceinline__ double prb_spec_div(const double a, const double b, bool& bad) {
+    const double ab = fabs(b);
+    bad |= !(ab > 1e-290 && ab < 1e290);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    const double e = fma(-b, r, 1.0);                  // r0 = (1 - e) / b with |e| <= ~2^-20
+    r = fma(r, fma(e, e, e), r);                       // cubic step: r0 (1 + e + e^2) = (1 - e^3) / b
+    return a * r;
 }
 __device__ __forceinline__ double prb_fast_div(const double a, const double b) {
     const double ab = fabs(b);
@@ -257,7 +346,7 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
     if use_etab:
         src.append("#define PRB_USE_ETAB 1")
     init = ["__device__ __forceinline__ void prb_thread_init(PrbThread& T, const prb_kernel_args& A, long long b) {",
-            "    T.b = b; T.B = A.n_inst; T.etab = nullptr;",
+            "    T.b = b; T.B = A.n_inst; T.etab = nullptr; T.etab_s = 0u;",
             "    T.slots = (real*)A.slots; T.rings = (real*)A.rings; T.tables = (const real*)A.tables;"]
     if np_:
         init.append("    const real* __restrict__ P = (const real*)A.params;")
@@ -267,8 +356,25 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
     init.append("}")
     init.append("__device__ __forceinline__ void prb_thread_exit(PrbThread&, const prb_kernel_args&, long long) {}")
     src.append("\n".join(init))
+    if body and body[0].startswith("// PRB_LIT = {"):
+        vals = body.pop(0)[len("// PRB_LIT = {"):-1]
+        src.append(f"__device__ __constant__ double PRB_LIT[{vals.count(',') + 1}] = {{{vals}}};")
+    if spec:
+        src.append("__device__ __noinline__ void prb_rhs_exact(const prb_time t, const real (&y)[PRB_NS], real (&dy)[PRB_NS], PrbThread& T) {")
+        src.extend("    " + l for l in exact_body)
+        src.append("}")
     src.append("__device__ __forceinline__ void prb_rhs(const prb_time t, const real (&y)[PRB_NS], real (&dy)[PRB_NS], PrbThread& T) {")
+    if spec:
+        src.append("    bool bad = false;")
     src.extend("    " + l for l in body)
+    if spec:
+        src.append("    if (bad) {                  // an exp / division argument left the fast range: redo this evaluation exactly")
+        src.append("        real yl[PRB_NS], dl[PRB_NS];")
+        src.append("        PrbThread Tl = T;")
+        src.append("        _Pragma(\"unroll\") for (int j = 0; j < PRB_NS; ++j) yl[j] = y[j];")
+        src.append("        prb_rhs_exact(t, yl, dl, Tl);")
+        src.append("        _Pragma(\"unroll\") for (int j = 0; j < PRB_NS; ++j) dy[j] = dl[j];")
+        src.append("    }")
     src.append("}")
     rec = ["__device__ __forceinline__ void prb_record(const real (&y)[PRB_NS], real* __restrict__ row, long long b, long long B) {"]
     for o, idx in enumerate(observers):
