@@ -36,6 +36,7 @@ SWEEP = [("u", 0), ("weight_v2", 0), ("weight_v2", 1), ("weight", 0), ("weight_v
 # dram__bytes_read.sum + dram__bytes_write.sum of one prb_integrate launch (2^20 instances x 1000 steps, 100 samples)
 # from the `ncu --set full` capture summarised in profiles/r01_c2_prb_integrate_ncu_full.txt (114.07 + 848.98 MB).
 NCU_TRAFFIC_BYTES_PER_LAUNCH = 963.04e6
+FP64_INSTR = {True: 317, False: 505}     # fp64-pipe instructions per instance-step in the loop (cuobjdump, fast / exact kernel)
 METRIC = "state-updates/sec (nodes x sweeps x steps/s), JRC RK4 grid_search"
 UNIT = "node-steps/s"
 
@@ -123,7 +124,8 @@ def main():
     ap.add_argument("--cpu-sim-time", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strict-div", action="store_true",
-                    help="keep IEEE divisions by constants (default: multiply by the reciprocal)")
+                    help="exact kernels: IEEE divisions, library exp (default: reciprocal multiplies, table exp, rcp + cubic "
+                         "step, folded constant chains — each <= 2 ulp, trajectories within 1e-15 of the exact kernel)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -246,9 +248,13 @@ def main():
                      "algorithmic_bytes_per_launch": B_ALG * inst_steps_per_launch, "peak_source": which, "kernel": "prb_integrate (fused JRC rhs + RK4 + observer store)",
                      "algorithmic_bytes_per_instance_step": B_ALG, "launch_ms": launch_s * 1e3,
                      "note": "state/stages are register-resident across the launch: real DRAM traffic is only the "
-                             "observer store; the true bound is the FP64 pipe (see DESIGN.md)"},
+                             "observer store, so the SURVEY 8d round-trip model can exceed 1.0; the true bound is the FP64 pipe",
+                     "fp64_pipe": {"instr_per_instance_step": FP64_INSTR[not a.strict_div],
+                                   "frac": FP64_INSTR[not a.strict_div] * 2.0 * (value / NODES / world / 32) / (148 * 4 * 1.965e9),
+                                   "model": "fp64-pipe warp instructions (DFMA/DMUL/DADD/DSETP) in the SASS time loop x 2 issue "
+                                            "cycles (16 lanes/SMSP) / (148 SMs x 4 SMSPs x 1.965 GHz)"}},
         "kernel": {"regs": info["regs"], "local_bytes": info["local_bytes"], "blocks_per_sm": info["max_blocks_per_sm"],
-                   "block": sw.model.kernel.block, "const_div_to_mul": not a.strict_div, "fast_math": False},
+                   "block": sw.model.kernel.block, "const_div_to_mul": not a.strict_div, "fast_math": not a.strict_div},
         "jit_s": jit_s, "numa_node_rank0": numa_node,
         "clocks": clocks.stop(wall0, wall1) if clocks else None,
     }

@@ -48,16 +48,18 @@ class BatchedSweep:
                  chunk_samples: int = 100, const_div_to_mul: bool = True, block: int = 128,
                  pinned_result: bool = True, min_blocks: int = 5, solver_kwargs: Optional[dict] = None,
                  fast_math: Optional[bool] = None):
-        # min_blocks=5 caps the kernel at 96 registers -> 20 warps/SM; measured +3.5 % on the JRC/RK4 sweep
+        # min_blocks=5 caps the exact kernel at 96 registers -> 20 warps/SM; measured +3.5 % on the JRC/RK4 sweep
         # (scripts/tune_inst.py), the kernel being FP64-pipe bound either way
         from .engine import ADAPTIVE_SOLVERS
         self.adaptive = solver in ADAPTIVE_SOLVERS
         self.solver_kwargs = dict(solver_kwargs or {})
         self.T, self.dts = float(T), dts
         if fast_math is None:
-            fast_math = False        # measured +1.6 % on the JRC sweep (issue-bound once the fp64 count drops): opt-in only
+            fast_math = const_div_to_mul     # one switch: every <= 2 ulp instruction-count reduction of the fp64 kernels
         if self.adaptive:
             const_div_to_mul, fast_math, min_blocks = False, False, 1   # RK45 keeps 7 stage vectors in registers: no occupancy cap
+        if fast_math and min_blocks == 5:
+            min_blocks = 4       # the leaner fast_math loop prefers registers over occupancy (scripts/tune_inst.py: 22.6 vs 23.3 ms)
         self.model = InstanceModel(prog, solver=solver, sweep=sweep, observers=observers, block=block,
                                    const_div_to_mul=const_div_to_mul, min_blocks=min_blocks if block == 128 else 1,
                                    fast_math=fast_math)

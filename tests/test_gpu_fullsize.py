@@ -89,3 +89,48 @@ def test_c5_kuramoto_n1024_separable_full_state(gpu):
     ref, _ = orc.run(f, args, 8e-3, 1e-3, None, "rk4")
     out, _ = NetworkModel(prog, solver="rk4").run(8e-3, 1e-3, None)
     assert traj_rel_err(out[:, :, 0], ref) <= 1e-9
+
+
+def test_c2_bench_kernel_fast_math_full_grid_spot_checks(gpu):
+    """The exact configuration bench.py times (const_div_to_mul + fast_math, 2^20 instances): random grid points against
+    the oracle at the fp64 tolerance, over a horizon long enough for the JRC oscillation to develop (T = 0.3)."""
+    prog = Program.load(golden_path("jrc"))
+    grid = 1024
+    B = grid * grid
+    table = bench.param_table(grid, grid, 0, B)
+    T, dt, dts = 0.3, 1e-4, 1e-3
+    sw = BatchedSweep(prog, bench.SWEEP, observers=[0], solver="rk4", T=T, dt=dt, dts=dts, n_inst=B, chunk_samples=100,
+                      const_div_to_mul=True)
+    assert "prb_spec_exp(" in sw.model.kernel.source and "prb_rhs_exact" in sw.model.kernel.source
+    try:
+        out = np.array(sw.run(table), copy=True)
+        assert out.shape == (300, 1, B) and np.all(np.isfinite(out))
+        f = orc.build_vector_field(prog.source())
+        names = [a.name for a in prog.args]
+        for b in [0, B - 1] + sorted(np.random.default_rng(3).choice(B, 5, replace=False).tolist()):
+            u, C, C4, C08, _ = table[:, b]
+            args = [np.array(a.value, copy=True) for a in prog.args]
+            args[names.index("u")] = np.float64(u)
+            args[names.index("weight_v2")] = np.array([C, C4])
+            args[names.index("weight")] = np.float64(C08)
+            args[names.index("weight_v1")] = np.float64(C4)
+            rec, _ = orc.run(f, args, T, dt, dts, "rk4")
+            assert traj_rel_err(out[:, :, b], rec[:, [0]]) <= 1e-9, b
+    finally:
+        sw.free()
+
+
+def test_fast_math_falls_back_to_exact_evaluation_outside_the_fast_range(gpu):
+    """exp arguments beyond +-700 (overflow / underflow) and huge divisors: the speculative kernel must re-evaluate with
+    the library functions and agree with the exact kernel bit for bit there."""
+    prog = Program.load(golden_path("jrc"))
+    y0 = np.array(prog.y0, dtype=np.float64)
+    outs = []
+    for fm in (False, True):
+        m = InstanceModel(prog, solver="euler", fast_math=fm, const_div_to_mul=fm)
+        # v = y0[1]-ish potentials of +-3 drive 560*(0.006 - v) to about -+1700: exp over/underflows
+        y = np.stack([y0 + np.array([0, 0, 0, 0, 3.0, -3.0, 0, 0]), y0 + np.array([3.0, 0, -9.0, 0, 0, 0, 0, 0])], axis=1)
+        out, _ = m.run(2e-3, 1e-4, None, y0=y, n_inst=2)
+        outs.append(out)
+    assert np.all(np.isfinite(outs[0])) and traj_rel_err(outs[1][:, :, 0], outs[0][:, :, 0]) <= 1e-12
+    assert traj_rel_err(outs[1][:, :, 1], outs[0][:, :, 1]) <= 1e-12
