@@ -34,8 +34,9 @@ NODES = 3                      # JRC: pc, ein, iin
 B_ALG = (2 * 8 + 5) * 8 + 8 / 10   # (2*n_sv + n_pp)*s + n_obs*s/store_step = 168.8 B / instance-step
 SWEEP = [("u", 0), ("weight_v2", 0), ("weight_v2", 1), ("weight", 0), ("weight_v1", 0)]
 # dram__bytes_read.sum + dram__bytes_write.sum of one prb_integrate launch (2^20 instances x 1000 steps, 100 samples)
-# from the `ncu --set full` capture summarised in profiles/r01_c2_prb_integrate_ncu_full.txt (114.07 + 848.98 MB).
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 963.04e6
+# from the `ncu --set full` capture summarised in profiles/r01_c2_fastmath_prb_integrate_ncu_full.txt (110.79 + 847.40 MB;
+# the exact kernel, profiles/r01_c2_prb_integrate_ncu_full.txt: 114.07 + 848.98 MB — the observer store either way).
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 958.2e6
 FP64_INSTR = {True: 317, False: 505}     # fp64-pipe instructions per instance-step in the loop (cuobjdump, fast / exact kernel)
 METRIC = "state-updates/sec (nodes x sweeps x steps/s), JRC RK4 grid_search"
 UNIT = "node-steps/s"
@@ -244,7 +245,7 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                      "traffic": (NCU_TRAFFIC_BYTES_PER_LAUNCH if (a.grid == 1024 and inst_steps_per_launch == 2 ** 20 * 1000) else None),
-                     "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_c2_prb_integrate_ncu_full.txt)",
+                     "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_c2_fastmath_prb_integrate_ncu_full.txt)",
                      "algorithmic_bytes_per_launch": B_ALG * inst_steps_per_launch, "peak_source": which, "kernel": "prb_integrate (fused JRC rhs + RK4 + observer store)",
                      "algorithmic_bytes_per_instance_step": B_ALG, "launch_ms": launch_s * 1e3,
                      "note": "state/stages are register-resident across the launch: real DRAM traffic is only the "

@@ -151,12 +151,16 @@ def main():
         prog = to_float32(prog)
     dt = 1e-3
     sweep = [x for x in a.sweep.split(",") if x]
-    m = NetworkModel(prog, solver=a.solver, observers=[0], block=a.block, rank=rank, world=world, n_batch=a.batch,
+    # multi-GPU: a single network shards the ROWS of W (in-kernel all-gather); a sweep over a network shards its
+    # INSTANCES instead — every rank integrates its own `--batch` instances, no communication (weak scaling)
+    shard_instances = world > 1 and a.batch > 1
+    m = NetworkModel(prog, solver=a.solver, observers=[0], block=a.block, rank=0 if shard_instances else rank,
+                     world=1 if shard_instances else world, n_batch=a.batch,
                      sweep=sweep, tensor_core="auto" if a.tensor_core == "auto" else False, tc_max_acc=a.tc_max_acc)
     params = None
     if sweep:
-        params = m.param_defaults[:, None] * (1.0 + 0.1 * np.random.default_rng(3).uniform(-1, 1, (len(sweep), a.batch))) \
-            + 0.05 * np.random.default_rng(4).uniform(0, 1, (len(sweep), a.batch))
+        params = m.param_defaults[:, None] * (1.0 + 0.1 * np.random.default_rng(3 + rank).uniform(-1, 1, (len(sweep), a.batch))) \
+            + 0.05 * np.random.default_rng(4 + rank).uniform(0, 1, (len(sweep), a.batch))
     t0 = time.perf_counter()
     m.module
     jit_s = time.perf_counter() - t0
@@ -166,6 +170,9 @@ def main():
     rt.synchronize()
     s.check()
     s.reset(params=params)
+    if dist is not None:
+        rt.synchronize()
+        dist.barrier()
     e0, e1 = rt.Event(), rt.Event()
     e0.record()
     s.launch(a.steps, dt, 1)
@@ -185,20 +192,22 @@ def main():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         hbm = float(json.load(open(p))["hbm_gbs"])
-    wbytes_rank = wbytes / world
+    wbytes_rank = wbytes / (1 if shard_instances else world)
+    inst_total = a.batch * (world if shard_instances else 1)
     achieved = wbytes_rank * evals * a.steps / (ms * 1e-3) / 1e9
     if rank != 0:
         s.free()
         dist.destroy_process_group()
         return
     line = {"config": a.config, "n": a.n, "solver": a.solver, "n_gpus": world, "steps": a.steps, "ms_per_step": ms / a.steps,
-            "node_steps_per_s": nodes * a.batch * a.steps / (ms * 1e-3), "evals_per_step": evals, "W_bytes": wbytes,
+            "node_steps_per_s": nodes * inst_total * a.steps / (ms * 1e-3), "evals_per_step": evals, "W_bytes": wbytes,
+            "sharding": ("instances (no collective)" if shard_instances else "rows of W (in-kernel all-gather)") if world > 1 else "none",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "model": "this rank's W shard bytes x evaluations per step (state vectors negligible); per GPU"},
             "jit_s": jit_s, "phases": m.kernel.n_phases, "block": m.kernel.block, "batch": a.batch, "precision": a.precision}
     if a.batch > 1:
         # sweep-batched coupling is GEMM-shaped: 2 flops per (target, source, instance) and evaluation
-        flops = sum(2.0 * r.n * r.m for r in m.ir.reductions if r.kind == "row") * a.batch * evals * a.steps
+        flops = sum(2.0 * r.n * r.m for r in m.ir.reductions if r.kind == "row") * a.batch * evals * a.steps     # per GPU
         tf = flops / (ms * 1e-3) / 1e12
         if m.kernel.tc is not None:
             peak = 1388.2
