@@ -127,7 +127,7 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
         return i, f
 
     live = list(rhs.live_nodes())
-    if fast_math and not f32:
+    if fast_math:
         # nodes that only fed a folded chain are dead now: recompute liveness over the rewritten expressions
         needed, stack = set(), [n for n in rhs.dy] + [n for *_, n in rhs.ring_writes] + [n for _, n in rhs.slot_writes]
         while stack:
@@ -149,8 +149,10 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
         op, a = g.ops[i], g.args[i]
         if op in ("const", "state", "param", "t"):
             continue
-        if fast_math and not f32 and not g.isint[i] and op in ("mul", "div"):
+        if fast_math and not g.isint[i] and op in ("mul", "div"):
             base, f = const_chain(i)
+            if f32:
+                f = float(np.float32(f))
             if base != i and math.isfinite(f) and f != 0.0:
                 lines.append(f"const real v{i} = {ref(base)} * {lit(f)};")
                 continue
@@ -180,6 +182,8 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
                 c = float(g.const_value(a[1]))
                 inv = float(np.float32(1.0) / np.float32(c)) if f32 else 1.0 / c
                 expr = f"{ref(a[0])} * {lit(inv)}"
+            elif fast_math and f32:
+                expr = f"__fdividef({ref(a[0])}, {ref(a[1])})"          # rcp.approx + mul: 2 ulp (|divisor| < 2^126)
             elif fast_math and not f32:
                 expr = f"prb_spec_div({ref(a[0])}, {ref(a[1])}, bad)" if spec else f"prb_fast_div({ref(a[0])}, {ref(a[1])})"
             else:
@@ -194,6 +198,8 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
             expr = f"prb_min({ref(a[0])}, {ref(a[1])})"
         elif op == "sign":
             expr = f"prb_sign({ref(a[0])})"
+        elif op == "exp" and fast_math and f32:
+            expr = f"__expf({ref(a[0])})"                               # ex2.approx(x * log2 e): ~2 ulp + |x| 2^-24
         elif op == "exp" and fast_math and not f32:
             expr = f"prb_spec_exp({ref(a[0])}, T.etab_s, bad)" if spec else f"prb_fast_exp({ref(a[0])}, T.etab)"
         elif op in _FUNC:

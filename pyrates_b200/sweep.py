@@ -59,7 +59,9 @@ class BatchedSweep:
         if self.adaptive:
             const_div_to_mul, fast_math, min_blocks = False, False, 1   # RK45 keeps 7 stage vectors in registers: no occupancy cap
         if fast_math and min_blocks == 5:
-            min_blocks = 4       # the leaner fast_math loop prefers registers over occupancy (scripts/tune_inst.py: 22.6 vs 23.3 ms)
+            # fp64: the leaner fast_math loop prefers registers over occupancy (scripts/tune_inst.py: 22.6 vs 23.3 ms);
+            # fp32 (half the registers per value): 8 blocks x 128 threads at 64 registers (scripts/bench_f32.py)
+            min_blocks = 8 if prog.float_precision == "float32" else 4
         self.model = InstanceModel(prog, solver=solver, sweep=sweep, observers=observers, block=block,
                                    const_div_to_mul=const_div_to_mul, min_blocks=min_blocks if block == 128 else 1,
                                    fast_math=fast_math)

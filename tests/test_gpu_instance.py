@@ -139,3 +139,29 @@ def test_fast_math_variant_keeps_fp64_parity(gpu, name, solver):
     r = fx["run"]
     out, _ = InstanceModel(Program.load(golden_path(name)), solver=solver, fast_math=True, const_div_to_mul=True).run(r["T"], r["dt"], r["dts"])
     assert traj_rel_err(out[:, :, 0], fx["extra"][f"rec_{solver}"]) <= 1e-9
+
+
+def test_fast_math_float32_sweep_keeps_fp32_parity(gpu):
+    """float32 (the reference's default precision) with fast_math (__expf, __fdividef, folded constants): a JRC batch
+    against the float32 oracle per instance at the fp32 tolerance."""
+    import bench
+    import bench_configs as bc
+    prog = bc.to_float32(Program.load(golden_path("jrc")))
+    B = 256
+    table = bench.param_table(16, 16, 0, B)
+    m = InstanceModel(prog, solver="rk4", sweep=bench.SWEEP, observers=[0, 2], const_div_to_mul=True, fast_math=True, min_blocks=8)
+    assert "__expf(" in m.kernel.source and "__fdividef(" in m.kernel.source
+    order = [(p.arg, p.elem) for p in m.rhs.params]
+    out, _ = m.run(0.2, 1e-4, 1e-3, params=np.stack([table[bench.SWEEP.index(k)] for k in order]))
+    f = orc.build_vector_field(prog.source())
+    names = [a.name for a in prog.args]
+    for b in (0, 100, 255):
+        u, C, C4, C08, _ = table[:, b]
+        args = [np.array(a.value, copy=True) for a in prog.args]
+        args[names.index("u")] = np.float32(u)
+        args[names.index("weight_v2")] = np.array([C, C4], dtype=np.float32)
+        args[names.index("weight")] = np.float32(C08)
+        args[names.index("weight_v1")] = np.float32(C4)
+        with np.errstate(over="ignore"):
+            rec, _ = orc.run(f, args, 0.2, 1e-4, 1e-3, "rk4")
+        assert traj_rel_err(out[:, :, b], rec[:, [0, 2]]) <= 1e-4, b
