@@ -312,6 +312,10 @@ ADAPTIVE_CASES = {
     "qif_sfa_rk45": dict(build=_yaml(NM + "qif.qif_sfa"), T=2.0, dt=1e-3, dts=5e-3, out="p/qif_sfa_op/r",
                          kw=dict(rtol=1e-6, atol=1e-8)),
     "wc_n8_rk45":   dict(build=_wc_pop(8), T=0.5, dt=1e-3, dts=5e-3, out="e/rate_op/r", kw=dict(rtol=1e-6, atol=1e-9)),
+    # networks too large for one thread: adaptive integration in the persistent network kernel (grid-wide error norm)
+    "wc_n128_rk45": dict(build=_wc_pop(128), T=60.0, dt=1e-3, dts=0.5, out="e/rate_op/r", kw=dict(rtol=1e-7, atol=1e-10)),
+    "kuramoto_n128_rk45": dict(build=_kuramoto(128), T=10.0, dt=1e-3, dts=0.05, out="e/phase_op/theta",
+                               kw=dict(rtol=1e-8, atol=1e-10)),
 }
 
 

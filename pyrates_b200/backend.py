@@ -306,7 +306,16 @@ class CudaBackend:
         if solver in ADAPTIVE_SOLVERS:
             # BaseBackend._solve_scipy (:802-812): solve_ivp(first_step=dt, t_eval=times, **kwargs); one thread integrates the
             # circuit with SciPy's RK45 step controller and dense output (csrc/templates/inst_kernel.cuh)
-            model = InstanceModel(prog, solver=solver, fmad=self.fmad, max_nodes=20000)
+            try:
+                if self.exec_model == "network":
+                    raise UnsupportedModelError("model too large (network execution model requested)")
+                model = InstanceModel(prog, solver=solver, fmad=self.fmad, max_nodes=4000 if self.exec_model == "auto" else 20000)
+            except UnsupportedModelError as e:
+                if self.exec_model == "instance" or "too large" not in str(e):
+                    raise
+                # populations / dense coupling: the whole grid steps with one adaptive step size (net_kernel.cuh)
+                from .netengine import NetworkModel
+                model = NetworkModel(prog, solver=solver, fmad=self.fmad)
             self.last_model = model
             # like solve_ivp, ignore options that have no effect for RK45 (the reference forwards e.g. float_precision)
             opts = {k: v for k, v in kwargs.items() if k in ("rtol", "atol", "max_step", "method")}

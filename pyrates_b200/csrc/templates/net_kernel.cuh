@@ -33,7 +33,13 @@ struct PrbNet {
     const real* __restrict__ tables;
     long long oY, oYN, oS1, oS2, oS3, oACC;     // element offsets of the solver vectors inside `work`
     real dt, hdt, dt6;
-    long long t;
+    prb_time t;                  // integer step counter (fixed-step solvers) or float time (adaptive RK45)
+#if PRB_SOLVER == PRB_SOLVER_RK45
+    double h;                    // step size of the current attempt
+    double errsq;                // this thread's share of sum((err/scale)^2)
+    double rtol, atol;
+    long long oK[7], oSA, oSB;   // stage derivatives K0..K6 and the two alternating stage-input vectors inside `work`
+#endif
     int head[PRB_NRINGS > 0 ? PRB_NRINGS : 1];
     unsigned long long* bar;     // [0] local arrivals, [1] release epoch, [2] error flag, [8+q] epoch of rank q
     unsigned long long bar_target;
@@ -154,6 +160,25 @@ __device__ __forceinline__ real prb_block_sum(real v) {
     }
     __syncthreads();
     return total;
+}
+
+__device__ __forceinline__ double prb_block_sum_d(double v) {
+    __shared__ double redd[32];
+    __shared__ double totald;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) redd[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double s = (l < (int)(blockDim.x >> 5)) ? redd[l] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (l == 0) totald = s;
+    }
+    __syncthreads();
+    return totald;
 }
 
 __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
@@ -496,10 +521,46 @@ __device__ __forceinline__ void prb_gemm_batch(const PrbNet& C, const real* __re
 
 // ---- solver stage logic: what happens to the derivative k of state element e in stage STAGE.
 // HEUN_REF reproduces the reference's aliased `heun` (y += dt/2*(k2+k2), base_backend.py:763-765).
+#if PRB_SOLVER == PRB_SOLVER_RK45
+// Dormand-Prince tableau (emitted by pyrates_b200/rk45.py) — see the RK45 driver at the end of this file
+__device__ constexpr double PRB_RK_C[6] = PRB_RK45_C_INIT;
+__device__ constexpr double PRB_RK_A[6][5] = PRB_RK45_A_INIT;
+__device__ constexpr double PRB_RK_B[6] = PRB_RK45_B_INIT;
+__device__ constexpr double PRB_RK_E[7] = PRB_RK45_E_INIT;
+__device__ constexpr double PRB_RK_P[7][4] = PRB_RK45_P_INIT;
+#endif
+
 template <int STAGE>
-__device__ __forceinline__ void prb_emit_k(const PrbNet& C, const long long e, const real k) {
+__device__ __forceinline__ void prb_emit_k(PrbNet& C, const long long e, const real k) {
     const real y = C.work[C.oY + e];
-#if PRB_SOLVER == PRB_SOLVER_EULER
+#if PRB_SOLVER == PRB_SOLVER_RK45
+    // STAGE = E - 1 for evaluation E = 1..6 (K_E = k); STAGE 6 = the initial f(t0, y0) -> K0.  Each evaluation also
+    // builds, for ITS element only, the input of the next one: y + h * sum_q A[E+1][q] K_q (E < 5), y_new (E = 5).
+    constexpr int E = STAGE + 1;
+    if constexpr (STAGE == 6) {
+        C.work[C.oK[0] + e] = k;
+    } else if constexpr (E < 5) {
+        C.work[C.oK[E] + e] = k;
+        double d = 0.0;
+#pragma unroll
+        for (int q = 0; q <= E; ++q) d += (q == E ? (double)k : (double)C.work[C.oK[q] + e]) * PRB_RK_A[E + 1][q];
+        prb_st_work(C, ((E & 1) ? C.oSB : C.oSA) + e, (real)((double)y + d * C.h));
+    } else if constexpr (E == 5) {
+        C.work[C.oK[5] + e] = k;
+        double d = 0.0;
+#pragma unroll
+        for (int q = 0; q <= 5; ++q) d += (q == 5 ? (double)k : (double)C.work[C.oK[q] + e]) * PRB_RK_B[q];
+        prb_st_work(C, C.oYN + e, (real)((double)y + C.h * d));            // y_new: input of evaluation 6 and the next state
+    } else {
+        C.work[C.oK[6] + e] = k;
+        double er = 0.0;
+#pragma unroll
+        for (int q = 0; q <= 6; ++q) er += (q == 6 ? (double)k : (double)C.work[C.oK[q] + e]) * PRB_RK_E[q];
+        const double scale = C.atol + fmax(fabs((double)y), fabs((double)C.work[C.oYN + e])) * C.rtol;
+        const double r = er * C.h / scale;
+        C.errsq += r * r;
+    }
+#elif PRB_SOLVER == PRB_SOLVER_EULER
     prb_st_work(C, C.oYN + e, y + C.dt * k);
 #elif PRB_SOLVER == PRB_SOLVER_HEUN_REF
     if (STAGE == 0) prb_st_work(C, C.oS1 + e, y + C.dt * k);
@@ -560,6 +621,103 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
     prb_tc_setup(C.tc, C.bar + 2);
 #endif
 
+#if PRB_SOLVER == PRB_SOLVER_RK45
+    // ---- adaptive: the reference's solver='scipy' == solve_ivp(method='RK45', first_step=dt, t_eval=times)
+    // (base_backend.py:802-812) for a network too large for one thread.  Same algorithm as the instance kernel
+    // (inst_kernel.cuh): Dormand-Prince stages, SciPy's controller and dense output, K[0] = the most recent rhs
+    // evaluation (the reference's aliased buffer).  The whole grid advances with ONE step size: every evaluation is a
+    // persistent-grid phase, the RMS error norm is a grid-wide sum (per-CTA partials, one atomicAdd each, read behind the
+    // evaluation's barrier), and every thread replays the same controller arithmetic on the same numbers.
+    // Options (A.slots, doubles): [0] rtol [1] atol [2] t_start [3] t_bound [4] first_step [5] sample spacing
+    // [6] max_step [7] max attempts, [8..10] error-norm accumulators (rotating), [11] status out, [12] attempts out.
+    double* opt = (double*)A.slots;
+    C.rtol = opt[0]; C.atol = opt[1];
+    const double t_bound = opt[3], te_step = opt[5], max_step = opt[6];
+    const long long max_attempts = (long long)opt[7];
+    double t = opt[2], h_abs = opt[4];
+    C.oSA = C.oY + 2LL * nsb; C.oSB = C.oY + 3LL * nsb;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) C.oK[q] = C.oY + (4LL + q) * nsb;
+    C.errsq = 0.0; C.h = 0.0;
+    real* extY = (real*)A.y;
+    for (long long e = C.gtid; e < nsb; e += C.gsize) C.work[C.oY + e] = extY[e];
+    prb_grid_barrier(C);
+    C.t = (prb_time)t;
+    prb_stage<6>(C, C.oY);                                            // K0 = f(t0, y0)
+    real* out = (real*)A.out;
+    long long sample = A.sample0;
+    const long long n_samples = A.sample0 + A.n_steps;
+    long long attempts = 0;
+    unsigned int status = 0;
+    while (t != t_bound && status == 0) {
+        const double min_step = 10.0 * fabs(nextafter(t, __longlong_as_double(0x7ff0000000000000LL)) - t);
+        if (h_abs > max_step) h_abs = max_step;
+        else if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false;
+        double h = 0.0, t_new = t;
+        for (;;) {
+            if (h_abs < min_step) { status = 1; break; }
+            if (++attempts > max_attempts) { status = 2; break; }
+            t_new = t + h_abs;
+            if (t_new - t_bound > 0.0) t_new = t_bound;
+            h = t_new - t;
+            h_abs = fabs(h);
+            C.h = h;
+            const int slot = (int)(attempts % 3);
+            if (C.gtid == 0) opt[8 + (slot + 1) % 3] = 0.0;           // the accumulator of the NEXT attempt (last read 2 attempts ago)
+            // input of evaluation 1: y + h * A[1][0] * K0
+            for (long long e = C.gtid; e < nsb; e += C.gsize)
+                prb_st_work(C, C.oSA + e, (real)((double)C.work[C.oY + e] + (double)C.work[C.oK[0] + e] * PRB_RK_A[1][0] * h));
+            prb_grid_barrier(C);
+            C.t = (prb_time)(t + PRB_RK_C[1] * h); prb_stage<0>(C, C.oSA);
+            C.t = (prb_time)(t + PRB_RK_C[2] * h); prb_stage<1>(C, C.oSB);
+            C.t = (prb_time)(t + PRB_RK_C[3] * h); prb_stage<2>(C, C.oSA);
+            C.t = (prb_time)(t + PRB_RK_C[4] * h); prb_stage<3>(C, C.oSB);
+            C.t = (prb_time)(t + PRB_RK_C[5] * h); prb_stage<4>(C, C.oSA);
+            C.t = (prb_time)(t + h);
+            C.yin = C.work + C.oYN;
+            prb_eval<5>(C);                                           // K6 = f(t + h, y_new) + this thread's error share
+            {
+                const double part = prb_block_sum_d(C.errsq);
+                C.errsq = 0.0;
+                if (threadIdx.x == 0) atomicAdd(opt + 8 + slot, part);
+            }
+            prb_grid_barrier(C);
+            const double sq = *((volatile double*)(opt + 8 + slot));
+            const double error_norm = sqrt(sq) / sqrt((double)nsb);
+            // K[0] of the next attempt is the newest evaluation whether or not this one is accepted (aliased buffer)
+            { const long long tmp = C.oK[0]; C.oK[0] = C.oK[6]; C.oK[6] = tmp; }
+            if (error_norm < 1.0) {
+                double factor = (error_norm == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -0.2));
+                if (rejected) factor = fmin(1.0, factor);
+                h_abs *= factor;
+                break;
+            }
+            h_abs *= fmax(0.2, 0.9 * pow(error_norm, -0.2));
+            rejected = true;
+        }
+        if (status != 0) break;
+        // dense output at the sample times inside (t, t_new]; after the swap K6 sits at oK[0] and the old K0 at oK[6]
+        while (sample < n_samples && (double)(sample - A.sample0) * te_step <= t_new) {
+            const double x = ((double)(sample - A.sample0) * te_step - t) / h;
+            const double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x;
+            for (long long q = C.gtid; q < PRB_NOBS; q += C.gsize) {
+                const long long e = PRB_OBS_INDEX(q);
+                double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll
+                for (int s_ = 0; s_ < 7; ++s_) {
+                    const double kv = (double)C.work[C.oK[s_ == 0 ? 6 : (s_ == 6 ? 0 : s_)] + e];
+                    q0 += kv * PRB_RK_P[s_][0]; q1 += kv * PRB_RK_P[s_][1]; q2 += kv * PRB_RK_P[s_][2]; q3 += kv * PRB_RK_P[s_][3];
+                }
+                out[sample * (long long)PRB_NOBS + q] = (real)(h * (((q0 * p1 + q1 * p2) + q2 * p3) + q3 * p4) + (double)C.work[C.oY + e]);
+            }
+            ++sample;
+        }
+        t = t_new;
+        { const long long tmp = C.oY; C.oY = C.oYN; C.oYN = tmp; }
+    }
+    if (C.gtid == 0) { opt[11] = (double)status; opt[12] = (double)attempts; }
+#else
     real* extY = (real*)A.y;
     for (long long e = C.gtid; e < nsb; e += C.gsize) C.work[C.oY + e] = extY[e];   // every rank holds a full replica
     prb_grid_barrier(C);
@@ -593,6 +751,7 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
 #endif
         const long long tmp = C.oY; C.oY = C.oYN; C.oYN = tmp;
     }
+#endif   // fixed-step solvers
     for (long long e = C.gtid; e < nsb; e += C.gsize) extY[e] = C.work[C.oY + e];
 #ifdef PRB_TC
     prb_tc_teardown(C.tc);

@@ -11,7 +11,7 @@ from typing import Dict, List, Optional, Sequence, Set, Tuple
 
 import numpy as np
 
-from .emit_inst import SOLVER_IDS, _FUNC, _lit, read_template
+from .emit_inst import ADAPTIVE_SOLVERS, SOLVER_IDS, _FUNC, _lit, read_template
 from .netcompile import MemArray, NetIR, Reduction, Store
 from .scalarize import UnsupportedModelError
 
@@ -267,6 +267,15 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     f32 = precision == "float32"
     g = ir.graph
     ns = ir.n_state
+    adaptive = solver in ADAPTIVE_SOLVERS
+    if adaptive:
+        if f32 or int(n_batch) != 1 or world != 1:
+            raise UnsupportedModelError("adaptive integration of networks (solver='scipy') is implemented for float64, one "
+                                        "instance, one GPU")
+        if any(a.space in ("ring", "table") for a in ir.arrays.values()):
+            raise UnsupportedModelError("adaptive integration (solver='scipy') needs a pure vector field: delay ring buffers "
+                                        "and step-indexed input tables are fixed-step constructs")
+    n_solver_vecs = 11 if adaptive else 6          # RK45: Y, YN, two stage inputs, K0..K6
     # reduction results get a work array so that consumers outside the fused row task can read them
     work_size = ir.work_size
     nb = int(n_batch)
@@ -349,7 +358,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 cur = (p, n, True)
                 BT, CPT = tc["bt"], tc["bt"] // tc["e"]
                 n_mb, n_nbk = (n + 127) // 128, nb // BT
-                tc_base = (work_size + 6 * ns) * nb
+                tc_base = (work_size + n_solver_vecs * ns) * nb
                 plan = []
                 for r in reds:
                     wname = r.simple[0]
@@ -574,6 +583,10 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     src.append("// Generated by pyrates_b200.emit_net — do not edit.  Network execution model (persistent cooperative grid).")
     src.append(read_template("prb_kernel_abi.cuh"))
     src.append(f"typedef {'float' if f32 else 'double'} real;")
+    src.append(f"typedef {'double' if adaptive else 'long long'} prb_time;")
+    if adaptive:
+        from .rk45 import cuda_tables
+        src.append(cuda_tables())
     src.append(f"#define PRB_NS {ns}LL")
     src.append(f"#define PRB_NOBS {obs.size}LL")
     src.append(f"#define PRB_NRINGS {len(rings)}")
@@ -628,12 +641,12 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     iconst = pack("iconst", iconst_size, np.int32)
     if not all_state:
         iconst[obs_off:obs_off + obs.size] = obs
-    evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4}[solver]
+    evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4, "scipy": 6, "rk45": 6}[solver]
     smem = gemm_smem
     if tc is not None:
         smem = tc["nstage"] * (2 * 128 * 32 * 4 + 2 * tc["bt"] * 32 * 4)
         tc = dict(tc, smem=smem, xt_elems=tc_work)
-    return NetKernel("\n".join(src) + "\n", ns, int(obs.size), (work_size + 6 * ns) * nb + tc_work, work_size,
+    return NetKernel("\n".join(src) + "\n", ns, int(obs.size), (work_size + n_solver_vecs * ns) * nb + tc_work, work_size,
                      pack("work", work_size, real), const_buf, iconst,
                      pack("ring", ir.ring_size, real), pack("table", ir.table_size, real), block, solver, precision,
                      evals, n_phases, smem_bytes=smem, tc=tc)

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import runtime as rt
 from .emit_net import NetKernel, emit_net_kernel, tc_config
-from .engine import FIXED_STEP_SOLVERS, n_steps_for
+from .engine import ADAPTIVE_SOLVERS, FIXED_STEP_SOLVERS, n_steps_for
 from .netcompile import NetIR, netcompile
 from .program import Program
 
@@ -30,11 +30,12 @@ class NetworkModel:
         ``sweep`` names the scalar / uniform-vector arguments that vary per instance.  ``tensor_core``: run the batched
         dense couplings as tcgen05 3xTF32 GEMMs (float32 models, batch a multiple of 32; "auto" = whenever that
         applies), otherwise as fp32/fp64 FMA register tiles (one pass over W per 8 instances)."""
-        if solver not in FIXED_STEP_SOLVERS:
+        if solver not in FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS:
             raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
-                                      f"Supported solvers: {list(FIXED_STEP_SOLVERS)}.")
+                                      f"Supported solvers: {list(FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS)}.")
         self.prog = prog
         self.solver = solver
+        self.adaptive = solver in ADAPTIVE_SOLVERS
         self.precision = prog.float_precision
         self.real = prog.real_dtype
         self.n_batch = int(n_batch)
@@ -51,7 +52,8 @@ class NetworkModel:
         self.fmad = fmad
         self.blocks_per_sm = blocks_per_sm
         self._module: Optional[rt.Module] = None
-        self.t0 = int(np.asarray(prog.arg_by_kind("t").value))
+        t0 = np.asarray(prog.arg_by_kind("t").value)
+        self.t0 = float(t0) if self.adaptive else int(t0)
 
     @property
     def module(self) -> rt.Module:
@@ -67,13 +69,19 @@ class NetworkModel:
         return NetworkSession(self, n_samples, stream)
 
     def run(self, T: float, dt: float, dts: Optional[float] = None, *, y0: Optional[np.ndarray] = None,
-            params: Optional[np.ndarray] = None, **_):
-        """Returns ``(out[n_samples, n_obs, n_batch], y_final[n_state, n_batch])``."""
+            params: Optional[np.ndarray] = None, **solver_kwargs):
+        """Returns ``(out[n_samples, n_obs, n_batch], y_final[n_state, n_batch])``.  ``solver='scipy'`` accepts SciPy's
+        ``rtol`` / ``atol`` / ``max_step`` / ``method='RK45'`` (base_backend.py:802-812)."""
         steps, store_step, n_samples = n_steps_for(T, dt, dts)
+        if self.adaptive:
+            n_samples = int(round(T / (dts if dts else dt)))
         s = self.session(n_samples)
         try:
             s.reset(y0, params)
-            s.launch(steps, dt, store_step)
+            if self.adaptive:
+                s.launch_adaptive(T, dt, dts, **solver_kwargs)
+            else:
+                s.launch(steps, dt, store_step)
             out = s.download()
             y_final = s.download_state()
         finally:
@@ -188,6 +196,49 @@ class NetworkSession:
         self.samples_done += new_samples
         return new_samples
 
+    def launch_adaptive(self, T: float, dt: float, dts: Optional[float] = None, *, rtol: float = 1e-3, atol: float = 1e-6,
+                        max_step: float = np.inf, method: str = "RK45", max_attempts: int = 10_000_000, **unknown):
+        """solve_ivp(method='RK45', first_step=dt, t_eval=linspace(0, T, round(T/dts), endpoint=False)) for the whole
+        network in ONE persistent launch (grid-wide error norm, one step size for all units)."""
+        if method not in (None, "RK45"):
+            raise rt.CudaBackendError(f"solver='scipy' on the CUDA backend implements method='RK45'; got method={method!r}")
+        if unknown:
+            raise TypeError(f"unsupported solve_ivp options on the CUDA backend: {sorted(unknown)}")
+        if np.ndim(atol) or np.ndim(rtol):
+            raise rt.CudaBackendError("per-component tolerances are not supported; pass scalar rtol / atol")
+        k = self.m.kernel
+        step = dts if dts else dt
+        n_samples = int(round(T / step))
+        if n_samples > self.n_samples:
+            raise ValueError(f"session holds {self.n_samples} samples, the run records {n_samples}")
+        rtol = max(float(rtol), 100 * np.finfo(float).eps)
+        opts = np.zeros(16)
+        opts[:8] = [rtol, float(atol), self.m.t0, float(T), float(dt), (float(T) / n_samples) if n_samples else 0.0,
+                    float(max_step), float(max_attempts)]
+        self.d_opts = rt.DeviceBuffer.from_host(opts)
+        self.d_sync.zero(self.stream)
+        a = rt.KernelArgs()
+        a.n_steps, a.store_step, a.step0, a.t0, a.eval0 = n_samples, 1, 0, 0, 0
+        a.n_inst, a.sample0, a.dt = self.B, 0, float(dt)
+        a.y, a.out = self.d_y.ptr, self.d_out.ptr
+        a.params, a.slots = self.d_params.ptr, self.d_opts.ptr
+        a.rings, a.tables = self.d_rings.ptr, self.d_tables.ptr
+        a.consts, a.iconsts = self.d_consts.ptr, self.d_iconsts.ptr
+        a.work, a.sync, a.peers = self.d_work.ptr, self.d_sync.ptr, None
+        a.rank, a.world = 0, 1
+        self.m.module.run(k.kernel_name, a, block=k.block, grid=self.sm_count * self.m.blocks_per_sm,
+                          smem=k.smem_bytes, cooperative=True, stream=self.stream)
+        self.d_opts.download(opts, self.stream)
+        if self.stream is not None:
+            self.stream.synchronize()
+        self.check()
+        self.samples_done = n_samples
+        self.attempts = int(opts[12])
+        if int(opts[11]) != 0:
+            why = {1: "Required step size is less than spacing between numbers.", 2: "attempt budget exhausted"}
+            raise rt.CudaBackendError(f"adaptive integration failed: {why.get(int(opts[11]), 'unknown')}")
+        return n_samples
+
     def check(self):
         """Raise if a barrier timed out inside the kernel (lost peer / launch failure on another rank)."""
         words = np.zeros(8, dtype=np.uint64)
@@ -225,7 +276,7 @@ class NetworkSession:
             self._peer_ptrs = []
             if dist.is_initialized():
                 dist.barrier()                  # nobody frees memory a peer may still have mapped
-        for n in ("d_y", "d_out", "d_consts", "d_iconsts", "d_tables", "d_work", "d_rings", "d_sync", "d_peers", "d_params"):
+        for n in ("d_y", "d_out", "d_consts", "d_iconsts", "d_tables", "d_work", "d_rings", "d_sync", "d_peers", "d_params", "d_opts"):
             b = getattr(self, n, None)
             if b is not None:
                 b.free()

@@ -214,3 +214,32 @@ def test_grid_search_with_adaptive_solver_matches_reference_runs(gpu, registered
         c = adapt_circuit(path, {"u": float(grid["u"].values[i])}, pm)
         ref = c.run(outputs={"v": "pc/rpo_e_in/v"}, backend="default", verbose=False, clear=True, **kw)
         assert traj_rel_err(res.iloc[:, [i]].values, ref.values) <= 1e-7, i
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_population_network_run_with_scipy_solver_uses_the_adaptive_network_kernel(gpu, registered):
+    """CircuitTemplate.run(solver='scipy') on a population with dense Connectivity: too large for one thread, so the
+    whole network integrates adaptively in the persistent kernel; compared with the reference's solve_ivp run."""
+    from copy import deepcopy
+    from oracle.make_golden import _wc_pop
+    from pyrates_b200.netengine import NetworkModel
+    import pyrates_b200.backend as be
+    tpl = _wc_pop(128)()
+    kw = dict(simulation_time=40.0, step_size=1e-3, sampling_step_size=0.5, solver="scipy", outputs={"r": "e/rate_op/r"},
+              verbose=False, float_precision="float64", clear=True, rtol=1e-7, atol=1e-10)
+    ref = deepcopy(tpl).run(backend="default", **kw)
+    seen = []
+    orig = NetworkModel.__init__
+
+    def spy(self, *a, **k):
+        seen.append(k.get("solver"))
+        return orig(self, *a, **k)
+    NetworkModel.__init__ = spy
+    try:
+        got = deepcopy(tpl).run(backend="cuda", **kw)
+    finally:
+        NetworkModel.__init__ = orig
+    assert seen == ["scipy"]
+    assert got.shape == ref.shape == (80, 128)
+    assert traj_rel_err(got.values, ref.values) <= 1e-9

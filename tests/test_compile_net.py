@@ -96,3 +96,17 @@ def test_operand_tiling_roundtrip_and_split():
     hi, lo = tcgemm.split_tf32(m)
     assert np.array_equal(hi + lo, m) and not np.any(hi.view(np.uint32) & 0x1FFF)
     assert np.max(np.abs(lo)) <= np.max(np.abs(m)) * 2.0 ** -10
+
+
+@pytest.mark.parametrize("name", ["wc_n128_rk45", "kuramoto_n128_rk45"])
+def test_adaptive_network_kernel_compiles(name):
+    os.environ["PRB_CACHE_DIR"] = "off"
+    m = NetworkModel(Program.load(golden_path(name)), solver="scipy")
+    assert "typedef double prb_time" in m.kernel.source and "#define PRB_SOLVER 4" in m.kernel.source
+    assert m.kernel.work_elems >= 11 * m.kernel.n_state            # Y, YN, two stage inputs, K0..K6
+    mod = rt.compile_module(m.kernel.source, f"{name}.cu", verbose_ptxas=True)
+    assert all("0 bytes spill stores" in l for l in mod.log.splitlines() if "spill" in l), mod.log
+    with pytest.raises(UnsupportedModelError, match="adaptive"):
+        NetworkModel(Program.load(golden_path("wc_n128_f32")), solver="scipy")
+    with pytest.raises(UnsupportedModelError, match="adaptive"):
+        NetworkModel(Program.load(golden_path("qsfa_both_n96")), solver="scipy")

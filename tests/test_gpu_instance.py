@@ -14,8 +14,8 @@ from pyrates_b200.program import Program
 pytestmark = pytest.mark.gpu
 
 SKIP = {"kuramoto_n128", "qsfa_both_n96", "wc_n128", "wc_n128_f32", "jrc_grid_b1024", "wc_n300_f32",
-        "qsfa_both_n96_f32", "kuramoto_n128_f32"}                                             # network-mode fixtures
-ADAPTIVE = [n for n in golden_names() if "_rk45" in n]
+        "qsfa_both_n96_f32", "kuramoto_n128_f32", "wc_n128_rk45", "kuramoto_n128_rk45"}                                             # network-mode fixtures
+ADAPTIVE = [n for n in golden_names() if "_rk45" in n and n not in SKIP]
 NAMES = [n for n in golden_names() if n not in SKIP and n not in ADAPTIVE]
 SOLVERS = ["euler", "heun", "heun_true", "rk4"]
 

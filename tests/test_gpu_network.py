@@ -12,6 +12,7 @@ from pyrates_b200.program import Program
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
 
+ADAPTIVE = ["qif_rk45", "jrc_rk45_tight", "qif_sfa_rk45", "wc_n8_rk45", "wc_n128_rk45", "kuramoto_n128_rk45"]
 NAMES = ["wc_n8", "wc_n128", "wc_n128_f32", "wc_n300_f32", "qsfa_both_n96_f32", "kuramoto_n128_f32", "qsfa_cascade_n8", "qsfa_ring_n8", "qsfa_both_n8", "qsfa_both_n96",
          "kuramoto_n8", "kuramoto_n128", "kuramoto_scalar_n128", "jrc_grid_b16", "jrc_grid_b1024", "jrc", "net8", "net9",
          "net13", "jrc_2delay", "qif_input", "ring_kat", "gamma_kat"]
@@ -142,3 +143,35 @@ def test_tensor_core_network_sweep_matches_per_instance_oracle(gpu, name, sweep,
         rec, _ = orc.run(f, args, r["T"], r["dt"], r["dts"], solver)
         assert traj_rel_err(out[:, :, b], rec) <= RTOL["float32"], (name, b)
         assert traj_rel_err(out[:, :, b], simt[:, :, b]) <= RTOL["float32"], (name, b)
+
+
+@pytest.mark.parametrize("name", ADAPTIVE)
+def test_adaptive_rk45_network_kernel_matches_reference_scipy(gpu, name):
+    """solver='scipy' in the persistent network kernel: SciPy's RK45 with a grid-wide error norm (one step size for the
+    whole network), stage vectors in HBM, dense output at the sample times — vs the real reference + SciPy."""
+    fx = orc.load_fixture(golden_path(name))
+    r = fx["run"]
+    m = NetworkModel(Program.load(golden_path(name)), solver="scipy")
+    before = rt.launch_count()
+    s = m.session(int(round(r["T"] / r["dts"])))
+    try:
+        s.reset()
+        s.launch_adaptive(r["T"], r["dt"], r["dts"], rtol=r["rtol"], atol=r["atol"])
+        out = s.download()[:, :, 0]
+        attempts = s.attempts
+    finally:
+        s.free()
+    assert rt.launch_count() == before + 1
+    ref = fx["extra"]["rec_scipy"]
+    assert out.shape == ref.shape
+    f = orc.build_vector_field(fx["source"])
+    n = [0]
+
+    def counted(*a):
+        n[0] += 1
+        return f(*a)
+    args = [np.array(a, copy=True) for a in fx["args"]]
+    args[0] = args[0][()]
+    orc.run_adaptive(counted, args, r["T"], r["dt"], r["dts"], rtol=r["rtol"], atol=r["atol"])
+    assert attempts == (n[0] - 1) // 6                      # same accept / reject sequence as SciPy
+    assert traj_rel_err(out, ref) <= 1e-9, name
