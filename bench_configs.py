@@ -205,6 +205,21 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "model": "this rank's W shard bytes x evaluations per step (state vectors negligible); per GPU"},
             "jit_s": jit_s, "phases": m.kernel.n_phases, "block": m.kernel.block, "batch": a.batch, "precision": a.precision}
+    if a.batch > 1 and params is not None:
+        # end to end through the host API of a network sweep: swept parameters + initial state from host memory in,
+        # recorded trajectories [n_samples, n_obs, B] back in host memory (constants stay resident, like a model would
+        # across grid_search chunks)
+        e2e_steps = a.steps
+        t_e = time.perf_counter()
+        s.reset(params=params)
+        s.samples_done = 0
+        s.launch(e2e_steps, dt, 1)
+        host = s.download()
+        e2e_s = time.perf_counter() - t_e
+        line["e2e"] = {"value": nodes * a.batch * e2e_steps / e2e_s, "unit": "node-steps/s", "steps": e2e_steps,
+                       "h2d_bytes_per_step": int((params.nbytes + m.n_state * a.batch * np.dtype(m.real).itemsize) / e2e_steps),
+                       "d2h_bytes_per_step": int(host[:e2e_steps].nbytes / e2e_steps), "ms_per_step": e2e_s * 1e3 / e2e_steps,
+                       "api": "NetworkSession.reset / launch / download (what NetworkSweep.run does per call)"}
     if a.batch > 1:
         # sweep-batched coupling is GEMM-shaped: 2 flops per (target, source, instance) and evaluation
         flops = sum(2.0 * r.n * r.m for r in m.ir.reductions if r.kind == "row") * a.batch * evals * a.steps     # per GPU

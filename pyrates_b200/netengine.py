@@ -156,9 +156,9 @@ class NetworkSession:
             if params.shape != (n_par, B):
                 raise ValueError(f"params must have shape ({n_par}, {B}) in the order {self.m.param_names}")
             self.d_params.upload(params, self.stream)
-        work = np.zeros(max(k.work_elems, 1), dtype=real)
-        work[: k.work_init.size * B] = np.repeat(k.work_init, B)
-        self.d_work.upload(work, self.stream)
+        self.d_work.zero(self.stream)                        # solver vectors / operand tiles: cleared on the device
+        if k.work_init.size:
+            self.d_work.upload(np.ascontiguousarray(np.repeat(k.work_init, B), dtype=real), self.stream)
         self.d_rings.upload(np.ascontiguousarray(np.repeat(k.ring_init, B), dtype=real), self.stream)
         self.steps_done = 0
         self.samples_done = 0

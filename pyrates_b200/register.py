@@ -239,9 +239,12 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
         # together in the persistent network kernel, their couplings as one GEMM per evaluation
         ns = NetworkSweep(prog, sweep, base["observers"], solver=solver, T=simulation_time, dt=step_size,
                           dts=sampling_step_size, n_inst=B, tensor_core=tensor_core)
-        for elem, k in y0_rows:
-            ns.set_y0(elem, grid_vals[k])
-        res = ns.run(table)
+        try:
+            for elem, k in y0_rows:
+                ns.set_y0(elem, grid_vals[k])
+            res = ns.run(table)
+        finally:
+            ns.free()
 
     circuit_names = [f"{name}_{idx}" for idx in param_grid.index]
     param_grid = param_grid.copy()

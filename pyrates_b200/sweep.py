@@ -216,6 +216,7 @@ class NetworkSweep:
         self.y0 = np.repeat(np.asarray(prog.y0, dtype=self.model.real)[:, None], self.Bp, axis=1)
         self.n_obs = len(self.model.observers)
         self._y_final = None
+        self._sess = None            # device buffers (connectivity tiles, work vectors) live across run() calls
 
     def set_y0(self, elem: int, values: np.ndarray):
         self.y0[elem, : self.B] = values
@@ -229,11 +230,20 @@ class NetworkSweep:
         for r, arg in enumerate(self.names):
             params[r, : self.B] = table[self.rows[arg]]
             params[r, self.B:] = table[self.rows[arg], -1]
-        out, self._y_final = self.model.run(self.T, self.dt, self.dts, y0=self.y0, params=params)
+        steps, store_step, n_samples = n_steps_for(self.T, self.dt, self.dts)
+        if self._sess is None:
+            self._sess = self.model.session(n_samples)       # uploads the packed constants (W, or its hi / lo tiles) once
+        s = self._sess
+        s.reset(self.y0, params)                             # H2D: initial state, swept parameters, buffer images
+        s.launch(steps, self.dt, store_step)
+        out = s.download()                                   # D2H: [n_samples, n_obs, Bp]
+        self._y_final = s.download_state()
         return out[:, :, : self.B]
 
     def final_state(self) -> np.ndarray:
         return self._y_final[:, : self.B]
 
     def free(self):
-        pass
+        if self._sess is not None:
+            self._sess.free()
+            self._sess = None
