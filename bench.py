@@ -37,6 +37,9 @@ SWEEP = [("u", 0), ("weight_v2", 0), ("weight_v2", 1), ("weight", 0), ("weight_v
 # from the `ncu --set full` capture summarised in profiles/r01_c2_fastmath_prb_integrate_ncu_full.txt (110.79 + 847.40 MB;
 # the exact kernel, profiles/r01_c2_prb_integrate_ncu_full.txt: 114.07 + 848.98 MB — the observer store either way).
 NCU_TRAFFIC_BYTES_PER_LAUNCH = 958.2e6
+# per-launch DRAM bytes by instance-steps per launch: 1000-step launches (--chunk-samples 100) and the default 250-step
+# launches (--chunk-samples 25; profiles/r01_c2_fastmath_chunk25_ncu_full.txt)
+NCU_TRAFFIC = {2 ** 20 * 1000: NCU_TRAFFIC_BYTES_PER_LAUNCH, 2 ** 20 * 250: 329.29e6}    # 110.80 + 218.48 MB
 FP64_INSTR = {True: 317, False: 505}     # fp64-pipe instructions per instance-step in the loop (cuobjdump, fast / exact kernel)
 METRIC = "state-updates/sec (nodes x sweeps x steps/s), JRC RK4 grid_search"
 UNIT = "node-steps/s"
@@ -124,6 +127,8 @@ def main():
     ap.add_argument("--sim-time", type=float, default=1.0)
     ap.add_argument("--cpu-sim-time", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk-samples", type=int, default=25,
+                    help="samples per launch: the D2H of chunk c overlaps the kernel of chunk c+1, the last chunk's copy is the e2e tail")
     ap.add_argument("--strict-div", action="store_true",
                     help="exact kernels: IEEE divisions, library exp (default: reciprocal multiplies, table exp, rcp + cubic "
                          "step, folded constant chains — each <= 2 ulp, trajectories within 1e-15 of the exact kernel)")
@@ -182,7 +187,7 @@ def main():
     B = a.grid * a.grid
     t_jit = time.perf_counter()
     sw = BatchedSweep(prog, SWEEP, observers=[0], solver="rk4", T=a.sim_time, dt=1e-4, dts=1e-3, n_inst=B,
-                      chunk_samples=100, const_div_to_mul=not a.strict_div)
+                      chunk_samples=a.chunk_samples, const_div_to_mul=not a.strict_div)
     sw.model.module                      # JIT (NVRTC) happens here, outside every timed region
     jit_s = time.perf_counter() - t_jit
     table = param_table(a.grid, a.grid, rank * B, (rank + 1) * B)     # weak scaling: each rank its own grid block
@@ -244,8 +249,8 @@ def main():
                 "ms_per_step": e2e_s * 1e3 / a.steps, "api": "pyrates_b200.sweep.BatchedSweep.run", "checksum": checksum},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": (NCU_TRAFFIC_BYTES_PER_LAUNCH if (a.grid == 1024 and inst_steps_per_launch == 2 ** 20 * 1000) else None),
-                     "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_c2_fastmath_prb_integrate_ncu_full.txt)",
+                     "traffic": (NCU_TRAFFIC.get(int(inst_steps_per_launch)) if a.grid == 1024 else None),
+                     "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_c2_fastmath_*_ncu_full.txt)",
                      "algorithmic_bytes_per_launch": B_ALG * inst_steps_per_launch, "peak_source": which, "kernel": "prb_integrate (fused JRC rhs + RK4 + observer store)",
                      "algorithmic_bytes_per_instance_step": B_ALG, "launch_ms": launch_s * 1e3,
                      "note": "state/stages are register-resident across the launch: real DRAM traffic is only the "

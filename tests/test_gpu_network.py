@@ -175,3 +175,28 @@ def test_adaptive_rk45_network_kernel_matches_reference_scipy(gpu, name):
     orc.run_adaptive(counted, args, r["T"], r["dt"], r["dts"], rtol=r["rtol"], atol=r["atol"])
     assert attempts == (n[0] - 1) // 6                      # same accept / reject sequence as SciPy
     assert traj_rel_err(out, ref) <= 1e-9, name
+
+
+def test_tensor_core_sweep_chunked_launches_continue(gpu):
+    """Two launches that continue from the device-resident state == one launch, on the tcgen05 path (pipeline state,
+    TMEM allocation and operand tiles are rebuilt per launch; ring heads and sample counters carry over)."""
+    name, sweep, B = "qsfa_both_n96_f32", ["I_ext"], 64
+    fx = orc.load_fixture(golden_path(name))
+    prog = Program.load(golden_path(name))
+    r = fx["run"]
+    from pyrates_b200.engine import n_steps_for
+    steps, ss, ns = n_steps_for(r["T"], r["dt"], r["dts"])
+    m = NetworkModel(prog, solver="heun", n_batch=B, sweep=sweep)
+    assert m.kernel.tc is not None
+    params = m.param_defaults[:, None] + np.linspace(-0.2, 0.4, B)[None, :]
+    one, _ = m.run(r["T"], r["dt"], r["dts"], params=params)
+    s = m.session(ns)
+    try:
+        s.reset(params=params)
+        cut = steps // 2 + 1
+        s.launch(cut, r["dt"], ss)
+        s.launch(steps - cut, r["dt"], ss)
+        two = s.download()
+    finally:
+        s.free()
+    assert np.array_equal(one, two)
