@@ -312,6 +312,9 @@ ADAPTIVE_CASES = {
     "qif_sfa_rk45": dict(build=_yaml(NM + "qif.qif_sfa"), T=2.0, dt=1e-3, dts=5e-3, out="p/qif_sfa_op/r",
                          kw=dict(rtol=1e-6, atol=1e-8)),
     "wc_n8_rk45":   dict(build=_wc_pop(8), T=0.5, dt=1e-3, dts=5e-3, out="e/rate_op/r", kw=dict(rtol=1e-6, atol=1e-9)),
+    # extrinsic input with an adaptive solver: the frontend emits interp(t, time, u_input) (circuit.py:1692-1709)
+    "qif_input_rk45": dict(build=_yaml(NM + "qif.qif"), T=2.0, dt=1e-3, dts=1e-2, out="p/qif_op/r",
+                           inputs=lambda: {"p/qif_op/I_ext": _sin_input(2000) * 3.0}, kw=dict(rtol=1e-7, atol=1e-9)),
     # networks too large for one thread: adaptive integration in the persistent network kernel (grid-wide error norm)
     "wc_n128_rk45": dict(build=_wc_pop(128), T=60.0, dt=1e-3, dts=0.5, out="e/rate_op/r", kw=dict(rtol=1e-7, atol=1e-10)),
     "kuramoto_n128_rk45": dict(build=_kuramoto(128), T=10.0, dt=1e-3, dts=0.05, out="e/phase_op/theta",
@@ -330,6 +333,7 @@ def make_adaptive_case(name: str, spec: dict, cap: Capture) -> str:
         try:
             circuit = spec["build"]()
             circuit.run(simulation_time=T, step_size=dt, sampling_step_size=dts, solver="scipy", outputs={"o": spec["out"]},
+                        inputs=spec["inputs"]() if "inputs" in spec else None,
                         backend="default", float_precision="float64", verbose=False, clear=True, **kw)
         finally:
             os.chdir(cwd)

@@ -268,7 +268,11 @@ prb_rhs_eval(const __grid_constant__ prb_kernel_args A)
     real y[PRB_NS], k[PRB_NS];
     PRB_UNROLL_NS
     for (int j = 0; j < PRB_NS; ++j) y[j] = Y[(long long)j * B + b];
+#if PRB_SOLVER == PRB_SOLVER_RK45
+    prb_rhs((prb_time)A.dt, y, k, T);            // float time of the evaluation travels in args.dt
+#else
     prb_rhs(A.step0 + A.t0, y, k, T);
+#endif
     real* __restrict__ out = (real*)A.out;
     PRB_UNROLL_NS
     for (int j = 0; j < PRB_NS; ++j) out[(long long)j * B + b] = k[j];

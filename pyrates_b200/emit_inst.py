@@ -166,6 +166,9 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
         elif op == "table":
             tab, tnode, col, ncols = g.payload[i]
             expr = f"T.tables[{int(tab_off[tab])}LL + {ref(tnode, False)} * {ncols}LL + {col}LL]"
+        elif op == "interp":
+            tx, tf, n_pts = g.payload[i]
+            expr = f"prb_interp(T.tables + {int(tab_off[tx])}LL, T.tables + {int(tab_off[tf])}LL, {n_pts}, {ref(a[0])})"
         elif op == "ring":
             ring, row, col, shift = g.payload[i]
             L = rhs.rings[ring].length
@@ -234,7 +237,8 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     ns = rhs.n_state
     nrings = len(rhs.rings)
     adaptive = solver in ADAPTIVE_SOLVERS
-    if adaptive and (rhs.rings or rhs.tables or rhs.slots):
+    step_tables = any(rhs.graph.ops[i] == "table" for i in rhs.live_nodes())
+    if adaptive and (rhs.rings or step_tables or rhs.slots):
         raise UnsupportedModelError("adaptive integration (solver='scipy') needs a pure vector field: delay ring buffers, "
                                     "step-indexed input tables and mutable buffers are fixed-step constructs")
     pure = not (rhs.rings or rhs.slots or rhs.ring_writes or rhs.slot_writes)
@@ -338,6 +342,20 @@ __device__ __forceinline__ double prb_fast_div(const double a, const double b) {
 __device__ __forceinline__ real prb_max(real a, real b) { return (a != a || b != b) ? a + b : (a > b ? a : b); }
 __device__ __forceinline__ real prb_min(real a, real b) { return (a != a || b != b) ? a + b : (a < b ? a : b); }
 __device__ __forceinline__ real prb_sign(real a) { return (real)((a > (real)0) - (a < (real)0)); }
+// numpy.interp(x, xp, fp) for one x (timed inputs of the adaptive solvers): clamp outside [xp[0], xp[n-1]], else
+// slope * (x - xp[j]) + fp[j] with xp[j] <= x < xp[j+1] (the expression NumPy's C loop evaluates)
+__device__ __forceinline__ real prb_interp(const real* __restrict__ xp, const real* __restrict__ fp, const int n, const real x) {
+    if (!(x > __ldg(xp))) return __ldg(fp);
+    if (x >= __ldg(xp + n - 1)) return __ldg(fp + n - 1);
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(xp + mid) <= x) lo = mid; else hi = mid;
+    }
+    const real x0 = __ldg(xp + lo), f0 = __ldg(fp + lo);
+    const real slope = (__ldg(fp + lo + 1) - f0) / (__ldg(xp + lo + 1) - x0);
+    return slope * (x - x0) + f0;
+}
 // physical ring position of logical column `col` (may be negative by the pending roll) at head `head`
 __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
     int p = col - head;

@@ -254,15 +254,18 @@ class InstanceSession:
                 b.free()
 
 
-def evaluate_rhs(prog: Program) -> np.ndarray:
-    """One evaluation ``dy = f(t, y, *args)`` of the vector field on the GPU (kernel ``prb_rhs_eval``)."""
-    m = InstanceModel(prog, solver="euler")
+def evaluate_rhs(prog: Program, t: Optional[float] = None) -> np.ndarray:
+    """One evaluation ``dy = f(t, y, *args)`` of the vector field on the GPU (kernel ``prb_rhs_eval``).  Programs built
+    for an adaptive solver carry a float ``t`` (optionally overridden by ``t``)."""
+    float_time = not np.issubdtype(np.asarray(prog.arg_by_kind("t").value).dtype, np.integer)
+    m = InstanceModel(prog, solver="scipy" if float_time else "euler")
     s = m.session(1, 0)
     d_dy = rt.DeviceBuffer(max(m.n_state, 1) * np.dtype(m.real).itemsize)
     try:
         s.reset()
         a = rt.KernelArgs()
-        a.n_steps, a.store_step, a.step0, a.t0, a.eval0, a.n_inst, a.sample0, a.dt = 0, 1, 0, m.t0, 0, 1, 0, 0.0
+        a.n_steps, a.store_step, a.step0, a.eval0, a.n_inst, a.sample0 = 0, 1, 0, 0, 1, 0
+        a.t0, a.dt = (0, float(m.t0 if t is None else t)) if float_time else (int(m.t0), 0.0)
         a.y, a.out, a.params = s.d_y.ptr, d_dy.ptr, s.d_params.ptr
         a.slots, a.rings, a.tables = s.d_slots.ptr, s.d_rings.ptr, s.d_tables.ptr
         m.module.run("prb_rhs_eval", a, block=m.kernel.block)

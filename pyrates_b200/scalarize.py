@@ -368,6 +368,7 @@ class _Interp:
                   ast.parse(f"_[{s.lhs_idx}]", mode="eval").body.slice if s.lhs_idx is not None else None)
                  for s in prog.stmts]
         self.trees = trees
+        self.interp_args = set()
         t_indexed, rolled = self._prescan(trees)
 
         for a in prog.args:
@@ -383,6 +384,10 @@ class _Interp:
                 arr = np.empty(v.size, dtype=object)
                 arr[:] = None
                 self.env[a.name] = arr
+            elif a.name in self.interp_args:
+                if a.kind != "const" or any(n == a.name for n, _ in sweep):
+                    raise UnsupportedModelError(f"interpolation table `{a.name}` must be a constant that is not swept")
+                self.env[a.name] = None                          # only ever used as an argument of interp()
             elif a.name in t_indexed:
                 if a.kind != "const":
                     raise UnsupportedModelError(f"time-indexed buffer `{a.name}` must be constant")
@@ -438,9 +443,12 @@ class _Interp:
                 if isinstance(node, ast.Call) and getattr(node.func, "id", None) == "roll":
                     if node.args and isinstance(node.args[0], ast.Name):
                         rolled.add(node.args[0].id)
-                if isinstance(node, ast.Call) and getattr(node.func, "id", None) in ("interp", "interp_rows"):
-                    raise UnsupportedModelError("interpolated (adaptive-step) inputs are not supported; use a "
-                                                "fixed-step solver ('euler', 'heun', 'heun_true', 'rk4')")
+                if isinstance(node, ast.Call) and getattr(node.func, "id", None) == "interp_rows":
+                    raise UnsupportedModelError("multi-column interpolated (adaptive-step) inputs are not supported")
+                if isinstance(node, ast.Call) and getattr(node.func, "id", None) == "interp":
+                    for arg in node.args[1:]:
+                        if isinstance(arg, ast.Name):
+                            self.interp_args.add(arg.id)       # (time, value) tables: read from memory, never unrolled
         return t_indexed, rolled
 
     # -- expression evaluation
@@ -541,6 +549,19 @@ class _Interp:
             if axis is None or (axis % nd) != nd - 1:
                 raise UnsupportedModelError("ring buffers must be rolled along their last axis")
             return _Rolled(base, shift, axis)
+        if fname == "interp":
+            # adaptive solvers: timed inputs are interpolated, `interp(t, time, u_input)` (frontend/template/circuit.py:
+            # 1692-1709; numpy.interp semantics) -> one 'interp' node over two constant tables (time grid, values)
+            if len(n.args) != 3 or not all(isinstance(a, ast.Name) for a in n.args[1:]):
+                raise UnsupportedModelError(f"unsupported interp call `{ast.unparse(n)}`")
+            tv = self._arr(self.ev(n.args[0]))
+            xp = np.asarray(self.p.arg(n.args[1].id).value, dtype=np.float64)
+            fp = np.asarray(self.p.arg(n.args[2].id).value, dtype=np.float64)
+            if tv.ndim != 0 or xp.ndim != 1 or fp.shape != xp.shape or xp.size < 2:
+                raise UnsupportedModelError("interp is supported for a scalar time over 1-d (time, value) tables")
+            self.tables.append(TableSpec(n.args[1].id, xp.shape, xp))
+            self.tables.append(TableSpec(n.args[2].id, fp.shape, fp))
+            return _obj(g._node("interp", (tv[()].id,), (len(self.tables) - 2, len(self.tables) - 1, int(xp.size))))
         args = [self.ev(a) for a in n.args]
         if fname in UNARY_FUNCS:
             return self._map1(fname, args[0])

@@ -107,7 +107,25 @@ def test_adaptive_rk45_matches_reference_scipy(gpu, name):
     assert rt.launch_count() == before + 1
     ref = fx["extra"]["rec_scipy"]
     assert out[:, :, 0].shape == ref.shape
-    assert traj_rel_err(out[:, :, 0], ref) <= 1e-9, name
+    # a piecewise-linear input makes the embedded error estimate jump at every knot: accept / reject decisions then hang on
+    # the last bit (perturbing y0 by 2e-16 moves the ORACLE by 2.8e-5 and changes its attempt count 451 -> 470), so this
+    # fixture is compared at the solver's own accuracy; the interpolation itself is pinned by the rhs test below
+    tol = 1e-3 if name == "qif_input_rk45" else 1e-9
+    assert traj_rel_err(out[:, :, 0], ref) <= tol, name
+
+
+def test_interpolated_input_rhs_matches_numpy_interp(gpu):
+    """interp(t, time, u_input) of the adaptive build (numpy.interp semantics): knots, interior points, both clamps."""
+    from pyrates_b200.engine import evaluate_rhs
+    fx = orc.load_fixture(golden_path("qif_input_rk45"))
+    prog = Program.load(golden_path("qif_input_rk45"))
+    f = orc.build_vector_field(fx["source"])
+    time = fx["args"][fx["names"].index("time")]
+    for t in [0.0, float(time[1]), float(time[7]) * 0.999999, 0.123456789, float(time[-2]) + 1e-7, float(time[-1]), 2.5, -0.3]:
+        args = [np.array(a, copy=True) for a in fx["args"]]
+        ref = f(t, args[1], *args[2:]).copy()
+        got = evaluate_rhs(prog, t=t)
+        np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-13)
 
 
 def test_adaptive_rk45_batch_has_independent_step_sequences(gpu):
