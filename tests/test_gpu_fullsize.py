@@ -134,3 +134,24 @@ def test_fast_math_falls_back_to_exact_evaluation_outside_the_fast_range(gpu):
         outs.append(out)
     assert np.all(np.isfinite(outs[0])) and traj_rel_err(outs[1][:, :, 0], outs[0][:, :, 0]) <= 1e-12
     assert traj_rel_err(outs[1][:, :, 1], outs[0][:, :, 1]) <= 1e-12
+
+
+def test_sweep_results_can_stay_on_the_device_as_torch_tensors(gpu):
+    """BatchedSweep.run_torch: parameters from a CUDA tensor, trajectories left in a CUDA tensor the kernels wrote —
+    bit-identical to the host path, and usable by torch on the same stream without synchronisation calls."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("torch sees no CUDA device")
+    prog = Program.load(golden_path("jrc"))
+    B = 4096
+    table = bench.param_table(64, 64, 0, B)
+    sw = BatchedSweep(prog, bench.SWEEP, observers=[0, 2], solver="rk4", T=0.05, dt=1e-4, dts=1e-3, n_inst=B, chunk_samples=10)
+    try:
+        host = np.array(sw.run(table), copy=True)
+        dev = sw.run_torch(torch.as_tensor(table, device="cuda"))
+        assert dev.is_cuda and tuple(dev.shape) == host.shape
+        peak = dev.abs().amax(dim=0)                        # consumer on torch's stream, right behind the kernel
+        assert np.array_equal(dev.cpu().numpy(), host)
+        np.testing.assert_array_equal(peak.cpu().numpy(), np.abs(host).max(axis=0))
+    finally:
+        sw.free()
