@@ -56,10 +56,14 @@ enum { PRB_SOLVER_EULER = 0, PRB_SOLVER_HEUN_REF = 1, PRB_SOLVER_HEUN = 2, PRB_S
  *   out    [n_samples][n_obs][B]   recorded observers; row k holds the state at step k*store_step,
  *                                  sampled BEFORE the update (base_backend.py:730-733)
  *   params [n_params][B]           per-instance (swept) parameters
- *   slots  [n_slots][B]            persistent mutable scalars (non-ring buffers mutated by the rhs)
+ *   slots  [n_slots][B]            persistent mutable scalars (non-ring buffers mutated by the rhs); adaptive NETWORK kernels
+ *                                  (PRB_SOLVER_RK45, cooperative) read their 8 option doubles here and use [8..12] as
+ *                                  error-norm accumulators / status / attempt count
  *   rings  [ring elems][B]         delay ring buffers, physical storage, circular addressing
  *   tables [..]                    timed-input tables u[t] shared by all instances (circuit.py:1711-1719)
- *   consts / iconsts               packed real / int32 constant arrays of network-mode kernels (W, idx)
+ *   consts / iconsts               packed real / int32 constant arrays of network-mode kernels (W, idx; for the tcgen05
+ *                                  sweep kernels also W split into hi / lo K-major 128 x 32 tiles); adaptive INSTANCE
+ *                                  kernels read their 8 option doubles behind `consts`
  *   work                           network-mode scratch (stage vectors, materialised intermediates)
  *   sync                           network-mode barrier words, 64-bit each (zero-initialised by the caller):
  *                                  [0] local CTA arrivals, [1] release epoch, [2] error flag, [8+q] arrival epoch of rank q
@@ -96,7 +100,7 @@ typedef struct prb_run_desc {
     int32_t  cooperative;   /* 0: plain launch (instance kernels); 1: cooperative persistent grid (network kernels) */
     uint32_t grid_dim;      /* 0 = library chooses: ceil(n_inst/block) or SMs x occupancy for cooperative */
     uint32_t block_dim;
-    uint32_t smem_bytes;    /* dynamic shared memory */
+    uint32_t smem_bytes;    /* dynamic shared memory (tcgen05 operand ring: up to 192 KB; DMMA / FMA GEMM tiles: up to 75 KB) */
     uint32_t reserved;
     void*    stream;        /* CUstream or NULL */
     prb_kernel_args args;
