@@ -243,3 +243,34 @@ def test_population_network_run_with_scipy_solver_uses_the_adaptive_network_kern
     assert seen == ["scipy"]
     assert got.shape == ref.shape == (80, 128)
     assert traj_rel_err(got.values, ref.values) <= 1e-9
+
+
+NM, OSC = "model_templates.neural_mass_models.", "model_templates.oscillators."
+ZOO = [  # every circuit of the reference's model_templates that the reference itself can build (3 have template errors),
+         # except the complex-valued ones (theta.kmo_theta, kuramoto.kmo_mf*: UnsupportedModelError by design)
+    (NM + "ik.ik_eta", "p/ik_eta_op/r", 30.0, 1e-2), (NM + "ik.ik_nodim", "p/ik_nodim_op/r", 1.0, 1e-3),
+    (NM + "ik.ik_theta", "p/ik_theta_op/r", 30.0, 1e-2), (NM + "jansenrit.JRC2", "jrc/jrc_op/V_e", 0.2, 1e-4),
+    (NM + "qif.qif_conduct", "p/qif_conduct_op/r", 1.0, 1e-3), (NM + "qif.qif_sd", "p/qif_op/r", 1.0, 1e-3),
+    (NM + "qif.qif_tsodyks", "p/qif_op/v", 1.0, 1e-3), (NM + "wilsoncowan.WC", "e/rate_op/r", 20.0, 1e-2),
+    (NM + "wilsoncowan.WC_stp", "e/rate_op/r", 20.0, 1e-2), (OSC + "kuramoto.kmo", "p/phase_op/theta", 2.0, 1e-3),
+    (OSC + "kuramoto.kmo_2coupled", "p1/phase_op/theta", 2.0, 1e-3), (OSC + "stuartlandau.sl", "p/sl_op/x", 5.0, 1e-3),
+    (OSC + "vanderpol.vdp", "p/vdp_op/x", 5.0, 1e-3),
+]
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("solver", ["heun", "scipy"])
+@pytest.mark.parametrize("path,out,T,dt", ZOO)
+def test_model_zoo_runs_on_cuda_like_on_numpy(gpu, registered, path, out, T, dt, solver):
+    """The reference's own model templates through the public run() call, both backends, fixed-step and adaptive."""
+    kw = dict(simulation_time=T, step_size=dt, sampling_step_size=dt * 10, solver=solver, outputs={"o": out}, verbose=False,
+              float_precision="float64", clear=True)
+    if solver == "scipy":
+        kw.update(rtol=1e-7, atol=1e-10)
+    ref = _fresh(path).run(backend="default", **kw)
+    got = _fresh(path).run(backend="cuda", **kw)
+    assert got.shape == ref.shape
+    if not np.all(np.isfinite(ref.values)):
+        pytest.skip("the reference trajectory itself is not finite for the template defaults")
+    assert traj_rel_err(got.values, ref.values) <= (1e-9 if solver == "heun" else 1e-7)
