@@ -24,6 +24,8 @@ from __future__ import annotations
 import os
 from typing import Callable, Dict, List, Optional, Tuple, Union
 
+import warnings
+
 import numpy as np
 
 from . import runtime as rt
@@ -175,12 +177,16 @@ class CudaBackend:
     def get_var(self, v):
         """base_backend.py:326-340: value in backend precision; (1,) constants squeezed to 0-d."""
         if v.is_float or v.is_complex:
-            if v.is_complex:
-                raise UnsupportedModelError("complex-valued models are not supported by the CUDA backend")
             dtype = self._float_precision
+            if 'complex' in str(dtype):
+                raise UnsupportedModelError("complex-valued models (float_precision='complex64/128') are not supported by the "
+                                            "CUDA backend")
         else:
             dtype = self._int_precision
-        result = np.asarray(v.value, dtype=dtype)
+        with warnings.catch_warnings():
+            # like the reference, a complex template variable built with a real float_precision keeps its real part
+            warnings.simplefilter("ignore")
+            result = np.asarray(v.value, dtype=dtype)
         if result.shape == (1,) and v.vtype == 'constant':
             result = result.squeeze()
         return result

@@ -565,8 +565,13 @@ class _Interp:
         args = [self.ev(a) for a in n.args]
         if fname in UNARY_FUNCS:
             return self._map1(fname, args[0])
-        if fname == "conjugate" or fname in ("real", "imag"):
-            raise UnsupportedModelError("complex-valued models are not supported by the CUDA backend")
+        if fname in ("conjugate", "real"):
+            return args[0]          # real-valued build (complex argument arrays are rejected up front): identity, as in NumPy
+        if fname == "imag":
+            a0 = self._arr(args[0])
+            out = np.empty(a0.shape, dtype=object)
+            out[...] = g.const(0.0)
+            return out if a0.ndim else _obj(g.const(0.0))
         if fname == "sigmoid":
             x = self._arr(args[0])
             one = _obj(g.const(1.0, weak=True))

@@ -246,15 +246,16 @@ def test_population_network_run_with_scipy_solver_uses_the_adaptive_network_kern
 
 
 NM, OSC = "model_templates.neural_mass_models.", "model_templates.oscillators."
-ZOO = [  # every circuit of the reference's model_templates that the reference itself can build (3 have template errors),
-         # except the complex-valued ones (theta.kmo_theta, kuramoto.kmo_mf*: UnsupportedModelError by design)
+ZOO = [  # every circuit of the reference's model_templates that the reference itself can build (3 have template errors);
+         # theta.kmo_theta / kuramoto.kmo_mf* are built real-valued here (float_precision='float64': i = 0, conjugate = identity)
     (NM + "ik.ik_eta", "p/ik_eta_op/r", 30.0, 1e-2), (NM + "ik.ik_nodim", "p/ik_nodim_op/r", 1.0, 1e-3),
     (NM + "ik.ik_theta", "p/ik_theta_op/r", 30.0, 1e-2), (NM + "jansenrit.JRC2", "jrc/jrc_op/V_e", 0.2, 1e-4),
     (NM + "qif.qif_conduct", "p/qif_conduct_op/r", 1.0, 1e-3), (NM + "qif.qif_sd", "p/qif_op/r", 1.0, 1e-3),
     (NM + "qif.qif_tsodyks", "p/qif_op/v", 1.0, 1e-3), (NM + "wilsoncowan.WC", "e/rate_op/r", 20.0, 1e-2),
     (NM + "wilsoncowan.WC_stp", "e/rate_op/r", 20.0, 1e-2), (OSC + "kuramoto.kmo", "p/phase_op/theta", 2.0, 1e-3),
     (OSC + "kuramoto.kmo_2coupled", "p1/phase_op/theta", 2.0, 1e-3), (OSC + "stuartlandau.sl", "p/sl_op/x", 5.0, 1e-3),
-    (OSC + "vanderpol.vdp", "p/vdp_op/x", 5.0, 1e-3),
+    (OSC + "vanderpol.vdp", "p/vdp_op/x", 5.0, 1e-3), (NM + "theta.kmo_theta", "p/theta_op/z", 2.0, 1e-3),
+    (OSC + "kuramoto.kmo_mf", "p/kmo_op/z", 2.0, 1e-3), (OSC + "kuramoto.kmo_mf_2coupled", "p1/kmo_op/z", 2.0, 1e-3),
 ]
 
 
