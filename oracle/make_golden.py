@@ -315,6 +315,10 @@ ADAPTIVE_CASES = {
     # extrinsic input with an adaptive solver: the frontend emits interp(t, time, u_input) (circuit.py:1692-1709)
     "qif_input_rk45": dict(build=_yaml(NM + "qif.qif"), T=2.0, dt=1e-3, dts=1e-2, out="p/qif_op/r",
                            inputs=lambda: {"p/qif_op/I_ext": _sin_input(2000) * 3.0}, kw=dict(rtol=1e-7, atol=1e-9)),
+    # SciPy's RK23 (the reference's own solver test uses it, tests/test_backend_simulations.py:370)
+    "jrc_rk23":     dict(build=_yaml(NM + "jansenrit.JRC"), T=0.3, dt=1e-4, dts=1e-3, out="pc/rpo_e_in/v",
+                         kw=dict(method="RK23", rtol=1e-6, atol=1e-9)),
+    "qif_sfa_rk23": dict(build=_yaml(NM + "qif.qif_sfa"), T=2.0, dt=1e-3, dts=5e-3, out="p/qif_sfa_op/r", kw=dict(method="RK23")),
     # networks too large for one thread: adaptive integration in the persistent network kernel (grid-wide error norm)
     "wc_n128_rk45": dict(build=_wc_pop(128), T=60.0, dt=1e-3, dts=0.5, out="e/rate_op/r", kw=dict(rtol=1e-7, atol=1e-10)),
     "kuramoto_n128_rk45": dict(build=_kuramoto(128), T=10.0, dt=1e-3, dts=0.05, out="e/phase_op/theta",
@@ -351,7 +355,7 @@ def make_adaptive_case(name: str, spec: dict, cap: Capture) -> str:
         clear(circuit)
     except Exception:
         pass
-    run_meta = {"T": T, "dt": dt, "dts": dts, "solver": "scipy", "method": "RK45", "precision": "float64",
+    run_meta = {"T": T, "dt": dt, "dts": dts, "solver": "scipy", "method": kw.get("method", "RK45"), "precision": "float64",
                 "rtol": kw.get("rtol", 1e-3), "atol": kw.get("atol", 1e-6), "reference_solvers": ["scipy"],
                 "reference_version": "1.2.3", "scipy_version": __import__("scipy").__version__, "out": spec["out"]}
     path = os.path.join(GOLDEN, f"{name}.npz")

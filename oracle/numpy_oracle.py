@@ -172,17 +172,28 @@ RK45_P = np.array([[1, -8048581381 / 2820520608, 8663915743 / 2820520608, -12715
                    [0, 40617522 / 29380423, -110615467 / 29380423, 69997945 / 29380423]])
 
 
-def solve_rk45(func, args, T, dt, y0, t0, times, rtol=1e-3, atol=1e-6, max_step=np.inf, aliased=True):
+# SciPy's RK23 (Bogacki-Shampine 3(2), cubic Hermite dense output): same driver, other tableau
+RK23_C = np.array([0, 1 / 2, 3 / 4])
+RK23_A = np.array([[0, 0, 0], [1 / 2, 0, 0], [0, 3 / 4, 0]])
+RK23_B = np.array([2 / 9, 1 / 3, 4 / 9])
+RK23_E = np.array([5 / 72, -1 / 12, -1 / 9, 1 / 8])
+RK23_P = np.array([[1, -4 / 3, 5 / 9], [0, 1, -2 / 3], [0, 4 / 3, -8 / 9], [0, -1, 1]])
+TABLEAUS = {"RK45": (RK45_C, RK45_A, RK45_B, RK45_E, RK45_P, -1 / 5), "RK23": (RK23_C, RK23_A, RK23_B, RK23_E, RK23_P, -1 / 3)}
+
+
+def solve_rk45(func, args, T, dt, y0, t0, times, rtol=1e-3, atol=1e-6, max_step=np.inf, aliased=True, method="RK45"):
     """solve_ivp(method='RK45', first_step=dt, t_eval=times) around the reference rhs; returns state_rec[len(times), n].
     The state is integrated in float64 whatever the model precision (scipy/integrate/_ivp/base.py: check_arguments).
     ``aliased=True`` is the reference's behaviour (rhs returns its in-place buffer, see above); ``aliased=False`` is plain
     SciPy around a function that returns fresh arrays (a rejected attempt restarts from the true f(t, y))."""
+    C_, A_, B_, E_, P_, expo = TABLEAUS[method]
+    nst = B_.size
     y = np.asarray(y0).astype(float, copy=False)
     n = y.size
     t, t_bound = float(t0), float(T)
     f = np.asarray(func(t, y, *args), dtype=float)           # alias of the rhs buffer
     h_abs = float(dt)
-    K = np.empty((7, n))
+    K = np.empty((nst + 1, n))
     rec = np.empty((len(times), n))
     i_eval = 0
     while t != t_bound:
@@ -201,33 +212,33 @@ def solve_rk45(func, args, T, dt, y0, t0, times, rtol=1e-3, atol=1e-6, max_step=
             h = t_new - t
             h_abs = np.abs(h)
             K[0] = f
-            for s in range(1, 6):
-                dy = np.dot(K[:s].T, RK45_A[s, :s]) * h
-                K[s] = func(t + RK45_C[s] * h, y + dy, *args)
-            y_new = y + h * np.dot(K[:-1].T, RK45_B)
+            for s in range(1, nst):
+                dy = np.dot(K[:s].T, A_[s, :s]) * h
+                K[s] = func(t + C_[s] * h, y + dy, *args)
+            y_new = y + h * np.dot(K[:-1].T, B_)
             f_new = np.asarray(func(t + h, y_new, *args), dtype=float)
             K[-1] = f_new
             if aliased:
                 f = f_new
             scale = atol + np.maximum(np.abs(y), np.abs(y_new)) * rtol
-            err = np.dot(K.T, RK45_E) * h / scale
+            err = np.dot(K.T, E_) * h / scale
             error_norm = np.linalg.norm(err) / err.size ** 0.5
             if error_norm < 1:
-                factor = 10.0 if error_norm == 0 else min(10.0, 0.9 * error_norm ** -0.2)
+                factor = 10.0 if error_norm == 0 else min(10.0, 0.9 * error_norm ** expo)
                 if rejected:
                     factor = min(1, factor)
                 h_abs *= factor
                 f = f_new
                 break
-            h_abs *= max(0.2, 0.9 * error_norm ** -0.2)
+            h_abs *= max(0.2, 0.9 * error_norm ** expo)
             rejected = True
         t_old, y_old = t, y
         t, y = t_new, y_new
         i_new = int(np.searchsorted(times, t, side="right"))
         if i_new > i_eval:
-            Q = K.T.dot(RK45_P)
+            Q = K.T.dot(P_)
             x = (times[i_eval:i_new] - t_old) / h
-            p = np.cumprod(np.tile(x, (4, 1)), axis=0)
+            p = np.cumprod(np.tile(x, (P_.shape[1], 1)), axis=0)
             rec[i_eval:i_new] = (h * np.dot(Q, p) + y_old[:, None]).T
             i_eval = i_new
     return rec[:i_eval]

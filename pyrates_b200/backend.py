@@ -315,7 +315,8 @@ class CudaBackend:
             try:
                 if self.exec_model == "network":
                     raise UnsupportedModelError("model too large (network execution model requested)")
-                model = InstanceModel(prog, solver=solver, fmad=self.fmad, max_nodes=4000 if self.exec_model == "auto" else 20000)
+                model = InstanceModel(prog, solver=solver, fmad=self.fmad, max_nodes=4000 if self.exec_model == "auto" else 20000,
+                                      rk_method=kwargs.get("method"))
             except UnsupportedModelError as e:
                 if self.exec_model == "instance" or "too large" not in str(e):
                     raise

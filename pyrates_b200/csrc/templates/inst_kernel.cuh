@@ -55,11 +55,12 @@ __device__ __forceinline__ void prb_axpy(real (&o)[N], const real (&y)[N], const
 extern "C" __global__ void __launch_bounds__(PRB_BLOCK, PRB_MIN_BLOCKS)
 prb_integrate(const __grid_constant__ prb_kernel_args A)
 {
-    constexpr double C_[6] = PRB_RK45_C_INIT;            // Dormand-Prince tableau, emitted by pyrates_b200/rk45.py
-    constexpr double A_[6][5] = PRB_RK45_A_INIT;
-    constexpr double B_[6] = PRB_RK45_B_INIT;
-    constexpr double E_[7] = PRB_RK45_E_INIT;
-    constexpr double P_[7][4] = PRB_RK45_P_INIT;         // dense output: y(t_old + x h) = y_old + h * sum_c Q[:, c] x^(c+1), Q = K^T P
+    constexpr int NST = PRB_RK_NST, NP = PRB_RK_NP;      // stages (RK45: 6, RK23: 3) and dense-output polynomial terms (4 / 3)
+    constexpr double C_[NST] = PRB_RK_C_INIT;            // tableau emitted by pyrates_b200/rk45.py (SciPy's RK45 / RK23)
+    constexpr double A_[NST][NST - 1] = PRB_RK_A_INIT;
+    constexpr double B_[NST] = PRB_RK_B_INIT;
+    constexpr double E_[NST + 1] = PRB_RK_E_INIT;
+    constexpr double P_[NST + 1][NP] = PRB_RK_P_INIT;    // dense output: y(t_old + x h) = y_old + h * sum_c Q[:, c] x^(c+1), Q = K^T P
     const long long B = A.n_inst;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     PRB_STAGE_ETAB
@@ -74,12 +75,12 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
 
     real* __restrict__ Y = (real*)A.y;
     double y[PRB_NS], f[PRB_NS];
-    real yr[PRB_NS], kr[PRB_NS];
+    areal yr[PRB_NS], kr[PRB_NS];          // rhs input / output in the rhs arithmetic type (double for float32 models too,
+    real yo[PRB_NS];                       // see emit_inst.py), recorded samples in the storage type
     PRB_UNROLL_NS
-    for (int j = 0; j < PRB_NS; ++j) { yr[j] = Y[(long long)j * B + b]; y[j] = (double)yr[j]; }
-    prb_rhs((prb_time)t, yr, kr, T);                                   // self.f = fun(t0, y0)
-    PRB_UNROLL_NS
-    for (int j = 0; j < PRB_NS; ++j) f[j] = (double)kr[j];
+    for (int j = 0; j < PRB_NS; ++j) { y[j] = (double)Y[(long long)j * B + b]; f[j] = 0.0; }
+    bool need_f = true;                    // f must be (re)computed as f(t, y): at the start (self.f = fun(t0, y0)) and after
+                                           // a rejected attempt whose aliased f overflowed (see below); ONE inlined call site
 
     real* __restrict__ out = (real*)A.out;
     long long sample = A.sample0;
@@ -92,9 +93,17 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
         if (h_abs > max_step) h_abs = max_step;
         else if (h_abs < min_step) h_abs = min_step;
         bool rejected = false;
-        double K[7][PRB_NS], y_new[PRB_NS];
+        double K[NST + 1][PRB_NS], y_new[PRB_NS];
         double h = 0.0, t_new = t;
         for (;;) {
+            if (need_f) {
+                PRB_UNROLL_NS
+                for (int j = 0; j < PRB_NS; ++j) yr[j] = (areal)y[j];
+                prb_rhs((prb_time)t, yr, kr, T);
+                PRB_UNROLL_NS
+                for (int j = 0; j < PRB_NS; ++j) f[j] = (double)kr[j];
+                need_f = false;
+            }
             if (h_abs < min_step) { status = 1; break; }
             if (++attempts > max_attempts) { status = 2; break; }
             t_new = t + h_abs;
@@ -104,13 +113,13 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
             PRB_UNROLL_NS
             for (int j = 0; j < PRB_NS; ++j) K[0][j] = f[j];
 #pragma unroll
-            for (int s = 1; s < 6; ++s) {
+            for (int s = 1; s < NST; ++s) {
                 PRB_UNROLL_NS
                 for (int j = 0; j < PRB_NS; ++j) {
                     double d = 0.0;
 #pragma unroll
                     for (int q = 0; q < s; ++q) d += K[q][j] * A_[s][q];
-                    yr[j] = (real)(y[j] + d * h);
+                    yr[j] = (areal)(y[j] + d * h);
                 }
                 prb_rhs((prb_time)(t + C_[s] * h), yr, kr, T);
                 PRB_UNROLL_NS
@@ -120,46 +129,62 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
             for (int j = 0; j < PRB_NS; ++j) {
                 double d = 0.0;
 #pragma unroll
-                for (int q = 0; q < 6; ++q) d += K[q][j] * B_[q];
+                for (int q = 0; q < NST; ++q) d += K[q][j] * B_[q];
                 y_new[j] = y[j] + h * d;
-                yr[j] = (real)y_new[j];
+                yr[j] = (areal)y_new[j];
             }
             prb_rhs((prb_time)(t + h), yr, kr, T);
             double sq = 0.0;
             PRB_UNROLL_NS
             for (int j = 0; j < PRB_NS; ++j) {
                 f[j] = (double)kr[j];                                  // the aliased buffer: newest evaluation
-                K[6][j] = f[j];
+                K[NST][j] = f[j];
                 double e = 0.0;
 #pragma unroll
-                for (int q = 0; q < 7; ++q) e += K[q][j] * E_[q];
+                for (int q = 0; q <= NST; ++q) e += K[q][j] * E_[q];
                 const double scale = atol + fmax(fabs(y[j]), fabs(y_new[j])) * rtol;
                 const double r = e * h / scale;
                 sq += r * r;
             }
             const double error_norm = sqrt(sq) / sqrt((double)PRB_NS);
             if (error_norm < 1.0) {
-                double factor = (error_norm == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -0.2));
+                double factor = (error_norm == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, PRB_RK_EXPONENT));
                 if (rejected) factor = fmin(1.0, factor);
                 h_abs *= factor;
                 break;
             }
-            h_abs *= fmax(0.2, 0.9 * pow(error_norm, -0.2));
+            h_abs *= fmax(0.2, 0.9 * pow(error_norm, PRB_RK_EXPONENT));
             rejected = true;
+            // The aliased buffer now holds f(t + h_rej, y_rej).  If that attempt overflowed, the reference is stuck with a
+            // NaN K[0] for ever and solve_ivp dies with "step size too small" (seen with its own test_3_2 inputs, on
+            // either side of a rounding coin flip).  Whenever the reference survives this value is finite and used as is;
+            // otherwise recover with the true f(t, y) instead of reproducing the crash.
+            bool finite = true;
+            PRB_UNROLL_NS
+            for (int j = 0; j < PRB_NS; ++j) finite = finite && (fabs(f[j]) <= 1.7976931348623157e308);
+            need_f = !finite;
         }
         if (status != 0) break;
-        // samples inside (t_old, t_new]: dense output  y_old + h * Q . (x, x^2, x^3, x^4),  Q = K^T P
+        // samples inside (t_old, t_new]: dense output  y_old + h * Q . (x, x^2, .., x^NP),  Q = K^T P
         while (sample < n_samples && (double)(sample - A.sample0) * te_step <= t_new) {
             const double x = ((double)(sample - A.sample0) * te_step - t) / h;
-            const double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x;
+            double pw[NP];
+            pw[0] = x;
+#pragma unroll
+            for (int c = 1; c < NP; ++c) pw[c] = pw[c - 1] * x;          // numpy.cumprod
             PRB_UNROLL_NS
             for (int j = 0; j < PRB_NS; ++j) {
-                double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+                double acc = 0.0;
 #pragma unroll
-                for (int s = 0; s < 7; ++s) { q0 += K[s][j] * P_[s][0]; q1 += K[s][j] * P_[s][1]; q2 += K[s][j] * P_[s][2]; q3 += K[s][j] * P_[s][3]; }
-                yr[j] = (real)(h * (((q0 * p1 + q1 * p2) + q2 * p3) + q3 * p4) + y[j]);
+                for (int c = 0; c < NP; ++c) {
+                    double qc = 0.0;
+#pragma unroll
+                    for (int s = 0; s <= NST; ++s) qc += K[s][j] * P_[s][c];
+                    acc += qc * pw[c];                                   // numpy.dot(Q, p): left to right
+                }
+                yo[j] = (real)(h * acc + y[j]);
             }
-            prb_record(yr, out + sample * (long long)PRB_NOBS * B, b, B);
+            prb_record(yo, out + sample * (long long)PRB_NOBS * B, b, B);
             ++sample;
         }
         t = t_new;
@@ -265,9 +290,9 @@ prb_rhs_eval(const __grid_constant__ prb_kernel_args A)
     prb_thread_init(T, A, b);
     PRB_SET_ETAB
     const real* __restrict__ Y = (const real*)A.y;
-    real y[PRB_NS], k[PRB_NS];
+    areal y[PRB_NS], k[PRB_NS];
     PRB_UNROLL_NS
-    for (int j = 0; j < PRB_NS; ++j) y[j] = Y[(long long)j * B + b];
+    for (int j = 0; j < PRB_NS; ++j) y[j] = (areal)Y[(long long)j * B + b];
 #if PRB_SOLVER == PRB_SOLVER_RK45
     prb_rhs((prb_time)A.dt, y, k, T);            // float time of the evaluation travels in args.dt
 #else
@@ -275,5 +300,5 @@ prb_rhs_eval(const __grid_constant__ prb_kernel_args A)
 #endif
     real* __restrict__ out = (real*)A.out;
     PRB_UNROLL_NS
-    for (int j = 0; j < PRB_NS; ++j) out[(long long)j * B + b] = k[j];
+    for (int j = 0; j < PRB_NS; ++j) out[(long long)j * B + b] = (real)k[j];
 }

@@ -695,6 +695,12 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
             }
             h_abs *= fmax(0.2, 0.9 * pow(error_norm, -0.2));
             rejected = true;
+            if (!(error_norm <= 1.7976931348623157e308)) {
+                // the rejected attempt overflowed: its f(t + h, y_new), now aliased as K0, is not finite and would poison
+                // every later attempt (the reference dies here with "step size too small"); recover with the true f(t, y)
+                C.t = (prb_time)t;
+                prb_stage<6>(C, C.oY);
+            }
         }
         if (status != 0) break;
         // dense output at the sample times inside (t, t_new]; after the swap K6 sits at oK[0] and the old K0 at oK[6]

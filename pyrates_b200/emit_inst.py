@@ -10,7 +10,7 @@ from __future__ import annotations
 import math
 import os
 from dataclasses import dataclass
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -71,7 +71,8 @@ def _lit(v: float, f32: bool) -> str:
 
 
 def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time: bool = False,
-                  fast_math: bool = False, spec: bool = False) -> List[str]:
+                  fast_math: bool = False, spec: bool = False, round_dy_f32: bool = False,
+                  slot_consts: Optional[dict] = None) -> List[str]:
     """Straight-line statements computing dy[] (+ ring / slot stores) from y[], T."""
     g = rhs.graph
     ring_off = np.cumsum([0] + [r.rows * r.length for r in rhs.rings])
@@ -103,10 +104,10 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
         if op == "t":
             if not want_real and float_time:
                 raise UnsupportedModelError("the model indexes arrays with the time step; adaptive solvers pass a float time")
-            return "((real)t)" if want_real else "t"
+            return "((areal)t)" if want_real else "t"
         name = f"v{i}"
         if g.isint[i] and want_real:
-            return f"((real){name})"
+            return f"((areal){name})"
         return name
 
     def const_chain(i: int):
@@ -154,14 +155,16 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
             if f32:
                 f = float(np.float32(f))
             if base != i and math.isfinite(f) and f != 0.0:
-                lines.append(f"const real v{i} = {ref(base)} * {lit(f)};")
+                lines.append(f"const areal v{i} = {ref(base)} * {lit(f)};")
                 continue
         if g.isint[i]:
             x, y_ = (ref(a[0], False), ref(a[1], False) if len(a) > 1 else None)
             expr = {"add": f"{x} + {y_}", "sub": f"{x} - {y_}", "mul": f"{x} * {y_}", "neg": f"-{x}"}[op]
             lines.append(f"const long long v{i} = {expr};")
             continue
-        if op == "slot":
+        if op == "slot" and slot_consts and g.payload[i] in slot_consts:
+            expr = lit(slot_consts[g.payload[i]])
+        elif op == "slot":
             expr = f"T.slots[{g.payload[i]}LL * T.B + T.b]"
         elif op == "table":
             tab, tnode, col, ncols = g.payload[i]
@@ -209,9 +212,9 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
             expr = f"{_FUNC[op]}({ref(a[0])})"
         else:
             raise NotImplementedError(f"no CUDA lowering for op `{op}`")
-        lines.append(f"const real v{i} = {expr};")
+        lines.append(f"const areal v{i} = {expr};")
     for j, n in enumerate(rhs.dy):
-        lines.append(f"dy[{j}] = {ref(n)};")
+        lines.append(f"dy[{j}] = (areal)(float)({ref(n)});" if round_dy_f32 else f"dy[{j}] = {ref(n)};")
     for ring, row, col, node in rhs.ring_writes:
         spec = rhs.rings[ring]
         L = spec.length
@@ -229,7 +232,7 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
 
 def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: Sequence[int],
                      block: int = 128, const_div_to_mul: bool = False, min_blocks: int = 1,
-                     fast_math: bool = False) -> InstKernel:
+                     fast_math: bool = False, rk_method: str = "RK45") -> InstKernel:
     """Generate the full CUDA C source of the fused rhs+solver instance kernel."""
     if solver not in SOLVER_IDS:
         raise ValueError(f"unknown solver `{solver}`; supported: {sorted(SOLVER_IDS)}")
@@ -237,14 +240,42 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     ns = rhs.n_state
     nrings = len(rhs.rings)
     adaptive = solver in ADAPTIVE_SOLVERS
+    slot_consts: dict = {}
+    if adaptive and rhs.slots and not rhs.rings:
+        # mutable buffers that are fully rewritten before they are read in the same evaluation (the vectorised frontend
+        # routes inputs through `u[target_idx] = interp(...)`) carry no state between evaluations: plain temporaries
+        g_, seen, stack = rhs.graph, set(), list(rhs.dy)
+        while stack:
+            i = stack.pop()
+            if i not in seen:
+                seen.add(i)
+                stack.extend(g_.args[i])
+        written = {slot for slot, _ in rhs.slot_writes}
+        read_first = {g_.payload[i] for i in seen if g_.ops[i] == "slot"}        # elements read before any write
+        if not (read_first & written):
+            # elements that are read but never written are constants (their initial value); the rest are temporaries
+            import copy
+            slot_consts = {k: float(rhs.slots[k][2]) for k in read_first}
+            rhs = copy.copy(rhs)
+            rhs.slots, rhs.slot_writes = [], []
     step_tables = any(rhs.graph.ops[i] == "table" for i in rhs.live_nodes())
     if adaptive and (rhs.rings or step_tables or rhs.slots):
         raise UnsupportedModelError("adaptive integration (solver='scipy') needs a pure vector field: delay ring buffers, "
                                     "step-indexed input tables and mutable buffers are fixed-step constructs")
     pure = not (rhs.rings or rhs.slots or rhs.ring_writes or rhs.slot_writes)
     spec = bool(fast_math and not f32 and pure)
-    body = emit_rhs_body(rhs, f32, const_div_to_mul, float_time=adaptive, fast_math=fast_math, spec=spec)
-    exact_body = emit_rhs_body(rhs, f32, const_div_to_mul, float_time=adaptive) if spec else None
+    if adaptive and f32:
+        fast_math = False
+    # adaptive + float32 model: SciPy integrates the state in float64 and hands float64 `y` to the generated function, so the
+    # reference's arithmetic is float64 on float32-valued constants with the result rounded into the float32 `dy` buffer
+    # (base.py check_arguments, computegraph.py:1220-1228).  A pure-float32 rhs is too noisy for the error estimator (the
+    # reference's own test_3_2_qif_theta then fails with "step size too small"); reproduce the reference instead.
+    arith64 = adaptive and f32
+    body_f32 = f32 and not arith64
+    body = emit_rhs_body(rhs, body_f32, const_div_to_mul, float_time=adaptive, fast_math=fast_math, spec=spec,
+                         round_dy_f32=arith64, slot_consts=slot_consts)
+    exact_body = emit_rhs_body(rhs, body_f32, const_div_to_mul, float_time=adaptive, round_dy_f32=arith64,
+                               slot_consts=slot_consts) if spec else None
     spec = spec and any("prb_spec_" in l for l in body)
     use_etab = any("prb_fast_exp(" in l or "prb_spec_exp(" in l for l in body)
     np_ = len(rhs.params)
@@ -252,6 +283,7 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     src.append("// Generated by pyrates_b200.emit_inst — do not edit.  Instance execution model (1 thread = 1 instance).")
     src.append(read_template("prb_kernel_abi.cuh"))
     src.append(f"typedef {'float' if f32 else 'double'} real;")
+    src.append(f"typedef {'double' if (adaptive and f32) else 'real'} areal;        // arithmetic type of the generated rhs")
     src.append(f"typedef {'double' if adaptive else 'long long'} prb_time;     // adaptive solvers hand the rhs a float time")
     src.append(f"#define PRB_NS {ns}")
     src.append(f"#define PRB_NP {np_}")
@@ -261,8 +293,8 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     src.append(f"#define PRB_BLOCK {block}")
     src.append(f"#define PRB_MIN_BLOCKS {int(min_blocks)}")
     if adaptive:
-        from .rk45 import cuda_tables
-        src.append(cuda_tables())
+        from .rk45 import cuda_method_tables
+        src.append(cuda_method_tables(rk_method))
     if ns > 64:
         src.append("#define PRB_UNROLL_NS")        # big states: keep loops rolled (state spills to local memory)
     src.append("""
@@ -339,21 +371,21 @@ __device__ __forceinline__ double prb_fast_div(const double a, const double b) {
     r = fma(r, e, r);
     return a * r;
 }
-__device__ __forceinline__ real prb_max(real a, real b) { return (a != a || b != b) ? a + b : (a > b ? a : b); }
-__device__ __forceinline__ real prb_min(real a, real b) { return (a != a || b != b) ? a + b : (a < b ? a : b); }
-__device__ __forceinline__ real prb_sign(real a) { return (real)((a > (real)0) - (a < (real)0)); }
+__device__ __forceinline__ areal prb_max(areal a, areal b) { return (a != a || b != b) ? a + b : (a > b ? a : b); }
+__device__ __forceinline__ areal prb_min(areal a, areal b) { return (a != a || b != b) ? a + b : (a < b ? a : b); }
+__device__ __forceinline__ areal prb_sign(areal a) { return (areal)((a > (areal)0) - (a < (areal)0)); }
 // numpy.interp(x, xp, fp) for one x (timed inputs of the adaptive solvers): clamp outside [xp[0], xp[n-1]], else
 // slope * (x - xp[j]) + fp[j] with xp[j] <= x < xp[j+1] (the expression NumPy's C loop evaluates)
-__device__ __forceinline__ real prb_interp(const real* __restrict__ xp, const real* __restrict__ fp, const int n, const real x) {
-    if (!(x > __ldg(xp))) return __ldg(fp);
-    if (x >= __ldg(xp + n - 1)) return __ldg(fp + n - 1);
+__device__ __forceinline__ areal prb_interp(const real* __restrict__ xp, const real* __restrict__ fp, const int n, const areal x) {
+    if (!(x > (areal)__ldg(xp))) return (areal)__ldg(fp);
+    if (x >= (areal)__ldg(xp + n - 1)) return (areal)__ldg(fp + n - 1);
     int lo = 0, hi = n - 1;
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (__ldg(xp + mid) <= x) lo = mid; else hi = mid;
+        if ((areal)__ldg(xp + mid) <= x) lo = mid; else hi = mid;
     }
-    const real x0 = __ldg(xp + lo), f0 = __ldg(fp + lo);
-    const real slope = (__ldg(fp + lo + 1) - f0) / (__ldg(xp + lo + 1) - x0);
+    const areal x0 = (areal)__ldg(xp + lo), f0 = (areal)__ldg(fp + lo);
+    const areal slope = ((areal)__ldg(fp + lo + 1) - f0) / ((areal)__ldg(xp + lo + 1) - x0);
     return slope * (x - x0) + f0;
 }
 // physical ring position of logical column `col` (may be negative by the pending roll) at head `head`
@@ -381,16 +413,16 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
         vals = body.pop(0)[len("// PRB_LIT = {"):-1]
         src.append(f"__device__ __constant__ double PRB_LIT[{vals.count(',') + 1}] = {{{vals}}};")
     if spec:
-        src.append("__device__ __noinline__ void prb_rhs_exact(const prb_time t, const real (&y)[PRB_NS], real (&dy)[PRB_NS], PrbThread& T) {")
+        src.append("__device__ __noinline__ void prb_rhs_exact(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NS], PrbThread& T) {")
         src.extend("    " + l for l in exact_body)
         src.append("}")
-    src.append("__device__ __forceinline__ void prb_rhs(const prb_time t, const real (&y)[PRB_NS], real (&dy)[PRB_NS], PrbThread& T) {")
+    src.append("__device__ __forceinline__ void prb_rhs(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NS], PrbThread& T) {")
     if spec:
         src.append("    bool bad = false;")
     src.extend("    " + l for l in body)
     if spec:
         src.append("    if (bad) {                  // an exp / division argument left the fast range: redo this evaluation exactly")
-        src.append("        real yl[PRB_NS], dl[PRB_NS];")
+        src.append("        areal yl[PRB_NS], dl[PRB_NS];")
         src.append("        PrbThread Tl = T;")
         src.append("        _Pragma(\"unroll\") for (int j = 0; j < PRB_NS; ++j) yl[j] = y[j];")
         src.append("        prb_rhs_exact(t, yl, dl, Tl);")
@@ -409,6 +441,8 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
     ring_init = np.concatenate([r.init.reshape(-1) for r in rhs.rings]) if rhs.rings else np.zeros(0)
     tabs = np.concatenate([np.asarray(t.value, dtype=np.float64).reshape(-1) for t in rhs.tables]) if rhs.tables else np.zeros(0)
     evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4, "scipy": 6, "rk45": 6}[solver]
+    if adaptive and rk_method == "RK23":
+        evals = 3
     return InstKernel("\n".join(src) + "\n", ns, np_, len(rhs.slots), len(observers), int(ring_init.size), ring_init,
                       [r.rolls_per_eval for r in rhs.rings], [r.length for r in rhs.rings], tabs,
                       np.array([s[2] for s in rhs.slots], dtype=np.float64),

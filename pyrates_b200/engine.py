@@ -36,13 +36,18 @@ class InstanceModel:
 
     def __init__(self, prog: Program, *, solver: str = "euler", sweep: Sequence[Tuple[str, int]] = (),
                  observers: Optional[Sequence[int]] = None, block: int = 128, fmad: bool = True,
-                 const_div_to_mul: bool = False, max_nodes: int = 6000, min_blocks: int = 1, fast_math: bool = False):
+                 const_div_to_mul: bool = False, max_nodes: int = 6000, min_blocks: int = 1, fast_math: bool = False,
+                 rk_method: Optional[str] = None):
         if solver not in FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS:
             raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
                                       f"Supported solvers: {list(FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS)}.")
         self.prog = prog
         self.solver = solver
         self.adaptive = solver in ADAPTIVE_SOLVERS
+        self.rk_method = (rk_method or "RK45") if self.adaptive else None     # solve_ivp's `method` (compile-time tableau)
+        if self.adaptive and self.rk_method not in ("RK45", "RK23"):
+            raise rt.CudaBackendError(f"solver='scipy' on the CUDA backend implements method='RK45' (SciPy's default) and "
+                                      f"'RK23'; got method={self.rk_method!r}")
         self.precision = prog.float_precision
         self.real = prog.real_dtype
         self.rhs: ScalarRhs = scalarize(prog, sweep, max_nodes=max_nodes)
@@ -50,7 +55,7 @@ class InstanceModel:
         self.kernel: InstKernel = emit_inst_kernel(self.rhs, solver=solver, precision=self.precision,
                                                    observers=self.observers, block=block,
                                                    const_div_to_mul=const_div_to_mul, min_blocks=min_blocks,
-                                                   fast_math=fast_math)
+                                                   fast_math=fast_math, rk_method=self.rk_method or "RK45")
         self.fmad = fmad
         self._module: Optional[rt.Module] = None
         t0 = np.asarray(prog.arg_by_kind("t").value)
@@ -183,13 +188,13 @@ class InstanceSession:
         return new_samples
 
     def launch_adaptive(self, T: float, dt: float, dts: Optional[float] = None, *, rtol: float = 1e-3, atol: float = 1e-6,
-                        max_step: float = np.inf, method: str = "RK45", max_attempts: int = 50_000_000, **unknown):
+                        max_step: float = np.inf, method: Optional[str] = None, max_attempts: int = 50_000_000, **unknown):
         """The whole adaptive integration of every instance in one launch: solve_ivp(method='RK45', first_step=dt,
         t_eval=linspace(0, T, round(T/dts), endpoint=False)) per instance, each thread with its own step sequence.
         Raises when an instance fails (step size underflow), like a failed solve_ivp would break the reference's run."""
-        if method not in (None, "RK45"):
-            raise rt.CudaBackendError(f"solver='scipy' on the CUDA backend implements method='RK45' (SciPy's default); "
-                                      f"got method={method!r}")
+        if method is not None and method != self.m.rk_method:
+            raise rt.CudaBackendError(f"this model was compiled for method={self.m.rk_method!r}; build it with "
+                                      f"rk_method={method!r} (the tableau is a compile-time constant of the kernel)")
         if unknown:
             raise TypeError(f"unsupported solve_ivp options on the CUDA backend: {sorted(unknown)}")
         if np.ndim(atol) or np.ndim(rtol):

@@ -22,6 +22,19 @@ P = [[1, -8048581381 / 2820520608, 8663915743 / 2820520608, -12715105075 / 11282
      [0, 40617522 / 29380423, -110615467 / 29380423, 69997945 / 29380423]]
 
 
+# Bogacki-Shampine 3(2) pair with its cubic Hermite interpolant — SciPy's ``RK23`` (the reference's own solver test uses
+# ``method='RK23'``, tests/test_backend_simulations.py:370-373)
+RK23 = dict(
+    C=[0, 1 / 2, 3 / 4],
+    A=[[0, 0], [1 / 2, 0], [0, 3 / 4]],
+    B=[2 / 9, 1 / 3, 4 / 9],
+    E=[5 / 72, -1 / 12, -1 / 9, 1 / 8],
+    P=[[1, -4 / 3, 5 / 9], [0, 1, -2 / 3], [0, 4 / 3, -8 / 9], [0, -1, 1]],
+    error_exponent=-1 / 3)
+RK45 = dict(C=C, A=A, B=B, E=E, P=P, error_exponent=-1 / 5)
+METHODS = {"RK45": RK45, "RK23": RK23}
+
+
 def _lit(v) -> str:
     r = repr(float(v))
     return r if ("." in r or "e" in r) else r + ".0"
@@ -29,6 +42,21 @@ def _lit(v) -> str:
 
 def _rows(m) -> str:
     return "{" + ", ".join("{" + ", ".join(_lit(v) for v in row) + "}" for row in m) + "}"
+
+
+def cuda_method_tables(method: str = "RK45") -> str:
+    """Tableau of one explicit Runge-Kutta pair for the instance kernel: stage count, interpolant degree, controller
+    exponent and the coefficient initialisers (exact double literals, repr round-trips)."""
+    m = METHODS[method]
+    nst, npoly = len(m["B"]), len(m["P"][0])
+    a_rows = [list(row) + [0] * (nst - 1 - len(row)) for row in m["A"]]
+    return "\n".join([
+        f"#define PRB_RK_NST {nst}", f"#define PRB_RK_NP {npoly}", f"#define PRB_RK_EXPONENT {_lit(m['error_exponent'])}",
+        "#define PRB_RK_C_INIT {" + ", ".join(_lit(v) for v in m["C"]) + "}",
+        "#define PRB_RK_A_INIT " + _rows(a_rows),
+        "#define PRB_RK_B_INIT {" + ", ".join(_lit(v) for v in m["B"]) + "}",
+        "#define PRB_RK_E_INIT {" + ", ".join(_lit(v) for v in m["E"]) + "}",
+        "#define PRB_RK_P_INIT " + _rows(m["P"])])
 
 
 def cuda_tables() -> str:

@@ -64,7 +64,7 @@ class BatchedSweep:
             min_blocks = 8 if prog.float_precision == "float32" else 4
         self.model = InstanceModel(prog, solver=solver, sweep=sweep, observers=observers, block=block,
                                    const_div_to_mul=const_div_to_mul, min_blocks=min_blocks if block == 128 else 1,
-                                   fast_math=fast_math)
+                                   fast_math=fast_math, rk_method=self.solver_kwargs.get("method"))
         order = [(p.arg, p.elem) for p in self.model.rhs.params]
         self._perm = [order.index((a, int(e))) for a, e in sweep]      # user row k -> kernel param row
         self.sweep = list(sweep)

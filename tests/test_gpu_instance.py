@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 SKIP = {"kuramoto_n128", "qsfa_both_n96", "wc_n128", "wc_n128_f32", "jrc_grid_b1024", "wc_n300_f32",
         "qsfa_both_n96_f32", "kuramoto_n128_f32", "wc_n128_rk45", "kuramoto_n128_rk45"}                                             # network-mode fixtures
-ADAPTIVE = [n for n in golden_names() if "_rk45" in n and n not in SKIP]
+ADAPTIVE = [n for n in golden_names() if ("_rk45" in n or "_rk23" in n) and n not in SKIP]
 NAMES = [n for n in golden_names() if n not in SKIP and n not in ADAPTIVE]
 SOLVERS = ["euler", "heun", "heun_true", "rk4"]
 
@@ -102,8 +102,8 @@ def test_adaptive_rk45_matches_reference_scipy(gpu, name):
     fx = orc.load_fixture(golden_path(name))
     r = fx["run"]
     before = rt.launch_count()
-    out, _ = InstanceModel(Program.load(golden_path(name)), solver="scipy").run(r["T"], r["dt"], r["dts"], rtol=r["rtol"],
-                                                                                atol=r["atol"])
+    out, _ = InstanceModel(Program.load(golden_path(name)), solver="scipy", rk_method=r["method"]).run(
+        r["T"], r["dt"], r["dts"], rtol=r["rtol"], atol=r["atol"], method=r["method"])
     assert rt.launch_count() == before + 1
     ref = fx["extra"]["rec_scipy"]
     assert out[:, :, 0].shape == ref.shape

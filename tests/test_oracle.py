@@ -7,7 +7,7 @@ from conftest import golden_names, golden_path
 from oracle import numpy_oracle as orc
 
 
-ADAPTIVE = [n for n in golden_names() if n.endswith("_rk45") or "_rk45_" in n]
+ADAPTIVE = [n for n in golden_names() if "_rk45" in n or "_rk23" in n]
 
 
 @pytest.mark.parametrize("name", ADAPTIVE)
@@ -19,7 +19,7 @@ def test_oracle_rk45_reproduces_reference_plus_scipy_bit_exact(name):
     f = orc.build_vector_field(fx["source"])
     args = [np.array(a, copy=True) for a in fx["args"]]
     args[0] = args[0][()]
-    rec, times = orc.run_adaptive(f, args, r["T"], r["dt"], r["dts"], rtol=r["rtol"], atol=r["atol"])
+    rec, times = orc.run_adaptive(f, args, r["T"], r["dt"], r["dts"], rtol=r["rtol"], atol=r["atol"], method=r["method"])
     ref = fx["extra"]["rec_scipy"]
     assert rec.shape == ref.shape and np.array_equal(rec, ref)
 
@@ -27,7 +27,8 @@ def test_oracle_rk45_reproduces_reference_plus_scipy_bit_exact(name):
 def test_oracle_rk45_coefficients_are_scipys():
     rk = pytest.importorskip("scipy.integrate._ivp.rk")
     for mine, theirs in ((orc.RK45_A, rk.RK45.A), (orc.RK45_B, rk.RK45.B), (orc.RK45_C, rk.RK45.C), (orc.RK45_E, rk.RK45.E),
-                         (orc.RK45_P, rk.RK45.P)):
+                         (orc.RK45_P, rk.RK45.P), (orc.RK23_A, rk.RK23.A), (orc.RK23_B, rk.RK23.B), (orc.RK23_C, rk.RK23.C),
+                         (orc.RK23_E, rk.RK23.E), (orc.RK23_P, rk.RK23.P)):
         assert np.array_equal(mine, theirs)
 
 
