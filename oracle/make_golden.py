@@ -231,6 +231,13 @@ CASES = {
     "wc_n300_f32": dict(build=_wc_pop(300), T=0.05, dt=1e-3, dts=2e-3, out="e/rate_op/r", precision="float32"),
     "qsfa_both_n96_f32": dict(build=_qif_sfa_pop(96, "both"), T=0.05, dt=1e-3, out="p1/qif_sfa_op/r", precision="float32"),
     "kuramoto_n128_f32": dict(build=_kuramoto(128), T=0.05, dt=1e-3, out="e/phase_op/theta", precision="float32"),
+    # complex precisions (Ott-Antonsen mean fields: complex state z, conjugate, i*omega)
+    "kmo_mf_c128": dict(build=_yaml("model_templates.oscillators.kuramoto.kmo_mf"), T=2.0, dt=1e-3, dts=1e-2, out="p/kmo_op/z",
+                        precision="complex128"),
+    "kmo_mf2_c64": dict(build=_yaml("model_templates.oscillators.kuramoto.kmo_mf_2coupled"), T=2.0, dt=1e-3, dts=1e-2,
+                        out="p1/kmo_op/z", precision="complex64"),
+    "kmo_theta_c128": dict(build=_yaml(NM + "theta.kmo_theta"), T=2.0, dt=1e-3, dts=1e-2, out="p/theta_op/z",
+                           precision="complex128"),
     "qsfa_cascade_n8":   dict(build=_qif_sfa_pop(8, "cascade"), T=0.1, dt=1e-3, out="p/qif_sfa_op/r"),
     "qsfa_ring_n8":      dict(build=_qif_sfa_pop(8, "ring"), T=0.1, dt=1e-3, out="p/qif_sfa_op/r"),
     "qsfa_both_n8":      dict(build=_qif_sfa_pop(8, "both"), T=0.1, dt=1e-3, out="p1/qif_sfa_op/r"),

@@ -135,9 +135,9 @@ class CudaBackend:
         self.idx_dummy_var = "temporary_pyrates_var_index"
         self._float_precision = kwargs.pop('float_precision', 'float32')      # reference default (:300)
         self._int_precision = kwargs.pop('int_precision', 'int32')
-        if self._float_precision not in ('float32', 'float64'):
-            raise _backend_error(f"CudaBackend supports float_precision 'float32' or 'float64', got "
-                                 f"`{self._float_precision}`")
+        if self._float_precision not in ('float32', 'float64', 'complex64', 'complex128'):
+            raise _backend_error(f"CudaBackend supports float_precision 'float32', 'float64', 'complex64' or 'complex128', "
+                                 f"got `{self._float_precision}`")
         self._idx_left, self._idx_right = '[', ']'
         self._start_idx = 0
         kwargs.pop('idx_left', None), kwargs.pop('idx_right', None), kwargs.pop('start_idx', None)
@@ -178,9 +178,8 @@ class CudaBackend:
         """base_backend.py:326-340: value in backend precision; (1,) constants squeezed to 0-d."""
         if v.is_float or v.is_complex:
             dtype = self._float_precision
-            if 'complex' in str(dtype):
-                raise UnsupportedModelError("complex-valued models (float_precision='complex64/128') are not supported by the "
-                                            "CUDA backend")
+            if 'complex' in str(dtype) and v.name in ['t', 'time']:
+                dtype = f'float{str(dtype)[7:]}'          # base_backend.py:329-330: time stays real in complex builds
         else:
             dtype = self._int_precision
         with warnings.catch_warnings():
@@ -333,9 +332,15 @@ class CudaBackend:
             self.last_model = model
             out, y_final = model.run(T, dt, dts)
         rec = np.ascontiguousarray(out[:, :, 0])
+        yf = y_final[:, 0]
+        if prog.is_complex:
+            # complex state k lives in real state variables (2k, 2k+1): hand complex arrays back like the reference
+            cdt = np.complex64 if prog.float_precision == "complex64" else np.complex128
+            rec = (rec[:, 0::2] + 1j * rec[:, 1::2]).astype(cdt)
+            yf = (yf[0::2] + 1j * yf[1::2]).astype(cdt)
         # mirror the reference's in-place semantics: y0 (func_args[1]) ends up holding the final state
         try:
-            np.asarray(func_args[1])[...] = y_final[:, 0]
+            np.asarray(func_args[1])[...] = yf
         except (ValueError, TypeError):
             pass
         return rec, times
@@ -356,4 +361,6 @@ def build_model(prog: Program, *, solver: str, exec_model: str = "auto", **kw):
     from .netengine import NetworkModel
     kw.pop("const_div_to_mul", None)
     kw.pop("fast_math", None)
+    if prog.is_complex:
+        raise UnsupportedModelError("complex-valued models are supported by the instance execution model only")
     return NetworkModel(prog, solver=solver, **kw)

@@ -48,7 +48,7 @@ class InstanceModel:
         if self.adaptive and self.rk_method not in ("RK45", "RK23"):
             raise rt.CudaBackendError(f"solver='scipy' on the CUDA backend implements method='RK45' (SciPy's default) and "
                                       f"'RK23'; got method={self.rk_method!r}")
-        self.precision = prog.float_precision
+        self.precision = "float32" if prog.real_dtype == np.float32 else "float64"      # complex64/128 -> real pairs
         self.real = prog.real_dtype
         self.rhs: ScalarRhs = scalarize(prog, sweep, max_nodes=max_nodes)
         self.observers = list(range(prog.n_state)) if observers is None else [int(o) for o in observers]

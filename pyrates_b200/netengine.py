@@ -17,6 +17,7 @@ from .emit_net import NetKernel, emit_net_kernel, tc_config
 from .engine import ADAPTIVE_SOLVERS, FIXED_STEP_SOLVERS, n_steps_for
 from .netcompile import NetIR, netcompile
 from .program import Program
+from .scalarize import UnsupportedModelError
 
 __all__ = ["NetworkModel", "NetworkSession", "build_check", "smoke_check"]
 
@@ -36,6 +37,8 @@ class NetworkModel:
         self.prog = prog
         self.solver = solver
         self.adaptive = solver in ADAPTIVE_SOLVERS
+        if prog.is_complex:
+            raise UnsupportedModelError("complex-valued models are supported by the instance execution model only")
         self.precision = prog.float_precision
         self.real = prog.real_dtype
         self.n_batch = int(n_batch)

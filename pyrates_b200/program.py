@@ -68,8 +68,13 @@ class Program:
 
     # ------------------------------------------------------------------ basic views
     @property
+    def is_complex(self) -> bool:
+        return "complex" in str(self.float_precision)
+
+    @property
     def n_state(self) -> int:
-        return int(self.arg("y").value.size)
+        """Number of REAL state variables (a complex state occupies two: re, im)."""
+        return int(self.arg_by_kind("y").value.size) * (2 if self.is_complex else 1)
 
     def arg(self, name: str) -> Arg:
         for a in self.args:
@@ -85,11 +90,14 @@ class Program:
 
     @property
     def y0(self) -> np.ndarray:
-        return np.asarray(self.arg_by_kind("y").value).reshape(-1)
+        y = np.asarray(self.arg_by_kind("y").value).reshape(-1)
+        if self.is_complex:
+            return np.stack([y.real, y.imag], axis=1).reshape(-1).astype(self.real_dtype)
+        return y
 
     @property
     def real_dtype(self):
-        return np.float32 if self.float_precision == "float32" else np.float64
+        return np.float32 if self.float_precision in ("float32", "complex64") else np.float64
 
     # ------------------------------------------------------------------ construction
     @classmethod

@@ -203,6 +203,9 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
 
     base, targets = _probe_positions(template, keys, param_map, build)
     prog: Program = base["program"]
+    if prog.is_complex:
+        raise NotImplementedError("grid_search on the CUDA backend batches real-valued builds; complex float precisions are "
+                                  "supported by CircuitTemplate.run only")
     y_name = prog.arg_by_kind("y").name
     sweep, rows, y0_rows = [], [], []
     for k in keys:

@@ -238,6 +238,8 @@ class Sym:
     def _bin(self, op, a, b):
         if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
             return NotImplemented            # let the ndarray operand broadcast element-wise
+        if isinstance(a, (CSym, complex)) or isinstance(b, (CSym, complex)):
+            return CSym.binop(self.g, op, a, b)
         return self.g.binop(op, a, b)
 
     def __add__(self, o): return self._bin("add", self, o)
@@ -256,6 +258,79 @@ class Sym:
     def __repr__(self):
         g = self.g
         return f"Sym#{self.id}<{g.ops[self.id]}>"
+
+
+class CSym:
+    """A complex value as a pair of real DAG nodes (float_precision='complex64' / 'complex128' builds: every float
+    argument arrives complex, pyrates/backend/base/base_backend.py:326-331).  Arithmetic is lowered to real operations
+    — (a+bi)(c+di) = (ac-bd) + (ad+bc)i, division through the conjugate — so constants with a zero imaginary part fold
+    away in the graph and the kernels stay real; the complex state occupies two consecutive real state variables."""
+    __slots__ = ("g", "re", "im")
+
+    def __init__(self, g: Graph, re, im):
+        self.g, self.re, self.im = g, g.lift(re), g.lift(im)
+
+    @staticmethod
+    def of(g: Graph, x) -> "CSym":
+        if isinstance(x, CSym):
+            return x
+        if isinstance(x, complex):
+            return CSym(g, g.const(float(x.real), weak=True), g.const(float(x.imag), weak=True))
+        if isinstance(x, (bool, np.bool_)):
+            raise TypeError("bool in complex arithmetic")
+        return CSym(g, x, g.const(0.0, weak=True))
+
+    @staticmethod
+    def binop(g: Graph, op: str, a, b):
+        a, b = CSym.of(g, a), CSym.of(g, b)
+        if op == "add":
+            return CSym(g, a.re + b.re, a.im + b.im)
+        if op == "sub":
+            return CSym(g, a.re - b.re, a.im - b.im)
+        if op == "mul":
+            return CSym(g, a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re)
+        if op == "div":
+            den = b.re * b.re + b.im * b.im
+            return CSym(g, (a.re * b.re + a.im * b.im) / den, (a.im * b.re - a.re * b.im) / den)
+        if op == "pow":
+            if g.is_const(b.im.id) and float(g.const_value(b.im.id)) == 0.0 and g.is_const(b.re.id):
+                e = float(g.const_value(b.re.id))
+                if e == int(e) and 0 <= int(e) <= 8:
+                    out = CSym.of(g, 1.0)
+                    for _ in range(int(e)):
+                        out = CSym.binop(g, "mul", out, a)
+                    return out
+            raise UnsupportedModelError("complex powers other than small non-negative integers")
+        raise UnsupportedModelError(f"`{op}` on complex values")
+
+    def _bin(self, op, a, b):
+        if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+            return NotImplemented
+        return CSym.binop(self.g, op, a, b)
+
+    def __add__(self, o): return self._bin("add", self, o)
+    def __radd__(self, o): return self._bin("add", o, self)
+    def __sub__(self, o): return self._bin("sub", self, o)
+    def __rsub__(self, o): return self._bin("sub", o, self)
+    def __mul__(self, o): return self._bin("mul", self, o)
+    def __rmul__(self, o): return self._bin("mul", o, self)
+    def __truediv__(self, o): return self._bin("div", self, o)
+    def __rtruediv__(self, o): return self._bin("div", o, self)
+    def __pow__(self, o): return self._bin("pow", self, o)
+    def __neg__(self): return CSym(self.g, -self.re, -self.im)
+    def __pos__(self): return self
+
+    def conj(self): return CSym(self.g, self.re, -self.im)
+
+    def abs(self):
+        return self.g.unop("sqrt", self.re * self.re + self.im * self.im)
+
+    def exp(self):
+        e = self.g.unop("exp", self.re)
+        return CSym(self.g, e * self.g.unop("cos", self.im), e * self.g.unop("sin", self.im))
+
+    def __repr__(self):
+        return f"CSym({self.re!r}, {self.im!r})"
 
 
 # ----------------------------------------------------------------------------- result container
@@ -334,6 +409,17 @@ class _Table:
         self.idx, self.spec = idx, spec
 
 
+def _real_table(name: str, v) -> np.ndarray:
+    """Input tables of complex builds arrive complex with a zero imaginary part (base_backend.py:326-331 casts every float
+    argument): the kernels read them as real tables."""
+    v = np.asarray(v)
+    if np.iscomplexobj(v):
+        if np.any(v.imag != 0):
+            raise UnsupportedModelError(f"input table `{name}` has a non-zero imaginary part")
+        v = np.ascontiguousarray(v.real)
+    return v
+
+
 def _obj(x) -> np.ndarray:
     a = np.empty((), dtype=object)
     a[()] = x
@@ -347,6 +433,7 @@ def _wrap(r):
 class _Interp:
     def __init__(self, prog: Program, sweep: Sequence[Tuple[str, int]], max_nodes: int):
         self.p = prog
+        self.complex = "complex" in str(prog.float_precision)
         self.g = Graph(prog.real_dtype)
         self.max_nodes = max_nodes
         self.env: Dict[str, object] = {}
@@ -369,6 +456,7 @@ class _Interp:
                  for s in prog.stmts]
         self.trees = trees
         self.interp_args = set()
+        self.slot_arrays_complex = set()
         t_indexed, rolled = self._prescan(trees)
 
         for a in prog.args:
@@ -378,7 +466,10 @@ class _Interp:
             elif a.kind == "y":
                 arr = np.empty(v.size, dtype=object)
                 for k in range(v.size):
-                    arr[k] = self.g.leaf("state", k)
+                    if self.complex:          # complex state k = real state variables (2k, 2k+1)
+                        arr[k] = CSym(self.g, self.g.leaf("state", 2 * k), self.g.leaf("state", 2 * k + 1))
+                    else:
+                        arr[k] = self.g.leaf("state", k)
                 self.env[a.name] = arr
             elif a.kind == "dy":
                 arr = np.empty(v.size, dtype=object)
@@ -391,7 +482,7 @@ class _Interp:
             elif a.name in t_indexed:
                 if a.kind != "const":
                     raise UnsupportedModelError(f"time-indexed buffer `{a.name}` must be constant")
-                self.tables.append(TableSpec(a.name, v.shape, v))
+                self.tables.append(TableSpec(a.name, v.shape, _real_table(a.name, v)))
                 self.env[a.name] = _Table(len(self.tables) - 1, self.tables[-1])
             elif a.name in rolled:
                 if v.ndim not in (1, 2):
@@ -405,7 +496,22 @@ class _Interp:
                     raise UnsupportedModelError(f"mutable integer buffer `{a.name}`")
                 self.env[a.name] = v.copy()           # concrete index array (never swept)
             elif np.iscomplexobj(v):
-                raise UnsupportedModelError("complex-valued models are not supported by the CUDA backend")
+                if any(n == a.name for n, _ in sweep):
+                    raise UnsupportedModelError(f"complex argument `{a.name}` cannot be swept")
+                if a.kind == "var":
+                    # mutable complex buffers are the vectorised frontend's input routing (`u[target_idx] = ...`, rewritten
+                    # in every evaluation before it is read): tracked symbolically, never stored back
+                    self.slot_arrays_complex.add(a.name)
+                arr = np.empty(v.shape, dtype=object)
+                flat = arr.reshape(-1) if v.ndim else None
+                vals = v.reshape(-1)
+                for k in range(vals.size):
+                    c = CSym(self.g, self.g.const(vals[k].real), self.g.const(vals[k].imag))
+                    if v.ndim:
+                        flat[k] = c
+                    else:
+                        arr[()] = c
+                self.env[a.name] = arr
             else:
                 arr = np.empty(v.shape, dtype=object)
                 flat = arr.reshape(-1) if v.ndim else None
@@ -516,7 +622,16 @@ class _Interp:
 
     def _map1(self, fname, v):
         g = self.g
-        f = np.frompyfunc(lambda s: g.unop(fname, s), 1, 1)
+
+        def one(x):
+            if isinstance(x, CSym):
+                if fname == "abs":
+                    return x.abs()
+                if fname == "exp":
+                    return x.exp()
+                raise UnsupportedModelError(f"`{fname}` of a complex value")
+            return g.unop(fname, x)
+        f = np.frompyfunc(one, 1, 1)
         r = f(self._arr(v))
         return r if isinstance(r, np.ndarray) else _obj(r)
 
@@ -555,8 +670,8 @@ class _Interp:
             if len(n.args) != 3 or not all(isinstance(a, ast.Name) for a in n.args[1:]):
                 raise UnsupportedModelError(f"unsupported interp call `{ast.unparse(n)}`")
             tv = self._arr(self.ev(n.args[0]))
-            xp = np.asarray(self.p.arg(n.args[1].id).value, dtype=np.float64)
-            fp = np.asarray(self.p.arg(n.args[2].id).value, dtype=np.float64)
+            xp = np.asarray(_real_table(n.args[1].id, self.p.arg(n.args[1].id).value), dtype=np.float64)
+            fp = np.asarray(_real_table(n.args[2].id, self.p.arg(n.args[2].id).value), dtype=np.float64)
             if tv.ndim != 0 or xp.ndim != 1 or fp.shape != xp.shape or xp.size < 2:
                 raise UnsupportedModelError("interp is supported for a scalar time over 1-d (time, value) tables")
             self.tables.append(TableSpec(n.args[1].id, xp.shape, xp))
@@ -565,13 +680,12 @@ class _Interp:
         args = [self.ev(a) for a in n.args]
         if fname in UNARY_FUNCS:
             return self._map1(fname, args[0])
-        if fname in ("conjugate", "real"):
-            return args[0]          # real-valued build (complex argument arrays are rejected up front): identity, as in NumPy
-        if fname == "imag":
-            a0 = self._arr(args[0])
-            out = np.empty(a0.shape, dtype=object)
-            out[...] = g.const(0.0)
-            return out if a0.ndim else _obj(g.const(0.0))
+        if fname in ("conjugate", "real", "imag"):
+            pick = {"conjugate": lambda x: x.conj() if isinstance(x, CSym) else x,
+                    "real": lambda x: x.re if isinstance(x, CSym) else x,
+                    "imag": lambda x: x.im if isinstance(x, CSym) else g.const(0.0)}[fname]
+            r = np.frompyfunc(pick, 1, 1)(self._arr(args[0]))
+            return r if isinstance(r, np.ndarray) else _obj(r)
         if fname == "sigmoid":
             x = self._arr(args[0])
             one = _obj(g.const(1.0, weak=True))
@@ -742,7 +856,7 @@ class _Interp:
                 raise UnsupportedModelError("`roll` result must be written back into its ring buffer")
             if not isinstance(target, np.ndarray) or target.dtype != object:
                 raise UnsupportedModelError(f"indexed assignment to `{s.lhs}`")
-            if s.lhs != self.dyname and s.lhs not in self.slot_arrays:
+            if s.lhs != self.dyname and s.lhs not in self.slot_arrays and s.lhs not in self.slot_arrays_complex:
                 # indexed write into a local intermediate: copy-on-write keeps earlier aliases intact
                 target = target.copy()
                 self.env[s.lhs] = target
@@ -764,7 +878,18 @@ class _Interp:
             r.spec.rolls_per_eval = r.shift
             for (row, col), node in r.writes.items():
                 ring_writes.append((r.idx, row, col, node.id))
-        out = ScalarRhs(g, dy.size, [x.id for x in dy], self.params, self.tables, [r.spec for r in self.rings],
+        if self.complex:
+            # complex state -> interleaved (re, im) real derivatives; real-valued right-hand sides get im = 0
+            flat = []
+            for x in dy:
+                c = CSym.of(g, x)
+                flat += [c.re, c.im]
+            n_out, dy_ids = len(flat), [x.id for x in flat]
+        else:
+            if any(isinstance(x, CSym) for x in dy):
+                raise UnsupportedModelError("complex derivative in a real-valued build")
+            n_out, dy_ids = dy.size, [g.lift(x).id for x in dy]
+        out = ScalarRhs(g, n_out, dy_ids, self.params, self.tables, [r.spec for r in self.rings],
                         ring_writes, self.slots, [], self.uses_t)
         # persistent slots: store back only if any evaluation can observe an incoming value
         slot_final = {}

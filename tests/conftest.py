@@ -12,7 +12,15 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 # tolerances of the north star (BASELINE.json): trajectories vs the reference NumPy backend
-RTOL = {"float64": 1e-9, "float32": 1e-4}
+RTOL = {"float64": 1e-9, "float32": 1e-4, "complex128": 1e-9, "complex64": 1e-4}
+
+
+def as_real_columns(ref):
+    """Complex reference recordings -> the kernels' layout: state k as real columns (2k, 2k+1) = (re, im)."""
+    ref = np.asarray(ref)
+    if np.iscomplexobj(ref):
+        return np.stack([ref.real, ref.imag], axis=2).reshape(ref.shape[0], -1)
+    return ref
 
 
 def pytest_configure(config):

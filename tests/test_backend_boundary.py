@@ -275,3 +275,27 @@ def test_model_zoo_runs_on_cuda_like_on_numpy(gpu, registered, path, out, T, dt,
     if not np.all(np.isfinite(ref.values)):
         pytest.skip("the reference trajectory itself is not finite for the template defaults")
     assert traj_rel_err(got.values, ref.values) <= (1e-9 if solver == "heun" else 1e-7)
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("path,out,precision,solver", [
+    (OSC + "kuramoto.kmo_mf", "p/kmo_op/z", "complex128", "heun"),
+    (NM + "theta.kmo_theta", "p/theta_op/z", "complex128", "euler"),
+    (OSC + "kuramoto.kmo_mf_2coupled", "p1/kmo_op/z", "complex64", "euler"),
+    (OSC + "kuramoto.kmo_mf_2coupled", "p2/kmo_op/z", "complex128", "scipy"),
+])
+def test_complex_precision_models_match_numpy_backend(gpu, registered, path, out, precision, solver):
+    """float_precision='complex64/128': the complex state is carried as (re, im) pairs of real state variables, complex
+    arithmetic is lowered to real operations; run() hands back complex frames like the reference."""
+    kw = dict(simulation_time=2.0, step_size=1e-3, sampling_step_size=1e-2, solver=solver, outputs={"z": out}, verbose=False,
+              float_precision=precision, clear=True)
+    if solver == "scipy":
+        kw.update(rtol=1e-8, atol=1e-10)
+    ref = _fresh(path).run(backend="default", **kw)
+    got = _fresh(path).run(backend="cuda", **kw)
+    assert got.shape == ref.shape and np.iscomplexobj(got.values) and got.values.dtype == ref.values.dtype
+    from conftest import as_real_columns
+    # adaptive: SciPy's error norm uses complex moduli, the kernel's treats re / im as separate components
+    tol = {"complex128": 1e-9, "complex64": 1e-4}[precision] if solver != "scipy" else 1e-6
+    assert traj_rel_err(as_real_columns(got.values), as_real_columns(ref.values)) <= tol

@@ -5,7 +5,7 @@ Tolerances are the north star's: rel 1e-9 in fp64, 1e-4 in fp32 (per-column scal
 import numpy as np
 import pytest
 
-from conftest import RTOL, golden_names, golden_path, traj_rel_err
+from conftest import RTOL, as_real_columns, golden_names, golden_path, traj_rel_err
 from oracle import numpy_oracle as orc
 from pyrates_b200 import runtime as rt
 from pyrates_b200.engine import InstanceModel, n_steps_for
@@ -29,7 +29,7 @@ def test_instance_kernel_matches_golden(gpu, name, solver):
     before = rt.launch_count()
     out, y_final = InstanceModel(prog, solver=solver).run(r["T"], r["dt"], r["dts"])
     assert rt.launch_count() == before + 1          # one fused kernel launch for the whole simulation
-    ref = fx["extra"][f"rec_{solver}"]
+    ref = as_real_columns(fx["extra"][f"rec_{solver}"])        # complex fixtures: state k -> real columns (2k, 2k+1)
     got = out[:, :, 0]
     assert got.shape == ref.shape
     err = traj_rel_err(got, ref)

@@ -44,10 +44,6 @@ def test_reference_test_passes_with_cuda_backend(gpu, tmp_path, monkeypatch, mod
     mod = _load(module)
     from pyrates.ir.node import clear_ir_caches
     clear_ir_caches()
-    if hasattr(mod, "complex_compat"):
-        # upstream's switch for backends without complex arithmetic: skips the float_precision='complex64' sub-cases of
-        # test_3_2 / test_3_4 (complex precisions raise UnsupportedModelError on the CUDA backend, DESIGN.md "out of scope")
-        mod.complex_compat = [False] * len(mod.complex_compat)
     try:
         getattr(mod, name)("cuda")
     finally:
