@@ -37,6 +37,18 @@ from pyrates_b200.program import Program     # noqa: E402
 GOLDEN = os.path.join(_ROOT, "tests", "golden")
 
 
+class HistInit:
+    """Stands for the reference's DDEHistory in captured argument lists: only its initial condition travels."""
+
+    def __init__(self, y0):
+        self._y = [np.array(y0, copy=True)]
+
+
+def _fresh(args):
+    """Copies of captured arguments for one oracle run (a new History per run)."""
+    return [orc.History(a._y[0]) if isinstance(a, HistInit) else np.array(a, copy=True) for a in args]
+
+
 class Capture:
     """Monkey-patches the reference NumPy backend to record what it generates and returns."""
 
@@ -58,7 +70,7 @@ class Capture:
             return cap._orig[0](self_, func_name, to_file=to_file, **kw)
 
         def run(self_, func, func_args, T, dt, dts, solver, **kw):
-            cap.func_args = [np.array(a, copy=True) for a in func_args]
+            cap.func_args = [HistInit(a._y[0]) if isinstance(a, bb.DDEHistory) else np.array(a, copy=True) for a in func_args]
             out = cap._orig[1](self_, func, func_args, T, dt, dts, solver, **kw)
             cap.rec = np.array(out[0], copy=True)
             return out
@@ -82,6 +94,36 @@ def _yaml(path):
     def build():
         from pyrates import CircuitTemplate
         return CircuitTemplate.from_yaml(path)
+    return build
+
+
+def _mackey_glass():
+    """Two delay-differential units in the explicit ``x(t-d)`` notation (pyrates/backend/parser.py:63-69 -> past(x, d) ->
+    hist lookups, computegraph.py:1358-1366): a Mackey-Glass oscillator driving a delayed-feedback relaxation unit."""
+    def build():
+        from pyrates import CircuitTemplate, NodeTemplate, OperatorTemplate
+        mg = OperatorTemplate(name="mg_op", equations=["x' = bet*x(t-tau)/(1 + x(t-tau)^10) - gam*x + k*x_in"],
+                              variables={"x": "output(1.2)", "bet": 2.0, "gam": 1.0, "tau": 0.0173, "k": 0.3,
+                                         "x_in": "input(0.0)"})
+        fb = OperatorTemplate(name="fb_op", equations=["z' = -a*z(t-d) + b*z_in - z^3"],
+                              variables={"z": "output(0.4)", "a": 3.0, "b": 0.5, "d": 0.0091, "z_in": "input(0.0)"})
+        n1 = NodeTemplate(name="n1", operators=[mg])
+        n2 = NodeTemplate(name="n2", operators=[fb])
+        return CircuitTemplate(name="mg_fb", nodes={"p1": n1, "p2": n2},
+                               edges=[("p1/mg_op/x", "p2/fb_op/z_in", None, {"weight": 1.0}),
+                                      ("p2/fb_op/z", "p1/mg_op/x_in", None, {"weight": 1.0})])
+    return build
+
+
+def _jrc_pair_delayed():
+    """Two Jansen-Rit circuits coupled through DISCRETE edge delays on a state variable: fixed-step solvers get ring buffers,
+    adaptive ones the DDE path (pyrates/ir/circuit.py:643-667)."""
+    def build():
+        from pyrates import CircuitTemplate
+        jrc = CircuitTemplate.from_yaml(NM + "jansenrit.JRC")
+        return CircuitTemplate(name="jrc_pair_dde", circuits={"jrc1": jrc, "jrc2": jrc},
+                               edges=[("jrc1/pc/rpo_e_in/v", "jrc2/pc/rpo_e_in/m_in", None, {"weight": 2000.0, "delay": 0.004}),
+                                      ("jrc2/pc/rpo_e_in/v", "jrc1/pc/rpo_e_in/m_in", None, {"weight": 4000.0, "delay": 0.0075})])
     return build
 
 
@@ -238,6 +280,14 @@ CASES = {
                         out="p1/kmo_op/z", precision="complex64"),
     "kmo_theta_c128": dict(build=_yaml(NM + "theta.kmo_theta"), T=2.0, dt=1e-3, dts=1e-2, out="p/theta_op/z",
                            precision="complex128"),
+    # delay-differential models, fixed-step solvers: `x(t-d)` notation -> hist(t*dt - d)[idx] lookups into the state history
+    # (DDEHistory, base_backend.py:88-177; the reference's own test: tests/test_backend_simulations.py:551-583)
+    "dde_net16":     dict(build=_yaml(TB + "net16"), T=0.5, dt=1e-3, out="p1/op_dde/x", run_kw=dict(vectorize=False)),
+    "dde_net16_f32": dict(build=_yaml(TB + "net16"), T=0.5, dt=1e-3, dts=2e-3, out="p1/op_dde/x", precision="float32",
+                          run_kw=dict(vectorize=False)),
+    "dde_mg":        dict(build=_mackey_glass(), T=0.3, dt=1e-4, dts=1e-3, out="p1/mg_op/x", run_kw=dict(vectorize=False)),
+    "dde_mg_f32":    dict(build=_mackey_glass(), T=0.3, dt=1e-4, dts=1e-3, out="p1/mg_op/x", precision="float32",
+                          run_kw=dict(vectorize=False)),
     "qsfa_cascade_n8":   dict(build=_qif_sfa_pop(8, "cascade"), T=0.1, dt=1e-3, out="p/qif_sfa_op/r"),
     "qsfa_ring_n8":      dict(build=_qif_sfa_pop(8, "ring"), T=0.1, dt=1e-3, out="p/qif_sfa_op/r"),
     "qsfa_both_n8":      dict(build=_qif_sfa_pop(8, "both"), T=0.1, dt=1e-3, out="p1/qif_sfa_op/r"),
@@ -274,7 +324,7 @@ def make_case(name: str, spec: dict, cap: Capture) -> str:
                     inputs = spec["inputs"]() if "inputs" in spec else None
                     circuit.run(simulation_time=T, step_size=dt, sampling_step_size=dts, solver=solver,
                                 outputs={"o": spec["out"]}, inputs=inputs, backend="default",
-                                float_precision=precision, verbose=False, clear=True)
+                                float_precision=precision, verbose=False, clear=True, **spec.get("run_kw", {}))
             finally:
                 os.chdir(cwd)
         recs[solver] = cap.rec
@@ -290,12 +340,12 @@ def make_case(name: str, spec: dict, cap: Capture) -> str:
     # oracle-defined solvers (no reference implementation): run around the reference-generated text
     func = orc.build_vector_field(prog.source())
     for solver in ("heun_true", "rk4"):
-        args = [np.array(a, copy=True) for a in first_args]
+        args = _fresh(first_args)
         rec, _ = orc.run(func, args, T, dt, dts, solver)
         recs[solver] = rec
     # cross-check: the oracle must reproduce the reference bit-for-bit on the reference's solvers
     for solver in ("euler", "heun"):
-        args = [np.array(a, copy=True) for a in first_args]
+        args = _fresh(first_args)
         rec, _ = orc.run(func, args, T, dt, dts, solver)
         diff = float(np.max(np.abs(rec - recs[solver]))) if rec.size else 0.0
         assert diff == 0.0 or not np.isfinite(diff), f"{name}/{solver}: oracle != reference (max abs diff {diff})"
@@ -326,6 +376,15 @@ ADAPTIVE_CASES = {
     "jrc_rk23":     dict(build=_yaml(NM + "jansenrit.JRC"), T=0.3, dt=1e-4, dts=1e-3, out="pc/rpo_e_in/v",
                          kw=dict(method="RK23", rtol=1e-6, atol=1e-9)),
     "qif_sfa_rk23": dict(build=_yaml(NM + "qif.qif_sfa"), T=2.0, dt=1e-3, dts=5e-3, out="p/qif_sfa_op/r", kw=dict(method="RK23")),
+    # delay-differential models with solver='scipy': scipy.integrate.ode('dopri5') restarted per sample interval, accepted
+    # steps appended to the DDEHistory (BaseBackend._solve_scipy_dde, base_backend.py:771-800)
+    "dde_net16_dopri5":     dict(build=_yaml(TB + "net16"), T=2.0, dt=1e-3, dts=1e-2, out="p1/op_dde/x", run_kw=dict(vectorize=False)),
+    "dde_net16_dopri5_f32": dict(build=_yaml(TB + "net16"), T=2.0, dt=1e-3, dts=1e-2, out="p1/op_dde/x", precision="float32",
+                                 run_kw=dict(vectorize=False)),
+    "dde_net10_dopri5":     dict(build=_yaml(TB + "net10"), T=3.0, dt=1e-3, dts=5e-2, out="pop0/op8/a", run_kw=dict(vectorize=False)),
+    "dde_mg_dopri5":        dict(build=_mackey_glass(), T=0.3, dt=1e-4, dts=1e-3, out="p1/mg_op/x", run_kw=dict(vectorize=False)),
+    "dde_jrc_pair_dopri5":  dict(build=_jrc_pair_delayed(), T=0.2, dt=1e-4, dts=1e-3, out="jrc1/pc/rpo_e_in/v",
+                                 run_kw=dict(vectorize=False)),
     # networks too large for one thread: adaptive integration in the persistent network kernel (grid-wide error norm)
     "wc_n128_rk45": dict(build=_wc_pop(128), T=60.0, dt=1e-3, dts=0.5, out="e/rate_op/r", kw=dict(rtol=1e-7, atol=1e-10)),
     "kuramoto_n128_rk45": dict(build=_kuramoto(128), T=10.0, dt=1e-3, dts=0.05, out="e/phase_op/theta",
@@ -337,6 +396,7 @@ def make_adaptive_case(name: str, spec: dict, cap: Capture) -> str:
     from pyrates import clear
     from pyrates.ir.node import clear_ir_caches
     T, dt, dts, kw = spec["T"], spec["dt"], spec.get("dts"), spec.get("kw", {})
+    precision = spec.get("precision", "float64")
     clear_ir_caches()
     cwd = os.getcwd()
     with tempfile.TemporaryDirectory() as tmp:
@@ -345,15 +405,16 @@ def make_adaptive_case(name: str, spec: dict, cap: Capture) -> str:
             circuit = spec["build"]()
             circuit.run(simulation_time=T, step_size=dt, sampling_step_size=dts, solver="scipy", outputs={"o": spec["out"]},
                         inputs=spec["inputs"]() if "inputs" in spec else None,
-                        backend="default", float_precision="float64", verbose=False, clear=True, **kw)
+                        backend="default", float_precision=precision, verbose=False, clear=True, **kw,
+                        **spec.get("run_kw", {}))
         finally:
             os.chdir(cwd)
     prog = Program.from_source(cap.source, list(zip(cap.names, cap.func_args)), state_vars=cap.state_vars,
-                               float_precision="float64")
+                               float_precision=precision)
     rec = cap.rec
     # the restatement (oracle.solve_rk45) must reproduce reference + SciPy bit for bit
     func = orc.build_vector_field(prog.source())
-    args = [np.array(a, copy=True) for a in cap.func_args]
+    args = _fresh(cap.func_args)
     args[0] = args[0][()]
     mine, _ = orc.run_adaptive(func, args, T, dt, dts, **kw)
     diff = float(np.max(np.abs(mine - rec)))
@@ -362,7 +423,7 @@ def make_adaptive_case(name: str, spec: dict, cap: Capture) -> str:
         clear(circuit)
     except Exception:
         pass
-    run_meta = {"T": T, "dt": dt, "dts": dts, "solver": "scipy", "method": kw.get("method", "RK45"), "precision": "float64",
+    run_meta = {"T": T, "dt": dt, "dts": dts, "solver": "scipy", "method": "dopri5" if prog.is_dde else kw.get("method", "RK45"), "precision": precision,
                 "rtol": kw.get("rtol", 1e-3), "atol": kw.get("atol", 1e-6), "reference_solvers": ["scipy"],
                 "reference_version": "1.2.3", "scipy_version": __import__("scipy").__version__, "out": spec["out"]}
     path = os.path.join(GOLDEN, f"{name}.npz")

@@ -32,6 +32,7 @@ test problems and against 4th-order convergence ("parity unpinned" w.r.t. the re
 """
 from __future__ import annotations
 
+import bisect
 import json
 from typing import Callable, List, Sequence, Tuple
 
@@ -74,6 +75,38 @@ def build_vector_field(source: str, func_name: str = "vector_field") -> Callable
     return ns[func_name]
 
 
+# ----------------------------------------------------------------------------- delay-differential histories
+class History:
+    """Restatement of ``DDEHistory`` (base_backend.py:88-177): (time, state) pairs, linear interpolation between the stored
+    points, the initial condition for t <= t0, the latest state for t >= the last stored time.  The generated rhs reads it
+    as ``hist(t*dt - d)[idx]`` (fixed-step solvers: ``t`` is the integer step counter) or ``hist(t - d)[idx]`` (adaptive),
+    base_backend.py:437-444."""
+
+    def __init__(self, y0, t0: float = 0.0):
+        self._t = [float(t0)]
+        self._y = [np.array(y0, copy=True)]
+
+    def update(self, t, y):
+        self._t.append(float(t))
+        self._y.append(np.array(y, dtype=self._y[0].dtype, copy=True))      # rows of a buffer with y0's dtype (:160)
+
+    def __call__(self, t):
+        t = float(t)
+        if t <= self._t[0]:
+            return self._y[0]
+        if t >= self._t[-1]:
+            return self._y[-1]
+        idx = bisect.bisect_right(self._t, t) - 1
+        t0_, t1_ = self._t[idx], self._t[idx + 1]
+        alpha = (t - t0_) / (t1_ - t0_)
+        return self._y[idx] + alpha * (self._y[idx + 1] - self._y[idx])
+
+
+def _dde(args):
+    """base_backend.py:724 / :755: ``has_dde = len(args) > 0 and isinstance(args[0], DDEHistory)``."""
+    return args[0] if len(args) > 0 and isinstance(args[0], History) else None
+
+
 # ----------------------------------------------------------------------------- solvers
 def _prep(T, dt, dts, y):
     steps = int(np.round(T / dt))
@@ -86,6 +119,7 @@ def _prep(T, dt, dts, y):
 def solve_euler(func, args, T, dt, dts, y, t0):
     """base_backend.py:712-740 (sample before update; integer step passed as t)."""
     steps, store_step, rec = _prep(T, dt, dts, y)
+    hist = _dde(args)
     idx = 0
     for i in range(steps):
         if i % store_step == 0:
@@ -94,12 +128,15 @@ def solve_euler(func, args, T, dt, dts, y, t0):
         step = i + t0
         rhs = func(step, y, *args)
         y += dt * rhs
+        if hist is not None:
+            hist.update((i + 1) * dt, y)
     return rec
 
 
 def solve_heun(func, args, T, dt, dts, y, t0):
     """base_backend.py:742-769 verbatim semantics, including the in-place ``dy`` aliasing."""
     steps, store_step, rec = _prep(T, dt, dts, y)
+    hist = _dde(args)
     idx = 0
     for i in range(steps):
         if i % store_step == 0:
@@ -109,12 +146,15 @@ def solve_heun(func, args, T, dt, dts, y, t0):
         rhs = func(step, y, *args)
         y_0 = y + dt * rhs
         y += dt / 2 * (rhs + func(step, y_0, *args))
+        if hist is not None:
+            hist.update((i + 1) * dt, y)
     return rec
 
 
 def solve_heun_true(func, args, T, dt, dts, y, t0):
     """Textbook Heun (explicit trapezoid): the first stage is copied before the second call."""
     steps, store_step, rec = _prep(T, dt, dts, y)
+    hist = _dde(args)
     idx = 0
     for i in range(steps):
         if i % store_step == 0:
@@ -125,12 +165,15 @@ def solve_heun_true(func, args, T, dt, dts, y, t0):
         y_0 = y + dt * k1
         k2 = func(step, y_0, *args)
         y += dt / 2 * (k1 + k2)
+        if hist is not None:
+            hist.update((i + 1) * dt, y)
     return rec
 
 
 def solve_rk4(func, args, T, dt, dts, y, t0):
     """Classic RK4 around the reference rhs (project definition, see module docstring)."""
     steps, store_step, rec = _prep(T, dt, dts, y)
+    hist = _dde(args)
     idx = 0
     for i in range(steps):
         if i % store_step == 0:
@@ -142,6 +185,8 @@ def solve_rk4(func, args, T, dt, dts, y, t0):
         k3 = func(step, y + (dt / 2) * k2, *args).copy()
         k4 = func(step, y + dt * k3, *args)
         y += (dt / 6) * (k1 + 2 * k2 + 2 * k3 + k4)
+        if hist is not None:
+            hist.update((i + 1) * dt, y)
     return rec
 
 
@@ -244,11 +289,110 @@ def solve_rk45(func, args, T, dt, y0, t0, times, rtol=1e-3, atol=1e-6, max_step=
     return rec[:i_eval]
 
 
+# ----------------------------------------------------------------------------- adaptive DDE: solver='scipy' with a history
+# Restatement of BaseBackend._solve_scipy_dde (base_backend.py:771-800):
+#   solver = scipy.integrate.ode(rhs).set_integrator('dopri5', first_step=dt, nsteps=50000); solver.set_solout(hist.update)
+#   for t_out in times: solver.integrate(t_out); state_rec[i] = solver.y
+# i.e. Hairer's DOPRI5 (third-party: SciPy's _dop extension, 1.18.1 installed here; rtol=1e-6, atol=1e-12, safety 0.9,
+# factors 0.2 / 10, beta 0.04 — the reference forwards none of the caller's tolerances) restarted for every sample interval
+# with h = first_step, and the accepted steps of every call (plus its starting point) appended to the history.
+D5_C = (0.2, 0.3, 0.8, 8.0 / 9.0)
+D5_A = ((0.2,), (3.0 / 40.0, 9.0 / 40.0), (44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0),
+        (19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0),
+        (9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0),
+        (35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0))
+D5_E = (71.0 / 57600.0, 0.0, -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0, 22.0 / 525.0, -1.0 / 40.0)
+
+
+def dopri5_call(f, x, y, xend, h, solout, rtol=1e-6, atol=1e-12, nmax=50000, safe=0.9, fac1=0.2, fac2=10.0, beta=0.04):
+    """One ``dopri5`` call (Hairer, Norsett, Wanner: DOPCOR) from x to xend with initial step h.  Returns (x, y, ok)."""
+    uround = 2.3e-16
+    n = y.size
+    facold, expo1 = 1e-4, 0.2 - beta * 0.75
+    facc1, facc2 = 1.0 / fac1, 1.0 / fac2
+    posneg = 1.0 if xend - x >= 0 else -1.0
+    hmax = abs(xend - x)
+    last, reject = False, False
+    k1 = np.array(f(x, y), dtype=float)
+    nstep = naccpt = 0
+    solout(x, y)
+    while True:
+        if nstep > nmax:
+            return x, y, False
+        if 0.1 * abs(h) <= abs(x) * uround:
+            return x, y, False
+        if (x + 1.01 * h - xend) * posneg > 0.0:
+            h = xend - x
+            last = True
+        nstep += 1
+        a = D5_A
+        k2 = np.array(f(x + D5_C[0] * h, y + h * a[0][0] * k1), dtype=float)
+        k3 = np.array(f(x + D5_C[1] * h, y + h * (a[1][0] * k1 + a[1][1] * k2)), dtype=float)
+        k4 = np.array(f(x + D5_C[2] * h, y + h * (a[2][0] * k1 + a[2][1] * k2 + a[2][2] * k3)), dtype=float)
+        k5 = np.array(f(x + D5_C[3] * h, y + h * (a[3][0] * k1 + a[3][1] * k2 + a[3][2] * k3 + a[3][3] * k4)), dtype=float)
+        ysti = y + h * (a[4][0] * k1 + a[4][1] * k2 + a[4][2] * k3 + a[4][3] * k4 + a[4][4] * k5)
+        xph = x + h
+        k6 = np.array(f(xph, ysti), dtype=float)
+        y1 = y + h * (a[5][0] * k1 + a[5][2] * k3 + a[5][3] * k4 + a[5][4] * k5 + a[5][5] * k6)
+        k7 = np.array(f(xph, y1), dtype=float)
+        e = D5_E
+        k4 = (e[0] * k1 + e[2] * k3 + e[3] * k4 + e[4] * k5 + e[5] * k6 + e[6] * k7) * h
+        sk = atol + rtol * np.maximum(np.abs(y), np.abs(y1))
+        err = 0.0
+        for i in range(n):
+            err += (k4[i] / sk[i]) ** 2
+        err = np.sqrt(err / n)
+        fac11 = err ** expo1
+        fac = fac11 / facold ** beta
+        fac = max(facc2, min(facc1, fac / safe))
+        hnew = h / fac
+        if err <= 1.0:
+            facold = max(err, 1e-4)
+            naccpt += 1
+            k1, y, x = k7, y1, xph
+            solout(x, y)
+            if last:
+                return x, y, True
+            if abs(hnew) > hmax:
+                hnew = posneg * hmax
+            if reject:
+                hnew = posneg * min(abs(hnew), abs(h))
+            reject = False
+        else:
+            hnew = h / min(facc1, fac11 / safe)
+            reject = True
+            last = False
+        h = hnew
+
+
+def solve_dopri5_dde(func, args, T, dt, y0, t0, times, **kwargs):
+    """base_backend.py:771-800; ``args[0]`` is the History.  Returns state_rec[len(times), n] (rows after a failed call stay
+    zero, like the reference's ``if not solver.successful(): break``)."""
+    hist = args[0]
+    y = np.asarray(y0).astype(float)          # scipy.integrate.ode works on float64 copies
+    x = float(t0)
+    rec = np.zeros((len(times), y.shape[0]), dtype=np.asarray(y0).dtype)
+
+    def rhs(t, y_):
+        # the extension hands the callback a Python float: `t - d` with a float32 constant d is then a float32 operation
+        return func(float(t), y_, *args)
+
+    ok = True
+    for i, t_out in enumerate(times):
+        if not ok:
+            break
+        x, y, ok = dopri5_call(rhs, x, y, float(t_out), float(dt), hist.update)
+        rec[i, :] = y
+    return rec
+
+
 def run_adaptive(func, func_args: Sequence, T: float, dt: float, dts: float = None, **kw):
     """base_backend.py:596-611 with solver='scipy' (method RK45)."""
     t0, y0 = func_args[0], func_args[1]
     step = dts if dts else dt
     times = np.linspace(0.0, T, num=round(T / step), endpoint=False)
+    if _dde(func_args[2:]) is not None:       # base_backend.py:704-706
+        return solve_dopri5_dde(func, tuple(func_args[2:]), T, dt, y0, t0, times, **kw), times
     return solve_rk45(func, tuple(func_args[2:]), T, dt, y0, t0, times, **kw), times
 
 
@@ -275,17 +419,31 @@ def load_fixture(path: str) -> dict:
     lines = [f"def {meta['func_name']}({','.join(names)}):"]
     for lhs, rhs, idx in meta["stmts"]:
         lines.append(f"\t{lhs}[{idx}] = {rhs}" if idx is not None else f"\t{lhs} = {rhs}")
-    lines.append(f"\treturn {names[2]}")
+    ret = next(a["name"] for a in meta["args"] if a["kind"] == "dy")
+    lines.append(f"\treturn {ret}")
     run_meta = json.loads(bytes(extra.pop("__run__").tobytes()).decode()) if "__run__" in extra else {}
     return {"meta": meta, "args": args, "names": names, "source": "\n".join(lines) + "\n",
             "run": run_meta, "extra": extra}
+
+
+def fixture_args(fx: dict) -> list:
+    """Fresh argument list of a loaded fixture; the 'hist' argument of delay-differential fixtures (stored as the float64
+    initial state the reference built its DDEHistory from) becomes a new History."""
+    args = [np.array(a, copy=True) for a in fx["args"]]
+    args[0] = args[0][()] if args[0].ndim == 0 else args[0]
+    for k, m in enumerate(fx["meta"]["args"]):
+        if m["kind"] == "hist":
+            args[k] = History(args[k])
+    return args
 
 
 def run_fixture(fx: dict, solver: str = None, T: float = None, dt: float = None, dts: float = None):
     """Integrate a loaded fixture with the oracle; returns ``(state_rec, times)``."""
     r = fx["run"]
     func = build_vector_field(fx["source"], fx["meta"]["func_name"])
-    args = [np.array(a, copy=True) for a in fx["args"]]
-    args[0] = args[0][()] if args[0].ndim == 0 else args[0]
+    args = fixture_args(fx)
+    if (solver or r["solver"]) == "scipy":
+        return run_adaptive(func, args, T if T is not None else r["T"], dt if dt is not None else r["dt"],
+                            dts if dts is not None else r.get("dts"))
     return run(func, args, T if T is not None else r["T"], dt if dt is not None else r["dt"],
                dts if dts is not None else r.get("dts"), solver or r["solver"])

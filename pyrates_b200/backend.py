@@ -75,6 +75,18 @@ _OPS: Dict[str, Tuple[str, Callable]] = {
 }
 
 
+class CudaHistory:
+    """Placeholder for ``DDEHistory`` (base_backend.py:88-177) in the argument tuple of a delay-differential vector field:
+    carries the initial condition only.  It cannot be called on the host — there is no CPU execution path."""
+
+    def __init__(self, y0, t0: float = 0.0):
+        self.y0 = np.array(y0, dtype=np.float64, copy=True)
+        self.t0 = float(t0)
+
+    def __call__(self, t):
+        raise _backend_error("the state history of a CUDA vector field lives on the device; it cannot be queried on the host")
+
+
 class CudaVectorField:
     """Handle returned by ``generate_func``: the recorded vector field.  Calling it evaluates the rhs ONCE
     on the GPU (``func(t, y, *args) -> dy``), matching what ``get_run_func`` hands to users
@@ -94,8 +106,14 @@ class CudaVectorField:
         assigned = {s.lhs for s in self.stmts}
         args = []
         for i, (name, val) in enumerate(zip(self.arg_names, func_args)):
-            if name == "hist" or callable(val):
-                raise UnsupportedModelError("delay-differential models (`past`) are not supported by the CUDA backend")
+            if name == "hist" and i == 2:
+                # the history object only carries the initial condition (DDEHistory.__init__, base_backend.py:130-146);
+                # the history itself lives on the device (csrc/templates/inst_kernel.cuh)
+                y_init = getattr(val, "y0", getattr(val, "_y", [func_args[1]])[0])
+                args.append(Arg(name, "hist", np.array(y_init, dtype=np.float64, copy=True)))
+                continue
+            if callable(val):
+                raise UnsupportedModelError(f"callable argument `{name}` of the vector field")
             kind = "t" if i == 0 else ("y" if name == self.state_var else ("dy" if name == self.return_var else
                                                                            ("var" if name in assigned else "const")))
             args.append(Arg(name, kind, np.array(val, copy=True)))
@@ -128,9 +146,10 @@ class CudaBackend:
         self.code: List[str] = []
         self.lvl = 0
         self._stmts: List[Stmt] = []
+        self._n_hist_stmts = 0
         self._imports: List[str] = []
         self._helper_funcs: List[str] = []
-        self.add_hist_arg = kwargs.pop('add_hist_arg', False)
+        self.add_hist_arg = kwargs.pop('add_hist_arg', True)                  # reference default (:295)
         self.lags = {}
         self.idx_dummy_var = "temporary_pyrates_var_index"
         self._float_precision = kwargs.pop('float_precision', 'float32')      # reference default (:300)
@@ -237,9 +256,18 @@ class CudaBackend:
         self._stmts.append(Stmt(lhs.name, rhs, idx_str))
         self.add_code_line(f"{lhs.name}[{idx_str}] = {rhs}" if idx_str is not None else f"{lhs.name} = {rhs}")
 
-    def add_var_hist(self, lhs: str, delay, state_idx: str, **kwargs):
-        raise UnsupportedModelError("delay-differential models (`past` / history functions) are not supported by the "
-                                    "CUDA backend; use discrete or gamma-kernel edge delays")
+    def add_var_hist(self, lhs: str, delay, state_idx, dt: Optional[float] = None, dt_adapt: bool = True, **kwargs):
+        """base_backend.py:437-444: ``lhs = hist(t*dt - d)[idx]`` for fixed-step solvers (t = integer step counter),
+        ``hist(t - d)[idx]`` for adaptive ones.  Recorded in the reference's text form; lowered by scalarize._hist_read."""
+        idx = self._process_idx(state_idx)
+        is_var = hasattr(delay, "vtype") and hasattr(delay, "name")                       # ComputeVar (:675-676)
+        d = f"{delay.name}[{self._start_idx}]" if is_var and delay.shape else (delay.name if is_var else f"{delay}")
+        rhs = f"hist(t*{dt:.10e}-{d})[{idx}]" if (dt is not None and not dt_adapt) else f"hist(t-{d})[{idx}]"
+        # ComputeGraph.to_func (computegraph.py:424-450) prints the body first, then the head and the history lookups, and
+        # re-inserts the body after them: the lookups precede every recorded body statement
+        self._stmts.insert(self._n_hist_stmts, Stmt(lhs, rhs, None))
+        self._n_hist_stmts += 1
+        self.add_code_line(f"{lhs} = {rhs}")
 
     def add_import(self, line: str):
         if line not in self._imports:
@@ -248,15 +276,13 @@ class CudaBackend:
     def generate_func_head(self, func_name: str, state_var: str = 'y', return_var: str = 'dy', func_args: list = None,
                            add_hist_func: Optional[bool] = None):
         """base_backend.py:483-528: signature order = t, y, [hist], then unique args in first-seen order."""
-        if add_hist_func:
-            raise UnsupportedModelError("delay-differential models (`past`) are not supported by the CUDA backend")
         names = [a.name for a in func_args] if func_args else []
         seen, uniq = set(), []
         for n in names:
             if n not in seen:
                 seen.add(n)
                 uniq.append(n)
-        args = ['t', state_var] + uniq
+        args = ['t', state_var] + (['hist'] if add_hist_func else []) + uniq
         self._head = (func_name, state_var, return_var, args)
         self.add_linebreak()
         self.add_code_line(f"def {func_name}({','.join(args)}):")
@@ -279,7 +305,9 @@ class CudaBackend:
 
     @staticmethod
     def get_hist_func(y: np.ndarray, t0: float = 0.0):
-        raise UnsupportedModelError("delay-differential models (`past`) are not supported by the CUDA backend")
+        """base_backend.py:648-649.  The returned object stands for the state history in the argument tuple; the history
+        itself is kept on the device."""
+        return CudaHistory(y, t0)
 
     @staticmethod
     def to_file(fn: str, **kwargs):
@@ -288,6 +316,7 @@ class CudaBackend:
     def clear(self):
         self.code.clear()
         self._stmts = []
+        self._n_hist_stmts = 0
         self._head = None
 
     # ------------------------------------------------------------------ integration

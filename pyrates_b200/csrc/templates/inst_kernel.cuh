@@ -196,6 +196,133 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
     if (A.sync) A.sync[b] = status | ((unsigned int)(attempts > 0xFFFFFFF ? 0xFFFFFFF : attempts) << 4);   // low 4 bits: status, rest: rhs attempts
     prb_thread_exit(T, A, b);
 }
+#elif PRB_SOLVER == PRB_SOLVER_DOPRI5
+// ---- adaptive solver of delay-differential models: the reference's solver='scipy' with a state history ==
+// BaseBackend._solve_scipy_dde (pyrates/backend/base/base_backend.py:771-800):
+//     solver = scipy.integrate.ode(rhs).set_integrator('dopri5', first_step=dt, nsteps=50000); set_solout(hist.update)
+//     for t_out in times: solver.integrate(t_out); state_rec[i] = solver.y
+// i.e. Hairer's DOPRI5 core (rtol 1e-6, atol 1e-12, safety 0.9, step factors in [0.2, 10], beta 0.04 — the reference
+// forwards none of the caller's tolerances), RESTARTED for every sample interval with h = first_step, and every accepted
+// step (plus the starting point of every call) appended to the history the rhs interpolates in (prb_hist).  One thread
+// integrates one instance; the state is double whatever the model precision (scipy.integrate.ode converts it).
+// Options (A.consts, doubles): [0] rtol [1] atol [2] t_start [4] first_step [5] sample spacing [7] nsteps
+// [8] history capacity [9..] float64 initial condition of the history.  A.work: history ring.  Status per instance
+// (A.sync): 0 ok, 1 step size too small, 2 more than nsteps steps in one call, 3 history ring too small (host retries).
+extern "C" __global__ void __launch_bounds__(PRB_BLOCK, PRB_MIN_BLOCKS)
+prb_integrate(const __grid_constant__ prb_kernel_args A)
+{
+    constexpr double C2 = 0.2, C3 = 0.3, C4 = 0.8, C5 = 8.0 / 9.0;
+    constexpr double A21 = 0.2, A31 = 3.0 / 40.0, A32 = 9.0 / 40.0, A41 = 44.0 / 45.0, A42 = -56.0 / 15.0, A43 = 32.0 / 9.0,
+        A51 = 19372.0 / 6561.0, A52 = -25360.0 / 2187.0, A53 = 64448.0 / 6561.0, A54 = -212.0 / 729.0,
+        A61 = 9017.0 / 3168.0, A62 = -355.0 / 33.0, A63 = 46732.0 / 5247.0, A64 = 49.0 / 176.0, A65 = -5103.0 / 18656.0,
+        A71 = 35.0 / 384.0, A73 = 500.0 / 1113.0, A74 = 125.0 / 192.0, A75 = -2187.0 / 6784.0, A76 = 11.0 / 84.0;
+    constexpr double E1 = 71.0 / 57600.0, E3 = -71.0 / 16695.0, E4 = 71.0 / 1920.0, E5 = -17253.0 / 339200.0,
+        E6 = 22.0 / 525.0, E7 = -1.0 / 40.0;
+    constexpr double SAFE = 0.9, BETA = 0.04, EXPO1 = 0.2 - BETA * 0.75, FACC1 = 1.0 / 0.2, FACC2 = 1.0 / 10.0,
+        UROUND = 2.3e-16;
+    const long long B = A.n_inst;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    PRB_STAGE_ETAB
+    if (b >= B) return;
+    PrbThread T;
+    prb_thread_init(T, A, b);
+    PRB_SET_ETAB
+    const double* __restrict__ opt = (const double*)A.consts;
+    const double rtol = opt[0], atol = opt[1], first_step = opt[4], te_step = opt[5];
+    const long long nmax = (long long)opt[7];
+    double x = opt[2];
+
+    real* __restrict__ Y = (real*)A.y;
+    double y[PRB_NS], y1[PRB_NS], k1[PRB_NS], k2[PRB_NS], k3[PRB_NS], k4[PRB_NS], k5[PRB_NS], k6[PRB_NS];
+    areal yr[PRB_NS], kr[PRB_NS];
+    real yo[PRB_NS];
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) y[j] = (double)Y[(long long)j * B + b];
+
+    real* __restrict__ out = (real*)A.out;
+    long long steps_total = 0;
+    unsigned int status = 0;
+
+#define PRB_D5_STAGE(tt, kout, expr)                                              \
+    PRB_UNROLL_NS                                                                 \
+    for (int j = 0; j < PRB_NS; ++j) yr[j] = (areal)(y[j] + (expr));              \
+    prb_rhs((prb_time)(tt), yr, kr, T);                                           \
+    PRB_UNROLL_NS                                                                 \
+    for (int j = 0; j < PRB_NS; ++j) kout[j] = (double)kr[j];
+
+    for (long long sample = 0; sample < A.n_steps && status == 0; ++sample) {
+        const double xend = (double)sample * te_step;               // numpy.linspace(0, T, n, endpoint=False)[sample]
+        // ---- one dopri5 call from x to xend (DOPCOR)
+        double h = first_step, facold = 1e-4;
+        const double posneg = (xend - x >= 0.0) ? 1.0 : -1.0, hmax = fabs(xend - x);
+        bool last = false, reject = false;
+        long long nstep = 0;
+        PRB_UNROLL_NS
+        for (int j = 0; j < PRB_NS; ++j) yr[j] = (areal)y[j];
+        prb_rhs((prb_time)x, yr, kr, T);
+        PRB_UNROLL_NS
+        for (int j = 0; j < PRB_NS; ++j) k1[j] = (double)kr[j];
+        prb_hist_push(T, x, y);                                      // solout at the start of the call
+        for (;;) {
+            if (nstep > nmax) { status = 2; break; }
+            if (0.1 * fabs(h) <= fabs(x) * UROUND) { status = 1; break; }
+            if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = true; }
+            ++nstep;
+            PRB_D5_STAGE(x + C2 * h, k2, h * A21 * k1[j])
+            PRB_D5_STAGE(x + C3 * h, k3, h * (A31 * k1[j] + A32 * k2[j]))
+            PRB_D5_STAGE(x + C4 * h, k4, h * (A41 * k1[j] + A42 * k2[j] + A43 * k3[j]))
+            PRB_D5_STAGE(x + C5 * h, k5, h * (A51 * k1[j] + A52 * k2[j] + A53 * k3[j] + A54 * k4[j]))
+            const double xph = x + h;
+            PRB_D5_STAGE(xph, k6, h * (A61 * k1[j] + A62 * k2[j] + A63 * k3[j] + A64 * k4[j] + A65 * k5[j]))
+            PRB_UNROLL_NS
+            for (int j = 0; j < PRB_NS; ++j) {
+                y1[j] = y[j] + h * (A71 * k1[j] + A73 * k3[j] + A74 * k4[j] + A75 * k5[j] + A76 * k6[j]);
+                yr[j] = (areal)y1[j];
+            }
+            prb_rhs((prb_time)xph, yr, kr, T);                       // k7 (first stage of the next step)
+            double err = 0.0;
+            PRB_UNROLL_NS
+            for (int j = 0; j < PRB_NS; ++j) {
+                k2[j] = (double)kr[j];
+                const double e = (E1 * k1[j] + E3 * k3[j] + E4 * k4[j] + E5 * k5[j] + E6 * k6[j] + E7 * k2[j]) * h;
+                const double sk = atol + rtol * fmax(fabs(y[j]), fabs(y1[j]));
+                err += (e / sk) * (e / sk);
+            }
+            err = sqrt(err / (double)PRB_NS);
+            const double fac11 = pow(err, EXPO1);
+            double fac = fac11 / pow(facold, BETA);
+            fac = fmax(FACC2, fmin(FACC1, fac / SAFE));
+            double hnew = h / fac;
+            if (err <= 1.0) {
+                facold = fmax(err, 1e-4);
+                PRB_UNROLL_NS
+                for (int j = 0; j < PRB_NS; ++j) { k1[j] = k2[j]; y[j] = y1[j]; }
+                x = xph;
+                prb_hist_push(T, x, y);                              // solout after every accepted step
+                if (last) break;
+                if (fabs(hnew) > hmax) hnew = posneg * hmax;
+                if (reject) hnew = posneg * fmin(fabs(hnew), fabs(h));
+                reject = false;
+            } else {
+                hnew = h / fmin(FACC1, fac11 / SAFE);
+                reject = true;
+                last = false;
+            }
+            h = hnew;
+        }
+        steps_total += nstep;
+        if (T.hovf) status = 3;
+        if (status != 0) break;
+        PRB_UNROLL_NS
+        for (int j = 0; j < PRB_NS; ++j) yo[j] = (real)y[j];
+        prb_record(yo, out + (A.sample0 + sample) * (long long)PRB_NOBS * B, b, B);
+    }
+#undef PRB_D5_STAGE
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) Y[(long long)j * B + b] = (real)y[j];
+    if (A.sync) A.sync[b] = status | ((unsigned int)(steps_total > 0xFFFFFFF ? 0xFFFFFFF : steps_total) << 4);
+    prb_thread_exit(T, A, b);
+}
 #else
 extern "C" __global__ void __launch_bounds__(PRB_BLOCK, PRB_MIN_BLOCKS)
 prb_integrate(const __grid_constant__ prb_kernel_args A)
@@ -269,6 +396,9 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
 #else
 #error "unknown PRB_SOLVER"
 #endif
+#if PRB_NH > 0
+        prb_hist_push(T, y, A.step0 + i + 1);        // DDEHistory.update((i + 1) * dt, y)
+#endif
     }
 
     PRB_UNROLL_NS
@@ -293,7 +423,7 @@ prb_rhs_eval(const __grid_constant__ prb_kernel_args A)
     areal y[PRB_NS], k[PRB_NS];
     PRB_UNROLL_NS
     for (int j = 0; j < PRB_NS; ++j) y[j] = (areal)Y[(long long)j * B + b];
-#if PRB_SOLVER == PRB_SOLVER_RK45
+#if PRB_SOLVER == PRB_SOLVER_RK45 || PRB_SOLVER == PRB_SOLVER_DOPRI5
     prb_rhs((prb_time)A.dt, y, k, T);            // float time of the evaluation travels in args.dt
 #else
     prb_rhs(A.step0 + A.t0, y, k, T);

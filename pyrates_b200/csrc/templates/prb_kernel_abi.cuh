@@ -33,4 +33,5 @@ static_assert(sizeof(prb_kernel_args) == 8 * 8 + 10 * 8 + 16, "prb_kernel_args l
 #define PRB_SOLVER_HEUN     2
 #define PRB_SOLVER_RK4      3
 #define PRB_SOLVER_RK45     4
+#define PRB_SOLVER_DOPRI5   5
 #endif

@@ -18,8 +18,8 @@ from .scalarize import ScalarRhs, UnsupportedModelError
 
 _TPL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "templates")
 
-SOLVER_IDS = {"euler": 0, "heun": 1, "heun_ref": 1, "heun_true": 2, "rk4": 3, "scipy": 4, "rk45": 4}
-ADAPTIVE_SOLVERS = ("scipy", "rk45")
+SOLVER_IDS = {"euler": 0, "heun": 1, "heun_ref": 1, "heun_true": 2, "rk4": 3, "scipy": 4, "rk45": 4, "dopri5_dde": 5}
+ADAPTIVE_SOLVERS = ("scipy", "rk45", "dopri5_dde")
 
 _FUNC = {"exp": "exp", "log": "log", "sin": "sin", "cos": "cos", "tan": "tan", "tanh": "tanh", "sinh": "sinh",
          "cosh": "cosh", "arctan": "atan", "arcsin": "asin", "arccos": "acos", "sqrt": "sqrt", "abs": "fabs",
@@ -43,6 +43,9 @@ class InstKernel:
     ring_rolls: List[int]
     ring_lengths: List[int]
     table_values: np.ndarray  # packed tables
+    n_hist: int              # delay-differential models: state elements with a device-side history ...
+    hist_depth: int          # ... and (fixed-step solvers) the ring depth in steps
+    hist_vars: List[int]
     slot_init: np.ndarray
     param_defaults: np.ndarray
     block: int
@@ -72,7 +75,7 @@ def _lit(v: float, f32: bool) -> str:
 
 def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time: bool = False,
                   fast_math: bool = False, spec: bool = False, round_dy_f32: bool = False,
-                  slot_consts: Optional[dict] = None) -> List[str]:
+                  slot_consts: Optional[dict] = None, model_f32: bool = False) -> List[str]:
     """Straight-line statements computing dy[] (+ ring / slot stores) from y[], T."""
     g = rhs.graph
     ring_off = np.cumsum([0] + [r.rows * r.length for r in rhs.rings])
@@ -149,6 +152,18 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
     for i in live:
         op, a = g.ops[i], g.args[i]
         if op in ("const", "state", "param", "t"):
+            continue
+        if op == "hist":
+            # delayed state: the query time follows NumPy's promotion in the reference-generated text (base_backend.py:442-444)
+            hv, scale, dhex, strong = g.payload[i]
+            d = float.fromhex(dhex)
+            if scale is not None:
+                tq = f"((double)t * {float(scale)!r} - {d!r})"          # `t*dt - d`: int step * Python float -> float64
+            elif strong and model_f32:
+                tq = f"(double)((float)t - {float(np.float32(d))!r}f)"  # Python-float t - float32 array: a float32 operation
+            else:
+                tq = f"((double)t - {d!r})"
+            lines.append(f"const areal v{i} = (areal)prb_hist(T, {hv}, {tq});")
             continue
         if fast_math and not g.isint[i] and op in ("mul", "div"):
             base, f = const_chain(i)
@@ -258,6 +273,17 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
             slot_consts = {k: float(rhs.slots[k][2]) for k in read_first}
             rhs = copy.copy(rhs)
             rhs.slots, rhs.slot_writes = [], []
+    n_hist = len(rhs.hist_vars)
+    hist_depth = 0
+    if n_hist:
+        if adaptive != (solver == "dopri5_dde") or adaptive != (rhs.hist_dt is None):
+            raise UnsupportedModelError("delay-differential models: fixed-step solvers need the `hist(t*dt - d)` form, "
+                                        "solver='scipy' the `hist(t - d)` form of the vector field (rebuild for the solver)")
+        if not adaptive:
+            need = int(math.ceil(max(rhs.hist_delays) / rhs.hist_dt)) + 3
+            hist_depth = 1 << max(2, (need - 1).bit_length())            # power of two: slot = step & (depth - 1)
+    elif solver == "dopri5_dde":
+        raise UnsupportedModelError("solver 'dopri5_dde' is the adaptive path of delay-differential models")
     step_tables = any(rhs.graph.ops[i] == "table" for i in rhs.live_nodes())
     if adaptive and (rhs.rings or step_tables or rhs.slots):
         raise UnsupportedModelError("adaptive integration (solver='scipy') needs a pure vector field: delay ring buffers, "
@@ -273,9 +299,9 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     arith64 = adaptive and f32
     body_f32 = f32 and not arith64
     body = emit_rhs_body(rhs, body_f32, const_div_to_mul, float_time=adaptive, fast_math=fast_math, spec=spec,
-                         round_dy_f32=arith64, slot_consts=slot_consts)
+                         round_dy_f32=arith64, slot_consts=slot_consts, model_f32=f32)
     exact_body = emit_rhs_body(rhs, body_f32, const_div_to_mul, float_time=adaptive, round_dy_f32=arith64,
-                               slot_consts=slot_consts) if spec else None
+                               slot_consts=slot_consts, model_f32=f32) if spec else None
     spec = spec and any("prb_spec_" in l for l in body)
     use_etab = any("prb_fast_exp(" in l or "prb_spec_exp(" in l for l in body)
     np_ = len(rhs.params)
@@ -292,7 +318,9 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     src.append(f"#define PRB_SOLVER {SOLVER_IDS[solver]}")
     src.append(f"#define PRB_BLOCK {block}")
     src.append(f"#define PRB_MIN_BLOCKS {int(min_blocks)}")
-    if adaptive:
+    src.append(f"#define PRB_NH {n_hist}")
+    src.append(f"#define PRB_HDEPTH {hist_depth}")
+    if adaptive and solver != "dopri5_dde":
         from .rk45 import cuda_method_tables
         src.append(cuda_method_tables(rk_method))
     if ns > 64:
@@ -307,7 +335,64 @@ struct PrbThread {
     const real* __restrict__ tables;
     const double* etab;            // shared-memory copy of PRB_EXP_TAB (fast_math kernels)
     unsigned int etab_s;           // the same as a 32-bit shared-window address (ld.shared without S2UR per use)
+#if PRB_NH > 0
+#if PRB_HDEPTH > 0                 // fixed-step history: ring [PRB_HDEPTH][PRB_NH][B] of the states after steps 0..hn
+    real* __restrict__ hist;
+    long long hn;                  // latest stored step
+    double hdt;                    // step size of the history times (i + 1) * dt
+#else                              // adaptive history: ring of (time, state) entries [cap][B] / [cap][PRB_NH][B]
+    double* __restrict__ ht;
+    double* __restrict__ hy;
+    long long hn, hcap;            // entries so far (entry 0 = the initial condition), ring capacity
+    double ht0, hy0[PRB_NH];       // entry 0 is never evicted: the pre-history
+    bool hovf;                     // a lookup needed an entry that was already overwritten
+#endif
+#endif
 };
+#if PRB_NH > 0
+// Delayed state for delay-differential models — the device-side counterpart of DDEHistory.__call__
+// (pyrates/backend/base/base_backend.py:165-177): the initial condition for t <= t0, the latest stored state for
+// t >= the last stored time, else linear interpolation between the two stored states that bracket t
+// (idx = bisect_right(times, t) - 1).
+#if PRB_HDEPTH > 0
+// fixed-step solvers: the history holds the state after every step, at times T_0 = 0, T_j = j * dt
+// (BaseBackend._solve_euler / _solve_heun: args[0].update((i + 1) * dt, y), :737-738 / :766-767)
+__device__ __forceinline__ real prb_hist(const PrbThread& T, const int k, const double tq) {
+    const long long n = T.hn;
+    const double dt = T.hdt;
+    const real* __restrict__ H = T.hist + (long long)k * T.B;
+    const long long stride = (long long)PRB_NH * T.B;
+    if (tq <= 0.0) return H[0];                                             // slot of step 0 (depth > max delay / dt + 2)
+    if (tq >= (double)n * dt) return H[(n & (PRB_HDEPTH - 1)) * stride];
+    long long j = (long long)(tq / dt);
+    j = j < 0 ? 0 : (j > n - 1 ? n - 1 : j);
+    while (j + 1 < n && (double)(j + 1) * dt <= tq) ++j;                    // bisect_right(times, tq) - 1 on T_j = fl(j * dt)
+    while (j > 0 && (double)j * dt > tq) --j;
+    const double t0 = (double)j * dt, t1 = (double)(j + 1) * dt;
+    const double alpha = (tq - t0) / (t1 - t0);
+    const real a = H[(j & (PRB_HDEPTH - 1)) * stride], c = H[((j + 1) & (PRB_HDEPTH - 1)) * stride];
+    return a + (real)alpha * (c - a);
+}
+#else
+__device__ __forceinline__ double prb_hist(PrbThread& T, const int k, const double tq) {
+    if (tq <= T.ht0) return T.hy0[k];
+    const long long n = T.hn, last = n - 1;
+    const long long sy = (long long)PRB_NH * T.B;
+    const double* __restrict__ HY = T.hy + (long long)k * T.B;
+    if (tq >= T.ht[(last % T.hcap) * T.B]) return HY[(last % T.hcap) * sy];
+    long long a = n > T.hcap ? n - T.hcap : 0, c = last;
+    if (T.ht[(a % T.hcap) * T.B] > tq) { T.hovf = true; return HY[(a % T.hcap) * sy]; }
+    while (c - a > 1) {                                                     // invariant: time[a] <= tq < time[c]
+        const long long m = (a + c) >> 1;
+        if (T.ht[(m % T.hcap) * T.B] <= tq) a = m; else c = m;
+    }
+    const double t0 = T.ht[(a % T.hcap) * T.B], t1 = T.ht[((a + 1) % T.hcap) * T.B];
+    const double alpha = (tq - t0) / (t1 - t0);
+    const double y0 = HY[(a % T.hcap) * sy], y1 = HY[((a + 1) % T.hcap) * sy];
+    return y0 + alpha * (y1 - y0);
+}
+#endif
+#endif
 // ---- fast_math (fp64): cheaper exp / division for FP64-pipe-bound kernels (the JRC sweep spends ~70 % of its fp64
 // instructions in 3 sigmoids per evaluation).  exp: x = (256 k + j) ln2/256 + r, |r| <= ln2/512,
 // e^x = 2^k * 2^(j/256) * (1 + r + .. + r^4/24): 9 fp64 instructions + one shared-memory table read instead of ~20;
@@ -406,7 +491,31 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
         init.append("    _Pragma(\"unroll\") for (int k = 0; k < PRB_NP; ++k) T.p[k] = P[(long long)k * T.B + b];")
     for k, r in enumerate(rhs.rings):
         init.append(f"    T.head[{k}] = (int)((A.eval0 * {r.rolls_per_eval}LL) % {r.length}LL);")
+    if n_hist and not adaptive:
+        init.append("    T.hist = (real*)A.work + b; T.hn = A.step0; T.hdt = A.dt;")
+    elif n_hist:
+        init.append("    const double* __restrict__ O = (const double*)A.consts;")
+        init.append("    T.hcap = (long long)O[8]; T.ht = (double*)A.work + b; T.hy = (double*)A.work + T.hcap * T.B + b;")
+        init.append("    T.hn = 1; T.ht0 = O[2]; T.hovf = false;")
+        init.append("    _Pragma(\"unroll\") for (int k = 0; k < PRB_NH; ++k) { T.hy0[k] = O[9 + k]; T.hy[(long long)k * T.B] = O[9 + k]; }")
+        init.append("    T.ht[0] = O[2];")
     init.append("}")
+    if n_hist and not adaptive:
+        push = ["// DDEHistory.update((i + 1) * dt, y): the state after step n - 1 becomes history entry n",
+                "__device__ __forceinline__ void prb_hist_push(PrbThread& T, const real (&y)[PRB_NS], const long long n) {",
+                "    real* __restrict__ H = T.hist + (n & (PRB_HDEPTH - 1)) * (long long)PRB_NH * T.B;"]
+        push += [f"    H[{k}LL * T.B] = y[{e}];" for k, e in enumerate(rhs.hist_vars)]
+        push += ["    T.hn = n;", "}"]
+        init.append("\n".join(push))
+    elif n_hist:
+        push = ["// solout(t, y) -> DDEHistory.update(t, y): one entry per accepted step and per call start",
+                "__device__ __forceinline__ void prb_hist_push(PrbThread& T, const double t, const double (&y)[PRB_NS]) {",
+                "    const long long s = T.hn % T.hcap;",
+                "    T.ht[s * T.B] = t;",
+                "    double* __restrict__ H = T.hy + s * (long long)PRB_NH * T.B;"]
+        push += [f"    H[{k}LL * T.B] = y[{e}];" for k, e in enumerate(rhs.hist_vars)]
+        push += ["    ++T.hn;", "}"]
+        init.append("\n".join(push))
     init.append("__device__ __forceinline__ void prb_thread_exit(PrbThread&, const prb_kernel_args&, long long) {}")
     src.append("\n".join(init))
     if body and body[0].startswith("// PRB_LIT = {"):
@@ -440,10 +549,11 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
 
     ring_init = np.concatenate([r.init.reshape(-1) for r in rhs.rings]) if rhs.rings else np.zeros(0)
     tabs = np.concatenate([np.asarray(t.value, dtype=np.float64).reshape(-1) for t in rhs.tables]) if rhs.tables else np.zeros(0)
-    evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4, "scipy": 6, "rk45": 6}[solver]
+    evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4, "scipy": 6, "rk45": 6, "dopri5_dde": 6}[solver]
     if adaptive and rk_method == "RK23":
         evals = 3
     return InstKernel("\n".join(src) + "\n", ns, np_, len(rhs.slots), len(observers), int(ring_init.size), ring_init,
                       [r.rolls_per_eval for r in rhs.rings], [r.length for r in rhs.rings], tabs,
+                      n_hist, hist_depth, list(rhs.hist_vars),
                       np.array([s[2] for s in rhs.slots], dtype=np.float64),
                       np.array([p.default for p in rhs.params], dtype=np.float64), block, solver, precision, evals)

@@ -44,15 +44,19 @@ class InstanceModel:
         self.prog = prog
         self.solver = solver
         self.adaptive = solver in ADAPTIVE_SOLVERS
-        self.rk_method = (rk_method or "RK45") if self.adaptive else None     # solve_ivp's `method` (compile-time tableau)
-        if self.adaptive and self.rk_method not in ("RK45", "RK23"):
+        # delay-differential models: the reference integrates them with scipy.integrate.ode('dopri5') and ignores `method`
+        # and the tolerances (BaseBackend._solve_scipy_dde, base_backend.py:771-800)
+        self.dde = prog.is_dde
+        self.rk_method = (rk_method or "RK45") if (self.adaptive and not self.dde) else None     # solve_ivp's `method`
+        if self.adaptive and not self.dde and self.rk_method not in ("RK45", "RK23"):
             raise rt.CudaBackendError(f"solver='scipy' on the CUDA backend implements method='RK45' (SciPy's default) and "
                                       f"'RK23'; got method={self.rk_method!r}")
         self.precision = "float32" if prog.real_dtype == np.float32 else "float64"      # complex64/128 -> real pairs
         self.real = prog.real_dtype
         self.rhs: ScalarRhs = scalarize(prog, sweep, max_nodes=max_nodes)
         self.observers = list(range(prog.n_state)) if observers is None else [int(o) for o in observers]
-        self.kernel: InstKernel = emit_inst_kernel(self.rhs, solver=solver, precision=self.precision,
+        self.kernel_solver = "dopri5_dde" if (self.adaptive and self.dde) else solver
+        self.kernel: InstKernel = emit_inst_kernel(self.rhs, solver=self.kernel_solver, precision=self.precision,
                                                    observers=self.observers, block=block,
                                                    const_div_to_mul=const_div_to_mul, min_blocks=min_blocks,
                                                    fast_math=fast_math, rk_method=self.rk_method or "RK45")
@@ -60,11 +64,17 @@ class InstanceModel:
         self._module: Optional[rt.Module] = None
         t0 = np.asarray(prog.arg_by_kind("t").value)
         self.t0 = float(t0) if self.adaptive else int(t0)
+        # history of delay-differential models: entry 0 is the float64 initial state the reference builds its DDEHistory
+        # from (computegraph.py:471-478), which is NOT rounded to the model precision
+        self.hist_y0 = np.zeros(0)
+        if self.kernel.n_hist:
+            h0 = np.asarray(next(a.value for a in prog.args if a.kind == "hist"), dtype=np.float64).reshape(-1)
+            self.hist_y0 = h0[self.kernel.hist_vars]
 
     @property
     def module(self) -> rt.Module:
         if self._module is None:
-            self._module = rt.compile_module(self.kernel.source, f"prb_inst_{self.solver}.cu", fmad=self.fmad)
+            self._module = rt.compile_module(self.kernel.source, f"prb_inst_{self.kernel_solver}.cu", fmad=self.fmad)
         return self._module
 
     @property
@@ -122,6 +132,9 @@ class InstanceSession:
         self.d_rings = rt.DeviceBuffer(max(k.ring_elems * B * r, 8))
         self.d_tables = rt.DeviceBuffer.from_host(np.asarray(k.table_values, dtype=model.real)) \
             if k.table_values.size else rt.DeviceBuffer(8)
+        # delay-differential models, fixed-step solvers: ring [hist_depth][n_hist][B] of past states (the adaptive path
+        # sizes its (time, state) ring per run, launch_adaptive)
+        self.d_hist = rt.DeviceBuffer(k.hist_depth * k.n_hist * B * r) if (k.n_hist and k.hist_depth) else None
         self.steps_done = 0
         self.samples_done = 0
 
@@ -129,7 +142,10 @@ class InstanceSession:
     def reset(self, y0: Optional[np.ndarray] = None, params: Optional[np.ndarray] = None):
         """(Re-)initialise state, parameters, slots and ring buffers; host->device copies."""
         k, B, real = self.m.kernel, self.B, self.m.real
+        y0_given = None if y0 is None else np.asarray(y0)
         y0 = self.m.prog.y0 if y0 is None else np.asarray(y0)
+        if y0_given is not None and y0_given.ndim == 1:
+            y0_given = np.repeat(y0_given[:, None], B, axis=1)
         if y0.ndim == 1:
             y0 = np.repeat(y0.astype(real)[:, None], B, axis=1)
         if y0.shape != (k.n_state, B):
@@ -143,6 +159,11 @@ class InstanceSession:
             self.d_slots.upload(np.repeat(k.slot_init.astype(real)[:, None], B, axis=1), self.stream)
         if k.ring_elems:
             self.d_rings.upload(np.repeat(k.ring_init.astype(real)[:, None], B, axis=1), self.stream)
+        if self.d_hist is not None:
+            h = np.zeros((k.hist_depth, k.n_hist, B), dtype=real)
+            h[0] = (self.m.hist_y0.astype(real)[:, None] if y0_given is None
+                    else np.ascontiguousarray(y0_given, dtype=real)[k.hist_vars])          # entry 0: the state at t0
+            self.d_hist.upload(h, self.stream)
         self.steps_done = 0
         self.samples_done = 0
 
@@ -182,6 +203,12 @@ class InstanceSession:
         a.y, a.out, a.params = self.d_y.ptr, (out.ptr if out is not None else self.d_out.ptr), self.d_params.ptr
         a.slots, a.rings, a.tables = self.d_slots.ptr, self.d_rings.ptr, self.d_tables.ptr
         a.consts = a.iconsts = a.work = a.sync = None
+        if self.d_hist is not None:
+            hdt = self.m.rhs.hist_dt
+            if abs(float(dt) - hdt) > 1e-9 * hdt:
+                raise rt.CudaBackendError(f"this delay-differential vector field was generated for step_size={hdt!r} (its history "
+                                          f"lookups are `hist(t*{hdt!r} - d)`); got dt={dt!r}")
+            a.work = self.d_hist.ptr
         self.m.module.run(k.kernel_name, a, block=k.block, stream=self.stream)
         self.steps_done += int(n_steps)
         self.samples_done += new_samples
@@ -192,6 +219,8 @@ class InstanceSession:
         """The whole adaptive integration of every instance in one launch: solve_ivp(method='RK45', first_step=dt,
         t_eval=linspace(0, T, round(T/dts), endpoint=False)) per instance, each thread with its own step sequence.
         Raises when an instance fails (step size underflow), like a failed solve_ivp would break the reference's run."""
+        if self.m.dde:
+            return self._launch_dopri5_dde(T, dt, dts)
         if method is not None and method != self.m.rk_method:
             raise rt.CudaBackendError(f"this model was compiled for method={self.m.rk_method!r}; build it with "
                                       f"rk_method={method!r} (the tableau is a compile-time constant of the kernel)")
@@ -232,6 +261,67 @@ class InstanceSession:
                                       f"{why.get(int(status[bad[0]]), 'unknown')}")
         return n_samples
 
+    def _launch_dopri5_dde(self, T: float, dt: float, dts: Optional[float] = None, *, nsteps: int = 50000,
+                           capacity: Optional[int] = None, max_capacity_bytes: int = 8 << 30):
+        """BaseBackend._solve_scipy_dde (base_backend.py:771-800) for every instance in one launch: dopri5 (rtol 1e-6, atol
+        1e-12, first_step=dt, nsteps=50000) restarted per sample interval, accepted steps appended to the device history.
+        The history is a ring of ``capacity`` (time, state) entries per instance; a run that needs an entry that was
+        already overwritten reports status 3 and is repeated with a ring twice as large."""
+        k, B = self.m.kernel, self.B
+        step = dts if dts else dt
+        n_samples = int(round(T / step))
+        if n_samples > self.n_samples:
+            raise ValueError(f"session holds {self.n_samples} samples, the run records {n_samples}")
+        te_step = (float(T) - 0.0) / n_samples if n_samples else 0.0
+        dmax = max(self.m.rhs.hist_delays)
+        if capacity is None:
+            per_interval = 2 + min(int(np.ceil(te_step / dt)) if dt > 0 else 1, 8)
+            capacity = max(256, int(2 * (np.ceil(dmax / max(te_step, 1e-300)) + 2) * per_interval))
+        y_start = np.empty((k.n_state, B), dtype=self.m.real)
+        self.d_y.download(y_start, self.stream)
+        if self.stream is not None:
+            self.stream.synchronize() if hasattr(self.stream, "synchronize") else rt.synchronize()
+        self.d_status = rt.DeviceBuffer(4 * B)
+        while True:
+            if capacity * (1 + k.n_hist) * B * 8 > max_capacity_bytes:
+                raise rt.CudaBackendError(f"the state history of this delay-differential run needs more than "
+                                          f"{max_capacity_bytes >> 20} MiB (capacity {capacity} entries x {B} instances)")
+            opts = np.concatenate([[1e-6, 1e-12, self.m.t0, float(T), float(dt), te_step, 0.0, float(nsteps), float(capacity)],
+                                   self.m.hist_y0])
+            d_opts = rt.DeviceBuffer.from_host(opts)
+            d_work = rt.DeviceBuffer(capacity * (1 + k.n_hist) * B * 8)
+            try:
+                self.d_status.zero(self.stream)
+                a = rt.KernelArgs()
+                a.n_steps, a.store_step, a.step0, a.t0, a.eval0 = n_samples, 1, 0, 0, 0
+                a.n_inst, a.sample0, a.dt = B, 0, float(dt)
+                a.y, a.out, a.params = self.d_y.ptr, self.d_out.ptr, self.d_params.ptr
+                a.slots, a.rings, a.tables = self.d_slots.ptr, self.d_rings.ptr, self.d_tables.ptr
+                a.consts, a.sync, a.work = d_opts.ptr, self.d_status.ptr, d_work.ptr
+                a.iconsts = None
+                self.m.module.run(k.kernel_name, a, block=k.block, stream=self.stream)
+                status = np.zeros(B, dtype=np.uint32)
+                self.d_status.download(status, self.stream)
+                if self.stream is not None:
+                    self.stream.synchronize() if hasattr(self.stream, "synchronize") else rt.synchronize()
+            finally:
+                d_opts.free()
+                d_work.free()
+            self.hist_capacity = capacity
+            if not np.any((status & 15) == 3):
+                break
+            capacity *= 2                                   # history ring too small: restart from the initial state
+            self.d_y.upload(y_start, self.stream)
+        self.samples_done = n_samples
+        self.attempts = (status >> 4).astype(np.int64)        # dopri5 steps (accepted + rejected) per instance
+        status = status & 15
+        if status.any():
+            bad = np.nonzero(status)[0]
+            why = {1: "step size becomes too small", 2: "larger nsteps is needed"}
+            raise rt.CudaBackendError(f"adaptive integration (dopri5) failed for {bad.size} instance(s), first {int(bad[0])}: "
+                                      f"{why.get(int(status[bad[0]]), 'unknown')}")
+        return n_samples
+
     # -- results
     def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Recorded observers as ``[n_samples, n_obs, B]`` (row k = state at step k*store_step)."""
@@ -253,7 +343,7 @@ class InstanceSession:
         return y
 
     def free(self):
-        for n in ("d_y", "d_out", "d_params", "d_slots", "d_rings", "d_tables", "d_opts", "d_status"):
+        for n in ("d_y", "d_out", "d_params", "d_slots", "d_rings", "d_tables", "d_opts", "d_status", "d_hist"):
             b = getattr(self, n, None)
             if b is not None:
                 b.free()
@@ -266,6 +356,7 @@ def evaluate_rhs(prog: Program, t: Optional[float] = None) -> np.ndarray:
     m = InstanceModel(prog, solver="scipy" if float_time else "euler")
     s = m.session(1, 0)
     d_dy = rt.DeviceBuffer(max(m.n_state, 1) * np.dtype(m.real).itemsize)
+    d_extra = []
     try:
         s.reset()
         a = rt.KernelArgs()
@@ -273,10 +364,18 @@ def evaluate_rhs(prog: Program, t: Optional[float] = None) -> np.ndarray:
         a.t0, a.dt = (0, float(m.t0 if t is None else t)) if float_time else (int(m.t0), 0.0)
         a.y, a.out, a.params = s.d_y.ptr, d_dy.ptr, s.d_params.ptr
         a.slots, a.rings, a.tables = s.d_slots.ptr, s.d_rings.ptr, s.d_tables.ptr
+        if m.kernel.n_hist and float_time:          # history = the initial condition only (a fresh DDEHistory)
+            d_extra.append(rt.DeviceBuffer.from_host(np.concatenate([[0, 0, m.t0, 0, 0, 0, 0, 0, 1.0], m.hist_y0])))
+            d_extra.append(rt.DeviceBuffer((1 + m.kernel.n_hist) * 8))
+            a.consts, a.work = d_extra[0].ptr, d_extra[1].ptr
+        elif m.kernel.n_hist:
+            a.work, a.dt = s.d_hist.ptr, float(m.rhs.hist_dt)
         m.module.run("prb_rhs_eval", a, block=m.kernel.block)
         dy = np.empty(m.n_state, dtype=m.real)
         d_dy.download(dy)
         return dy
     finally:
         d_dy.free()
+        for d in d_extra:
+            d.free()
         s.free()

@@ -33,9 +33,10 @@ class Arg:
     """One entry of the generated function's signature ``(t, y, dy, *constants)``.
 
     ``kind``: 't' (step counter / time), 'y' (state vector), 'dy' (vector-field buffer),
-    'const' (read-only parameter / index array / input table) or 'var' (mutable non-state
+    'const' (read-only parameter / index array / input table), 'var' (mutable non-state
     buffer that persists across rhs evaluations because the reference mutates it in place,
-    e.g. delay ring buffers, pyrates/ir/circuit.py:400-425).
+    e.g. delay ring buffers, pyrates/ir/circuit.py:400-425) or 'hist' (the state-history callable of
+    delay-differential models, base_backend.py:88-177; its value is the initial state it starts from).
     """
     name: str
     kind: str
@@ -96,6 +97,10 @@ class Program:
         return y
 
     @property
+    def is_dde(self) -> bool:
+        return any(a.kind == "hist" for a in self.args)
+
+    @property
     def real_dtype(self):
         return np.float32 if self.float_precision in ("float32", "complex64") else np.float64
 
@@ -139,13 +144,19 @@ class Program:
             else:
                 raise NotImplementedError(f"unsupported assignment target: {ast.unparse(tgt)}")
         out_args = []
+        has_hist = len(sig) > 2 and sig[2] == "hist"       # DDE signature: (t, y, hist, dy, ...) base_backend.py:505-509
         for i, (name, (aname, val)) in enumerate(zip(sig, args)):
+            if has_hist and i == 2:
+                # the history callable does not travel; its value is the float64 initial state it was built from
+                # (ComputeGraph.to_func: get_hist_func(np.asarray(state_vec[:])), computegraph.py:471-478)
+                out_args.append(Arg(name, "hist", np.array(getattr(val, "_y", [args[1][1]])[0], dtype=np.float64, copy=True)))
+                continue
             val = np.asarray(val)
             if i == 0:
                 kind = "t"
             elif i == 1:
                 kind = "y"
-            elif i == 2:
+            elif i == (3 if has_hist else 2):
                 kind = "dy"
             else:
                 kind = "var" if name in assigned else "const"

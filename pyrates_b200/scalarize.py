@@ -370,6 +370,11 @@ class ScalarRhs:
     slots: List[Tuple[str, int, float]]            # persistent slots: (arg, elem, init)
     slot_writes: List[Tuple[int, int]]             # (slot, node)
     uses_t: bool = False
+    # delay-differential models (`hist(t*dt - d)[idx]` lookups, base_backend.py:437-444): state elements whose history is
+    # kept, every delay that is looked up, and the step size baked into the fixed-step query text (None: adaptive form)
+    hist_vars: List[int] = field(default_factory=list)
+    hist_delays: List[float] = field(default_factory=list)
+    hist_dt: Optional[float] = None
 
     def live_nodes(self) -> List[int]:
         """Topologically ordered ids of all nodes reachable from the outputs."""
@@ -443,6 +448,10 @@ class _Interp:
         self.slots: List[Tuple[str, int, float]] = []
         self.slot_arrays: Dict[str, np.ndarray] = {}
         self.uses_t = False
+        self.hist_vars: List[int] = []
+        self.hist_delays: List[float] = []
+        self.hist_dt: Optional[float] = None
+        self.hist_name = next((a.name for a in prog.args if a.kind == "hist"), None)
         self.tname = prog.arg_by_kind("t").name
         self.yname = prog.arg_by_kind("y").name
         self.dyname = prog.arg_by_kind("dy").name
@@ -475,6 +484,8 @@ class _Interp:
                 arr = np.empty(v.size, dtype=object)
                 arr[:] = None
                 self.env[a.name] = arr
+            elif a.kind == "hist":
+                self.env[a.name] = None                          # only ever called: hist(t - d)[idx]
             elif a.name in self.interp_args:
                 if a.kind != "const" or any(n == a.name for n, _ in sweep):
                     raise UnsupportedModelError(f"interpolation table `{a.name}` must be a constant that is not swept")
@@ -740,8 +751,8 @@ class _Interp:
         if fname == "index_1d":
             return self._arr(args[0])[self._index_value(args[1])]
         if fname in ("past", "hist"):
-            raise UnsupportedModelError("delay-differential `past()` terms need the adaptive DDE path, which the CUDA "
-                                        "backend does not implement")
+            raise UnsupportedModelError(f"unsupported delay-differential term `{ast.unparse(n)}` (expected the generated form "
+                                        f"`hist(t - d)[idx]`)")
         if fname == "randn":
             raise UnsupportedModelError("stochastic `randn` terms are not supported by the CUDA backend")
         raise UnsupportedModelError(f"function `{fname}` is not supported by the CUDA backend")
@@ -773,7 +784,65 @@ class _Interp:
             return None
         return self._index_value(self.ev(sl))
 
+    def _hist_read(self, n: ast.Subscript):
+        """``hist(t*dt - d)[idx]`` (fixed-step solvers, integer step counter t) / ``hist(t - d)[idx]`` (adaptive):
+        the delayed value of state element(s) idx, linearly interpolated in the recorded history (DDEHistory.__call__,
+        base_backend.py:165-177).  One 'hist' leaf per (state element, delay); the delay must be a compile-time constant."""
+        g = self.g
+        call = n.value
+        if self.complex:
+            raise UnsupportedModelError("delay-differential terms in complex-valued builds")
+        if len(call.args) != 1 or call.keywords or not isinstance(call.args[0], ast.BinOp) or not isinstance(call.args[0].op, ast.Sub):
+            raise UnsupportedModelError(f"unsupported history lookup `{ast.unparse(n)}`")
+        tq, dl = call.args[0].left, call.args[0].right
+        scale = None
+        if isinstance(tq, ast.BinOp) and isinstance(tq.op, ast.Mult) and isinstance(tq.left, ast.Name) \
+                and isinstance(tq.right, ast.Constant) and isinstance(tq.right.value, float):
+            scale, tq = float(tq.right.value), tq.left
+        if not (isinstance(tq, ast.Name) and tq.id == self.tname):
+            raise UnsupportedModelError(f"unsupported history lookup `{ast.unparse(n)}`")
+        t_is_int = bool(g.isint[self.env[self.tname][()].id])
+        if (scale is None) == t_is_int:
+            raise UnsupportedModelError(f"history lookup `{ast.unparse(n)}` does not match the solver's time argument")
+        self.uses_t = True
+        # NumPy promotion of `t - d` in the reference: a named (array-typed) delay is strong, a literal is a Python float
+        strong = not isinstance(dl, ast.Constant)
+        dv = self.ev(dl)
+        if isinstance(dv, (int, np.integer)):
+            dval = float(dv)
+        else:
+            dv = self._arr(dv)
+            dv = dv[()] if isinstance(dv, np.ndarray) and dv.ndim == 0 else (dv.reshape(-1)[0] if isinstance(dv, np.ndarray) and dv.size == 1 else dv)
+            if not isinstance(dv, Sym) or not g.is_const(dv.id):
+                raise UnsupportedModelError("history delays must be constants (not swept, not state-dependent)")
+            dval = float(g.const_value(dv.id))
+        if not (dval >= 0.0) or not math.isfinite(dval):
+            raise UnsupportedModelError(f"history delay {dval!r}")
+        if scale is not None:
+            if self.hist_dt is not None and self.hist_dt != scale:
+                raise UnsupportedModelError("history lookups with different step sizes")
+            self.hist_dt = scale
+        idx = self._index(n.slice)
+        n_state = int(np.asarray(self.p.arg_by_kind("y").value).size)
+        elems = np.arange(n_state)[idx]
+
+        def one(e):
+            e = int(e)
+            if e not in self.hist_vars:
+                self.hist_vars.append(e)
+            if dval not in self.hist_delays:
+                self.hist_delays.append(dval)
+            return g._node("hist", (), (self.hist_vars.index(e), scale, float(dval).hex(), strong))
+        if np.ndim(elems) == 0:
+            return _obj(one(elems))
+        out = np.empty(elems.shape, dtype=object)
+        for k, e in enumerate(elems.reshape(-1)):
+            out.reshape(-1)[k] = one(e)
+        return out
+
     def subscript(self, n: ast.Subscript):
+        if isinstance(n.value, ast.Call) and getattr(n.value.func, "id", None) == "hist" and self.hist_name == "hist":
+            return self._hist_read(n)
         base = self.ev(n.value)
         if isinstance(base, _Table):
             return self._table_read(base, n.slice)
@@ -890,7 +959,7 @@ class _Interp:
                 raise UnsupportedModelError("complex derivative in a real-valued build")
             n_out, dy_ids = dy.size, [g.lift(x).id for x in dy]
         out = ScalarRhs(g, n_out, dy_ids, self.params, self.tables, [r.spec for r in self.rings],
-                        ring_writes, self.slots, [], self.uses_t)
+                        ring_writes, self.slots, [], self.uses_t, list(self.hist_vars), list(self.hist_delays), self.hist_dt)
         # persistent slots: store back only if any evaluation can observe an incoming value
         slot_final = {}
         for name, arr in self.slot_arrays.items():

@@ -15,6 +15,7 @@ class DagMachine:
         self.slots = np.array([s[2] for s in rhs.slots], dtype=real)
         self.params = np.array([p.default for p in rhs.params], dtype=real)
         self.order = rhs.live_nodes()
+        self.hist = None              # delay-differential programs: oracle History over the FULL state (set by the drivers)
 
     def eval(self, t, y):
         g, real = self.rhs.graph, self.real
@@ -32,7 +33,18 @@ class DagMachine:
                 elif op == "slot":
                     val[i] = self.slots[g.payload[i]]
                 elif op == "t":
-                    val[i] = int(t)
+                    val[i] = int(t) if g.isint[i] else float(t)
+                elif op == "hist":
+                    # the reference-generated lookup hist(t*dt - d)[idx] / hist(t - d)[idx] (base_backend.py:437-444)
+                    hv, scale, dhex, strong = g.payload[i]
+                    d = float.fromhex(dhex)
+                    if scale is not None:
+                        tq = int(t) * scale - d
+                    elif strong and real is np.float32:
+                        tq = float(np.float32(t) - np.float32(d))
+                    else:
+                        tq = float(t) - d
+                    val[i] = real(self.hist(tq)[self.rhs.hist_vars[hv]])
                 elif op == "table":
                     tab, tnode, col, ncols = g.payload[i]
                     arr = np.asarray(self.rhs.tables[tab].value).reshape(-1)
@@ -67,11 +79,14 @@ class DagMachine:
             self.slots[slot] = val[node]
         return dy
 
-    def euler(self, y0, t0, n_steps, dt, store_step=1):
+    def euler(self, y0, t0, n_steps, dt, store_step=1, hist=None):
         y = np.array(y0, dtype=self.real)
+        self.hist = hist
         rec = []
         for i in range(n_steps):
             if i % store_step == 0:
                 rec.append(y.copy())
             y = y + self.real(dt) * self.eval(i + t0, y)
+            if hist is not None:
+                hist.update((i + 1) * dt, y)
         return np.array(rec)

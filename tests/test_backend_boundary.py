@@ -66,6 +66,55 @@ def test_cuda_backend_records_same_program_as_numpy_backend(registered, name, pa
 
 
 @needs_ref
+@pytest.mark.parametrize("name,solver", [("dde_net16", "euler"), ("dde_net16_dopri5", "scipy"), ("dde_net10_dopri5", "scipy")])
+def test_cuda_backend_records_delay_differential_programs(registered, name, solver):
+    """`x(t-d)` terms / delayed edges under an adaptive solver: ComputeGraph.to_func drives add_var_hist and asks for the
+    `hist` argument (computegraph.py:424-450, 471-478); the recorded program (history lookups first, `(t, y, hist, dy, ..)`
+    signature, float64 initial condition as the history's value) is the one the NumPy backend printed."""
+    from pyrates import clear
+    path = "model_templates.test_resources.test_backend." + name.split("_")[1]
+    c = _fresh(path)
+    fx = orc.load_fixture(golden_path(name))
+    func, args, names, svmap = c.get_run_func("vector_field", step_size=fx["run"]["dt"], backend="cuda", solver=solver,
+                                              float_precision="float64", verbose=False, vectorize=False)
+    prog = func.program(args)
+    gold = Program.load(golden_path(name))
+    assert prog.is_dde and names[2] == "hist"
+    assert _norm(prog.stmts) == _norm(gold.stmts)
+    assert [(a.name, a.kind) for a in prog.args] == [(a.name, a.kind) for a in gold.args]
+    for a, b in zip(prog.args, gold.args):
+        assert a.value.dtype == b.value.dtype and np.array_equal(a.value, b.value), a.name
+    with pytest.raises(Exception, match="lives on the device"):
+        args[2](0.0)
+    clear(c)
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("path,out,solver,precision,T,dts", [
+    ("net16", "p1/op_dde/x", "euler", "float64", 0.5, 1e-3),       # the reference's own DDE test (test_2_8_dde)
+    ("net16", "p1/op_dde/x", "heun", "float32", 0.5, 2e-3),
+    ("net16", "p1/op_dde/x", "scipy", "float64", 2.0, 1e-2),
+    ("net16", "p1/op_dde/x", "scipy", "float32", 2.0, 1e-2),
+    ("net10", "pop0/op8/a", "scipy", "float64", 3.0, 5e-2),        # delayed edges under an adaptive solver -> DDE
+])
+def test_delay_differential_models_match_numpy_backend(gpu, registered, path, out, solver, precision, T, dts):
+    """CircuitTemplate.run on delay-differential models: `x(t-d)` notation with fixed-step solvers (history ring on the
+    device) and solver='scipy' (dopri5 + growing history, BaseBackend._solve_scipy_dde) vs the reference NumPy backend."""
+    kw = dict(simulation_time=T, step_size=1e-3, sampling_step_size=dts, solver=solver, outputs={"o": out}, verbose=False,
+              float_precision=precision, clear=True, vectorize=False)
+    model = "model_templates.test_resources.test_backend." + path
+    ref = _fresh(model).run(backend="default", **kw)
+    got = _fresh(model).run(backend="cuda", **kw)
+    assert got.shape == ref.shape and got.values.dtype == ref.values.dtype
+    assert traj_rel_err(got.values, ref.values) <= RTOL[precision]
+    if path == "net16" and solver == "euler":
+        x = got["o"].values.squeeze()                 # the assertions of tests/test_backend_simulations.py:568-583
+        np.testing.assert_allclose(x[:100], 1.0 - np.arange(100) * 1e-3, atol=5e-3)
+        assert x[0] == pytest.approx(1.0, abs=1e-5) and np.all(np.abs(x) < 5.0)
+
+
+@needs_ref
 def test_new_solver_names_are_fixed_step(registered):
     import pyrates.frontend.template.circuit as fc
     assert not fc.is_integration_adaptive("rk4") and not fc.is_integration_adaptive("heun_true")

@@ -9,7 +9,10 @@ from pyrates_b200.engine import InstanceModel
 from pyrates_b200.program import Program
 
 CASES = [("qif", "euler"), ("qif_f32", "heun"), ("jrc", "rk4"), ("net12", "heun_true"), ("qif_input", "rk4"),
-         ("jrc_2delay", "euler"), ("qsfa_both_n8", "heun")]
+         ("jrc_2delay", "euler"), ("qsfa_both_n8", "heun"),
+         # delay-differential models: history ring (fixed step) / dopri5 + (time, state) history (solver='scipy')
+         ("dde_mg", "rk4"), ("dde_net16_f32", "heun"), ("dde_mg_dopri5", "scipy"), ("dde_net16_dopri5_f32", "scipy"),
+         ("dde_jrc_pair_dopri5", "scipy")]
 
 
 @pytest.mark.parametrize("name,solver", CASES)
@@ -31,6 +34,23 @@ def test_jrc_rk4_stays_in_registers():
     mod = rt.compile_module(m.kernel.source, "jrc_rk4.cu", verbose_ptxas=True)
     line = [l for l in mod.log.splitlines() if "spill" in l][-1]
     assert "0 bytes spill stores" in line and "0 bytes stack frame" in line, mod.log
+
+
+def test_delay_differential_kernels_carry_a_history():
+    fixed = InstanceModel(Program.load(golden_path("dde_mg")), solver="euler")
+    k = fixed.kernel
+    # delays 0.0173 / 0.0091 at dt = 1e-4: 173 steps back, interpolation needs two neighbours -> ring of 256 steps
+    assert k.n_hist == 2 and k.hist_vars == [0, 1] and k.hist_depth == 256 and fixed.rhs.hist_dt == 1e-4
+    assert "prb_hist_push(T, y, A.step0 + i + 1)" in k.source and "#define PRB_SOLVER 0" in k.source
+    adaptive = InstanceModel(Program.load(golden_path("dde_mg_dopri5")), solver="scipy")
+    assert adaptive.kernel_solver == "dopri5_dde" and adaptive.kernel.hist_depth == 0 and "#define PRB_SOLVER 5" in adaptive.kernel.source
+    assert list(adaptive.hist_y0) == [1.2, 0.4]
+    # a vector field generated for the other solver family is refused (its history lookups use the other time argument)
+    from pyrates_b200.scalarize import UnsupportedModelError
+    with pytest.raises(UnsupportedModelError):
+        InstanceModel(Program.load(golden_path("dde_mg")), solver="scipy")
+    with pytest.raises(UnsupportedModelError):
+        InstanceModel(Program.load(golden_path("dde_mg_dopri5")), solver="heun")
 
 
 def test_unknown_solver_is_rejected():

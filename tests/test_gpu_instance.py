@@ -16,7 +16,8 @@ pytestmark = pytest.mark.gpu
 SKIP = {"kuramoto_n128", "qsfa_both_n96", "wc_n128", "wc_n128_f32", "jrc_grid_b1024", "wc_n300_f32",
         "qsfa_both_n96_f32", "kuramoto_n128_f32", "wc_n128_rk45", "kuramoto_n128_rk45"}                                             # network-mode fixtures
 ADAPTIVE = [n for n in golden_names() if ("_rk45" in n or "_rk23" in n) and n not in SKIP]
-NAMES = [n for n in golden_names() if n not in SKIP and n not in ADAPTIVE]
+DDE_ADAPTIVE = [n for n in golden_names() if "_dopri5" in n]
+NAMES = [n for n in golden_names() if n not in SKIP and n not in ADAPTIVE and n not in DDE_ADAPTIVE]
 SOLVERS = ["euler", "heun", "heun_true", "rk4"]
 
 
@@ -112,6 +113,74 @@ def test_adaptive_rk45_matches_reference_scipy(gpu, name):
     # fixture is compared at the solver's own accuracy; the interpolation itself is pinned by the rhs test below
     tol = 1e-3 if name == "qif_input_rk45" else 1e-9
     assert traj_rel_err(out[:, :, 0], ref) <= tol, name
+
+
+@pytest.mark.parametrize("name", DDE_ADAPTIVE)
+def test_adaptive_dde_dopri5_matches_reference(gpu, name):
+    """Delay-differential models with solver='scipy' (BaseBackend._solve_scipy_dde, base_backend.py:771-800): dopri5 restarted
+    per sample interval, accepted steps appended to the device-side history the rhs interpolates in — vs the trajectories of
+    the real reference + scipy.integrate.ode."""
+    fx = orc.load_fixture(golden_path(name))
+    r = fx["run"]
+    prog = Program.load(golden_path(name))
+    assert prog.is_dde
+    before = rt.launch_count()
+    m = InstanceModel(prog, solver="scipy")
+    out, _ = m.run(r["T"], r["dt"], r["dts"])
+    assert rt.launch_count() == before + 1
+    ref = fx["extra"]["rec_scipy"]
+    assert out[:, :, 0].shape == ref.shape
+    # accept/reject decisions are discrete: fp64 rounding differences (FMA contraction) stay at 1e-12, the float32 build is
+    # compared at the north star's float32 tolerance
+    assert traj_rel_err(out[:, :, 0], ref) <= RTOL[prog.float_precision], name
+
+
+def test_adaptive_dde_history_ring_grows_when_too_small(gpu):
+    """A history ring that is too small for the delay window is detected on the device (status 3) and the run repeated with a
+    larger one: same trajectory."""
+    name = "dde_net10_dopri5"
+    fx = orc.load_fixture(golden_path(name))
+    r = fx["run"]
+    m = InstanceModel(Program.load(golden_path(name)), solver="scipy")
+    n_samples = int(round(r["T"] / r["dts"]))
+    s = m.session(1, n_samples)
+    try:
+        s.reset()
+        s._launch_dopri5_dde(r["T"], r["dt"], r["dts"], capacity=4)
+        assert s.hist_capacity > 4
+        out = s.download()
+    finally:
+        s.free()
+    assert traj_rel_err(out[:, :, 0], fx["extra"]["rec_scipy"]) <= 1e-9
+
+
+def test_dde_batch_of_instances_and_chunked_launches(gpu):
+    """Every instance keeps its own history; launches that continue from the device-resident history == one launch."""
+    name = "dde_mg"
+    fx = orc.load_fixture(golden_path(name))
+    r = fx["run"]
+    prog = Program.load(golden_path(name))
+    steps, store_step, n_samples = n_steps_for(r["T"], r["dt"], r["dts"])
+    m = InstanceModel(prog, solver="heun")
+    B = 67
+    s = m.session(B, n_samples)
+    try:
+        s.reset()
+        cut = (steps // 3) | 1
+        s.launch(cut, r["dt"], store_step)
+        s.launch(steps - cut, r["dt"], store_step)
+        got = s.download()
+    finally:
+        s.free()
+    for b in (0, 31, 66):
+        assert traj_rel_err(got[:, :, b], fx["extra"]["rec_heun"]) <= 1e-9
+    with pytest.raises(rt.CudaBackendError):
+        s2 = m.session(1, n_samples)
+        try:
+            s2.reset()
+            s2.launch(10, 2 * r["dt"], store_step)        # the vector field was generated for another step size
+        finally:
+            s2.free()
 
 
 def test_interpolated_input_rhs_matches_numpy_interp(gpu):

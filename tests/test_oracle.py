@@ -8,6 +8,54 @@ from oracle import numpy_oracle as orc
 
 
 ADAPTIVE = [n for n in golden_names() if "_rk45" in n or "_rk23" in n]
+DDE_ADAPTIVE = [n for n in golden_names() if "_dopri5" in n]
+
+
+@pytest.mark.parametrize("name", DDE_ADAPTIVE)
+def test_oracle_dopri5_dde_reproduces_reference_plus_scipy_bit_exact(name):
+    """solver='scipy' on a delay-differential model: the restated Hairer DOPRI5 core, its restart per sample interval and the
+    history updates (BaseBackend._solve_scipy_dde + DDEHistory) give exactly what the real reference + scipy.integrate.ode
+    produced in the build container."""
+    fx = orc.load_fixture(golden_path(name))
+    rec, times = orc.run_fixture(fx, solver="scipy")
+    ref = fx["extra"]["rec_scipy"]
+    assert rec.shape == ref.shape and rec.dtype == ref.dtype and np.array_equal(rec, ref)
+
+
+def test_oracle_dopri5_matches_scipy_ode_on_a_plain_function():
+    """Without a history the restated core is scipy.integrate.ode('dopri5') itself, solout calls included."""
+    integ = pytest.importorskip("scipy.integrate")
+    f = lambda t, y: np.array([y[1], -4.0 * y[0] - 0.1 * y[1] + np.sin(3 * t)])
+    seen_ref, seen = [], []
+    solver = integ.ode(f).set_integrator("dopri5", first_step=1e-3, nsteps=50000)
+    solver.set_initial_value(np.array([1.0, 0.0]), 0.0)
+    solver.set_solout(lambda t, y: seen_ref.append((t, y.copy())) and None)
+    x, y = 0.0, np.array([1.0, 0.0])
+    for t_out in np.linspace(0.0, 3.0, 7):
+        solver.integrate(t_out)
+        x, y, ok = orc.dopri5_call(f, x, y, float(t_out), 1e-3, lambda t, y_: seen.append((t, y_.copy())))
+        assert ok and x == solver.t and np.array_equal(y, solver.y)
+    assert len(seen) == len(seen_ref) and all(a[0] == b[0] and np.array_equal(a[1], b[1]) for a, b in zip(seen, seen_ref))
+
+
+def test_oracle_history_is_the_references_ddehistory():
+    """Known answers of DDEHistory.__call__ (base_backend.py:165-177): initial condition before t0, latest state after the
+    last stored time, linear interpolation in between, the LAST of duplicated times as the left bracket; and the reference's
+    own DDE test (tests/test_backend_simulations.py:551-583): x' = -x(t-d) decays linearly while t < d."""
+    h = orc.History(np.array([1.0, -2.0]))
+    h.update(0.0, np.array([1.0, -2.0]))
+    h.update(0.5, np.array([2.0, 0.0]))
+    h.update(0.5, np.array([4.0, 4.0]))
+    h.update(1.0, np.array([6.0, 8.0]))
+    assert np.array_equal(h(-3.0), [1.0, -2.0]) and np.array_equal(h(0.0), [1.0, -2.0])
+    assert np.array_equal(h(0.25), [1.5, -1.0])
+    assert np.array_equal(h(0.5), [4.0, 4.0]) and np.array_equal(h(0.75), [5.0, 6.0])
+    assert np.array_equal(h(1.0), [6.0, 8.0]) and np.array_equal(h(7.0), [6.0, 8.0])
+    fx = orc.load_fixture(golden_path("dde_net16"))
+    rec, _ = orc.run_fixture(fx, solver="euler")
+    x = rec[:, 0]
+    np.testing.assert_allclose(x[:100], 1.0 - np.arange(100) * 1e-3, atol=5e-3)
+    assert np.all(np.abs(x) < 5.0)
 
 
 @pytest.mark.parametrize("name", ADAPTIVE)
@@ -45,7 +93,7 @@ def test_oracle_rk45_matches_solve_ivp_on_a_plain_function():
     assert 1e-6 < np.max(np.abs(quirk - ref)) < 1e-2
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names() if n not in ADAPTIVE])
+@pytest.mark.parametrize("name", [n for n in golden_names() if n not in ADAPTIVE and n not in DDE_ADAPTIVE])
 @pytest.mark.parametrize("solver", ["euler", "heun"])
 def test_oracle_reproduces_reference_bit_exact(name, solver):
     fx = orc.load_fixture(golden_path(name))
