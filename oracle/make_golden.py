@@ -431,16 +431,92 @@ def make_adaptive_case(name: str, spec: dict, cap: Capture) -> str:
     return path
 
 
+# Jacobian functions (ComputeGraph.get_jacobian_func, computegraph.py:516-763): the reference differentiates the vector field
+# symbolically and has the backend print `J0 = zeros((n, n)); J0[i, j] = expr; return J0`
+def _transcendental():
+    def build():
+        from pyrates import CircuitTemplate, NodeTemplate, OperatorTemplate
+        op = OperatorTemplate(name="trans_op", equations=["u' = -u + exp(-a*u) + cos(w)", "w' = -w + sin(u)"],
+                              variables={"u": "output(0.1)", "w": "variable(0.2)", "a": 1.5})      # tests/test_jacobian.py:185-192
+        return CircuitTemplate(name="trans_circ", nodes={"p": NodeTemplate(name="trans_pop", operators=[op])})
+    return build
+
+
+JACOBIAN_CASES = {
+    "jac_vdp":   dict(build=_yaml("model_templates.oscillators.vanderpol.vdp"), scale=1.0),
+    "jac_trans": dict(build=_transcendental(), scale=0.5),
+    "jac_jrc":   dict(build=_yaml(NM + "jansenrit.JRC"), scale=5e-3),
+    "jac_qif_sfa_f32": dict(build=_yaml(NM + "qif.qif_sfa"), scale=0.3, precision="float32"),
+}
+
+
+def make_jacobian_case(name: str, spec: dict, cap: Capture) -> str:
+    import ast
+    from pyrates import clear
+    from pyrates.ir.node import clear_ir_caches
+    from pyrates_b200.program import Arg, Stmt
+    precision = spec.get("precision", "float64")
+    clear_ir_caches()
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            circuit = spec["build"]()
+            func, args, names, sv = circuit.get_jacobian_func(func_name="jacobian", step_size=1e-3, solver="euler", in_place=False,
+                                                              clear=False, vectorize=False, backend="default",
+                                                              float_precision=precision, verbose=False)
+        finally:
+            os.chdir(cwd)
+    fdef = next(n for n in ast.parse(cap.source.replace("\t", "    ")).body if isinstance(n, ast.FunctionDef))
+    sig = [a.arg for a in fdef.args.args]
+    assert len(sig) == len(args) and sig[:2] == ["t", "y"]
+    stmts, jname, shape = [], None, None
+    for node in fdef.body:
+        if isinstance(node, ast.Return):
+            assert isinstance(node.value, ast.Name) and node.value.id == jname
+        elif isinstance(node.targets[0], ast.Name):              # J0 = zeros((n, n), dtype=...)
+            jname, shape = node.targets[0].id, tuple(ast.literal_eval(node.value.args[0]))
+        else:
+            full = ast.unparse(node.targets[0])
+            stmts.append(Stmt(jname, ast.unparse(node.value), full[len(jname) + 1:-1]))
+    n = shape[0]
+    pargs = [Arg("t", "t", np.asarray(0.0)), Arg("y", "y", np.asarray(args[1], dtype=precision)),
+             Arg(jname, "dy", np.zeros(shape, dtype=precision))]
+    pargs += [Arg(s_, "const", np.array(a, copy=True), lab) for s_, a, lab in zip(sig[2:], args[2:], names[2:])]
+    prog = Program(pargs, stmts, dict(sv), precision, "jacobian")
+    # the reference function at its own state and at 15 perturbed states (float64 states, as users pass them)
+    rng = np.random.default_rng(7)
+    y0 = np.asarray(args[1], dtype=np.float64)
+    pts = np.vstack([y0[None, :], y0[None, :] + spec["scale"] * rng.normal(size=(15, n))])
+    ref = np.stack([np.asarray(func(0.0, y.copy(), *args[2:])) for y in pts])
+    # the oracle executes the regenerated text (output buffer passed in instead of allocated inside): identical numbers
+    f2 = orc.build_vector_field(prog.source(), "jacobian")
+    mine = np.stack([np.array(f2(0.0, y.copy(), np.zeros(shape, dtype=precision), *args[2:])) for y in pts])
+    assert ref.dtype == mine.dtype and np.array_equal(ref, mine, equal_nan=True), f"{name}: oracle != reference Jacobian"
+    try:
+        clear(circuit)
+    except Exception:
+        pass
+    run_meta = {"kind": "jacobian", "precision": precision, "reference_version": "1.2.3", "solver": "euler", "T": 0.0, "dt": 1e-3,
+                "dts": None}
+    path = os.path.join(GOLDEN, f"{name}.npz")
+    prog.save(path, __run__=np.frombuffer(json.dumps(run_meta).encode(), dtype=np.uint8), jac_points=pts, jac_ref=ref)
+    return path
+
+
 def main(argv):
     warnings.filterwarnings("ignore")
     if import_reference() is None:
         raise SystemExit("reference PyRates not importable here; fixtures can only be regenerated in the build container")
     os.makedirs(GOLDEN, exist_ok=True)
-    names = argv or (list(CASES) + list(ADAPTIVE_CASES))
+    names = argv or (list(CASES) + list(ADAPTIVE_CASES) + list(JACOBIAN_CASES))
     cap = Capture()
     try:
         for n in names:
-            p = make_adaptive_case(n, ADAPTIVE_CASES[n], cap) if n in ADAPTIVE_CASES else make_case(n, CASES[n], cap)
+            if n in JACOBIAN_CASES:
+                p = make_jacobian_case(n, JACOBIAN_CASES[n], cap)
+            else:
+                p = make_adaptive_case(n, ADAPTIVE_CASES[n], cap) if n in ADAPTIVE_CASES else make_case(n, CASES[n], cap)
             print(f"{n:24s} -> {os.path.relpath(p, _ROOT)}  ({os.path.getsize(p) / 1024:.1f} KiB)")
     finally:
         cap.close()

@@ -22,6 +22,7 @@ There is no CPU fallback: unsupported ops / solvers raise, a missing GPU raises.
 from __future__ import annotations
 
 import os
+import re
 from typing import Callable, Dict, List, Optional, Tuple, Union
 
 import warnings
@@ -75,6 +76,9 @@ _OPS: Dict[str, Tuple[str, Callable]] = {
 }
 
 
+_YHIST = re.compile(r"^(_yhist_\w+) = hist\((.*)\)$")
+
+
 class CudaHistory:
     """Placeholder for ``DDEHistory`` (base_backend.py:88-177) in the argument tuple of a delay-differential vector field:
     carries the initial condition only.  It cannot be called on the host — there is no CPU execution path."""
@@ -93,14 +97,19 @@ class CudaVectorField:
     (pyrates/frontend/template/circuit.py:552-650)."""
 
     def __init__(self, backend: "CudaBackend", func_name: str, arg_names: List[str], stmts: List[Stmt],
-                 state_var: str, return_var: str):
+                 state_var: str, return_var: str, jacobian: Optional[Tuple[str, tuple]] = None):
         self.backend = backend
         self.__name__ = func_name
         self.arg_names = list(arg_names)
         self.stmts = list(stmts)
         self.state_var, self.return_var = state_var, return_var
+        # get_jacobian_func (computegraph.py:516-763): `J0 = zeros((n, n)); J0[i, j] = expr; return J0` — the signature has
+        # no output buffer, the (name, shape) of the locally allocated matrix is kept here instead
+        self.jacobian = jacobian
 
     def program(self, func_args) -> Program:
+        if self.jacobian is not None:
+            return self._jacobian_program(func_args)
         if len(func_args) != len(self.arg_names):
             raise ValueError(f"vector field takes {len(self.arg_names)} arguments, got {len(func_args)}")
         assigned = {s.lhs for s in self.stmts}
@@ -119,11 +128,50 @@ class CudaVectorField:
             args.append(Arg(name, kind, np.array(val, copy=True)))
         return Program(args, self.stmts, {}, self.backend._float_precision, self.__name__)
 
+    def _jacobian_program(self, func_args) -> Program:
+        name, shape, _ = self.jacobian
+        if len(func_args) != len(self.arg_names):
+            raise ValueError(f"Jacobian function takes {len(self.arg_names)} arguments, got {len(func_args)}")
+        prec = self.backend._float_precision
+        if "complex" in str(prec):
+            raise UnsupportedModelError("Jacobian functions of complex-valued builds")
+        args = []
+        for i, (n, val) in enumerate(zip(self.arg_names, func_args)):
+            if n == "hist" and i == 2:
+                y_init = getattr(val, "y0", getattr(val, "_y", [func_args[1]])[0])
+                args.append(Arg(n, "hist", np.array(y_init, dtype=np.float64, copy=True)))
+                continue
+            if callable(val):
+                raise UnsupportedModelError(f"callable argument `{n}` of the Jacobian function")
+            if i == 0:
+                args.append(Arg(n, "t", np.asarray(float(np.asarray(val)))))
+            elif n == self.state_var:
+                args.append(Arg(n, "y", np.array(val, dtype=prec).reshape(-1)))      # the caller's float64 state, model precision
+            else:
+                args.append(Arg(n, "const", np.array(val, copy=True)))
+        args.insert(3 if len(args) > 2 and args[2].kind == "hist" else 2, Arg(name, "dy", np.zeros(shape, dtype=prec)))
+        return Program(args, self.stmts, {}, prec, self.__name__)
+
     def source(self) -> str:
+        if self.jacobian is not None:
+            name, shape, _ = self.jacobian
+            lines = [f"def {self.__name__}({','.join(self.arg_names)}):", f"\t{name} = zeros({tuple(shape)})"]
+            lines += ["\t" + st.text() for st in self.stmts] + [f"\treturn {name}"]
+            return "\n".join(lines) + "\n"
         return Program([Arg(n, "const", np.zeros(())) for n in self.arg_names], self.stmts,
                        func_name=self.__name__).source().replace("return t", f"return {self.return_var}")
 
     def __call__(self, t, y, *args):
+        from .engine import evaluate_rhs
+        if self.jacobian is not None:
+            # J(t, y, *params) -> ndarray (n, n); a batch of states y[n, B] gives (n, n, B) from one launch
+            y = np.asarray(y)
+            prog = self.program([t, y if y.ndim == 1 else y[:, 0], *args])
+            shape, n_hist = tuple(self.jacobian[1]), self.jacobian[2]
+            out = evaluate_rhs(prog, t=float(np.asarray(t)), y=None if y.ndim == 1 else y)
+            out = out.reshape(shape if y.ndim == 1 else shape + (y.shape[1],))
+            # delay-differential models: (J0, [J_tau1, ...]), computegraph.py:521-524
+            return out if n_hist is None else (out[0], [out[k] for k in range(1, n_hist + 1)])
         names = self.arg_names
         dy = np.zeros_like(np.asarray(y))
         full = [np.asarray(t), np.asarray(y)] + list(args)
@@ -147,6 +195,9 @@ class CudaBackend:
         self.lvl = 0
         self._stmts: List[Stmt] = []
         self._n_hist_stmts = 0
+        self._local_arrays: Dict[str, tuple] = {}
+        self._yhist_stmts: List[Stmt] = []
+        self._return_expr: Optional[str] = None
         self._imports: List[str] = []
         self._helper_funcs: List[str] = []
         self.add_hist_arg = kwargs.pop('add_hist_arg', True)                  # reference default (:295)
@@ -180,6 +231,11 @@ class CudaBackend:
     def add_code_line(self, code_str: str):
         for code in code_str.split('\n'):
             self.code.append("\t" * self.lvl + code)
+        # get_jacobian_func of a delay-differential model prints `_yhist_<d> = hist(t - <d>)` through this generic hook
+        # (computegraph.py:697-701): kept as a lookup of the whole delayed state
+        m = _YHIST.match(code_str.strip())
+        if m:
+            self._yhist_stmts.append(Stmt(m.group(1), f"hist({m.group(2)})[:]", None))
 
     def add_linebreak(self):
         self.code.append("")
@@ -273,6 +329,24 @@ class CudaBackend:
         if line not in self._imports:
             self._imports.append(line)
 
+    # ------------------------------------------------------------------ Jacobian assembly (base_backend.py:417-435)
+    def declare_local_array_imports(self) -> None:
+        pass
+
+    def emit_local_array_alloc(self, name: str, shape: tuple, dtype: str) -> None:
+        """``name = zeros(shape)``: the matrix a Jacobian function fills and returns (computegraph.py:704-729)."""
+        if not self._local_arrays:
+            # the body of a Jacobian function starts with its first allocation; whole-state history lookups
+            # (`_yhist_d = hist(t - d)`, recorded by add_code_line) precede it
+            self._stmts, self._n_hist_stmts = list(self._yhist_stmts), 0
+        self._local_arrays[name] = tuple(int(x) for x in shape)
+        self.add_code_line(f"{name} = zeros({tuple(shape)}, dtype='{dtype}')")
+
+    def emit_local_array_assign(self, name: str, indices: tuple, expr: str) -> None:
+        idx = ', '.join(str(i) for i in indices)
+        self._stmts.append(Stmt(name, str(expr), idx))
+        self.add_code_line(f"{name}[{idx}] = {expr}")
+
     def generate_func_head(self, func_name: str, state_var: str = 'y', return_var: str = 'dy', func_args: list = None,
                            add_hist_func: Optional[bool] = None):
         """base_backend.py:483-528: signature order = t, y, [hist], then unique args in first-seen order."""
@@ -290,6 +364,7 @@ class CudaBackend:
         return args
 
     def generate_func_tail(self, rhs_var: str = 'dy'):
+        self._return_expr = rhs_var
         self.add_code_line(f"return {rhs_var}")
         self.remove_indent()
 
@@ -297,7 +372,23 @@ class CudaBackend:
         if self._head is None:
             raise _backend_error("generate_func called before generate_func_head")
         _, state_var, return_var, args = self._head
-        func = CudaVectorField(self, func_name, args, self._stmts, state_var, return_var)
+        jac, stmts = None, self._stmts
+        if self._local_arrays:
+            # `return J0` or, for delay-differential models, `return J0, [J_hist_<d>, ...]` (computegraph.py:731-743)
+            names = re.findall(r"[A-Za-z_]\w*", self._return_expr or return_var)
+            if not names or any(n not in self._local_arrays for n in names) or "csr_matrix" in names:
+                raise _backend_error(f"generated function returns `{self._return_expr}`, expected its local arrays")
+            shapes = {self._local_arrays[n] for n in names}
+            if len(shapes) != 1:
+                raise _backend_error("Jacobian blocks of different shapes")
+            if len(names) > 1:
+                # several matrices: one stacked output buffer [K + 1, n, n]
+                stmts = [Stmt("_jac_blocks", st.rhs, f"{names.index(st.lhs)}, {st.lhs_idx}") if st.lhs in names else st
+                         for st in stmts]
+                jac = ("_jac_blocks", (len(names),) + next(iter(shapes)), len(names) - 1)
+            else:
+                jac = (names[0], self._local_arrays[names[0]], None)
+        func = CudaVectorField(self, func_name, args, stmts, state_var, return_var, jacobian=jac)
         decorator = kwargs.pop('decorator', None)
         if decorator:
             raise _backend_error("CudaBackend does not support python decorators on the vector field")
@@ -317,6 +408,8 @@ class CudaBackend:
         self.code.clear()
         self._stmts = []
         self._n_hist_stmts = 0
+        self._local_arrays = {}
+        self._yhist_stmts = []
         self._head = None
 
     # ------------------------------------------------------------------ integration

@@ -39,7 +39,9 @@ __device__ __forceinline__ void prb_axpy(real (&o)[N], const real (&y)[N], const
 #define PRB_SET_ETAB
 #endif
 
-#if PRB_SOLVER == PRB_SOLVER_RK45
+#ifdef PRB_EVAL_ONLY
+// Jacobian programs (get_jacobian_func): n*n outputs from n state variables, evaluated once per call — no integrator.
+#elif PRB_SOLVER == PRB_SOLVER_RK45
 // ---- adaptive solver: the reference's solver='scipy' == scipy.integrate.solve_ivp(method='RK45', first_step=dt,
 // t_eval=times) (BaseBackend._solve_scipy, pyrates/backend/base/base_backend.py:802-812).  Dormand-Prince 5(4) with
 // SciPy's step controller (safety 0.9, factors in [0.2, 10], RMS error norm against atol + rtol*max(|y|,|y_new|)) and
@@ -420,7 +422,7 @@ prb_rhs_eval(const __grid_constant__ prb_kernel_args A)
     prb_thread_init(T, A, b);
     PRB_SET_ETAB
     const real* __restrict__ Y = (const real*)A.y;
-    areal y[PRB_NS], k[PRB_NS];
+    areal y[PRB_NS], k[PRB_NDY];
     PRB_UNROLL_NS
     for (int j = 0; j < PRB_NS; ++j) y[j] = (areal)Y[(long long)j * B + b];
 #if PRB_SOLVER == PRB_SOLVER_RK45 || PRB_SOLVER == PRB_SOLVER_DOPRI5
@@ -430,5 +432,5 @@ prb_rhs_eval(const __grid_constant__ prb_kernel_args A)
 #endif
     real* __restrict__ out = (real*)A.out;
     PRB_UNROLL_NS
-    for (int j = 0; j < PRB_NS; ++j) out[(long long)j * B + b] = (real)k[j];
+    for (int j = 0; j < PRB_NDY; ++j) out[(long long)j * B + b] = (real)k[j];
 }

@@ -312,6 +312,11 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     src.append(f"typedef {'double' if (adaptive and f32) else 'real'} areal;        // arithmetic type of the generated rhs")
     src.append(f"typedef {'double' if adaptive else 'long long'} prb_time;     // adaptive solvers hand the rhs a float time")
     src.append(f"#define PRB_NS {ns}")
+    src.append(f"#define PRB_NDY {rhs.n_out if rhs.n_out is not None else ns}        // outputs of prb_rhs (Jacobian programs: n*n)")
+    if rhs.n_out is not None:
+        if rhs.rings or rhs.slots:
+            raise UnsupportedModelError("Jacobian functions of models with delay ring buffers / mutable buffers")
+        src.append("#define PRB_EVAL_ONLY 1               // no integrator: only the single-evaluation kernel")
     src.append(f"#define PRB_NP {np_}")
     src.append(f"#define PRB_NOBS {len(observers)}")
     src.append(f"#define PRB_NRINGS {nrings}")
@@ -522,20 +527,20 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
         vals = body.pop(0)[len("// PRB_LIT = {"):-1]
         src.append(f"__device__ __constant__ double PRB_LIT[{vals.count(',') + 1}] = {{{vals}}};")
     if spec:
-        src.append("__device__ __noinline__ void prb_rhs_exact(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NS], PrbThread& T) {")
+        src.append("__device__ __noinline__ void prb_rhs_exact(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NDY], PrbThread& T) {")
         src.extend("    " + l for l in exact_body)
         src.append("}")
-    src.append("__device__ __forceinline__ void prb_rhs(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NS], PrbThread& T) {")
+    src.append("__device__ __forceinline__ void prb_rhs(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NDY], PrbThread& T) {")
     if spec:
         src.append("    bool bad = false;")
     src.extend("    " + l for l in body)
     if spec:
         src.append("    if (bad) {                  // an exp / division argument left the fast range: redo this evaluation exactly")
-        src.append("        areal yl[PRB_NS], dl[PRB_NS];")
+        src.append("        areal yl[PRB_NS], dl[PRB_NDY];")
         src.append("        PrbThread Tl = T;")
         src.append("        _Pragma(\"unroll\") for (int j = 0; j < PRB_NS; ++j) yl[j] = y[j];")
         src.append("        prb_rhs_exact(t, yl, dl, Tl);")
-        src.append("        _Pragma(\"unroll\") for (int j = 0; j < PRB_NS; ++j) dy[j] = dl[j];")
+        src.append("        _Pragma(\"unroll\") for (int j = 0; j < PRB_NDY; ++j) dy[j] = dl[j];")
         src.append("    }")
     src.append("}")
     rec = ["__device__ __forceinline__ void prb_record(const real (&y)[PRB_NS], real* __restrict__ row, long long b, long long B) {"]

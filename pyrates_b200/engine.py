@@ -14,7 +14,7 @@ import numpy as np
 from . import runtime as rt
 from .emit_inst import InstKernel, emit_inst_kernel
 from .program import Program
-from .scalarize import ScalarRhs, scalarize
+from .scalarize import ScalarRhs, UnsupportedModelError, scalarize
 
 __all__ = ["InstanceModel", "InstanceSession", "n_steps_for", "FIXED_STEP_SOLVERS", "ADAPTIVE_SOLVERS", "evaluate_rhs"]
 
@@ -349,31 +349,49 @@ class InstanceSession:
                 b.free()
 
 
-def evaluate_rhs(prog: Program, t: Optional[float] = None) -> np.ndarray:
+def evaluate_rhs(prog: Program, t: Optional[float] = None, y: Optional[np.ndarray] = None) -> np.ndarray:
     """One evaluation ``dy = f(t, y, *args)`` of the vector field on the GPU (kernel ``prb_rhs_eval``).  Programs built
-    for an adaptive solver carry a float ``t`` (optionally overridden by ``t``)."""
+    for an adaptive solver carry a float ``t`` (optionally overridden by ``t``).  ``y`` of shape ``(n_state, B)`` evaluates a
+    batch of B states in one launch (one thread each) and returns ``(n_out, B)``; Jacobian programs
+    (``CudaBackend`` recording ``get_jacobian_func``) return their ``n*n`` entries row-major."""
     float_time = not np.issubdtype(np.asarray(prog.arg_by_kind("t").value).dtype, np.integer)
-    m = InstanceModel(prog, solver="scipy" if float_time else "euler")
-    s = m.session(1, 0)
-    d_dy = rt.DeviceBuffer(max(m.n_state, 1) * np.dtype(m.real).itemsize)
+    # scalar float constants become runtime parameters: calls that only change parameter values (fitting / continuation
+    # loops around get_run_func / get_jacobian_func) reuse the compiled kernel (runtime.compile_module caches by source)
+    sweep = [(a.name, e) for a in prog.args if a.kind == "const" and np.issubdtype(a.value.dtype, np.floating)
+             and a.value.size <= 8 for e in range(a.value.size)]
+    m = None
+    if 0 < len(sweep) <= 96:
+        try:
+            m = InstanceModel(prog, solver="scipy" if float_time else "euler", sweep=sweep)
+        except (KeyError, UnsupportedModelError):
+            m = None                               # a constant that must stay compile-time (unused, delay, table ...)
+    if m is None:
+        m = InstanceModel(prog, solver="scipy" if float_time else "euler")
+    n_out = m.rhs.n_out if m.rhs.n_out is not None else m.n_state
+    batch = None if y is None or np.ndim(y) < 2 else int(np.shape(y)[1])
+    B = batch or 1
+    s = m.session(B, 0)
+    d_dy = rt.DeviceBuffer(max(n_out, 1) * B * np.dtype(m.real).itemsize)
     d_extra = []
     try:
-        s.reset()
+        s.reset(y0=None if y is None else np.asarray(y, dtype=m.real).reshape(m.n_state, B))
         a = rt.KernelArgs()
-        a.n_steps, a.store_step, a.step0, a.eval0, a.n_inst, a.sample0 = 0, 1, 0, 0, 1, 0
+        a.n_steps, a.store_step, a.step0, a.eval0, a.n_inst, a.sample0 = 0, 1, 0, 0, B, 0
         a.t0, a.dt = (0, float(m.t0 if t is None else t)) if float_time else (int(m.t0), 0.0)
         a.y, a.out, a.params = s.d_y.ptr, d_dy.ptr, s.d_params.ptr
         a.slots, a.rings, a.tables = s.d_slots.ptr, s.d_rings.ptr, s.d_tables.ptr
         if m.kernel.n_hist and float_time:          # history = the initial condition only (a fresh DDEHistory)
+            if B != 1:
+                raise rt.CudaBackendError("batched evaluation of delay-differential vector fields is not supported")
             d_extra.append(rt.DeviceBuffer.from_host(np.concatenate([[0, 0, m.t0, 0, 0, 0, 0, 0, 1.0], m.hist_y0])))
             d_extra.append(rt.DeviceBuffer((1 + m.kernel.n_hist) * 8))
             a.consts, a.work = d_extra[0].ptr, d_extra[1].ptr
         elif m.kernel.n_hist:
             a.work, a.dt = s.d_hist.ptr, float(m.rhs.hist_dt)
         m.module.run("prb_rhs_eval", a, block=m.kernel.block)
-        dy = np.empty(m.n_state, dtype=m.real)
+        dy = np.empty((n_out, B), dtype=m.real)
         d_dy.download(dy)
-        return dy
+        return dy if batch else dy[:, 0]
     finally:
         d_dy.free()
         for d in d_extra:

@@ -372,6 +372,7 @@ class ScalarRhs:
     uses_t: bool = False
     # delay-differential models (`hist(t*dt - d)[idx]` lookups, base_backend.py:437-444): state elements whose history is
     # kept, every delay that is looked up, and the step size baked into the fixed-step query text (None: adaptive form)
+    n_out: Optional[int] = None                    # outputs when they are not the state derivatives (Jacobian programs: n*n)
     hist_vars: List[int] = field(default_factory=list)
     hist_delays: List[float] = field(default_factory=list)
     hist_dt: Optional[float] = None
@@ -452,6 +453,7 @@ class _Interp:
         self.hist_delays: List[float] = []
         self.hist_dt: Optional[float] = None
         self.hist_name = next((a.name for a in prog.args if a.kind == "hist"), None)
+        self.jacobian = False
         self.tname = prog.arg_by_kind("t").name
         self.yname = prog.arg_by_kind("y").name
         self.dyname = prog.arg_by_kind("dy").name
@@ -481,8 +483,11 @@ class _Interp:
                         arr[k] = self.g.leaf("state", k)
                 self.env[a.name] = arr
             elif a.kind == "dy":
-                arr = np.empty(v.size, dtype=object)
-                arr[:] = None
+                # 2-d output buffer: a Jacobian program (`J0 = zeros((n, n)); J0[i, j] = expr`, computegraph.py:704-717),
+                # entries that are never assigned stay zero
+                self.jacobian = v.ndim >= 2
+                arr = np.empty(v.shape if self.jacobian else v.size, dtype=object)
+                arr[...] = self.g.const(0.0) if self.jacobian else None
                 self.env[a.name] = arr
             elif a.kind == "hist":
                 self.env[a.name] = None                          # only ever called: hist(t - d)[idx]
@@ -939,6 +944,7 @@ class _Interp:
                     target[idx] = np.full(np.shape(target[idx]), v, dtype=object)
                     continue
             target[idx] = v
+        dy = dy.reshape(-1)
         if any(x is None for x in dy):
             raise UnsupportedModelError("vector field leaves some state derivatives unassigned")
         # ring bookkeeping
@@ -958,8 +964,12 @@ class _Interp:
             if any(isinstance(x, CSym) for x in dy):
                 raise UnsupportedModelError("complex derivative in a real-valued build")
             n_out, dy_ids = dy.size, [g.lift(x).id for x in dy]
-        out = ScalarRhs(g, n_out, dy_ids, self.params, self.tables, [r.spec for r in self.rings],
-                        ring_writes, self.slots, [], self.uses_t, list(self.hist_vars), list(self.hist_delays), self.hist_dt)
+        n_in = int(np.asarray(self.p.arg_by_kind("y").value).size) * (2 if self.complex else 1)
+        if n_out != n_in and not self.jacobian:
+            raise UnsupportedModelError(f"vector field returns {n_out} derivatives for {n_in} state variables")
+        out = ScalarRhs(g, n_in, dy_ids, self.params, self.tables, [r.spec for r in self.rings],
+                        ring_writes, self.slots, [], self.uses_t, n_out if self.jacobian else None,
+                        list(self.hist_vars), list(self.hist_delays), self.hist_dt)
         # persistent slots: store back only if any evaluation can observe an incoming value
         slot_final = {}
         for name, arr in self.slot_arrays.items():

@@ -28,7 +28,13 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    """Trajectory fixtures (integration runs of the reference)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("jac_"))
+
+
+def jacobian_names():
+    """Jacobian fixtures (reference-generated get_jacobian_func evaluated at 16 states)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("jac_"))
 
 
 def golden_path(name):

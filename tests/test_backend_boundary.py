@@ -115,6 +115,32 @@ def test_delay_differential_models_match_numpy_backend(gpu, registered, path, ou
 
 
 @needs_ref
+@pytest.mark.parametrize("name,path,precision", [("jac_vdp", "model_templates.oscillators.vanderpol.vdp", "float64"),
+                                                 ("jac_jrc", "model_templates.neural_mass_models.jansenrit.JRC", "float64"),
+                                                 ("jac_qif_sfa_f32", "model_templates.neural_mass_models.qif.qif_sfa", "float32")])
+def test_cuda_backend_records_jacobian_functions(registered, name, path, precision):
+    """CircuitTemplate.get_jacobian_func(backend='cuda'): the graph differentiates symbolically and drives
+    emit_local_array_alloc / emit_local_array_assign (computegraph.py:704-729); the recorded `J0[i, j] = expr` stream and
+    the parameter arguments are the ones the NumPy backend printed.  sparse=True is refused like upstream's array backends."""
+    from pyrates import clear
+    c = _fresh(path)
+    func, args, names, svmap = c.get_jacobian_func(func_name="jacobian", step_size=1e-3, solver="euler", in_place=False,
+                                                   clear=False, vectorize=False, backend="cuda", float_precision=precision,
+                                                   verbose=False)
+    gold = Program.load(golden_path(name))
+    prog = func.program(args)
+    assert names[:2] == ("t", "y") and "def jacobian(" in func.source()
+    assert _norm(prog.stmts) == _norm(gold.stmts)
+    assert [(a.name, a.kind, a.value.shape) for a in prog.args] == [(a.name, a.kind, a.value.shape) for a in gold.args]
+    for a, b in zip(prog.args[3:], gold.args[3:]):
+        assert a.value.dtype == b.value.dtype and np.array_equal(a.value, b.value), a.name
+    clear(c)
+    with pytest.raises(NotImplementedError, match="sparse"):
+        _fresh(path).get_jacobian_func(func_name="jac_sp", step_size=1e-3, solver="euler", in_place=False, clear=True,
+                                       vectorize=False, backend="cuda", sparse=True, verbose=False)
+
+
+@needs_ref
 def test_new_solver_names_are_fixed_step(registered):
     import pyrates.frontend.template.circuit as fc
     assert not fc.is_integration_adaptive("rk4") and not fc.is_integration_adaptive("heun_true")

@@ -5,7 +5,7 @@ Tolerances are the north star's: rel 1e-9 in fp64, 1e-4 in fp32 (per-column scal
 import numpy as np
 import pytest
 
-from conftest import RTOL, as_real_columns, golden_names, golden_path, traj_rel_err
+from conftest import RTOL, as_real_columns, golden_names, golden_path, jacobian_names, traj_rel_err
 from oracle import numpy_oracle as orc
 from pyrates_b200 import runtime as rt
 from pyrates_b200.engine import InstanceModel, n_steps_for
@@ -181,6 +181,37 @@ def test_dde_batch_of_instances_and_chunked_launches(gpu):
             s2.launch(10, 2 * r["dt"], store_step)        # the vector field was generated for another step size
         finally:
             s2.free()
+
+
+@pytest.mark.parametrize("name", jacobian_names())
+def test_jacobian_kernel_matches_reference(gpu, name):
+    """get_jacobian_func on the device: the reference-generated `J0[i, j] = expr` stream evaluated by one thread per state,
+    16 states in ONE launch, vs the matrices the reference's own compiled NumPy function returned."""
+    from pyrates_b200.engine import evaluate_rhs
+    fx = orc.load_fixture(golden_path(name))
+    prog = Program.load(golden_path(name))
+    pts, ref = fx["extra"]["jac_points"], fx["extra"]["jac_ref"]
+    n = prog.n_state
+    before = rt.launch_count()
+    got = evaluate_rhs(prog, y=pts.T)                       # (n*n, 16)
+    assert rt.launch_count() == before + 1
+    got = got.reshape(n, n, -1).transpose(2, 0, 1)
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    tol = 1e-12 if prog.float_precision == "float64" else 1e-5
+    assert np.allclose(got, ref, rtol=tol, atol=tol * np.max(np.abs(ref)))
+    single = evaluate_rhs(prog).reshape(n, n)               # at the program's own state
+    assert np.allclose(single, ref[0], rtol=tol, atol=tol * np.max(np.abs(ref)))
+    # new parameter values reuse the compiled kernel (constants are runtime parameters of the evaluation kernel)
+    p2 = prog.clone()
+    for a in p2.args:
+        if a.kind == "const" and a.value.size == 1 and a.value.dtype.kind == "f":
+            a.value = (a.value * 1.25).astype(a.value.dtype)
+    n_mod = len(rt._module_cache)
+    other = evaluate_rhs(p2).reshape(n, n)
+    assert len(rt._module_cache) == n_mod and not np.allclose(other, single)
+    f = orc.build_vector_field(p2.source(), p2.func_name)
+    want = f(0.0, p2.y0.copy(), np.zeros((n, n), dtype=prog.real_dtype), *[a.value for a in p2.args[3:]])
+    assert np.allclose(other, want, rtol=tol, atol=tol * np.max(np.abs(want)))
 
 
 def test_interpolated_input_rhs_matches_numpy_interp(gpu):

@@ -3,7 +3,7 @@ real reference NumPy backend (bit-exact) and the reference's own hand-computed k
 import numpy as np
 import pytest
 
-from conftest import golden_names, golden_path
+from conftest import golden_names, golden_path, jacobian_names
 from oracle import numpy_oracle as orc
 
 
@@ -193,3 +193,32 @@ def test_solver_convergence_order(solver, order):
     truth = final(1e-4, "rk4")
     e1, e2 = abs(final(2e-2, solver) - truth), abs(final(1e-2, solver) - truth)
     assert abs(np.log2(e1 / e2) - order) < 0.35, (e1, e2)
+
+
+@pytest.mark.parametrize("name", jacobian_names())
+def test_oracle_jacobian_reproduces_reference(name):
+    """get_jacobian_func (computegraph.py:516-763): the oracle executes the reference-generated assignment stream
+    `J0[i, j] = expr` and must return exactly what the reference's own compiled function returned at 16 states."""
+    fx = orc.load_fixture(golden_path(name))
+    f = orc.build_vector_field(fx["source"], fx["meta"]["func_name"])
+    shape = fx["args"][2].shape
+    for y, ref in zip(fx["extra"]["jac_points"], fx["extra"]["jac_ref"]):
+        J = f(0.0, y.copy(), np.zeros(shape, dtype=fx["args"][2].dtype), *fx["args"][3:])
+        assert J.dtype == ref.dtype and np.array_equal(J, ref, equal_nan=True)
+
+
+def test_jacobian_fixture_known_answers():
+    """The reference's own analytical check (tests/test_jacobian.py:121-158): van der Pol at (x, z) = (0, 1), mu = 1 has
+    J = [[0, 1], [-1, 1]]; and the transcendental model's Jacobian agrees with central differences of its vector field."""
+    fx = orc.load_fixture(golden_path("jac_vdp"))
+    f = orc.build_vector_field(fx["source"], fx["meta"]["func_name"])
+    J = f(0.0, np.array([0.0, 1.0]), np.zeros((2, 2)), *fx["args"][3:])
+    assert np.allclose(J, [[0.0, 1.0], [-1.0, 1.0]], atol=1e-8)
+    fx = orc.load_fixture(golden_path("jac_trans"))
+    f = orc.build_vector_field(fx["source"], fx["meta"]["func_name"])
+    a = float(fx["args"][fx["names"].index("a")])
+    rhs = lambda y: np.array([-y[0] + np.exp(-a * y[0]) + np.cos(y[1]), -y[1] + np.sin(y[0])])
+    for y in fx["extra"]["jac_points"][:4]:
+        J = f(0.0, y.copy(), np.zeros((2, 2)), *fx["args"][3:])
+        fd = np.stack([(rhs(y + 1e-6 * e) - rhs(y - 1e-6 * e)) / 2e-6 for e in np.eye(2)], axis=1)
+        assert np.allclose(J, fd, atol=1e-6)

@@ -23,6 +23,12 @@ SUITES = {
                                      "test_connectivity_edge_kuramoto_sine", "test_connectivity_dynamic_edge",
                                      "test_matrix_discrete_delay", "test_matrix_gamma_kernel_delay"],
     "test_implemented_models": ["test_3_1_jansenrit", "test_3_2_qif_theta", "test_3_3_wilson_cowan", "test_3_4_kuramoto"],
+    # get_jacobian_func: symbolic Jacobians evaluated on the device (test_jacobian_sparse skips itself: the backend declares
+    # SUPPORTS_SPARSE_JACOBIAN = False, like upstream's torch / jax backends)
+    "test_jacobian": ["test_jacobian_ode_dimensions", "test_jacobian_ode_vs_finite_difference",
+                      "test_jacobian_ode_analytical_values", "test_jacobian_ode_transcendentals",
+                      "test_jacobian_stateful_edge", "test_jacobian_sparse", "test_jacobian_dde_structure",
+                      "test_jacobian_dde_j0_vs_finite_difference"],
 }
 
 
@@ -43,8 +49,20 @@ def test_reference_test_passes_with_cuda_backend(gpu, tmp_path, monkeypatch, mod
     monkeypatch.chdir(tmp_path)
     mod = _load(module)
     from pyrates.ir.node import clear_ir_caches
-    clear_ir_caches()
+
+    def reset():
+        # what upstream's autouse fixtures do between tests (tests/test_jacobian.py:16-33): templates are cached and
+        # update_template(in_place=True) mutates them
+        from pyrates import OperatorTemplate
+        from pyrates.frontend.template import template_cache
+        from pyrates.ir.circuit import in_edge_indices, in_edge_vars
+        OperatorTemplate.cache.clear()
+        clear_ir_caches()
+        in_edge_indices.clear()
+        in_edge_vars.clear()
+        template_cache.clear()
+    reset()
     try:
         getattr(mod, name)("cuda")
     finally:
-        clear_ir_caches()
+        reset()

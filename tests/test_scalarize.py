@@ -3,7 +3,7 @@ must reproduce the reference's Euler trajectories for every fixture small enough
 import numpy as np
 import pytest
 
-from conftest import as_real_columns, golden_names, golden_path, traj_rel_err
+from conftest import as_real_columns, golden_names, golden_path, jacobian_names, traj_rel_err
 from dag_eval import DagMachine
 from oracle import numpy_oracle as orc
 from pyrates_b200.program import Program
@@ -27,6 +27,24 @@ def test_dag_matches_reference_euler(name):
     ref = as_real_columns(fx["extra"]["rec_euler"])[: rec.shape[0]]
     tol = 1e-12 if prog.float_precision in ("float64", "complex128") else 1e-5
     assert traj_rel_err(rec, ref) <= tol
+
+
+@pytest.mark.parametrize("swept", [False, True])
+@pytest.mark.parametrize("name", jacobian_names())
+def test_jacobian_dag_matches_reference(name, swept):
+    """Jacobian programs (`J0[i, j] = expr` into an n x n output buffer): n*n outputs from n state inputs, unassigned
+    entries zero; with every scalar constant turned into a runtime parameter (what evaluate_rhs does) the values agree."""
+    fx = orc.load_fixture(golden_path(name))
+    prog = Program.load(golden_path(name))
+    sweep = [(a.name, 0) for a in prog.args if a.kind == "const" and a.value.size == 1] if swept else []
+    rhs = scalarize(prog, sweep)
+    n = prog.n_state
+    assert rhs.n_state == n and rhs.n_out == n * n and len(rhs.dy) == n * n and len(rhs.params) == len(sweep)
+    mach = DagMachine(rhs, prog.real_dtype)
+    tol = 1e-12 if prog.float_precision == "float64" else 1e-5
+    for y, ref in zip(fx["extra"]["jac_points"], fx["extra"]["jac_ref"]):
+        J = mach.eval(0.0, y.astype(prog.real_dtype)).reshape(n, n)
+        assert np.allclose(J, ref, rtol=tol, atol=tol * np.max(np.abs(ref)))
 
 
 @pytest.mark.parametrize("name", sorted(LARGE))
