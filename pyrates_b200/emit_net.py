@@ -632,7 +632,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 if space == "const" and world > 1 and v.ndim == 2:
                     lo, hi = em.bounds(v.shape[0])
                     v = v[lo:hi]                   # this rank's row shard of the connectivity
-                buf[a.offset:a.offset + v.size] = v.reshape(-1).astype(dtype)
+                buf[a.offset:a.offset + v.size] = v.reshape(-1)          # casts on assignment, no temporary
         return buf
 
     const_buf = pack("const", const_size, real)

@@ -193,7 +193,9 @@ class _NetInterp:
         if space in self.off:
             off = self.off[key]
             self.off[key] = off + ((size + 31) // 32) * 32       # 256-byte alignment for fp64 vector loads
-        arr = MemArray(name, space, tuple(shape), off, None if init is None else np.array(init, copy=True))
+        # read-only constants are referenced, not copied (a dense connectivity can be tens of GiB: C5 at N=65536 is 32 GiB)
+        keep = space in ("const", "iconst", "table") and init is not None and np.asarray(init).nbytes >= (1 << 20)
+        arr = MemArray(name, space, tuple(shape), off, None if init is None else (np.asarray(init) if keep else np.array(init, copy=True)))
         self.arrays[name] = arr
         self.avail[name] = 0
         return arr

@@ -104,7 +104,7 @@ class NetworkSession:
         self.d_y = rt.DeviceBuffer(max(k.n_state * B, 1) * item)
         self.d_out = rt.DeviceBuffer(max(self.n_samples * k.n_obs * B, 1) * item)
         self.d_params = rt.DeviceBuffer(max(len(model.param_names) * B, 1) * item)
-        self.d_consts = rt.DeviceBuffer.from_host(k.const_init.astype(real))
+        self.d_consts = rt.DeviceBuffer.from_host(np.asarray(k.const_init, dtype=real))
         self.d_iconsts = rt.DeviceBuffer.from_host(k.iconst_init.astype(np.int32))
         self.d_tables = rt.DeviceBuffer.from_host(k.table_init.astype(real))
         self.d_work = rt.DeviceBuffer(max(k.work_elems, 1) * item)

@@ -114,8 +114,17 @@ class BatchedSweep:
             s.d_slots.upload(np.repeat(k.slot_init.astype(self.real)[:, None], self.B, axis=1), self.compute)
         if k.ring_elems:
             s.d_rings.upload(np.repeat(k.ring_init.astype(self.real)[:, None], self.B, axis=1), self.compute)
+        self._upload_history(self.compute)
         s.steps_done = 0
         s.samples_done = 0
+
+    def _upload_history(self, stream):
+        """Delay-differential models, fixed-step solvers: entry 0 of every instance's history ring is its initial state."""
+        s, k = self.sess, self.model.kernel
+        if s.d_hist is not None:
+            h = np.zeros((k.hist_depth, k.n_hist, self.B), dtype=self.real)
+            h[0] = self.h_y0.array[k.hist_vars]
+            s.d_hist.upload(h, stream)
 
     def integrate(self, read_back: bool = True):
         """Launch all time chunks; with ``read_back`` stream each chunk D2H into the result array."""
@@ -195,6 +204,7 @@ class BatchedSweep:
             s.d_slots.upload(np.repeat(k.slot_init.astype(self.real)[:, None], self.B, axis=1), stream)
         if k.ring_elems:
             s.d_rings.upload(np.repeat(k.ring_init.astype(self.real)[:, None], self.B, axis=1), stream)
+        self._upload_history(stream)
         s.steps_done = 0
         s.samples_done = 0
         out = torch.empty((max(self.n_samples, 1), self.n_obs, self.B), dtype=tdt, device=dev)

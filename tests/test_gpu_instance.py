@@ -214,6 +214,34 @@ def test_jacobian_kernel_matches_reference(gpu, name):
     assert np.allclose(other, want, rtol=tol, atol=tol * np.max(np.abs(want)))
 
 
+@pytest.mark.parametrize("solver", ["heun", "rk4", "scipy"])
+def test_dde_sweep_matches_per_instance_oracle(gpu, solver):
+    """grid_search-style batch over a delay-differential model (Mackey-Glass + delayed-feedback unit): every instance has its
+    own parameters AND its own history; chunked streaming launches continue from the device-resident history rings."""
+    from pyrates_b200.sweep import BatchedSweep
+    name = "dde_mg_dopri5" if solver == "scipy" else "dde_mg"
+    prog = Program.load(golden_path(name))
+    fx = orc.load_fixture(golden_path(name))
+    B = 300
+    rng = np.random.default_rng(5)
+    table = np.stack([rng.uniform(1.5, 2.5, B), rng.uniform(2.0, 4.0, B)])          # bet, a
+    T, dt, dts = 0.1, 1e-4, 1e-3
+    sw = BatchedSweep(prog, [("bet", 0), ("a", 0)], observers=[0, 1], solver=solver, T=T, dt=dt, dts=dts, n_inst=B,
+                      chunk_samples=7, const_div_to_mul=False)
+    try:
+        out = np.array(sw.run(table), copy=True)
+    finally:
+        sw.free()
+    assert out.shape == (100, 2, B)
+    f = orc.build_vector_field(fx["source"])
+    for b in (0, 17, 299):
+        args = orc.fixture_args(fx)
+        args[fx["names"].index("bet")] = np.float64(table[0, b])
+        args[fx["names"].index("a")] = np.float64(table[1, b])
+        rec = orc.run_adaptive(f, args, T, dt, dts)[0] if solver == "scipy" else orc.run(f, args, T, dt, dts, solver)[0]
+        assert traj_rel_err(out[:, :, b], rec) <= 1e-9, (solver, b)
+
+
 def test_interpolated_input_rhs_matches_numpy_interp(gpu):
     """interp(t, time, u_input) of the adaptive build (numpy.interp semantics): knots, interior points, both clamps."""
     from pyrates_b200.engine import evaluate_rhs
