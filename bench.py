@@ -230,6 +230,25 @@ def main():
     e2e_val = NODES * B * world * n_steps * a.steps / e2e_s
     checksum = float(out[-1, 0, :8].sum())
 
+    # ---- the same sweep with the observer reduced on the device (grid_search(reduce=True)): host table in, per-instance
+    # mean / var / min / max / last out.  Informational — the headline e2e above returns every trajectory like the reference.
+    red = BatchedSweep(prog, SWEEP, observers=[0], solver="rk4", T=a.sim_time, dt=1e-4, dts=1e-3, n_inst=B,
+                       const_div_to_mul=not a.strict_div, reduce=True)
+    red.model.module
+    for _ in range(2):
+        red.run(table)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(a.steps):
+        stats = red.run(table)
+    barrier()
+    red_s = max_over_ranks(time.perf_counter() - t0)
+    red_info = {"value": NODES * B * world * n_steps * a.steps / red_s, "unit": UNIT, "ms_per_step": red_s * 1e3 / a.steps,
+                "h2d_bytes_per_step": red.h2d_bytes, "d2h_bytes_per_step": red.d2h_bytes,
+                "api": "pyrates_b200.sweep.BatchedSweep(reduce=True).run", "stats": ["mean", "var", "min", "max", "last"],
+                "mean_matches_full_run": bool(np.allclose(stats[0, 0, :64], out[:, 0, :64].mean(axis=0), rtol=1e-10, atol=0))}
+    red.free()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -247,6 +266,7 @@ def main():
         "instance_steps_per_s": value / NODES,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": sw.h2d_bytes, "d2h_bytes_per_step": sw.d2h_bytes,
                 "ms_per_step": e2e_s * 1e3 / a.steps, "api": "pyrates_b200.sweep.BatchedSweep.run", "checksum": checksum},
+        "e2e_reduced": red_info,
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                      "traffic": (NCU_TRAFFIC.get(int(inst_steps_per_launch)) if a.grid == 1024 else None),

@@ -127,6 +127,17 @@ def _jrc_pair_delayed():
     return build
 
 
+def _two_qif():
+    """Two coupled QIF populations, vectorised: an input to `all/...` arrives as a (steps, 2) table -> interp_rows."""
+    def build():
+        from pyrates import CircuitTemplate, NodeTemplate
+        qif = NodeTemplate.from_yaml(NM + "qif.qif_pop")
+        return CircuitTemplate("two_qif", nodes={"p1": qif, "p2": qif},
+                               edges=[("p1/qif_op/r", "p2/qif_op/r_in", None, {"weight": 5.0}),
+                                      ("p2/qif_op/r", "p1/qif_op/r_in", None, {"weight": 8.0})])
+    return build
+
+
 def _wc_pop(N, seed=42):
     def build():
         from pyrates import CircuitTemplate, NodeTemplate
@@ -372,6 +383,9 @@ ADAPTIVE_CASES = {
     # extrinsic input with an adaptive solver: the frontend emits interp(t, time, u_input) (circuit.py:1692-1709)
     "qif_input_rk45": dict(build=_yaml(NM + "qif.qif"), T=2.0, dt=1e-3, dts=1e-2, out="p/qif_op/r",
                            inputs=lambda: {"p/qif_op/I_ext": _sin_input(2000) * 3.0}, kw=dict(rtol=1e-7, atol=1e-9)),
+    # vector-valued input with an adaptive solver: interp_rows(t, time, u_input) over a (steps, 2) table (circuit.py:1696-1700)
+    "qif2_input_rk45": dict(build=_two_qif(), T=1.0, dt=1e-3, dts=1e-2, out="all/qif_op/r",
+                            inputs=lambda: {"all/qif_op/I_ext": _sin_input(1000, cols=2)}, kw=dict(rtol=1e-7, atol=1e-9)),
     # SciPy's RK23 (the reference's own solver test uses it, tests/test_backend_simulations.py:370)
     "jrc_rk23":     dict(build=_yaml(NM + "jansenrit.JRC"), T=0.3, dt=1e-4, dts=1e-3, out="pc/rpo_e_in/v",
                          kw=dict(method="RK23", rtol=1e-6, atol=1e-9)),

@@ -354,9 +354,38 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
     long long sample = A.sample0;
     long long t = A.step0 + A.t0;
 
+#ifdef PRB_REDUCE
+    // On-device observer reduction: instead of storing every decimated sample, each thread keeps running
+    // statistics of its observers over the samples with index >= A.sample0 (the `cutoff` of CircuitTemplate.run /
+    // grid_search, frontend/template/circuit.py:550) and stores [mean, var, min, max, last][observer][instance] once at
+    // the end: a 2^20-instance sweep returns 42 MB instead of 8.4 GB.  Welford's update, population variance (numpy.var).
+    real r_mean[PRB_NOBS], r_m2[PRB_NOBS], r_min[PRB_NOBS], r_max[PRB_NOBS], r_last[PRB_NOBS];
+    long long r_cnt = 0;
+    sample = 0;
+#pragma unroll
+    for (int o = 0; o < PRB_NOBS; ++o) { r_mean[o] = (real)0; r_m2[o] = (real)0; r_min[o] = (real)0; r_max[o] = (real)0; r_last[o] = (real)0; }
+#endif
     for (long long i = 0; i < A.n_steps; ++i, ++t) {
         if (until_store == 0) {
+#ifdef PRB_REDUCE
+            if (sample >= A.sample0) {
+                real cur[PRB_NOBS];
+                prb_record(y, cur, 0, 1);
+                ++r_cnt;
+                const real inv = (real)1 / (real)r_cnt;
+#pragma unroll
+                for (int o = 0; o < PRB_NOBS; ++o) {
+                    const real d = cur[o] - r_mean[o];
+                    r_mean[o] += d * inv;
+                    r_m2[o] += d * (cur[o] - r_mean[o]);
+                    r_min[o] = (r_cnt == 1 || cur[o] < r_min[o]) ? cur[o] : r_min[o];
+                    r_max[o] = (r_cnt == 1 || cur[o] > r_max[o]) ? cur[o] : r_max[o];
+                    r_last[o] = cur[o];
+                }
+            }
+#else
             prb_record(y, out + sample * (long long)PRB_NOBS * B, b, B);
+#endif
             ++sample;
             until_store = store_step;
         }
@@ -403,6 +432,16 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
 #endif
     }
 
+#ifdef PRB_REDUCE
+#pragma unroll
+    for (int o = 0; o < PRB_NOBS; ++o) {
+        out[(0LL * PRB_NOBS + o) * B + b] = r_mean[o];
+        out[(1LL * PRB_NOBS + o) * B + b] = r_cnt > 0 ? r_m2[o] / (real)r_cnt : (real)0;
+        out[(2LL * PRB_NOBS + o) * B + b] = r_min[o];
+        out[(3LL * PRB_NOBS + o) * B + b] = r_max[o];
+        out[(4LL * PRB_NOBS + o) * B + b] = r_last[o];
+    }
+#endif
     PRB_UNROLL_NS
     for (int j = 0; j < PRB_NS; ++j) Y[(long long)j * B + b] = y[j];
     prb_thread_exit(T, A, b);

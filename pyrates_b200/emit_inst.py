@@ -247,8 +247,9 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
 
 def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: Sequence[int],
                      block: int = 128, const_div_to_mul: bool = False, min_blocks: int = 1,
-                     fast_math: bool = False, rk_method: str = "RK45") -> InstKernel:
-    """Generate the full CUDA C source of the fused rhs+solver instance kernel."""
+                     fast_math: bool = False, rk_method: str = "RK45", reduce: bool = False) -> InstKernel:
+    """Generate the full CUDA C source of the fused rhs+solver instance kernel.  ``reduce``: the kernel keeps running
+    statistics of the observers (mean, var, min, max, last) instead of storing every sample (fixed-step solvers)."""
     if solver not in SOLVER_IDS:
         raise ValueError(f"unknown solver `{solver}`; supported: {sorted(SOLVER_IDS)}")
     f32 = precision == "float32"
@@ -323,6 +324,10 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     src.append(f"#define PRB_SOLVER {SOLVER_IDS[solver]}")
     src.append(f"#define PRB_BLOCK {block}")
     src.append(f"#define PRB_MIN_BLOCKS {int(min_blocks)}")
+    if reduce:
+        if adaptive:
+            raise UnsupportedModelError("on-device observer reduction is implemented for the fixed-step solvers")
+        src.append("#define PRB_REDUCE 1")
     src.append(f"#define PRB_NH {n_hist}")
     src.append(f"#define PRB_HDEPTH {hist_depth}")
     if adaptive and solver != "dopri5_dde":

@@ -37,7 +37,7 @@ class InstanceModel:
     def __init__(self, prog: Program, *, solver: str = "euler", sweep: Sequence[Tuple[str, int]] = (),
                  observers: Optional[Sequence[int]] = None, block: int = 128, fmad: bool = True,
                  const_div_to_mul: bool = False, max_nodes: int = 6000, min_blocks: int = 1, fast_math: bool = False,
-                 rk_method: Optional[str] = None):
+                 rk_method: Optional[str] = None, reduce: bool = False):
         if solver not in FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS:
             raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
                                       f"Supported solvers: {list(FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS)}.")
@@ -59,7 +59,8 @@ class InstanceModel:
         self.kernel: InstKernel = emit_inst_kernel(self.rhs, solver=self.kernel_solver, precision=self.precision,
                                                    observers=self.observers, block=block,
                                                    const_div_to_mul=const_div_to_mul, min_blocks=min_blocks,
-                                                   fast_math=fast_math, rk_method=self.rk_method or "RK45")
+                                                   fast_math=fast_math, rk_method=self.rk_method or "RK45", reduce=reduce)
+        self.reduce = bool(reduce)
         self.fmad = fmad
         self._module: Optional[rt.Module] = None
         t0 = np.asarray(prog.arg_by_kind("t").value)
@@ -189,6 +190,8 @@ class InstanceSession:
         With ``out`` the samples of this launch go to rows 0.. of that buffer (chunked/streamed runs)
         instead of being appended to the session's own recording."""
         k = self.m.kernel
+        if self.m.reduce:
+            raise rt.CudaBackendError("this model reduces its observers on the device: use launch_reduce")
         new_samples = self.samples_in(n_steps, store_step)
         if out is not None:
             if new_samples > (out_capacity if out_capacity is not None else new_samples):
@@ -213,6 +216,39 @@ class InstanceSession:
         self.steps_done += int(n_steps)
         self.samples_done += new_samples
         return new_samples
+
+    REDUCE_STATS = ("mean", "var", "min", "max", "last")
+
+    def launch_reduce(self, n_steps: int, dt: float, store_step: int = 1, skip_samples: int = 0,
+                      out: Optional[rt.DeviceBuffer] = None):
+        """Models built with ``reduce=True``: integrate ``n_steps`` steps in ONE launch and leave
+        ``[len(REDUCE_STATS), n_obs, B]`` running statistics of the decimated samples ``>= skip_samples`` in the output
+        buffer (numpy.mean / var / min / max over the sample axis, and the last sample)."""
+        if not self.m.reduce:
+            raise rt.CudaBackendError("launch_reduce needs a model built with reduce=True")
+        k = self.m.kernel
+        need = len(self.REDUCE_STATS) * k.n_obs * self.B * np.dtype(self.m.real).itemsize
+        if out is None and self.d_out.nbytes < need:
+            self.d_out.free()
+            self.d_out = rt.DeviceBuffer(need)
+        a = rt.KernelArgs()
+        a.n_steps, a.store_step, a.step0 = int(n_steps), int(store_step), 0
+        a.t0, a.eval0 = self.m.t0, 0
+        a.n_inst, a.sample0, a.dt = self.B, int(skip_samples), float(dt)
+        a.y, a.out, a.params = self.d_y.ptr, (out.ptr if out is not None else self.d_out.ptr), self.d_params.ptr
+        a.slots, a.rings, a.tables = self.d_slots.ptr, self.d_rings.ptr, self.d_tables.ptr
+        a.consts = a.iconsts = a.work = a.sync = None
+        if self.d_hist is not None:
+            a.work = self.d_hist.ptr
+        self.m.module.run(k.kernel_name, a, block=k.block, stream=self.stream)
+        self.steps_done = int(n_steps)
+
+    def download_reduced(self) -> np.ndarray:
+        out = np.empty((len(self.REDUCE_STATS), self.m.kernel.n_obs, self.B), dtype=self.m.real)
+        self.d_out.download(out, self.stream)
+        if self.stream is not None:
+            self.stream.synchronize() if hasattr(self.stream, "synchronize") else rt.synchronize()
+        return out
 
     def launch_adaptive(self, T: float, dt: float, dts: Optional[float] = None, *, rtol: float = 1e-3, atol: float = 1e-6,
                         max_step: float = np.inf, method: Optional[str] = None, max_attempts: int = 50_000_000, **unknown):

@@ -136,7 +136,10 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     param_grid DataFrame re-indexed '<name>_<i>')`` — but the circuit is compiled ONCE as a single instance
     and all grid points are integrated as one batch (one CUDA thread per grid point).  Extra keywords:
     ``as_arrays=True`` returns ``(ndarray[n_samples, n_out, B], param_grid)`` without building the frame;
-    ``shard=(rank, world)`` integrates only that contiguous slice of the grid (one process per GPU).
+    ``shard=(rank, world)`` integrates only that contiguous slice of the grid (one process per GPU);
+    ``reduce=True`` reduces every output over time ON THE DEVICE (samples at times >= ``cutoff``) and returns a frame with
+    index ``('mean', 'var', 'min', 'max', 'last')`` (or ``ndarray[5, n_out, B]``) instead of the trajectories — fixed-step
+    solvers, instance model.
     """
     import pandas as pd
     from pyrates import CircuitTemplate
@@ -152,6 +155,7 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     solver = kwargs.pop("solver", "euler")
     cutoff = kwargs.pop("cutoff", 0.0)
     as_arrays = kwargs.pop("as_arrays", False)
+    reduce = bool(kwargs.pop("reduce", False))
     shard = kwargs.pop("shard", None)
     verbose = kwargs.pop("verbose", False)
     kwargs.pop("clear", None)
@@ -226,10 +230,13 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
         try:
             sw = BatchedSweep(prog, sweep, base["observers"], solver=solver, T=simulation_time, dt=step_size,
                               dts=sampling_step_size, n_inst=B, chunk_samples=chunk_samples,
-                              const_div_to_mul=const_div_to_mul, solver_kwargs=solver_kw, fast_math=fast_math)
+                              const_div_to_mul=const_div_to_mul, solver_kwargs=solver_kw, fast_math=fast_math,
+                              reduce=reduce, cutoff=cutoff)
         except UnsupportedModelError as e:
             if exec_model == "instance" or "too large" not in str(e):
                 raise
+    if sw is None and reduce:
+        raise NotImplementedError("reduce=True is implemented for sweeps of the instance execution model")
     if sw is not None:
         try:
             for elem, k in y0_rows:
@@ -255,12 +262,17 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     step = sampling_step_size if sampling_step_size else step_size
     times = np.linspace(0.0, simulation_time, num=round(simulation_time / step), endpoint=False)
     if as_arrays:
-        return res[times >= cutoff], param_grid
+        return (res if reduce else res[times >= cutoff]), param_grid
     columns, data = [], []
     for o, (key, nodes, opvar) in enumerate(base["columns"]):
         for i in range(B):
             columns.append((key, circuit_names[lo + i]) + nodes + (opvar,))
         data.append(res[:, o, :])
+    if reduce:
+        from .engine import InstanceSession
+        frame = pd.DataFrame(np.concatenate(data, axis=1), columns=pd.MultiIndex.from_tuples(columns),
+                             index=list(InstanceSession.REDUCE_STATS))
+        return frame, param_grid
     frame = pd.DataFrame(np.concatenate(data, axis=1) if data else np.zeros((len(times), 0)),
                          columns=pd.MultiIndex.from_tuples(columns), index=times)
     return frame.loc[cutoff:, :], param_grid

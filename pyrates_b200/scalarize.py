@@ -565,9 +565,7 @@ class _Interp:
                 if isinstance(node, ast.Call) and getattr(node.func, "id", None) == "roll":
                     if node.args and isinstance(node.args[0], ast.Name):
                         rolled.add(node.args[0].id)
-                if isinstance(node, ast.Call) and getattr(node.func, "id", None) == "interp_rows":
-                    raise UnsupportedModelError("multi-column interpolated (adaptive-step) inputs are not supported")
-                if isinstance(node, ast.Call) and getattr(node.func, "id", None) == "interp":
+                if isinstance(node, ast.Call) and getattr(node.func, "id", None) in ("interp", "interp_rows"):
                     for arg in node.args[1:]:
                         if isinstance(arg, ast.Name):
                             self.interp_args.add(arg.id)       # (time, value) tables: read from memory, never unrolled
@@ -693,6 +691,24 @@ class _Interp:
             self.tables.append(TableSpec(n.args[1].id, xp.shape, xp))
             self.tables.append(TableSpec(n.args[2].id, fp.shape, fp))
             return _obj(g._node("interp", (tv[()].id,), (len(self.tables) - 2, len(self.tables) - 1, int(xp.size))))
+        if fname == "interp_rows":
+            # vector-valued timed inputs of adaptive runs: `interp_rows(t, time, u_input)` interpolates every column of the
+            # (steps, n_cols) table (frontend/template/circuit.py:1696-1700) -> one 'interp' node per column
+            if len(n.args) != 3 or not all(isinstance(a, ast.Name) for a in n.args[1:]):
+                raise UnsupportedModelError(f"unsupported interp_rows call `{ast.unparse(n)}`")
+            tv = self._arr(self.ev(n.args[0]))
+            xp = np.asarray(_real_table(n.args[1].id, self.p.arg(n.args[1].id).value), dtype=np.float64)
+            fp = np.asarray(_real_table(n.args[2].id, self.p.arg(n.args[2].id).value), dtype=np.float64)
+            if tv.ndim != 0 or xp.ndim != 1 or fp.ndim != 2 or fp.shape[0] != xp.size or xp.size < 2:
+                raise UnsupportedModelError("interp_rows is supported for a scalar time over (time[n], values[n, cols]) tables")
+            self.tables.append(TableSpec(n.args[1].id, xp.shape, xp))
+            tx = len(self.tables) - 1
+            out = np.empty(fp.shape[1], dtype=object)
+            for c in range(fp.shape[1]):
+                col = np.ascontiguousarray(fp[:, c])
+                self.tables.append(TableSpec(f"{n.args[2].id}[:, {c}]", col.shape, col))
+                out[c] = g._node("interp", (tv[()].id,), (tx, len(self.tables) - 1, int(xp.size)))
+            return out
         args = [self.ev(a) for a in n.args]
         if fname in UNARY_FUNCS:
             return self._map1(fname, args[0])

@@ -225,6 +225,35 @@ def test_grid_search_cuda_matches_reference_grid_search(gpu, registered, solver)
 
 @pytest.mark.gpu
 @needs_ref
+def test_grid_search_reduce_equals_statistics_of_the_reference_frames(gpu, registered):
+    """grid_search(reduce=True, cutoff=...): per-grid-point mean / var / min / max / last computed on the device == the same
+    statistics of the frame the REFERENCE's grid_search produced (golden), same column labels."""
+    import pyrates
+    from pyrates.utility import linearize_grid
+    fx = orc.load_fixture(golden_path("jrc_grid_b16"))
+    grid = linearize_grid({"C": np.linspace(68.0, 1350.0, 4), "u": np.linspace(120.0, 320.0, 4)}, permute=True)
+    grid["C2"], grid["C4"] = 0.8 * grid["C"], 0.25 * grid["C"]
+    param_map = {"C": {"vars": ["weight"], "edges": [("pc/pro/m", "ein/rpo_e/m_in")]},
+                 "C2": {"vars": ["weight"], "edges": [("ein/pro/m", "pc/rpo_e_in/m_in")]},
+                 "C4": {"vars": ["weight"], "edges": [("pc/pro/m", "iin/rpo_e/m_in"), ("iin/pro/m", "pc/rpo_i/m_in")]},
+                 "u": {"vars": ["rpo_e_in/u"], "nodes": ["pc"]}}
+    cutoff = 0.02
+    res, pmap = pyrates.grid_search("model_templates.neural_mass_models.jansenrit.JRC", grid, param_map, step_size=1e-4,
+                                    simulation_time=0.05, outputs={"v": "pc/rpo_e_in/v"}, sampling_step_size=1e-3,
+                                    solver="heun", backend="cuda", float_precision="float64", verbose=False, reduce=True,
+                                    cutoff=cutoff)
+    ref_cols = [tuple(c) for c in json.loads(bytes(fx["extra"]["frame_columns"]).decode())]
+    assert [tuple(map(str, c)) for c in res.columns] == ref_cols and list(res.index) == ["mean", "var", "min", "max", "last"]
+    frame = fx["extra"]["frame_heun"]
+    times = np.linspace(0.0, 0.05, num=frame.shape[0], endpoint=False)
+    keep = frame[times >= cutoff]
+    want = np.stack([keep.mean(axis=0), keep.var(axis=0), keep.min(axis=0), keep.max(axis=0), keep[-1]])
+    scale = np.max(np.abs(keep), axis=0)
+    assert np.max(np.abs(res.values - want) / np.stack([scale, scale ** 2, scale, scale, scale])) <= 1e-9
+
+
+@pytest.mark.gpu
+@needs_ref
 @pytest.mark.parametrize("precision,solver", [("float64", "heun"), ("float32", "euler")])
 def test_grid_search_over_population_network_matches_reference_runs(gpu, registered, precision, solver):
     """grid_search over a *network* (WC population, dense Connectivity shared by all grid points): the grid steps as one

@@ -111,7 +111,7 @@ def test_adaptive_rk45_matches_reference_scipy(gpu, name):
     # a piecewise-linear input makes the embedded error estimate jump at every knot: accept / reject decisions then hang on
     # the last bit (perturbing y0 by 2e-16 moves the ORACLE by 2.8e-5 and changes its attempt count 451 -> 470), so this
     # fixture is compared at the solver's own accuracy; the interpolation itself is pinned by the rhs test below
-    tol = 1e-3 if name == "qif_input_rk45" else 1e-9
+    tol = 1e-3 if "_input_" in name else 1e-9
     assert traj_rel_err(out[:, :, 0], ref) <= tol, name
 
 
@@ -240,6 +240,42 @@ def test_dde_sweep_matches_per_instance_oracle(gpu, solver):
         args[fx["names"].index("a")] = np.float64(table[1, b])
         rec = orc.run_adaptive(f, args, T, dt, dts)[0] if solver == "scipy" else orc.run(f, args, T, dt, dts, solver)[0]
         assert traj_rel_err(out[:, :, b], rec) <= 1e-9, (solver, b)
+
+
+@pytest.mark.parametrize("name,solver", [("jrc", "rk4"), ("qif_f32", "heun"), ("dde_mg", "euler")])
+def test_on_device_observer_reduction_matches_numpy_statistics(gpu, name, solver):
+    """reduce=True: mean / var / min / max / last of every observer over the decimated samples at times >= cutoff, computed
+    in registers by the integration kernel, equal NumPy's statistics of the full trajectories of the same sweep."""
+    from pyrates_b200.sweep import BatchedSweep
+    prog = Program.load(golden_path(name))
+    r = orc.load_fixture(golden_path(name))["run"]
+    sweep = {"jrc": [("u", 0), ("weight", 0)], "qif_f32": [("eta", 0)], "dde_mg": [("bet", 0), ("a", 0)]}[name]
+    B = 130
+    rng = np.random.default_rng(3)
+    base = np.array([float(np.asarray(prog.arg(a).value).reshape(-1)[e]) for a, e in sweep])
+    table = base[:, None] * rng.uniform(0.8, 1.2, (len(sweep), B))
+    obs = list(range(min(prog.n_state, 3)))
+    T, dt, dts = r["T"], r["dt"], (r["dts"] or r["dt"])
+    cutoff = 0.25 * T
+    kw = dict(solver=solver, T=T, dt=dt, dts=dts, n_inst=B, const_div_to_mul=False)
+    full_sw = BatchedSweep(prog, sweep, obs, chunk_samples=9, **kw)
+    red_sw = BatchedSweep(prog, sweep, obs, reduce=True, cutoff=cutoff, **kw)
+    try:
+        full = np.array(full_sw.run(table), copy=True)
+        before = rt.launch_count()
+        red = np.array(red_sw.run(table), copy=True)
+        assert rt.launch_count() == before + 1 and red_sw.d2h_bytes == 5 * len(obs) * B * full.itemsize
+    finally:
+        full_sw.free()
+        red_sw.free()
+    times = np.linspace(0.0, T, num=full.shape[0], endpoint=False)
+    keep = full[times >= cutoff].astype(np.float64)
+    assert red.shape == (5, len(obs), B) and 0 < keep.shape[0] < full.shape[0]
+    tol = 1e-12 if prog.float_precision == "float64" else 2e-5
+    scale = np.max(np.abs(keep), axis=0) + 1e-300
+    for k, want in enumerate([keep.mean(axis=0), keep.var(axis=0), keep.min(axis=0), keep.max(axis=0), keep[-1]]):
+        s = scale ** 2 if k == 1 else scale
+        assert np.max(np.abs(red[k] - want) / s) <= tol, InstanceModel.__name__ + f" stat {k}"
 
 
 def test_interpolated_input_rhs_matches_numpy_interp(gpu):
