@@ -28,10 +28,10 @@ __device__ __forceinline__ void prb_axpy(real (&o)[N], const real (&y)[N], const
 #define PRB_MIN_BLOCKS 1
 #endif
 
-// fast_math kernels read 2^(j/256) from shared memory (divergent indices: a __constant__ read would serialise)
+// fast_math kernels read 2^(j/2048) from shared memory (divergent indices: a __constant__ read would serialise)
 #ifdef PRB_USE_ETAB
-#define PRB_STAGE_ETAB __shared__ double prb_etab[256]; \
-    for (int q = threadIdx.x; q < 256; q += blockDim.x) prb_etab[q] = PRB_EXP_TAB[q]; \
+#define PRB_STAGE_ETAB __shared__ double prb_etab[PRB_ETAB_N]; \
+    for (int q = threadIdx.x; q < PRB_ETAB_N; q += blockDim.x) prb_etab[q] = PRB_EXP_TAB[q]; \
     __syncthreads();
 #define PRB_SET_ETAB T.etab = prb_etab; T.etab_s = (unsigned int)__cvta_generic_to_shared(prb_etab);
 #else
