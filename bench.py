@@ -39,8 +39,8 @@ SWEEP = [("u", 0), ("weight_v2", 0), ("weight_v2", 1), ("weight", 0), ("weight_v
 NCU_TRAFFIC_BYTES_PER_LAUNCH = 958.2e6
 # per-launch DRAM bytes by instance-steps per launch: 1000-step launches (--chunk-samples 100) and the default 250-step
 # launches (--chunk-samples 25; profiles/r01_c2_fastmath_chunk25_ncu_full.txt)
-NCU_TRAFFIC = {2 ** 20 * 1000: NCU_TRAFFIC_BYTES_PER_LAUNCH, 2 ** 20 * 250: 328.79e6}    # 109.10 + 219.68 MB (r01_c2_exp2048 capture)
-FP64_INSTR = {True: 305, False: 505}     # fp64-pipe instructions per instance-step in the loop (cuobjdump, fast / exact kernel)
+NCU_TRAFFIC = {2 ** 20 * 1000: NCU_TRAFFIC_BYTES_PER_LAUNCH, 2 ** 20 * 250: 331.16e6}    # 109.19 + 221.97 MB (r01_c2_reassoc capture)
+FP64_INSTR = {True: 265, False: 505}     # fp64-pipe instructions per instance-step in the loop (cuobjdump, fast / exact kernel)
 METRIC = "state-updates/sec (nodes x sweeps x steps/s), JRC RK4 grid_search"
 UNIT = "node-steps/s"
 
@@ -270,7 +270,7 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                      "traffic": (NCU_TRAFFIC.get(int(inst_steps_per_launch)) if a.grid == 1024 else None),
-                     "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_c2_exp2048_prb_integrate_ncu_full.txt)",
+                     "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_c2_reassoc_prb_integrate_ncu_full.txt)",
                      "algorithmic_bytes_per_launch": B_ALG * inst_steps_per_launch, "peak_source": which, "kernel": "prb_integrate (fused JRC rhs + RK4 + observer store)",
                      "algorithmic_bytes_per_instance_step": B_ALG, "launch_ms": launch_s * 1e3,
                      "note": "state/stages are register-resident across the launch: real DRAM traffic is only the "

@@ -99,8 +99,11 @@ def _lit(v: float, f32: bool) -> str:
 
 def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time: bool = False,
                   fast_math: bool = False, spec: bool = False, round_dy_f32: bool = False,
-                  slot_consts: Optional[dict] = None, model_f32: bool = False) -> List[str]:
-    """Straight-line statements computing dy[] (+ ring / slot stores) from y[], T."""
+                  slot_consts: Optional[dict] = None, model_f32: bool = False,
+                  hoist: Optional[List[str]] = None) -> List[str]:
+    """Straight-line statements computing dy[] (+ ring / slot stores) from y[], T.  With ``hoist`` (a list that receives
+    statements for prb_thread_init), thread-invariant sub-expressions — literals and swept parameters only, grouped by
+    ``reassoc.fold_invariants`` — are computed once per thread into ``T.q[k]`` with exact arithmetic."""
     g = rhs.graph
     ring_off = np.cumsum([0] + [r.rows * r.length for r in rhs.rings])
     tab_off = np.cumsum([0] + [int(np.prod(t.shape)) for t in rhs.tables])
@@ -117,8 +120,16 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
             lit_table.append(v)
         return f"PRB_LIT[{lit_table.index(v)}]"
 
+    qslot: dict = {}
+    invariant: dict = {}
+    if hoist is not None:
+        from .reassoc import invariant_nodes
+        invariant = invariant_nodes(rhs)
+
     def ref(i: int, want_real: bool = True) -> str:
         op = g.ops[i]
+        if i in qslot:
+            return f"T.q[{qslot[i]}]"
         if op == "const":
             v = g.const_value(i)
             if g.isint[i]:
@@ -154,6 +165,15 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
                 break
         return i, f
 
+    def safe_divisor(i: int) -> bool:
+        if g.ops[i] != "add":
+            return False
+        x, y_ = g.args[i]
+        for c, e in ((x, y_), (y_, x)):
+            if g.is_const(c) and g.ops[e] == "exp" and 1e-200 <= float(g.const_value(c)) <= 1e200:
+                return True
+        return False
+
     live = list(rhs.live_nodes())
     if fast_math:
         # nodes that only fed a folded chain are dead now: recompute liveness over the rewritten expressions
@@ -163,6 +183,9 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
             if i in needed:
                 continue
             needed.add(i)
+            if hoist is not None and invariant.get(i):
+                stack.extend(g.args[i])          # hoisted nodes are emitted as plain expressions of their operands
+                continue
             if not g.isint[i] and g.ops[i] in ("mul", "div"):
                 base, f = const_chain(i)
                 if base != i and math.isfinite(f) and f != 0.0:
@@ -177,6 +200,16 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
         op, a = g.ops[i], g.args[i]
         if op in ("const", "state", "param", "t"):
             continue
+        if hoist is not None and invariant.get(i) and not g.isint[i]:
+            # thread-invariant: once per thread, exact arithmetic (prb_thread_init)
+            plain = {"add": "{0} + {1}", "sub": "{0} - {1}", "mul": "{0} * {1}", "div": "{0} / {1}", "neg": "-{0}",
+                     "pow": "pow({0}, {1})", "maximum": "prb_max({0}, {1})", "minimum": "prb_min({0}, {1})",
+                     "sign": "prb_sign({0})"}
+            fmt = plain.get(op) or (_FUNC[op] + "({0})" if op in _FUNC else None)
+            if fmt is not None:
+                qslot[i] = len(qslot)
+                hoist.append(f"T.q[{qslot[i]}] = " + fmt.format(*[ref(x) for x in a]) + ";")
+                continue
         if op == "hist":
             # delayed state: the query time follows NumPy's promotion in the reference-generated text (base_backend.py:442-444)
             hv, scale, dhex, strong = g.payload[i]
@@ -229,6 +262,10 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
                 expr = f"{ref(a[0])} * {lit(inv)}"
             elif fast_math and f32:
                 expr = f"__fdividef({ref(a[0])}, {ref(a[1])})"          # rcp.approx + mul: 2 ulp (|divisor| < 2^126)
+            elif fast_math and not f32 and spec and g.is_const(a[0]) and float(g.const_value(a[0])) == 1.0:
+                # bare reciprocal: no final multiply; no range check when the divisor is c + exp(.) with a moderate c > 0
+                # (the exp's own check already confines it to [c, c + e^700], inside the reciprocal's fast range)
+                expr = f"prb_spec_rcp_nc({ref(a[1])})" if safe_divisor(a[1]) else f"prb_spec_rcp({ref(a[1])}, bad)"
             elif fast_math and not f32:
                 expr = f"prb_spec_div({ref(a[0])}, {ref(a[1])}, bad)" if spec else f"prb_fast_div({ref(a[0])}, {ref(a[1])})"
             else:
@@ -323,8 +360,14 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     # reference's own test_3_2_qif_theta then fails with "step size too small"); reproduce the reference instead.
     arith64 = adaptive and f32
     body_f32 = f32 and not arith64
-    body = emit_rhs_body(rhs, body_f32, const_div_to_mul, float_time=adaptive, fast_math=fast_math, spec=spec,
-                         round_dy_f32=arith64, slot_consts=slot_consts, model_f32=f32)
+    hoist: Optional[List[str]] = None
+    fast_rhs = rhs
+    if spec and not adaptive and rhs.n_out is None and not n_hist:
+        # FP64-pipe-bound sweeps: group thread-invariant factors (swept parameters x literals) and compute them once per thread
+        from .reassoc import fold_invariants
+        fast_rhs, hoist = fold_invariants(rhs), []
+    body = emit_rhs_body(fast_rhs, body_f32, const_div_to_mul, float_time=adaptive, fast_math=fast_math, spec=spec,
+                         round_dy_f32=arith64, slot_consts=slot_consts, model_f32=f32, hoist=hoist)
     exact_body = emit_rhs_body(rhs, body_f32, const_div_to_mul, float_time=adaptive, round_dy_f32=arith64,
                                slot_consts=slot_consts, model_f32=f32) if spec else None
     spec = spec and any("prb_spec_" in l for l in body)
@@ -352,6 +395,7 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
         if adaptive:
             raise UnsupportedModelError("on-device observer reduction is implemented for the fixed-step solvers")
         src.append("#define PRB_REDUCE 1")
+    src.append(f"#define PRB_NQ {len(hoist) if hoist else 0}")
     src.append(f"#define PRB_NH {n_hist}")
     src.append(f"#define PRB_HDEPTH {hist_depth}")
     if adaptive and solver != "dopri5_dde":
@@ -363,6 +407,7 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
 struct PrbThread {
     long long b, B;
     real p[PRB_NP > 0 ? PRB_NP : 1];
+    areal q[PRB_NQ > 0 ? PRB_NQ : 1];     // thread-invariant sub-expressions (fast_math: reassoc.fold_invariants)
     int head[PRB_NRINGS > 0 ? PRB_NRINGS : 1];
     real* __restrict__ slots;
     real* __restrict__ rings;
@@ -457,7 +502,7 @@ __device__ __forceinline__ double prb_spec_exp(const double z, const unsigned in
     bad |= (unsigned int)(__double2hiint(z) & 0x7fffffff) > 0x4085e000u;     // |z| > 700 (or NaN)
     const double t = fma(z, PRB_EXP_K[0], 6755399441055744.0);
     const int n = __double2loint(t);
-    const double nd = t - 6755399441055744.0;
+    const double nd = t - 6755399441055744.0;                                // (an I2F on the conversion pipe instead was measured: no gain)
     double r = fma(nd, PRB_EXP_K[1], z);
     r = fma(nd, PRB_EXP_K[2], r);
     double q = fma(r, 1.0 / 6.0, PRB_EXP_K[3]);
@@ -475,6 +520,19 @@ __device__ __forceinline__ double prb_spec_div(const double a, const double b, b
     const double e = fma(-b, r, 1.0);                  // r0 = (1 - e) / b with |e| <= ~2^-20
     r = fma(r, fma(e, e, e), r);                       // cubic step: r0 (1 + e + e^2) = (1 - e^3) / b
     return a * r;
+}
+__device__ __forceinline__ double prb_spec_rcp_nc(const double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    const double e = fma(-b, r, 1.0);
+    return fma(r, fma(e, e, e), r);
+}
+__device__ __forceinline__ double prb_spec_rcp(const double b, bool& bad) {
+    bad |= (((unsigned int)__double2hiint(b) & 0x7ff00000u) - 0x04000000u) >= 0x77c00000u;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    const double e = fma(-b, r, 1.0);
+    return fma(r, fma(e, e, e), r);
 }
 __device__ __forceinline__ double prb_fast_div(const double a, const double b) {
     const double ab = fabs(b);
@@ -514,12 +572,21 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
 """.replace("@@EXP_TABLES@@\n", exp_tables()))
     if use_etab:
         src.append("#define PRB_USE_ETAB 1")
+    if body and body[0].startswith("// PRB_LIT = {"):
+        vals = body.pop(0)[len("// PRB_LIT = {"):-1]
+        src.append(f"__device__ __constant__ double PRB_LIT[{vals.count(',') + 1}] = {{{vals}}};")
     init = ["__device__ __forceinline__ void prb_thread_init(PrbThread& T, const prb_kernel_args& A, long long b) {",
             "    T.b = b; T.B = A.n_inst; T.etab = nullptr; T.etab_s = 0u;",
             "    T.slots = (real*)A.slots; T.rings = (real*)A.rings; T.tables = (const real*)A.tables;"]
     if np_:
         init.append("    const real* __restrict__ P = (const real*)A.params;")
         init.append("    _Pragma(\"unroll\") for (int k = 0; k < PRB_NP; ++k) T.p[k] = P[(long long)k * T.B + b];")
+    for line in hoist or []:
+        init.append("    " + line)
+    if hoist:
+        # keep the invariants in registers: without the barrier the compiler rematerialises cheap ones (q = 100 * q') inside
+        # the time loop, i.e. puts the multiplies we just hoisted back on the FP64 pipe (seen in SASS)
+        init.append("    _Pragma(\"unroll\") for (int k = 0; k < PRB_NQ; ++k) asm volatile(\"\" : \"+d\"(T.q[k]));")
     for k, r in enumerate(rhs.rings):
         init.append(f"    T.head[{k}] = (int)((A.eval0 * {r.rolls_per_eval}LL) % {r.length}LL);")
     if n_hist and not adaptive:
@@ -549,9 +616,6 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
         init.append("\n".join(push))
     init.append("__device__ __forceinline__ void prb_thread_exit(PrbThread&, const prb_kernel_args&, long long) {}")
     src.append("\n".join(init))
-    if body and body[0].startswith("// PRB_LIT = {"):
-        vals = body.pop(0)[len("// PRB_LIT = {"):-1]
-        src.append(f"__device__ __constant__ double PRB_LIT[{vals.count(',') + 1}] = {{{vals}}};")
     if spec:
         src.append("__device__ __noinline__ void prb_rhs_exact(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NDY], PrbThread& T) {")
         src.extend("    " + l for l in exact_body)

@@ -61,12 +61,18 @@ class BatchedSweep:
             fast_math = const_div_to_mul     # one switch: every <= 2 ulp instruction-count reduction of the fp64 kernels
         if self.adaptive:
             const_div_to_mul, fast_math, min_blocks = False, False, 1   # RK45 keeps 7 stage vectors in registers: no occupancy cap
-        if fast_math and min_blocks == 5:
-            # fp64: the leaner fast_math loop prefers registers over occupancy (scripts/tune_inst.py: 22.6 vs 23.3 ms);
+        launch_bounds = min_blocks if block == 128 else 1
+        if fast_math and min_blocks == 5 and block == 128:
+            # fp64: the leaner fast_math loop prefers registers over occupancy; after the invariant-folding pass
+            # (reassoc.py) 64-thread blocks x 7 (128 registers, 16 warps/SM) measured best on the JRC/RK4 sweep
+            # (scripts/tune_inst.py: 20.29 ms per 1000 steps x 2^20 vs 21.26 at 128 x 4, 23.06 at 128 x 5);
             # fp32 (half the registers per value): 8 blocks x 128 threads at 64 registers (scripts/bench_f32.py)
-            min_blocks = 8 if prog.float_precision == "float32" else 4
+            if prog.float_precision == "float32":
+                launch_bounds = 8
+            else:
+                block, launch_bounds = 64, 7
         self.model = InstanceModel(prog, solver=solver, sweep=sweep, observers=observers, block=block,
-                                   const_div_to_mul=const_div_to_mul, min_blocks=min_blocks if block == 128 else 1,
+                                   const_div_to_mul=const_div_to_mul, min_blocks=launch_bounds,
                                    fast_math=fast_math, rk_method=self.solver_kwargs.get("method"), reduce=self.reduce)
         order = [(p.arg, p.elem) for p in self.model.rhs.params]
         self._perm = [order.index((a, int(e))) for a, e in sweep]      # user row k -> kernel param row
