@@ -362,7 +362,7 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     body_f32 = f32 and not arith64
     hoist: Optional[List[str]] = None
     fast_rhs = rhs
-    if spec and not adaptive and rhs.n_out is None and not n_hist:
+    if (spec or (fast_math and f32 and pure)) and not adaptive and rhs.n_out is None and not n_hist:
         # FP64-pipe-bound sweeps: group thread-invariant factors (swept parameters x literals) and compute them once per thread
         from .reassoc import fold_invariants
         fast_rhs, hoist = fold_invariants(rhs), []
@@ -586,7 +586,8 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
     if hoist:
         # keep the invariants in registers: without the barrier the compiler rematerialises cheap ones (q = 100 * q') inside
         # the time loop, i.e. puts the multiplies we just hoisted back on the FP64 pipe (seen in SASS)
-        init.append("    _Pragma(\"unroll\") for (int k = 0; k < PRB_NQ; ++k) asm volatile(\"\" : \"+d\"(T.q[k]));")
+        init.append("    _Pragma(\"unroll\") for (int k = 0; k < PRB_NQ; ++k) asm volatile(\"\" : \"+%s\"(T.q[k]));"
+                    % ("f" if body_f32 else "d"))
     for k, r in enumerate(rhs.rings):
         init.append(f"    T.head[{k}] = (int)((A.eval0 * {r.rolls_per_eval}LL) % {r.length}LL);")
     if n_hist and not adaptive:

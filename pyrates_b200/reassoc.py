@@ -19,7 +19,8 @@ the scalar DAG into that form:
 
 This is algebraically exact and changes rounding by a few ulp per folded factor — inside ``fast_math``'s contract (the
 trajectories stay within 1e-9 of the exact kernel; ``tests/test_gpu_fullsize.py``), never applied to the exact kernels.
-Only pure vector fields (no ring buffers / mutable slots) in float64 are rewritten.
+Only pure vector fields (no ring buffers / mutable slots) are rewritten (float64: speculative exp / reciprocal kernels;
+float32: `__expf` / `__fdividef` kernels — JRC RK4 sweep 3.7e11 -> 4.0e11 node-steps/s).
 """
 from __future__ import annotations
 
