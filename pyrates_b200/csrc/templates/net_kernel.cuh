@@ -107,13 +107,51 @@ __device__ __forceinline__ bool prb_spin_until(PrbNet& C, const unsigned long lo
 
 __device__ __forceinline__ void prb_grid_barrier(PrbNet& C) {
     __syncthreads();
+#if PRB_WORLD > 1 && PRB_BARRIER_PARALLEL
+    // two-level multi-GPU barrier: local arrivals on a gpu-scope counter; the LAST local arriver (it has observed every
+    // other CTA's fenced stores) publishes this rank's epoch to every peer with one store over NVLink; every CTA then
+    // waits for the local count and for the epoch flags of all peers.  Warp 0 waits in ONE converged polling loop: lane 0
+    // on the local counter, lane 1 + q on peer q's flag.  Opt-in (PRB_BARRIER_PARALLEL=1): measured against the serial
+    // variant below on 8 GPUs it is within run-to-run noise, and ~1 us slower with a single peer.
+    if (threadIdx.x < 32) {
+        C.bar_target += gridDim.x;
+        C.epoch += 1ULL;
+        const int lane = threadIdx.x;
+        if (lane == 0) {
+            __threadfence_system();
+            const unsigned long long old = atomicAdd(C.bar, 1ULL);
+            if (old + 1ULL == C.bar_target) {
+                __threadfence_system();
+#pragma unroll
+                for (int p = 0; p < PRB_WORLD; ++p)
+                    if (p != PRB_RANK)
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(C.peer_sync[p] + 8 + PRB_RANK), "l"(C.epoch) : "memory");
+            }
+        }
+        __syncwarp();
+        const bool active = lane == 0 || (lane <= PRB_WORLD && lane - 1 != PRB_RANK);
+        const unsigned long long* flag = lane == 0 ? C.bar : C.bar + 8 + (active ? lane - 1 : 0);
+        const unsigned long long target = lane == 0 ? C.bar_target : C.epoch;
+        const long long t0 = clock64();
+        unsigned int it = 0;
+        for (;;) {
+            const bool done = !active || prb_ld_acquire<true>(flag) >= target;
+            if (__all_sync(0xffffffffu, done)) break;
+            if ((++it & 1023u) == 0) {
+                bool stop = prb_ld_acquire<false>(C.bar + 2) != 0ULL;
+                if (!stop && clock64() - t0 > PRB_SPIN_LIMIT) { atomicExch(C.bar + 2, 1ULL); stop = true; }
+                if (__any_sync(0xffffffffu, stop)) break;
+            }
+        }
+        __threadfence_system();
+    }
+#else
     if (threadIdx.x == 0) {
         C.bar_target += gridDim.x;
         C.epoch += 1ULL;
 #if PRB_WORLD > 1
-        // two-level multi-GPU barrier: local arrivals on a gpu-scope counter; the LAST local arriver (it has observed
-        // every other CTA's fenced stores) publishes this rank's epoch to every peer with one release store over
-        // NVLink; every CTA then waits for the local count and for the epoch flags of all peers.
+        // serial variant: thread 0 arrives, the last local arriver publishes the epoch, then thread 0 waits for the local
+        // count and for the peers' flags one after the other
         __threadfence_system();
         const unsigned long long old = atomicAdd(C.bar, 1ULL);
         if (old + 1ULL == C.bar_target) {
@@ -135,6 +173,7 @@ __device__ __forceinline__ void prb_grid_barrier(PrbNet& C) {
         __threadfence();
 #endif
     }
+#endif
     __syncthreads();
 }
 

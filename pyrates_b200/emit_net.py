@@ -6,6 +6,8 @@ between) — and splices it into the hand-written solver template ``csrc/templat
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Set, Tuple
 
@@ -596,6 +598,11 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     src.append(f"#define PRB_NB {nb}")
     src.append(f"#define PRB_RANK {rank}")
     src.append(f"#define PRB_WORLD {world}")
+    # multi-GPU barrier variant (net_kernel.cuh: prb_grid_barrier): 0 = thread 0 polls the peers' flags one after the other
+    # (default), 1 = warp 0 polls them in one converged loop.  Measured on 8 GPUs (profiles/r01_multigpu.md): no consistent
+    # difference (C3 N=8192 RK4 0.116 vs 0.103 ms/step, N=16384 Euler 0.0585 vs 0.0612) — polling is not what costs.
+    par = os.environ.get("PRB_BARRIER_PARALLEL")
+    src.append(f"#define PRB_BARRIER_PARALLEL {int(par) if par in ('0', '1') else 0}")
     src.append("#define PRB_OBS_INDEX(o) (o)" if all_state else f"#define PRB_OBS_INDEX(o) ((long long)A.iconsts[{obs_off}LL + (o)])")
     src.append("struct PrbNet;")
     src.append("__device__ __forceinline__ void prb_net_init_heads(PrbNet& C, long long eval0);")
