@@ -385,44 +385,90 @@ class InstanceSession:
                 b.free()
 
 
+_EVAL_MODELS: "dict" = {}          # structure key -> InstanceModel of the single-evaluation kernels (insertion-ordered, bounded)
+_EVAL_MODELS_MAX = 64
+
+
+def _eval_model(prog: Program, float_time: bool) -> InstanceModel:
+    """InstanceModel for ONE evaluation of ``prog``; cached by program structure.  Scalar float constants become runtime
+    parameters, so calls that only change parameter values (fitting / continuation loops around get_run_func /
+    get_jacobian_func, finite-difference probes) reuse both the lowered model and the compiled kernel."""
+    solver = "scipy" if float_time else "euler"
+    cand = [(a.name, e) for a in prog.args if a.kind == "const" and np.issubdtype(a.value.dtype, np.floating)
+            and a.value.size <= 8 for e in range(a.value.size)]
+    if not 0 < len(cand) <= 96:
+        cand = []
+    swept = {n for n, _ in cand}
+
+    def key(with_values_of_swept: bool):
+        sig = []
+        for a in prog.args:
+            v = np.asarray(a.value)
+            baked = a.kind in ("const", "var", "hist") and (with_values_of_swept or a.name not in swept)
+            sig.append((a.name, a.kind, v.shape, str(v.dtype), v.tobytes() if baked else None))
+        return (prog.source(), prog.float_precision, solver, tuple(sig))
+
+    for k, sweep in ((key(False), cand), (key(True), [])):
+        if k in _EVAL_MODELS:
+            m = _EVAL_MODELS[k]
+            if m is not None:
+                return m
+            continue                                # swept form known not to lower: try the baked form
+        try:
+            m = InstanceModel(prog, solver=solver, sweep=sweep)
+        except (KeyError, UnsupportedModelError):
+            if not sweep:
+                raise
+            m = None                                # a constant that must stay compile-time (unused, delay, table ...)
+        while len(_EVAL_MODELS) >= _EVAL_MODELS_MAX:
+            _EVAL_MODELS.pop(next(iter(_EVAL_MODELS)))
+        _EVAL_MODELS[k] = m
+        if m is not None:
+            return m
+    raise AssertionError("unreachable")
+
+
 def evaluate_rhs(prog: Program, t: Optional[float] = None, y: Optional[np.ndarray] = None) -> np.ndarray:
     """One evaluation ``dy = f(t, y, *args)`` of the vector field on the GPU (kernel ``prb_rhs_eval``).  Programs built
     for an adaptive solver carry a float ``t`` (optionally overridden by ``t``).  ``y`` of shape ``(n_state, B)`` evaluates a
     batch of B states in one launch (one thread each) and returns ``(n_out, B)``; Jacobian programs
     (``CudaBackend`` recording ``get_jacobian_func``) return their ``n*n`` entries row-major."""
-    float_time = not np.issubdtype(np.asarray(prog.arg_by_kind("t").value).dtype, np.integer)
-    # scalar float constants become runtime parameters: calls that only change parameter values (fitting / continuation
-    # loops around get_run_func / get_jacobian_func) reuse the compiled kernel (runtime.compile_module caches by source)
-    sweep = [(a.name, e) for a in prog.args if a.kind == "const" and np.issubdtype(a.value.dtype, np.floating)
-             and a.value.size <= 8 for e in range(a.value.size)]
-    m = None
-    if 0 < len(sweep) <= 96:
-        try:
-            m = InstanceModel(prog, solver="scipy" if float_time else "euler", sweep=sweep)
-        except (KeyError, UnsupportedModelError):
-            m = None                               # a constant that must stay compile-time (unused, delay, table ...)
-    if m is None:
-        m = InstanceModel(prog, solver="scipy" if float_time else "euler")
+    t_arg = np.asarray(prog.arg_by_kind("t").value)
+    float_time = not np.issubdtype(t_arg.dtype, np.integer)
+    m = _eval_model(prog, float_time)
     n_out = m.rhs.n_out if m.rhs.n_out is not None else m.n_state
     batch = None if y is None or np.ndim(y) < 2 else int(np.shape(y)[1])
     B = batch or 1
+    # the cached model may have been built from other values: state, parameters and time come from THIS program
+    y0 = prog.y0 if y is None else np.asarray(y, dtype=m.real).reshape(m.n_state, B)
+    params = None
+    if m.kernel.n_params:
+        vals = np.array([np.asarray(prog.arg(ps.arg).value).reshape(-1)[ps.elem] for ps in m.rhs.params], dtype=m.real)
+        params = np.repeat(vals[:, None], B, axis=1)
+    hist_y0 = m.hist_y0
+    if m.kernel.n_hist:
+        h0 = np.asarray(next(a.value for a in prog.args if a.kind == "hist"), dtype=np.float64).reshape(-1)
+        hist_y0 = h0[m.kernel.hist_vars]
     s = m.session(B, 0)
     d_dy = rt.DeviceBuffer(max(n_out, 1) * B * np.dtype(m.real).itemsize)
     d_extra = []
     try:
-        s.reset(y0=None if y is None else np.asarray(y, dtype=m.real).reshape(m.n_state, B))
+        s.reset(y0=y0, params=params)
         a = rt.KernelArgs()
         a.n_steps, a.store_step, a.step0, a.eval0, a.n_inst, a.sample0 = 0, 1, 0, 0, B, 0
-        a.t0, a.dt = (0, float(m.t0 if t is None else t)) if float_time else (int(m.t0), 0.0)
+        a.t0, a.dt = (0, float(t_arg if t is None else t)) if float_time else (int(t_arg), 0.0)
         a.y, a.out, a.params = s.d_y.ptr, d_dy.ptr, s.d_params.ptr
         a.slots, a.rings, a.tables = s.d_slots.ptr, s.d_rings.ptr, s.d_tables.ptr
         if m.kernel.n_hist and float_time:          # history = the initial condition only (a fresh DDEHistory)
             if B != 1:
                 raise rt.CudaBackendError("batched evaluation of delay-differential vector fields is not supported")
-            d_extra.append(rt.DeviceBuffer.from_host(np.concatenate([[0, 0, m.t0, 0, 0, 0, 0, 0, 1.0], m.hist_y0])))
+            d_extra.append(rt.DeviceBuffer.from_host(np.concatenate([[0, 0, float(t_arg), 0, 0, 0, 0, 0, 1.0], hist_y0])))
             d_extra.append(rt.DeviceBuffer((1 + m.kernel.n_hist) * 8))
             a.consts, a.work = d_extra[0].ptr, d_extra[1].ptr
         elif m.kernel.n_hist:
+            h = np.zeros((m.kernel.hist_depth, m.kernel.n_hist, B), dtype=m.real)
+            h[0] = hist_y0.astype(m.real)[:, None]
+            s.d_hist.upload(h)
             a.work, a.dt = s.d_hist.ptr, float(m.rhs.hist_dt)
         m.module.run("prb_rhs_eval", a, block=m.kernel.block)
         dy = np.empty((n_out, B), dtype=m.real)
