@@ -47,7 +47,13 @@ enum { PRB_SOLVER_EULER = 0, PRB_SOLVER_HEUN_REF = 1, PRB_SOLVER_HEUN = 2, PRB_S
        /* the reference's solver='scipy': solve_ivp(method='RK45', first_step=dt, t_eval=times), base_backend.py:802-812;
         * options (rtol, atol, t_start, t_bound, first_step, sample spacing, max_step, max attempts) are 8 doubles behind
         * args.consts, args.n_steps = samples, per-instance status words behind args.sync */
-       PRB_SOLVER_RK45 = 4 };
+       PRB_SOLVER_RK45 = 4,
+       /* the reference's solver='scipy' on a delay-differential model: scipy.integrate.ode('dopri5', first_step=dt,
+        * nsteps=50000) restarted per sample interval, accepted steps appended to the state history
+        * (BaseBackend._solve_scipy_dde, base_backend.py:771-800); options behind args.consts: [0] rtol [1] atol [2] t_start
+        * [4] first_step [5] sample spacing [7] nsteps [8] history capacity [9..] float64 initial condition of the history;
+        * args.work = history ring, status per instance behind args.sync (3 = ring too small, caller retries larger) */
+       PRB_SOLVER_DOPRI5 = 5 };
 
 /* Kernel argument block.  Passed BY VALUE as the single __grid_constant__ parameter of every generated
  * kernel; the generated CUDA source embeds the identical definition (pyrates_b200/csrc/prb_kernel_abi.h).
@@ -64,7 +70,10 @@ enum { PRB_SOLVER_EULER = 0, PRB_SOLVER_HEUN_REF = 1, PRB_SOLVER_HEUN = 2, PRB_S
  *   consts / iconsts               packed real / int32 constant arrays of network-mode kernels (W, idx; for the tcgen05
  *                                  sweep kernels also W split into hi / lo K-major 128 x 32 tiles); adaptive INSTANCE
  *                                  kernels read their 8 option doubles behind `consts`
- *   work                           network-mode scratch (stage vectors, materialised intermediates)
+ *   work                           network-mode scratch (stage vectors, materialised intermediates); instance kernels of
+ *                                  delay-differential models keep their state history here: fixed-step solvers a ring
+ *                                  [depth][n_hist][B] of past states, PRB_SOLVER_DOPRI5 times [cap][B] + states [cap][n_hist][B]
+ *   out (reduce kernels)           [5][n_obs][B]: mean, var, min, max, last of the observers over the samples >= sample0
  *   sync                           network-mode barrier words, 64-bit each (zero-initialised by the caller):
  *                                  [0] local CTA arrivals, [1] release epoch, [2] error flag, [8+q] arrival epoch of rank q
  *   peers                          multi-GPU network mode: device array of 3*world pointers
