@@ -85,6 +85,54 @@ def test_jrc_sweep_batch_matches_per_instance_oracle(gpu, solver):
         assert traj_rel_err(out[:, :, b], rec[:, [0, 2]]) <= 1e-9
 
 
+@pytest.mark.parametrize("T,dt,dts", [
+    (0.0101, 1e-3, 3e-3),     # round(T/dts) = 3 rows but steps 0, 3, 6, 9 sample: the reference overruns its buffer
+    (0.0119, 1e-3, 3e-3),     # sampling step does not divide the horizon: 12 steps, 4 rows
+    (6e-3, 1e-3, 5e-3),       # sampling step almost as long as the run: 6 steps, store_step 5, round(1.2) = 1 row, 2 sample points
+    (4e-4, 1e-3, None),       # horizon shorter than one step: round(0.4) = 0 steps, empty recording
+    (1e-3, 1e-3, None),       # exactly one step: the recording holds the initial state only
+    (0.0155, 1e-3, 2e-3),     # banker's rounding in np.round: 15.5 -> 16 steps, 7.75 -> 8 samples
+])
+@pytest.mark.parametrize("solver", ["euler", "heun"])
+def test_ragged_horizons_follow_the_reference_rounding(gpu, T, dt, dts, solver):
+    """Edge cases of BaseBackend._solve_euler/_solve_heun bookkeeping (base_backend.py:716-733): steps = round(T/dt),
+    rows = round(T/dts), store_step = round(dts/dt), a row whenever i % store_step == 0 — including recordings the
+    reference itself would overrun (more sample points than rows are not produced by these combinations)."""
+    fx = orc.load_fixture(golden_path("qif_sfa"))
+    prog = Program.load(golden_path("qif_sfa"))
+    f = orc.build_vector_field(fx["source"])
+    steps, store_step, n_samples = n_steps_for(T, dt, dts)
+    want_rows = len(range(0, steps, store_step))
+    if want_rows > n_samples:
+        # the reference's own recording buffer overruns (IndexError in its time loop): refused here before launching
+        with pytest.raises(IndexError):
+            orc.run(f, orc.fixture_args(fx), T, dt, dts, solver)
+        with pytest.raises(ValueError, match="would record"):
+            InstanceModel(prog, solver=solver).run(T, dt, dts)
+        return
+    ref, _ = orc.run(f, orc.fixture_args(fx), T, dt, dts, solver)
+    out, y_final = InstanceModel(prog, solver=solver).run(T, dt, dts)
+    got = out[:, :, 0]
+    assert got.shape == ref.shape == (n_samples, prog.n_state)
+    if want_rows:
+        assert traj_rel_err(got[:want_rows], ref[:want_rows]) <= 1e-9
+    # final state == the oracle's in-place updated y0 (the reference mutates its state vector)
+    args = orc.fixture_args(fx)
+    orc.run(f, args, T, dt, dts, solver)
+    assert np.allclose(y_final[:, 0], args[1], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("B", [1, 31, 129])
+def test_odd_batch_sizes_cover_partial_blocks_and_warps(gpu, B):
+    prog = Program.load(golden_path("jrc"))
+    m = InstanceModel(prog, solver="rk4", sweep=[("u", 0)], observers=[0])
+    u = np.linspace(120.0, 320.0, B)[None, :]
+    out, _ = m.run(0.02, 1e-4, 1e-3, params=u)
+    assert out.shape == (20, 1, B) and np.all(np.isfinite(out))
+    single, _ = m.run(0.02, 1e-4, 1e-3, params=u[:, -1:])
+    assert np.array_equal(single[:, :, 0], out[:, :, -1])
+
+
 def test_missing_device_buffers_are_rejected(gpu):
     a = rt.KernelArgs()
     a.n_steps, a.store_step, a.n_inst = 1, 1, 1
