@@ -212,14 +212,18 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
                 continue
         if op == "hist":
             # delayed state: the query time follows NumPy's promotion in the reference-generated text (base_backend.py:442-444)
-            hv, scale, dhex, strong = g.payload[i]
-            d = float.fromhex(dhex)
-            if scale is not None:
-                tq = f"((double)t * {float(scale)!r} - {d!r})"          # `t*dt - d`: int step * Python float -> float64
-            elif strong and model_f32:
-                tq = f"(double)((float)t - {float(np.float32(d))!r}f)"  # Python-float t - float32 array: a float32 operation
+            hv, scale, dkey, strong = g.payload[i]
+            if isinstance(dkey, tuple):                                 # swept delay: per-instance parameter
+                d, df = f"(double)T.p[{dkey[1]}]", f"(float)T.p[{dkey[1]}]"
             else:
-                tq = f"((double)t - {d!r})"
+                d = repr(float.fromhex(dkey))
+                df = repr(float(np.float32(float.fromhex(dkey)))) + "f"
+            if scale is not None:
+                tq = f"((double)t * {float(scale)!r} - {d})"            # `t*dt - d`: int step * Python float -> float64
+            elif strong and model_f32:
+                tq = f"(double)((float)t - {df})"                       # Python-float t - float32 array: a float32 operation
+            else:
+                tq = f"((double)t - {d})"
             lines.append(f"const areal v{i} = (areal)prb_hist(T, {hv}, {tq});")
             continue
         if fast_math and not g.isint[i] and op in ("mul", "div"):
@@ -308,7 +312,8 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
 
 def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: Sequence[int],
                      block: int = 128, const_div_to_mul: bool = False, min_blocks: int = 1,
-                     fast_math: bool = False, rk_method: str = "RK45", reduce: bool = False) -> InstKernel:
+                     fast_math: bool = False, rk_method: str = "RK45", reduce: bool = False,
+                     hist_max_delay: Optional[float] = None) -> InstKernel:
     """Generate the full CUDA C source of the fused rhs+solver instance kernel.  ``reduce``: the kernel keeps running
     statistics of the observers (mean, var, min, max, last) instead of storing every sample (fixed-step solvers)."""
     if solver not in SOLVER_IDS:
@@ -342,7 +347,13 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
             raise UnsupportedModelError("delay-differential models: fixed-step solvers need the `hist(t*dt - d)` form, "
                                         "solver='scipy' the `hist(t - d)` form of the vector field (rebuild for the solver)")
         if not adaptive:
-            need = int(math.ceil(max(rhs.hist_delays) / rhs.hist_dt)) + 3
+            dmax = max(rhs.hist_delays)
+            if rhs.hist_delay_params:
+                # swept delays: the ring must hold the longest delay of the sweep (the caller's bound on the parameter table)
+                if hist_max_delay is None:
+                    raise UnsupportedModelError("a swept history delay needs `hist_max_delay` (upper bound of the swept values)")
+                dmax = max(dmax, float(hist_max_delay))
+            need = int(math.ceil(dmax / rhs.hist_dt)) + 3
             hist_depth = 1 << max(2, (need - 1).bit_length())            # power of two: slot = step & (depth - 1)
     elif solver == "dopri5_dde":
         raise UnsupportedModelError("solver 'dopri5_dde' is the adaptive path of delay-differential models")

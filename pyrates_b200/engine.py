@@ -37,7 +37,7 @@ class InstanceModel:
     def __init__(self, prog: Program, *, solver: str = "euler", sweep: Sequence[Tuple[str, int]] = (),
                  observers: Optional[Sequence[int]] = None, block: int = 128, fmad: bool = True,
                  const_div_to_mul: bool = False, max_nodes: int = 6000, min_blocks: int = 1, fast_math: bool = False,
-                 rk_method: Optional[str] = None, reduce: bool = False):
+                 rk_method: Optional[str] = None, reduce: bool = False, hist_max_delay: Optional[float] = None):
         if solver not in FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS:
             raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
                                       f"Supported solvers: {list(FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS)}.")
@@ -59,7 +59,10 @@ class InstanceModel:
         self.kernel: InstKernel = emit_inst_kernel(self.rhs, solver=self.kernel_solver, precision=self.precision,
                                                    observers=self.observers, block=block,
                                                    const_div_to_mul=const_div_to_mul, min_blocks=min_blocks,
-                                                   fast_math=fast_math, rk_method=self.rk_method or "RK45", reduce=reduce)
+                                                   fast_math=fast_math, rk_method=self.rk_method or "RK45", reduce=reduce,
+                                                   hist_max_delay=hist_max_delay)
+        # swept delays of delay-differential models: the bound the history was sized for (checked against every table)
+        self.hist_max_delay = None if hist_max_delay is None else float(hist_max_delay)
         self.reduce = bool(reduce)
         self.fmad = fmad
         self._module: Optional[rt.Module] = None
@@ -173,7 +176,19 @@ class InstanceSession:
         params = np.ascontiguousarray(params, dtype=self.m.real)
         if params.shape != (k.n_params, B):
             raise ValueError(f"params must have shape ({k.n_params}, {B}), got {params.shape}")
+        self.check_delays(params)
         self.d_params.upload(params, self.stream)
+
+    def check_delays(self, params: np.ndarray):
+        """Swept delays must stay inside [0, hist_max_delay]: the history was sized for that bound."""
+        rows = self.m.rhs.hist_delay_params
+        if rows:
+            d = np.asarray(params)[rows]
+            bound = self.m.hist_max_delay if self.m.hist_max_delay is not None else max(self.m.rhs.hist_delays)
+            if not np.all((d >= 0) & (d <= bound * (1 + 1e-12))):
+                raise rt.CudaBackendError(f"swept history delays must lie in [0, {bound}] (hist_max_delay); got "
+                                          f"[{float(d.min())}, {float(d.max())}]")
+        self.delay_max = float(np.asarray(params)[rows].max()) if rows else None
 
     # -- launch
     def samples_in(self, n_steps: int, store_step: int) -> int:
@@ -309,7 +324,7 @@ class InstanceSession:
         if n_samples > self.n_samples:
             raise ValueError(f"session holds {self.n_samples} samples, the run records {n_samples}")
         te_step = (float(T) - 0.0) / n_samples if n_samples else 0.0
-        dmax = max(self.m.rhs.hist_delays)
+        dmax = max(self.m.rhs.hist_delays + ([self.m.hist_max_delay] if self.m.hist_max_delay is not None else []))
         if capacity is None:
             per_interval = 2 + min(int(np.ceil(te_step / dt)) if dt > 0 else 1, 8)
             capacity = max(256, int(2 * (np.ceil(dmax / max(te_step, 1e-300)) + 2) * per_interval))

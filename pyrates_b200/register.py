@@ -225,13 +225,26 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     grid_vals = {k: np.asarray(param_grid[k].values[lo:hi], dtype=np.float64) for k in keys}
     table = np.stack([grid_vals[k] for k in rows]) if rows else np.zeros((0, B))
 
+    # grid keys that land in history delays of a delay-differential model: the device-side history is sized for the
+    # longest delay of the grid
+    hist_max_delay = None
+    if prog.is_dde and sweep:
+        from .scalarize import scalarize
+        try:
+            pre = scalarize(prog, sweep)
+        except UnsupportedModelError:
+            pre = None
+        if pre is not None and pre.hist_delay_params:
+            idx = [sweep.index((pre.params[i].arg, pre.params[i].elem)) for i in pre.hist_delay_params]
+            hist_max_delay = float(np.max(table[idx]))
+
     sw = None
     if exec_model in ("auto", "instance"):
         try:
             sw = BatchedSweep(prog, sweep, base["observers"], solver=solver, T=simulation_time, dt=step_size,
                               dts=sampling_step_size, n_inst=B, chunk_samples=chunk_samples,
                               const_div_to_mul=const_div_to_mul, solver_kwargs=solver_kw, fast_math=fast_math,
-                              reduce=reduce, cutoff=cutoff)
+                              reduce=reduce, cutoff=cutoff, hist_max_delay=hist_max_delay)
         except UnsupportedModelError as e:
             if exec_model == "instance" or "too large" not in str(e):
                 raise

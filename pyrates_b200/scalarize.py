@@ -376,6 +376,7 @@ class ScalarRhs:
     hist_vars: List[int] = field(default_factory=list)
     hist_delays: List[float] = field(default_factory=list)
     hist_dt: Optional[float] = None
+    hist_delay_params: List[int] = field(default_factory=list)      # swept delays: parameter rows that are looked up as delays
 
     def live_nodes(self) -> List[int]:
         """Topologically ordered ids of all nodes reachable from the outputs."""
@@ -452,6 +453,7 @@ class _Interp:
         self.hist_vars: List[int] = []
         self.hist_delays: List[float] = []
         self.hist_dt: Optional[float] = None
+        self.hist_delay_params: List[int] = []
         self.hist_name = next((a.name for a in prog.args if a.kind == "hist"), None)
         self.jacobian = False
         self.tname = prog.arg_by_kind("t").name
@@ -829,14 +831,21 @@ class _Interp:
         # NumPy promotion of `t - d` in the reference: a named (array-typed) delay is strong, a literal is a Python float
         strong = not isinstance(dl, ast.Constant)
         dv = self.ev(dl)
+        dparam = None
         if isinstance(dv, (int, np.integer)):
             dval = float(dv)
         else:
             dv = self._arr(dv)
             dv = dv[()] if isinstance(dv, np.ndarray) and dv.ndim == 0 else (dv.reshape(-1)[0] if isinstance(dv, np.ndarray) and dv.size == 1 else dv)
-            if not isinstance(dv, Sym) or not g.is_const(dv.id):
-                raise UnsupportedModelError("history delays must be constants (not swept, not state-dependent)")
-            dval = float(g.const_value(dv.id))
+            if isinstance(dv, Sym) and g.ops[dv.id] == "param":
+                # swept delay (grid_search over `d`): a per-instance parameter; the history depth comes from the caller's
+                # bound on the table (InstanceModel(hist_max_delay=...))
+                dparam = int(g.payload[dv.id])
+                dval = float(self.params[dparam].default)
+            elif not isinstance(dv, Sym) or not g.is_const(dv.id):
+                raise UnsupportedModelError("history delays must be constants or swept parameters (not state-dependent)")
+            else:
+                dval = float(g.const_value(dv.id))
         if not (dval >= 0.0) or not math.isfinite(dval):
             raise UnsupportedModelError(f"history delay {dval!r}")
         if scale is not None:
@@ -853,7 +862,10 @@ class _Interp:
                 self.hist_vars.append(e)
             if dval not in self.hist_delays:
                 self.hist_delays.append(dval)
-            return g._node("hist", (), (self.hist_vars.index(e), scale, float(dval).hex(), strong))
+            if dparam is not None and dparam not in self.hist_delay_params:
+                self.hist_delay_params.append(dparam)
+            dkey = float(dval).hex() if dparam is None else ("p", dparam)
+            return g._node("hist", (), (self.hist_vars.index(e), scale, dkey, strong))
         if np.ndim(elems) == 0:
             return _obj(one(elems))
         out = np.empty(elems.shape, dtype=object)
@@ -985,7 +997,7 @@ class _Interp:
             raise UnsupportedModelError(f"vector field returns {n_out} derivatives for {n_in} state variables")
         out = ScalarRhs(g, n_in, dy_ids, self.params, self.tables, [r.spec for r in self.rings],
                         ring_writes, self.slots, [], self.uses_t, n_out if self.jacobian else None,
-                        list(self.hist_vars), list(self.hist_delays), self.hist_dt)
+                        list(self.hist_vars), list(self.hist_delays), self.hist_dt, list(self.hist_delay_params))
         # persistent slots: store back only if any evaluation can observe an incoming value
         slot_final = {}
         for name, arr in self.slot_arrays.items():

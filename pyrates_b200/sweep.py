@@ -47,7 +47,8 @@ class BatchedSweep:
                  solver: str, T: float, dt: float, dts: Optional[float], n_inst: int,
                  chunk_samples: int = 100, const_div_to_mul: bool = True, block: int = 128,
                  pinned_result: bool = True, min_blocks: int = 5, solver_kwargs: Optional[dict] = None,
-                 fast_math: Optional[bool] = None, reduce: bool = False, cutoff: float = 0.0):
+                 fast_math: Optional[bool] = None, reduce: bool = False, cutoff: float = 0.0,
+                 hist_max_delay: Optional[float] = None):
         # reduce=True: the kernels keep running statistics (InstanceSession.REDUCE_STATS) of every observer over the samples
         # at times >= cutoff instead of storing trajectories — the result is [5, n_obs, B] and the D2H leg all but disappears
         # min_blocks=5 caps the exact kernel at 96 registers -> 20 warps/SM; measured +3.5 % on the JRC/RK4 sweep
@@ -73,7 +74,8 @@ class BatchedSweep:
                 block, launch_bounds = 64, 7
         self.model = InstanceModel(prog, solver=solver, sweep=sweep, observers=observers, block=block,
                                    const_div_to_mul=const_div_to_mul, min_blocks=launch_bounds,
-                                   fast_math=fast_math, rk_method=self.solver_kwargs.get("method"), reduce=self.reduce)
+                                   fast_math=fast_math, rk_method=self.solver_kwargs.get("method"), reduce=self.reduce,
+                                   hist_max_delay=hist_max_delay)
         order = [(p.arg, p.elem) for p in self.model.rhs.params]
         self._perm = [order.index((a, int(e))) for a, e in sweep]      # user row k -> kernel param row
         self.sweep = list(sweep)
@@ -118,6 +120,7 @@ class BatchedSweep:
             raise ValueError(f"parameter table must have shape ({len(self.sweep)}, {self.B}), got {table.shape}")
         for k, row in enumerate(self._perm):
             self.h_params.array[row, :] = table[k]
+        self.sess.check_delays(self.h_params.array)
 
     def upload(self):
         """H2D: parameters + initial state (+ slots / ring buffers once) on the compute stream."""

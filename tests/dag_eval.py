@@ -36,8 +36,8 @@ class DagMachine:
                     val[i] = int(t) if g.isint[i] else float(t)
                 elif op == "hist":
                     # the reference-generated lookup hist(t*dt - d)[idx] / hist(t - d)[idx] (base_backend.py:437-444)
-                    hv, scale, dhex, strong = g.payload[i]
-                    d = float.fromhex(dhex)
+                    hv, scale, dkey, strong = g.payload[i]
+                    d = float(self.params[dkey[1]]) if isinstance(dkey, tuple) else float.fromhex(dkey)
                     if scale is not None:
                         tq = int(t) * scale - d
                     elif strong and real is np.float32:

@@ -326,6 +326,38 @@ def test_on_device_observer_reduction_matches_numpy_statistics(gpu, name, solver
         assert np.max(np.abs(red[k] - want) / s) <= tol, InstanceModel.__name__ + f" stat {k}"
 
 
+@pytest.mark.parametrize("solver", ["heun", "scipy"])
+def test_sweep_over_history_delays_matches_per_instance_oracle(gpu, solver):
+    """grid_search over the DELAY of a delay-differential model: every instance looks a different distance back into its own
+    history; the device-side history is sized from the bound on the swept delays, which every parameter table is checked
+    against."""
+    from pyrates_b200.sweep import BatchedSweep
+    name = "dde_mg_dopri5" if solver == "scipy" else "dde_mg"
+    prog = Program.load(golden_path(name))
+    fx = orc.load_fixture(golden_path(name))
+    B = 96
+    rng = np.random.default_rng(9)
+    table = np.stack([rng.uniform(0.004, 0.03, B), rng.uniform(0.002, 0.02, B), rng.uniform(1.5, 2.5, B)])     # tau, d, bet
+    T, dt, dts = 0.1, 1e-4, 1e-3
+    sw = BatchedSweep(prog, [("tau", 0), ("d", 0), ("bet", 0)], observers=[0, 1], solver=solver, T=T, dt=dt, dts=dts, n_inst=B,
+                      chunk_samples=13, const_div_to_mul=False, hist_max_delay=0.03)
+    try:
+        out = np.array(sw.run(table), copy=True)
+        bad = table.copy()
+        bad[0, 5] = 0.031
+        with pytest.raises(rt.CudaBackendError, match="hist_max_delay"):
+            sw.run(bad)
+    finally:
+        sw.free()
+    f = orc.build_vector_field(fx["source"])
+    for b in (0, 41, 95):
+        args = orc.fixture_args(fx)
+        for k, nm in enumerate(("tau", "d", "bet")):
+            args[fx["names"].index(nm)] = np.float64(table[k, b])
+        rec = orc.run_adaptive(f, args, T, dt, dts)[0] if solver == "scipy" else orc.run(f, args, T, dt, dts, solver)[0]
+        assert traj_rel_err(out[:, :, b], rec) <= 1e-9, (solver, b)
+
+
 def test_interpolated_input_rhs_matches_numpy_interp(gpu):
     """interp(t, time, u_input) of the adaptive build (numpy.interp semantics): knots, interior points, both clamps."""
     from pyrates_b200.engine import evaluate_rhs

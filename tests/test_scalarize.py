@@ -47,6 +47,29 @@ def test_jacobian_dag_matches_reference(name, swept):
         assert np.allclose(J, ref, rtol=tol, atol=tol * np.max(np.abs(ref)))
 
 
+def test_swept_history_delay_is_a_runtime_parameter():
+    """grid_search over the delay of a delay-differential model: the lookup `hist(t*dt - d)` reads d from the instance's
+    parameters; the history depth is sized from the caller's bound; the DAG reproduces the oracle for another delay."""
+    from pyrates_b200.engine import InstanceModel
+    fx = orc.load_fixture(golden_path("dde_mg"))
+    prog = Program.load(golden_path("dde_mg"))
+    rhs = scalarize(prog, [("tau", 0), ("bet", 0)])
+    assert rhs.hist_delay_params == [0] and [p.arg for p in rhs.params] == ["tau", "bet"]
+    with pytest.raises(UnsupportedModelError, match="hist_max_delay"):
+        InstanceModel(prog, solver="euler", sweep=[("tau", 0)])
+    m = InstanceModel(prog, solver="euler", sweep=[("tau", 0)], hist_max_delay=0.05)
+    assert m.kernel.hist_depth == 512 and "T.p[0]" in m.kernel.source          # ceil(0.05 / 1e-4) + 3 = 503 -> 512
+    mach = DagMachine(rhs, np.float64)
+    mach.params = np.array([0.0123, 2.2])
+    r = fx["run"]
+    rec = mach.euler(prog.y0, 0, 300, r["dt"], 10, hist=orc.History(prog.arg("hist").value))
+    args = orc.fixture_args(fx)
+    args[fx["names"].index("tau")] = np.float64(0.0123)
+    args[fx["names"].index("bet")] = np.float64(2.2)
+    ref, _ = orc.run(orc.build_vector_field(fx["source"]), args, 300 * r["dt"], r["dt"], 10 * r["dt"], "euler")
+    assert traj_rel_err(rec, ref) <= 1e-12
+
+
 @pytest.mark.parametrize("name", sorted(LARGE))
 def test_large_models_refuse_to_unroll(name):
     with pytest.raises(UnsupportedModelError):
