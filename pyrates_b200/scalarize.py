@@ -830,7 +830,14 @@ class _Interp:
         self.uses_t = True
         # NumPy promotion of `t - d` in the reference: a named (array-typed) delay is strong, a literal is a Python float
         strong = not isinstance(dl, ast.Constant)
-        dv = self.ev(dl)
+        try:
+            dv = self.ev(dl)
+        except IndexError:
+            # vectorised builds print `d[0]` for a (1,)-shaped delay that reaches the backend squeezed to 0-d
+            # (base_backend.py:338-339 vs :675-676): take the only element
+            if not isinstance(dl, ast.Subscript):
+                raise
+            dv = self.ev(dl.value)
         dparam = None
         if isinstance(dv, (int, np.integer)):
             dval = float(dv)

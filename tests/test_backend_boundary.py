@@ -140,6 +140,26 @@ def test_cuda_backend_records_jacobian_functions(registered, name, path, precisi
                                        vectorize=False, backend="cuda", sparse=True, verbose=False)
 
 
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("solver", ["euler", "scipy"])
+def test_grid_search_over_a_history_delay_matches_reference_runs(gpu, registered, solver):
+    """pyrates.grid_search(backend='cuda') over the delay d of x' = -x(t-d) (the reference's DDE test model): one batch, every
+    grid point with its own delay and history; checked against the reference NumPy backend run once per grid point."""
+    import pyrates
+    from pyrates.utility import adapt_circuit
+    path = "model_templates.test_resources.test_backend.net16"
+    grid = {"d": np.linspace(0.05, 0.4, 8)}
+    pm = {"d": {"vars": ["op_dde/d"], "nodes": ["p1"]}}
+    kw = dict(step_size=1e-3, simulation_time=1.0, sampling_step_size=1e-2, solver=solver, float_precision="float64")
+    res, pmap = pyrates.grid_search(path, grid, pm, outputs={"x": "p1/op_dde/x"}, backend="cuda", verbose=False, **kw)
+    assert res.shape == (100, 8)
+    for i in (0, 3, 7):
+        c = adapt_circuit(path, {"d": float(grid["d"][i])}, pm)
+        ref = c.run(outputs={"x": "p1/op_dde/x"}, backend="default", verbose=False, clear=True, vectorize=False, **kw)
+        assert traj_rel_err(res.iloc[:, [i]].values, ref.values) <= 1e-9, (solver, i)
+
+
 @needs_ref
 def test_new_solver_names_are_fixed_step(registered):
     import pyrates.frontend.template.circuit as fc
