@@ -53,6 +53,45 @@ def test_delay_differential_kernels_carry_a_history():
         InstanceModel(Program.load(golden_path("dde_mg_dopri5")), solver="heun")
 
 
+def test_c2_bench_kernel_instruction_mix():
+    """The kernel bench.py times (JRC RK4 sweep, fast_math + invariant folding, 64 x 7 launch bounds): its time loop must
+    keep the FP64-pipe instruction count DESIGN.md / bench.py quote (265 per instance-step; 317 before the folding pass, 505
+    for the exact kernel) — counted in the SASS like scripts do, no GPU needed."""
+    import re
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    os.environ["PRB_CACHE_DIR"] = "off"
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    m = InstanceModel(Program.load(golden_path("jrc")), solver="rk4", sweep=bench.SWEEP, observers=[0], const_div_to_mul=True,
+                      fast_math=True, block=64, min_blocks=7)
+    mod = rt.compile_module(m.kernel.source, "c2_mix.cu")
+    path = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"c2_mix_{os.getpid()}.cubin")
+    with open(path, "wb") as f:
+        f.write(mod.cubin)
+    try:
+        sass = subprocess.run(["cuobjdump", "-sass", "-fun", "prb_integrate", path], capture_output=True, text=True).stdout
+    finally:
+        os.remove(path)
+    lines = [l for l in sass.splitlines() if re.search(r"/\*[0-9a-f]{4}\*/", l)]
+    addr = lambda l: int(re.search(r"/\*([0-9a-f]{4,})\*/", l).group(1), 16)
+    loop = None
+    for l in lines:                                   # the time loop = the backward branch with the largest span
+        if "BRA" in l:
+            t = re.search(r"0x([0-9a-f]+)", l.split("BRA")[1])
+            if t and int(t.group(1), 16) < addr(l) and (loop is None or addr(l) - int(t.group(1), 16) > loop[1] - loop[0]):
+                loop = (int(t.group(1), 16), addr(l))
+    assert loop is not None
+    ops = [re.search(r"\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", l) for l in lines if loop[0] <= addr(l) <= loop[1]]
+    ops = [o.group(1) for o in ops if o]
+    fp64 = sum(o in ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX") for o in ops)
+    assert fp64 == bench.FP64_INSTR[True], (fp64, bench.FP64_INSTR)
+    assert fp64 <= 270 and ops.count("MUFU") == 12 and len(ops) <= 640, (fp64, len(ops))
+
+
 def test_unknown_solver_is_rejected():
     with pytest.raises(rt.CudaBackendError, match="does not support solver"):
         InstanceModel(Program.load(golden_path("qif")), solver="lsoda")
