@@ -31,23 +31,25 @@ ETAB_BITS = 11
 
 def exp_tables() -> str:
     """Constants of prb_fast_exp / prb_spec_exp: 2^(j/2048) rounded from extended precision, 2048/ln2, and -ln2/2048 split
-    into a high part with 26 trailing zero bits (n * hi is exact for |x| <= 700) and a low part; K[3] is the minimax r^2
-    coefficient of the degree-3 polynomial on |r| <= R = ln2/4096 (1/2 + 0.0345 R^2: truncation error 0.0072 R^4 < 1e-16)."""
+    into a high part whose LOW WORD IS ZERO (21 significant bits: n * hi is exact for |x| <= 700, and the value is an
+    instruction immediate instead of a constant-bank load) and a low part.  The degree-3 polynomial r + r^2/2 + c3 r^3 on
+    |r| <= ln2/4096 truncates at 0.3 ulp; c3 is 1/6 cut to its high word (the cubic term is < 1e-12, so 2e-7 relative on its
+    coefficient is invisible) — again an immediate."""
     n = 1 << ETAB_BITS
     ld = np.longdouble
     tab = [float(np.exp2(ld(j) / ld(n))) for j in range(n)]
     ln2 = np.log(ld(2))
     c = -ln2 / ld(n)
-    hi = float(c)
-    hi = float(np.array([np.float64(hi).view(np.uint64) & ~np.uint64((1 << 26) - 1)], dtype=np.uint64).view(np.float64)[0])
+
+    def high_word(x: float) -> float:
+        return float(np.array([np.float64(x).view(np.uint64) & ~np.uint64(0xFFFFFFFF)], dtype=np.uint64).view(np.float64)[0])
+    hi = high_word(float(c))
     lo = float(c - ld(hi))
-    R = float(ln2) / (2 * n)
-    a = (np.sqrt(2.0) - 1.0) / 12.0
-    k = [float(ld(n) / ln2), float(hi), float(lo), float(0.5 + a * R * R)]
     return (f"#define PRB_ETAB_BITS {ETAB_BITS}\n#define PRB_ETAB_N {n}\n"
+            f"#define PRB_EXP_HI ({hi!r})\n#define PRB_EXP_C3 ({high_word(1.0 / 6.0)!r})\n"
             f"__device__ __constant__ double PRB_EXP_TAB[{n}] = {{" + ", ".join(repr(v) for v in tab) + "};\n"
-            f"__device__ __constant__ double PRB_EXP_K[4] = {{" + ", ".join(repr(v) for v in k) + "};   "
-            f"// {n}/ln2, -ln2/{n} (hi, lo), minimax r^2 coefficient\n")
+            f"__device__ __constant__ double PRB_EXP_K[2] = {{{float(ld(n) / ln2)!r}, {lo!r}}};   "
+            f"// {n}/ln2, low part of -ln2/{n}\n")
 
 
 def read_template(name: str) -> str:
@@ -497,10 +499,10 @@ __device__ __forceinline__ double prb_fast_exp(const double z, const double* __r
     const double t = fma(z, PRB_EXP_K[0], 6755399441055744.0);               // 256/ln2, 1.5 * 2^52 (an immediate)
     const int n = __double2loint(t);
     const double nd = t - 6755399441055744.0;
-    double r = fma(nd, PRB_EXP_K[1], z);                                     // -ln2/256, high part (26 trailing zero bits)
-    r = fma(nd, PRB_EXP_K[2], r);                                            //           low part
-    double q = fma(r, 1.0 / 6.0, PRB_EXP_K[3]);                              // |r| <= ln2/4096: degree 3 with a minimax r^2
-    q = fma(q, r, 1.0);                                                      // coefficient (K[3] = 1/2 + 0.0345 R^2): < 1e-16
+    double r = fma(nd, PRB_EXP_HI, z);                                       // -ln2/2048, high word (an immediate)
+    r = fma(nd, PRB_EXP_K[1], r);                                            //            low part
+    double q = fma(r, PRB_EXP_C3, 0.5);                                      // |r| <= ln2/4096: degree 3, every coefficient
+    q = fma(q, r, 1.0);                                                      // an instruction immediate
     q = q * r;
     const double tj = tab[n & (PRB_ETAB_N - 1)];
     const double e = fma(tj, q, tj);
@@ -514,9 +516,9 @@ __device__ __forceinline__ double prb_spec_exp(const double z, const unsigned in
     const double t = fma(z, PRB_EXP_K[0], 6755399441055744.0);
     const int n = __double2loint(t);
     const double nd = t - 6755399441055744.0;                                // (an I2F on the conversion pipe instead was measured: no gain)
-    double r = fma(nd, PRB_EXP_K[1], z);
-    r = fma(nd, PRB_EXP_K[2], r);
-    double q = fma(r, 1.0 / 6.0, PRB_EXP_K[3]);
+    double r = fma(nd, PRB_EXP_HI, z);
+    r = fma(nd, PRB_EXP_K[1], r);
+    double q = fma(r, PRB_EXP_C3, 0.5);
     q = fma(q, r, 1.0);
     q = q * r;
     double tj;

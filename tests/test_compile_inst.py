@@ -133,23 +133,28 @@ def test_rk45_tableau_is_scipys_and_reaches_the_kernel_exactly():
 
 
 def test_fast_math_exp_algorithm_is_within_2_ulp_on_the_host():
-    """NumPy twin of prb_fast_exp / prb_spec_exp (emit_inst.py): 2^(j/2048) table + degree-3 polynomial with a minimax r^2
-    coefficient, with the very constants the kernel source carries."""
+    """NumPy twin of prb_fast_exp / prb_spec_exp (emit_inst.py): 2^(j/2048) table + degree-3 polynomial, with the very
+    constants the kernel source carries."""
     import re
     import numpy as np
     src = InstanceModel(Program.load(golden_path("jrc")), solver="rk4", fast_math=True).kernel.source
     assert "prb_spec_exp(" in src and "prb_spec_div(" in src and "#define PRB_USE_ETAB 1" in src and "prb_rhs_exact" in src
     tab = np.array([float(x) for x in re.search(r"PRB_EXP_TAB\[2048\] = \{([^}]*)\}", src).group(1).split(",")])
-    inv, mlhi, mllo, c2 = [float(x) for x in re.search(r"PRB_EXP_K\[4\] = \{([^}]*)\}", src).group(1).split(",")]
+    inv, mllo = [float(x) for x in re.search(r"PRB_EXP_K\[2\] = \{([^}]*)\}", src).group(1).split(",")]
+    mlhi = float(re.search(r"#define PRB_EXP_HI \(([^)]*)\)", src).group(1))
+    c3 = float(re.search(r"#define PRB_EXP_C3 \(([^)]*)\)", src).group(1))
     assert tab.size == 2048 and abs(tab[1024] - 2 ** 0.5) < 1e-15 and abs(inv * np.log(2) / 2048 - 1) < 1e-15
-    assert (np.float64(mlhi).view(np.uint64) & np.uint64((1 << 26) - 1)) == 0          # n * hi is exact
+    # instruction immediates: the low words of the high part of -ln2/2048 and of the cubic coefficient are zero
+    assert all((np.float64(v).view(np.uint64) & np.uint64(0xFFFFFFFF)) == 0 for v in (mlhi, c3)) and abs(c3 * 6 - 1) < 1e-6
+    assert abs((mlhi + mllo) * 2048 / np.log(2) + 1) < 1e-15
     z = np.random.default_rng(0).uniform(-700, 700, 400_000)
     t = z * inv + 6755399441055744.0
     n = (t.view(np.int64) & 0xFFFFFFFF).astype(np.int64)
     n = np.where(n >= 2 ** 31, n - 2 ** 32, n)
     nd = t - 6755399441055744.0
+    assert np.array_equal(nd * mlhi, (nd.astype(np.longdouble) * np.longdouble(mlhi)).astype(np.float64))     # exact product
     r = (z + nd * mlhi) + nd * mllo
-    q = r * (1.0 + r * (c2 + r * (1 / 6)))
+    q = r * (1.0 + r * (0.5 + r * c3))
     got = np.ldexp(tab[n & 2047] + tab[n & 2047] * q, n >> 11)
     ref = np.exp(z.astype(np.longdouble))
     assert float(np.max(np.abs(got.astype(np.longdouble) - ref) / ref)) < 2.5 * 2.0 ** -53
