@@ -326,6 +326,70 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
     prb_thread_exit(T, A, b);
 }
 #else
+// One solver step y -> yn.  SPEC (fast_math kernels of pure vector fields, PRB_SPEC_STEP): every stage runs the speculative
+// rhs, which only ORs range violations of its exp / reciprocal arguments into `bad`; the caller looks at the flag once per
+// step and recomputes the step with the exact rhs (prb_step_exact) in the rare case it is set — the stages of a step stay one
+// basic block instead of ending in a reconvergence point each.
+template <bool SPEC>
+__device__ __forceinline__ void prb_stage(const long long t, const real (&y)[PRB_NS], real (&k)[PRB_NS], PrbThread& T, bool& bad) {
+#ifdef PRB_SPEC_STEP
+    if (SPEC) prb_rhs_spec(t, y, k, T, bad);
+    else      prb_rhs_exact(t, y, k, T);
+#else
+    prb_rhs(t, y, k, T);
+#endif
+}
+
+template <bool SPEC>
+__device__ __forceinline__ void prb_step(const long long t, const real (&y)[PRB_NS], real (&yn)[PRB_NS], PrbThread& T,
+                                         const real dt, const real hdt, const real dt6, bool& bad) {
+    real k[PRB_NS];
+    (void)hdt; (void)dt6;
+#if PRB_SOLVER == PRB_SOLVER_EULER
+    prb_stage<SPEC>(t, y, k, T, bad);
+    prb_axpy(yn, y, dt, k);
+#elif PRB_SOLVER == PRB_SOLVER_HEUN_REF
+    // reference `heun`: rhs buffer is aliased, so both summands are the 2nd evaluation
+    real ys[PRB_NS];
+    prb_stage<SPEC>(t, y, k, T, bad);
+    prb_axpy(ys, y, dt, k);
+    prb_stage<SPEC>(t, ys, k, T, bad);
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) yn[j] = y[j] + hdt * (k[j] + k[j]);
+#elif PRB_SOLVER == PRB_SOLVER_HEUN
+    real ys[PRB_NS], k2[PRB_NS];
+    prb_stage<SPEC>(t, y, k, T, bad);
+    prb_axpy(ys, y, dt, k);
+    prb_stage<SPEC>(t, ys, k2, T, bad);
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) yn[j] = y[j] + hdt * (k[j] + k2[j]);
+#elif PRB_SOLVER == PRB_SOLVER_RK4
+    real ys[PRB_NS], acc[PRB_NS];
+    prb_stage<SPEC>(t, y, k, T, bad);                       // k1
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) { acc[j] = k[j]; ys[j] = y[j] + hdt * k[j]; }
+    prb_stage<SPEC>(t, ys, k, T, bad);                      // k2
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) { acc[j] = acc[j] + (real)2 * k[j]; ys[j] = y[j] + hdt * k[j]; }
+    prb_stage<SPEC>(t, ys, k, T, bad);                      // k3
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) { acc[j] = acc[j] + (real)2 * k[j]; ys[j] = y[j] + dt * k[j]; }
+    prb_stage<SPEC>(t, ys, k, T, bad);                      // k4
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) yn[j] = y[j] + dt6 * (acc[j] + k[j]);
+#else
+#error "unknown PRB_SOLVER"
+#endif
+}
+
+#ifdef PRB_SPEC_STEP
+__device__ __noinline__ void prb_step_exact(const long long t, const real (&y)[PRB_NS], real (&yn)[PRB_NS], PrbThread& T,
+                                            const real dt, const real hdt, const real dt6) {
+    bool unused = false;
+    prb_step<false>(t, y, yn, T, dt, hdt, dt6, unused);
+}
+#endif
+
 extern "C" __global__ void __launch_bounds__(PRB_BLOCK, PRB_MIN_BLOCKS)
 prb_integrate(const __grid_constant__ prb_kernel_args A)
 {
@@ -391,42 +455,16 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
         }
         --until_store;
 
-        real k[PRB_NS];
-#if PRB_SOLVER == PRB_SOLVER_EULER
-        prb_rhs(t, y, k, T);
-        prb_axpy(y, y, dt, k);
-#elif PRB_SOLVER == PRB_SOLVER_HEUN_REF
-        // reference `heun`: rhs buffer is aliased, so both summands are the 2nd evaluation
-        real ys[PRB_NS];
-        prb_rhs(t, y, k, T);
-        prb_axpy(ys, y, dt, k);
-        prb_rhs(t, ys, k, T);
-        PRB_UNROLL_NS
-        for (int j = 0; j < PRB_NS; ++j) y[j] = y[j] + hdt * (k[j] + k[j]);
-#elif PRB_SOLVER == PRB_SOLVER_HEUN
-        real ys[PRB_NS], k2[PRB_NS];
-        prb_rhs(t, y, k, T);
-        prb_axpy(ys, y, dt, k);
-        prb_rhs(t, ys, k2, T);
-        PRB_UNROLL_NS
-        for (int j = 0; j < PRB_NS; ++j) y[j] = y[j] + hdt * (k[j] + k2[j]);
-#elif PRB_SOLVER == PRB_SOLVER_RK4
-        real ys[PRB_NS], acc[PRB_NS];
-        prb_rhs(t, y, k, T);                       // k1
-        PRB_UNROLL_NS
-        for (int j = 0; j < PRB_NS; ++j) { acc[j] = k[j]; ys[j] = y[j] + hdt * k[j]; }
-        prb_rhs(t, ys, k, T);                      // k2
-        PRB_UNROLL_NS
-        for (int j = 0; j < PRB_NS; ++j) { acc[j] = acc[j] + (real)2 * k[j]; ys[j] = y[j] + hdt * k[j]; }
-        prb_rhs(t, ys, k, T);                      // k3
-        PRB_UNROLL_NS
-        for (int j = 0; j < PRB_NS; ++j) { acc[j] = acc[j] + (real)2 * k[j]; ys[j] = y[j] + dt * k[j]; }
-        prb_rhs(t, ys, k, T);                      // k4
-        PRB_UNROLL_NS
-        for (int j = 0; j < PRB_NS; ++j) y[j] = y[j] + dt6 * (acc[j] + k[j]);
+        real yn[PRB_NS];
+        bool bad = false;
+#ifdef PRB_SPEC_STEP
+        prb_step<true>(t, y, yn, T, dt, hdt, dt6, bad);
+        if (bad) prb_step_exact(t, y, yn, T, dt, hdt, dt6);          // an argument left the fast range: redo the step exactly
 #else
-#error "unknown PRB_SOLVER"
+        prb_step<false>(t, y, yn, T, dt, hdt, dt6, bad);
 #endif
+        PRB_UNROLL_NS
+        for (int j = 0; j < PRB_NS; ++j) y[j] = yn[j];
 #if PRB_NH > 0
         prb_hist_push(T, y, A.step0 + i + 1);        // DDEHistory.update((i + 1) * dt, y)
 #endif

@@ -634,11 +634,23 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
         src.append("__device__ __noinline__ void prb_rhs_exact(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NDY], PrbThread& T) {")
         src.extend("    " + l for l in exact_body)
         src.append("}")
+    if spec:
+        # speculative evaluation: `bad` is only accumulated; the caller decides when to look at it.  The fixed-step solver
+        # template checks it ONCE PER STEP (PRB_SPEC_STEP): the stages of a step then form one basic block (no reconvergence
+        # point after every evaluation), and a step that saw an out-of-range argument is recomputed by prb_step_exact.
+        # Opt-in (PRB_SPEC_PER_STEP=1).  Measured A/B on one B200 (JRC RK4 sweep): the per-step form issues 7 % fewer
+        # instructions but takes the same number of cycles (the kernel is bound by dependency latency at 4 warps per
+        # scheduler) while drawing 1009 W instead of 743 W — the board then power-caps to 1822 MHz and the run is 8.6 %
+        # SLOWER (218.0 vs 200.5 ms).  The per-evaluation check stays the default.
+        if os.environ.get("PRB_SPEC_PER_STEP") == "1":
+            src.append("#define PRB_SPEC_STEP 1")
+        src.append("__device__ __forceinline__ void prb_rhs_spec(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NDY], PrbThread& T, bool& bad) {")
+        src.extend("    " + l for l in body)
+        src.append("}")
     src.append("__device__ __forceinline__ void prb_rhs(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NDY], PrbThread& T) {")
     if spec:
         src.append("    bool bad = false;")
-    src.extend("    " + l for l in body)
-    if spec:
+        src.append("    prb_rhs_spec(t, y, dy, T, bad);")
         src.append("    if (bad) {                  // an exp / division argument left the fast range: redo this evaluation exactly")
         src.append("        areal yl[PRB_NS], dl[PRB_NDY];")
         src.append("        PrbThread Tl = T;")
@@ -646,6 +658,8 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
         src.append("        prb_rhs_exact(t, yl, dl, Tl);")
         src.append("        _Pragma(\"unroll\") for (int j = 0; j < PRB_NDY; ++j) dy[j] = dl[j];")
         src.append("    }")
+    else:
+        src.extend("    " + l for l in body)
     src.append("}")
     rec = ["__device__ __forceinline__ void prb_record(const real (&y)[PRB_NS], real* __restrict__ row, long long b, long long B) {"]
     for o, idx in enumerate(observers):

@@ -138,7 +138,8 @@ def test_fast_math_exp_algorithm_is_within_2_ulp_on_the_host():
     import re
     import numpy as np
     src = InstanceModel(Program.load(golden_path("jrc")), solver="rk4", fast_math=True).kernel.source
-    assert "prb_spec_exp(" in src and "prb_spec_div(" in src and "#define PRB_USE_ETAB 1" in src and "prb_rhs_exact" in src
+    assert "prb_spec_exp(" in src and "prb_spec_div(" in src and "#define PRB_USE_ETAB 1" in src and "void prb_rhs_exact(" in src
+    assert "void prb_rhs_spec(" in src and "#define PRB_SPEC_STEP 1" not in src        # per-step check is opt-in
     tab = np.array([float(x) for x in re.search(r"PRB_EXP_TAB\[2048\] = \{([^}]*)\}", src).group(1).split(",")])
     inv, mllo = [float(x) for x in re.search(r"PRB_EXP_K\[2\] = \{([^}]*)\}", src).group(1).split(",")]
     mlhi = float(re.search(r"#define PRB_EXP_HI \(([^)]*)\)", src).group(1))
@@ -160,4 +161,4 @@ def test_fast_math_exp_algorithm_is_within_2_ulp_on_the_host():
     assert float(np.max(np.abs(got.astype(np.longdouble) - ref) / ref)) < 2.5 * 2.0 ** -53
     # models with mutable buffers keep the branching variant (a speculative re-evaluation would replay side effects)
     src2 = InstanceModel(Program.load(golden_path("jrc_2delay")), solver="heun", fast_math=True).kernel.source
-    assert "prb_fast_div(" in src2 and "prb_rhs_exact" not in src2
+    assert "prb_fast_div(" in src2 and "#define PRB_SPEC_STEP" not in src2 and "void prb_rhs_exact(" not in src2

@@ -35,14 +35,14 @@ def test_jrc_sweep_kernel_hoists_parameter_products():
     m = InstanceModel(prog, solver="rk4", sweep=JRC_SWEEP, observers=[0], const_div_to_mul=True, fast_math=True, block=64,
                       min_blocks=7)
     src = m.kernel.source
-    body = src[src.index("void prb_rhs(const prb_time"):src.index("if (bad)")]
+    body = src[src.index("void prb_rhs_spec(const prb_time"):src.index("void prb_rhs(const prb_time")]
     init = src[src.index("void prb_thread_init("):src.index("void prb_thread_exit(")]
     # every swept parameter enters the time loop only through hoisted products (T.q), never as T.p
     assert "T.p[" not in body and body.count("T.q[") == 5 and init.count("T.q[") >= 6 and 'asm volatile("" : "+d"(T.q[k]))' in init
     # sigmoids: table exp, bare reciprocal without a range check (the divisor is 1 + exp), one FMA with the hoisted weight
     assert body.count("prb_spec_exp(") == 3 and body.count("prb_spec_rcp_nc(") == 3 and "prb_spec_div(" not in body
     # the exact re-evaluation path still uses the parameters as the reference wrote them
-    exact = src[src.index("void prb_rhs_exact("):src.index("void prb_rhs(const prb_time")]
+    exact = src[src.index("void prb_rhs_exact("):src.index("void prb_rhs_spec(const prb_time")]
     assert "T.p[" in exact and "T.q[" not in exact
     # models with mutable buffers / exact kernels are not rewritten
     plain = InstanceModel(prog, solver="rk4", sweep=JRC_SWEEP, observers=[0]).kernel.source
