@@ -75,9 +75,21 @@ def fold_invariants(rhs: ScalarRhs, max_terms: int = 6) -> ScalarRhs:
             return a
         return ng.binop("mul", a, b)
 
+    depth_memo: Dict[int, int] = {}
+    cost = {"exp": 8, "div": 5, "log": 8, "sin": 12, "cos": 12, "tan": 14, "tanh": 12, "pow": 16, "sqrt": 5}
+
+    def depth(i: int) -> int:
+        """Length of the dependency chain that ends in node i of the new graph (rough instruction latencies)."""
+        if i not in depth_memo:
+            a = ng.args[i]
+            depth_memo[i] = (cost.get(ng.ops[i], 1) + max(depth(x) for x in a)) if a else 0
+        return depth_memo[i]
+
     def mat(lc: _LC) -> Sym:
+        # shallow bases first: the term that hangs on the longest chain (a sigmoid's reciprocal) joins the sum LAST, so
+        # only one FMA follows it on the critical path of the evaluation (the kernels are bound by dependency latency)
         acc = lc.inv
-        for k, b in lc.terms:
+        for k, b in sorted(lc.terms, key=lambda kb: depth(kb[1].id)):
             t = b if k is None else ng.binop("mul", b, k)
             acc = t if acc is None else ng.binop("add", acc, t)
         return acc if acc is not None else ng.const(0.0, weak=True)
