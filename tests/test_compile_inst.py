@@ -159,6 +159,14 @@ def test_fast_math_exp_algorithm_is_within_2_ulp_on_the_host():
     got = np.ldexp(tab[n & 2047] + tab[n & 2047] * q, n >> 11)
     ref = np.exp(z.astype(np.longdouble))
     assert float(np.max(np.abs(got.astype(np.longdouble) - ref) / ref)) < 2.5 * 2.0 ** -53
+    # Estrin form of the speculative kernels and the fused 1 + e^z of sigmoid denominators (prb_spec_exp_plus)
+    q2 = r + (r * r) * (0.5 + r * c3)
+    got2 = np.ldexp(tab[n & 2047] + tab[n & 2047] * q2, n >> 11)
+    assert float(np.max(np.abs(got2.astype(np.longdouble) - ref) / ref)) < 2.5 * 2.0 ** -53
+    ts = np.ldexp(tab[n & 2047], n >> 11)
+    plus = ts * q2 + (ts + 1.0)
+    assert float(np.max(np.abs(plus.astype(np.longdouble) - (ref + 1)) / (ref + 1))) < 2.5 * 2.0 ** -53
+    assert "prb_spec_exp_plus(" in src          # defined; used only with PRB_EXP_PLUS=1 (measured: no gain)
     # models with mutable buffers keep the branching variant (a speculative re-evaluation would replay side effects)
     src2 = InstanceModel(Program.load(golden_path("jrc_2delay")), solver="heun", fast_math=True).kernel.source
     assert "prb_fast_div(" in src2 and "#define PRB_SPEC_STEP" not in src2 and "void prb_rhs_exact(" not in src2
