@@ -207,9 +207,6 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
 
     base, targets = _probe_positions(template, keys, param_map, build)
     prog: Program = base["program"]
-    if prog.is_complex:
-        raise NotImplementedError("grid_search on the CUDA backend batches real-valued builds; complex float precisions are "
-                                  "supported by CircuitTemplate.run only")
     y_name = prog.arg_by_kind("y").name
     sweep, rows, y0_rows = [], [], []
     for k in keys:
@@ -219,6 +216,15 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
             else:
                 sweep.append((arg, elem))
                 rows.append(k)
+    observers = list(base["observers"])
+    if prog.is_complex:
+        # complex state k = real state variables (2k, 2k+1); swept parameters are the real parts of complex-typed constants
+        if y0_rows or reduce:
+            raise NotImplementedError("sweeping initial conditions / reduce=True on a complex-valued build")
+        if exec_model == "network":
+            raise NotImplementedError("complex float precisions run in the instance execution model")
+        exec_model = "instance"
+        observers = [j for o in observers for j in (2 * o, 2 * o + 1)]
     B_total = len(param_grid.index)
     lo, hi = (0, B_total) if shard is None else shard_bounds(B_total, shard[1], shard[0])
     B = hi - lo
@@ -241,7 +247,7 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     sw = None
     if exec_model in ("auto", "instance"):
         try:
-            sw = BatchedSweep(prog, sweep, base["observers"], solver=solver, T=simulation_time, dt=step_size,
+            sw = BatchedSweep(prog, sweep, observers, solver=solver, T=simulation_time, dt=step_size,
                               dts=sampling_step_size, n_inst=B, chunk_samples=chunk_samples,
                               const_div_to_mul=const_div_to_mul, solver_kwargs=solver_kw, fast_math=fast_math,
                               reduce=reduce, cutoff=cutoff, hist_max_delay=hist_max_delay)
@@ -269,6 +275,9 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
         finally:
             ns.free()
 
+    if prog.is_complex and not reduce:
+        cdt = np.complex64 if prog.float_precision == "complex64" else np.complex128
+        res = (res[:, 0::2, :] + 1j * res[:, 1::2, :]).astype(cdt)           # complex frames, like the reference returns
     circuit_names = [f"{name}_{idx}" for idx in param_grid.index]
     param_grid = param_grid.copy()
     param_grid.index = circuit_names

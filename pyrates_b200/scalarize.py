@@ -514,8 +514,9 @@ class _Interp:
                     raise UnsupportedModelError(f"mutable integer buffer `{a.name}`")
                 self.env[a.name] = v.copy()           # concrete index array (never swept)
             elif np.iscomplexobj(v):
-                if any(n == a.name for n, _ in sweep):
-                    raise UnsupportedModelError(f"complex argument `{a.name}` cannot be swept")
+                cswept = {e for n, e in sweep if n == a.name}
+                if cswept and (a.kind != "const" or np.any(v.reshape(-1)[sorted(cswept)].imag != 0)):
+                    raise UnsupportedModelError(f"complex argument `{a.name}` can only be swept as a real-valued constant")
                 if a.kind == "var":
                     # mutable complex buffers are the vectorised frontend's input routing (`u[target_idx] = ...`, rewritten
                     # in every evaluation before it is read): tracked symbolically, never stored back
@@ -524,7 +525,13 @@ class _Interp:
                 flat = arr.reshape(-1) if v.ndim else None
                 vals = v.reshape(-1)
                 for k in range(vals.size):
-                    c = CSym(self.g, self.g.const(vals[k].real), self.g.const(vals[k].imag))
+                    if k in cswept:
+                        # a real parameter of a complex build (every float argument arrives complex, base_backend.py:326-331):
+                        # the sweep varies its real part
+                        self.params.append(ParamSpec(a.name, k, float(vals[k].real)))
+                        c = CSym(self.g, self.g.leaf("param", len(self.params) - 1), self.g.const(0.0))
+                    else:
+                        c = CSym(self.g, self.g.const(vals[k].real), self.g.const(vals[k].imag))
                     if v.ndim:
                         flat[k] = c
                     else:

@@ -160,6 +160,28 @@ def test_grid_search_over_a_history_delay_matches_reference_runs(gpu, registered
         assert traj_rel_err(res.iloc[:, [i]].values, ref.values) <= 1e-9, (solver, i)
 
 
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("precision", ["complex128", "complex64"])
+def test_grid_search_over_a_complex_valued_model_matches_reference_runs(gpu, registered, precision):
+    """grid_search over the Ott-Antonsen mean field (complex state z, float_precision='complex64/128'): swept parameters are
+    the real parts of complex-typed constants, results come back as complex frames; vs the reference run per grid point."""
+    import pyrates
+    from pyrates.utility import adapt_circuit, linearize_grid
+    path = "model_templates.oscillators.kuramoto.kmo_mf"
+    grid = linearize_grid({"Delta": np.linspace(0.5, 2.0, 4), "omega": np.linspace(5.0, 15.0, 3)}, permute=True)
+    pm = {"Delta": {"vars": ["kmo_op/Delta"], "nodes": ["p"]}, "omega": {"vars": ["kmo_op/omega"], "nodes": ["p"]}}
+    kw = dict(step_size=1e-3, simulation_time=1.0, sampling_step_size=1e-2, solver="heun", float_precision=precision)
+    res, pmap = pyrates.grid_search(path, grid, pm, outputs={"z": "p/kmo_op/z"}, backend="cuda", verbose=False, **kw)
+    assert res.shape == (100, 12) and np.iscomplexobj(res.values)
+    from conftest import as_real_columns
+    for i in (0, 5, 11):
+        c = adapt_circuit(path, {k: float(grid[k].values[i]) for k in pm}, pm)
+        ref = c.run(outputs={"z": "p/kmo_op/z"}, backend="default", verbose=False, clear=True, **kw)
+        assert res.values.dtype == ref.values.dtype
+        assert traj_rel_err(as_real_columns(res.iloc[:, [i]].values), as_real_columns(ref.values)) <= RTOL[precision], i
+
+
 @needs_ref
 def test_new_solver_names_are_fixed_step(registered):
     import pyrates.frontend.template.circuit as fc

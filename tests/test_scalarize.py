@@ -47,6 +47,28 @@ def test_jacobian_dag_matches_reference(name, swept):
         assert np.allclose(J, ref, rtol=tol, atol=tol * np.max(np.abs(ref)))
 
 
+def test_complex_build_sweeps_real_parameters():
+    """Complex precisions: every float constant arrives complex; a swept one (zero imaginary part) becomes a real runtime
+    parameter, one with an imaginary part (the imaginary unit `i` of the Ott-Antonsen templates) cannot be swept."""
+    fx = orc.load_fixture(golden_path("kmo_mf_c128"))
+    prog = Program.load(golden_path("kmo_mf_c128"))
+    rhs = scalarize(prog, [("Delta", 0), ("omega", 0)])
+    assert sorted(p.arg for p in rhs.params) == ["Delta", "omega"] and rhs.n_state == 2
+    with pytest.raises(UnsupportedModelError, match="real-valued"):
+        scalarize(prog, [("i", 0)])
+    mach = DagMachine(rhs, np.float64)
+    vals = {"Delta": 0.7, "omega": 12.0}
+    mach.params = np.array([vals[p.arg] for p in rhs.params])
+    f = orc.build_vector_field(fx["source"])
+    args = orc.fixture_args(fx)
+    for k, v in vals.items():
+        args[fx["names"].index(k)] = np.complex128(v)
+    for y in (0.3 + 0.2j, -0.1 + 0.6j):
+        ref = f(0, np.array([y]), *args[2:]).copy()
+        got = mach.eval(0, np.array([y.real, y.imag]))
+        assert np.allclose(got, [ref[0].real, ref[0].imag], rtol=1e-13)
+
+
 def test_swept_history_delay_is_a_runtime_parameter():
     """grid_search over the delay of a delay-differential model: the lookup `hist(t*dt - d)` reads d from the instance's
     parameters; the history depth is sized from the caller's bound; the DAG reproduces the oracle for another delay."""
