@@ -255,7 +255,7 @@ def main():
         return 0
 
     hbm, which = peaks()
-    inst_steps_per_launch = B * n_steps / sw.launches_per_run
+    inst_steps_per_launch = B * n_steps * a.steps / launches        # launches of the device-resident (value) timing
     launch_s = kernel_ms * 1e-3 / launches
     achieved = B_ALG * inst_steps_per_launch / launch_s / 1e9
     info = sw.model.module.kernel_info("prb_integrate", sw.model.kernel.block)

@@ -118,8 +118,19 @@ class BatchedSweep:
         table = np.asarray(table)
         if table.shape != (len(self.sweep), self.B):
             raise ValueError(f"parameter table must have shape ({len(self.sweep)}, {self.B}), got {table.shape}")
-        for k, row in enumerate(self._perm):
-            self.h_params.array[row, :] = table[k]
+        if self.B >= (1 << 18) and len(self._perm) > 1:
+            # big sweeps: the row copies into pinned memory are the host-side leg of the upload (NumPy releases the GIL)
+            from concurrent.futures import ThreadPoolExecutor
+            if not hasattr(self, "_pool"):
+                self._pool = ThreadPoolExecutor(max_workers=min(8, len(self._perm)))
+            dst = self.h_params.array
+
+            def put(k_row):
+                dst[k_row[1], :] = table[k_row[0]]
+            list(self._pool.map(put, enumerate(self._perm)))
+        else:
+            for k, row in enumerate(self._perm):
+                self.h_params.array[row, :] = table[k]
         self.sess.check_delays(self.h_params.array)
 
     def upload(self):
@@ -167,8 +178,20 @@ class BatchedSweep:
         done, sample, c = 0, 0, 0
         item = np.dtype(self.real).itemsize
         n_launch = 0
-        while done < self.steps:
-            n = min(steps_per_chunk, self.steps - done)
+        # chunk schedule: equal chunks; when results stream to the host the LAST chunk is split into halves (.., 1/2, 1/4,
+        # 1/8, 1/8): its D2H copy is the un-overlapped tail of the run, so it should be short
+        sizes = []
+        left = self.steps
+        while left > 0:
+            sizes.append(min(steps_per_chunk, left))
+            left -= sizes[-1]
+        if read_back and len(sizes) >= 4 and sizes[-1] // self.store_step >= 8:
+            tail = sizes.pop()
+            last = tail // self.store_step
+            parts = [last - last // 2, last // 2 - last // 4, last // 4 - last // 8, last // 8]
+            sizes += [p * self.store_step for p in parts if p > 0]
+            sizes[-1] += tail - last * self.store_step                          # steps beyond the last whole sample
+        for n in sizes:
             i = c & 1
             if read_back and c >= 2:
                 self.compute.wait_event(self.ev_free[i])
@@ -249,6 +272,8 @@ class BatchedSweep:
 
     def free(self):
         self.wait()
+        if hasattr(self, "_pool"):
+            self._pool.shutdown(wait=True)
         self.sess.free()
         for b in self.d_chunks:
             b.free()
