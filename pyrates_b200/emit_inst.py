@@ -399,7 +399,7 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     body_f32 = f32 and not arith64
     hoist: Optional[List[str]] = None
     fast_rhs = rhs
-    if (spec or (fast_math and f32 and pure)) and not adaptive and rhs.n_out is None and not n_hist:
+    if (spec or (fast_math and f32 and pure)) and not adaptive and rhs.n_out is None:
         # FP64-pipe-bound sweeps: group thread-invariant factors (swept parameters x literals) and compute them once per thread
         from .reassoc import fold_invariants
         fast_rhs, hoist = fold_invariants(rhs), []

@@ -281,6 +281,16 @@ def test_dde_sweep_matches_per_instance_oracle(gpu, solver):
     finally:
         sw.free()
     assert out.shape == (100, 2, B)
+    if solver != "scipy":
+        # the fast_math build (invariant folding + speculative exp / reciprocal) of the same sweep stays within 1e-9
+        fast = BatchedSweep(prog, [("bet", 0), ("a", 0)], observers=[0, 1], solver=solver, T=T, dt=dt, dts=dts, n_inst=B,
+                            chunk_samples=50)
+        try:
+            assert fast.model.kernel.source.count("T.q[") > 0
+            out_fast = np.array(fast.run(table), copy=True)
+        finally:
+            fast.free()
+        assert traj_rel_err(out_fast.reshape(100, -1), out.reshape(100, -1)) <= 1e-9
     f = orc.build_vector_field(fx["source"])
     for b in (0, 17, 299):
         args = orc.fixture_args(fx)

@@ -13,7 +13,7 @@ from pyrates_b200.scalarize import scalarize
 
 JRC_SWEEP = [("u", 0), ("weight_v2", 0), ("weight_v2", 1), ("weight", 0), ("weight_v1", 0)]
 CASES = [("jrc", JRC_SWEEP, 0.01), ("jrc", [], 0.01), ("qif", [("eta", 0)], 0.5), ("qif_sfa", [("eta", 0), ("alpha", 0)], 0.3),
-         ("net13", [], 0.5), ("qif_input", [("eta", 0)], 0.3)]
+         ("net13", [], 0.5), ("qif_input", [("eta", 0)], 0.3), ("dde_mg", [("bet", 0), ("tau", 0)], 0.1)]
 
 
 @pytest.mark.parametrize("name,sweep,scale", CASES)
@@ -24,7 +24,14 @@ def test_folded_dag_is_the_same_vector_field(name, sweep, scale):
     a, b = DagMachine(rhs), DagMachine(folded)
     rng = np.random.default_rng(1)
     a.params = b.params = a.params * rng.uniform(0.7, 1.3, a.params.shape)
+    if prog.is_dde:                                   # a short shared history: the lookups interpolate in it
+        from oracle import numpy_oracle as orc
+        hist = orc.History(prog.arg("hist").value)
+        for j in range(1, 400):
+            hist.update(j * 1e-4, prog.y0 * (1 + 0.01 * np.sin(0.05 * j)))
+        a.hist = b.hist = hist
     for k in range(8):
+        k = 399 + k if prog.is_dde else k
         y = prog.y0 + scale * rng.normal(size=prog.n_state)
         want, got = a.eval(k, y), b.eval(k, y)
         assert np.allclose(got, want, rtol=1e-12, atol=1e-12 * np.max(np.abs(want)))
