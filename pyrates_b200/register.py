@@ -175,7 +175,16 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     name = template.name
 
     def build(circuit):
-        func, args, _, _ = circuit.get_run_func("vector_field", step_size=step_size, inputs=dict(inputs) if inputs else None,
+        # extrinsic inputs: CircuitTemplate._add_input returns a NEW template (input nodes added), and only that object
+        # carries the vectorisation maps get_variable_positions needs (frontend/template/circuit.py:456-461, 604-607) —
+        # add them here, like run() does, and build the returned template with inputs=None
+        if inputs:
+            import pyrates.frontend.template.circuit as fc
+            adaptive_steps = fc.is_integration_adaptive(solver, **solver_kw)
+            for target, arr in inputs.items():
+                arr = np.asarray(arr)
+                circuit = circuit._add_input(target, arr, adaptive_steps, arr.shape[0] * step_size, True)
+        func, args, _, _ = circuit.get_run_func("vector_field", step_size=step_size, inputs=None,
                                                 backend="cuda", solver=solver, verbose=verbose, clear=False,
                                                 float_precision=float_precision, **kwargs)
         prog = func.program(args)

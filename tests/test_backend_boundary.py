@@ -182,6 +182,32 @@ def test_grid_search_over_a_complex_valued_model_matches_reference_runs(gpu, reg
         assert traj_rel_err(as_real_columns(res.iloc[:, [i]].values), as_real_columns(ref.values)) <= RTOL[precision], i
 
 
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("precision", ["float64", "float32"])
+def test_documentation_parameter_sweep_example_runs_unchanged_on_cuda(gpu, registered, precision):
+    """The reference's own gallery example (documentation/model_analysis/parameter_sweeps.py:44-88): a sweep over the
+    Jansen-Rit connectivity scaling C with a shared noise input, two outputs and a cutoff — the call is repeated verbatim with
+    backend='cuda' (shorter horizon) and must return the same frames (labels, index, values) as backend='default'."""
+    import pyrates
+    T, dt, dts, cutoff = 0.5, 1e-4, 1e-3, 0.1
+    param_grid = {'C': [68., 128., 135., 270., 675., 1350.]}
+    param_map = {'C': {'vars': ['jrc_op/c'], 'nodes': ['jrc']}}
+    noise = np.random.default_rng(0).uniform(120.0, 320.0, size=(int(np.round(T / dt, decimals=0)), 1))
+    kw = dict(circuit_template="model_templates.neural_mass_models.jansenrit.JRC2", param_grid=param_grid, param_map=param_map,
+              simulation_time=T, step_size=dt, sampling_step_size=dts, inputs={'jrc/jrc_op/u': noise},
+              outputs={'V_pce': 'jrc/jrc_op/V_e', 'V_pci': 'jrc/jrc_op/V_i'}, solver="euler", cutoff=cutoff, verbose=False,
+              float_precision=precision)
+    ref, ref_map = pyrates.grid_search(backend="default", **kw)
+    from pyrates.ir.node import clear_ir_caches
+    clear_ir_caches()
+    got, got_map = pyrates.grid_search(backend="cuda", **kw)
+    assert [tuple(map(str, c)) for c in got.columns] == [tuple(map(str, c)) for c in ref.columns]
+    assert got.shape == ref.shape and np.allclose(got.index.values, ref.index.values)
+    assert list(got_map.index) == list(ref_map.index) and np.array_equal(got_map["C"].values, ref_map["C"].values)
+    assert traj_rel_err(got.values, ref.values) <= RTOL[precision]
+
+
 @needs_ref
 def test_new_solver_names_are_fixed_step(registered):
     import pyrates.frontend.template.circuit as fc
