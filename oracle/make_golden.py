@@ -399,6 +399,12 @@ ADAPTIVE_CASES = {
     "dde_mg_dopri5":        dict(build=_mackey_glass(), T=0.3, dt=1e-4, dts=1e-3, out="p1/mg_op/x", run_kw=dict(vectorize=False)),
     "dde_jrc_pair_dopri5":  dict(build=_jrc_pair_delayed(), T=0.2, dt=1e-4, dts=1e-3, out="jrc1/pc/rpo_e_in/v",
                                  run_kw=dict(vectorize=False)),
+    # SciPy's DOP853 (8th order; the reference's documentation runs it: documentation/model_analysis/entrainment.py:56)
+    "jrc_dop853":   dict(build=_yaml(NM + "jansenrit.JRC"), T=0.5, dt=1e-4, dts=1e-3, out="pc/rpo_e_in/v",
+                         kw=dict(method="DOP853", rtol=1e-8, atol=1e-10)),
+    "qif_sfa_dop853": dict(build=_yaml(NM + "qif.qif_sfa"), T=2.0, dt=1e-3, dts=5e-3, out="p/qif_sfa_op/r", kw=dict(method="DOP853")),
+    "vdp_dop853":   dict(build=_yaml("model_templates.oscillators.vanderpol.vdp"), T=20.0, dt=1e-3, dts=5e-2, out="p/vdp_op/x",
+                         kw=dict(method="DOP853", rtol=1e-6, atol=1e-9)),
     # networks too large for one thread: adaptive integration in the persistent network kernel (grid-wide error norm)
     "wc_n128_rk45": dict(build=_wc_pop(128), T=60.0, dt=1e-3, dts=0.5, out="e/rate_op/r", kw=dict(rtol=1e-7, atol=1e-10)),
     "kuramoto_n128_rk45": dict(build=_kuramoto(128), T=10.0, dt=1e-3, dts=0.05, out="e/phase_op/theta",

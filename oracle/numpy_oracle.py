@@ -289,6 +289,103 @@ def solve_rk45(func, args, T, dt, y0, t0, times, rtol=1e-3, atol=1e-6, max_step=
     return rec[:i_eval]
 
 
+# ----------------------------------------------------------------------------- adaptive: solve_ivp(method='DOP853')
+# The reference's documentation uses it (documentation/model_analysis/entrainment.py:56,142).  Restatement of SciPy's DOP853
+# (scipy/integrate/_ivp/rk.py: class DOP853, rk_step, RungeKutta._step_impl, Dop853DenseOutput; coefficients of Hairer,
+# Norsett & Wanner's DOP853 in scipy/integrate/_ivp/dop853_coefficients.py — third-party, read from the installed SciPy):
+# 12 stages, error estimate from the 5th- and 3rd-order embedded formulas, controller exponent -1/8, and a 7th-order dense
+# output that costs three EXTRA rhs evaluations for every step that contains sample times.  The reference's aliased rhs
+# buffer matters twice here: `self.f` is the MOST RECENT evaluation — after a rejected attempt f(t + h_rej, y_rej), and
+# after a dense output the last extra stage — and it is what the dense output uses as "f at the step end" and what the next
+# attempt starts from.
+def solve_dop853(func, args, T, dt, y0, t0, times, rtol=1e-3, atol=1e-6, max_step=np.inf, coeffs=None):
+    if coeffs is None:
+        from scipy.integrate._ivp import dop853_coefficients as coeffs
+    NS, NX = coeffs.N_STAGES, coeffs.N_STAGES_EXTENDED
+    A_, C_, B_ = coeffs.A[:NS, :NS], coeffs.C[:NS], coeffs.B
+    E3, E5, D_ = coeffs.E3, coeffs.E5, coeffs.D
+    A_EXTRA, C_EXTRA = coeffs.A[NS + 1:], coeffs.C[NS + 1:]
+    expo = -1 / 8
+    y = np.asarray(y0).astype(float, copy=False)
+    n = y.size
+    t, t_bound = float(t0), float(T)
+    f = np.asarray(func(t, y, *args), dtype=float)           # alias of the rhs buffer
+    h_abs = float(dt)
+    KX = np.empty((NX, n))
+    K = KX[:NS + 1]
+    rec = np.empty((len(times), n))
+    i_eval = 0
+    while t != t_bound:
+        min_step = 10 * np.abs(np.nextafter(t, np.inf) - t)
+        if h_abs > max_step:
+            h_abs = max_step
+        elif h_abs < min_step:
+            h_abs = min_step
+        rejected = False
+        while True:
+            if h_abs < min_step:
+                raise RuntimeError("Required step size is less than spacing between numbers.")
+            t_new = t + h_abs
+            if t_new - t_bound > 0:
+                t_new = t_bound
+            h = t_new - t
+            h_abs = np.abs(h)
+            K[0] = f
+            for s in range(1, NS):
+                dy = np.dot(K[:s].T, A_[s, :s]) * h
+                K[s] = func(t + C_[s] * h, y + dy, *args)
+            y_new = y + h * np.dot(K[:-1].T, B_)
+            f_new = np.asarray(func(t + h, y_new, *args), dtype=float)
+            K[-1] = f_new
+            f = f_new                                             # aliased buffer
+            scale = atol + np.maximum(np.abs(y), np.abs(y_new)) * rtol
+            err5 = np.dot(K.T, E5) / scale
+            err3 = np.dot(K.T, E3) / scale
+            err5_norm_2 = np.linalg.norm(err5) ** 2
+            err3_norm_2 = np.linalg.norm(err3) ** 2
+            if err5_norm_2 == 0 and err3_norm_2 == 0:
+                error_norm = 0.0
+            else:
+                denom = err5_norm_2 + 0.01 * err3_norm_2
+                error_norm = np.abs(h) * err5_norm_2 / np.sqrt(denom * len(scale))
+            if error_norm < 1:
+                factor = 10.0 if error_norm == 0 else min(10.0, 0.9 * error_norm ** expo)
+                if rejected:
+                    factor = min(1, factor)
+                h_abs *= factor
+                break
+            h_abs *= max(0.2, 0.9 * error_norm ** expo)
+            rejected = True
+        t_old, y_old = t, y
+        t, y = t_new, y_new
+        i_new = int(np.searchsorted(times, t, side="right"))
+        if i_new > i_eval:
+            # Dop853 dense output: three extra stages (they overwrite the aliased buffer f), then the 7-term polynomial
+            for s, (a, c) in enumerate(zip(A_EXTRA, C_EXTRA), start=NS + 1):
+                dy = np.dot(KX[:s].T, a[:s]) * h
+                KX[s] = func(t_old + c * h, y_old + dy, *args)
+                f = np.asarray(KX[s], dtype=float)                # what the aliased buffer holds now
+            F = np.empty((coeffs.INTERPOLATOR_POWER, n))
+            f_old = KX[0]
+            delta_y = y - y_old
+            F[0] = delta_y
+            F[1] = h * f_old - delta_y
+            F[2] = 2 * delta_y - h * (f + f_old)
+            F[3:] = h * np.dot(D_, KX)
+            x = ((times[i_eval:i_new] - t_old) / h)[:, None]
+            out = np.zeros((len(x), n))
+            for i, fi in enumerate(reversed(F)):
+                out += fi
+                if i % 2 == 0:
+                    out *= x
+                else:
+                    out *= 1 - x
+            out += y_old
+            rec[i_eval:i_new] = out
+            i_eval = i_new
+    return rec[:i_eval]
+
+
 # ----------------------------------------------------------------------------- adaptive DDE: solver='scipy' with a history
 # Restatement of BaseBackend._solve_scipy_dde (base_backend.py:771-800):
 #   solver = scipy.integrate.ode(rhs).set_integrator('dopri5', first_step=dt, nsteps=50000); solver.set_solout(hist.update)
@@ -393,6 +490,9 @@ def run_adaptive(func, func_args: Sequence, T: float, dt: float, dts: float = No
     times = np.linspace(0.0, T, num=round(T / step), endpoint=False)
     if _dde(func_args[2:]) is not None:       # base_backend.py:704-706
         return solve_dopri5_dde(func, tuple(func_args[2:]), T, dt, y0, t0, times, **kw), times
+    if kw.get("method") == "DOP853":
+        kw = {k: v for k, v in kw.items() if k != "method"}
+        return solve_dop853(func, tuple(func_args[2:]), T, dt, y0, t0, times, **kw), times
     return solve_rk45(func, tuple(func_args[2:]), T, dt, y0, t0, times, **kw), times
 
 

@@ -57,12 +57,26 @@ __device__ __forceinline__ void prb_axpy(real (&o)[N], const real (&y)[N], const
 extern "C" __global__ void __launch_bounds__(PRB_BLOCK, PRB_MIN_BLOCKS)
 prb_integrate(const __grid_constant__ prb_kernel_args A)
 {
-    constexpr int NST = PRB_RK_NST, NP = PRB_RK_NP;      // stages (RK45: 6, RK23: 3) and dense-output polynomial terms (4 / 3)
+    constexpr int NST = PRB_RK_NST, NP = PRB_RK_NP;      // stages (RK45: 6, RK23: 3, DOP853: 12) and dense-output terms (4 / 3 / 7)
+#ifdef PRB_RK_DOP853
+    // SciPy's DOP853 (pyrates_b200/dop853.py): 12 stages, error estimate from the embedded 5th- and 3rd-order formulas,
+    // 7th-order dense output that needs three EXTRA stages (rows 13..15 of the extended tableau) in every step that contains
+    // sample times.  Row 12 of K is f at the step end.
+    constexpr int NK = PRB_RK_NX;
+    constexpr double C_[NK] = PRB_RK_C_INIT;
+    constexpr double A_[NK][NK - 1] = PRB_RK_A_INIT;
+    constexpr double B_[NST] = PRB_RK_B_INIT;
+    constexpr double E3_[NST + 1] = PRB_RK_E3_INIT;
+    constexpr double E5_[NST + 1] = PRB_RK_E5_INIT;
+    constexpr double D_[NP - 3][NK] = PRB_RK_D_INIT;
+#else
+    constexpr int NK = NST + 1;
     constexpr double C_[NST] = PRB_RK_C_INIT;            // tableau emitted by pyrates_b200/rk45.py (SciPy's RK45 / RK23)
     constexpr double A_[NST][NST - 1] = PRB_RK_A_INIT;
     constexpr double B_[NST] = PRB_RK_B_INIT;
     constexpr double E_[NST + 1] = PRB_RK_E_INIT;
     constexpr double P_[NST + 1][NP] = PRB_RK_P_INIT;    // dense output: y(t_old + x h) = y_old + h * sum_c Q[:, c] x^(c+1), Q = K^T P
+#endif
     const long long B = A.n_inst;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     PRB_STAGE_ETAB
@@ -95,7 +109,7 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
         if (h_abs > max_step) h_abs = max_step;
         else if (h_abs < min_step) h_abs = min_step;
         bool rejected = false;
-        double K[NST + 1][PRB_NS], y_new[PRB_NS];
+        double K[NK][PRB_NS], y_new[PRB_NS];
         double h = 0.0, t_new = t;
         for (;;) {
             if (need_f) {
@@ -136,6 +150,23 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
                 yr[j] = (areal)y_new[j];
             }
             prb_rhs((prb_time)(t + h), yr, kr, T);
+#ifdef PRB_RK_DOP853
+            double sq5 = 0.0, sq3 = 0.0;
+            PRB_UNROLL_NS
+            for (int j = 0; j < PRB_NS; ++j) {
+                f[j] = (double)kr[j];                                  // the aliased buffer: newest evaluation
+                K[NST][j] = f[j];
+                double e5 = 0.0, e3 = 0.0;
+#pragma unroll
+                for (int q = 0; q <= NST; ++q) { e5 += K[q][j] * E5_[q]; e3 += K[q][j] * E3_[q]; }
+                const double scale = atol + fmax(fabs(y[j]), fabs(y_new[j])) * rtol;
+                e5 /= scale; e3 /= scale;
+                sq5 += e5 * e5; sq3 += e3 * e3;
+            }
+            // DOP853._estimate_error_norm: |h| * ||err5||^2 / sqrt((||err5||^2 + 0.01 ||err3||^2) * n)
+            const double error_norm = (sq5 == 0.0 && sq3 == 0.0) ? 0.0
+                : fabs(h) * sq5 / sqrt((sq5 + 0.01 * sq3) * (double)PRB_NS);
+#else
             double sq = 0.0;
             PRB_UNROLL_NS
             for (int j = 0; j < PRB_NS; ++j) {
@@ -149,6 +180,7 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
                 sq += r * r;
             }
             const double error_norm = sqrt(sq) / sqrt((double)PRB_NS);
+#endif
             if (error_norm < 1.0) {
                 double factor = (error_norm == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, PRB_RK_EXPONENT));
                 if (rejected) factor = fmin(1.0, factor);
@@ -167,6 +199,57 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
             need_f = !finite;
         }
         if (status != 0) break;
+#ifdef PRB_RK_DOP853
+        // samples inside (t_old, t_new]: Dop853DenseOutput.  Three extra stages (each overwrites the reference's aliased rhs
+        // buffer, so `f` ends up as the LAST of them — that is what the interpolant uses as "f at the step end" and what
+        // the next attempt starts from), F[0..2] from the step's end points, F[3..6] = h * D . K, then the nested product
+        // y = y_old + x (F0 + (1-x) (F1 + x (F2 + (1-x) (F3 + x (F4 + (1-x) (F5 + x F6))))))
+        if (sample < n_samples && (double)(sample - A.sample0) * te_step <= t_new) {
+#pragma unroll
+            for (int s = NST + 1; s < NK; ++s) {
+                PRB_UNROLL_NS
+                for (int j = 0; j < PRB_NS; ++j) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int q = 0; q < s; ++q) d += K[q][j] * A_[s][q];
+                    yr[j] = (areal)(y[j] + d * h);
+                }
+                prb_rhs((prb_time)(t + C_[s] * h), yr, kr, T);
+                PRB_UNROLL_NS
+                for (int j = 0; j < PRB_NS; ++j) { K[s][j] = (double)kr[j]; f[j] = K[s][j]; }
+            }
+            double F[NP][PRB_NS];
+            PRB_UNROLL_NS
+            for (int j = 0; j < PRB_NS; ++j) {
+                const double dy_ = y_new[j] - y[j];
+                F[0][j] = dy_;
+                F[1][j] = h * K[0][j] - dy_;
+                F[2][j] = 2.0 * dy_ - h * (f[j] + K[0][j]);
+#pragma unroll
+                for (int c = 0; c < NP - 3; ++c) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int q = 0; q < NK; ++q) d += D_[c][q] * K[q][j];
+                    F[3 + c][j] = h * d;
+                }
+            }
+            while (sample < n_samples && (double)(sample - A.sample0) * te_step <= t_new) {
+                const double x = ((double)(sample - A.sample0) * te_step - t) / h;
+                PRB_UNROLL_NS
+                for (int j = 0; j < PRB_NS; ++j) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) {
+                        acc += F[NP - 1 - i][j];
+                        acc *= (i % 2 == 0) ? x : (1.0 - x);
+                    }
+                    yo[j] = (real)(acc + y[j]);
+                }
+                prb_record(yo, out + sample * (long long)PRB_NOBS * B, b, B);
+                ++sample;
+            }
+        }
+#else
         // samples inside (t_old, t_new]: dense output  y_old + h * Q . (x, x^2, .., x^NP),  Q = K^T P
         while (sample < n_samples && (double)(sample - A.sample0) * te_step <= t_new) {
             const double x = ((double)(sample - A.sample0) * te_step - t) / h;
@@ -189,6 +272,7 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
             prb_record(yo, out + sample * (long long)PRB_NOBS * B, b, B);
             ++sample;
         }
+#endif
         t = t_new;
         PRB_UNROLL_NS
         for (int j = 0; j < PRB_NS; ++j) y[j] = y_new[j];

@@ -436,8 +436,12 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     src.append(f"#define PRB_NH {n_hist}")
     src.append(f"#define PRB_HDEPTH {hist_depth}")
     if adaptive and solver != "dopri5_dde":
-        from .rk45 import cuda_method_tables
-        src.append(cuda_method_tables(rk_method))
+        if rk_method == "DOP853":
+            from .dop853 import cuda_tables as dop853_tables
+            src.append(dop853_tables())
+        else:
+            from .rk45 import cuda_method_tables
+            src.append(cuda_method_tables(rk_method))
     if ns > 64:
         src.append("#define PRB_UNROLL_NS")        # big states: keep loops rolled (state spills to local memory)
     src.append("""
@@ -727,6 +731,8 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
     evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4, "scipy": 6, "rk45": 6, "dopri5_dde": 6}[solver]
     if adaptive and rk_method == "RK23":
         evals = 3
+    if adaptive and rk_method == "DOP853":
+        evals = 12
     return InstKernel("\n".join(src) + "\n", ns, np_, len(rhs.slots), len(observers), int(ring_init.size), ring_init,
                       [r.rolls_per_eval for r in rhs.rings], [r.length for r in rhs.rings], tabs,
                       n_hist, hist_depth, list(rhs.hist_vars),

@@ -48,9 +48,9 @@ class InstanceModel:
         # and the tolerances (BaseBackend._solve_scipy_dde, base_backend.py:771-800)
         self.dde = prog.is_dde
         self.rk_method = (rk_method or "RK45") if (self.adaptive and not self.dde) else None     # solve_ivp's `method`
-        if self.adaptive and not self.dde and self.rk_method not in ("RK45", "RK23"):
-            raise rt.CudaBackendError(f"solver='scipy' on the CUDA backend implements method='RK45' (SciPy's default) and "
-                                      f"'RK23'; got method={self.rk_method!r}")
+        if self.adaptive and not self.dde and self.rk_method not in ("RK45", "RK23", "DOP853"):
+            raise rt.CudaBackendError(f"solver='scipy' on the CUDA backend implements SciPy's explicit Runge-Kutta methods "
+                                      f"'RK45' (default), 'RK23' and 'DOP853'; got method={self.rk_method!r}")
         self.precision = "float32" if prog.real_dtype == np.float32 else "float64"      # complex64/128 -> real pairs
         self.real = prog.real_dtype
         self.rhs: ScalarRhs = scalarize(prog, sweep, max_nodes=max_nodes)

@@ -12,15 +12,15 @@ CASES = [("qif", "euler"), ("qif_f32", "heun"), ("jrc", "rk4"), ("net12", "heun_
          ("jrc_2delay", "euler"), ("qsfa_both_n8", "heun"),
          # delay-differential models: history ring (fixed step) / dopri5 + (time, state) history (solver='scipy')
          ("dde_mg", "rk4"), ("dde_net16_f32", "heun"), ("dde_mg_dopri5", "scipy"), ("dde_net16_dopri5_f32", "scipy"),
-         ("dde_jrc_pair_dopri5", "scipy")]
+         ("dde_jrc_pair_dopri5", "scipy"), ("jrc_dop853", "scipy")]
 
 
 @pytest.mark.parametrize("name,solver", CASES)
 def test_instance_kernel_compiles(name, solver):
     os.environ["PRB_CACHE_DIR"] = "off"
-    m = InstanceModel(Program.load(golden_path(name)), solver=solver)
+    m = InstanceModel(Program.load(golden_path(name)), solver=solver, rk_method="DOP853" if "dop853" in name else None)
     src = m.kernel.source
-    assert "prb_integrate" in src and "__grid_constant__" in src
+    assert "prb_integrate" in src and "__grid_constant__" in src and ("PRB_RK_DOP853 1" in src) == ("dop853" in name)
     mod = rt.compile_module(src, f"{name}.cu", verbose_ptxas=True)
     assert mod.cubin[:4] == b"\x7fELF"
     assert "registers" in mod.log

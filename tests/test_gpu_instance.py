@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 SKIP = {"kuramoto_n128", "qsfa_both_n96", "wc_n128", "wc_n128_f32", "jrc_grid_b1024", "wc_n300_f32",
         "qsfa_both_n96_f32", "kuramoto_n128_f32", "wc_n128_rk45", "kuramoto_n128_rk45"}                                             # network-mode fixtures
-ADAPTIVE = [n for n in golden_names() if ("_rk45" in n or "_rk23" in n) and n not in SKIP]
+ADAPTIVE = [n for n in golden_names() if ("_rk45" in n or "_rk23" in n or "_dop853" in n) and n not in SKIP]
 DDE_ADAPTIVE = [n for n in golden_names() if "_dopri5" in n]
 NAMES = [n for n in golden_names() if n not in SKIP and n not in ADAPTIVE and n not in DDE_ADAPTIVE]
 SOLVERS = ["euler", "heun", "heun_true", "rk4"]
@@ -160,6 +160,11 @@ def test_adaptive_rk45_matches_reference_scipy(gpu, name):
     # the last bit (perturbing y0 by 2e-16 moves the ORACLE by 2.8e-5 and changes its attempt count 451 -> 470), so this
     # fixture is compared at the solver's own accuracy; the interpolation itself is pinned by the rhs test below
     tol = 1e-3 if "_input_" in name else 1e-9
+    if "_dop853" in name:
+        # DOP853 + the reference's aliased rhs buffer: the dense output takes "f at the step end" from the LAST extra stage, so
+        # its error depends on the step sequence; one flipped accept / reject decision moves the samples far more than the
+        # solver tolerance (a 1-ulp change of one parameter moves the ORACLE by 2.5e-6 on jrc_dop853, 5.5e-8 on vdp_dop853)
+        tol = 1e-5
     assert traj_rel_err(out[:, :, 0], ref) <= tol, name
 
 

@@ -7,7 +7,7 @@ from conftest import golden_names, golden_path, jacobian_names
 from oracle import numpy_oracle as orc
 
 
-ADAPTIVE = [n for n in golden_names() if "_rk45" in n or "_rk23" in n]
+ADAPTIVE = [n for n in golden_names() if "_rk45" in n or "_rk23" in n or "_dop853" in n]
 DDE_ADAPTIVE = [n for n in golden_names() if "_dopri5" in n]
 
 
@@ -78,6 +78,31 @@ def test_oracle_rk45_coefficients_are_scipys():
                          (orc.RK45_P, rk.RK45.P), (orc.RK23_A, rk.RK23.A), (orc.RK23_B, rk.RK23.B), (orc.RK23_C, rk.RK23.C),
                          (orc.RK23_E, rk.RK23.E), (orc.RK23_P, rk.RK23.P)):
         assert np.array_equal(mine, theirs)
+
+
+def test_dop853_coefficients_are_scipys_and_oracle_matches_solve_ivp():
+    """pyrates_b200/dop853.py carries the doubles of SciPy's dop853_coefficients; the restated DOP853 (error estimate from
+    the 5th / 3rd order pair, extra stages + 7-term dense output) is scipy.solve_ivp itself on a function that returns fresh
+    arrays — apart from the aliasing of `f`, which a plain function does not have: emulate plain SciPy by handing the oracle a
+    function whose result is copied."""
+    integ = pytest.importorskip("scipy.integrate")
+    from scipy.integrate._ivp import dop853_coefficients as d
+    from pyrates_b200 import dop853 as mine
+    for name in ("A", "B", "C", "E3", "E5", "D"):
+        assert np.array_equal(np.array(getattr(mine, name)), getattr(d, name)), name
+    assert (mine.N_STAGES, mine.N_STAGES_EXTENDED, mine.INTERPOLATOR_POWER) == (d.N_STAGES, d.N_STAGES_EXTENDED, d.INTERPOLATOR_POWER)
+    buf = np.zeros(2)
+
+    def f_alias(t, y):                       # like the reference's generated rhs: returns its in-place buffer
+        buf[0] = y[1]
+        buf[1] = -4.0 * y[0] - 0.1 * y[1] + np.sin(3 * t)
+        return buf
+    times = np.linspace(0.0, 5.0, 100, endpoint=False)
+    ref = integ.solve_ivp(f_alias, (0.0, 5.0), np.array([1.0, 0.0]), first_step=1e-3, t_eval=times, rtol=1e-8, atol=1e-10,
+                          method="DOP853").y.T
+    buf[:] = 0
+    rec = orc.solve_dop853(f_alias, (), 5.0, 1e-3, np.array([1.0, 0.0]), 0.0, times, rtol=1e-8, atol=1e-10)
+    assert np.array_equal(rec, ref)
 
 
 def test_oracle_rk45_matches_solve_ivp_on_a_plain_function():

@@ -14,7 +14,7 @@ LARGE = {"kuramoto_n128", "qsfa_both_n96", "wc_n128", "wc_n128_f32", "jrc_grid_b
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names() if n not in LARGE and "_rk45" not in n and "_rk23" not in n
-                                  and "_dopri5" not in n])
+                                  and "_dopri5" not in n and "_dop853" not in n])
 def test_dag_matches_reference_euler(name):
     fx = orc.load_fixture(golden_path(name))
     prog = Program.load(golden_path(name))
