@@ -158,8 +158,8 @@ class CudaVectorField:
             lines = [f"def {self.__name__}({','.join(self.arg_names)}):", f"\t{name} = zeros({tuple(shape)})"]
             lines += ["\t" + st.text() for st in self.stmts] + [f"\treturn {name}"]
             return "\n".join(lines) + "\n"
-        return Program([Arg(n, "const", np.zeros(())) for n in self.arg_names], self.stmts,
-                       func_name=self.__name__).source().replace("return t", f"return {self.return_var}")
+        lines = [f"def {self.__name__}({','.join(self.arg_names)}):"] + ["\t" + st.text() for st in self.stmts]
+        return "\n".join(lines + [f"\treturn {self.return_var}"]) + "\n"
 
     def __call__(self, t, y, *args):
         from .engine import evaluate_rhs
@@ -211,10 +211,13 @@ class CudaBackend:
         self._idx_left, self._idx_right = '[', ']'
         self._start_idx = 0
         kwargs.pop('idx_left', None), kwargs.pop('idx_right', None), kwargs.pop('start_idx', None)
+        # like the reference (base_backend.py:316-324) the generated function is written to `<file_name>.py` for inspection
+        # — here in the NumPy-syntax form the compute graph printed, i.e. the text the CUDA kernels are lowered from
         fname = kwargs.pop('file_name', 'pyrates_run')
-        self.fdir = ""
+        self.fdir = os.path.dirname(fname)
         self._fname = os.path.basename(fname).split('.')[0]
-        self._fend = ".cu"
+        self._fend = ".py"
+        self._written: Optional[str] = None
         # CUDA-specific options, popped so they never leak into solver kwargs (SURVEY §5 "config / flags")
         self.device = kwargs.pop('device', None)
         self.fmad = kwargs.pop('fmad', True)
@@ -389,6 +392,17 @@ class CudaBackend:
             else:
                 jac = (names[0], self._local_arrays[names[0]], None)
         func = CudaVectorField(self, func_name, args, stmts, state_var, return_var, jacobian=jac)
+        if to_file:
+            try:
+                if self.fdir:
+                    os.makedirs(self.fdir, exist_ok=True)
+                path = os.path.join(self.fdir, f"{self._fname}{self._fend}")
+                with open(path, "w") as f:
+                    f.write("# vector field recorded by pyrates_b200.CudaBackend (NumPy-syntax form; lowered to CUDA C at run time)\n")
+                    f.write(self.generate() + "\n")
+                self._written = path
+            except OSError:
+                self._written = None
         decorator = kwargs.pop('decorator', None)
         if decorator:
             raise _backend_error("CudaBackend does not support python decorators on the vector field")
@@ -405,6 +419,12 @@ class CudaBackend:
         np.savez(fn, **kwargs)
 
     def clear(self):
+        if getattr(self, "_written", None):             # base_backend.py:613-627: generated files go with the model
+            try:
+                os.remove(self._written)
+            except OSError:
+                pass
+            self._written = None
         self.code.clear()
         self._stmts = []
         self._n_hist_stmts = 0

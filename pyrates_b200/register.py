@@ -15,6 +15,8 @@ See INTEGRATION.md for the three-line upstream patch that would replace the monk
 """
 from __future__ import annotations
 
+import os
+
 import functools
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -158,7 +160,7 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     reduce = bool(kwargs.pop("reduce", False))
     shard = kwargs.pop("shard", None)
     verbose = kwargs.pop("verbose", False)
-    kwargs.pop("clear", None)
+    user_clear = kwargs.pop("clear", True)
     chunk_samples = kwargs.pop("chunk_samples", 100)
     const_div_to_mul = kwargs.pop("const_div_to_mul", False)
     fast_math = kwargs.pop("fast_math", False)
@@ -208,14 +210,24 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
                     full = var_key if var_key is not None else outputs[key]
                     *nodes, op, var = full.split("/")
                     cols.append((key, tuple(nodes), f"{op}/{var}"))
+        text = func.source()
         try:
             circuit.clear()
         except Exception:
             pass
-        return {"program": prog, "observers": obs, "columns": cols}
+        return {"program": prog, "observers": obs, "columns": cols, "text": text}
 
     base, targets = _probe_positions(template, keys, param_map, build)
     prog: Program = base["program"]
+    if user_clear is False:
+        # clear=False keeps the generated function file of the reference around (its documentation prints it,
+        # documentation/model_analysis/entrainment.py:144-157): here the single-instance vector field every grid point runs
+        fname = str(kwargs.get("file_name", "pyrates_run"))
+        try:
+            with open(os.path.splitext(fname)[0] + ".py", "w") as fh:
+                fh.write("# vector field of ONE grid point, recorded by pyrates_b200 (all grid points run it as a batch)\n" + base["text"])
+        except OSError:
+            pass
     y_name = prog.arg_by_kind("y").name
     sweep, rows, y0_rows = [], [], []
     for k in keys:

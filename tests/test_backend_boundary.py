@@ -254,6 +254,25 @@ def test_documentation_entrainment_example_dop853_on_cuda(gpu, registered):
 
 
 @needs_ref
+def test_generated_function_file_is_written_and_cleared_like_the_reference(registered, tmp_path):
+    """`file_name=` / `clear=`: like the NumPy backend (base_backend.py:316-324, 537-578, 613-627) the recorded vector field is
+    written to `<file_name>.py` (users and the reference's documentation print it) and removed again by clear()."""
+    from pyrates import clear
+    c = _fresh("model_templates.neural_mass_models.qif.qif")
+    func, args, names, _ = c.get_run_func("vector_field", step_size=1e-3, backend="cuda", solver="euler", verbose=False,
+                                          clear=False, file_name="qif_generated")
+    path = tmp_path / "qif_generated.py"
+    assert path.exists()
+    text = path.read_text()
+    assert "def vector_field(t,y,dy" in text and "dy[0] =" in text and "return dy" in text
+    src = func.source()
+    assert src.startswith("def vector_field(") and src.rstrip().endswith("return dy")
+    assert all(st.text() in src for st in func.stmts)
+    clear(c)
+    assert not path.exists()
+
+
+@needs_ref
 def test_new_solver_names_are_fixed_step(registered):
     import pyrates.frontend.template.circuit as fc
     assert not fc.is_integration_adaptive("rk4") and not fc.is_integration_adaptive("heun_true")
