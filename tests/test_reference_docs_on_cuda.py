@@ -1,0 +1,30 @@
+"""Drop-in check on the reference's own documentation gallery: every script that works upstream runs unchanged with
+backend='cuda' up to the kernel launch (tests/docs_harness.py: program capture, lowering, CUDA emission, NVRTC compile for
+sm_100a; the launch itself is covered by the GPU suites).  Needs the reference source tree (build container only)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+DOCS = "/root/reference/documentation"
+SCRIPTS = ["model_introductions/kuramoto", "model_introductions/vanderpol", "model_introductions/stuartlandau",
+           "model_introductions/qif", "model_introductions/theta", "model_introductions/izhikevich",
+           "model_introductions/jansenrit", "model_introductions/wilsoncowan", "model_analysis/simulations",
+           "model_analysis/parameter_sweeps",       # grid_search with a shared noise input, two outputs, cutoff
+           "model_analysis/entrainment",            # solver='scipy', method='DOP853', run + grid_search, prints the generated file
+           "model_implementation/delay_coupling", "model_implementation/edge_definitions",
+           "model_implementation/population_connectivity"]
+# not listed: model_analysis/dde.py (fails upstream too: buffer-name collision in ir/circuit.py:674), continuation.py
+# (needs the fortran backend / PyCoBi), optimization.py and jacobian_parameter_fitting.py (minutes of SciPy optimisation)
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(DOCS), reason="reference documentation tree not present on this machine")
+
+
+@pytest.mark.parametrize("script", SCRIPTS)
+def test_documentation_script_builds_and_compiles_on_cuda(script, tmp_path):
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, os.path.join(here, "docs_harness.py"), os.path.join(DOCS, script + ".py"), str(tmp_path)],
+                         capture_output=True, text=True, timeout=600)
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
+    assert line and line[-1].startswith("RESULT OK"), (line[-1] if line else out.stderr[-800:])
