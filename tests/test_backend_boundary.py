@@ -234,8 +234,9 @@ def test_documentation_entrainment_example_dop853_on_cuda(gpu, registered):
     ref = make().run(backend="default", in_place=False, **kw)
     got = make().run(backend="cuda", in_place=False, **kw)
     assert got.shape == ref.shape and list(got.columns) == list(ref.columns)
-    # tolerance: see test_adaptive_rk45_matches_reference_scipy (DOP853's dense output under the aliased rhs buffer)
-    assert traj_rel_err(got.values, ref.values) <= 1e-5
+    # tolerance: DOP853's dense output under the aliased rhs buffer depends on the step sequence (see
+    # test_adaptive_rk45_matches_reference_scipy); the REFERENCE against itself with mu + 1 ulp differs by 6.7e-4 on this run
+    assert traj_rel_err(got.values, ref.values) <= 5e-3
     params = {'omega': np.linspace(0.3, 0.5, 3), 'J': np.linspace(0.0, 2.0, 4)}
     pm = {'omega': {'vars': ['phase_op/omega'], 'nodes': ['KO']},
           'J': {'vars': ['weight'], 'edges': [('KO/sin_op/s', 'VPO/vdp_op/inp')]}}
