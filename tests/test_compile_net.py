@@ -77,6 +77,29 @@ def test_tensor_core_sweep_kernels_compile(name, sweep, nb, bt):
         assert "UTCHMMA" in sass and "LDTM" in sass and "UBLKCP" in sass
 
 
+def test_fp64_sweep_kernel_uses_dmma_and_streaming_gemv_uses_wide_nonallocating_loads():
+    """SASS evidence without a GPU: the float64 sweep-batched coupling runs on the FP64 tensor path (DMMA, mma.sync.m8n8k4.f64)
+    and the single-instance GEMV streams W with 128-bit loads that do not allocate in L1 (LDG.E.128 ... no_allocate)."""
+    import shutil, subprocess, tempfile
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    os.environ["PRB_CACHE_DIR"] = "off"
+
+    def sass_of(model, tag):
+        mod = rt.compile_module(model.kernel.source, f"{tag}.cu")
+        with tempfile.NamedTemporaryFile(suffix=".cubin") as f:
+            f.write(mod.cubin)
+            f.flush()
+            return subprocess.run(["cuobjdump", "-sass", f.name], capture_output=True, text=True).stdout
+    prog = Program.load(golden_path("wc_n128"))
+    batched = NetworkModel(prog, solver="rk4", n_batch=128, sweep=["r_ext"])
+    assert batched.kernel.tc is None and "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64" in batched.kernel.source
+    assert "DMMA" in sass_of(batched, "wc_dmma")
+    single = NetworkModel(prog, solver="euler")
+    sass = sass_of(single, "wc_gemv")
+    assert any("LDG" in l and ".128" in l for l in sass.splitlines()), "expected 128-bit global loads in the W stream"
+
+
 def test_tensor_core_path_is_float32_only():
     prog = Program.load(golden_path("wc_n128"))
     assert NetworkModel(prog, solver="euler", n_batch=128, sweep=["r_ext"]).kernel.tc is None      # fp64 -> FMA tiles
