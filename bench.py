@@ -1,19 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the PyRates numerical-integration hot path on B200.
+"""bench.py — the PyRates numerical-integration hot path on B200: headline benchmark + every BASELINE.json config.
 
-Workload (BASELINE.json configs[1]): Jansen-Rit 3-population circuit (8 state
-variables), classic RK4, dt=1e-4, T=1 (1e4 solver steps), grid_search over a 1024x1024 (C, u) grid =
-2^20 parameter sets per GPU, observer pc/rpo_e_in/v sampled every 1e-3 -> [1000, 2^20] fp64.
-One bench "step" = one complete simulation of all instances of this rank (1e4 solver steps each).
-Instances shard across GPUs with no data-path collective (weak scaling: 2^20 instances per GPU).
+Headline (BASELINE.json configs[1]): Jansen-Rit 3-population circuit (8 state variables), classic
+RK4, dt=1e-4, T=1 (1e4 solver steps), grid_search over a 1024x1024 (C, u) grid = 2^20 parameter sets per GPU, observer
+pc/rpo_e_in/v sampled every 1e-3 -> [1000, 2^20] fp64.  One bench "step" = one complete simulation of all instances of
+this rank.  Instances shard across GPUs with no data-path collective (weak scaling: 2^20 instances per GPU); the
+strong-scaling record (2^20 instances in total, split over the GPUs) rides along as `strong_scaling`.
 
 Metric: state-updates/s = nodes x sweep-instances x solver-steps / s  (nodes = 3 for the JRC).
 
   value : device-resident inputs, kernels only (CUDA events on the launching stream)
   e2e   : the public BatchedSweep.run() call — host parameter table in, host trajectories out
           (pinned H2D of parameters + initial state, chunked D2H of all observers overlapped with compute)
-  --impl reference : the reference algorithm on the host CPU (oracle port of the NumPy backend running
-          the reference-generated vectorised grid program, tests/golden/jrc_grid_b1024.npz)
+  configs : the other BASELINE.json configurations in the same JSON line, each with value / roofline / e2e / cpu_baseline:
+          c1 (QIF, one instance), c3 / c3_rk4 (Wilson-Cowan N=8192 dense GEMV), c4 (QIF-SFA 2 x 1024, gamma cascade + delay
+          ring), c4_2x2048, c5 / c5_rk4 (Kuramoto N=65536, dense 32 GiB W generated on the device), c5a (scalar all-to-all
+          `vsum`), c3_sweep_f32 / c3_sweep_f64 (grid_search over the N=8192 network: coupling as ONE tcgen05 / DMMA GEMM per
+          evaluation).  Under torchrun the single networks (c3, c4, c5) shard the ROWS of W over the ranks with the stage
+          vectors exchanged inside the kernel (LL packets over NVLink); network sweeps shard their instances.
+  public_api : pyrates.grid_search(JRC yaml, 1024x1024 grid, backend='cuda', solver='rk4', as_arrays=True) timed through the
+          reference front end installed under baseline/_ref (N = 1 only)
+  --impl reference : the reference itself on the host CPU (baseline/_ref: its own grid_search build + NumPy backend; an RK4
+          loop around its generated vector field, one process per host core)
 """
 from __future__ import annotations
 
@@ -33,24 +41,25 @@ sys.path.insert(0, ROOT)
 NODES = 3                      # JRC: pc, ein, iin
 B_ALG = (2 * 8 + 5) * 8 + 8 / 10   # (2*n_sv + n_pp)*s + n_obs*s/store_step = 168.8 B / instance-step
 SWEEP = [("u", 0), ("weight_v2", 0), ("weight_v2", 1), ("weight", 0), ("weight_v1", 0)]
-# dram__bytes_read.sum + dram__bytes_write.sum of one prb_integrate launch (2^20 instances x 1000 steps, 100 samples)
-# from the `ncu --set full` capture summarised in profiles/r01_c2_fastmath_prb_integrate_ncu_full.txt (110.79 + 847.40 MB;
-# the exact kernel, profiles/r01_c2_prb_integrate_ncu_full.txt: 114.07 + 848.98 MB — the observer store either way).
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 958.2e6
-# per-launch DRAM bytes by instance-steps per launch: 1000-step launches (--chunk-samples 100) and the default 250-step
-# launches (--chunk-samples 25; profiles/r01_c2_fastmath_chunk25_ncu_full.txt)
-NCU_TRAFFIC = {2 ** 20 * 1000: NCU_TRAFFIC_BYTES_PER_LAUNCH, 2 ** 20 * 250: 331.16e6}    # 109.19 + 221.97 MB (r01_c2_reassoc capture)
-FP64_INSTR = {True: 265, False: 505}     # fp64-pipe instructions per instance-step in the loop (cuobjdump, fast / exact kernel)
+# dram__bytes_read.sum + dram__bytes_write.sum of one prb_integrate launch from `ncu --set full` captures: 1000-step launches
+# (--chunk-samples 100; profiles/r01_c2_fastmath_prb_integrate_ncu_full.txt) and the default 250-step launches
+# (--chunk-samples 25; 109.19 + 221.97 MB, profiles/r01_c2_reassoc_prb_integrate_ncu_full.txt)
+NCU_TRAFFIC = {2 ** 20 * 1000: 958.2e6, 2 ** 20 * 250: 331.16e6}
+# fp64-pipe warp instructions per instance-step inside the SASS time loop (cuobjdump; tests/test_compile_inst.py pins them)
+FP64_INSTR = {True: 265, False: 505}
 METRIC = "state-updates/sec (nodes x sweeps x steps/s), JRC RK4 grid_search"
 UNIT = "node-steps/s"
+JRC_YAML = "model_templates.neural_mass_models.jansenrit.JRC"
 
 
-def peaks():
+def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+            d = json.load(f)
+        return {"hbm": float(d["hbm_gbs"]), "bf16": float(d.get("bf16_tflops", 1656.7)),
+                "bf16_sustained": float(d.get("bf16_tflops_sustained", 1388.2)), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "bf16": 1656.7, "bf16_sustained": 1388.2, "source": "fallback (B200_PROFILING.md)"}
 
 
 def param_table(n_c: int, n_u: int, lo: int, hi: int) -> np.ndarray:
@@ -60,6 +69,19 @@ def param_table(n_c: int, n_u: int, lo: int, hi: int) -> np.ndarray:
     idx = np.arange(lo, hi)
     Cv, uv = C[idx % n_c], u[(idx // n_c) % n_u]
     return np.stack([uv, Cv, Cv / 4, 0.8 * Cv, Cv / 4])
+
+
+def jrc_grid(side: int):
+    """The (C, u) sweep of documentation/model_analysis/parameter_sweeps.py:44-90 as pyrates.grid_search takes it: a
+    linearised side x side grid over C and u, the four JRC coupling weights tied to C (C, 0.8 C, C/4, C/4)."""
+    from pyrates.utility import linearize_grid
+    grid = linearize_grid({"C": np.linspace(68.0, 1350.0, side), "u": np.linspace(120.0, 320.0, side)}, permute=True)
+    grid["C2"], grid["C4"] = 0.8 * grid["C"], 0.25 * grid["C"]
+    pmap = {"C": {"vars": ["weight"], "edges": [("pc/pro/m", "ein/rpo_e/m_in")]},
+            "C2": {"vars": ["weight"], "edges": [("ein/pro/m", "pc/rpo_e_in/m_in")]},
+            "C4": {"vars": ["weight"], "edges": [("pc/pro/m", "iin/rpo_e/m_in"), ("iin/pro/m", "pc/rpo_i/m_in")]},
+            "u": {"vars": ["rpo_e_in/u"], "nodes": ["pc"]}}
+    return grid, pmap
 
 
 class ClockSampler:
@@ -96,10 +118,10 @@ class ClockSampler:
                 "samples": len(rows), "reasons": reasons}
 
 
-# ----------------------------------------------------------------------------- CPU arm
-def cpu_reference(steps: int, warmup: int, sim_T: float):
-    """Reference algorithm on the host: oracle port (NumPy) of BaseBackend's loop around the
-    reference-generated *vectorised* grid program (B=1024, what pyrates.grid_search builds)."""
+# ============================================================================= CPU arms
+def cpu_port_c2(steps: int, warmup: int, sim_T: float):
+    """The reference ALGORITHM on the host: oracle port (NumPy) of BaseBackend's loop around the reference-generated
+    *vectorised* grid program (B=1024, what pyrates.grid_search builds), one NumPy thread."""
     from oracle import numpy_oracle as orc
     fx = orc.load_fixture(os.path.join(ROOT, "tests", "golden", "jrc_grid_b1024.npz"))
     B = 1024
@@ -117,6 +139,427 @@ def cpu_reference(steps: int, warmup: int, sim_T: float):
     return val, sec, {"value": val, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": "port", "sample": sample}
 
 
+def _ref_rk4_worker(q_in, q_out, func, func_args, n_steps, dt, store_step, n_samples):
+    """One host process of the reference arm: classic RK4 around the reference-generated vector field, written like
+    BaseBackend._solve_euler (base_backend.py:712-740: record before the update, integer step counter for every stage,
+    `.copy()` because the generated function returns its in-place dy buffer)."""
+    t0, y, *args = func_args
+    y = np.array(y, copy=True)
+    while True:
+        msg = q_in.get()
+        if msg is None:
+            return
+        y[:] = func_args[1]
+        rec = np.zeros((n_samples, y.shape[0]), dtype=y.dtype)
+        t = time.perf_counter()
+        idx = 0
+        for i in range(n_steps):
+            if i % store_step == 0:
+                rec[idx] = y
+                idx += 1
+            step = i + t0
+            k1 = func(step, y, *args).copy()
+            k2 = func(step, y + (0.5 * dt) * k1, *args).copy()
+            k3 = func(step, y + (0.5 * dt) * k2, *args).copy()
+            k4 = func(step, y + dt * k3, *args)
+            y += (dt / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
+        q_out.put((time.perf_counter() - t, float(rec[-1, 0])))
+
+
+def reference_arm(a, config):
+    """`--impl reference`: the UNMODIFIED reference installed under baseline/_ref on the host cores — its own grid_search
+    build (deep copies + vectorisation, utility.py:244-251) and NumPy backend.  The reference has no fixed-step RK4
+    (SURVEY headline 3), so the RK4 number is a hand loop in the style of its _solve_euler around ITS generated function
+    (one process per host core, each integrating a B-point block); its stock `solver='heun'` run is timed next to it."""
+    import multiprocessing as mp
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle.ref_env import import_reference
+    B = a.ref_batch
+    sim_T = a.cpu_sim_time
+    dt, dts = 1e-4, 1e-3
+    n_steps = int(round(sim_T / dt))
+    pyrates = import_reference()
+    if pyrates is None:
+        val, sec, cb = cpu_port_c2(a.steps, a.warmup, sim_T)
+        cb["note"] = "baseline/_ref not importable: oracle port timed instead"
+        return val, sec, cb
+    import pyrates.backend.base.base_backend as bb
+    side = int(round(B ** 0.5))
+    grid, pmap = jrc_grid(side)
+    captured = {}
+    orig_run = bb.BaseBackend.run
+
+    def timed_run(self, func, func_args, T, dt, dts, solver, **kw):          # timing wrapper only (SURVEY Appendix A.4)
+        captured["func"], captured["args"] = func, [np.array(x, copy=True) for x in func_args]
+        t = time.perf_counter()
+        out = orig_run(self, func, func_args, T, dt, dts, solver, **kw)
+        captured["run_s"] = time.perf_counter() - t
+        return out
+
+    bb.BaseBackend.run = timed_run
+    cwd = os.getcwd()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    os.chdir(os.path.join(ROOT, "gpurun_out"))                               # the reference writes its generated module to the cwd
+    try:
+        t = time.perf_counter()
+        pyrates.grid_search(JRC_YAML, grid, pmap, step_size=dt, simulation_time=min(sim_T, 0.2), sampling_step_size=dts,
+                            outputs={"v": "pc/rpo_e_in/v"}, solver="heun", backend="default",
+                            float_precision="float64", clear=False, verbose=False)
+        total_s = time.perf_counter() - t
+    finally:
+        bb.BaseBackend.run = orig_run
+        os.chdir(cwd)
+    heun_steps = int(round(min(sim_T, 0.2) / dt))
+    heun_val = NODES * side * side * heun_steps / captured["run_s"]
+    build_s = total_s - captured["run_s"]
+    # RK4: one process per host core around the captured reference function
+    cores = max(1, min(os.cpu_count() or 1, a.ref_procs if a.ref_procs else (os.cpu_count() or 1)))
+    ctx = mp.get_context("fork")
+    store_step = int(round(dts / dt))
+    n_samples = int(round(sim_T / dts))
+    qs = [(ctx.Queue(), ctx.Queue()) for _ in range(cores)]
+    procs = [ctx.Process(target=_ref_rk4_worker, args=(qi, qo, captured["func"], captured["args"], n_steps, dt, store_step, n_samples),
+                         daemon=True) for qi, qo in qs]
+    for p in procs:
+        p.start()
+    times = []
+    for it in range(a.warmup + a.steps):
+        t = time.perf_counter()
+        for qi, _ in qs:
+            qi.put(1)
+        res = [qo.get() for _, qo in qs]
+        wall = time.perf_counter() - t
+        if it >= a.warmup:
+            times.append(wall)
+    for qi, _ in qs:
+        qi.put(None)
+    for p in procs:
+        p.join(timeout=10)
+    sec = float(np.mean(times))
+    val = NODES * side * side * cores * n_steps / sec
+    cb = {"value": val, "unit": UNIT, "cores": cores, "host_cores": os.cpu_count(), "kind": "reference",
+          "sample": (f"{cores} processes x B={side * side} ({side}x{side} (C,u) block built by the reference's own grid_search), "
+                     f"T={sim_T} ({n_steps} RK4 steps around the reference-generated NumPy vector field, fp64)"),
+          "build_s": build_s, "stock_heun": {"value": heun_val, "unit": UNIT, "run_s": captured["run_s"], "steps": heun_steps,
+                                             "note": "pyrates.grid_search(..., solver='heun') as shipped, 1 process"},
+          "checksum": res[0][1]}
+    return val, sec, cb
+
+
+# ============================================================================= network configs (C3 / C4 / C5)
+class Ctx:
+    """Process-level state of the GPU arm."""
+
+    def __init__(self, a):
+        self.a = a
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.dist = None
+        self.peaks = measured_peaks()
+
+    def barrier(self):
+        from pyrates_b200 import runtime as rt
+        if self.dist is not None:
+            self.dist.barrier()
+        rt.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def _oracle_network_cpu(prog, solver, dt, cpu_steps, nodes):
+    """NumPy path on the host cores: the oracle port executing the reference-generated program (OpenBLAS threads = default)."""
+    from oracle import numpy_oracle as orc
+    f = orc.build_vector_field(prog.source())
+    args = [np.array(x.value, copy=True) for x in prog.args]
+    args[0] = args[0][()]
+    orc.run(f, [np.array(x, copy=True) for x in args], 2 * dt, dt, None, solver)          # warm-up (BLAS threads, caches)
+    t0 = time.perf_counter()
+    orc.run(f, args, cpu_steps * dt, dt, None, solver)
+    cpu_s = time.perf_counter() - t0
+    return {"value": nodes * cpu_steps / cpu_s, "unit": UNIT, "kind": "port", "cores": os.cpu_count(),
+            "sample": f"{cpu_steps} {solver} steps of the same program, NumPy oracle port, OpenBLAS default threads"}
+
+
+def bench_network(cx: Ctx, tag: str, prog, how: str, *, solver: str, nodes: int, sim_steps: int, e2e_steps: int, workload: str,
+                  obs, store_step: int = 10, dt: float = 1e-3, cpu_prog=None, cpu_steps: int = 0, cpu_note: str = "",
+                  resident: str = "hbm"):
+    """One single-network config: rows of W sharded over the ranks when world > 1 (in-kernel exchange), else one GPU."""
+    from pyrates_b200 import runtime as rt
+    from pyrates_b200.netengine import NetworkModel
+    a = cx.a
+    t0 = time.perf_counter()
+    m = NetworkModel(prog, solver=solver, observers=obs, rank=cx.rank, world=cx.world)
+    m.module
+    jit_s = time.perf_counter() - t0
+    n_samples = -(-max(sim_steps, e2e_steps) // store_step)
+    s = m.session(n_samples)
+    K, W = a.steps, max(a.warmup, 3)
+    for _ in range(W):
+        s.reset()
+        s.launch(sim_steps, dt, store_step)
+    cx.barrier()
+    s.check()
+    ev = [(rt.Event(), rt.Event()) for _ in range(K)]
+    for k in range(K):
+        s.reset()
+        s.launch(sim_steps, dt, store_step, events=ev[k])
+    cx.barrier()
+    s.check()
+    ms = cx.max_over_ranks(sum(e0.elapsed_ms(e1) for e0, e1 in ev))
+    value = nodes * sim_steps * K / (ms * 1e-3)
+    evals = m.kernel.evals_per_step
+    item = np.dtype(m.real).itemsize
+    wbytes_rank = sum((hi - lo) * arr.shape[1] for arr, (lo, hi) in
+                      ((arr, _bounds(arr.shape[0], cx.world, cx.rank)) for arr in m.ir.arrays.values()
+                       if arr.space == "const" and len(arr.shape) == 2)) * item
+    achieved = wbytes_rank * evals * sim_steps * K / (ms * 1e-3) / 1e9
+    # end to end: host state in (constants stay resident in the session, like the arguments of a compiled model across
+    # run() calls), recorded trajectories + final state back in host memory
+    y0 = np.array(prog.y0, copy=True)
+    e2e_t = []
+    for k in range(1 + min(K, 2)):
+        cx.barrier()
+        t = time.perf_counter()
+        s.reset(y0)
+        s.launch(e2e_steps, dt, store_step)
+        host = s.download()
+        yf = s.download_state()
+        e2e_t.append(time.perf_counter() - t)
+    e2e_s = cx.max_over_ranks(float(np.mean(e2e_t[1:])))
+    ns_e2e = -(-e2e_steps // store_step)
+    rec = {"workload": workload, "program": how, "solver": solver, "n_gpus": cx.world,
+           "sharding": "rows of W (stage vectors exchanged in-kernel as LL packets over NVLink)" if cx.world > 1 else "none",
+           "value": value, "unit": UNIT, "steps": K, "warmup": W, "solver_steps_per_step": sim_steps,
+           "ms_per_step": ms / K, "us_per_solver_step": ms * 1e3 / (K * sim_steps), "evals_per_solver_step": evals,
+           "dtype": "f64" if item == 8 else "f32",
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": cx.peaks["hbm"], "unit": "GB/s", "frac": achieved / cx.peaks["hbm"],
+                        "algorithmic_bytes_per_launch": wbytes_rank * evals * sim_steps,
+                        "model": "this rank's rows of W (fp64) x rhs evaluations per solver step x solver steps; vectors negligible",
+                        "W_resident_in": resident, "peak_source": cx.peaks["source"], "traffic": None},
+           "e2e": {"value": nodes * e2e_steps / e2e_s, "unit": UNIT, "solver_steps": e2e_steps, "ms": e2e_s * 1e3,
+                   "h2d_bytes_per_step": int(y0.nbytes + m.kernel.ring_init.nbytes + m.kernel.work_init.nbytes),
+                   "d2h_bytes_per_step": int(host[:ns_e2e].nbytes + yf.nbytes),
+                   "api": "NetworkSession.reset(y0) / launch / download (constants resident)", "checksum": float(host[ns_e2e - 1, 0, 0])},
+           "gpu_launches": K, "jit_s": jit_s, "phases": m.kernel.n_phases, "block": m.kernel.block}
+    s.free()
+    if cx.rank == 0 and cx.world == 1 and cpu_steps and not a.no_cpu_baseline:
+        cb = _oracle_network_cpu(cpu_prog if cpu_prog is not None else prog, solver, dt, cpu_steps, nodes if cpu_prog is None else
+                                 int(np.asarray(cpu_prog.y0).size))
+        if cpu_note:
+            cb["sample"] += "; " + cpu_note
+        rec["cpu_baseline"] = cb
+    return rec
+
+
+def _bounds(n, world, rank):
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def bench_network_sweep(cx: Ctx, tag: str, prog, how: str, *, precision: str, batch: int, sweep, sim_steps: int, nodes: int,
+                        workload: str, dt: float = 1e-3):
+    """grid_search over a network: all instances share the connectivity, the coupling is ONE GEMM per evaluation (tcgen05
+    3xTF32 for float32, DMMA for float64).  Under torchrun the INSTANCES shard (every rank its own `batch`), no collective."""
+    import bench_configs as bc
+    from pyrates_b200 import runtime as rt
+    from pyrates_b200.netengine import NetworkModel
+    a = cx.a
+    if precision == "float32":
+        prog = bc.to_float32(prog)
+    t0 = time.perf_counter()
+    m = NetworkModel(prog, solver="euler", observers=[0], n_batch=batch, sweep=sweep)
+    m.module
+    jit_s = time.perf_counter() - t0
+    params = m.param_defaults[:, None] * (1.0 + 0.1 * np.random.default_rng(3 + cx.rank).uniform(-1, 1, (len(sweep), batch))) \
+        + 0.05 * np.random.default_rng(4 + cx.rank).uniform(0, 1, (len(sweep), batch))
+    s = m.session(sim_steps)
+    K, W = a.steps, max(a.warmup, 3)
+    for _ in range(W):
+        s.reset(params=params)
+        s.launch(sim_steps, dt, 1)
+    cx.barrier()
+    s.check()
+    ev = [(rt.Event(), rt.Event()) for _ in range(K)]
+    for k in range(K):
+        s.reset(params=params)
+        s.launch(sim_steps, dt, 1, events=ev[k])
+    cx.barrier()
+    s.check()
+    ms = cx.max_over_ranks(sum(e0.elapsed_ms(e1) for e0, e1 in ev))
+    value = nodes * batch * cx.world * sim_steps * K / (ms * 1e-3)
+    flops = sum(2.0 * r.n * r.m for r in m.ir.reductions if r.kind == "row") * batch * sim_steps * K       # per GPU
+    tf = flops / (ms * 1e-3) / 1e12
+    if m.kernel.tc is not None:
+        peak = cx.peaks["bf16"] / 2
+        roof = {"bound": "tensor", "achieved": 3 * tf, "peak": peak, "unit": "TFLOP/s", "frac": 3 * tf / peak,
+                "frac_of_sustained": 3 * tf / (cx.peaks["bf16_sustained"] / 2), "fp32_equivalent_tflops": tf,
+                "model": "tf32 tensor-pipe flops = 3 x (2 N_t N_s B) per evaluation (3xTF32 error-compensated products); peak = "
+                         "measured BURST bf16 dense / 2 (tf32 runs at half the bf16 rate)", "peak_source": cx.peaks["source"],
+                "traffic": None, "tiles": m.kernel.tc}
+    else:
+        peak = 148 * 64 * 2 * 1.965e9 / 1e12 if precision == "float64" else 148 * 128 * 2 * 1.965e9 / 1e12
+        roof = {"bound": "fp64_pipe" if precision == "float64" else "fma", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
+                "frac": tf / peak, "model": "2 N_t N_s B flops per evaluation (DMMA m8n8k4 f64); peak = nominal 148 SMs x 64 "
+                                            "fp64 FMA/clk x 1.965 GHz", "traffic": None}
+    t = time.perf_counter()
+    s.reset(params=params)
+    s.launch(sim_steps, dt, 1)
+    host = s.download()
+    e2e_s = cx.max_over_ranks(time.perf_counter() - t)
+    item = np.dtype(m.real).itemsize
+    rec = {"workload": workload, "program": how, "solver": "euler", "n_gpus": cx.world,
+           "sharding": "instances (no collective)" if cx.world > 1 else "none", "value": value, "unit": UNIT, "steps": K, "warmup": W,
+           "solver_steps_per_step": sim_steps, "ms_per_step": ms / K, "ms_per_solver_step": ms / (K * sim_steps),
+           "instances_per_gpu": batch, "dtype": "f32 (3xTF32 products, fp32 accumulate)" if precision == "float32" else "f64",
+           "roofline": roof,
+           "e2e": {"value": nodes * batch * cx.world * sim_steps / e2e_s, "unit": UNIT, "ms": e2e_s * 1e3,
+                   "h2d_bytes_per_step": int(params.nbytes + m.n_state * batch * item), "d2h_bytes_per_step": int(host.nbytes),
+                   "api": "NetworkSession.reset / launch / download (what NetworkSweep.run does per call)"},
+           "gpu_launches": K, "jit_s": jit_s}
+    s.free()
+    return rec
+
+
+def bench_c1(cx: Ctx):
+    """C1: Montbrio QIF single population, Euler dt=1e-3, T=100 (1e5 steps), one instance = one CUDA thread: a latency
+    anchor, not a roofline point (replicas only across GPUs: rank 0 runs it)."""
+    from pyrates_b200 import runtime as rt
+    from pyrates_b200.engine import InstanceModel
+    from pyrates_b200.program import Program
+    a = cx.a
+    prog = Program.load(os.path.join(ROOT, "tests", "golden", "qif.npz"))
+    T, dt = 100.0, 1e-3
+    steps = int(round(T / dt))
+    m = InstanceModel(prog, solver="euler")
+    m.module
+    s = m.session(1, steps)
+    K, W = a.steps, max(a.warmup, 3)
+    for _ in range(W):
+        s.reset()
+        s.launch(steps, dt, 1)
+    rt.synchronize()
+    ev = [(rt.Event(), rt.Event()) for _ in range(K)]
+    for k in range(K):
+        s.reset()
+        ev[k][0].record(s.stream)
+        s.launch(steps, dt, 1)
+        ev[k][1].record(s.stream)
+    rt.synchronize()
+    ms = sum(e0.elapsed_ms(e1) for e0, e1 in ev)
+    s.free()
+    e2e_t = []
+    for k in range(3):
+        t = time.perf_counter()
+        out, _ = m.run(T, dt, None)
+        e2e_t.append(time.perf_counter() - t)
+    e2e_s = float(np.mean(e2e_t[1:]))
+    rec = {"workload": "C1: Montbrio QIF mean-field single population (qif.yaml), Euler dt=1e-3 T=100, outputs r, v every step",
+           "solver": "euler", "n_gpus": 1, "sharding": "replicas only (one tiny ODE does not shard)", "value": steps * K / (ms * 1e-3),
+           "unit": UNIT, "steps": K, "warmup": W, "solver_steps_per_step": steps, "ms_per_step": ms / K,
+           "ns_per_solver_step": ms * 1e6 / (K * steps), "dtype": "f64",
+           "roofline": {"bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                        "model": "one thread, 1e5 dependent steps: bounded by the dependent-instruction latency of the Euler "
+                                 "update (fp64 FMA chain + one division), not by a throughput roofline"},
+           "e2e": {"value": steps / e2e_s, "unit": UNIT, "ms": e2e_s * 1e3, "h2d_bytes_per_step": int(prog.y0.nbytes),
+                   "d2h_bytes_per_step": int(out.nbytes), "api": "InstanceModel.run (what CudaBackend.run calls)"},
+           "gpu_launches": K}
+    if not a.no_cpu_baseline:
+        from oracle import numpy_oracle as orc
+        fx = orc.load_fixture(os.path.join(ROOT, "tests", "golden", "qif.npz"))
+        t = time.perf_counter()
+        orc.run_fixture(fx, solver="euler", T=20.0, dt=dt, dts=dt)
+        cpu_s = time.perf_counter() - t
+        rec["cpu_baseline"] = {"value": 20000 / cpu_s, "unit": UNIT, "kind": "port", "cores": 1,
+                               "sample": "T=20 (2e4 Euler steps) of the same program, NumPy oracle port (BaseBackend._solve_euler loop)"}
+    return rec
+
+
+def network_configs(cx: Ctx, want):
+    """Build and time the network configs named in `want`; every entry is independent (a failure is recorded, not fatal)."""
+    import bench_configs as bc
+    out = {}
+
+    def run(tag, fn):
+        if tag not in want:
+            return
+        t = time.perf_counter()
+        try:
+            out[tag] = fn()
+        except Exception as e:                                      # noqa: BLE001 — keep the headline line alive
+            out[tag] = {"error": f"{type(e).__name__}: {e}"[:500]}
+        out[tag]["bench_wall_s"] = time.perf_counter() - t
+        if cx.rank == 0:
+            print(f"[bench] {tag}: {json.dumps(out[tag])[:300]}", file=sys.stderr, flush=True)
+
+    a = cx.a
+    progs = {}
+
+    def prog_of(cfg, n, **kw):
+        key = (cfg, n, tuple(sorted(kw.items())))
+        if key not in progs:
+            progs[key] = bc.build_program(cfg, n, front_end=a.front_end, **kw)
+        return progs[key]
+
+    if cx.rank == 0:
+        run("c1", lambda: bench_c1(cx))
+    n3 = a.c3_size
+    c3_obs = lambda: list(range(n3))
+    run("c3", lambda: bench_network(
+        cx, "c3", *prog_of("c3", n3), solver="euler", nodes=n3, sim_steps=1000, e2e_steps=5000, obs=c3_obs(),
+        workload=f"C3: Wilson-Cowan N={n3}, dense random connectivity (benchmark_population_connectivity shape: diag 15, "
+                 f"N(0,1/sqrt(N)), seed 42), Euler dt=1e-3, all {n3} rates recorded every 10 steps; e2e horizon T=5 as the example",
+        cpu_steps=100))
+    run("c3_rk4", lambda: bench_network(
+        cx, "c3_rk4", *prog_of("c3", n3), solver="rk4", nodes=n3, sim_steps=250, e2e_steps=1000, obs=c3_obs(),
+        workload=f"C3 with RK4 (4 passes over W per solver step)", cpu_steps=25))
+    for tag, n4 in (("c4", a.c4_size), ("c4_2x2048", 2048)):
+        run(tag, lambda n4=n4: bench_network(
+            cx, tag, *prog_of("c4", n4), solver="heun", nodes=2 * n4, sim_steps=1000, e2e_steps=1000,
+            obs=list(range(n4)), resident="l2 (2 x %d MiB)" % (n4 * n4 * 8 // 2 ** 20),
+            workload=f"C4: QIF-SFA, two populations of {n4} units, p1->p2 gamma-kernel delay (4 cascade stages), p2->p1 3-step "
+                     f"delay ring buffer, reference-'heun' (aliased) dt=1e-3 T=1; W (2 x {n4}^2 fp64) is L2-resident by nature of "
+                     f"the workload (re-read every evaluation): no L2 flush", cpu_steps=200))
+    n5 = a.c5_size
+    for tag, solver, st in (("c5", "euler", 20), ("c5_rk4", "rk4", 8)):
+        if tag not in want:
+            continue
+        cpu_prog = None
+        if cx.rank == 0 and cx.world == 1 and not a.no_cpu_baseline:
+            cpu_prog = bc.make_c5(2048)
+        run(tag, lambda: bench_network(
+            cx, tag, *prog_of("c5", n5, device_w=True), solver=solver, nodes=n5, sim_steps=st, e2e_steps=st, obs=list(range(0, n5, 64)),
+            store_step=1,
+            workload=f"C5: Kuramoto N={n5}, dense all-to-all sin coupling W ~ U(0, 2/N) ({n5 * n5 * 8 / 2 ** 30:.0f} GiB fp64, generated "
+                     f"on the device), {solver} dt=1e-3, separable rewrite (two GEMVs over one pass of W per evaluation)",
+            cpu_prog=cpu_prog, cpu_steps=3, cpu_note="N=2048 pair-space wsum(sin) as the reference evaluates it (3 N x N temporaries; "
+                                                     "N=65536 needs 96 GiB of them: infeasible)"))
+    run("c5a", lambda: bench_network(
+        cx, "c5a", *prog_of("c5a", n5), solver="rk4", nodes=n5, sim_steps=1000, e2e_steps=1000, obs=list(range(0, n5, 64)),
+        workload=f"C5a: Kuramoto N={n5}, scalar all-to-all weight 1/N lowered to a global vsum (every rank reduces its complete "
+                 f"replica of the phase vector), RK4 dt=1e-3", resident="n/a (no matrix)", cpu_steps=200))
+    sw_prog = lambda: prog_of("c3", n3)
+    run("c3_sweep_f32", lambda: bench_network_sweep(
+        cx, "c3_sweep_f32", *sw_prog(), precision="float32", batch=a.sweep_batch, sweep=["r_ext", "k"], sim_steps=20, nodes=n3,
+        workload=f"grid_search over the C3 network (N={n3}), {a.sweep_batch} instances per GPU sharing W, Euler, float32 = the "
+                 f"reference's default precision: coupling as a tcgen05 kind::tf32 GEMM (3xTF32) with the rhs + solver update "
+                 f"fused into the TMEM epilogue"))
+    run("c3_sweep_f64", lambda: bench_network_sweep(
+        cx, "c3_sweep_f64", *sw_prog(), precision="float64", batch=a.sweep_batch // 2, sweep=["r_ext", "k"], sim_steps=10, nodes=n3,
+        workload=f"same grid_search in float64 (the parity precision), {a.sweep_batch // 2} instances per GPU: coupling as a DMMA "
+                 f"(mma.sync.m8n8k4.f64) GEMM"))
+    return out
+
+
+# ============================================================================= main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -132,10 +575,21 @@ def main():
     ap.add_argument("--strict-div", action="store_true",
                     help="exact kernels: IEEE divisions, library exp (default: reciprocal multiplies, table exp, rcp + cubic "
                          "step, folded constant chains — each <= 2 ulp, trajectories within 1e-15 of the exact kernel)")
+    ap.add_argument("--configs", default="all",
+                    help="comma list of extra records: c1,c3,c3_rk4,c4,c4_2x2048,c5,c5_rk4,c5a,c3_sweep_f32,c3_sweep_f64,"
+                         "strong,d2h,public_api ('all', 'none')")
+    ap.add_argument("--c3-size", type=int, default=8192)
+    ap.add_argument("--c4-size", type=int, default=1024)
+    ap.add_argument("--c5-size", type=int, default=65536)
+    ap.add_argument("--sweep-batch", type=int, default=1024)
+    ap.add_argument("--front-end", default="auto", choices=["auto", "reference", "resized"])
+    ap.add_argument("--ref-batch", type=int, default=256, help="--impl reference: grid points per host process")
+    ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: host processes (0 = all cores)")
     a = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ALL = ["c1", "c3", "c3_rk4", "c4", "c4_2x2048", "c5", "c5_rk4", "c5a", "c3_sweep_f32", "c3_sweep_f64", "strong", "d2h", "public_api"]
+    want = set(ALL) if a.configs == "all" else set(x for x in a.configs.split(",") if x and x != "none")
+    cx = Ctx(a)
+    rank, local_rank, world = cx.rank, cx.local_rank, cx.world
     W = max(a.warmup, 3) if a.impl == "ours" else a.warmup
 
     config = {"workload": "C2: Jansen-Rit 3-population circuit, RK4 dt=1e-4 T=%g, grid_search over %dx%d (C,u) grid per GPU, "
@@ -147,7 +601,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        val, sec, cb = cpu_reference(a.steps, a.warmup, a.cpu_sim_time)
+        val, sec, cb = reference_arm(a, config)
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
                           "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": cb,
@@ -158,37 +612,25 @@ def main():
     from pyrates_b200.program import Program
     from pyrates_b200.sweep import BatchedSweep
 
-    dist = None
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cx.dist = dist
     rt.set_device(local_rank)
     numa_node = None
     if world > 1:
         from pyrates_b200.distributed import bind_to_gpu_numa_node
         numa_node = bind_to_gpu_numa_node(local_rank)      # pinned result buffers next to this GPU's PCIe root
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        rt.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    barrier, max_over_ranks = cx.barrier, cx.max_over_ranks
 
     prog = Program.load(os.path.join(ROOT, "tests", "golden", "jrc.npz"))
     B = a.grid * a.grid
     t_jit = time.perf_counter()
     sw = BatchedSweep(prog, SWEEP, observers=[0], solver="rk4", T=a.sim_time, dt=1e-4, dts=1e-3, n_inst=B,
                       chunk_samples=a.chunk_samples, const_div_to_mul=not a.strict_div)
-    sw.model.module                      # JIT (NVRTC) happens here, outside every timed region
+    sw.model.compile(shared=world > 1)   # JIT (NVRTC) outside every timed region; one rank compiles, the others receive the cubin
     jit_s = time.perf_counter() - t_jit
     table = param_table(a.grid, a.grid, rank * B, (rank + 1) * B)     # weak scaling: each rank its own grid block
     sw.stage_params(table)
@@ -230,11 +672,33 @@ def main():
     e2e_val = NODES * B * world * n_steps * a.steps / e2e_s
     checksum = float(out[-1, 0, :8].sum())
 
+    # ---- what the box can move: every rank copies its result volume D2H (pinned, cuMemcpyDtoHAsync per chunk, no kernel)
+    d2h = None
+    if "d2h" in want:
+        nbytes, chunk = sw.d2h_bytes, sw._chunk_bytes
+        for rep in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            off = 0
+            while off < nbytes:
+                n = min(chunk, nbytes - off)
+                rt._check(rt.lib().prb_memcpy_d2h(sw.h_out.ptr + off, sw.d_chunks[(off // chunk) & 1].ptr, n, sw.copy.handle))
+                off += n
+            sw.copy.synchronize()
+            barrier()
+            d2h_s = max_over_ranks(time.perf_counter() - t0)
+        ceiling = nbytes * world / d2h_s / 1e9
+        used = sw.d2h_bytes * world * a.steps / e2e_s / 1e9
+        d2h = {"d2h_ceiling_gbs": ceiling, "d2h_gbs_in_e2e": used, "frac_of_ceiling": used / ceiling,
+               "ceiling_how": f"{world} rank(s) x {nbytes / 1e9:.2f} GB pinned cuMemcpyDtoHAsync in {chunk / 1e6:.0f} MB pieces, no kernel running, "
+                              f"wall clock max over ranks",
+               "e2e_floor_ms_from_d2h": nbytes * world / (ceiling * 1e9) * 1e3}
+
     # ---- the same sweep with the observer reduced on the device (grid_search(reduce=True)): host table in, per-instance
     # mean / var / min / max / last out.  Informational — the headline e2e above returns every trajectory like the reference.
     red = BatchedSweep(prog, SWEEP, observers=[0], solver="rk4", T=a.sim_time, dt=1e-4, dts=1e-3, n_inst=B,
                        const_div_to_mul=not a.strict_div, reduce=True)
-    red.model.module
+    red.model.compile(shared=world > 1)
     for _ in range(2):
         red.run(table)
     barrier()
@@ -248,50 +712,152 @@ def main():
                 "api": "pyrates_b200.sweep.BatchedSweep(reduce=True).run", "stats": ["mean", "var", "min", "max", "last"],
                 "mean_matches_full_run": bool(np.allclose(stats[0, 0, :64], out[:, 0, :64].mean(axis=0), rtol=1e-10, atol=0))}
     red.free()
+    info = sw.model.module.kernel_info("prb_integrate", sw.model.kernel.block)
+    block = sw.model.kernel.block
+    h2d_bytes, d2h_bytes = sw.h2d_bytes, sw.d2h_bytes
+    sw.free()
+
+    # ---- strong scaling: BASELINE.json configs[1] as written — 2^20 parameter sets in total, sharded across the GPUs
+    strong = None
+    if "strong" in want and world > 1:
+        Bs_lo, Bs_hi = _bounds(B, world, rank)
+        Bs = Bs_hi - Bs_lo
+        ss = BatchedSweep(prog, SWEEP, observers=[0], solver="rk4", T=a.sim_time, dt=1e-4, dts=1e-3, n_inst=Bs,
+                          chunk_samples=a.chunk_samples, const_div_to_mul=not a.strict_div)
+        ss.model.compile(shared=True)
+        tb = param_table(a.grid, a.grid, Bs_lo, Bs_hi)
+        ss.stage_params(tb)
+        for _ in range(W):
+            ss.upload()
+            ss.integrate(read_back=False)
+        barrier()
+        ev = [(rt.Event(), rt.Event()) for _ in range(a.steps)]
+        for k in range(a.steps):
+            ss.upload()
+            ev[k][0].record(ss.compute)
+            ss.integrate(read_back=False)
+            ev[k][1].record(ss.compute)
+        barrier()
+        s_ms = max_over_ranks(sum(e0.elapsed_ms(e1) for e0, e1 in ev))
+        for _ in range(2):
+            ss.run(tb)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(a.steps):
+            ss.run(tb)
+        barrier()
+        s_e2e = max_over_ranks(time.perf_counter() - t0)
+        ctas = -(-Bs // block)
+        strong = {"scaling": "strong", "instances_total": B, "instances_per_gpu": Bs, "value": NODES * B * n_steps * a.steps / (s_ms * 1e-3),
+                  "unit": UNIT, "ms_per_step": s_ms / a.steps,
+                  "e2e": {"value": NODES * B * n_steps * a.steps / s_e2e, "unit": UNIT, "ms_per_step": s_e2e * 1e3 / a.steps,
+                          "h2d_bytes_per_step": ss.h2d_bytes, "d2h_bytes_per_step": ss.d2h_bytes},
+                  "launch_shape": {"ctas_per_gpu": ctas, "block": block, "resident_ctas_per_gpu": 148 * info["max_blocks_per_sm"],
+                                   "waves": ctas / (148 * info["max_blocks_per_sm"])}}
+        ss.free()
+
+    extra = network_configs(cx, want) if (want - {"strong", "d2h", "public_api"}) else {}
+
+    public = None
+    if "public_api" in want and world == 1:
+        try:
+            public = bench_public_api(a)
+        except Exception as e:                                      # noqa: BLE001
+            public = {"error": f"{type(e).__name__}: {e}"[:500]}
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        if cx.dist is not None:
+            cx.dist.destroy_process_group()
         return 0
 
-    hbm, which = peaks()
+    hbm, which = cx.peaks["hbm"], cx.peaks["source"]
     inst_steps_per_launch = B * n_steps * a.steps / launches        # launches of the device-resident (value) timing
     launch_s = kernel_ms * 1e-3 / launches
-    achieved = B_ALG * inst_steps_per_launch / launch_s / 1e9
-    info = sw.model.module.kernel_info("prb_integrate", sw.model.kernel.block)
+    fast = not a.strict_div
+    pipe_frac = FP64_INSTR[fast] * 2.0 * (value / NODES / world / 32) / (148 * 4 * 1.965e9)
+    hbm_model = B_ALG * inst_steps_per_launch / launch_s / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W,
         "ms_per_step": kernel_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config,
         "instance_steps_per_s": value / NODES,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": sw.h2d_bytes, "d2h_bytes_per_step": sw.d2h_bytes,
-                "ms_per_step": e2e_s * 1e3 / a.steps, "api": "pyrates_b200.sweep.BatchedSweep.run", "checksum": checksum},
+        "e2e": dict({"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                     "ms_per_step": e2e_s * 1e3 / a.steps, "api": "pyrates_b200.sweep.BatchedSweep.run", "checksum": checksum},
+                    **(d2h or {})),
         "e2e_reduced": red_info,
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+        "roofline": {"bound": "fp64_pipe", "achieved": FP64_INSTR[fast] * (value / NODES / world / 32) / 1e9,
+                     "peak": 148 * 4 * 1.965e9 / 2.0 / 1e9, "unit": "G warp-instr/s", "frac": pipe_frac,
+                     "model": "fp64-pipe warp instructions (DFMA/DMUL/DADD/DSETP) inside the SASS time loop per instance-step "
+                              "(cuobjdump, pinned by tests/test_compile_inst.py) x instance-steps/s / 32 lanes; peak = 148 SMs x 4 "
+                              "SMSPs x 1.965 GHz / 2 issue cycles per fp64 warp instruction (16 lanes per SMSP)",
+                     "instr_per_instance_step": FP64_INSTR[fast], "kernel": "prb_integrate (fused JRC rhs + RK4 + observer store)",
+                     "launch_ms": launch_s * 1e3,
                      "traffic": (NCU_TRAFFIC.get(int(inst_steps_per_launch)) if a.grid == 1024 else None),
-                     "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_c2_reassoc_prb_integrate_ncu_full.txt)",
-                     "algorithmic_bytes_per_launch": B_ALG * inst_steps_per_launch, "peak_source": which, "kernel": "prb_integrate (fused JRC rhs + RK4 + observer store)",
-                     "algorithmic_bytes_per_instance_step": B_ALG, "launch_ms": launch_s * 1e3,
-                     "note": "state/stages are register-resident across the launch: real DRAM traffic is only the "
-                             "observer store, so the SURVEY 8d round-trip model can exceed 1.0; the true bound is the FP64 pipe",
-                     "fp64_pipe": {"instr_per_instance_step": FP64_INSTR[not a.strict_div],
-                                   "frac": FP64_INSTR[not a.strict_div] * 2.0 * (value / NODES / world / 32) / (148 * 4 * 1.965e9),
-                                   "model": "fp64-pipe warp instructions (DFMA/DMUL/DADD/DSETP) in the SASS time loop x 2 issue "
-                                            "cycles (16 lanes/SMSP) / (148 SMs x 4 SMSPs x 1.965 GHz)"}},
+                     "traffic_unit": "bytes per launch (ncu dram read+write)",
+                     "hbm_round_trip_model": {"achieved": hbm_model, "peak": hbm, "unit": "GB/s", "frac": hbm_model / hbm,
+                                              "algorithmic_bytes_per_instance_step": B_ALG,
+                                              "algorithmic_bytes_per_launch": B_ALG * inst_steps_per_launch, "peak_source": which,
+                                              "note": "SURVEY 8d round-trip model (state + parameters re-read every step); the "
+                                                      "state is register-resident for the whole launch, so this is NOT a DRAM "
+                                                      "utilisation and may exceed 1 — the kernel is bound by the FP64 pipe"}},
         "kernel": {"regs": info["regs"], "local_bytes": info["local_bytes"], "blocks_per_sm": info["max_blocks_per_sm"],
-                   "block": sw.model.kernel.block, "const_div_to_mul": not a.strict_div, "fast_math": not a.strict_div},
+                   "block": block, "const_div_to_mul": fast, "fast_math": fast},
         "jit_s": jit_s, "numa_node_rank0": numa_node,
         "clocks": clocks.stop(wall0, wall1) if clocks else None,
     }
+    if strong is not None:
+        line["strong_scaling"] = strong
+    if extra:
+        line["configs"] = extra
+    if public is not None:
+        line["public_api"] = public
     if world == 1 and not a.no_cpu_baseline:
-        _, _, cb = cpu_reference(1, 0, a.cpu_sim_time)
+        _, _, cb = cpu_port_c2(1, 0, a.cpu_sim_time)
         line["cpu_baseline"] = cb
     print(json.dumps(line))
-    sw.free()
-    if dist is not None:
-        dist.destroy_process_group()
+    if cx.dist is not None:
+        cx.dist.destroy_process_group()
     return 0
+
+
+def bench_public_api(a):
+    """pyrates.grid_search(JRC yaml, 1024 x 1024 grid, backend='cuda', solver='rk4', float_precision='float64',
+    as_arrays=True) through the reference front end (baseline/_ref): the call a PyRates user makes (utility.py:189-275)."""
+    import bench_configs as bc
+    pyrates = bc.import_pyrates()
+    if pyrates is None:
+        return {"unavailable": "PyRates front end not importable (baseline/_ref missing)"}
+    side = a.grid
+    cwd = os.getcwd()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    os.chdir(os.path.join(ROOT, "gpurun_out"))
+    runs = []
+    try:
+        for rep in range(2):
+            tm = {}
+            t = time.perf_counter()
+            grid, pmap = jrc_grid(side)                       # building the 2^20-row parameter frame is part of the user's call
+            tm["grid_frame_s"] = time.perf_counter() - t
+            res, pg = pyrates.grid_search(JRC_YAML, grid, pmap, step_size=1e-4, simulation_time=a.sim_time, sampling_step_size=1e-3,
+                                          outputs={"v": "pc/rpo_e_in/v"}, solver="rk4", backend="cuda", verbose=False,
+                                          float_precision="float64", as_arrays=True, timings=tm, chunk_samples=a.chunk_samples)
+            tm["total_s"] = time.perf_counter() - t
+            tm["shape"] = list(res.shape)
+            tm["checksum"] = float(res[-1, 0, :8].sum())
+            runs.append(tm)
+            del res
+    finally:
+        os.chdir(cwd)
+    n_steps = int(round(a.sim_time / 1e-4))
+    best = runs[-1]
+    return {"api": "pyrates.grid_search(JRC, linearize_grid({C: 1024, u: 1024}, permute=True) + tied weights, backend='cuda', "
+                   "solver='rk4', float_precision='float64', as_arrays=True)", "instances": side * side,
+            "value": NODES * side * side * n_steps / best["total_s"], "unit": UNIT, "total_s": best["total_s"],
+            "probe_build_s": best["probe_build_s"], "jit_s": best["jit_s"], "run_s": best["run_s"], "frame_s": best["frame_s"],
+            "other_s": best["total_s"] - sum(best[k] for k in ("probe_build_s", "jit_s", "run_s", "frame_s")),
+            "first_call": runs[0], "note": "second call reported (cubin + template caches warm); first_call shows the cold one. "
+                                           "run_s includes pinned-buffer allocation (8.4 GB) + H2D + kernels + streamed D2H"}
 
 
 if __name__ == "__main__":

@@ -45,7 +45,11 @@ def resize_program(prog: Program, n_old: int, n_new: int, fill) -> Program:
             shape = (v.size * f,)
         else:
             shape = tuple(n_new if d == n_old else d for d in v.shape)
-        args.append(Arg(a.name, a.kind, np.asarray(fill(a.name, shape, v), dtype=v.dtype).reshape(shape), a.label))
+        new = fill(a.name, shape, v)
+        if hasattr(new, "fill") and hasattr(new, "host"):           # device-generated constant: no host array
+            args.append(Arg(a.name, a.kind, new, a.label))
+        else:
+            args.append(Arg(a.name, a.kind, np.asarray(new, dtype=v.dtype).reshape(shape), a.label))
     return Program(args, stmts, {}, prog.float_precision, prog.func_name)
 
 
@@ -94,12 +98,15 @@ def make_c4(n: int) -> Program:
     return resize_program(base, 8, n, fill)
 
 
-def make_c5(n: int) -> Program:
-    """Kuramoto, N phase oscillators, dense W ~ U(0, 2/N) with sin(theta_j - theta_i) pair coupling."""
+def make_c5(n: int, weight=None) -> Program:
+    """Kuramoto, N phase oscillators, dense W ~ U(0, 2/N) with sin(theta_j - theta_i) pair coupling.
+    ``weight``: a replacement for the matrix (e.g. a device-generated constant, pyrates_b200.devgen.DeviceUniform)."""
     base = Program.load(os.path.join(ROOT, "tests", "golden", "kuramoto_n8.npz"))
 
     def fill(name, shape, old):
         if name == "weight":
+            if weight is not None:
+                return weight
             return np.random.default_rng(2).uniform(0.0, 2.0 / n, shape)
         if name == "y":
             return np.random.default_rng(1).uniform(0, 2 * np.pi, shape)
@@ -107,6 +114,127 @@ def make_c5(n: int) -> Program:
             return np.random.default_rng(1).normal(10, 1, shape)
         return _tile(old, shape)
     return resize_program(base, 8, n, fill)
+
+
+# ----------------------------------------------------------------------------- the configs through the REAL front end
+def import_pyrates():
+    """An importable PyRates for the front end (templates -> IR -> compute graph), with backend='cuda' registered.
+    On the GPU box that is the unmodified reference installed under baseline/_ref (plus the `ruamel.yaml` stand-in of
+    baseline/shims: the image lacks that dependency of the reference).  Returns the module or None."""
+    import importlib
+    try:
+        importlib.import_module("pyrates")
+    except Exception:
+        for sub in ("shims", "_ref"):
+            d = os.path.join(ROOT, "baseline", sub)
+            if os.path.isdir(d) and d not in sys.path:
+                sys.path.insert(0, d)
+        try:
+            importlib.import_module("pyrates")
+        except Exception:
+            return None
+    import pyrates_b200.register as reg
+    if not reg.register():
+        return None
+    return sys.modules["pyrates"]
+
+
+def _capture(circuit, dt: float, solver: str = "euler", precision: str = "float64") -> Program:
+    """CircuitTemplate -> Program through the reference's own pipeline driving CudaBackend (the drop-in boundary)."""
+    from pyrates.ir.node import clear_ir_caches
+    func, args, _, _ = circuit.get_run_func("vector_field", step_size=dt, backend="cuda", solver=solver,
+                                            float_precision=precision, verbose=False, clear=False)
+    prog = func.program(args)
+    try:
+        circuit.clear()
+    except Exception:
+        pass
+    clear_ir_caches()
+    return prog
+
+
+def circuit_c3(n: int):
+    """WC population, dense connectivity: examples/benchmark_population_connectivity.py:31-39,86-106 (W diag 15, off-diagonal
+    N(0, 1/sqrt(N)), seed 42); random initial rates / thresholds so that the trajectory leaves the template's fixed point."""
+    from pyrates import CircuitTemplate, NodeTemplate
+    from pyrates.frontend.template.population import Connectivity, PopulationTemplate
+    rng = np.random.default_rng(42)
+    W = rng.normal(0.0, 1.0 / np.sqrt(n), (n, n))
+    np.fill_diagonal(W, 15.0)
+    exc = NodeTemplate.from_yaml("model_templates.neural_mass_models.wilsoncowan.exc_pop")
+    pop = PopulationTemplate(name="e", node=exc, n=n, params={"rate_op/r": list(rng.uniform(0.05, 0.6, n)),
+                                                              "se_op/theta": list(rng.normal(2.0, 0.5, n))})
+    return CircuitTemplate(name=f"wc_n{n}", populations={"e": pop},
+                           connections=[Connectivity(source="e/rate_op/r", target="e/se_op/r_in", weights=W)])
+
+
+def circuit_c4(n: int):
+    """QIF-SFA, two populations of n units: p1 -> p2 gamma-kernel delay (mean 4 ms, spread 2 ms: cascade
+    of 4 stages), p2 -> p1 ring-buffer delay of 3 steps; eta ~ N(-5, 1), W ~ N(0, 1/sqrt(n)), seed 42."""
+    from pyrates import CircuitTemplate, NodeTemplate
+    from pyrates.frontend.template.population import Connectivity, PopulationTemplate
+    rng = np.random.default_rng(42)
+    eta = rng.normal(-5.0, 1.0, n)
+    W = rng.normal(0.0, 1.0 / np.sqrt(n), (n, n))
+    W2 = rng.normal(0.0, 1.0 / np.sqrt(n), (n, n))
+    qs = NodeTemplate.from_yaml("model_templates.neural_mass_models.qif.qif_sfa_pop")
+    p1 = PopulationTemplate(name="p1", node=qs, n=n, params={"qif_sfa_op/eta": list(eta)})
+    p2 = PopulationTemplate(name="p2", node=qs, n=n, params={"qif_sfa_op/eta": list(eta[::-1])})
+    c12 = Connectivity(source="p1/qif_sfa_op/r", target="p2/qif_sfa_op/r_in", weights=W, delays=4e-3, spread=2e-3)
+    c21 = Connectivity(source="p2/qif_sfa_op/r", target="p1/qif_sfa_op/r_in", weights=W2, delays=3e-3)
+    return CircuitTemplate(name="qsfa_both", populations={"p1": p1, "p2": p2}, connections=[c12, c21])
+
+
+def circuit_c5(n: int, dense: bool = True, W=None):
+    """Kuramoto phase oscillators with sin(theta_j - theta_i) coupling (model_templates/oscillators/kuramoto.yaml:20-27,75-78):
+    dense W ~ U(0, 2/N) (C5b) or the scalar all-to-all weight 1/N (C5a, lowered to a global `vsum`)."""
+    from pyrates import CircuitTemplate, EdgeTemplate, NodeTemplate
+    from pyrates.frontend.template.population import Connectivity, PopulationTemplate
+    phase_pop = NodeTemplate.from_yaml("model_templates.oscillators.kuramoto.phase_pop")
+    sin_edge = EdgeTemplate.from_yaml("model_templates.oscillators.kuramoto.sin_edge")
+    theta = np.random.default_rng(1).uniform(0, 2 * np.pi, n)
+    omega = np.random.default_rng(1).normal(10, 1, n)
+    pop = PopulationTemplate(name="e", node=phase_pop, n=n, params={"phase_op/theta": list(theta), "phase_op/omega": list(omega)})
+    if W is None:
+        W = np.random.default_rng(2).uniform(0, 2.0 / n, (n, n)) if dense else 1.0 / n
+    conn = Connectivity(source="e/phase_op/theta", target="e/phase_op/s_in", weights=W, edge=sin_edge,
+                        edge_var_map={"theta_s": "source", "theta_t": "e/phase_op/theta"})
+    return CircuitTemplate(name="kuramoto", populations={"e": pop}, connections=[conn])
+
+
+def build_program(config: str, n: int, *, dt: float = 1e-3, front_end: str = "auto", device_w: bool = False):
+    """Program of a BASELINE.json network config at size n -> (Program, how).  ``front_end``: 'reference' builds the circuit
+    with PopulationTemplate + Connectivity and captures the program the reference's compute graph hands to CudaBackend;
+    'resized' re-sizes the committed N = 8 fixture of the same circuit (no PyRates needed); 'auto' prefers the former.
+    ``device_w`` (c5): the dense weight matrix becomes a device-generated U(0, 2/N) constant (devgen.DeviceUniform) — the
+    32 GiB matrix of N = 65536 never exists in host memory; the circuit is built at N = 8 and re-sized."""
+    if config == "c5" and device_w:
+        from pyrates_b200.devgen import DeviceUniform
+        prog = make_c5(n, weight=DeviceUniform((n, n), 2.0 / n, 2))
+        return prog, "N=8 program of the reference re-sized, W generated on the device (splitmix64 U(0, 2/N))"
+    if front_end in ("auto", "reference") and import_pyrates() is not None:
+        circuit = {"c3": circuit_c3, "c4": circuit_c4, "c5": circuit_c5, "c5a": lambda k: circuit_c5(k, dense=False)}[config](n)
+        return _capture(circuit, dt), "reference front end (PopulationTemplate + Connectivity -> ComputeGraph -> CudaBackend)"
+    if front_end == "reference":
+        raise RuntimeError("PyRates is not importable (expected the reference under baseline/_ref)")
+    prog = {"c3": make_c3, "c4": make_c4, "c5": make_c5, "c5a": make_c5a}[config](n)
+    return prog, "N=8 program of the reference re-sized (tests/golden fixtures)"
+
+
+def make_c5a(n: int) -> Program:
+    """Kuramoto with the scalar all-to-all weight 1/N: the coupling is a global `vsum`."""
+    base = Program.load(os.path.join(ROOT, "tests", "golden", "kuramoto_scalar_n128.npz"))
+
+    def fill(name, shape, old):
+        if name == "y":
+            return np.random.default_rng(1).uniform(0, 2 * np.pi, shape)
+        if name == "omega":
+            return np.random.default_rng(1).normal(10, 1, shape)
+        old = np.asarray(old)
+        if old.ndim == 0 and np.isclose(float(old), 1.0 / 128):
+            return np.asarray(1.0 / n)
+        return _tile(old, shape)
+    return resize_program(base, 128, n, fill)
 
 
 def to_float32(prog: Program) -> Program:

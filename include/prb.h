@@ -139,6 +139,7 @@ typedef struct prb_module prb_module;
 int         prb_abi_version(void);
 const char* prb_last_error(void);             /* thread-local message of the last failing call */
 int64_t     prb_launch_count(void);           /* kernels launched by this library since load */
+int         prb_nvrtc_version(int* major, int* minor);   /* toolkit that prb_compile uses (part of the callers' cubin cache key) */
 
 /* --- device ------------------------------------------------------------------------------------- */
 int prb_device_count(int* count);

@@ -5,7 +5,7 @@ The reference lives read-only at /root/reference in the build container and is N
 present on the GPU box; everything that runs there uses committed fixtures instead.
 
 Applies the two harness shims documented in SURVEY.md (headline 8):
-  * ``ruamel.yaml`` stand-in (oracle/shims) when ruamel is not installed,
+  * ``ruamel.yaml`` stand-in (baseline/shims) when ruamel is not installed,
   * networkx >= 3.6 ``Graph.__new__(backend=...)`` collision with
     ``ComputeGraph.__init__(self, backend: str, ...)`` (pyrates/backend/computegraph.py:223-228).
 """
@@ -32,7 +32,7 @@ def import_reference():
     try:
         importlib.import_module("ruamel.yaml")
     except ImportError:
-        shim = os.path.join(_HERE, "shims")
+        shim = os.path.join(os.path.dirname(_HERE), "baseline", "shims")
         if shim not in sys.path:
             sys.path.insert(0, shim)
     if root not in sys.path:

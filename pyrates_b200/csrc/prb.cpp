@@ -165,6 +165,10 @@ extern "C" {
 int prb_abi_version(void) { return PRB_ABI_VERSION; }
 const char* prb_last_error(void) { return g_err.c_str(); }
 int64_t prb_launch_count(void) { return g_launches.load(); }
+int prb_nvrtc_version(int* major, int* minor) {
+    if (!major || !minor) return fail(PRB_ERR_INVALID, "NULL argument");
+    return nvrtcVersion(major, minor) == NVRTC_SUCCESS ? PRB_OK : fail(PRB_ERR_COMPILE, "nvrtcVersion failed");
+}
 
 // ---------------------------------------------------------------- device
 int prb_device_count(int* count) {

@@ -41,13 +41,15 @@ struct PrbNet {
     long long oK[7], oSA, oSB;   // stage derivatives K0..K6 and the two alternating stage-input vectors inside `work`
 #endif
     int head[PRB_NRINGS > 0 ? PRB_NRINGS : 1];
-    unsigned long long* bar;     // [0] local arrivals, [1] release epoch, [2] error flag, [8+q] epoch of rank q
+    unsigned long long* bar;     // [0] local arrivals, [2] error flag
     unsigned long long bar_target;
     unsigned long long epoch;
 #if PRB_WORLD > 1
-    real* peer_work[PRB_WORLD];
-    real* peer_rings[PRB_WORLD];
+    uint4* ll_peer[PRB_WORLD];   // receive mirrors of all ranks (IPC-mapped; [PRB_RANK] = this rank's own)
+    uint4* ll_mine;
     unsigned long long* peer_sync[PRB_WORLD];
+    long long ll_par;            // slot offset of the parity half that the NEXT barrier consumes
+    unsigned int ll_tag;         // tag of the packets sent before the next barrier (epoch + 1 with the top bit set: never 0)
 #endif
     long long gtid, gsize, gwarp, nwarps;
     int lane;
@@ -56,40 +58,70 @@ struct PrbNet {
 #endif
 };
 
-// ---- shared stores: values other CTAs (and, with PRB_WORLD > 1, other GPUs) will read.  In a multi-GPU run every
-// rank owns a contiguous row shard; the owner writes its elements into the replica of every peer over NVLink
-// (P2P stores on IPC-mapped pointers), so the all-gather of the stage vector is fused into the producing kernel.
+// ---- shared stores: values other CTAs (and, with PRB_WORLD > 1, other GPUs) will read.
+// Multi-GPU (one process per GPU, rows of every index space sharded): every rank keeps a complete replica of the work /
+// ring arrays.  The owner of an element stores it locally and sends it to every peer as ONE self-validating 16-byte
+// packet {lo32, tag, hi32, tag} (the LL protocol: each 8-byte half carries its own flag, and 8-byte stores are single
+// transactions on NVLink) into the peer's receive MIRROR — fire-and-forget st.volatile over the IPC mapping, no
+// system-scope fence anywhere.  Before a grid barrier the receiving grid polls the mirror slots of the elements its peers
+// own (the emitter knows which regions every phase stores: prb_ll_unpack*), writes the values into its local replica and
+// then runs the ordinary single-GPU barrier: the data carries the flag, so "the peers have arrived" and "their values are
+// here" are the same event.  Mirrors are double-buffered by barrier parity; a per-barrier heartbeat packet from every
+// rank keeps all ranks within one barrier of each other, which is what makes two parities enough (a sender can only
+// reach the stores of barrier k + 2 after it consumed packets that its peers sent after finishing barrier k).
+// r01 (scalar 8-byte replica stores + a system-scope fence + flag round): ~15 us per exchange at 8 GPUs.
+#if PRB_WORLD > 1
+#define PRB_LL_SLOTS (PRB_LL_WORK + PRB_LL_RING + 32LL)          // work | rings | heartbeats (one slot per rank)
+__device__ __forceinline__ void prb_ll_send(const PrbNet& C, const long long slot, const real v) {
+    uint4 pk;
+    if (sizeof(real) == 8) {
+        const unsigned long long u = (unsigned long long)__double_as_longlong((double)v);
+        pk.x = (unsigned int)u; pk.z = (unsigned int)(u >> 32);
+    } else {
+        pk.x = __float_as_uint((float)v); pk.z = 0u;
+    }
+    pk.y = C.ll_tag; pk.w = C.ll_tag;
+#pragma unroll
+    for (int p = 0; p < PRB_WORLD; ++p)
+        if (p != PRB_RANK)
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};"
+                         :: "l"(C.ll_peer[p] + C.ll_par + slot), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+}
+#endif
 __device__ __forceinline__ void prb_st_work(const PrbNet& C, const long long off, const real v) {
     C.work[off] = v;
 #if PRB_WORLD > 1
-#pragma unroll
-    for (int p = 0; p < PRB_WORLD; ++p)
-        if (p != PRB_RANK) C.peer_work[p][off] = v;
+    prb_ll_send(C, off, v);
 #endif
 }
 __device__ __forceinline__ void prb_st_ring(const PrbNet& C, const long long off, const real v) {
     C.rings[off] = v;
 #if PRB_WORLD > 1
-#pragma unroll
-    for (int p = 0; p < PRB_WORLD; ++p)
-        if (p != PRB_RANK) C.peer_rings[p][off] = v;
+    prb_ll_send(C, PRB_LL_WORK + off, v);
 #endif
 }
 
-// ---- barriers.  Single GPU: monotonic counter, one arrival per CTA (host zeroes the words before launch).
-// Multi GPU: local arrival counter + one epoch flag per rank pushed to every peer by the last local arriver
-// (measured alternatives: CTA-0 relay 3 hops, and 148 remote atomics per rank — both ~10 us).  Spins are bounded (~4e9 cycles): on timeout the error word is set and every
-// later barrier falls through, so a lost peer can never hang the GPU.
-#define PRB_SPIN_LIMIT 4000000000LL
+// ---- barriers.  Monotonic counter, one arrival per CTA (host zeroes the words before launch).  Spins are bounded: on
+// timeout the error word is set (and pushed to the peers) and every later wait falls through, so a lost peer can never
+// hang the GPU.
+#define PRB_SPIN_LIMIT 20000000000LL
 
 template <bool SYS>
 __device__ __forceinline__ unsigned long long prb_ld_acquire(const unsigned long long* p) {
     unsigned long long v;
-    // relaxed polling loads; the fence that follows every barrier wait supplies the acquire ordering (an acquire
-    // load / release store per iteration or per peer costs a full fence each: measured 3x slower at 8 GPUs)
+    // relaxed polling loads; the fence that follows every barrier wait supplies the acquire ordering
     if (SYS) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     else     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+
+__device__ __forceinline__ void prb_raise_timeout(PrbNet& C) {
+    atomicExch(C.bar + 2, 1ULL);
+#if PRB_WORLD > 1
+#pragma unroll
+    for (int p = 0; p < PRB_WORLD; ++p)
+        if (p != PRB_RANK) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(C.peer_sync[p] + 2), "l"(1ULL) : "memory");
+#endif
 }
 
 template <bool SYS>
@@ -99,80 +131,77 @@ __device__ __forceinline__ bool prb_spin_until(PrbNet& C, const unsigned long lo
     while (prb_ld_acquire<SYS>(p) < target) {
         if ((++it & 1023u) == 0) {
             if (prb_ld_acquire<false>(C.bar + 2) != 0ULL) return false;
-            if (clock64() - t0 > PRB_SPIN_LIMIT) { atomicExch(C.bar + 2, 1ULL); return false; }
+            if (clock64() - t0 > PRB_SPIN_LIMIT) { prb_raise_timeout(C); return false; }
         }
     }
     return true;
 }
 
-__device__ __forceinline__ void prb_grid_barrier(PrbNet& C) {
-    __syncthreads();
-#if PRB_WORLD > 1 && PRB_BARRIER_PARALLEL
-    // two-level multi-GPU barrier: local arrivals on a gpu-scope counter; the LAST local arriver (it has observed every
-    // other CTA's fenced stores) publishes this rank's epoch to every peer with one store over NVLink; every CTA then
-    // waits for the local count and for the epoch flags of all peers.  Warp 0 waits in ONE converged polling loop: lane 0
-    // on the local counter, lane 1 + q on peer q's flag.  Opt-in (PRB_BARRIER_PARALLEL=1): measured against the serial
-    // variant below on 8 GPUs it is within run-to-run noise, and ~1 us slower with a single peer.
-    if (threadIdx.x < 32) {
-        C.bar_target += gridDim.x;
-        C.epoch += 1ULL;
-        const int lane = threadIdx.x;
-        if (lane == 0) {
-            __threadfence_system();
-            const unsigned long long old = atomicAdd(C.bar, 1ULL);
-            if (old + 1ULL == C.bar_target) {
-                __threadfence_system();
-#pragma unroll
-                for (int p = 0; p < PRB_WORLD; ++p)
-                    if (p != PRB_RANK)
-                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(C.peer_sync[p] + 8 + PRB_RANK), "l"(C.epoch) : "memory");
-            }
+#if PRB_WORLD > 1
+// wait for the packet in mirror slot `slot` of the current parity and return its payload
+__device__ __forceinline__ real prb_ll_recv(PrbNet& C, const long long slot) {
+    const uint4* p = C.ll_mine + C.ll_par + slot;
+    uint4 pk;
+    const long long t0 = clock64();
+    unsigned int it = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "l"(p) : "memory");
+        if (pk.y == C.ll_tag && pk.w == C.ll_tag) break;
+        if ((++it & 1023u) == 0) {
+            if (prb_ld_acquire<false>(C.bar + 2) != 0ULL) break;
+            if (clock64() - t0 > PRB_SPIN_LIMIT) { prb_raise_timeout(C); break; }
         }
-        __syncwarp();
-        const bool active = lane == 0 || (lane <= PRB_WORLD && lane - 1 != PRB_RANK);
-        const unsigned long long* flag = lane == 0 ? C.bar : C.bar + 8 + (active ? lane - 1 : 0);
-        const unsigned long long target = lane == 0 ? C.bar_target : C.epoch;
-        const long long t0 = clock64();
-        unsigned int it = 0;
-        for (;;) {
-            const bool done = !active || prb_ld_acquire<true>(flag) >= target;
-            if (__all_sync(0xffffffffu, done)) break;
-            if ((++it & 1023u) == 0) {
-                bool stop = prb_ld_acquire<false>(C.bar + 2) != 0ULL;
-                if (!stop && clock64() - t0 > PRB_SPIN_LIMIT) { atomicExch(C.bar + 2, 1ULL); stop = true; }
-                if (__any_sync(0xffffffffu, stop)) break;
-            }
-        }
-        __threadfence_system();
     }
-#else
+    if (sizeof(real) == 8) return (real)__longlong_as_double((long long)(((unsigned long long)pk.z << 32) | (unsigned long long)pk.x));
+    return (real)__uint_as_float(pk.x);
+}
+// elements [0, n) of a region at `off`, this rank owns [lo, hi): fetch everything else from the mirror into the replica
+__device__ __forceinline__ void prb_ll_unpack(PrbNet& C, const long long off, const long long n, const long long lo, const long long hi) {
+    const long long own = hi - lo;
+    for (long long q = C.gtid; q < n - own; q += C.gsize) {
+        const long long e = off + (q < lo ? q : q + own);
+        C.work[e] = prb_ll_recv(C, e);
+    }
+}
+__device__ __forceinline__ void prb_ll_unpack_ring(PrbNet& C, const long long off, const long long n, const long long lo, const long long hi) {
+    const long long own = hi - lo;
+    for (long long q = C.gtid; q < n - own; q += C.gsize) {
+        const long long e = off + (q < lo ? q : q + own);
+        C.rings[e] = prb_ll_recv(C, PRB_LL_WORK + e);
+    }
+}
+// scatter stores arr[idx[i]] = v_i, i sharded like every index space: the (constant) index array names the slots
+__device__ __forceinline__ void prb_ll_unpack_scatter(PrbNet& C, const long long off, const int* __restrict__ idx, const long long nb,
+                                                      const long long n, const long long lo, const long long hi) {
+    const long long own = hi - lo;
+    for (long long q = C.gtid; q < (n - own) * nb; q += C.gsize) {
+        const long long r = q / nb, b = q - r * nb;
+        const long long i = r < lo ? r : r + own;
+        const long long e = (off + (long long)__ldg(idx + i)) * nb + b;
+        C.work[e] = prb_ll_recv(C, e);
+    }
+}
+#endif
+
+__device__ __forceinline__ void prb_grid_barrier(PrbNet& C) {
+#if PRB_WORLD > 1
+    // heartbeat: one packet per rank and barrier; consuming the peers' heartbeats keeps the ranks in lockstep even at a
+    // barrier whose data regions happen to involve only some of them
+    if (C.gtid == 0) prb_ll_send(C, PRB_LL_WORK + PRB_LL_RING + PRB_RANK, (real)0);
+    if (C.gtid >= 32 && C.gtid < 32 + PRB_WORLD && C.gtid - 32 != PRB_RANK) (void)prb_ll_recv(C, PRB_LL_WORK + PRB_LL_RING + (C.gtid - 32));
+#endif
+    __syncthreads();
     if (threadIdx.x == 0) {
         C.bar_target += gridDim.x;
-        C.epoch += 1ULL;
-#if PRB_WORLD > 1
-        // serial variant: thread 0 arrives, the last local arriver publishes the epoch, then thread 0 waits for the local
-        // count and for the peers' flags one after the other
-        __threadfence_system();
-        const unsigned long long old = atomicAdd(C.bar, 1ULL);
-        if (old + 1ULL == C.bar_target) {
-            __threadfence_system();
-#pragma unroll
-            for (int p = 0; p < PRB_WORLD; ++p)
-                if (p != PRB_RANK)
-                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(C.peer_sync[p] + 8 + PRB_RANK), "l"(C.epoch) : "memory");
-        }
-        bool ok = prb_spin_until<false>(C, C.bar, C.bar_target);
-#pragma unroll
-        for (int q = 0; q < PRB_WORLD; ++q)
-            if (q != PRB_RANK && ok) ok = prb_spin_until<true>(C, C.bar + 8 + q, C.epoch);
-        __threadfence_system();
-#else
         __threadfence();
         atomicAdd(C.bar, 1ULL);
         prb_spin_until<false>(C, C.bar, C.bar_target);
         __threadfence();
-#endif
     }
+    C.epoch += 1ULL;
+#if PRB_WORLD > 1
+    C.ll_tag = (unsigned int)(C.epoch + 1ULL) | 0x80000000u;
+    C.ll_par = (long long)((C.epoch + 1ULL) & 1ULL) * PRB_LL_SLOTS;
 #endif
     __syncthreads();
 }
@@ -615,6 +644,18 @@ __device__ __forceinline__ void prb_emit_k(PrbNet& C, const long long e, const r
 #endif
 }
 
+// where prb_emit_k<STAGE> stores the stage input it builds (the region the peers' packets of this evaluation land in)
+template <int STAGE>
+__device__ __forceinline__ long long prb_stage_target(const PrbNet& C) {
+#if PRB_SOLVER == PRB_SOLVER_HEUN_REF || PRB_SOLVER == PRB_SOLVER_HEUN
+    return STAGE == 0 ? C.oS1 : C.oYN;
+#elif PRB_SOLVER == PRB_SOLVER_RK4
+    return STAGE == 0 ? C.oS1 : (STAGE == 1 ? C.oS2 : (STAGE == 2 ? C.oS3 : C.oYN));
+#else
+    return C.oYN;
+#endif
+}
+
 template <int STAGE> __device__ void prb_eval(PrbNet& C);     // generated
 
 template <int STAGE>
@@ -645,10 +686,12 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
 #if PRB_WORLD > 1
 #pragma unroll
     for (int p = 0; p < PRB_WORLD; ++p) {
-        C.peer_work[p] = (real*)A.peers[p];
-        C.peer_rings[p] = (real*)A.peers[PRB_WORLD + p];
-        C.peer_sync[p] = (unsigned long long*)A.peers[2 * PRB_WORLD + p];
+        C.ll_peer[p] = (uint4*)A.peers[p];
+        C.peer_sync[p] = (unsigned long long*)A.peers[PRB_WORLD + p];
     }
+    C.ll_mine = C.ll_peer[PRB_RANK];
+    C.ll_tag = 1u | 0x80000000u;
+    C.ll_par = PRB_LL_SLOTS;
 #endif
     C.gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     C.gsize = (long long)gridDim.x * blockDim.x;

@@ -6,14 +6,13 @@ between) — and splices it into the hand-written solver template ``csrc/templat
 """
 from __future__ import annotations
 
-import os
-
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Set, Tuple
 
 import numpy as np
 
 from .emit_inst import ADAPTIVE_SOLVERS, SOLVER_IDS, _FUNC, _lit, read_template
+from .devgen import is_device_generated
 from .netcompile import MemArray, NetIR, Reduction, Store
 from .scalarize import UnsupportedModelError
 
@@ -40,6 +39,9 @@ class NetKernel:
     kernel_name: str = "prb_integrate_net"
     smem_bytes: int = 0        # dynamic shared memory (tcgen05 operand ring)
     tc: Optional[dict] = None  # tcgen05 coupling-GEMM configuration, None = SIMT row reductions
+    ll_slots: int = 0          # multi-GPU: 16-byte packet slots per parity of the receive mirror (work | rings | heartbeats)
+    const_elems: int = 0       # size of the constant space on the device (>= const_init.size when parts are device-generated)
+    const_fills: tuple = ()    # (element offset, devgen generator, row_lo, row_hi): slices filled on the device
 
 
 class _Emitter:
@@ -49,6 +51,26 @@ class _Emitter:
         self.roles: Dict[int, frozenset] = {}
         self.red_work: Dict[int, MemArray] = {}
         self.ring_index = {name: k for k, name in enumerate(a.name for a in ir.arrays.values() if a.space == "ring")}
+        self.pending: List[str] = []      # multi-GPU: unpack calls for the regions stored since the last grid barrier
+
+    # ---- multi-GPU exchange bookkeeping (net_kernel.cuh: prb_ll_*): every store another rank must see is sent as an LL
+    # packet by its owner; the receiving grid fetches the regions its peers own right before the next grid barrier
+    def note_region(self, base: str, n: int, ring: bool = False):
+        """`base`: C expression of the region's first element (already in batched element units), n: index-space length."""
+        if self.world > 1:
+            lo, hi = self.bounds(n)
+            if hi - lo < n:
+                call = (f"prb_ll_unpack{'_ring' if ring else ''}(C, {base}, {n * self.nb}LL, {lo * self.nb}LL, {hi * self.nb}LL);")
+                if call not in self.pending:
+                    self.pending.append(call)
+
+    def note_work(self, offset: int, n: int):
+        self.note_region(f"{offset * self.nb}LL", n)
+
+    def flush(self, indent: str = "    ") -> List[str]:
+        out = [indent + c for c in self.pending]
+        self.pending = []
+        return out
 
     def source_ptr(self, r: Reduction) -> str:
         """Pointer to element j = 0 (instance 0) of the source vector of a simple dot reduction."""
@@ -225,21 +247,32 @@ class _Emitter:
         t = st.target
         B = self.bidx
         if t[0] == "dy":
+            self.note_region(f"prb_stage_target<STAGE>(C) + {t[1] * self.nb}LL", st.n)
             return f"prb_emit_k<STAGE>(C, {B(f'{t[1]}LL + i')}, {val});"
         if t[0] == "work":
             arr = self.ir.arrays[t[1]]
+            self.note_work(arr.offset, st.n)
             return f"prb_st_work(C, {B(f'{arr.offset}LL + i')}, {val});"
         if t[0] == "work_at":
             arr = self.ir.arrays[t[1]]
+            self.note_work(arr.offset + t[2], st.n)
             return f"prb_st_work(C, {B(f'{arr.offset + t[2]}LL')}, {val});"
         if t[0] == "scatter":
             arr, iarr = self.ir.arrays[t[1]], self.ir.arrays[t[2]]
+            if self.world > 1:
+                lo, hi = self.bounds(st.n)
+                call = (f"prb_ll_unpack_scatter(C, {arr.offset}LL, C.iconsts + {iarr.offset}LL, {self.nb}LL, {st.n}LL, "
+                        f"{lo}LL, {hi}LL);")
+                if call not in self.pending:
+                    self.pending.append(call)
             return f"prb_st_work(C, {B(f'{arr.offset}LL + (long long){self._load(iarr, chr(105))}')}, {val});"
         if t[0] == "ring":
             arr = self.ir.arrays[t[1]]
             rows, L = arr.shape
             k = self.ring_index[t[1]]
-            pos = f"{arr.offset}LL + prb_ring_pos(C.head[{k}], {t[2] - arr.rolls}, {L}) * {rows}LL + i"
+            col = f"{arr.offset}LL + prb_ring_pos(C.head[{k}], {t[2] - arr.rolls}, {L}) * {rows}LL"
+            self.note_region(f"({col}) * {self.nb}LL", st.n, ring=True)
+            pos = f"{col} + i"
             return f"prb_st_ring(C, {B(pos)}, {val});"
         raise NotImplementedError(t[0])
 
@@ -296,17 +329,28 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     tc_work = 0
     gemm_smem = 0
     tc_extra: List[Tuple[int, np.ndarray]] = []         # (const offset, tiled hi / lo image)
-    # multi-GPU: 2-d constants (connectivity) are row-sharded -> re-pack the constant space with shard sizes
+    # multi-GPU: 2-d constants (connectivity) are row-sharded -> re-pack the constant space with shard sizes.
+    # Device-generated constants (devgen.DeviceUniform) go to the END of the space: the host image (const_init) covers only
+    # what is uploaded, the session allocates the full space and lets each generator fill its (row-sharded) slice.
     const_size = ir.const_size
-    if world > 1:
+    const_host = const_size
+    const_fills: List[Tuple[int, object, int, int]] = []      # (element offset, generator, row_lo, row_hi)
+    lazy_arrays = [a for a in ir.arrays.values() if a.space == "const" and is_device_generated(a.init)]
+    if world > 1 or lazy_arrays:
         const_size = 0
-        for a in ir.arrays.values():
-            if a.space == "const":
-                rows = a.shape[0]
-                lo, hi = em.bounds(rows) if len(a.shape) == 2 else (0, rows)
-                size = (hi - lo) * (a.shape[1] if len(a.shape) == 2 else 1) if a.shape else 1
-                a.offset = const_size
-                const_size += ((max(size, 1) + 31) // 32) * 32
+        consts = [a for a in ir.arrays.values() if a.space == "const"]
+        for a in [a for a in consts if a not in lazy_arrays] + lazy_arrays:
+            if a is (lazy_arrays[0] if lazy_arrays else None):
+                const_host = const_size
+            rows = a.shape[0] if a.shape else 1
+            lo, hi = em.bounds(rows) if len(a.shape) == 2 else (0, rows)
+            size = (hi - lo) * (a.shape[1] if len(a.shape) == 2 else 1) if a.shape else 1
+            a.offset = const_size
+            const_size += ((max(size, 1) + 31) // 32) * 32
+            if a in lazy_arrays:
+                const_fills.append((a.offset, a.init.astype(np.float32 if f32 else np.float64), lo, hi))
+        if not lazy_arrays:
+            const_host = const_size
     for red in ir.reductions:
         if red.kind == "row":
             arr = MemArray(f"__red{red.id}", "work", (red.n,), work_size, np.zeros(red.n))
@@ -459,6 +503,8 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                     warr = ir.arrays[r.simple[0]]
                     body.append(f"    prb_gemm_batch<{cb}>(C, C.consts + {warr.offset}LL, {lo}LL, {hi - lo}, {r.m}, {em.source_ptr(r)}, "
                                 f"{em.red_work[r.id].offset}LL);      // n = {n}")
+                    em.note_work(em.red_work[r.id].offset, n)
+                body.extend(em.flush())
                 body.append("    prb_grid_barrier(C);")
                 if sts:
                     cur = (p, n, False)
@@ -497,6 +543,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                     need = any(_uses_red(g, em, s_.node, r.id) and (s_.phase, s_.n) != (p, n) for s_ in ir.stores) or \
                         any(_uses_red(g, em, x.node, r.id) for x in ir.reductions)
                     if need:
+                        em.note_work(em.red_work[r.id].offset, n)
                         body.append(f"            prb_st_work(C, {em.bidx(f'{em.red_work[r.id].offset}LL + i')}, red{r.id});")
                 nodes = em.order([s_.node for s_ in sts])
                 body.extend(em.emit_nodes(nodes, cur, emitted, "            "))
@@ -530,6 +577,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                             need = any(_uses_red(g, em, s.node, q.id) and (s.phase, s.n) != (p, n) for s in ir.stores) or \
                                 any(_uses_red(g, em, x.node, q.id) for x in ir.reductions)
                             if need:
+                                em.note_work(em.red_work[q.id].offset, n)
                                 body.append(f"        if (C.lane == 0) prb_st_work(C, {em.red_work[q.id].offset}LL + i, red{q.id});")
                         continue
                     else:
@@ -552,6 +600,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                     need_store = any(_uses_red(g, em, s.node, r.id) and (s.phase, s.n) != (p, n) for s in ir.stores) or \
                         any(_uses_red(g, em, q.node, r.id) for q in ir.reductions)
                     if need_store:
+                        em.note_work(em.red_work[r.id].offset, n)
                         body.append(f"        if (C.lane == 0) prb_st_work(C, {em.red_work[r.id].offset}LL + i, red{r.id});")
                 roots = [s.node for s in sts]
                 nodes = em.order(roots)
@@ -577,6 +626,9 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 for s in sts:
                     body.append("        " + em.store_stmt(s, cur, "STAGE"))
                 body.append("    }")
+        # multi-GPU: fetch what the peers stored in this phase into the local replicas (the last phase's regions are
+        # fetched here as well: the barrier that ends the evaluation follows in prb_stage)
+        body.extend(em.flush())
         if p < n_phases - 1:
             body.append("    prb_grid_barrier(C);")
 
@@ -598,11 +650,9 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     src.append(f"#define PRB_NB {nb}")
     src.append(f"#define PRB_RANK {rank}")
     src.append(f"#define PRB_WORLD {world}")
-    # multi-GPU barrier variant (net_kernel.cuh: prb_grid_barrier): 0 = thread 0 polls the peers' flags one after the other
-    # (default), 1 = warp 0 polls them in one converged loop.  Measured on 8 GPUs (profiles/r01_multigpu.md): no consistent
-    # difference (C3 N=8192 RK4 0.116 vs 0.103 ms/step, N=16384 Euler 0.0585 vs 0.0612) — polling is not what costs.
-    par = os.environ.get("PRB_BARRIER_PARALLEL")
-    src.append(f"#define PRB_BARRIER_PARALLEL {int(par) if par in ('0', '1') else 0}")
+    # multi-GPU receive mirror (net_kernel.cuh: prb_ll_*): one 16-byte packet slot per work / ring element, two parities
+    src.append(f"#define PRB_LL_WORK {(work_size + n_solver_vecs * ns) * nb + tc_work}LL")
+    src.append(f"#define PRB_LL_RING {ir.ring_size * nb}LL")
     src.append("#define PRB_OBS_INDEX(o) (o)" if all_state else f"#define PRB_OBS_INDEX(o) ((long long)A.iconsts[{obs_off}LL + (o)])")
     src.append("struct PrbNet;")
     src.append("__device__ __forceinline__ void prb_net_init_heads(PrbNet& C, long long eval0);")
@@ -632,7 +682,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     def pack(space, size, dtype):
         buf = np.zeros(max(size, 1), dtype=dtype)
         for a in ir.arrays.values():
-            if a.space == space and a.init is not None:
+            if a.space == space and a.init is not None and not is_device_generated(a.init):
                 v = np.asarray(a.init)
                 if space == "ring":
                     v = v.T                        # device layout [L][rows]: a delay column is contiguous
@@ -642,7 +692,9 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 buf[a.offset:a.offset + v.size] = v.reshape(-1)          # casts on assignment, no temporary
         return buf
 
-    const_buf = pack("const", const_size, real)
+    if lazy_arrays and tc_extra:
+        raise UnsupportedModelError("device-generated connectivities are not supported on the tcgen05 sweep path")
+    const_buf = pack("const", const_host if lazy_arrays else const_size, real)
     for off, img in tc_extra:
         const_buf[off:off + img.size] = img
     iconst = pack("iconst", iconst_size, np.int32)
@@ -656,7 +708,9 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     return NetKernel("\n".join(src) + "\n", ns, int(obs.size), (work_size + n_solver_vecs * ns) * nb + tc_work, work_size,
                      pack("work", work_size, real), const_buf, iconst,
                      pack("ring", ir.ring_size, real), pack("table", ir.table_size, real), block, solver, precision,
-                     evals, n_phases, smem_bytes=smem, tc=tc)
+                     evals, n_phases, smem_bytes=smem, tc=tc,
+                     ll_slots=((work_size + n_solver_vecs * ns) * nb + tc_work + ir.ring_size * nb + 32) if world > 1 else 0,
+                     const_elems=max(const_size, 1), const_fills=tuple(const_fills))
 
 
 def _uses_red(g, em: _Emitter, node: int, rid: int) -> bool:

@@ -77,8 +77,13 @@ class InstanceModel:
 
     @property
     def module(self) -> rt.Module:
+        return self.compile()
+
+    def compile(self, shared: bool = False) -> rt.Module:
+        """NVRTC-compile the kernel (cached).  ``shared``: under an initialised torch.distributed group rank 0 compiles and
+        the other ranks receive the cubin — every rank of a sharded sweep runs the same source (collective call)."""
         if self._module is None:
-            self._module = rt.compile_module(self.kernel.source, f"prb_inst_{self.kernel_solver}.cu", fmad=self.fmad)
+            self._module = rt.compile_module(self.kernel.source, f"prb_inst_{self.kernel_solver}.cu", fmad=self.fmad, shared=shared)
         return self._module
 
     @property

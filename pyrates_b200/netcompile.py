@@ -27,6 +27,7 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 
+from .devgen import is_device_generated
 from .program import Program
 from .scalarize import Graph, Sym, UnsupportedModelError, UNARY_FUNCS
 
@@ -137,7 +138,11 @@ class _NetInterp:
             raise KeyError(f"sweep targets {unknown} are not arguments of the program")
         bound = set()
         for a in prog.args:
-            v = np.asarray(a.value)
+            # device-generated constants (devgen.DeviceUniform) own no host memory: they only flow to the constant space
+            lazy = is_device_generated(a.value)
+            if lazy and (a.kind != "const" or a.value.ndim != 2 or a.name in sweep):
+                raise UnsupportedModelError(f"device-generated argument `{a.name}` must be a 2-d read-only constant")
+            v = a.value if lazy else np.asarray(a.value)
             if a.kind == "t":
                 self.env[a.name] = _V(SCALAR, self.g.leaf("t", None, isint=True))
             elif a.kind == "y":
@@ -153,13 +158,13 @@ class _NetInterp:
                     raise UnsupportedModelError("network model supports 2-d (rows x delay) ring buffers only")
                 arr = self._add_array(a.name, "ring", v.shape, v)
                 self.env[a.name] = ("ring", a.name)
-            elif a.is_int:
+            elif not lazy and a.is_int:
                 if v.ndim == 0:
                     self.env[a.name] = int(v)
                 else:
                     self._add_array(a.name, "iconst", v.shape, v.astype(np.int32))
                     self.env[a.name] = ("index", a.name)
-            elif np.iscomplexobj(v):
+            elif not lazy and np.iscomplexobj(v):
                 raise UnsupportedModelError("complex-valued models are not supported by the CUDA backend")
             elif a.name in sweep:
                 # per-instance scalar of a batched sweep (a 0-d parameter, or a uniform per-node vector swept as a whole)
@@ -194,6 +199,11 @@ class _NetInterp:
             off = self.off[key]
             self.off[key] = off + ((size + 31) // 32) * 32       # 256-byte alignment for fp64 vector loads
         # read-only constants are referenced, not copied (a dense connectivity can be tens of GiB: C5 at N=65536 is 32 GiB)
+        if is_device_generated(init):
+            arr = MemArray(name, space, tuple(shape), off, init)
+            self.arrays[name] = arr
+            self.avail[name] = 0
+            return arr
         keep = space in ("const", "iconst", "table") and init is not None and np.asarray(init).nbytes >= (1 << 20)
         arr = MemArray(name, space, tuple(shape), off, None if init is None else (np.asarray(init) if keep else np.array(init, copy=True)))
         self.arrays[name] = arr

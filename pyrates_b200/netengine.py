@@ -19,7 +19,7 @@ from .netcompile import NetIR, netcompile
 from .program import Program
 from .scalarize import UnsupportedModelError
 
-__all__ = ["NetworkModel", "NetworkSession", "build_check", "smoke_check"]
+__all__ = ["NetworkModel", "NetworkSession", "build_check", "build_check_sweeps"]
 
 
 class NetworkModel:
@@ -104,34 +104,41 @@ class NetworkSession:
         self.d_y = rt.DeviceBuffer(max(k.n_state * B, 1) * item)
         self.d_out = rt.DeviceBuffer(max(self.n_samples * k.n_obs * B, 1) * item)
         self.d_params = rt.DeviceBuffer(max(len(model.param_names) * B, 1) * item)
-        self.d_consts = rt.DeviceBuffer.from_host(np.asarray(k.const_init, dtype=real))
+        self.d_consts = rt.DeviceBuffer(max(k.const_elems, k.const_init.size, 1) * item)
+        self.d_consts.upload(np.asarray(k.const_init, dtype=real))
+        for off, gen, lo, hi in k.const_fills:                # device-generated connectivity: this rank's rows only
+            gen.fill(self.d_consts.ptr + off * item, lo, hi, stream)
         self.d_iconsts = rt.DeviceBuffer.from_host(k.iconst_init.astype(np.int32))
         self.d_tables = rt.DeviceBuffer.from_host(k.table_init.astype(real))
         self.d_work = rt.DeviceBuffer(max(k.work_elems, 1) * item)
         self.d_rings = rt.DeviceBuffer(max(k.ring_init.size * B, 1) * item)
-        self.d_sync = rt.DeviceBuffer(8 * (8 + max(model.world, 8)))
+        self.d_sync = rt.DeviceBuffer(8 * 16)
         self.sm_count = rt.device_info()["sm_count"]
         self.steps_done = 0
         self.samples_done = 0
         self.d_peers = None
+        self.d_mirror = None
         self._peer_ptrs = []
         if model.world > 1:
             self._connect_peers()
 
     def _connect_peers(self):
-        """Exchange CUDA IPC handles of (work, rings, sync) with the other ranks (one process per GPU) and build the
-        device table kernels use for NVLink peer stores.  torch.distributed is only the control plane here."""
+        """Multi-GPU (one process per GPU, rows sharded): allocate this rank's receive mirror (two parities of one 16-byte
+        packet slot per work / ring element, net_kernel.cuh: prb_ll_*), exchange CUDA IPC handles of (mirror, sync) with the
+        other ranks and build the device table the kernels use for NVLink peer stores.  torch.distributed is only the
+        control plane here."""
         import torch.distributed as dist
         m = self.m
         if not dist.is_initialized() or dist.get_world_size() != m.world or dist.get_rank() != m.rank:
             raise rt.CudaBackendError("multi-GPU network runs need an initialised torch.distributed group matching rank/world")
-        mine = [rt.ipc_handle(b) for b in (self.d_work, self.d_rings, self.d_sync)]
+        self.d_mirror = rt.DeviceBuffer(2 * 16 * m.kernel.ll_slots)
+        mine = [rt.ipc_handle(b) for b in (self.d_mirror, self.d_sync)]
         everyone = [None] * m.world
         dist.all_gather_object(everyone, mine)
-        table = np.zeros(3 * m.world, dtype=np.uint64)
-        own = (self.d_work.ptr, self.d_rings.ptr, self.d_sync.ptr)
+        table = np.zeros(2 * m.world, dtype=np.uint64)
+        own = (self.d_mirror.ptr, self.d_sync.ptr)
         for p in range(m.world):
-            for k in range(3):
+            for k in range(2):
                 if p == m.rank:
                     ptr = own[k]
                 else:
@@ -139,6 +146,9 @@ class NetworkSession:
                     self._peer_ptrs.append(ptr)
                 table[k * m.world + p] = ptr
         self.d_peers = rt.DeviceBuffer.from_host(table)
+        # JIT + module load happen here, on every rank, BEFORE any launch-time barrier: the in-kernel waits are bounded, and
+        # a rank that still compiles while its peers already spin would otherwise trip them
+        m.module.kernel_info(m.kernel.kernel_name, m.kernel.block, m.kernel.smem_bytes)
         dist.barrier()
 
     def reset(self, y0: Optional[np.ndarray] = None, params: Optional[np.ndarray] = None):
@@ -166,7 +176,9 @@ class NetworkSession:
         self.steps_done = 0
         self.samples_done = 0
 
-    def launch(self, n_steps: int, dt: float, store_step: int = 1):
+    def launch(self, n_steps: int, dt: float, store_step: int = 1, events=None):
+        """``events``: optional ``(start, stop)`` runtime.Event pair recorded on the launch stream right before / after the
+        kernel (behind the host-side rendezvous of a multi-GPU launch), for device-side timing."""
         k = self.m.kernel
         new_samples = 0
         if n_steps > 0:
@@ -178,10 +190,11 @@ class NetworkSession:
         self.d_sync.zero(self.stream)
         if self.m.world > 1:
             import torch.distributed as dist
+            self.d_mirror.zero(self.stream)     # packet tags restart with every launch
             if self.stream is not None:
                 self.stream.synchronize()
             rt.synchronize()
-            dist.barrier()                      # every rank's barrier words are zero before any kernel signals
+            dist.barrier()                      # every rank's mirror / barrier words are zero before any kernel sends
         a = rt.KernelArgs()
         a.n_steps, a.store_step, a.step0 = int(n_steps), int(store_step), int(self.steps_done)
         a.t0, a.eval0 = self.m.t0, int(self.steps_done) * k.evals_per_step
@@ -193,8 +206,12 @@ class NetworkSession:
         a.work, a.sync = self.d_work.ptr, self.d_sync.ptr
         a.peers = self.d_peers.ptr if self.d_peers is not None else None
         a.rank, a.world = self.m.rank, self.m.world
+        if events is not None:
+            events[0].record(self.stream)
         self.m.module.run(k.kernel_name, a, block=k.block, grid=self.sm_count * self.m.blocks_per_sm,
                           smem=k.smem_bytes, cooperative=True, stream=self.stream)
+        if events is not None:
+            events[1].record(self.stream)
         self.steps_done += int(n_steps)
         self.samples_done += new_samples
         return new_samples
@@ -251,7 +268,7 @@ class NetworkSession:
         if words[2] != 0:
             what = {101: "tcgen05 producer (smem slot never freed)", 102: "tcgen05 MMA issuer (operand tile never arrived)",
                     103: "tcgen05 epilogue (accumulator never completed)", 104: "tcgen05 MMA issuer (TMEM buffer never drained)"
-                    }.get(int(words[2]), "grid barrier (a CTA or peer rank did not arrive)")
+                    }.get(int(words[2]), "grid barrier / peer exchange (a CTA or peer rank did not arrive)")
             raise rt.CudaBackendError(f"network kernel wait timed out: {what}")
 
     def download(self) -> np.ndarray:
@@ -279,7 +296,7 @@ class NetworkSession:
             self._peer_ptrs = []
             if dist.is_initialized():
                 dist.barrier()                  # nobody frees memory a peer may still have mapped
-        for n in ("d_y", "d_out", "d_consts", "d_iconsts", "d_tables", "d_work", "d_rings", "d_sync", "d_peers", "d_params", "d_opts"):
+        for n in ("d_y", "d_out", "d_consts", "d_iconsts", "d_tables", "d_work", "d_rings", "d_sync", "d_peers", "d_params", "d_opts", "d_mirror"):
             b = getattr(self, n, None)
             if b is not None:
                 b.free()
@@ -309,41 +326,3 @@ def build_check_sweeps(golden_dir: str) -> None:
         assert cubin[:4] == b"\x7fELF", name
         kind = f"tcgen05 tiles 128x{m.kernel.tc['bt']}" if m.kernel.tc else "DMMA / FMA tiles"
         print(f"[build] net sweep {name}/{solver} x{nb}: {kind}, cubin {len(cubin)} bytes")
-
-
-def smoke_check_sweep(golden_dir: str) -> None:
-    """One small float32 network sweep on the tcgen05 path, two instances checked against the oracle."""
-    from oracle import numpy_oracle as orc
-    name, solver, nb, sweep = _CHECK_SWEEP[0]
-    path = os.path.join(golden_dir, name + ".npz")
-    fx = orc.load_fixture(path)
-    prog = Program.load(path)
-    r = fx["run"]
-    m = NetworkModel(prog, solver=solver, n_batch=nb, sweep=sweep)
-    assert m.kernel.tc is not None
-    params = m.param_defaults[:, None] + np.linspace(-0.2, 0.5, nb)[None, :]
-    out, _ = m.run(r["T"], r["dt"], r["dts"], params=params)
-    f = orc.build_vector_field(prog.source())
-    names = [a.name for a in prog.args]
-    worst = 0.0
-    for b in (0, nb - 1):
-        args = [np.array(a.value, copy=True) for a in prog.args]
-        args[0] = args[0][()]
-        v = args[names.index(sweep[0])]
-        args[names.index(sweep[0])] = np.asarray(params[0, b], dtype=v.dtype)[()]
-        rec, _ = orc.run(f, args, r["T"], r["dt"], r["dts"], solver)
-        worst = max(worst, float(np.max(np.abs(out[:, :, b] - rec)) / np.max(np.abs(rec))))
-    print(f"[smoke] WC N=300 float32 sweep x{nb} (tcgen05 3xTF32 coupling GEMM): max scaled error vs oracle {worst:.3e}")
-    assert worst < 1e-4, worst
-
-
-def smoke_check(golden_dir: str) -> None:
-    from oracle import numpy_oracle as orc
-    path = os.path.join(golden_dir, "wc_n128.npz")
-    fx = orc.load_fixture(path)
-    r = fx["run"]
-    out, _ = NetworkModel(Program.load(path), solver="rk4").run(r["T"], r["dt"], r["dts"])
-    ref = fx["extra"]["rec_rk4"]
-    err = float(np.max(np.abs(out[:, :, 0] - ref)) / np.max(np.abs(ref)))
-    print(f"[smoke] WC N=128 dense, rk4 (network kernel): max scaled error vs oracle {err:.3e}")
-    assert err < 1e-9, err

@@ -58,6 +58,7 @@ SYMBOLS = {
     "prb_abi_version": (C.c_int, []),
     "prb_last_error": (C.c_char_p, []),
     "prb_launch_count": (C.c_int64, []),
+    "prb_nvrtc_version": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "prb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "prb_set_device": (C.c_int, [C.c_int]),
     "prb_get_device_info": (C.c_int, [C.POINTER(DeviceInfo)]),
@@ -221,12 +222,22 @@ class PinnedBuffer:
         p = C.c_void_p()
         _check(lib().prb_host_alloc(C.byref(p), max(self.nbytes, 1)))
         self.ptr = p.value
-        self.array = np.frombuffer((C.c_char * max(self.nbytes, 1)).from_address(self.ptr), dtype=self.dtype,
-                                   count=int(np.prod(self.shape))).reshape(self.shape)
+        self._raw = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(self._raw, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def detach(self) -> np.ndarray:
+        """Hand the memory over to the array: the pinned allocation is released when the last NumPy view of it dies
+        (results of a sweep are returned without a second multi-GB host copy)."""
+        import weakref
+        arr, ptr = self.array, self.ptr
+        weakref.finalize(self._raw, _free_pinned, ptr)
+        self.ptr, self.array, self._raw = None, None, None
+        return arr
 
     def free(self):
         if getattr(self, "ptr", None):
             self.array = None
+            self._raw = None
             try:
                 lib().prb_host_free(self.ptr)
             finally:
@@ -237,6 +248,13 @@ class PinnedBuffer:
             self.free()
         except Exception:
             pass
+
+
+def _free_pinned(ptr):
+    try:
+        lib().prb_host_free(ptr)
+    except Exception:
+        pass
 
 
 def _s(stream):
@@ -329,6 +347,17 @@ class Module:
 
 
 _module_cache: Dict[str, Module] = {}
+_toolchain = None
+
+
+def _toolchain_tag() -> str:
+    """NVRTC version + libprb ABI version: part of the cubin cache key, so a toolkit upgrade cannot reuse stale cubins."""
+    global _toolchain
+    if _toolchain is None:
+        major, minor = C.c_int(0), C.c_int(0)
+        lib().prb_nvrtc_version(C.byref(major), C.byref(minor))
+        _toolchain = f"nvrtc{major.value}.{minor.value}/abi{lib().prb_abi_version()}"
+    return _toolchain
 DEFAULT_OPTS = ("--std=c++17", "-lineinfo", "--extra-device-vectorization")
 
 
@@ -345,14 +374,44 @@ def _cache_dir() -> Optional[str]:
         return None
 
 
+def _compile_shared(key: str, build) -> Optional[Module]:
+    """One NVRTC run for all ranks of a torch.distributed group: rank 0 builds, the cubin is broadcast.  Collective —
+    every rank must call it for the same source (checked: mismatching keys fall back to local compilation)."""
+    try:
+        import torch.distributed as dist
+    except ImportError:
+        return None
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    keys = [None] * dist.get_world_size()
+    dist.all_gather_object(keys, key)
+    if any(k != key for k in keys):
+        return None
+    box = [build().cubin if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    if dist.get_rank() == 0:
+        return None                                  # rank 0 keeps the module it just built (caller's cache has it)
+    handle = C.c_void_p()
+    _check(lib().prb_module_from_cubin(box[0], len(box[0]), C.byref(handle)))
+    return Module(handle.value, "", "")
+
+
 def compile_module(source: str, name: str = "prb_kernel.cu", opts: Sequence[str] = (), *, fmad: bool = True,
-                   verbose_ptxas: bool = False) -> Module:
+                   verbose_ptxas: bool = False, shared: bool = False) -> Module:
     """NVRTC-compile ``source`` for sm_100a.  Cached in memory and on disk by source hash
     (cf. the reference's SHA-256 module cache, base_backend.py:557)."""
     all_opts = list(DEFAULT_OPTS) + list(opts) + [f"--fmad={'true' if fmad else 'false'}"]
     if verbose_ptxas:
         all_opts += ["--ptxas-options=-v"]
-    key = hashlib.sha256(("\0".join(all_opts) + "\0" + ARCH + "\0" + source).encode()).hexdigest()
+    if shared:
+        key = hashlib.sha256(("\0".join(all_opts) + "\0" + ARCH + "\0" + _toolchain_tag() + "\0" + source).encode()).hexdigest()
+        if key not in _module_cache:
+            m = _compile_shared(key, lambda: compile_module(source, name, opts, fmad=fmad))
+            if m is not None:
+                m.source = source
+                _module_cache[key] = m
+                return m
+    key = hashlib.sha256(("\0".join(all_opts) + "\0" + ARCH + "\0" + _toolchain_tag() + "\0" + source).encode()).hexdigest()
     m = _module_cache.get(key)
     if m is not None:
         return m

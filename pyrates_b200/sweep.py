@@ -82,6 +82,13 @@ class BatchedSweep:
         self.B = int(n_inst)
         self.dt = float(dt)
         self.steps, self.store_step, self.n_samples = n_steps_for(T, dt, dts)
+        # the kernels record ceil(steps / store_step) samples; the reference sizes its recording as round(T / dts) rows and
+        # dies with an IndexError when the loop stores more (base_backend.py:723,730-733) — refuse up front, never write
+        # past the pinned result buffer
+        recorded = -(-self.steps // self.store_step) if self.steps > 0 else 0
+        if not self.adaptive and recorded > self.n_samples:
+            raise IndexError(f"the run records {recorded} samples (steps={self.steps}, every {self.store_step}) but the result "
+                             f"holds round(T/dts) = {self.n_samples} rows; choose T as a multiple of the sampling step size")
         self.n_obs = len(self.model.observers)
         self.real = self.model.real
         self.chunk_samples = max(1, min(int(chunk_samples), max(self.n_samples, 1)))
@@ -266,6 +273,18 @@ class BatchedSweep:
             s.stream = saved
         self.launches_per_run = 1
         return out[: self.n_samples]
+
+    def detach_result(self) -> np.ndarray:
+        """The result of the last ``run()`` as an array that OWNS its (pinned) memory: the buffer leaves this object and is
+        released when the last view of the array dies — ``grid_search`` returns 8.4 GB of trajectories without copying
+        them.  The sweep cannot ``run()`` again afterwards."""
+        if self.h_out is None:
+            raise rt.CudaBackendError("no pinned result buffer to detach")
+        self.wait()
+        n = self.h_out.shape[0] if self.reduce else self.n_samples
+        arr = self.h_out.detach()
+        self.h_out = None
+        return arr[:n]
 
     def final_state(self) -> np.ndarray:
         return self.sess.download_state()

@@ -30,8 +30,30 @@ def test_struct_layout_matches_header():
     assert rt.lib().prb_abi_version() == 2
 
 
-def test_nvrtc_compiles_without_gpu_and_reports_errors():
-    os.environ["PRB_CACHE_DIR"] = "off"
+def test_documented_ctypes_stub_matches_the_header(tmp_path):
+    """INTEGRATION.md section 2 documents the binding a maintainer would write: its structures must have the size gcc
+    computes from include/prb.h (field offsets of the members the stub touches included) and agree with runtime.py."""
+    import subprocess
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if "class KernelArgs(C.Structure)" in b)
+    ns = {}
+    exec(stub, ns)
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "prb.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(prb_kernel_args), sizeof(prb_run_desc), offsetof(prb_kernel_args, peers), offsetof(prb_kernel_args, world), '
+                   'offsetof(prb_run_desc, stream), offsetof(prb_run_desc, args)); return 0; }\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    ka, rd, o_peers, o_world, o_stream, o_args = map(int, subprocess.check_output([str(exe)]).split())
+    for K, R in ((ns["KernelArgs"], ns["RunDesc"]), (rt.KernelArgs, rt.RunDesc)):
+        assert (ctypes.sizeof(K), ctypes.sizeof(R)) == (ka, rd)
+        assert (K.peers.offset, K.world.offset, R.stream.offset, R.args.offset) == (o_peers, o_world, o_stream, o_args)
+    assert [f[0] for f in ns["KernelArgs"]._fields_] == [f[0] for f in rt.KernelArgs._fields_]
+
+
+def test_nvrtc_compiles_without_gpu_and_reports_errors(monkeypatch):
+    monkeypatch.setenv("PRB_CACHE_DIR", "off")
     m = rt.compile_module('extern "C" __global__ void k(float* x) { x[threadIdx.x] *= 2.f; }', "t.cu")
     assert len(m.cubin) > 500 and m.cubin[:4] == b"\x7fELF"
     with pytest.raises(rt.CudaBackendError, match="error"):

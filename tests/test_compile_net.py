@@ -44,7 +44,7 @@ def test_multi_gpu_variants_compile_and_shard_constants(world):
     sizes = []
     for rank in range(world):
         m = NetworkModel(prog, solver="rk4", rank=rank, world=world)
-        assert f"#define PRB_WORLD {world}" in m.kernel.source and "st.relaxed.sys" in m.kernel.source
+        assert f"#define PRB_WORLD {world}" in m.kernel.source and "st.volatile.global.v4.u32" in m.kernel.source
         rt.compile_module(m.kernel.source, f"mg{rank}.cu")
         sizes.append(m.kernel.const_init.size)
     full = NetworkModel(prog, solver="rk4").kernel.const_init.size
@@ -133,3 +133,57 @@ def test_adaptive_network_kernel_compiles(name):
         NetworkModel(Program.load(golden_path("wc_n128_f32")), solver="scipy")
     with pytest.raises(UnsupportedModelError, match="adaptive"):
         NetworkModel(Program.load(golden_path("qsfa_both_n96")), solver="scipy")
+
+
+def test_multi_gpu_exchange_regions_cover_every_shared_store():
+    """Row-sharded kernels: every store another rank must see (stage vectors, materialised intermediates, ring columns,
+    scatter targets) is sent as an LL packet by its owner and fetched by the receiving grid right before the next grid
+    barrier — the emitter must list an unpack call for each stored region, with this rank's row bounds, and no
+    system-scope fence may remain on the data path."""
+    import re
+    cases = {"kuramoto_n128": ["prb_ll_unpack(C, 0LL, 128LL,", "prb_ll_unpack(C, 128LL, 128LL,", "prb_stage_target<STAGE>(C) + 0LL"],
+             "qsfa_both_n96": ["prb_ll_unpack_ring(C,", "prb_stage_target<STAGE>(C) + 1056LL"],
+             "jrc_2delay": ["prb_ll_unpack_scatter(C,"], "net13": ["prb_ll_unpack_scatter(C,"]}
+    for name, needles in cases.items():
+        prog = Program.load(golden_path(name))
+        m = NetworkModel(prog, solver="heun", rank=1, world=4)
+        src = m.kernel.source
+        body = src[src.rindex("template <int STAGE> __device__ void prb_eval"):]
+        for n in needles:
+            assert n in body, (name, n)
+        n_dy = len(re.findall(r"prb_emit_k<STAGE>\(", body))
+        assert len(re.findall(r"prb_ll_unpack\(C, prb_stage_target<STAGE>", body)) == n_dy       # one region per dy store
+        lo, hi = [(0, 32), (32, 64), (64, 96), (96, 128)][1] if name == "kuramoto_n128" else (None, None)
+        if lo is not None:
+            assert f"128LL, {lo}LL, {hi}LL);" in body
+        # every unpack precedes the barrier of its phase: no store region is left pending behind the last barrier call
+        assert body.rstrip().endswith("}") and "prb_ll_unpack" in body.split("prb_grid_barrier(C);")[-1]
+        assert "__threadfence_system" not in src and m.kernel.ll_slots > 0
+        assert m.module.cubin[:4] == b"\x7fELF"
+    single = NetworkModel(Program.load(golden_path("kuramoto_n128")), solver="heun")
+    assert "prb_ll_unpack(C" not in single.kernel.source[single.kernel.source.rindex("template <int STAGE> __device__ void prb_eval"):]
+
+
+def test_device_generated_connectivity_twin_and_constant_layout():
+    """devgen.DeviceUniform: the NumPy twin is a pure function of (seed, global element index) — any row shard equals the
+    slice of the whole — and the emitter puts the generated matrix behind the uploaded constants, row-sharded per rank."""
+    import numpy as np
+    from pyrates_b200.devgen import DeviceUniform
+    from pyrates_b200.program import Arg
+    g = DeviceUniform((12, 5), 2.0 / 12, 2)
+    full = g.host()
+    assert full.shape == (12, 5) and 0.0 <= full.min() and full.max() < 2.0 / 12 and len(np.unique(full)) == 60
+    np.testing.assert_array_equal(g.host(3, 9), full[3:9])
+    np.testing.assert_array_equal(DeviceUniform((12, 5), 2.0 / 12, 2).host(), full)
+    assert not np.array_equal(DeviceUniform((12, 5), 2.0 / 12, 3).host(), full)
+    # known answer: SplitMix64 of seed 0 at index 0 is 0xE220A8397B1DCDAF
+    assert DeviceUniform((1, 1), 1.0, 0).host()[0, 0] == (0xE220A8397B1DCDAF >> 11) * 2.0 ** -53
+    p = Program.load(golden_path("kuramoto_n128"))
+    lazy = Program([Arg(a.name, a.kind, DeviceUniform((128, 128), 2.0 / 128, 2) if a.name == "weight" else a.value, a.label)
+                    for a in p.args], p.stmts, {}, p.float_precision, p.func_name)
+    for world, rank in ((1, 0), (4, 3)):
+        k = NetworkModel(lazy, solver="euler", rank=rank, world=world).kernel
+        (off, gen, lo, hi), = k.const_fills
+        assert off == k.const_init.size and k.const_elems == off + (hi - lo) * 128 and (lo, hi) == ((0, 128) if world == 1 else (96, 128))
+    from pyrates_b200.devgen import _fill_module
+    assert _fill_module("float32").cubin[:4] == b"\x7fELF"

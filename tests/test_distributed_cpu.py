@@ -62,3 +62,46 @@ def test_gloo_world2_shard_and_gather(n_inst):
     s, o = np.meshgrid(np.arange(5), np.arange(2), indexing="ij")
     want = s[..., None] * 1000.0 + o[..., None] * 100.0 + np.arange(n_inst)[None, None, :]
     np.testing.assert_array_equal(full, want)
+
+
+def test_sweep_refuses_a_horizon_that_overflows_the_result_rows():
+    """T not a multiple of the sampling step: the loop would record ceil(steps / store_step) samples into round(T / dts)
+    rows.  The reference dies with an IndexError there (base_backend.py:723,730-733); BatchedSweep must refuse before it
+    allocates anything (no write past the pinned result buffer)."""
+    from conftest import golden_path
+    from pyrates_b200.program import Program
+    from pyrates_b200.sweep import BatchedSweep
+    prog = Program.load(golden_path("jrc"))
+    with pytest.raises(IndexError, match="records 4 samples"):
+        BatchedSweep(prog, [("u", 0)], observers=[0], solver="euler", T=10.0, dt=1.0, dts=3.0, n_inst=4)
+
+
+def _compile_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), PRB_CACHE_DIR="off")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pyrates_b200 import runtime as rt
+    calls = []
+    real = rt.lib().prb_compile
+    src = 'extern "C" __global__ void k(float* x) { x[threadIdx.x] *= 3.f; }'
+    m = rt.compile_module(src, "shared.cu", shared=True)          # rank 0 compiles, rank 1 receives the cubin
+    # a source only THIS rank has: keys differ -> every rank compiles locally instead of dead-locking
+    own = rt.compile_module(f'extern "C" __global__ void k{rank}(float* x) {{ x[0] = {rank}.f; }}', "own.cu", shared=True)
+    q.put((rank, bytes(m.cubin), m.log, len(own.cubin)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_rank0_compiles_and_broadcasts_the_cubin():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_compile_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict((r, (c, log, n)) for r, c, log, n in (q.get(timeout=180) for _ in range(2)))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got[0][0] == got[1][0] and got[0][0][:4] == b"\x7fELF" and got[0][2] > 500 and got[1][2] > 500
