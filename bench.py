@@ -321,6 +321,14 @@ def bench_network(cx: Ctx, tag: str, prog, how: str, *, solver: str, nodes: int,
                       ((arr, _bounds(arr.shape[0], cx.world, cx.rank)) for arr in m.ir.arrays.values()
                        if arr.space == "const" and len(arr.shape) == 2)) * item
     achieved = wbytes_rank * evals * sim_steps * K / (ms * 1e-3) / 1e9
+    model = "this rank's rows of W (fp64) x rhs evaluations per solver step x solver steps; vectors negligible"
+    alg_bytes = wbytes_rank * evals * sim_steps
+    if wbytes_rank == 0:
+        # no matrix (global vsum coupling): SURVEY 8d C5a model, 3 words per node-step; the run is bound by the per-evaluation
+        # grid barrier latency, the fraction of the HBM roofline is reported for completeness
+        alg_bytes = 24.0 * nodes * sim_steps / cx.world
+        achieved = alg_bytes * K / (ms * 1e-3) / 1e9
+        model = "SURVEY 8d C5a: (2 n_sv + n_pp) x 8 B = 24 B per node-step; latency-bound (one grid barrier per evaluation)"
     # end to end: host state in (constants stay resident in the session, like the arguments of a compiled model across
     # run() calls), recorded trajectories + final state back in host memory
     y0 = np.array(prog.y0, copy=True)
@@ -341,8 +349,7 @@ def bench_network(cx: Ctx, tag: str, prog, how: str, *, solver: str, nodes: int,
            "ms_per_step": ms / K, "us_per_solver_step": ms * 1e3 / (K * sim_steps), "evals_per_solver_step": evals,
            "dtype": "f64" if item == 8 else "f32",
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": cx.peaks["hbm"], "unit": "GB/s", "frac": achieved / cx.peaks["hbm"],
-                        "algorithmic_bytes_per_launch": wbytes_rank * evals * sim_steps,
-                        "model": "this rank's rows of W (fp64) x rhs evaluations per solver step x solver steps; vectors negligible",
+                        "algorithmic_bytes_per_launch": alg_bytes, "model": model,
                         "W_resident_in": resident, "peak_source": cx.peaks["source"], "traffic": None},
            "e2e": {"value": nodes * e2e_steps / e2e_s, "unit": UNIT, "solver_steps": e2e_steps, "ms": e2e_s * 1e3,
                    "h2d_bytes_per_step": int(y0.nbytes + m.kernel.ring_init.nbytes + m.kernel.work_init.nbytes),

@@ -70,7 +70,9 @@ class FakeBatched:
     def run(self, table):
         stats["grid"] += 1
         ns = E.n_steps_for(self.T, self.dt, self.dts)[2]
-        return np.zeros((ns, self.n_obs, self.B))
+        self._res = np.zeros((ns, self.n_obs, self.B))
+        return self._res
+    def detach_result(self): return self._res
     def free(self): pass
 S.BatchedSweep = FakeBatched
 script = sys.argv[1]
