@@ -179,6 +179,10 @@ int prb_ipc_open_handle(const unsigned char* handle, void** dptr);
 int prb_ipc_close_handle(void* dptr);
 int prb_host_alloc(void** hptr, size_t bytes);       /* pinned host memory */
 int prb_host_free(void* hptr);
+/* page-lock caller-allocated host memory (e.g. an anonymous mapping backed by transparent huge pages: an 8 GB result
+ * buffer registers several times faster than cuMemHostAlloc builds it from 4 KB pages) */
+int prb_host_register(void* hptr, size_t bytes);
+int prb_host_unregister(void* hptr);
 int prb_stream_create(void** stream);
 int prb_stream_destroy(void* stream);
 int prb_stream_synchronize(void* stream);

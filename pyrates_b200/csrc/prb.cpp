@@ -47,7 +47,7 @@ int fail(int code, const char* fmt, ...) {
     X(cuFuncGetAttribute) X(cuFuncSetAttribute) X(cuOccupancyMaxActiveBlocksPerMultiprocessor)    \
     X(cuLaunchKernel) X(cuLaunchCooperativeKernel) X(cuMemAlloc_v2) X(cuMemFree_v2)               \
     X(cuMemsetD8Async) X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2) X(cuMemcpyDtoDAsync_v2)    \
-    X(cuMemHostAlloc) X(cuMemFreeHost) X(cuStreamCreate) X(cuStreamDestroy_v2)                    \
+    X(cuMemHostAlloc) X(cuMemFreeHost) X(cuMemHostRegister_v2) X(cuMemHostUnregister) X(cuStreamCreate) X(cuStreamDestroy_v2)                    \
     X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuEventCreate) X(cuEventDestroy_v2) X(cuEventRecord)                 \
     X(cuEventSynchronize) X(cuEventElapsedTime) X(cuGetErrorString) X(cuGetErrorName)             \
     X(cuIpcGetMemHandle) X(cuIpcOpenMemHandle_v2) X(cuIpcCloseMemHandle)
@@ -419,6 +419,18 @@ int prb_host_free(void* hptr) {
     if (!hptr) return PRB_OK;
     if (int e = need_ctx()) return e;
     CU(cuMemFreeHost(hptr));
+    return PRB_OK;
+}
+int prb_host_register(void* hptr, size_t bytes) {
+    if (!hptr || !bytes) return fail(PRB_ERR_INVALID, "hptr/bytes is NULL");
+    if (int e = need_ctx()) return e;
+    CU(cuMemHostRegister_v2(hptr, bytes, CU_MEMHOSTREGISTER_PORTABLE));
+    return PRB_OK;
+}
+int prb_host_unregister(void* hptr) {
+    if (!hptr) return PRB_OK;
+    if (int e = need_ctx()) return e;
+    CU(cuMemHostUnregister(hptr));
     return PRB_OK;
 }
 int prb_stream_create(void** stream) {

@@ -22,6 +22,9 @@
 #ifndef PRB_NB
 #define PRB_NB 1                 // sweep instances integrated together (batch index b is the fastest-varying dimension)
 #endif
+#ifndef PRB_DOT_DEEP
+#define PRB_DOT_DEEP 0           // fp64 row dot: 8 instead of 4 independent 16-byte loads per lane (set by the emitter)
+#endif
 
 struct PrbNet {
     const real* yin;             // stage input of the current evaluation (written in-kernel: plain loads only)
@@ -155,31 +158,25 @@ __device__ __forceinline__ real prb_ll_recv(PrbNet& C, const long long slot) {
     if (sizeof(real) == 8) return (real)__longlong_as_double((long long)(((unsigned long long)pk.z << 32) | (unsigned long long)pk.x));
     return (real)__uint_as_float(pk.x);
 }
-// elements [0, n) of a region at `off`, this rank owns [lo, hi): fetch everything else from the mirror into the replica
-__device__ __forceinline__ void prb_ll_unpack(PrbNet& C, const long long off, const long long n, const long long lo, const long long hi) {
-    const long long own = hi - lo;
-    for (long long q = C.gtid; q < n - own; q += C.gsize) {
-        const long long e = off + (q < lo ? q : q + own);
-        C.work[e] = prb_ll_recv(C, e);
-    }
+// One fetch = one element a peer owns: wait for its packet, write it into the local replica.  The emitter merges all
+// regions stored in a phase into ONE grid-strided loop (prb_eval: "fetch what the peers own"), so every thread polls at
+// most a few packets whatever the number of regions (12 state variables + a ring column for the QIF-SFA network).
+// `q` indexes the elements of the region [0, n) that this rank does NOT own: rows [0, lo) then [lo + own, n).
+__device__ __forceinline__ void prb_ll_fetch(PrbNet& C, const long long off, const long long q, const long long lo, const long long own) {
+    const long long e = off + (q < lo ? q : q + own);
+    C.work[e] = prb_ll_recv(C, e);
 }
-__device__ __forceinline__ void prb_ll_unpack_ring(PrbNet& C, const long long off, const long long n, const long long lo, const long long hi) {
-    const long long own = hi - lo;
-    for (long long q = C.gtid; q < n - own; q += C.gsize) {
-        const long long e = off + (q < lo ? q : q + own);
-        C.rings[e] = prb_ll_recv(C, PRB_LL_WORK + e);
-    }
+__device__ __forceinline__ void prb_ll_fetch_ring(PrbNet& C, const long long off, const long long q, const long long lo, const long long own) {
+    const long long e = off + (q < lo ? q : q + own);
+    C.rings[e] = prb_ll_recv(C, PRB_LL_WORK + e);
 }
 // scatter stores arr[idx[i]] = v_i, i sharded like every index space: the (constant) index array names the slots
-__device__ __forceinline__ void prb_ll_unpack_scatter(PrbNet& C, const long long off, const int* __restrict__ idx, const long long nb,
-                                                      const long long n, const long long lo, const long long hi) {
-    const long long own = hi - lo;
-    for (long long q = C.gtid; q < (n - own) * nb; q += C.gsize) {
-        const long long r = q / nb, b = q - r * nb;
-        const long long i = r < lo ? r : r + own;
-        const long long e = (off + (long long)__ldg(idx + i)) * nb + b;
-        C.work[e] = prb_ll_recv(C, e);
-    }
+__device__ __forceinline__ void prb_ll_fetch_scatter(PrbNet& C, const long long off, const int* __restrict__ idx, const long long nb,
+                                                     const long long q, const long long lo, const long long own) {
+    const long long r = q / nb, b = q - r * nb;
+    const long long i = r < lo ? r : r + own;
+    const long long e = (off + (long long)__ldg(idx + i)) * nb + b;
+    C.work[e] = prb_ll_recv(C, e);
 }
 #endif
 
@@ -282,6 +279,25 @@ __device__ __forceinline__ double prb_row_dot(const double* __restrict__ w, cons
         const double2* x2 = (const double2*)x;
         const int m2 = m >> 1;
         int j = lane;
+#if PRB_DOT_DEEP
+        // 8 independent 16-byte loads per lane in flight: rows handled by few warps (row-sharded shards, small networks) are
+        // bound by the number of bytes in flight, not by the stream rate
+        for (; j + 224 < m2; j += 256) {
+            double2 wv[8], xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) wv[u] = prb_ld_stream(w2 + j + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = x2[j + 32 * u];
+            a0 = fma(wv[0].x, xv[0].x, a0); a0 = fma(wv[0].y, xv[0].y, a0);
+            a1 = fma(wv[1].x, xv[1].x, a1); a1 = fma(wv[1].y, xv[1].y, a1);
+            a2 = fma(wv[2].x, xv[2].x, a2); a2 = fma(wv[2].y, xv[2].y, a2);
+            a3 = fma(wv[3].x, xv[3].x, a3); a3 = fma(wv[3].y, xv[3].y, a3);
+            a0 = fma(wv[4].x, xv[4].x, a0); a0 = fma(wv[4].y, xv[4].y, a0);
+            a1 = fma(wv[5].x, xv[5].x, a1); a1 = fma(wv[5].y, xv[5].y, a1);
+            a2 = fma(wv[6].x, xv[6].x, a2); a2 = fma(wv[6].y, xv[6].y, a2);
+            a3 = fma(wv[7].x, xv[7].x, a3); a3 = fma(wv[7].y, xv[7].y, a3);
+        }
+#endif
         for (; j + 96 < m2; j += 128) {
             const double2 wa = prb_ld_stream(w2 + j), wb = prb_ld_stream(w2 + j + 32);
             const double2 wc = prb_ld_stream(w2 + j + 64), wd = prb_ld_stream(w2 + j + 96);

@@ -448,6 +448,7 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
 struct PrbThread {
     long long b, B;
     real p[PRB_NP > 0 ? PRB_NP : 1];
+    const real* __restrict__ pbase;       // params[0][0]: the exact fallback of fast_math kernels re-reads its parameters
     areal q[PRB_NQ > 0 ? PRB_NQ : 1];     // thread-invariant sub-expressions (fast_math: reassoc.fold_invariants)
     int head[PRB_NRINGS > 0 ? PRB_NRINGS : 1];
     real* __restrict__ slots;
@@ -645,7 +646,7 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
         vals = body.pop(0)[len("// PRB_LIT = {"):-1]
         src.append(f"__device__ __constant__ double PRB_LIT[{vals.count(',') + 1}] = {{{vals}}};")
     init = ["__device__ __forceinline__ void prb_thread_init(PrbThread& T, const prb_kernel_args& A, long long b) {",
-            "    T.b = b; T.B = A.n_inst; T.etab = nullptr; T.etab_s = 0u;",
+            "    T.b = b; T.B = A.n_inst; T.etab = nullptr; T.etab_s = 0u; T.pbase = (const real*)A.params;",
             "    T.slots = (real*)A.slots; T.rings = (real*)A.rings; T.tables = (const real*)A.tables;"]
     if np_:
         init.append("    const real* __restrict__ P = (const real*)A.params;")
@@ -710,6 +711,9 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
         src.append("    if (bad) {                  // an exp / division argument left the fast range: redo this evaluation exactly")
         src.append("        areal yl[PRB_NS], dl[PRB_NDY];")
         src.append("        PrbThread Tl = T;")
+        # the swept parameters are re-read from global memory on this (rare) path: keeping T.p alive across the time loop
+        # for it costs 2 registers per parameter in a kernel whose fast path only needs the folded invariants T.q
+        src.append("        _Pragma(\"unroll\") for (int k = 0; k < PRB_NP; ++k) Tl.p[k] = T.pbase[(long long)k * T.B + T.b];")
         src.append("        _Pragma(\"unroll\") for (int j = 0; j < PRB_NS; ++j) yl[j] = y[j];")
         src.append("        prb_rhs_exact(t, yl, dl, Tl);")
         src.append("        _Pragma(\"unroll\") for (int j = 0; j < PRB_NDY; ++j) dy[j] = dl[j];")

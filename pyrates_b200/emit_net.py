@@ -60,15 +60,36 @@ class _Emitter:
         if self.world > 1:
             lo, hi = self.bounds(n)
             if hi - lo < n:
-                call = (f"prb_ll_unpack{'_ring' if ring else ''}(C, {base}, {n * self.nb}LL, {lo * self.nb}LL, {hi * self.nb}LL);")
-                if call not in self.pending:
-                    self.pending.append(call)
+                item = ("prb_ll_fetch_ring" if ring else "prb_ll_fetch", f"{base}, ", (n - (hi - lo)) * self.nb,
+                        f", {lo * self.nb}LL, {(hi - lo) * self.nb}LL")
+                if item not in self.pending:
+                    self.pending.append(item)
 
     def note_work(self, offset: int, n: int):
         self.note_region(f"{offset * self.nb}LL", n)
 
+    def note_scatter(self, arr_offset: int, iarr_offset: int, n: int):
+        if self.world > 1:
+            lo, hi = self.bounds(n)
+            if hi - lo < n:
+                item = ("prb_ll_fetch_scatter", f"{arr_offset}LL, C.iconsts + {iarr_offset}LL, {self.nb}LL, ",
+                        (n - (hi - lo)) * self.nb, f", {lo}LL, {hi - lo}LL")
+                if item not in self.pending:
+                    self.pending.append(item)
+
     def flush(self, indent: str = "    ") -> List[str]:
-        out = [indent + c for c in self.pending]
+        """One grid-strided loop over ALL elements the peers own of the regions stored since the last barrier."""
+        if not self.pending:
+            return []
+        total = sum(cnt for _, _, cnt, _ in self.pending)
+        out = [f"{indent}for (long long q = C.gtid; q < {total}LL; q += C.gsize) {{   // fetch what the peers own "
+               f"({len(self.pending)} region(s))"]
+        start = 0
+        for k, (fn, head, cnt, tail) in enumerate(self.pending):
+            cond = "" if k == len(self.pending) - 1 else f"if (q < {start + cnt}LL) "
+            out.append(f"{indent}    {'else ' if k else ''}{cond}{fn}(C, {head}q - {start}LL{tail});")
+            start += cnt
+        out.append(f"{indent}}}")
         self.pending = []
         return out
 
@@ -259,12 +280,7 @@ class _Emitter:
             return f"prb_st_work(C, {B(f'{arr.offset + t[2]}LL')}, {val});"
         if t[0] == "scatter":
             arr, iarr = self.ir.arrays[t[1]], self.ir.arrays[t[2]]
-            if self.world > 1:
-                lo, hi = self.bounds(st.n)
-                call = (f"prb_ll_unpack_scatter(C, {arr.offset}LL, C.iconsts + {iarr.offset}LL, {self.nb}LL, {st.n}LL, "
-                        f"{lo}LL, {hi}LL);")
-                if call not in self.pending:
-                    self.pending.append(call)
+            self.note_scatter(arr.offset, iarr.offset, st.n)
             return f"prb_st_work(C, {B(f'{arr.offset}LL + (long long){self._load(iarr, chr(105))}')}, {val});"
         if t[0] == "ring":
             arr = self.ir.arrays[t[1]]
@@ -296,7 +312,7 @@ def tc_config(ir: NetIR, precision: str, n_batch: int, world: int, tc_max_acc: i
 
 def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequence[int], block: int = 512,
                     rank: int = 0, world: int = 1, n_batch: int = 1, tensor_core: bool = False,
-                    tc_max_acc: int = 128) -> NetKernel:
+                    tc_max_acc: int = 128, split_rows: bool = True, dot_deep: bool = True) -> NetKernel:
     if solver not in SOLVER_IDS:
         raise ValueError(f"unknown solver `{solver}`")
     f32 = precision == "float32"
@@ -362,6 +378,19 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     all_state = obs.size == ns and np.array_equal(obs, np.arange(ns))
     obs_off = ir.iconst_size
     iconst_size = ir.iconst_size + (0 if all_state else ((obs.size + 31) // 32) * 32)
+
+    def row_split(reds, n) -> int:
+        """Warps that share one row of a plain dot(W, x) reduction group (1 = the classic warp per row): the largest power
+        of two that still gives every team a row, assuming one CTA per SM on the 148 SMs of a B200."""
+        if nb != 1 or not split_rows or any(r.simple is None for r in reds) or block % 32:
+            return 1
+        lo_, hi_ = em.bounds(n)
+        rows, wpb = hi_ - lo_, block // 32
+        S = 1
+        m_min = min(r.m for r in reds)
+        while S * 2 <= wpb and rows * S * 2 <= 148 * wpb and m_min // (S * 2) >= 128:      # >= 2 double2 per lane and warp
+            S *= 2
+        return S if rows > 0 else 1
 
     body: List[str] = []
     full_reds = [r for r in ir.reductions if r.kind == "full"]
@@ -551,6 +580,72 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                     body.append("            " + em.store_stmt(s_, cur, "STAGE"))
                 body.append("        }")
                 body.append("    }")
+            elif reds and row_split(reds, n) > 1:
+                # few rows per GPU (row-sharded shards, small networks): S consecutive warps of a CTA share one row — each
+                # takes a contiguous segment of the W row, the partial sums meet in shared memory and the team's first warp runs
+                # the element-wise tail.  With one warp per row a 1024-row shard keeps only 1024 x 4 loads in flight (~2 MB):
+                # ~30 % of what the HBM / L2 stream needs.  The summation order differs from the one-warp form (1e-16).
+                cur = (p, n, True)
+                lo, hi = em.bounds(n)
+                S = row_split(reds, n)
+                wpb = block // 32
+                tpb = wpb // S
+                tagp = f"{p}_{n}"
+                body.append(f"    {{   // {S} warps per row, n = {n} ({hi - lo} rows on this GPU)")
+                body.append(f"        __shared__ real prb_part{tagp}[{len(reds)}][{wpb}];")
+                body.append(f"        const int wib = (int)(threadIdx.x >> 5), tib = wib / {S}, wit = wib - tib * {S};")
+                body.append(f"        const long long nteams = (long long)gridDim.x * {tpb}, team = (long long)blockIdx.x * {tpb} + tib;")
+                body.append(f"        for (long long i0 = {lo}LL; i0 < {hi}LL; i0 += nteams) {{")
+                body.append(f"            const long long i = i0 + team;")
+                body.append(f"            const bool act = i < {hi}LL;")
+                body.append(f"            if (act) {{")
+                fused_done: Set[int] = set()
+                pairs = []
+                for r in reds:
+                    if r.id in fused_done:
+                        continue
+                    mate = next((q for q in reds if q.id != r.id and q.id not in fused_done and q.simple[0] == r.simple[0]
+                                 and q.m == r.m), None)
+                    fused_done.add(r.id)
+                    if mate is not None:
+                        fused_done.add(mate.id)
+                    pairs.append((r, mate))
+                for r, mate in pairs:
+                    warr = ir.arrays[r.simple[0]]
+                    seg = -(-(-(-r.m // S)) // 4) * 4                     # elements per warp, a multiple of 4: keeps the 16-byte alignment
+                    body.append(f"                {{")
+                    body.append(f"                    const int s0 = wit * {seg}, len = ({r.m} - s0) < {seg} ? (({r.m} - s0) > 0 ? ({r.m} - s0) : 0) : {seg};")
+                    wptr = f"C.consts + {warr.offset}LL + (i - {lo}LL) * {r.m}LL + s0"
+                    if mate is not None:
+                        body.append(f"                    real pa, pb;")
+                        body.append(f"                    prb_row_dot2({wptr}, {em.source_ptr(r)} + s0, {em.source_ptr(mate)} + s0, len, C.lane, pa, pb);")
+                        body.append(f"                    if (C.lane == 0) {{ prb_part{tagp}[{reds.index(r)}][wib] = pa; prb_part{tagp}[{reds.index(mate)}][wib] = pb; }}")
+                    else:
+                        body.append(f"                    const real pa = prb_row_dot({wptr}, {em.source_ptr(r)} + s0, len, C.lane);")
+                        body.append(f"                    if (C.lane == 0) prb_part{tagp}[{reds.index(r)}][wib] = pa;")
+                    body.append(f"                }}")
+                body.append(f"            }}")
+                body.append(f"            __syncthreads();")
+                body.append(f"            if (act && wit == 0) {{")
+                emitted = set()
+                for k, r in enumerate(reds):
+                    terms = " + ".join(f"prb_part{tagp}[{k}][tib * {S} + {w}]" for w in range(S))
+                    body.append(f"                const real red{r.id} = {terms};")
+                    need = any(_uses_red(g, em, s_.node, r.id) and (s_.phase, s_.n) != (p, n) for s_ in ir.stores) or \
+                        any(_uses_red(g, em, x.node, r.id) for x in ir.reductions)
+                    if need:
+                        em.note_work(em.red_work[r.id].offset, n)
+                        body.append(f"                if (C.lane == 0) prb_st_work(C, {em.red_work[r.id].offset}LL + i, red{r.id});")
+                body.extend(em.emit_nodes(em.order([s_.node for s_ in sts]), cur, emitted, "                "))
+                if sts:
+                    body.append("                if (C.lane == 0) {")
+                    for s_ in sts:
+                        body.append("                    " + em.store_stmt(s_, cur, "STAGE"))
+                    body.append("                }")
+                body.append(f"            }}")
+                body.append(f"            __syncthreads();")
+                body.append(f"        }}")
+                body.append(f"    }}")
             elif reds:
                 cur = (p, n, True)
                 lo, hi = em.bounds(n)
@@ -648,6 +743,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     src.append(f"#define PRB_BLOCK {block}")
     src.append(f"#define PRB_WORK_USER {work_size}LL")
     src.append(f"#define PRB_NB {nb}")
+    src.append(f"#define PRB_DOT_DEEP {1 if dot_deep else 0}")
     src.append(f"#define PRB_RANK {rank}")
     src.append(f"#define PRB_WORLD {world}")
     # multi-GPU receive mirror (net_kernel.cuh: prb_ll_*): one 16-byte packet slot per work / ring element, two parities

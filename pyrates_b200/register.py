@@ -143,7 +143,8 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     index ``('mean', 'var', 'min', 'max', 'last')`` (or ``ndarray[5, n_out, B]``) instead of the trajectories — fixed-step
     solvers, instance model.
     ``timings``: a dict that receives ``probe_build_s`` (two single-instance builds through the reference front end),
-    ``jit_s`` (lowering + NVRTC), ``run_s`` (H2D + kernels + streamed D2H) and ``frame_s`` (result assembly).
+    ``jit_s`` (lowering + NVRTC), ``alloc_s`` (device buffers + the pinned result buffer), ``run_s`` (H2D + kernels +
+    streamed D2H) and ``frame_s`` (result assembly).
     ``fast_math`` / ``const_div_to_mul`` (float64 sweeps; default ON): table-based exp, reciprocal-multiply divisions and
     folded invariants — each <= 2 ulp, trajectories within 1e-15 of the exact kernels and inside the 1e-9 parity tolerance;
     values outside the fast ranges are re-evaluated exactly.  Pass ``fast_math=False, const_div_to_mul=False`` for the
@@ -288,7 +289,8 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
         except UnsupportedModelError as e:
             if exec_model == "instance" or "too large" not in str(e):
                 raise
-    timings["jit_s"] = time.perf_counter() - t_jit
+    timings["alloc_s"] = sw.timing["alloc_s"] if sw is not None else 0.0      # device + pinned result buffers
+    timings["jit_s"] = time.perf_counter() - t_jit - timings["alloc_s"]       # lowering + NVRTC / cubin cache
     if sw is None and reduce:
         raise NotImplementedError("reduce=True is implemented for sweeps of the instance execution model")
     t_run = time.perf_counter()

@@ -81,6 +81,8 @@ SYMBOLS = {
     "prb_ipc_close_handle": (C.c_int, [C.c_void_p]),
     "prb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "prb_host_free": (C.c_int, [C.c_void_p]),
+    "prb_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "prb_host_unregister": (C.c_int, [C.c_void_p]),
     "prb_stream_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "prb_stream_destroy": (C.c_int, [C.c_void_p]),
     "prb_stream_synchronize": (C.c_int, [C.c_void_p]),

@@ -72,10 +72,13 @@ class BatchedSweep:
                 launch_bounds = 8
             else:
                 block, launch_bounds = 64, 7
+        import time
+        t_build = time.perf_counter()
         self.model = InstanceModel(prog, solver=solver, sweep=sweep, observers=observers, block=block,
                                    const_div_to_mul=const_div_to_mul, min_blocks=launch_bounds,
                                    fast_math=fast_math, rk_method=self.solver_kwargs.get("method"), reduce=self.reduce,
                                    hist_max_delay=hist_max_delay)
+        self.timing = {"lower_s": time.perf_counter() - t_build}     # Program -> scalar DAG -> CUDA C (no NVRTC yet)
         order = [(p.arg, p.elem) for p in self.model.rhs.params]
         self._perm = [order.index((a, int(e))) for a, e in sweep]      # user row k -> kernel param row
         self.sweep = list(sweep)
@@ -97,6 +100,7 @@ class BatchedSweep:
         self.skip_samples = int(np.count_nonzero(np.linspace(0.0, T, num=self.n_samples, endpoint=False) < cutoff)) if cutoff else 0
         if self.reduce:
             self.chunk_samples = 1                       # chunk buffers are not used
+        t_alloc = time.perf_counter()
         self.compute = rt.Stream()
         self.copy = rt.Stream()
         if self.adaptive:
@@ -118,6 +122,7 @@ class BatchedSweep:
         self.d2h_bytes = (n_rows if self.reduce else self.n_samples) * self.n_obs * self.B * item
         self.launches_per_run = 0
         self._static_ready = False
+        self.timing["alloc_s"] = time.perf_counter() - t_alloc       # device buffers + pinned host buffers (the result!)
 
     # ------------------------------------------------------------------ pieces
     def stage_params(self, table: np.ndarray):

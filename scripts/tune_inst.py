@@ -11,7 +11,10 @@ sweep = [("u", 0), ("weight_v2", 0), ("weight_v2", 1), ("weight", 0), ("weight_v
 B, steps, ss = 2**20, 1000, 10
 Cv = np.linspace(68, 1350, B); u = np.linspace(120, 320, B)
 out_ref = None
-for block, mb, fm in [(128, 5, False), (64, 7, True), (64, 8, True), (64, 9, True), (96, 6, True), (32, 16, True), (32, 18, True), (64, 6, True)]:
+SHAPES = [(64, 7, True), (64, 8, True), (64, 10, True), (128, 4, True), (128, 5, True), (96, 6, True), (32, 16, True), (32, 20, True), (256, 2, True)]
+if len(sys.argv) > 1:
+    SHAPES = [tuple(int(x) for x in a.split("x")) + (True,) for a in sys.argv[1:]]
+for block, mb, fm in SHAPES:
     m = InstanceModel(prog, solver="rk4", sweep=sweep, observers=[0], block=block, const_div_to_mul=True, min_blocks=mb, fast_math=fm)
     vals = {("u", 0): u, ("weight_v2", 0): Cv, ("weight_v2", 1): Cv/4, ("weight", 0): 0.8*Cv, ("weight_v1", 0): Cv/4}
     params = np.stack([vals[(p.arg, p.elem)] for p in m.rhs.params])

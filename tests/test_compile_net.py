@@ -141,9 +141,10 @@ def test_multi_gpu_exchange_regions_cover_every_shared_store():
     barrier — the emitter must list an unpack call for each stored region, with this rank's row bounds, and no
     system-scope fence may remain on the data path."""
     import re
-    cases = {"kuramoto_n128": ["prb_ll_unpack(C, 0LL, 128LL,", "prb_ll_unpack(C, 128LL, 128LL,", "prb_stage_target<STAGE>(C) + 0LL"],
-             "qsfa_both_n96": ["prb_ll_unpack_ring(C,", "prb_stage_target<STAGE>(C) + 1056LL"],
-             "jrc_2delay": ["prb_ll_unpack_scatter(C,"], "net13": ["prb_ll_unpack_scatter(C,"]}
+    cases = {"kuramoto_n128": ["prb_ll_fetch(C, 0LL, q - 0LL, 32LL, 32LL)", "prb_ll_fetch(C, 128LL, q - 96LL, 32LL, 32LL)",
+                               "prb_stage_target<STAGE>(C) + 0LL"],
+             "qsfa_both_n96": ["prb_ll_fetch_ring(C,", "prb_stage_target<STAGE>(C) + 1056LL"],
+             "jrc_2delay": ["prb_ll_fetch_scatter(C,"], "net13": ["prb_ll_fetch_scatter(C,"]}
     for name, needles in cases.items():
         prog = Program.load(golden_path(name))
         m = NetworkModel(prog, solver="heun", rank=1, world=4)
@@ -152,16 +153,30 @@ def test_multi_gpu_exchange_regions_cover_every_shared_store():
         for n in needles:
             assert n in body, (name, n)
         n_dy = len(re.findall(r"prb_emit_k<STAGE>\(", body))
-        assert len(re.findall(r"prb_ll_unpack\(C, prb_stage_target<STAGE>", body)) == n_dy       # one region per dy store
-        lo, hi = [(0, 32), (32, 64), (64, 96), (96, 128)][1] if name == "kuramoto_n128" else (None, None)
-        if lo is not None:
-            assert f"128LL, {lo}LL, {hi}LL);" in body
-        # every unpack precedes the barrier of its phase: no store region is left pending behind the last barrier call
-        assert body.rstrip().endswith("}") and "prb_ll_unpack" in body.split("prb_grid_barrier(C);")[-1]
+        assert len(re.findall(r"prb_ll_fetch\(C, prb_stage_target<STAGE>", body)) == n_dy       # one region per dy store
+        # every fetch loop precedes the barrier of its phase; the last phase's regions are fetched before prb_eval returns
+        assert body.rstrip().endswith("}") and "prb_ll_fetch" in body.split("prb_grid_barrier(C);")[-1]
+        assert body.count("// fetch what the peers own") == m.kernel.n_phases
         assert "__threadfence_system" not in src and m.kernel.ll_slots > 0
         assert m.module.cubin[:4] == b"\x7fELF"
     single = NetworkModel(Program.load(golden_path("kuramoto_n128")), solver="heun")
-    assert "prb_ll_unpack(C" not in single.kernel.source[single.kernel.source.rindex("template <int STAGE> __device__ void prb_eval"):]
+    assert "prb_ll_fetch" not in single.kernel.source[single.kernel.source.rindex("template <int STAGE> __device__ void prb_eval"):]
+
+
+def test_few_rows_per_gpu_share_a_row_between_warps():
+    """Row splitting (emit_net.row_split): a shard with fewer rows than warps gives every row to S consecutive warps of a CTA
+    (partial sums through shared memory); enough rows -> the classic warp-per-row loop.  Both forms build for sm_100a."""
+    import bench_configs as bc
+    prog = bc.make_c3(2048)
+    one = NetworkModel(prog, solver="euler")                               # 2048 rows on 2368 warps: warp per row
+    assert "warp per row" in one.kernel.source and "warps per row" not in one.kernel.source
+    eight = NetworkModel(prog, solver="euler", rank=3, world=8)            # 256 rows per GPU: 8 warps per row
+    assert "// 8 warps per row, n = 2048 (256 rows on this GPU)" in eight.kernel.source
+    assert "prb_part0_2048[1][16]" in eight.kernel.source and eight.module.cubin[:4] == b"\x7fELF"
+    off = NetworkModel(prog, solver="euler", rank=3, world=8, split_rows=False, dot_deep=False)
+    assert "warps per row" not in off.kernel.source and "#define PRB_DOT_DEEP 0" in off.kernel.source
+    c4 = NetworkModel(bc.make_c4(1024), solver="heun")                      # two dots per row, 1024 rows: 2 warps per row
+    assert "// 2 warps per row, n = 1024" in c4.kernel.source and c4.module.cubin[:4] == b"\x7fELF"
 
 
 def test_device_generated_connectivity_twin_and_constant_layout():
