@@ -216,15 +216,35 @@ def ipc_close(ptr: int):
 
 
 class PinnedBuffer:
-    """Pinned host memory exposed as a NumPy array (for async H2D/D2H in the end-to-end path)."""
+    """Pinned host memory exposed as a NumPy array (for async H2D/D2H in the end-to-end path).
+
+    Small buffers come from ``cuMemHostAlloc``.  Large ones (>= 64 MiB: the multi-GB result array of a sweep) are an
+    anonymous mapping advised to transparent huge pages, first-touched by a few threads and then page-locked with
+    ``cuMemHostRegister``: measured on the B200 box for the 8.39 GB result of the 2^20-instance sweep, 3.35 s for
+    cuMemHostAlloc vs 0.3 s registration + the (parallel) first touch, same 56 GB/s D2H rate
+    (profiles/r02_pinned_probe.txt).  ``PRB_PINNED=cuda`` forces the driver allocator."""
+
+    HUGE_MIN = 64 << 20
 
     def __init__(self, shape, dtype):
         self.shape, self.dtype = tuple(shape), np.dtype(dtype)
         self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
-        p = C.c_void_p()
-        _check(lib().prb_host_alloc(C.byref(p), max(self.nbytes, 1)))
-        self.ptr = p.value
-        self._raw = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self._map = None
+        n = max(self.nbytes, 1)
+        if n >= self.HUGE_MIN and os.environ.get("PRB_PINNED", "hugepage") != "cuda":
+            self._map, self.ptr = _map_huge(n)
+            try:
+                _check(lib().prb_host_register(self.ptr, n))
+            except CudaBackendError:
+                self._map.close()
+                self._map = None
+                raise
+            self._raw = (C.c_char * n).from_address(self.ptr)
+        else:
+            p = C.c_void_p()
+            _check(lib().prb_host_alloc(C.byref(p), n))
+            self.ptr = p.value
+            self._raw = (C.c_char * n).from_address(self.ptr)
         self.array = np.frombuffer(self._raw, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
 
     def detach(self) -> np.ndarray:
@@ -232,18 +252,17 @@ class PinnedBuffer:
         (results of a sweep are returned without a second multi-GB host copy)."""
         import weakref
         arr, ptr = self.array, self.ptr
-        weakref.finalize(self._raw, _free_pinned, ptr)
-        self.ptr, self.array, self._raw = None, None, None
+        weakref.finalize(self._raw, _free_pinned, ptr, self._map)
+        self.ptr, self.array, self._raw, self._map = None, None, None, None
         return arr
 
     def free(self):
         if getattr(self, "ptr", None):
             self.array = None
             self._raw = None
-            try:
-                lib().prb_host_free(self.ptr)
-            finally:
-                self.ptr = None
+            ptr, mp = self.ptr, self._map
+            self.ptr, self._map = None, None
+            _free_pinned(ptr, mp)
 
     def __del__(self):
         try:
@@ -252,9 +271,43 @@ class PinnedBuffer:
             pass
 
 
-def _free_pinned(ptr):
+def _map_huge(n: int):
+    """Anonymous private mapping of n bytes, 2 MiB aligned, MADV_HUGEPAGE, first-touched in parallel."""
+    import mmap
+    from concurrent.futures import ThreadPoolExecutor
+    two = 2 << 20
+    mp = mmap.mmap(-1, n + two, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+    base = C.addressof(C.c_char.from_buffer(mp))
+    ptr = (base + two - 1) & ~(two - 1)
     try:
-        lib().prb_host_free(ptr)
+        libc = C.CDLL(None, use_errno=True)
+        libc.madvise.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+        libc.madvise(ptr, n, 14)                                     # MADV_HUGEPAGE (advisory: 4 KB pages work as well)
+    except (OSError, AttributeError):
+        pass
+    view = np.frombuffer(mp, dtype=np.uint8, count=n, offset=ptr - base)
+    workers = max(1, min(8, (os.cpu_count() or 1), n // (256 << 20)))
+    step = -(-n // workers)
+    step += (-step) % two
+
+    def touch(k):
+        view[k * step:min(n, (k + 1) * step):4096] = 0                # the page faults are what costs; NumPy releases the GIL
+    if workers > 1:
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            list(ex.map(touch, range(workers)))
+    else:
+        touch(0)
+    del view
+    return mp, ptr
+
+
+def _free_pinned(ptr, mapping=None):
+    try:
+        if mapping is None:
+            lib().prb_host_free(ptr)
+        else:
+            lib().prb_host_unregister(ptr)
+            mapping.close()
     except Exception:
         pass
 
