@@ -134,8 +134,17 @@ __host__ __device__ constexpr long long prb_tc_tile_off(int rows, int r, int k) 
 // warps >= 4 = epilogue (TMEM -> register accumulators -> generated element-wise tail + solver update).
 // Two TMEM accumulator buffers of BT columns alternate between the MMA issuer and the epilogue warps.
 #ifdef PRB_TC
-#define PRB_TC_A_BYTES (128 * PRB_TC_BK * 4)
-#define PRB_TC_B_BYTES (PRB_TC_BT * PRB_TC_BK * 4)
+// Pipeline granularity PRB_TC_CK (K values per shared-memory stage): a K slab of 32 is stored core-column-major, so its first
+// 16 K values are the contiguous first half of the tile, in the same canonical layout (same LBO / SBO).  Staging half slabs
+// doubles the ring depth inside the same 192 KB: with 256-instance tiles a full-slab stage is 96 KB, i.e. ONE slab in flight
+// behind the one being multiplied — the bulk copies' latency was not covered (r01: tensor pipe and its smem reads both 44 %).
+#ifndef PRB_TC_CK
+#define PRB_TC_CK PRB_TC_BK
+#endif
+static_assert(PRB_TC_BK % PRB_TC_CK == 0 && PRB_TC_CK % 8 == 0, "stage granularity");
+#define PRB_TC_SPLIT (PRB_TC_BK / PRB_TC_CK)
+#define PRB_TC_A_BYTES (128 * PRB_TC_CK * 4)
+#define PRB_TC_B_BYTES (PRB_TC_BT * PRB_TC_CK * 4)
 #define PRB_TC_STAGE_BYTES (2 * PRB_TC_A_BYTES + 2 * PRB_TC_B_BYTES)
 #define PRB_TC_SMEM_BYTES (PRB_TC_NSTAGE * PRB_TC_STAGE_BYTES)
 #define PRB_TC_NCOLS (2 * PRB_TC_BT)
@@ -213,16 +222,16 @@ __device__ __forceinline__ void prb_tc_prep(const long long gtid, const long lon
 // a_* / b_* point at the first slab tile; consecutive slabs are one tile apart.
 __device__ __forceinline__ void prb_tc_produce(PrbTc& T, const float* a_hi, const float* a_lo, const float* b_hi,
                                                const float* b_lo, const int KS) {
-    for (int ks = 0; ks < KS && T.ok; ++ks) {
+    for (int hs = 0; hs < KS * PRB_TC_SPLIT && T.ok; ++hs) {          // consecutive stages are one (part of a) tile apart
         T.ok = prb_mbar_wait(PRB_TC_EMPTY(T, T.s), T.ph ^ 1u, T.err, 101);
         if (!T.ok) break;
         const unsigned int full = PRB_TC_FULL(T, T.s);
         prb_mbar_expect_tx(full, PRB_TC_STAGE_BYTES);
         const unsigned int base = T.smem0 + T.s * PRB_TC_STAGE_BYTES;
-        prb_bulk_g2s(base, a_hi + (long long)ks * (128 * PRB_TC_BK), PRB_TC_A_BYTES, full);
-        prb_bulk_g2s(base + PRB_TC_A_BYTES, a_lo + (long long)ks * (128 * PRB_TC_BK), PRB_TC_A_BYTES, full);
-        prb_bulk_g2s(base + 2 * PRB_TC_A_BYTES, b_hi + (long long)ks * (PRB_TC_BT * PRB_TC_BK), PRB_TC_B_BYTES, full);
-        prb_bulk_g2s(base + 2 * PRB_TC_A_BYTES + PRB_TC_B_BYTES, b_lo + (long long)ks * (PRB_TC_BT * PRB_TC_BK), PRB_TC_B_BYTES, full);
+        prb_bulk_g2s(base, a_hi + (long long)hs * (128 * PRB_TC_CK), PRB_TC_A_BYTES, full);
+        prb_bulk_g2s(base + PRB_TC_A_BYTES, a_lo + (long long)hs * (128 * PRB_TC_CK), PRB_TC_A_BYTES, full);
+        prb_bulk_g2s(base + 2 * PRB_TC_A_BYTES, b_hi + (long long)hs * (PRB_TC_BT * PRB_TC_CK), PRB_TC_B_BYTES, full);
+        prb_bulk_g2s(base + 2 * PRB_TC_A_BYTES + PRB_TC_B_BYTES, b_lo + (long long)hs * (PRB_TC_BT * PRB_TC_CK), PRB_TC_B_BYTES, full);
         if (++T.s == PRB_TC_NSTAGE) { T.s = 0; T.ph ^= 1u; }
     }
 }
@@ -237,7 +246,7 @@ __device__ __forceinline__ void prb_tc_mma(PrbTc& T, const int KS) {
         prb_tc_fence_after();
         const unsigned int tmem_d = T.tmem + T.buf * PRB_TC_BT;
         const int ks1 = (ks0 + PRB_TC_KC < KS) ? ks0 + PRB_TC_KC : KS;
-        for (int ks = ks0; ks < ks1; ++ks) {
+        for (int hs = ks0 * PRB_TC_SPLIT; hs < ks1 * PRB_TC_SPLIT; ++hs) {
             T.ok = prb_mbar_wait(PRB_TC_FULL(T, T.s), T.ph, T.err, 102);
             if (!T.ok) break;
             prb_tc_fence_after();
@@ -245,12 +254,12 @@ __device__ __forceinline__ void prb_tc_mma(PrbTc& T, const int KS) {
             const unsigned int sa_hi = base, sa_lo = base + PRB_TC_A_BYTES;
             const unsigned int sb_hi = base + 2 * PRB_TC_A_BYTES, sb_lo = sb_hi + PRB_TC_B_BYTES;
 #pragma unroll
-            for (int k = 0; k < PRB_TC_BK / 8; ++k) {
+            for (int k = 0; k < PRB_TC_CK / 8; ++k) {
                 const unsigned long long dah = prb_umma_smem_desc(sa_hi + k * 2 * lboA, lboA, sbo);
                 const unsigned long long dal = prb_umma_smem_desc(sa_lo + k * 2 * lboA, lboA, sbo);
                 const unsigned long long dbh = prb_umma_smem_desc(sb_hi + k * 2 * lboB, lboB, sbo);
                 const unsigned long long dbl = prb_umma_smem_desc(sb_lo + k * 2 * lboB, lboB, sbo);
-                prb_umma_tf32(tmem_d, dal, dbh, idesc, (ks != ks0 || k != 0) ? 1u : 0u);     // small terms first
+                prb_umma_tf32(tmem_d, dal, dbh, idesc, (hs != ks0 * PRB_TC_SPLIT || k != 0) ? 1u : 0u);     // small terms first
                 prb_umma_tf32(tmem_d, dah, dbl, idesc, 1u);
                 prb_umma_tf32(tmem_d, dah, dbh, idesc, 1u);
             }

@@ -6,6 +6,8 @@ between) — and splices it into the hand-written solver template ``csrc/templat
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Set, Tuple
 
@@ -306,8 +308,13 @@ def tc_config(ir: NetIR, precision: str, n_batch: int, world: int, tc_max_acc: i
     bt = next((c for c in (256, 128, 64, 32) if n_batch % c == 0 and per_group * c // e <= limit), None)
     if bt is None:
         return None
-    stage = 2 * 128 * 32 * 4 + 2 * bt * 32 * 4
-    return {"bt": bt, "e": e, "nstage": max(2, min(4, (200 * 1024) // stage)), "kc": 8, "block": 128 * (1 + e)}
+    # K values per shared-memory stage: half slabs (16) when a full-slab stage (2 x 16 KB of W + 2 x bt x 128 B of x) would
+    # leave fewer than 3 stages inside ~200 KB, i.e. for the 256-instance tiles
+    ck = 32
+    if (200 * 1024) // (2 * 128 * ck * 4 + 2 * bt * ck * 4) < 3 and os.environ.get("PRB_TC_CK", "16") == "16":
+        ck = 16
+    stage = 2 * 128 * ck * 4 + 2 * bt * ck * 4
+    return {"bt": bt, "e": e, "nstage": max(2, min(4, (200 * 1024) // stage)), "kc": 8, "block": 128 * (1 + e), "ck": ck}
 
 
 def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequence[int], block: int = 512,
@@ -759,6 +766,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
         src.append(f"#define PRB_TC_E {tc['e']}")
         src.append(f"#define PRB_TC_NSTAGE {tc['nstage']}")
         src.append(f"#define PRB_TC_KC {tc['kc']}")
+        src.append(f"#define PRB_TC_CK {tc['ck']}")
         src.append(read_template("tc_gemm.cuh"))
     src.append(read_template("net_kernel.cuh"))
     heads_i, heads_a = [], []
@@ -799,7 +807,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4, "scipy": 6, "rk45": 6}[solver]
     smem = gemm_smem
     if tc is not None:
-        smem = tc["nstage"] * (2 * 128 * 32 * 4 + 2 * tc["bt"] * 32 * 4)
+        smem = tc["nstage"] * (2 * 128 * tc["ck"] * 4 + 2 * tc["bt"] * tc["ck"] * 4)
         tc = dict(tc, smem=smem, xt_elems=tc_work)
     return NetKernel("\n".join(src) + "\n", ns, int(obs.size), (work_size + n_solver_vecs * ns) * nb + tc_work, work_size,
                      pack("work", work_size, real), const_buf, iconst,
