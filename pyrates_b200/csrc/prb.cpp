@@ -66,6 +66,7 @@ std::once_flag g_drv_once;
 std::mutex g_ctx_mu;
 CUcontext g_ctx = nullptr;
 int g_dev = -1;
+std::map<int, CUcontext> g_ctx_of;     // retained primary contexts, one per device ever selected
 
 void load_driver() {
     g_drv.lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
@@ -120,6 +121,7 @@ int need_ctx() {
         CU(cuDeviceGet(&dev, 0));
         CU(cuDevicePrimaryCtxRetain(&g_ctx, dev));
         g_dev = 0;
+        g_ctx_of[0] = g_ctx;
     }
     CUcontext cur = nullptr;
     g_drv.cuCtxGetCurrent(&cur);
@@ -129,12 +131,17 @@ int need_ctx() {
 
 }  // namespace
 
+// A module is a cubin; it is loaded lazily into the context of whichever device is current at launch time, once per
+// device (CudaBackend(device=0) and CudaBackend(device=1) may share one compiled model inside a process).
+struct prb_loaded {
+    CUmodule mod = nullptr;
+    std::map<std::string, CUfunction> funcs;
+};
 struct prb_module {
     std::string name;
     std::string log;
     std::vector<char> cubin;
-    CUmodule mod = nullptr;
-    std::map<std::string, CUfunction> funcs;
+    std::map<int, prb_loaded> on;      // device ordinal -> loaded image
     std::mutex mu;
 };
 
@@ -142,17 +149,18 @@ namespace {
 
 int module_function(prb_module* m, const char* kernel, CUfunction* out) {
     std::lock_guard<std::mutex> lk(m->mu);
-    if (!m->mod) {
+    prb_loaded& L = m->on[g_dev];
+    if (!L.mod) {
         if (m->cubin.empty()) return fail(PRB_ERR_INVALID, "module `%s` holds no cubin", m->name.c_str());
-        CU(cuModuleLoadData(&m->mod, m->cubin.data()));
+        CU(cuModuleLoadData(&L.mod, m->cubin.data()));
     }
-    auto it = m->funcs.find(kernel);
-    if (it == m->funcs.end()) {
+    auto it = L.funcs.find(kernel);
+    if (it == L.funcs.end()) {
         CUfunction f;
-        CUresult r = g_drv.cuModuleGetFunction(&f, m->mod, kernel);
+        CUresult r = g_drv.cuModuleGetFunction(&f, L.mod, kernel);
         if (r != CUDA_SUCCESS)
             return fail(PRB_ERR_NOT_FOUND, "kernel `%s` not found in module `%s`", kernel, m->name.c_str());
-        it = m->funcs.emplace(kernel, f).first;
+        it = L.funcs.emplace(kernel, f).first;
     }
     *out = it->second;
     return PRB_OK;
@@ -182,10 +190,16 @@ int prb_set_device(int ordinal) {
     if (int e = need_driver()) return e;
     std::lock_guard<std::mutex> lk(g_ctx_mu);
     if (g_ctx && g_dev == ordinal) return g_drv.cuCtxSetCurrent(g_ctx) == CUDA_SUCCESS ? PRB_OK : fail(PRB_ERR_CUDA, "cuCtxSetCurrent");
-    CUdevice dev;
-    CU(cuDeviceGet(&dev, ordinal));
-    CUcontext ctx;
-    CU(cuDevicePrimaryCtxRetain(&ctx, dev));
+    CUcontext ctx = nullptr;
+    auto it = g_ctx_of.find(ordinal);
+    if (it != g_ctx_of.end()) {
+        ctx = it->second;                       // retained once per device: switching back and forth leaks nothing
+    } else {
+        CUdevice dev;
+        CU(cuDeviceGet(&dev, ordinal));
+        CU(cuDevicePrimaryCtxRetain(&ctx, dev));
+        g_ctx_of[ordinal] = ctx;
+    }
     CU(cuCtxSetCurrent(ctx));
     g_ctx = ctx;
     g_dev = ordinal;
@@ -280,7 +294,18 @@ int prb_module_log(const prb_module* m, const char** log) {
 
 int prb_module_free(prb_module* m) {
     if (!m) return PRB_OK;
-    if (m->mod && g_drv.ok) g_drv.cuModuleUnload(m->mod);
+    if (g_drv.ok) {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        CUcontext cur = nullptr;
+        g_drv.cuCtxGetCurrent(&cur);
+        for (auto& kv : m->on) {
+            auto c = g_ctx_of.find(kv.first);
+            if (!kv.second.mod || c == g_ctx_of.end()) continue;
+            g_drv.cuCtxSetCurrent(c->second);   // a module is unloaded in the context that loaded it
+            g_drv.cuModuleUnload(kv.second.mod);
+        }
+        if (cur) g_drv.cuCtxSetCurrent(cur);
+    }
     delete m;
     return PRB_OK;
 }

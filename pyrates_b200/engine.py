@@ -227,15 +227,20 @@ class InstanceSession:
         a.slots, a.rings, a.tables = self.d_slots.ptr, self.d_rings.ptr, self.d_tables.ptr
         a.consts = a.iconsts = a.work = a.sync = None
         if self.d_hist is not None:
-            hdt = self.m.rhs.hist_dt
-            if abs(float(dt) - hdt) > 1e-9 * hdt:
-                raise rt.CudaBackendError(f"this delay-differential vector field was generated for step_size={hdt!r} (its history "
-                                          f"lookups are `hist(t*{hdt!r} - d)`); got dt={dt!r}")
+            self._check_hist_dt(dt)
             a.work = self.d_hist.ptr
         self.m.module.run(k.kernel_name, a, block=k.block, stream=self.stream)
         self.steps_done += int(n_steps)
         self.samples_done += new_samples
         return new_samples
+
+    def _check_hist_dt(self, dt: float):
+        """Delay-differential models, fixed-step solvers: the generated history lookups `hist(t*dt - d)` carry the step size
+        the vector field was built for; integrating with another one would silently interpolate a wrong history."""
+        hdt = self.m.rhs.hist_dt
+        if abs(float(dt) - hdt) > 1e-9 * hdt:
+            raise rt.CudaBackendError(f"this delay-differential vector field was generated for step_size={hdt!r} (its history "
+                                      f"lookups are `hist(t*{hdt!r} - d)`); got dt={dt!r}")
 
     REDUCE_STATS = ("mean", "var", "min", "max", "last")
 
@@ -259,6 +264,7 @@ class InstanceSession:
         a.slots, a.rings, a.tables = self.d_slots.ptr, self.d_rings.ptr, self.d_tables.ptr
         a.consts = a.iconsts = a.work = a.sync = None
         if self.d_hist is not None:
+            self._check_hist_dt(dt)
             a.work = self.d_hist.ptr
         self.m.module.run(k.kernel_name, a, block=k.block, stream=self.stream)
         self.steps_done = int(n_steps)
@@ -292,6 +298,10 @@ class InstanceSession:
         rtol = max(float(rtol), 100 * np.finfo(float).eps)          # validate_tol, scipy/integrate/_ivp/common.py
         te_step = (float(T) - 0.0) / n_samples if n_samples else 0.0   # numpy.linspace: step = delta / div
         opts = np.array([rtol, float(atol), self.m.t0, float(T), float(dt), te_step, float(max_step), float(max_attempts)])
+        for name in ("d_opts", "d_status"):                     # buffers of an earlier launch_adaptive call
+            old = getattr(self, name, None)
+            if old is not None:
+                old.free()
         self.d_opts = rt.DeviceBuffer.from_host(opts)
         self.d_status = rt.DeviceBuffer(4 * self.B)
         self.d_status.zero(self.stream)
@@ -337,6 +347,8 @@ class InstanceSession:
         self.d_y.download(y_start, self.stream)
         if self.stream is not None:
             self.stream.synchronize() if hasattr(self.stream, "synchronize") else rt.synchronize()
+        if getattr(self, "d_status", None) is not None:
+            self.d_status.free()
         self.d_status = rt.DeviceBuffer(4 * B)
         while True:
             if capacity * (1 + k.n_hist) * B * 8 > max_capacity_bytes:

@@ -236,6 +236,8 @@ class NetworkSession:
         opts = np.zeros(16)
         opts[:8] = [rtol, float(atol), self.m.t0, float(T), float(dt), (float(T) / n_samples) if n_samples else 0.0,
                     float(max_step), float(max_attempts)]
+        if getattr(self, "d_opts", None) is not None:           # buffer of an earlier launch_adaptive call
+            self.d_opts.free()
         self.d_opts = rt.DeviceBuffer.from_host(opts)
         self.d_sync.zero(self.stream)
         a = rt.KernelArgs()
