@@ -12,8 +12,16 @@ timeout 1200 $TR --master-port 29522 bench.py --gpus $N > gpurun_out/r02_bench_n
 echo "bench rc=$?"; tail -c 400 gpurun_out/r02_bench_n$N.err
 python - <<PY
 import json
-d=json.load(open('gpurun_out/r02_bench_n$N.json'))
+d=[json.loads(l) for l in open('gpurun_out/r02_bench_n$N.json') if l.startswith('{')][-1]
 print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e'].get('d2h_ceiling_gbs'), d['e2e'].get('frac_of_ceiling'), 'red', d['e2e_reduced']['value'], 'jit', d['jit_s'], 'alloc', d['alloc_s'])
 print('strong', d.get('strong_scaling'))
 for k,v in d.get('configs',{}).items(): print(k, v.get('value'), v.get('us_per_solver_step', v.get('ms_per_solver_step')), v.get('roofline',{}).get('frac'), v.get('error'))
 PY
+if [ "$N" = "8" ]; then
+  # small networks across 8 GPUs (latency regime): N = 2048 / 1024 dense WC, QIF-SFA 2 x 1024
+  for cfg in "c3 2048 euler 2000" "c3 1024 euler 2000" "c3 4096 rk4 500" "c3 16384 euler 200"; do
+    set -- $cfg
+    timeout 300 $TR --master-port 29523 bench_configs.py --config $1 --size $2 --solver $3 --steps $4 --check --cpu-steps 5 >> gpurun_out/r02_cfg_n8.jsonl 2>> gpurun_out/r02_cfg_n8.err
+  done
+  cut -c1-260 gpurun_out/r02_cfg_n8.jsonl
+fi
