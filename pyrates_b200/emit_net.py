@@ -20,6 +20,9 @@ from .scalarize import UnsupportedModelError
 
 __all__ = ["NetKernel", "emit_net_kernel"]
 
+FULL_TWO_LEVEL = 8192        # full reductions at least this long run in two levels (partials per CTA + grid barrier)
+FULL_PART_STRIDE = 256       # partial slots per rank: the persistent grid has one CTA per SM (148 on B200), never more than this
+
 
 @dataclass
 class NetKernel:
@@ -374,12 +377,19 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 const_fills.append((a.offset, a.init.astype(np.float32 if f32 else np.float64), lo, hi))
         if not lazy_arrays:
             const_host = const_size
+    full_part: Dict[int, MemArray] = {}
     for red in ir.reductions:
         if red.kind == "row":
             arr = MemArray(f"__red{red.id}", "work", (red.n,), work_size, np.zeros(red.n))
             work_size += ((red.n + 31) // 32) * 32
             ir.arrays[arr.name] = arr
             em.red_work[red.id] = arr
+        elif nb == 1 and red.m >= FULL_TWO_LEVEL:
+            # per-CTA partial sums of a two-level full reduction: FULL_PART_STRIDE slots per rank (grid <= 256 CTAs)
+            arr = MemArray(f"__part{red.id}", "work", (world * FULL_PART_STRIDE,), work_size, np.zeros(world * FULL_PART_STRIDE))
+            work_size += world * FULL_PART_STRIDE
+            ir.arrays[arr.name] = arr
+            full_part[red.id] = arr
     # observer index table goes to the end of iconsts
     obs = np.asarray(list(observers), dtype=np.int32)
     all_state = obs.size == ns and np.array_equal(obs, np.arange(ns))
@@ -408,8 +418,40 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     n_phases = ir.n_phases
     for p in range(n_phases):
         body.append(f"    // ---------------- phase {p}")
-        # (1) full reductions, block-redundant
-        for r in [r for r in full_reds if r.phase == p]:
+        # (1) full reductions.  Long ones (one instance, m >= FULL_TWO_LEVEL) run in two levels: every CTA of every rank sums
+        # its share of the rows this rank owns and publishes ONE partial (multi-GPU: as an LL packet to the peers), a grid
+        # barrier, then every CTA adds the world x 256 partials — instead of every CTA walking the whole vector (N = 65536:
+        # 148 x 512 KB of L2 reads per evaluation) and, across GPUs, instead of every rank reducing its complete replica.
+        two_level = [r for r in full_reds if r.phase == p and nb == 1 and r.m >= FULL_TWO_LEVEL]
+        for r in two_level:
+            cur = (p, -1, False)
+            emitted = set()
+            nodes = em.order([r.node])
+            part = full_part[r.id]
+            lo, hi = em.bounds(r.m)
+            body.append(f"    {{   // full reduction {r.id}, level 1: rows {lo}..{hi} of {r.m}, one partial per CTA")
+            body.append("        real acc = (real)0;")
+            body.append(f"        for (long long j = {lo}LL + C.gtid; j < {hi}LL; j += C.gsize) {{")
+            body.extend(em.emit_nodes(nodes, cur, emitted, "            "))
+            body.append(f"            acc += {em.ref(r.node, cur)};")
+            body.append("        }")
+            body.append("        acc = prb_block_sum(acc);")
+            body.append(f"        if (threadIdx.x == 0) prb_st_work(C, {part.offset + rank * FULL_PART_STRIDE}LL + blockIdx.x, acc);")
+            body.append(f"        if (blockIdx.x == 0 && threadIdx.x >= gridDim.x && threadIdx.x < {FULL_PART_STRIDE})   // unused slots: zeros")
+            body.append(f"            prb_st_work(C, {part.offset + rank * FULL_PART_STRIDE}LL + threadIdx.x, (real)0);")
+            body.append("    }")
+            em.note_work(part.offset, world * FULL_PART_STRIDE)
+        if two_level:
+            body.extend(em.flush())
+            body.append("    prb_grid_barrier(C);")
+            for r in two_level:
+                part = full_part[r.id]
+                body.append(f"    {{   // level 2: sum of the {world} x {FULL_PART_STRIDE} partials")
+                body.append("        real acc = (real)0;")
+                body.append(f"        for (int q = threadIdx.x; q < {world * FULL_PART_STRIDE}; q += blockDim.x) acc += C.work[{part.offset}LL + q];")
+                body.append(f"        red{r.id} = prb_block_sum(acc);")
+                body.append("    }")
+        for r in [r for r in full_reds if r.phase == p and r not in two_level]:
             cur = (p, -1, False)
             emitted: Set[int] = set()
             nodes = em.order([r.node])

@@ -115,6 +115,8 @@ class NetworkSession:
         self.d_rings = rt.DeviceBuffer(max(k.ring_init.size * B, 1) * item)
         self.d_sync = rt.DeviceBuffer(8 * 16)
         self.sm_count = rt.device_info()["sm_count"]
+        if self.sm_count * model.blocks_per_sm > 256 and "__part" in "".join(model.ir.arrays):
+            raise rt.CudaBackendError("two-level full reductions hold 256 per-CTA partials per rank; the persistent grid is larger")
         self.steps_done = 0
         self.samples_done = 0
         self.d_peers = None

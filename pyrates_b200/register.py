@@ -289,7 +289,7 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
         except UnsupportedModelError as e:
             if exec_model == "instance" or "too large" not in str(e):
                 raise
-    timings["alloc_s"] = sw.timing["alloc_s"] if sw is not None else 0.0      # device + pinned result buffers
+    timings["alloc_s"] = getattr(sw, "timing", {}).get("alloc_s", 0.0) if sw is not None else 0.0   # device + pinned buffers
     timings["jit_s"] = time.perf_counter() - t_jit - timings["alloc_s"]       # lowering + NVRTC / cubin cache
     if sw is None and reduce:
         raise NotImplementedError("reduce=True is implemented for sweeps of the instance execution model")

@@ -66,6 +66,7 @@ class FakeBatched:
         self.B, self.T, self.dt, self.dts = n_inst, T, dt, dts
         self.h_y0 = types.SimpleNamespace(array=np.zeros((self.model.n_state, n_inst)))
         self.n_obs = len(observers)
+        self.timing = {"lower_s": 0.0, "alloc_s": 0.0}
         stats["models"].append(("BatchedSweep", solver, prog.n_state, prog.float_precision))
     def run(self, table):
         stats["grid"] += 1

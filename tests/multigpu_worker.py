@@ -49,6 +49,8 @@ def main():
         r = fx["run"]
         cases.append((name, Program.load(golden_path(name)), solver, r["T"], r["dt"], r["dts"], 1e-9))
     cases.append(("c4_qsfa_2x512_heun", bc.make_c4(512), "heun", 10e-3, 1e-3, None, 1e-9))
+    # global vsum coupling over a long vector: two-level reduction, per-CTA partials of every rank exchanged as LL packets
+    cases.append(("c5a_vsum_n8192_rk4", bc.make_c5a(8192), "rk4", 20e-3, 1e-3, None, 1e-9))
     worst = {}
     ok = True
     for name, prog, solver, T, dt, dts, tol in cases:

@@ -202,3 +202,20 @@ def test_device_generated_connectivity_twin_and_constant_layout():
         assert off == k.const_init.size and k.const_elems == off + (hi - lo) * 128 and (lo, hi) == ((0, 128) if world == 1 else (96, 128))
     from pyrates_b200.devgen import _fill_module
     assert _fill_module("float32").cubin[:4] == b"\x7fELF"
+
+
+def test_long_full_reductions_run_in_two_levels():
+    """`sum(x)` over >= 8192 elements: per-CTA partial sums + one grid barrier + sum of the partials, instead of every CTA
+    walking the whole vector; across GPUs each rank reduces only the rows it owns and the partials travel as LL packets."""
+    import bench_configs as bc
+    short = NetworkModel(Program.load(golden_path("kuramoto_scalar_n128")), solver="euler")
+    assert "level 1" not in short.kernel.source
+    prog = bc.make_c5a(8192)
+    one = NetworkModel(prog, solver="euler")
+    body = one.kernel.source[one.kernel.source.rindex("template <int STAGE> __device__ void prb_eval"):]
+    assert "level 1: rows 0..8192 of 8192" in body and "level 2: sum of the 1 x 256 partials" in body and body.count("prb_grid_barrier(C);") == 1
+    four = NetworkModel(prog, solver="euler", rank=2, world=4)
+    body = four.kernel.source[four.kernel.source.rindex("template <int STAGE> __device__ void prb_eval"):]
+    assert "level 1: rows 4096..6144 of 8192" in body and "level 2: sum of the 4 x 256 partials" in body
+    assert "prb_ll_fetch(C, 0LL, q - 0LL, 512LL, 256LL)" in body        # partials of ranks 0, 1 | 3 around this rank's 256 slots
+    assert four.module.cubin[:4] == b"\x7fELF"

@@ -104,6 +104,17 @@ def test_c5_kuramoto_n4096_vs_oracle_pair_space(gpu):
     assert traj_rel_err(out[:, :, 0], ref) <= 1e-9, how
 
 
+def test_c5a_global_vsum_n65536_two_level_reduction(gpu):
+    """Scalar all-to-all weight -> `weight * sum(theta)` (pyrates/ir/circuit.py:752-761) at the named size: the full
+    reduction runs in two levels (one partial per CTA, grid barrier, sum of the partials)."""
+    prog, how = bc.build_program("c5a", 65536, front_end="resized")
+    m = NetworkModel(prog, solver="rk4")
+    assert "level 2: sum of the 1 x 256 partials" in m.kernel.source
+    ref = _oracle(prog, 5e-3, 1e-3, "rk4")
+    out, _ = m.run(5e-3, 1e-3, None)
+    assert traj_rel_err(out[:, :, 0], ref) <= 1e-9, how
+
+
 def test_c5_device_generated_connectivity_equals_its_numpy_twin(gpu):
     """The N = 65536 bench generates W on the device (devgen.DeviceUniform): same program with the generator's NumPy twin
     uploaded from the host must give bit-identical trajectories, and the oracle (fed the twin) agrees at 1e-9."""
