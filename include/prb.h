@@ -75,9 +75,13 @@ enum { PRB_SOLVER_EULER = 0, PRB_SOLVER_HEUN_REF = 1, PRB_SOLVER_HEUN = 2, PRB_S
  *                                  [depth][n_hist][B] of past states, PRB_SOLVER_DOPRI5 times [cap][B] + states [cap][n_hist][B]
  *   out (reduce kernels)           [5][n_obs][B]: mean, var, min, max, last of the observers over the samples >= sample0
  *   sync                           network-mode barrier words, 64-bit each (zero-initialised by the caller):
- *                                  [0] local CTA arrivals, [1] release epoch, [2] error flag, [8+q] arrival epoch of rank q
- *   peers                          multi-GPU network mode: device array of 3*world pointers
- *                                  {work[0..world), rings[0..world), sync[0..world)} of all ranks (IPC-mapped)
+ *                                  [0] local CTA arrivals, [2] error flag (a bounded wait timed out; peers set it remotely)
+ *   peers                          multi-GPU network mode (rows sharded, one process per GPU): device array of 2*world
+ *                                  pointers {mirror[0..world), sync[0..world)} of all ranks (IPC-mapped; entry `rank` is the
+ *                                  caller's own).  A mirror holds two parities of one 16-byte packet slot per work / ring
+ *                                  element + 32 heartbeat slots: owners send {lo32, tag, hi32, tag} packets into their peers'
+ *                                  mirrors, receivers unpack them into their replicas before each grid barrier
+ *                                  (csrc/templates/net_kernel.cuh: prb_ll_*); zero-initialised by the caller before a launch
  */
 typedef struct prb_kernel_args {
     int64_t n_steps;      /* solver steps to perform in this launch */

@@ -410,6 +410,16 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
     prb_thread_exit(T, A, b);
 }
 #else
+#ifdef PRB_Y_SMEM
+__device__ __forceinline__ real prb_ysm_ld(const PrbThread& T, const int j) {
+    real v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(T.ysm_s + (unsigned int)(j * PRB_BLOCK * 8)));
+    return v;
+}
+__device__ __forceinline__ void prb_ysm_st(const PrbThread& T, const int j, const real v) {
+    asm volatile("st.shared.f64 [%0], %1;" :: "r"(T.ysm_s + (unsigned int)(j * PRB_BLOCK * 8)), "d"(v) : "memory");
+}
+#endif
 // One solver step y -> yn.  SPEC (fast_math kernels of pure vector fields, PRB_SPEC_STEP): every stage runs the speculative
 // rhs, which only ORs range violations of its exp / reciprocal arguments into `bad`; the caller looks at the flag once per
 // step and recomputes the step with the exact rhs (prb_step_exact) in the rare case it is set — the stages of a step stay one
@@ -447,6 +457,27 @@ __device__ __forceinline__ void prb_step(const long long t, const real (&y)[PRB_
     prb_stage<SPEC>(t, ys, k2, T, bad);
     PRB_UNROLL_NS
     for (int j = 0; j < PRB_NS; ++j) yn[j] = y[j] + hdt * (k[j] + k2[j]);
+#elif PRB_SOLVER == PRB_SOLVER_RK4 && defined(PRB_Y_SMEM)
+    // Register-lean variant (opt-in, PRB_Y_SMEM): the base state y lives in shared memory ([state][thread], one 8-byte word
+    // per thread and state variable: conflict-free) and is re-read where a stage needs it, so that only the stage input, the
+    // accumulator and the fresh derivatives are live across an evaluation.  `y` / `yn` are unused here: the caller passes
+    // the shared-memory column of this thread.
+    real ys[PRB_NS], acc[PRB_NS];
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) ys[j] = prb_ysm_ld(T, j);
+    prb_stage<SPEC>(t, ys, k, T, bad);                      // k1
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) { acc[j] = k[j]; ys[j] = prb_ysm_ld(T, j) + hdt * k[j]; }
+    prb_stage<SPEC>(t, ys, k, T, bad);                      // k2
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) { acc[j] = acc[j] + (real)2 * k[j]; ys[j] = prb_ysm_ld(T, j) + hdt * k[j]; }
+    prb_stage<SPEC>(t, ys, k, T, bad);                      // k3
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) { acc[j] = acc[j] + (real)2 * k[j]; ys[j] = prb_ysm_ld(T, j) + dt * k[j]; }
+    prb_stage<SPEC>(t, ys, k, T, bad);                      // k4
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) yn[j] = prb_ysm_ld(T, j) + dt6 * (acc[j] + k[j]);
+    (void)y;
 #elif PRB_SOLVER == PRB_SOLVER_RK4
     real ys[PRB_NS], acc[PRB_NS];
     prb_stage<SPEC>(t, y, k, T, bad);                       // k1
@@ -490,6 +521,12 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
     real y[PRB_NS];
     PRB_UNROLL_NS
     for (int j = 0; j < PRB_NS; ++j) y[j] = Y[(long long)j * B + b];
+#ifdef PRB_Y_SMEM
+    __shared__ real prb_ysm[PRB_NS][PRB_BLOCK];
+    T.ysm_s = (unsigned int)__cvta_generic_to_shared(&prb_ysm[0][threadIdx.x]);
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) prb_ysm_st(T, j, y[j]);
+#endif
 
     real* __restrict__ out = (real*)A.out;
     const real dt = (real)A.dt;
@@ -532,6 +569,10 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
                 }
             }
 #else
+#ifdef PRB_Y_SMEM
+            PRB_UNROLL_NS
+            for (int j = 0; j < PRB_NS; ++j) y[j] = prb_ysm_ld(T, j);
+#endif
             prb_record(y, out + sample * (long long)PRB_NOBS * B, b, B);
 #endif
             ++sample;
@@ -547,8 +588,13 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
 #else
         prb_step<false>(t, y, yn, T, dt, hdt, dt6, bad);
 #endif
+#ifdef PRB_Y_SMEM
+        PRB_UNROLL_NS
+        for (int j = 0; j < PRB_NS; ++j) prb_ysm_st(T, j, yn[j]);
+#else
         PRB_UNROLL_NS
         for (int j = 0; j < PRB_NS; ++j) y[j] = yn[j];
+#endif
 #if PRB_NH > 0
         prb_hist_push(T, y, A.step0 + i + 1);        // DDEHistory.update((i + 1) * dt, y)
 #endif
@@ -563,6 +609,10 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
         out[(3LL * PRB_NOBS + o) * B + b] = r_max[o];
         out[(4LL * PRB_NOBS + o) * B + b] = r_last[o];
     }
+#endif
+#ifdef PRB_Y_SMEM
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) y[j] = prb_ysm_ld(T, j);
 #endif
     PRB_UNROLL_NS
     for (int j = 0; j < PRB_NS; ++j) Y[(long long)j * B + b] = y[j];

@@ -339,7 +339,7 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
 def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: Sequence[int],
                      block: int = 128, const_div_to_mul: bool = False, min_blocks: int = 1,
                      fast_math: bool = False, rk_method: str = "RK45", reduce: bool = False,
-                     hist_max_delay: Optional[float] = None) -> InstKernel:
+                     hist_max_delay: Optional[float] = None, y_smem: bool = False) -> InstKernel:
     """Generate the full CUDA C source of the fused rhs+solver instance kernel.  ``reduce``: the kernel keeps running
     statistics of the observers (mean, var, min, max, last) instead of storing every sample (fixed-step solvers)."""
     if solver not in SOLVER_IDS:
@@ -428,6 +428,10 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     src.append(f"#define PRB_SOLVER {SOLVER_IDS[solver]}")
     src.append(f"#define PRB_BLOCK {block}")
     src.append(f"#define PRB_MIN_BLOCKS {int(min_blocks)}")
+    if y_smem:
+        if solver != "rk4" or precision != "float64" or reduce or n_hist:
+            raise ValueError("y_smem is implemented for the float64 fixed-step rk4 kernels without reduce / history")
+        src.append("#define PRB_Y_SMEM 1")
     if reduce:
         if adaptive:
             raise UnsupportedModelError("on-device observer reduction is implemented for the fixed-step solvers")
@@ -456,6 +460,7 @@ struct PrbThread {
     const real* __restrict__ tables;
     const double* etab;            // shared-memory copy of PRB_EXP_TAB (fast_math kernels)
     unsigned int etab_s;           // the same as a 32-bit shared-window address (ld.shared without S2UR per use)
+    unsigned int ysm_s;            // PRB_Y_SMEM: shared-window address of this thread's column of the base state
 #if PRB_NH > 0
 #if PRB_HDEPTH > 0                 // fixed-step history: ring [PRB_HDEPTH][PRB_NH][B] of the states after steps 0..hn
     real* __restrict__ hist;

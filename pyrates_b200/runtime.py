@@ -15,7 +15,7 @@ from typing import Dict, Optional, Sequence, Tuple
 import numpy as np
 
 __all__ = ["CudaBackendError", "lib", "Module", "DeviceBuffer", "compile_module", "KernelArgs", "RunDesc",
-           "device_info", "launch_count", "Stream", "Event", "synchronize", "PinnedBuffer", "set_device"]
+           "device_info", "launch_count", "Stream", "Event", "synchronize", "PinnedBuffer", "set_device", "release_pinned_pool"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libprb.so")
@@ -225,6 +225,7 @@ class PinnedBuffer:
     (profiles/r02_pinned_probe.txt).  ``PRB_PINNED=cuda`` forces the driver allocator."""
 
     HUGE_MIN = 64 << 20
+    _map_bytes: Dict[int, int] = {}          # id(mapping) -> registered bytes
 
     def __init__(self, shape, dtype):
         self.shape, self.dtype = tuple(shape), np.dtype(dtype)
@@ -232,13 +233,18 @@ class PinnedBuffer:
         self._map = None
         n = max(self.nbytes, 1)
         if n >= self.HUGE_MIN and os.environ.get("PRB_PINNED", "hugepage") != "cuda":
-            self._map, self.ptr = _map_huge(n)
-            try:
-                _check(lib().prb_host_register(self.ptr, n))
-            except CudaBackendError:
-                self._map.close()
-                self._map = None
-                raise
+            spare = _take_spare(n)
+            if spare is not None:
+                self._map, self.ptr = spare          # a released result buffer of a previous sweep: already registered
+            else:
+                self._map, self.ptr = _map_huge(n)
+                try:
+                    _check(lib().prb_host_register(self.ptr, n))
+                except CudaBackendError:
+                    self._map.close()
+                    self._map = None
+                    raise
+                self._map_bytes[id(self._map)] = n
             self._raw = (C.c_char * n).from_address(self.ptr)
         else:
             p = C.c_void_p()
@@ -301,13 +307,55 @@ def _map_huge(n: int):
     return mp, ptr
 
 
+# One released huge-page buffer is kept registered for the next sweep of a similar size (repeated grid_search calls: the
+# 8.4 GB result buffer costs ~0.5 s to map, touch and register, nothing to reuse).  PRB_PINNED_POOL=0 disables it.
+_spare = []          # [(mapping, ptr, bytes)] — at most one entry
+_spare_lock = threading.Lock()
+
+
+def _take_spare(n: int):
+    with _spare_lock:
+        if _spare and n <= _spare[0][2] <= 2 * n:
+            mp, ptr, _ = _spare.pop()
+            return mp, ptr
+    return None
+
+
+def release_pinned_pool():
+    """Unregister and unmap the spare pinned buffer (if any)."""
+    with _spare_lock:
+        items, _spare[:] = list(_spare), []
+    for mp, ptr, _ in items:
+        try:
+            lib().prb_host_unregister(ptr)
+            PinnedBuffer._map_bytes.pop(id(mp), None)
+            mp.close()
+        except Exception:
+            pass
+
+
 def _free_pinned(ptr, mapping=None):
     try:
         if mapping is None:
             lib().prb_host_free(ptr)
-        else:
-            lib().prb_host_unregister(ptr)
-            mapping.close()
+            return
+        size = PinnedBuffer._map_bytes.get(id(mapping), 0)
+        if size and os.environ.get("PRB_PINNED_POOL", "1") != "0":
+            with _spare_lock:
+                if not _spare or _spare[0][2] < size:
+                    old, _spare[:] = list(_spare), [(mapping, ptr, size)]
+                    mapping = None
+                else:
+                    old = []
+            for mp, p_, _ in old:
+                lib().prb_host_unregister(p_)
+                PinnedBuffer._map_bytes.pop(id(mp), None)
+                mp.close()
+            if mapping is None:
+                return
+        lib().prb_host_unregister(ptr)
+        PinnedBuffer._map_bytes.pop(id(mapping), None)
+        mapping.close()
     except Exception:
         pass
 
