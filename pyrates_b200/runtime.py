@@ -478,22 +478,28 @@ def _cache_dir() -> Optional[str]:
 
 
 def _compile_shared(key: str, build) -> Optional[Module]:
-    """One NVRTC run for all ranks of a torch.distributed group: rank 0 builds, the cubin is broadcast.  Collective —
-    every rank must call it for the same source (checked: mismatching keys fall back to local compilation)."""
+    """One NVRTC run for all ranks of a torch.distributed group: rank 0 builds (or takes the module from its cache), the
+    cubin is broadcast to the ranks that lack it.  Collective — every rank must call it at the same point; ranks whose
+    source differs (mismatching keys) fall back to local compilation, and the cache state may differ between ranks."""
     try:
         import torch.distributed as dist
     except ImportError:
         return None
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return None
-    keys = [None] * dist.get_world_size()
-    dist.all_gather_object(keys, key)
-    if any(k != key for k in keys):
+    have = key in _module_cache
+    state = [None] * dist.get_world_size()
+    dist.all_gather_object(state, (key, have))
+    if any(k != key for k, _ in state):
         return None
-    box = [build().cubin if dist.get_rank() == 0 else None]
-    dist.broadcast_object_list(box, src=0)
+    if all(h for _, h in state):
+        return _module_cache[key]
+    box = [None]
     if dist.get_rank() == 0:
-        return None                                  # rank 0 keeps the module it just built (caller's cache has it)
+        box[0] = (_module_cache[key] if have else build()).cubin
+    dist.broadcast_object_list(box, src=0)
+    if have or dist.get_rank() == 0:
+        return _module_cache.get(key)               # rank 0: build() put it into the cache
     handle = C.c_void_p()
     _check(lib().prb_module_from_cubin(box[0], len(box[0]), C.byref(handle)))
     return Module(handle.value, "", "")
@@ -508,12 +514,11 @@ def compile_module(source: str, name: str = "prb_kernel.cu", opts: Sequence[str]
         all_opts += ["--ptxas-options=-v"]
     if shared:
         key = hashlib.sha256(("\0".join(all_opts) + "\0" + ARCH + "\0" + _toolchain_tag() + "\0" + source).encode()).hexdigest()
-        if key not in _module_cache:
-            m = _compile_shared(key, lambda: compile_module(source, name, opts, fmad=fmad))
-            if m is not None:
-                m.source = source
-                _module_cache[key] = m
-                return m
+        m = _compile_shared(key, lambda: compile_module(source, name, opts, fmad=fmad))
+        if m is not None:
+            m.source = m.source or source
+            _module_cache[key] = m
+            return m
     key = hashlib.sha256(("\0".join(all_opts) + "\0" + ARCH + "\0" + _toolchain_tag() + "\0" + source).encode()).hexdigest()
     m = _module_cache.get(key)
     if m is not None:

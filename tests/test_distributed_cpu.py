@@ -87,6 +87,12 @@ def _compile_worker(rank, world, port, q):
     m = rt.compile_module(src, "shared.cu", shared=True)          # rank 0 compiles, rank 1 receives the cubin
     # a source only THIS rank has: keys differ -> every rank compiles locally instead of dead-locking
     own = rt.compile_module(f'extern "C" __global__ void k{rank}(float* x) {{ x[0] = {rank}.f; }}', "own.cu", shared=True)
+    # differing cache states: only rank 1 has this module already — the collective must still line up on both ranks
+    src3 = 'extern "C" __global__ void k3(float* x) { x[threadIdx.x] += 1.f; }'
+    if rank == 1:
+        rt.compile_module(src3, "third.cu")
+    third = rt.compile_module(src3, "third.cu", shared=True)
+    assert third.cubin[:4] == b"\x7fELF"
     q.put((rank, bytes(m.cubin), m.log, len(own.cubin)))
     dist.barrier()
     dist.destroy_process_group()
