@@ -129,7 +129,7 @@ class _Emitter:
         op, pl = g.ops[i], g.payload[i]
         if op == "ld":
             r = frozenset(pl[2])
-        elif op == "gather":
+        elif op in ("gather", "ldringg"):
             r = frozenset(pl[3])
         elif op == "ldring":
             r = frozenset(pl[2])
@@ -208,6 +208,14 @@ class _Emitter:
             rows, L = arr.shape
             k = self.ring_index[pl[0]]
             return ("C.rings[" + self.bidx(f"{arr.offset}LL + prb_ring_pos(C.head[{k}], {pl[1] - arr.rolls}, {L}) * {rows}LL + {pl[2]}") + "]")
+        if op == "ldringg":
+            # per-edge delayed read buf[source_idx[e], delays[e]]: the column is addressed relative to the ring head
+            arr, rarr, carr = ir.arrays[pl[0]], ir.arrays[pl[1]], ir.arrays[pl[2]]
+            rows, L = arr.shape
+            k = self.ring_index[pl[0]]
+            col = f"(int){self._load(carr, pl[3])} - {arr.rolls}"
+            row = f"(long long){self._load(rarr, pl[3])}"
+            return ("C.rings[" + self.bidx(f"{arr.offset}LL + prb_ring_pos(C.head[{k}], {col}, {L}) * {rows}LL + {row}") + "]")
         if op == "table":
             arr = ir.arrays[pl[0]]
             col = "i" if pl[2] == "i" else f"{pl[2]}LL"

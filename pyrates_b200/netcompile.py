@@ -242,6 +242,9 @@ class _NetInterp:
                 # only logical column 0 can hold a value written during this evaluation
                 if g.payload[i][1] == 0:
                     ph = max(ph, self.avail.get(g.payload[i][0] + "@0", 0))
+            elif op == "ldringg":
+                if g.payload[i][4]:                       # some edge has delay 0: it reads this evaluation's write
+                    ph = max(ph, self.avail.get(g.payload[i][0] + "@0", 0))
             elif op == "red":
                 ph = max(ph, self.red_phase[g.payload[i][0]])
             elif op == "table":
@@ -279,6 +282,8 @@ class _NetInterp:
                 r = self._leaf("gather", (pl[0], pl[1], pl[2], to))
             elif op == "ldring" and pl[2] == frm:
                 r = self._leaf("ldring", (pl[0], pl[1], to))
+            elif op == "ldringg" and pl[3] == frm:
+                r = self._leaf("ldringg", (pl[0], pl[1], pl[2], to, pl[4]))
             elif op == "red" and frm == "i":
                 raise UnsupportedModelError("internal: reduction result used as reduction source without materialisation")
             elif not a:
@@ -489,7 +494,7 @@ class _NetInterp:
             op, pl = g.ops[i], g.payload[i]
             if op in ("ld", "ldring"):
                 r = frozenset(pl[2])
-            elif op == "gather":
+            elif op in ("gather", "ldringg"):
                 r = frozenset(pl[3])
             elif op == "ldm":
                 r = frozenset("ij")
@@ -622,7 +627,18 @@ class _NetInterp:
             arr = self.arrays[base[1]]
             if isinstance(idx, tuple) and len(idx) == 2 and idx[0] == slice(None, None, None) and isinstance(idx[1], int):
                 return _V(VEC, self._leaf("ldring", (base[1], idx[1] % arr.shape[1], "i")), n=arr.shape[0])
-            raise UnsupportedModelError("network model supports ring reads of the form `buf[:, d]` only")
+            if isinstance(idx, tuple) and len(idx) == 2 and all(isinstance(x, tuple) and x[0] == "index" for x in idx):
+                # legacy per-edge delays (pyrates/ir/circuit.py:598-641): buf[source_idx, delays] gathers, for every edge e,
+                # the value its source wrote delays[e] evaluations ago
+                rows_a, cols_a = self.arrays[idx[0][1]], self.arrays[idx[1][1]]
+                if rows_a.size != cols_a.size:
+                    raise UnsupportedModelError("ring gather with index arrays of different lengths")
+                cols = np.asarray(cols_a.init).reshape(-1)
+                if cols.min() < 0 or cols.max() >= arr.shape[1] or np.asarray(rows_a.init).min() < 0 \
+                        or np.asarray(rows_a.init).max() >= arr.shape[0]:
+                    raise UnsupportedModelError("ring gather indices out of range")
+                return _V(VEC, self._leaf("ldringg", (base[1], idx[0][1], idx[1][1], "i", bool((cols == 0).any()))), n=rows_a.size)
+            raise UnsupportedModelError("network model supports ring reads of the form `buf[:, d]` and `buf[idx, delays]` only")
         if isinstance(base, tuple) and base[0] == "array":
             arr = self.arrays[base[1]]
             if len(arr.shape) != 1:

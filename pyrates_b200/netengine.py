@@ -47,6 +47,9 @@ class NetworkModel:
         self.param_defaults = np.array([d for _, d in self.ir.params], dtype=np.float64)
         self.observers = list(range(prog.n_state)) if observers is None else [int(o) for o in observers]
         self.rank, self.world = int(rank), int(world)
+        if not 0 <= self.rank < self.world or self.world > 32:
+            raise ValueError(f"rank {rank} / world {world}: row-sharded network runs support 1..32 GPUs of one NVLink domain "
+                             f"(32 heartbeat slots in the receive mirror)")
         if tensor_core == "auto":
             tensor_core = self.n_batch > 1 and tc_config(self.ir, self.precision, self.n_batch, self.world) is not None
         self.kernel: NetKernel = emit_net_kernel(self.ir, solver=solver, precision=self.precision,

@@ -44,6 +44,7 @@ def main():
                          ("wc_n128", "heun_true"),
                          ("jrc_grid_b16", "heun"),             # gather / scatter edges of a vectorised circuit
                          ("jrc_2delay", "rk4"),                # scatter stores u[target_idx] = ...
+                         ("net10", "heun"),                    # legacy per-edge delays: gathered ring reads buf[source_idx, delays]
                          ("net13", "euler")):
         fx = orc.load_fixture(golden_path(name))
         r = fx["run"]

@@ -51,9 +51,14 @@ def test_multi_gpu_variants_compile_and_shard_constants(world):
     assert max(sizes) < 0.6 * full if world == 2 else max(sizes) < 0.45 * full      # W rows are sharded
 
 
-def test_legacy_ring_gather_is_rejected_by_network_model():
-    with pytest.raises(UnsupportedModelError):
-        netcompile(Program.load(golden_path("net10")))
+def test_legacy_per_edge_ring_gather_lowers_to_a_head_relative_gather():
+    """`a_buffered = a_buffer[source_idx, a_delays]` (pyrates/ir/circuit.py:598-641, the legacy per-edge delays): one
+    gathered ring read per edge, column = delay relative to the circular head, no barrier (every delay >= 1 reads a column
+    written in an earlier evaluation)."""
+    ir = netcompile(Program.load(golden_path("net10")))
+    assert ir.n_phases == 1 and any(op == "ldringg" for op in ir.graph.ops)
+    m = NetworkModel(Program.load(golden_path("net10")), solver="heun")
+    assert "prb_ring_pos(C.head[0], (int)__ldg(C.iconsts +" in m.kernel.source and m.module.cubin[:4] == b"\x7fELF"
 
 
 @pytest.mark.parametrize("name,sweep,nb,bt", [("wc_n300_f32", ["r_ext"], 256, 256), ("wc_n300_f32", ["r_ext"], 384, 128), ("qsfa_both_n96_f32", ["I_ext"], 128, 64),

@@ -15,7 +15,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
 ADAPTIVE = ["qif_rk45", "jrc_rk45_tight", "qif_sfa_rk45", "wc_n8_rk45", "wc_n128_rk45", "kuramoto_n128_rk45"]
 NAMES = ["wc_n8", "wc_n128", "wc_n128_f32", "wc_n300_f32", "qsfa_both_n96_f32", "kuramoto_n128_f32", "qsfa_cascade_n8", "qsfa_ring_n8", "qsfa_both_n8", "qsfa_both_n96",
          "kuramoto_n8", "kuramoto_n128", "kuramoto_scalar_n128", "jrc_grid_b16", "jrc_grid_b1024", "jrc", "net8", "net9",
-         "net13", "jrc_2delay", "qif_input", "ring_kat", "gamma_kat"]
+         "net13", "jrc_2delay", "qif_input", "ring_kat", "gamma_kat", "net10"]
 SOLVERS = ["euler", "heun", "heun_true", "rk4"]
 
 
