@@ -253,6 +253,23 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
     return (long long)p;
 }
 
+// numpy.interp(x, xp, fp) for one x (timed inputs of adaptive runs, frontend/template/circuit.py:1692-1709): clamp outside
+// [xp[0], xp[n-1]], else slope * (x - xp[j]) + fp[j] with xp[j] <= x < xp[j+1] (the expression NumPy's C loop evaluates);
+// `stride` > 1 walks one column of a (steps, n_cols) table (interp_rows)
+__device__ __forceinline__ real prb_interp(const real* __restrict__ xp, const real* __restrict__ fp, const int stride, const int n,
+                                           const real x) {
+    if (!(x > __ldg(xp))) return __ldg(fp);
+    if (x >= __ldg(xp + n - 1)) return __ldg(fp + (long long)(n - 1) * stride);
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(xp + mid) <= x) lo = mid; else hi = mid;
+    }
+    const real x0 = __ldg(xp + lo), f0 = __ldg(fp + (long long)lo * stride);
+    const real slope = (__ldg(fp + (long long)(lo + 1) * stride) - f0) / (__ldg(xp + lo + 1) - x0);
+    return slope * (x - x0) + f0;
+}
+
 __device__ __forceinline__ real prb_max(real a, real b) { return (a != a || b != b) ? a + b : (a > b ? a : b); }
 __device__ __forceinline__ real prb_min(real a, real b) { return (a != a || b != b) ? a + b : (a < b ? a : b); }
 __device__ __forceinline__ real prb_sign(real a) { return (real)((a > (real)0) - (a < (real)0)); }

@@ -139,6 +139,8 @@ class _Emitter:
             r = frozenset("i") if pl[1] == "i" else frozenset()
         elif op == "table":
             r = frozenset("i") if pl[2] == "i" else frozenset()
+        elif op == "interprow":
+            r = frozenset(pl[4])
         else:
             r = frozenset()
             for a in g.args[i]:
@@ -208,6 +210,12 @@ class _Emitter:
             rows, L = arr.shape
             k = self.ring_index[pl[0]]
             return ("C.rings[" + self.bidx(f"{arr.offset}LL + prb_ring_pos(C.head[{k}], {pl[1] - arr.rolls}, {L}) * {rows}LL + {pl[2]}") + "]")
+        if op in ("interp", "interprow"):
+            # numpy.interp over two replicated constant tables; `C.t` is the float time of adaptive runs
+            xa, fa = ir.arrays[pl[0]], ir.arrays[pl[1]]
+            if op == "interp":
+                return f"prb_interp(C.consts + {xa.offset}LL, C.consts + {fa.offset}LL, 1, {pl[2]}, {r(a[0])})"
+            return f"prb_interp(C.consts + {xa.offset}LL, C.consts + {fa.offset}LL + {pl[4]}, {pl[3]}, {pl[2]}, {r(a[0])})"
         if op == "ldringg":
             # per-edge delayed read buf[source_idx[e], delays[e]]: the column is addressed relative to the ring head
             arr, rarr, carr = ir.arrays[pl[0]], ir.arrays[pl[1]], ir.arrays[pl[2]]
@@ -377,7 +385,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
             if a is (lazy_arrays[0] if lazy_arrays else None):
                 const_host = const_size
             rows = a.shape[0] if a.shape else 1
-            lo, hi = em.bounds(rows) if len(a.shape) == 2 else (0, rows)
+            lo, hi = em.bounds(rows) if (len(a.shape) == 2 and not a.replicate) else (0, rows)
             size = (hi - lo) * (a.shape[1] if len(a.shape) == 2 else 1) if a.shape else 1
             a.offset = const_size
             const_size += ((max(size, 1) + 31) // 32) * 32
@@ -840,7 +848,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 v = np.asarray(a.init)
                 if space == "ring":
                     v = v.T                        # device layout [L][rows]: a delay column is contiguous
-                if space == "const" and world > 1 and v.ndim == 2:
+                if space == "const" and world > 1 and v.ndim == 2 and not a.replicate:
                     lo, hi = em.bounds(v.shape[0])
                     v = v[lo:hi]                   # this rank's row shard of the connectivity
                 buf[a.offset:a.offset + v.size] = v.reshape(-1)          # casts on assignment, no temporary

@@ -46,6 +46,7 @@ class MemArray:
     init: Optional[np.ndarray] = None
     rolls: int = 0                  # rings: rolls per evaluation
     persistent: bool = False        # work arrays that keep their value across evaluations ('var' args)
+    replicate: bool = False         # 2-d constants every rank holds completely (interpolation tables), not row-sharded
 
     @property
     def size(self) -> int:
@@ -210,6 +211,19 @@ class _NetInterp:
         self.avail[name] = 0
         return arr
 
+    def _interp_table(self, name: str) -> MemArray:
+        """A (time or value) table of an interp call as a replicated constant array (never row-sharded, never folded)."""
+        arr = self.arrays.get(name)
+        if arr is None:
+            a = self.p.arg(name)
+            if a.kind != "const" or a.is_int or name in [n_ for n_, _ in self.params]:
+                raise UnsupportedModelError(f"interpolation table `{name}` must be a real-valued constant that is not swept")
+            arr = self._add_array(name, "const", np.asarray(a.value).shape, np.asarray(a.value))
+        if arr.space != "const":
+            raise UnsupportedModelError(f"interpolation table `{name}` must be a constant")
+        arr.replicate = True
+        return arr
+
     def _new_work(self, shape, hint="tmp") -> MemArray:
         self._tmp += 1
         return self._add_array(f"__{hint}{self._tmp}", "work", shape, np.zeros(shape))
@@ -284,6 +298,8 @@ class _NetInterp:
                 r = self._leaf("ldring", (pl[0], pl[1], to))
             elif op == "ldringg" and pl[3] == frm:
                 r = self._leaf("ldringg", (pl[0], pl[1], pl[2], to, pl[4]))
+            elif op == "interprow" and pl[4] == frm:
+                r = g._node("interprow", a, (pl[0], pl[1], pl[2], pl[3], to))
             elif op == "red" and frm == "i":
                 raise UnsupportedModelError("internal: reduction result used as reduction source without materialisation")
             elif not a:
@@ -482,7 +498,22 @@ class _NetInterp:
         if fname in ("past", "hist"):
             raise UnsupportedModelError("delay-differential `past()` terms are not supported by the CUDA backend")
         if fname in ("interp", "interp_rows"):
-            raise UnsupportedModelError("interpolated (adaptive-step) inputs are not supported; use a fixed-step solver")
+            # timed inputs of adaptive runs: `interp(t, time, u_input)` / `interp_rows(t, time, u_input[steps, cols])`
+            # (frontend/template/circuit.py:1692-1709; numpy.interp semantics) -> one node over two constant tables
+            if len(n.args) != 3 or not all(isinstance(a, ast.Name) for a in n.args[1:]):
+                raise UnsupportedModelError(f"unsupported {fname} call `{ast.unparse(n)}`")
+            tv = self.as_val(self.ev(n.args[0]))
+            xa, fa = (self._interp_table(a.id) for a in n.args[1:])
+            if tv.kind != SCALAR or len(xa.shape) != 1:
+                raise UnsupportedModelError("interp is supported for a scalar time over a 1-d time grid")
+            if fname == "interp":
+                if fa.shape != xa.shape:
+                    raise UnsupportedModelError("interp tables of different lengths")
+                return _V(SCALAR, g._node("interp", (tv.sym.id,), (xa.name, fa.name, int(xa.size))))
+            if len(fa.shape) != 2 or fa.shape[0] != xa.size:
+                raise UnsupportedModelError("interp_rows expects values of shape (len(time), n_cols)")
+            return _V(VEC, g._node("interprow", (tv.sym.id,), (xa.name, fa.name, int(xa.size), int(fa.shape[1]), "i")),
+                      n=int(fa.shape[1]))
         raise UnsupportedModelError(f"function `{fname}` is not supported by the CUDA network model")
 
     # ------------------------------------------------------------------ separable pair expressions
@@ -502,6 +533,8 @@ class _NetInterp:
                 r = frozenset("i") if pl[1] == "i" else frozenset()
             elif op == "table":
                 r = frozenset("i") if pl[2] == "i" else frozenset()
+            elif op == "interprow":
+                r = frozenset(pl[4])
             else:
                 r = frozenset()
                 for a in g.args[i]:
@@ -574,7 +607,7 @@ class _NetInterp:
         """Vector value as a j-indexed summand source.  Cheap expressions are inlined (recomputed at j),
         expensive ones (transcendentals, reductions) are materialised once and loaded."""
         g = self.g
-        heavy = self._has(v.sym.id, ("red",) + tuple(UNARY_FUNCS) + ("pow", "div"))
+        heavy = self._has(v.sym.id, ("red", "interp", "interprow") + tuple(UNARY_FUNCS) + ("pow", "div"))
         if heavy and g.ops[v.sym.id] != "ld":
             name, off = self._materialize(v, "src")
             return self._leaf("ld", (name, off, "j"))

@@ -224,3 +224,14 @@ def test_long_full_reductions_run_in_two_levels():
     assert "level 1: rows 4096..6144 of 8192" in body and "level 2: sum of the 4 x 256 partials" in body
     assert "prb_ll_fetch(C, 0LL, q - 0LL, 512LL, 256LL)" in body        # partials of ranks 0, 1 | 3 around this rank's 256 slots
     assert four.module.cubin[:4] == b"\x7fELF"
+
+
+def test_interpolated_inputs_lower_to_interp_nodes_over_replicated_tables():
+    """Adaptive runs feed timed inputs as `interp(t, time, u)` / `interp_rows(t, time, u[steps, cols])`
+    (frontend/template/circuit.py:1692-1709): one node over two constant tables, evaluated with numpy.interp's expression;
+    a vector of interpolated inputs that feeds a dot() is materialised first (one more phase)."""
+    a = NetworkModel(Program.load(golden_path("qif_input_rk45")), solver="scipy")
+    assert "prb_interp(C.consts +" in a.kernel.source and a.kernel.n_phases == 1
+    b = NetworkModel(Program.load(golden_path("qif2_input_rk45")), solver="scipy")
+    assert ", 2, 1000, ((real)C.t))" in b.kernel.source and b.kernel.n_phases == 2     # column stride 2, 1000 knots
+    assert b.ir.arrays["I_ext_input"].replicate and b.module.cubin[:4] == b"\x7fELF"

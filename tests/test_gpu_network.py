@@ -12,7 +12,8 @@ from pyrates_b200.program import Program
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
 
-ADAPTIVE = ["qif_rk45", "jrc_rk45_tight", "qif_sfa_rk45", "wc_n8_rk45", "wc_n128_rk45", "kuramoto_n128_rk45"]
+ADAPTIVE = ["qif_rk45", "jrc_rk45_tight", "qif_sfa_rk45", "wc_n8_rk45", "wc_n128_rk45", "kuramoto_n128_rk45",
+            "qif_input_rk45", "qif2_input_rk45"]     # timed inputs of adaptive runs: interp / interp_rows over constant tables
 NAMES = ["wc_n8", "wc_n128", "wc_n128_f32", "wc_n300_f32", "qsfa_both_n96_f32", "kuramoto_n128_f32", "qsfa_cascade_n8", "qsfa_ring_n8", "qsfa_both_n8", "qsfa_both_n96",
          "kuramoto_n8", "kuramoto_n128", "kuramoto_scalar_n128", "jrc_grid_b16", "jrc_grid_b1024", "jrc", "net8", "net9",
          "net13", "jrc_2delay", "qif_input", "ring_kat", "gamma_kat", "net10"]
@@ -173,6 +174,11 @@ def test_adaptive_rk45_network_kernel_matches_reference_scipy(gpu, name):
     args = [np.array(a, copy=True) for a in fx["args"]]
     args[0] = args[0][()]
     orc.run_adaptive(counted, args, r["T"], r["dt"], r["dts"], rtol=r["rtol"], atol=r["atol"])
+    if "_input_" in name:
+        # piecewise-linear inputs make RK45 ill-conditioned in the last bit (the error estimate jumps at every knot: a 2e-16
+        # perturbation of y0 moves the ORACLE by 2.8e-5 and its attempt count 451 -> 470): compared at 1e-3
+        assert traj_rel_err(out, ref) <= 1e-3, name
+        return
     assert attempts == (n[0] - 1) // 6                      # same accept / reject sequence as SciPy
     assert traj_rel_err(out, ref) <= 1e-9, name
 
