@@ -56,6 +56,7 @@ struct PrbNet {
 #endif
     long long gtid, gsize, gwarp, nwarps;
     int lane;
+    unsigned int wcache;         // bit g: the W rows of row group g are cached in shared memory (prb_net_stage_consts)
 #ifdef PRB_TC
     PrbTc tc;                    // tcgen05 coupling-GEMM pipeline state (tc_gemm.cuh)
 #endif
@@ -357,6 +358,54 @@ __device__ __forceinline__ float prb_row_dot(const float* __restrict__ w, const 
         for (int j = lane; j < m; j += 32) a0 = fmaf(__ldg(w + j), x[j], a0);
     }
     return prb_warp_sum((a0 + a1) + (a2 + a3));
+}
+
+// the same dot products with the W row segment in SHARED memory (W-stationary small networks: rows are copied once per
+// launch, prb_net_stage_consts); x comes from global / L1 as before
+__device__ __forceinline__ double prb_row_dot_sm(const double* w, const double* x, int m, int lane) {
+    double a0 = 0, a1 = 0;
+    if ((m & 1) == 0 && ((((unsigned long long)w) | ((unsigned long long)x)) & 15ULL) == 0) {
+        const double2* w2 = (const double2*)w;
+        const double2* x2 = (const double2*)x;
+        const int m2 = m >> 1;
+        int j = lane;
+        for (; j + 32 < m2; j += 64) {
+            const double2 wa = w2[j], wb = w2[j + 32], xa = x2[j], xb = x2[j + 32];
+            a0 = fma(wa.x, xa.x, a0); a0 = fma(wa.y, xa.y, a0);
+            a1 = fma(wb.x, xb.x, a1); a1 = fma(wb.y, xb.y, a1);
+        }
+        for (; j < m2; j += 32) { const double2 wa = w2[j], xa = x2[j]; a0 = fma(wa.x, xa.x, a0); a0 = fma(wa.y, xa.y, a0); }
+    } else {
+        for (int j = lane; j < m; j += 32) a0 = fma(w[j], x[j], a0);
+    }
+    return prb_warp_sum(a0 + a1);
+}
+__device__ __forceinline__ void prb_row_dot2_sm(const double* w, const double* x, const double* z, int m, int lane, double& rx, double& rz) {
+    double a0 = 0, b0 = 0;
+    if ((m & 1) == 0 && ((((unsigned long long)w) | ((unsigned long long)x) | ((unsigned long long)z)) & 15ULL) == 0) {
+        const double2* w2 = (const double2*)w;
+        const double2* x2 = (const double2*)x;
+        const double2* z2 = (const double2*)z;
+        for (int j = lane; j < (m >> 1); j += 32) {
+            const double2 wa = w2[j], xa = x2[j], za = z2[j];
+            a0 = fma(wa.x, xa.x, a0); a0 = fma(wa.y, xa.y, a0); b0 = fma(wa.x, za.x, b0); b0 = fma(wa.y, za.y, b0);
+        }
+    } else {
+        for (int j = lane; j < m; j += 32) { const double wv = w[j]; a0 = fma(wv, x[j], a0); b0 = fma(wv, z[j], b0); }
+    }
+    rx = prb_warp_sum(a0);
+    rz = prb_warp_sum(b0);
+}
+__device__ __forceinline__ float prb_row_dot_sm(const float* w, const float* x, int m, int lane) {
+    float a0 = 0;
+    for (int j = lane; j < m; j += 32) a0 = fmaf(w[j], x[j], a0);
+    return prb_warp_sum(a0);
+}
+__device__ __forceinline__ void prb_row_dot2_sm(const float* w, const float* x, const float* z, int m, int lane, float& rx, float& rz) {
+    float a0 = 0, b0 = 0;
+    for (int j = lane; j < m; j += 32) { const float wv = w[j]; a0 = fmaf(wv, x[j], a0); b0 = fmaf(wv, z[j], b0); }
+    rx = prb_warp_sum(a0);
+    rz = prb_warp_sum(b0);
 }
 
 // two right-hand sides over ONE pass of the row (separable pair-space couplings: W.sin(theta) and W.cos(theta))
@@ -732,6 +781,7 @@ prb_integrate_net(const __grid_constant__ prb_kernel_args A)
     C.gwarp = C.gtid >> 5;
     C.nwarps = C.gsize >> 5;
     prb_net_init_heads(C, A.eval0);
+    prb_net_stage_consts(C);
 #ifdef PRB_TC
     prb_tc_setup(C.tc, C.bar + 2);
 #endif

@@ -20,6 +20,7 @@ from .scalarize import UnsupportedModelError
 
 __all__ = ["NetKernel", "emit_net_kernel"]
 
+WCACHE_MAX_BYTES = 192 * 1024     # dynamic shared memory for W-stationary row groups (227 KB per CTA minus static use)
 FULL_TWO_LEVEL = 8192        # full reductions at least this long run in two levels (partials per CTA + grid barrier)
 FULL_PART_STRIDE = 256       # partial slots per rank: the persistent grid has one CTA per SM (148 on B200), never more than this
 
@@ -338,7 +339,8 @@ def tc_config(ir: NetIR, precision: str, n_batch: int, world: int, tc_max_acc: i
 
 def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequence[int], block: int = 512,
                     rank: int = 0, world: int = 1, n_batch: int = 1, tensor_core: bool = False,
-                    tc_max_acc: int = 128, split_rows: bool = True, dot_deep: bool = True) -> NetKernel:
+                    tc_max_acc: int = 128, split_rows: bool = True, dot_deep: bool = True,
+                    w_stationary: bool = False) -> NetKernel:
     if solver not in SOLVER_IDS:
         raise ValueError(f"unknown solver `{solver}`")
     f32 = precision == "float32"
@@ -424,6 +426,9 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
         while S * 2 <= wpb and rows * S * 2 <= 148 * wpb and m_min // (S * 2) >= 128:      # >= 2 double2 per lane and warp
             S *= 2
         return S if rows > 0 else 1
+
+    wcache_plan: List[dict] = []         # row groups whose W rows live in shared memory for the whole launch
+    wcache_used = 0                      # bytes of dynamic shared memory taken by them
 
     body: List[str] = []
     full_reds = [r for r in ir.reductions if r.kind == "full"]
@@ -656,14 +661,6 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 wpb = block // 32
                 tpb = wpb // S
                 tagp = f"{p}_{n}"
-                body.append(f"    {{   // {S} warps per row, n = {n} ({hi - lo} rows on this GPU)")
-                body.append(f"        __shared__ real prb_part{tagp}[{len(reds)}][{wpb}];")
-                body.append(f"        const int wib = (int)(threadIdx.x >> 5), tib = wib / {S}, wit = wib - tib * {S};")
-                body.append(f"        const long long nteams = (long long)gridDim.x * {tpb}, team = (long long)blockIdx.x * {tpb} + tib;")
-                body.append(f"        for (long long i0 = {lo}LL; i0 < {hi}LL; i0 += nteams) {{")
-                body.append(f"            const long long i = i0 + team;")
-                body.append(f"            const bool act = i < {hi}LL;")
-                body.append(f"            if (act) {{")
                 fused_done: Set[int] = set()
                 pairs = []
                 for r in reds:
@@ -675,18 +672,57 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                     if mate is not None:
                         fused_done.add(mate.id)
                     pairs.append((r, mate))
-                for r, mate in pairs:
+                # W-stationary rows (opt-in, w_stationary=True): when every team of the (148-CTA) grid owns at most ONE row of
+                # this group and the rows a CTA owns fit its shared memory, each CTA copies them there once per launch
+                # (prb_net_stage_consts) and every evaluation reads W from shared memory instead of streaming it from L2 again.
+                # Measured on B200 (profiles/r02_wcache.jsonl): correct but SLOWER than the 8-deep L2 stream (C4 2 x 1024: 16.0
+                # vs 13.7 us per step, C3 N=1024: 4.02 vs 3.47 us) — these networks are bound by the barrier / reduction latency
+                # chain, not by the W bytes, and the 128 KB carve-out costs L1.  Off by default.
+                row_elems = sum(r.m for r, _ in pairs)
+                cache_bit = None
+                if (w_stationary and not f32 and hi - lo <= 148 * tpb and all(r.m % 2 == 0 for r, _ in pairs)
+                        and wcache_used + tpb * row_elems * 8 <= WCACHE_MAX_BYTES and len(wcache_plan) < 30):
+                    cache_bit = len(wcache_plan)
+                    offs, o = [], 0
+                    for r, _ in pairs:
+                        offs.append(o)
+                        o += r.m
+                    wcache_plan.append({"bit": cache_bit, "S": S, "tpb": tpb, "lo": lo, "hi": hi, "base": wcache_used // 8,
+                                        "row_elems": row_elems, "rows": [(ir.arrays[r.simple[0]].offset, r.m, off) for (r, _), off in zip(pairs, offs)]})
+                    wcache_used += tpb * row_elems * 8
+                body.append(f"    {{   // {S} warps per row, n = {n} ({hi - lo} rows on this GPU)"
+                            + (f", W rows cached in shared memory (bit {cache_bit})" if cache_bit is not None else ""))
+                body.append(f"        __shared__ real prb_part{tagp}[{len(reds)}][{wpb}];")
+                body.append(f"        const int wib = (int)(threadIdx.x >> 5), tib = wib / {S}, wit = wib - tib * {S};")
+                body.append(f"        const long long nteams = (long long)gridDim.x * {tpb}, team = (long long)blockIdx.x * {tpb} + tib;")
+                if cache_bit is not None:
+                    body.append("        extern __shared__ __align__(16) unsigned char prb_dyn_smem[];")
+                    body.append(f"        const real* wsm = (const real*)prb_dyn_smem + {wcache_plan[-1]['base']}LL + (long long)tib * {row_elems}LL;")
+                    body.append(f"        const bool wcached = (C.wcache >> {cache_bit}) & 1u;")
+                body.append(f"        for (long long i0 = {lo}LL; i0 < {hi}LL; i0 += nteams) {{")
+                body.append(f"            const long long i = i0 + team;")
+                body.append(f"            const bool act = i < {hi}LL;")
+                body.append(f"            if (act) {{")
+                for pi_, (r, mate) in enumerate(pairs):
                     warr = ir.arrays[r.simple[0]]
                     seg = -(-(-(-r.m // S)) // 4) * 4                     # elements per warp, a multiple of 4: keeps the 16-byte alignment
                     body.append(f"                {{")
                     body.append(f"                    const int s0 = wit * {seg}, len = ({r.m} - s0) < {seg} ? (({r.m} - s0) > 0 ? ({r.m} - s0) : 0) : {seg};")
                     wptr = f"C.consts + {warr.offset}LL + (i - {lo}LL) * {r.m}LL + s0"
+                    wsp = f"wsm + {wcache_plan[-1]['rows'][pi_][2]}LL + s0" if cache_bit is not None else None
                     if mate is not None:
                         body.append(f"                    real pa, pb;")
+                        if wsp is not None:
+                            body.append(f"                    if (wcached) prb_row_dot2_sm({wsp}, {em.source_ptr(r)} + s0, {em.source_ptr(mate)} + s0, len, C.lane, pa, pb);")
+                            body.append(f"                    else")
                         body.append(f"                    prb_row_dot2({wptr}, {em.source_ptr(r)} + s0, {em.source_ptr(mate)} + s0, len, C.lane, pa, pb);")
                         body.append(f"                    if (C.lane == 0) {{ prb_part{tagp}[{reds.index(r)}][wib] = pa; prb_part{tagp}[{reds.index(mate)}][wib] = pb; }}")
                     else:
-                        body.append(f"                    const real pa = prb_row_dot({wptr}, {em.source_ptr(r)} + s0, len, C.lane);")
+                        if wsp is not None:
+                            body.append(f"                    const real pa = wcached ? prb_row_dot_sm({wsp}, {em.source_ptr(r)} + s0, len, C.lane)")
+                            body.append(f"                                            : prb_row_dot({wptr}, {em.source_ptr(r)} + s0, len, C.lane);")
+                        else:
+                            body.append(f"                    const real pa = prb_row_dot({wptr}, {em.source_ptr(r)} + s0, len, C.lane);")
                         body.append(f"                    if (C.lane == 0) prb_part{tagp}[{reds.index(r)}][wib] = pa;")
                     body.append(f"                }}")
                 body.append(f"            }}")
@@ -818,6 +854,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     src.append("struct PrbNet;")
     src.append("__device__ __forceinline__ void prb_net_init_heads(PrbNet& C, long long eval0);")
     src.append("__device__ __forceinline__ void prb_net_advance_heads(PrbNet& C);")
+    src.append("__device__ __forceinline__ void prb_net_stage_consts(PrbNet& C);")
     if tc is not None:
         src.append("#define PRB_TC 1")
         src.append(f"#define PRB_TC_BT {tc['bt']}")
@@ -835,6 +872,28 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
             heads_a.append(f"    C.head[{k}] = (C.head[{k}] + {a.rolls % L}) % {L};")
     src.append("__device__ __forceinline__ void prb_net_init_heads(PrbNet& C, long long eval0) {\n" + "\n".join(heads_i) + "\n}")
     src.append("__device__ __forceinline__ void prb_net_advance_heads(PrbNet& C) {\n" + "\n".join(heads_a) + "\n}")
+    stage = ["// once per launch: every CTA copies the W rows its warp teams own into shared memory (W-stationary small networks)",
+             "__device__ __forceinline__ void prb_net_stage_consts(PrbNet& C) {", "    C.wcache = 0u;"]
+    if wcache_plan:
+        stage.append("    extern __shared__ __align__(16) unsigned char prb_dyn_smem[];")
+        stage.append("    const int wib = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);")
+    for g_ in wcache_plan:
+        S_, tpb_ = g_["S"], g_["tpb"]
+        stage.append(f"    if ((long long)gridDim.x * {tpb_} >= {g_['hi'] - g_['lo']}LL) {{      // one row per team: the cached form is valid")
+        stage.append(f"        C.wcache |= {1 << g_['bit']}u;")
+        stage.append(f"        const int tib = wib / {S_}, wit = wib - tib * {S_};")
+        stage.append(f"        const long long i = {g_['lo']}LL + (long long)blockIdx.x * {tpb_} + tib;")
+        stage.append(f"        if (i < {g_['hi']}LL) {{")
+        for woff, m_, off in g_["rows"]:
+            stage.append(f"            {{ const double2* src_ = (const double2*)(C.consts + {woff}LL + (i - {g_['lo']}LL) * {m_}LL);")
+            stage.append(f"              double2* dst_ = (double2*)((real*)prb_dyn_smem + {g_['base']}LL + (long long)tib * {g_['row_elems']}LL + {off}LL);")
+            stage.append(f"              for (int j = wit * 32 + lane; j < {m_ // 2}; j += {S_ * 32}) dst_[j] = prb_ld_stream(src_ + j); }}")
+        stage.append("        }")
+        stage.append("    }")
+    if wcache_plan:
+        stage.append("    __syncthreads();")
+    stage.append("}")
+    src.append("\n".join(stage))
     src.append("template <int STAGE> __device__ void prb_eval(PrbNet& C) {")
     src.extend(body)
     src.append("}")
@@ -863,7 +922,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     if not all_state:
         iconst[obs_off:obs_off + obs.size] = obs
     evals = {"euler": 1, "heun": 2, "heun_ref": 2, "heun_true": 2, "rk4": 4, "scipy": 6, "rk45": 6}[solver]
-    smem = gemm_smem
+    smem = max(gemm_smem, wcache_used)
     if tc is not None:
         smem = tc["nstage"] * (2 * 128 * tc["ck"] * 4 + 2 * tc["bt"] * tc["ck"] * 4)
         tc = dict(tc, smem=smem, xt_elems=tc_work)

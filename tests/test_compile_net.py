@@ -182,6 +182,14 @@ def test_few_rows_per_gpu_share_a_row_between_warps():
     assert "warps per row" not in off.kernel.source and "#define PRB_DOT_DEEP 0" in off.kernel.source
     c4 = NetworkModel(bc.make_c4(1024), solver="heun")                      # two dots per row, 1024 rows: 2 warps per row
     assert "// 2 warps per row, n = 1024" in c4.kernel.source and c4.module.cubin[:4] == b"\x7fELF"
+    assert "prb_row_dot_sm(" not in c4.kernel.source.split("prb_eval(PrbNet& C) {")[1] and c4.kernel.smem_bytes == 0
+    # opt-in W-stationary form (measured slower, profiles/r02_wcache.jsonl): 8 teams per CTA x (1024 + 1024) fp64 of W rows =
+    # 128 KB of dynamic shared memory, filled once per launch
+    ws = NetworkModel(bc.make_c4(1024), solver="heun", w_stationary=True)
+    assert "W rows cached in shared memory (bit 0)" in ws.kernel.source and ws.kernel.smem_bytes == 8 * 2048 * 8
+    assert "prb_row_dot_sm(wsm +" in ws.kernel.source and "C.wcache |= 1u;" in ws.kernel.source and ws.module.cubin[:4] == b"\x7fELF"
+    big = NetworkModel(bc.make_c3(8192), solver="euler", rank=0, world=8, w_stationary=True)   # 8 x 64 KB per CTA: does not fit
+    assert "W rows cached" not in big.kernel.source
 
 
 def test_device_generated_connectivity_twin_and_constant_layout():
