@@ -22,6 +22,9 @@
 #ifndef PRB_NB
 #define PRB_NB 1                 // sweep instances integrated together (batch index b is the fastest-varying dimension)
 #endif
+#ifndef PRB_LL_REDUNDANT
+#define PRB_LL_REDUNDANT 0
+#endif
 #ifndef PRB_DOT_DEEP
 #define PRB_DOT_DEEP 0           // fp64 row dot: 8 instead of 4 independent 16-byte loads per lane (set by the emitter)
 #endif
@@ -44,7 +47,7 @@ struct PrbNet {
     long long oK[7], oSA, oSB;   // stage derivatives K0..K6 and the two alternating stage-input vectors inside `work`
 #endif
     int head[PRB_NRINGS > 0 ? PRB_NRINGS : 1];
-    unsigned long long* bar;     // [0] local arrivals, [2] error flag
+    unsigned long long* bar;     // [0] local arrivals, [1] CTAs done fetching (redundant exchange form), [2] error flag
     unsigned long long bar_target;
     unsigned long long epoch;
 #if PRB_WORLD > 1
@@ -181,11 +184,21 @@ __device__ __forceinline__ void prb_ll_fetch_scatter(PrbNet& C, const long long 
 }
 #endif
 
-__device__ __forceinline__ void prb_grid_barrier(PrbNet& C) {
+// The barrier in two halves.  arrive: this CTA's stores are done (multi-GPU: heartbeat out, peers' heartbeats in).
+// wait: all local CTAs have arrived.  prb_grid_barrier = arrive + wait.  In the REDUNDANT exchange form (PRB_LL_REDUNDANT,
+// small exchanges) the generated code puts its fetch loop BETWEEN the halves: every CTA polls all peer-owned elements itself
+// while the local arrivals trickle in, so the local barrier overlaps the NVLink flight instead of following it.  Word [1] of
+// the barrier block counts CTAs that have FINISHED fetching (one increment per CTA and barrier): the heartbeat of barrier
+// k + 1 is only sent once every local CTA is done with the packets of barrier k — the lockstep argument that makes two mirror
+// parities sufficient needs "this rank has consumed barrier k" to hold for all its CTAs, not just for the arrivals.
+__device__ __forceinline__ void prb_barrier_arrive(PrbNet& C) {
 #if PRB_WORLD > 1
-    // heartbeat: one packet per rank and barrier; consuming the peers' heartbeats keeps the ranks in lockstep even at a
-    // barrier whose data regions happen to involve only some of them
-    if (C.gtid == 0) prb_ll_send(C, PRB_LL_WORK + PRB_LL_RING + PRB_RANK, (real)0);
+    if (C.gtid == 0) {
+#if PRB_LL_REDUNDANT
+        prb_spin_until<false>(C, C.bar + 1, (unsigned long long)gridDim.x * C.epoch);
+#endif
+        prb_ll_send(C, PRB_LL_WORK + PRB_LL_RING + PRB_RANK, (real)0);
+    }
     if (C.gtid >= 32 && C.gtid < 32 + PRB_WORLD && C.gtid - 32 != PRB_RANK) (void)prb_ll_recv(C, PRB_LL_WORK + PRB_LL_RING + (C.gtid - 32));
 #endif
     __syncthreads();
@@ -193,6 +206,17 @@ __device__ __forceinline__ void prb_grid_barrier(PrbNet& C) {
         C.bar_target += gridDim.x;
         __threadfence();
         atomicAdd(C.bar, 1ULL);
+    }
+}
+
+__device__ __forceinline__ void prb_barrier_wait(PrbNet& C) {
+#if PRB_WORLD > 1 && PRB_LL_REDUNDANT
+    __syncthreads();                                     // every thread of this CTA is done with the mirror
+#endif
+    if (threadIdx.x == 0) {
+#if PRB_WORLD > 1 && PRB_LL_REDUNDANT
+        atomicAdd(C.bar + 1, 1ULL);
+#endif
         prb_spin_until<false>(C, C.bar, C.bar_target);
         __threadfence();
     }
@@ -202,6 +226,11 @@ __device__ __forceinline__ void prb_grid_barrier(PrbNet& C) {
     C.ll_par = (long long)((C.epoch + 1ULL) & 1ULL) * PRB_LL_SLOTS;
 #endif
     __syncthreads();
+}
+
+__device__ __forceinline__ void prb_grid_barrier(PrbNet& C) {
+    prb_barrier_arrive(C);
+    prb_barrier_wait(C);
 }
 
 __device__ __forceinline__ real prb_warp_sum(real v) {
@@ -745,7 +774,11 @@ __device__ __forceinline__ void prb_stage(PrbNet& C, const long long oyin) {
     C.yin = C.work + oyin;
     prb_eval<STAGE>(C);
     prb_net_advance_heads(C);
+#if PRB_WORLD > 1 && PRB_LL_REDUNDANT
+    prb_barrier_wait(C);                 // the generated evaluation ended with prb_barrier_arrive + its own fetch loop
+#else
     prb_grid_barrier(C);
+#endif
 }
 
 extern "C" __global__ void __launch_bounds__(PRB_BLOCK, 1)

@@ -20,6 +20,7 @@ from .scalarize import UnsupportedModelError
 
 __all__ = ["NetKernel", "emit_net_kernel"]
 
+LL_REDUNDANT_MAX = 4096           # multi-GPU: up to this many peer-owned elements per barrier every CTA polls them all itself
 WCACHE_MAX_BYTES = 192 * 1024     # dynamic shared memory for W-stationary row groups (227 KB per CTA minus static use)
 FULL_TWO_LEVEL = 8192        # full reductions at least this long run in two levels (partials per CTA + grid barrier)
 FULL_PART_STRIDE = 256       # partial slots per rank: the persistent grid has one CTA per SM (148 on B200), never more than this
@@ -58,6 +59,7 @@ class _Emitter:
         self.red_work: Dict[int, MemArray] = {}
         self.ring_index = {name: k for k, name in enumerate(a.name for a in ir.arrays.values() if a.space == "ring")}
         self.pending: List[str] = []      # multi-GPU: unpack calls for the regions stored since the last grid barrier
+        self.max_fetch = 0                # largest number of peer-owned elements fetched in front of one barrier
 
     # ---- multi-GPU exchange bookkeeping (net_kernel.cuh: prb_ll_*): every store another rank must see is sent as an LL
     # packet by its owner; the receiving grid fetches the regions its peers own right before the next grid barrier
@@ -84,11 +86,15 @@ class _Emitter:
                     self.pending.append(item)
 
     def flush(self, indent: str = "    ") -> List[str]:
-        """One grid-strided loop over ALL elements the peers own of the regions stored since the last barrier."""
+        """One loop over ALL elements the peers own of the regions stored since the last barrier.  The loop bounds and the
+        barrier calls are placeholders: emit_net_kernel decides afterwards whether the grid shares the polling (cooperative
+        form) or every CTA polls everything itself between an early arrival and the wait (redundant form)."""
         if not self.pending:
             return []
         total = sum(cnt for _, _, cnt, _ in self.pending)
-        out = [f"{indent}for (long long q = C.gtid; q < {total}LL; q += C.gsize) {{   // fetch what the peers own "
+        self.max_fetch = max(self.max_fetch, total)
+        out = [f"{indent}@@ARRIVE@@",
+               f"{indent}for (long long q = @@Q0@@; q < {total}LL; q += @@QS@@) {{   // fetch what the peers own "
                f"({len(self.pending)} region(s))"]
         start = 0
         for k, (fn, head, cnt, tail) in enumerate(self.pending):
@@ -340,7 +346,7 @@ def tc_config(ir: NetIR, precision: str, n_batch: int, world: int, tc_max_acc: i
 def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequence[int], block: int = 512,
                     rank: int = 0, world: int = 1, n_batch: int = 1, tensor_core: bool = False,
                     tc_max_acc: int = 128, split_rows: bool = True, dot_deep: bool = True,
-                    w_stationary: bool = False) -> NetKernel:
+                    w_stationary: bool = False, ll_redundant: bool = True) -> NetKernel:
     if solver not in SOLVER_IDS:
         raise ValueError(f"unknown solver `{solver}`")
     f32 = precision == "float32"
@@ -464,7 +470,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
             em.note_work(part.offset, world * FULL_PART_STRIDE)
         if two_level:
             body.extend(em.flush())
-            body.append("    prb_grid_barrier(C);")
+            body.append("    @@BARRIER@@")
             for r in two_level:
                 part = full_part[r.id]
                 body.append(f"    {{   // level 2: sum of the {world} x {FULL_PART_STRIDE} partials")
@@ -604,7 +610,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                                 f"{em.red_work[r.id].offset}LL);      // n = {n}")
                     em.note_work(em.red_work[r.id].offset, n)
                 body.extend(em.flush())
-                body.append("    prb_grid_barrier(C);")
+                body.append("    @@BARRIER@@")
                 if sts:
                     cur = (p, n, False)
                     emitted = set()
@@ -824,9 +830,12 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
                 body.append("    }")
         # multi-GPU: fetch what the peers stored in this phase into the local replicas (the last phase's regions are
         # fetched here as well: the barrier that ends the evaluation follows in prb_stage)
-        body.extend(em.flush())
+        last_fetch = em.flush()
+        body.extend(last_fetch)
         if p < n_phases - 1:
-            body.append("    prb_grid_barrier(C);")
+            body.append("    @@BARRIER@@")
+        elif not last_fetch:
+            body.append("    @@ARRIVE@@")       # redundant form: the evaluation always ends with the early arrival
 
     rings = [a for a in ir.arrays.values() if a.space == "ring"]
     src: List[str] = []
@@ -847,6 +856,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     src.append(f"#define PRB_DOT_DEEP {1 if dot_deep else 0}")
     src.append(f"#define PRB_RANK {rank}")
     src.append(f"#define PRB_WORLD {world}")
+    src.append("#define PRB_LL_REDUNDANT @@LLR@@")
     # multi-GPU receive mirror (net_kernel.cuh: prb_ll_*): one 16-byte packet slot per work / ring element, two parities
     src.append(f"#define PRB_LL_WORK {(work_size + n_solver_vecs * ns) * nb + tc_work}LL")
     src.append(f"#define PRB_LL_RING {ir.ring_size * nb}LL")
@@ -872,6 +882,26 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
             heads_a.append(f"    C.head[{k}] = (C.head[{k}] + {a.rolls % L}) % {L};")
     src.append("__device__ __forceinline__ void prb_net_init_heads(PrbNet& C, long long eval0) {\n" + "\n".join(heads_i) + "\n}")
     src.append("__device__ __forceinline__ void prb_net_advance_heads(PrbNet& C) {\n" + "\n".join(heads_a) + "\n}")
+    # multi-GPU exchange form.  Cooperative: the grid shares the polling of the peers' packets, then meets at the barrier
+    # (remote arrival and local barrier in series).  Redundant (small exchanges only): every CTA arrives EARLY, polls all
+    # peer-owned elements itself (identical values, benign duplicate stores into the replica) and only then waits for the
+    # local arrivals — the local barrier overlaps the NVLink flight instead of following it.
+    redundant = world > 1 and 0 < em.max_fetch <= LL_REDUNDANT_MAX and ll_redundant
+    fixed: List[str] = []
+    armed = False
+    for line in body:
+        if "@@ARRIVE@@" in line:
+            if redundant:
+                fixed.append(line.replace("@@ARRIVE@@", "prb_barrier_arrive(C);"))
+                armed = True
+            continue
+        if "@@BARRIER@@" in line:
+            fixed.append(line.replace("@@BARRIER@@", "prb_barrier_wait(C);" if (redundant and armed) else "prb_grid_barrier(C);"))
+            armed = False
+            continue
+        fixed.append(line.replace("@@Q0@@", "(long long)threadIdx.x" if redundant else "C.gtid")
+                     .replace("@@QS@@", "(long long)blockDim.x" if redundant else "C.gsize"))
+    body = fixed
     stage = ["// once per launch: every CTA copies the W rows its warp teams own into shared memory (W-stationary small networks)",
              "__device__ __forceinline__ void prb_net_stage_consts(PrbNet& C) {", "    C.wcache = 0u;"]
     if wcache_plan:
@@ -926,6 +956,7 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     if tc is not None:
         smem = tc["nstage"] * (2 * 128 * tc["ck"] * 4 + 2 * tc["bt"] * tc["ck"] * 4)
         tc = dict(tc, smem=smem, xt_elems=tc_work)
+    src = [x.replace("@@LLR@@", "1" if redundant else "0") for x in src]
     return NetKernel("\n".join(src) + "\n", ns, int(obs.size), (work_size + n_solver_vecs * ns) * nb + tc_work, work_size,
                      pack("work", work_size, real), const_buf, iconst,
                      pack("ring", ir.ring_size, real), pack("table", ir.table_size, real), block, solver, precision,

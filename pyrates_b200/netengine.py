@@ -26,7 +26,8 @@ class NetworkModel:
     def __init__(self, prog: Program, *, solver: str = "euler", observers: Optional[Sequence[int]] = None,
                  block: int = 512, fmad: bool = True, blocks_per_sm: int = 1, rank: int = 0, world: int = 1,
                  separable: bool = True, n_batch: int = 1, sweep: Sequence[str] = (), tensor_core="auto",
-                 tc_max_acc: int = 128, split_rows: bool = True, dot_deep: bool = True, w_stationary: bool = False):
+                 tc_max_acc: int = 128, split_rows: bool = True, dot_deep: bool = True, w_stationary: bool = False,
+                 ll_redundant: bool = True):
         """``n_batch`` > 1 integrates that many sweep instances of the network together (shared connectivity);
         ``sweep`` names the scalar / uniform-vector arguments that vary per instance.  ``tensor_core``: run the batched
         dense couplings as tcgen05 3xTF32 GEMMs (float32 models, batch a multiple of 32; "auto" = whenever that
@@ -55,7 +56,8 @@ class NetworkModel:
         self.kernel: NetKernel = emit_net_kernel(self.ir, solver=solver, precision=self.precision,
                                                  observers=self.observers, block=block, rank=self.rank, world=self.world,
                                                  n_batch=self.n_batch, tensor_core=bool(tensor_core), tc_max_acc=tc_max_acc,
-                                                 split_rows=split_rows, dot_deep=dot_deep, w_stationary=w_stationary)
+                                                 split_rows=split_rows, dot_deep=dot_deep, w_stationary=w_stationary,
+                                                 ll_redundant=ll_redundant)
         self.fmad = fmad
         self.blocks_per_sm = blocks_per_sm
         self._module: Optional[rt.Module] = None
