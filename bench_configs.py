@@ -263,7 +263,7 @@ def main():
     ap.add_argument("--tc-max-acc", type=int, default=128, help="fp32 accumulator registers per epilogue thread (128 -> 256-wide tiles)")
     ap.add_argument("--no-split", action="store_true", help="one warp per row even when the GPU has fewer rows than warps")
     ap.add_argument("--no-deep", action="store_true", help="4 instead of 8 independent loads per lane in the fp64 row dot")
-    ap.add_argument("--no-redundant", action="store_true", help="multi-GPU: always share the polling of the peers' packets over the grid")
+    ap.add_argument("--redundant", action="store_true", help="multi-GPU: small exchanges in the redundant-fetch form (every CTA polls)")
     ap.add_argument("--wcache", action="store_true", help="cache each CTA's W rows in shared memory when they fit (W-stationary; measured slower)")
     a = ap.parse_args()
     from pyrates_b200 import runtime as rt
@@ -289,7 +289,7 @@ def main():
     m = NetworkModel(prog, solver=a.solver, observers=[0], block=a.block, rank=0 if shard_instances else rank,
                      world=1 if shard_instances else world, n_batch=a.batch,
                      sweep=sweep, tensor_core="auto" if a.tensor_core == "auto" else False, tc_max_acc=a.tc_max_acc,
-                     split_rows=not a.no_split, dot_deep=not a.no_deep, w_stationary=a.wcache, ll_redundant=not a.no_redundant)
+                     split_rows=not a.no_split, dot_deep=not a.no_deep, w_stationary=a.wcache, ll_redundant=a.redundant)
     params = None
     if sweep:
         params = m.param_defaults[:, None] * (1.0 + 0.1 * np.random.default_rng(3 + rank).uniform(-1, 1, (len(sweep), a.batch))) \

@@ -346,7 +346,7 @@ def tc_config(ir: NetIR, precision: str, n_batch: int, world: int, tc_max_acc: i
 def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequence[int], block: int = 512,
                     rank: int = 0, world: int = 1, n_batch: int = 1, tensor_core: bool = False,
                     tc_max_acc: int = 128, split_rows: bool = True, dot_deep: bool = True,
-                    w_stationary: bool = False, ll_redundant: bool = True) -> NetKernel:
+                    w_stationary: bool = False, ll_redundant: bool = False) -> NetKernel:
     if solver not in SOLVER_IDS:
         raise ValueError(f"unknown solver `{solver}`")
     f32 = precision == "float32"
@@ -885,7 +885,10 @@ def emit_net_kernel(ir: NetIR, *, solver: str, precision: str, observers: Sequen
     # multi-GPU exchange form.  Cooperative: the grid shares the polling of the peers' packets, then meets at the barrier
     # (remote arrival and local barrier in series).  Redundant (small exchanges only): every CTA arrives EARLY, polls all
     # peer-owned elements itself (identical values, benign duplicate stores into the replica) and only then waits for the
-    # local arrivals — the local barrier overlaps the NVLink flight instead of following it.
+    # local arrivals — the local barrier overlaps the NVLink flight instead of following it.  Opt-in (ll_redundant=True):
+    # measured on 2 B200s (profiles/r02_redundant_n2.jsonl) it is worth 2-4 % for a single small region (C3 N=1024: 5.03 vs
+    # 5.26 us per step) and LOSES where many regions meet one barrier (QIF-SFA 2 x 512, 13 regions: 21.4 vs 16.0 us — every
+    # CTA walks the whole region list); the cooperative form stays the default.
     redundant = world > 1 and 0 < em.max_fetch <= LL_REDUNDANT_MAX and ll_redundant
     fixed: List[str] = []
     armed = False

@@ -27,7 +27,7 @@ class NetworkModel:
                  block: int = 512, fmad: bool = True, blocks_per_sm: int = 1, rank: int = 0, world: int = 1,
                  separable: bool = True, n_batch: int = 1, sweep: Sequence[str] = (), tensor_core="auto",
                  tc_max_acc: int = 128, split_rows: bool = True, dot_deep: bool = True, w_stationary: bool = False,
-                 ll_redundant: bool = True):
+                 ll_redundant: bool = False):
         """``n_batch`` > 1 integrates that many sweep instances of the network together (shared connectivity);
         ``sweep`` names the scalar / uniform-vector arguments that vary per instance.  ``tensor_core``: run the batched
         dense couplings as tcgen05 3xTF32 GEMMs (float32 models, batch a multiple of 32; "auto" = whenever that

@@ -246,25 +246,25 @@ def test_interpolated_inputs_lower_to_interp_nodes_over_replicated_tables():
 
 
 def test_small_exchanges_use_the_redundant_fetch_form():
-    """Multi-GPU exchange forms: up to LL_REDUNDANT_MAX peer-owned elements per barrier every CTA arrives EARLY, polls all of
-    them itself and then waits (the local barrier overlaps the NVLink flight); larger exchanges share the polling over the
-    grid and meet at the barrier afterwards.  Either way every barrier is one arrive + one wait."""
+    """Multi-GPU exchange forms.  Default: the grid shares the polling of the peers' packets and meets at the barrier afterwards.
+    Opt-in (ll_redundant=True, measured: profiles/r02_redundant_n2.jsonl): up to LL_REDUNDANT_MAX peer-owned elements per barrier
+    every CTA arrives EARLY, polls all of them itself and then waits.  Either way every barrier is one arrive + one wait."""
     import re
     import bench_configs as bc
-    small = NetworkModel(bc.make_c3(2048), solver="rk4", rank=1, world=8)            # 1792 peer-owned elements per barrier
+    small = NetworkModel(bc.make_c3(2048), solver="rk4", rank=1, world=8, ll_redundant=True)   # 1792 peer-owned elements per barrier
     src = small.kernel.source
     body = src[src.rindex("template <int STAGE> __device__ void prb_eval"):]
     assert "#define PRB_LL_REDUNDANT 1" in src and "@@" not in src
     assert "prb_barrier_arrive(C);" in body and "q = (long long)threadIdx.x; q < 1792LL; q += (long long)blockDim.x" in body
     assert "prb_grid_barrier(C);" not in body                   # the wait of the last phase sits in prb_stage
-    big = NetworkModel(bc.make_c3(8192), solver="rk4", rank=1, world=8)              # 7168 elements: cooperative form
+    big = NetworkModel(bc.make_c3(8192), solver="rk4", rank=1, world=8, ll_redundant=True)     # 7168 elements: cooperative form
     src = big.kernel.source
     body = src[src.rindex("template <int STAGE> __device__ void prb_eval"):]
     assert "#define PRB_LL_REDUNDANT 0" in src and "q = C.gtid; q < 7168LL; q += C.gsize" in body and "prb_barrier_arrive" not in body
-    two = NetworkModel(Program.load(golden_path("kuramoto_n128")), solver="euler", rank=0, world=2)   # two phases
+    two = NetworkModel(Program.load(golden_path("kuramoto_n128")), solver="euler", rank=0, world=2, ll_redundant=True)   # two phases
     body = two.kernel.source[two.kernel.source.rindex("template <int STAGE> __device__ void prb_eval"):]
     assert len(re.findall(r"prb_barrier_arrive\(C\);", body)) == 2 and len(re.findall(r"prb_barrier_wait\(C\);", body)) == 1
-    off = NetworkModel(bc.make_c3(2048), solver="rk4", rank=1, world=8, ll_redundant=False)
+    off = NetworkModel(bc.make_c3(2048), solver="rk4", rank=1, world=8)                        # the default: cooperative
     assert "#define PRB_LL_REDUNDANT 0" in off.kernel.source
     for m in (small, big, two, off):
         assert m.module.cubin[:4] == b"\x7fELF"
