@@ -46,7 +46,7 @@ SWEEP = [("u", 0), ("weight_v2", 0), ("weight_v2", 1), ("weight", 0), ("weight_v
 # (--chunk-samples 25; 109.19 + 221.97 MB, profiles/r01_c2_reassoc_prb_integrate_ncu_full.txt)
 NCU_TRAFFIC = {2 ** 20 * 1000: 958.2e6, 2 ** 20 * 250: 331.16e6}
 # fp64-pipe warp instructions per instance-step inside the SASS time loop (cuobjdump; tests/test_compile_inst.py pins them)
-FP64_INSTR = {True: 265, False: 505}
+FP64_INSTR = {True: 264, False: 505}
 METRIC = "state-updates/sec (nodes x sweeps x steps/s), JRC RK4 grid_search"
 UNIT = "node-steps/s"
 JRC_YAML = "model_templates.neural_mass_models.jansenrit.JRC"

@@ -30,10 +30,24 @@ __device__ __forceinline__ void prb_axpy(real (&o)[N], const real (&y)[N], const
 
 // fast_math kernels read 2^(j/2048) from shared memory (divergent indices: a __constant__ read would serialise)
 #ifdef PRB_USE_ETAB
-#define PRB_STAGE_ETAB __shared__ double prb_etab[PRB_ETAB_N]; \
+#ifdef PRB_ETAB_FILE_SCOPE
+#define PRB_DECL_ETAB
+#else
+#define PRB_DECL_ETAB __shared__ double prb_etab[PRB_ETAB_N + 2];
+#endif
+// entries N, N + 1 hold 2048/ln2: every thread reads ITS copy back after the barrier (T.ek0), which makes the multiplier a
+// per-thread register value — as a compile-time constant it would sit in a uniform register and be copied into a register
+// pair before every use (24 extra instructions per RK4 step of the JRC sweep)
+#define PRB_STAGE_ETAB PRB_DECL_ETAB \
     for (int q = threadIdx.x; q < PRB_ETAB_N; q += blockDim.x) prb_etab[q] = PRB_EXP_TAB[q]; \
+    if (threadIdx.x < 2) prb_etab[PRB_ETAB_N + threadIdx.x] = PRB_EXP_K[0]; \
     __syncthreads();
-#define PRB_SET_ETAB T.etab = prb_etab; T.etab_s = (unsigned int)__cvta_generic_to_shared(prb_etab);
+#if PRB_EXP_PINK0
+#define PRB_SET_ETAB T.etab = prb_etab; T.etab_s = (unsigned int)__cvta_generic_to_shared(prb_etab); \
+    T.ek0 = prb_etab[PRB_ETAB_N + (threadIdx.x & 1)];
+#else
+#define PRB_SET_ETAB T.etab = prb_etab; T.etab_s = (unsigned int)__cvta_generic_to_shared(prb_etab); T.ek0 = PRB_EXP_K[0];
+#endif
 #else
 #define PRB_STAGE_ETAB
 #define PRB_SET_ETAB
@@ -425,7 +439,7 @@ __device__ __forceinline__ void prb_ysm_st(const PrbThread& T, const int j, cons
 // step and recomputes the step with the exact rhs (prb_step_exact) in the rare case it is set — the stages of a step stay one
 // basic block instead of ending in a reconvergence point each.
 template <bool SPEC>
-__device__ __forceinline__ void prb_stage(const long long t, const real (&y)[PRB_NS], real (&k)[PRB_NS], PrbThread& T, bool& bad) {
+__device__ __forceinline__ void prb_stage(const long long t, const real (&y)[PRB_NS], real (&k)[PRB_NS], PrbThread& T, PrbBad& bad) {
 #ifdef PRB_SPEC_STEP
     if (SPEC) prb_rhs_spec(t, y, k, T, bad);
     else      prb_rhs_exact(t, y, k, T);
@@ -434,14 +448,24 @@ __device__ __forceinline__ void prb_stage(const long long t, const real (&y)[PRB
 #endif
 }
 
-template <bool SPEC>
+// FINAL = false: `yn` receives the increment direction d of the step instead of the new state (y_new = y + prb_step_coef * d);
+// the caller finishes the update itself (PRB_SPEC_STEP: after it has looked at `bad`, so that both outcomes write y in place).
+#if PRB_SOLVER == PRB_SOLVER_EULER
+#define prb_step_coef(dt, hdt, dt6) (dt)
+#elif PRB_SOLVER == PRB_SOLVER_RK4
+#define prb_step_coef(dt, hdt, dt6) (dt6)
+#else
+#define prb_step_coef(dt, hdt, dt6) (hdt)
+#endif
+template <bool SPEC, bool FINAL = true>
 __device__ __forceinline__ void prb_step(const long long t, const real (&y)[PRB_NS], real (&yn)[PRB_NS], PrbThread& T,
-                                         const real dt, const real hdt, const real dt6, bool& bad) {
+                                         const real dt, const real hdt, const real dt6, PrbBad& bad) {
     real k[PRB_NS];
     (void)hdt; (void)dt6;
 #if PRB_SOLVER == PRB_SOLVER_EULER
     prb_stage<SPEC>(t, y, k, T, bad);
-    prb_axpy(yn, y, dt, k);
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) yn[j] = FINAL ? y[j] + dt * k[j] : k[j];
 #elif PRB_SOLVER == PRB_SOLVER_HEUN_REF
     // reference `heun`: rhs buffer is aliased, so both summands are the 2nd evaluation
     real ys[PRB_NS];
@@ -449,14 +473,14 @@ __device__ __forceinline__ void prb_step(const long long t, const real (&y)[PRB_
     prb_axpy(ys, y, dt, k);
     prb_stage<SPEC>(t, ys, k, T, bad);
     PRB_UNROLL_NS
-    for (int j = 0; j < PRB_NS; ++j) yn[j] = y[j] + hdt * (k[j] + k[j]);
+    for (int j = 0; j < PRB_NS; ++j) yn[j] = FINAL ? y[j] + hdt * (k[j] + k[j]) : k[j] + k[j];
 #elif PRB_SOLVER == PRB_SOLVER_HEUN
     real ys[PRB_NS], k2[PRB_NS];
     prb_stage<SPEC>(t, y, k, T, bad);
     prb_axpy(ys, y, dt, k);
     prb_stage<SPEC>(t, ys, k2, T, bad);
     PRB_UNROLL_NS
-    for (int j = 0; j < PRB_NS; ++j) yn[j] = y[j] + hdt * (k[j] + k2[j]);
+    for (int j = 0; j < PRB_NS; ++j) yn[j] = FINAL ? y[j] + hdt * (k[j] + k2[j]) : k[j] + k2[j];
 #elif PRB_SOLVER == PRB_SOLVER_RK4 && defined(PRB_Y_SMEM)
     // Register-lean variant (opt-in, PRB_Y_SMEM): the base state y lives in shared memory ([state][thread], one 8-byte word
     // per thread and state variable: conflict-free) and is re-read where a stage needs it, so that only the stage input, the
@@ -491,7 +515,7 @@ __device__ __forceinline__ void prb_step(const long long t, const real (&y)[PRB_
     for (int j = 0; j < PRB_NS; ++j) { acc[j] = acc[j] + (real)2 * k[j]; ys[j] = y[j] + dt * k[j]; }
     prb_stage<SPEC>(t, ys, k, T, bad);                      // k4
     PRB_UNROLL_NS
-    for (int j = 0; j < PRB_NS; ++j) yn[j] = y[j] + dt6 * (acc[j] + k[j]);
+    for (int j = 0; j < PRB_NS; ++j) yn[j] = FINAL ? y[j] + dt6 * (acc[j] + k[j]) : acc[j] + k[j];
 #else
 #error "unknown PRB_SOLVER"
 #endif
@@ -500,7 +524,7 @@ __device__ __forceinline__ void prb_step(const long long t, const real (&y)[PRB_
 #ifdef PRB_SPEC_STEP
 __device__ __noinline__ void prb_step_exact(const long long t, const real (&y)[PRB_NS], real (&yn)[PRB_NS], PrbThread& T,
                                             const real dt, const real hdt, const real dt6) {
-    bool unused = false;
+    PrbBad unused;
     prb_step<false>(t, y, yn, T, dt, hdt, dt6, unused);
 }
 #endif
@@ -550,7 +574,14 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
 #pragma unroll
     for (int o = 0; o < PRB_NOBS; ++o) { r_mean[o] = (real)0; r_m2[o] = (real)0; r_min[o] = (real)0; r_max[o] = (real)0; r_last[o] = (real)0; }
 #endif
-    for (long long i = 0; i < A.n_steps; ++i, ++t) {
+    // The time loop runs in BURSTS: up to the next stored sample (or the end of the launch) the steps run under a 32-bit counter
+    // with nothing else in the loop — the 64-bit step / decimation counters cost ~10 uniform-datapath instructions per step,
+    // which are not free next to a saturated FP64 pipe (profiles/r02_issue_probe.txt).
+#ifndef PRB_BURST_UNROLL
+#define PRB_BURST_UNROLL
+#endif
+    long long i = 0;
+    while (i < A.n_steps) {
         if (until_store == 0) {
 #ifdef PRB_REDUCE
             if (sample >= A.sample0) {
@@ -578,13 +609,53 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
             ++sample;
             until_store = store_step;
         }
-        --until_store;
+        long long left = A.n_steps - i;
+        if (until_store < left) left = until_store;
+        if (left > 0x40000000LL) left = 0x40000000LL;
+        const int burst = (int)left;                 // >= 1: until_store >= 1 here and i < n_steps
+        until_store -= burst;
+        PRB_BURST_UNROLL
+        for (int s = 0; s < burst; ++s, ++t) {
 
+        PrbBad bad;
+#if defined(PRB_SPEC_STEP) && !defined(PRB_Y_SMEM)
+        {
+            real d[PRB_NS];
+            prb_step<true, false>(t, y, d, T, dt, hdt, dt6, bad);
+            if (bad) {                                               // an argument left the fast range: redo the step exactly
+                // local copies: arrays handed to the out-of-line function by reference would otherwise live in local
+                // memory (stored every step, on the fast path too)
+                real yl[PRB_NS], ynl[PRB_NS];
+                PrbThread Tl = T;
+#if PRB_NP > 0
+                _Pragma("unroll") for (int k = 0; k < PRB_NP; ++k) Tl.p[k] = T.pbase[(long long)k * T.B + T.b];
+#endif
+                PRB_UNROLL_NS
+                for (int j = 0; j < PRB_NS; ++j) yl[j] = y[j];
+                prb_step_exact(t, yl, ynl, Tl, dt, hdt, dt6);
+                PRB_UNROLL_NS
+                for (int j = 0; j < PRB_NS; ++j) y[j] = ynl[j];
+            } else {                                                 // both outcomes write y in place: no copies at the join
+                PRB_UNROLL_NS
+                for (int j = 0; j < PRB_NS; ++j) y[j] = y[j] + prb_step_coef(dt, hdt, dt6) * d[j];
+            }
+        }
+#else
         real yn[PRB_NS];
-        bool bad = false;
 #ifdef PRB_SPEC_STEP
         prb_step<true>(t, y, yn, T, dt, hdt, dt6, bad);
-        if (bad) prb_step_exact(t, y, yn, T, dt, hdt, dt6);          // an argument left the fast range: redo the step exactly
+        if (bad) {
+            real yl[PRB_NS], ynl[PRB_NS];
+            PrbThread Tl = T;
+#if PRB_NP > 0
+            _Pragma("unroll") for (int k = 0; k < PRB_NP; ++k) Tl.p[k] = T.pbase[(long long)k * T.B + T.b];
+#endif
+            PRB_UNROLL_NS
+            for (int j = 0; j < PRB_NS; ++j) yl[j] = y[j];
+            prb_step_exact(t, yl, ynl, Tl, dt, hdt, dt6);
+            PRB_UNROLL_NS
+            for (int j = 0; j < PRB_NS; ++j) yn[j] = ynl[j];
+        }
 #else
         prb_step<false>(t, y, yn, T, dt, hdt, dt6, bad);
 #endif
@@ -595,9 +666,12 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
         PRB_UNROLL_NS
         for (int j = 0; j < PRB_NS; ++j) y[j] = yn[j];
 #endif
-#if PRB_NH > 0
-        prb_hist_push(T, y, A.step0 + i + 1);        // DDEHistory.update((i + 1) * dt, y)
 #endif
+#if PRB_NH > 0
+        prb_hist_push(T, y, A.step0 + i + s + 1);    // DDEHistory.update((i + 1) * dt, y)
+#endif
+        }   // burst
+        i += burst;
     }
 
 #ifdef PRB_REDUCE

@@ -27,6 +27,11 @@ _FUNC = {"exp": "exp", "log": "log", "sin": "sin", "cos": "cos", "tan": "tan", "
 
 
 ETAB_BITS = 11
+# Integer side of the fast exp (round 2): scaled shared-memory index, pre-compensated table, min / max range checks — 4 instead
+# of 8 non-fp64 instructions per call (profiles/r02_issue_probe.txt: instructions of other pipes are NOT free next to a
+# saturated FP64 pipe on B200).  PRB_EXP_LEAN=0 restores the round-1 form.
+def exp_lean() -> bool:
+    return os.environ.get("PRB_EXP_LEAN", "1") == "1"
 
 
 def exp_tables() -> str:
@@ -45,8 +50,15 @@ def exp_tables() -> str:
         return float(np.array([np.float64(x).view(np.uint64) & ~np.uint64(0xFFFFFFFF)], dtype=np.uint64).view(np.float64)[0])
     hi = high_word(float(c))
     lo = float(c - ld(hi))
-    return (f"#define PRB_ETAB_BITS {ETAB_BITS}\n#define PRB_ETAB_N {n}\n"
-            f"#define PRB_EXP_ESTRIN {1 if os.environ.get('PRB_EXP_ESTRIN', '0') == '1' else 0}\n"
+    if exp_lean():
+        # entry j is stored with its high word lowered by j << (20 - ETAB_BITS): the kernel then scales by 2^k with ONE integer
+        # multiply-add  hi' + (n << (20 - ETAB_BITS))  (n = 2048 k + j), instead of shift + mask + add
+        raw = np.array(tab, dtype=np.float64).view(np.uint64)
+        raw = raw - (np.arange(n, dtype=np.uint64) << np.uint64(32 + 20 - ETAB_BITS))
+        tab = [float(v) for v in raw.view(np.float64)]
+    return (f"#define PRB_ETAB_BITS {ETAB_BITS}\n#define PRB_ETAB_N {n}\n#define PRB_EXP_LEAN {1 if exp_lean() else 0}\n"
+            f"#define PRB_EXP_PINK0 {1 if os.environ.get('PRB_EXP_PINK0', '1') == '1' else 0}\n"
+            f"#define PRB_EXP_ESTRIN {1 if os.environ.get('PRB_EXP_ESTRIN', '1') == '1' else 0}\n"
             f"#define PRB_EXP_HI ({hi!r})\n#define PRB_EXP_C3 ({high_word(1.0 / 6.0)!r})\n"
             f"__device__ __constant__ double PRB_EXP_TAB[{n}] = {{" + ", ".join(repr(v) for v in tab) + "};\n"
             f"__device__ __constant__ double PRB_EXP_K[2] = {{{float(ld(n) / ln2)!r}, {lo!r}}};   "
@@ -218,13 +230,28 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
         skip_exp = {e for e, _ in fused_exp.values()}
     else:
         skip_exp = set()
+    litscaled: dict = {}
+    regfirst = bool(spec and hoist is not None and os.environ.get("PRB_MAT_REGFIRST", "1") == "1")
+    lone_mul: set = set()            # register products that START a sum of literal-coefficient terms: kept a plain multiply
+    if regfirst:
+        def _litscaled(n):
+            if g.isint[n] or g.ops[n] not in ("mul", "div"):
+                return False
+            base, f = const_chain(n)
+            return base != n and math.isfinite(f) and f != 0.0
+        for i in live:
+            if g.ops[i] == "add" and not g.isint[i]:
+                for x, o in ((g.args[i][0], g.args[i][1]), (g.args[i][1], g.args[i][0])):
+                    if _litscaled(x) and g.ops[o] == "mul" and not _litscaled(o) and \
+                            (invariant.get(g.args[o][0]) or invariant.get(g.args[o][1])):
+                        lone_mul.add(o)
     for i in live:
         op, a = g.ops[i], g.args[i]
         if op in ("const", "state", "param", "t") or i in skip_exp:
             continue
         if i in fused_exp:
             e, c = fused_exp[i]
-            lines.append(f"const areal v{i} = prb_spec_exp_plus({ref(g.args[e][0])}, {lit(c)}, T.etab_s, bad);")
+            lines.append(f"const areal v{i} = prb_spec_exp_plus({ref(g.args[e][0])}, {lit(c)}, T.ek0, T.etab_s, bad);")
             continue
         if hoist is not None and invariant.get(i) and not g.isint[i]:
             # thread-invariant: once per thread, exact arithmetic (prb_thread_init)
@@ -258,6 +285,7 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
                 f = float(np.float32(f))
             if base != i and math.isfinite(f) and f != 0.0:
                 lines.append(f"const areal v{i} = {ref(base)} * {lit(f)};")
+                litscaled[i] = (base, f)
                 continue
         if g.isint[i]:
             x, y_ = (ref(a[0], False), ref(a[1], False) if len(a) > 1 else None)
@@ -279,6 +307,13 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
             L = rhs.rings[ring].length
             expr = (f"T.rings[({int(ring_off[ring]) + row * L}LL + prb_ring_pos(T.head[{ring}], {col - shift}, {L})) "
                     f"* T.B + T.b]")
+        elif op == "add" and regfirst and (a[1] in litscaled or a[0] in litscaled):
+            # explicit contraction: the literal-coefficient product joins by FMA (immediate operand, two register reads); left
+            # to the compiler, `q*s + y*c` may fuse the register product instead and multiply y*c separately (three reads)
+            x, o = (a[1], a[0]) if a[1] in litscaled else (a[0], a[1])
+            expr = f"fma({ref(litscaled[x][0])}, {lit(litscaled[x][1])}, {ref(o)})"
+        elif op == "mul" and i in lone_mul:
+            expr = f"__dmul_rn({ref(a[0])}, {ref(a[1])})"
         elif op == "add":
             expr = f"{ref(a[0])} + {ref(a[1])}"
         elif op == "sub":
@@ -313,7 +348,7 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
         elif op == "exp" and fast_math and f32:
             expr = f"__expf({ref(a[0])})"                               # ex2.approx(x * log2 e): ~2 ulp + |x| 2^-24
         elif op == "exp" and fast_math and not f32:
-            expr = f"prb_spec_exp({ref(a[0])}, T.etab_s, bad)" if spec else f"prb_fast_exp({ref(a[0])}, T.etab)"
+            expr = f"prb_spec_exp({ref(a[0])}, T.ek0, T.etab_s, bad)" if spec else f"prb_fast_exp({ref(a[0])}, T.etab)"
         elif op in _FUNC:
             expr = f"{_FUNC[op]}({ref(a[0])})"
         else:
@@ -460,6 +495,7 @@ struct PrbThread {
     const real* __restrict__ tables;
     const double* etab;            // shared-memory copy of PRB_EXP_TAB (fast_math kernels)
     unsigned int etab_s;           // the same as a 32-bit shared-window address (ld.shared without S2UR per use)
+    double ek0;                    // 2048/ln2, pinned in a register pair (prb_spec_exp)
     unsigned int ysm_s;            // PRB_Y_SMEM: shared-window address of this thread's column of the base state
 #if PRB_NH > 0
 #if PRB_HDEPTH > 0                 // fixed-step history: ring [PRB_HDEPTH][PRB_NH][B] of the states after steps 0..hn
@@ -528,67 +564,109 @@ __device__ __forceinline__ double prb_hist(PrbThread& T, const int k, const doub
 @@EXP_TABLES@@
 __device__ __noinline__ double prb_exp_slow(const double z) { return exp(z); }
 __device__ __noinline__ double prb_div_slow(const double a, const double b) { return a / b; }
+// Range violations of one speculative evaluation (or step).  exp arguments are checked through the running signed AND unsigned
+// maxima of their high words — |z| <= 700 and not NaN  <=>  hi <= 0x4085e000 as a signed int (covers z >= 0; every negative z
+// passes) and hi <= 0xc085e000 as an unsigned int (covers z < 0; every positive z passes) — i.e. two 3-input min/max
+// instructions per three calls instead of one mask per call plus the maximum.
+struct PrbBad {
+    int smax; unsigned int umax; bool flag;
+    __device__ __forceinline__ PrbBad() : smax((int)0x80000000), umax(0u), flag(false) {}
+    __device__ __forceinline__ PrbBad& operator|=(const bool b) { flag |= b; return *this; }
+    __device__ __forceinline__ void exp_arg(const int hi) { smax = max(smax, hi); umax = max(umax, (unsigned int)hi); }
+    __device__ __forceinline__ operator bool() const { return flag | (smax > 0x4085e000) | (umax > 0xc085e000u); }
+};
+#if PRB_EXP_LEAN
+// shared-memory copy of the table at file scope: the accessor sees a __shared__ array, so the load takes a scaled index
+// (LDS.64 [R.X8 + base]) and the entry — stored with its high word lowered by j << 9 — is scaled by 2^k with one integer
+// multiply-add: hi' + (n << 9) = hi(2^(j/2048)) + (k << 20) for n = 2048 k + j
+__shared__ double prb_etab[PRB_ETAB_N + 2];
+#define PRB_ETAB_FILE_SCOPE 1
+__device__ __forceinline__ double prb_etab_scaled(const int n) {
+    const double tj = prb_etab[n & (PRB_ETAB_N - 1)];
+    return __hiloint2double(__double2hiint(tj) + (n << (20 - PRB_ETAB_BITS)), __double2loint(tj));
+}
+#define PRB_ETAB_SCALED(tab, n) prb_etab_scaled(n)
+#else
+__device__ __forceinline__ double prb_etab_scaled_s(const unsigned int tab, const int n) {
+    double tj;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab + ((unsigned int)(n & (PRB_ETAB_N - 1)) << 3)));
+    return __hiloint2double(__double2hiint(tj) + ((n >> PRB_ETAB_BITS) << 20), __double2loint(tj));
+}
+#define PRB_ETAB_SCALED(tab, n) prb_etab_scaled_s(tab, n)
+#endif
+// q(r) = r + r^2/2 + c3 r^3 on |r| <= ln2/4096
+__device__ __forceinline__ double prb_exp_poly(const double r) {
+#if PRB_EXP_ESTRIN
+    const double r2 = r * r;                                                 // Estrin: q = r + r^2 (1/2 + c3 r), two levels deep
+    return fma(r2, fma(r, PRB_EXP_C3, 0.5), r);
+#else
+    double q = fma(r, PRB_EXP_C3, 0.5);                                      // every coefficient an instruction immediate
+    q = fma(q, r, 1.0);
+    return q * r;
+#endif
+}
 __device__ __forceinline__ double prb_fast_exp(const double z, const double* __restrict__ tab) {
     if (!(fabs(z) <= 700.0)) return prb_exp_slow(z);
-    const double t = fma(z, PRB_EXP_K[0], 6755399441055744.0);               // 256/ln2, 1.5 * 2^52 (an immediate)
+    const double t = fma(z, PRB_EXP_K[0], 6755399441055744.0);               // 2048/ln2, 1.5 * 2^52 (an immediate)
     const int n = __double2loint(t);
     const double nd = t - 6755399441055744.0;
     double r = fma(nd, PRB_EXP_HI, z);                                       // -ln2/2048, high word (an immediate)
     r = fma(nd, PRB_EXP_K[1], r);                                            //            low part
-    double q = fma(r, PRB_EXP_C3, 0.5);                                      // |r| <= ln2/4096: degree 3, every coefficient
-    q = fma(q, r, 1.0);                                                      // an instruction immediate
-    q = q * r;
+    const double q = prb_exp_poly(r);
+#if PRB_EXP_LEAN
+    const double ts = prb_etab_scaled(n);                                    // 2^k * 2^(j/2048): |x| <= 700 keeps it normal
+    return fma(ts, q, ts);
+#else
     const double tj = tab[n & (PRB_ETAB_N - 1)];
     const double e = fma(tj, q, tj);
-    return __hiloint2double(__double2hiint(e) + ((n >> PRB_ETAB_BITS) << 20), __double2loint(e));   // * 2^k: |x| <= 700 keeps it normal
+    return __hiloint2double(__double2hiint(e) + ((n >> PRB_ETAB_BITS) << 20), __double2loint(e));
+#endif
 }
-// speculative variants: no branch per call — the caller accumulates one `bad` flag per rhs evaluation and re-evaluates
-// the whole (pure) vector field with the library functions in the rare case an argument left the fast range.  The range
-// checks are integer compares on the high word (an fp64 compare would occupy the FP64 pipe the kernel is bound by).
-__device__ __forceinline__ double prb_spec_exp(const double z, const unsigned int tab, bool& bad) {
-    bad |= (unsigned int)(__double2hiint(z) & 0x7fffffff) > 0x4085e000u;     // |z| > 700 (or NaN)
-    const double t = fma(z, PRB_EXP_K[0], 6755399441055744.0);
+// speculative variants: no branch per call — the caller accumulates the range violations of one rhs evaluation in `bad` and
+// re-evaluates the whole (pure) vector field with the library functions in the rare case an argument left the fast range.
+// The range checks are integer work on the high word (an fp64 compare would occupy the FP64 pipe the kernel is bound by).
+// k0 = 2048/ln2 from a register the caller pins for the whole launch (T.ek0): as a __constant__ read the compiler keeps it in a
+// uniform register and copies it into a register pair before EVERY use (the multiply-add already has an immediate operand)
+__device__ __forceinline__ double prb_spec_exp(const double z, const double k0, const unsigned int tab, PrbBad& bad) {
+#if PRB_EXP_LEAN
+    bad.exp_arg(__double2hiint(z));                                          // |z| > 700 (or NaN)
+#else
+    bad |= (unsigned int)(__double2hiint(z) & 0x7fffffff) > 0x4085e000u;
+#endif
+    const double t = fma(z, k0, 6755399441055744.0);
     const int n = __double2loint(t);
     const double nd = t - 6755399441055744.0;                                // (an I2F on the conversion pipe instead was measured: no gain)
     double r = fma(nd, PRB_EXP_HI, z);
     r = fma(nd, PRB_EXP_K[1], r);
-#if PRB_EXP_ESTRIN
-    const double r2 = r * r;                                                 // Estrin: q = r + r^2 (1/2 + c3 r), two levels deep
-    const double q = fma(r2, fma(r, PRB_EXP_C3, 0.5), r);
+    const double q = prb_exp_poly(r);
+#if PRB_EXP_LEAN
+    const double ts = PRB_ETAB_SCALED(tab, n);
+    return fma(ts, q, ts);
 #else
-    double q = fma(r, PRB_EXP_C3, 0.5);
-    q = fma(q, r, 1.0);
-    q = q * r;
-#endif
     double tj;
     asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab + ((unsigned int)(n & (PRB_ETAB_N - 1)) << 3)));
     const double e = fma(tj, q, tj);
     return __hiloint2double(__double2hiint(e) + ((n >> PRB_ETAB_BITS) << 20), __double2loint(e));
+#endif
 }
 // c + e^z in one go (sigmoid denominators): the table value is scaled by 2^k first (integer work, off the critical path), so
 // the sum joins the final FMA: c + T (1 + q) = fma(T, q, T + c) — one dependent instruction less than exp followed by an add
-__device__ __forceinline__ double prb_spec_exp_plus(const double z, const double c, const unsigned int tab, bool& bad) {
+__device__ __forceinline__ double prb_spec_exp_plus(const double z, const double c, const double k0, const unsigned int tab, PrbBad& bad) {
+#if PRB_EXP_LEAN
+    bad.exp_arg(__double2hiint(z));
+#else
     bad |= (unsigned int)(__double2hiint(z) & 0x7fffffff) > 0x4085e000u;
-    const double t = fma(z, PRB_EXP_K[0], 6755399441055744.0);
+#endif
+    const double t = fma(z, k0, 6755399441055744.0);
     const int n = __double2loint(t);
     const double nd = t - 6755399441055744.0;
-    double tj;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab + ((unsigned int)(n & (PRB_ETAB_N - 1)) << 3)));
-    const double ts = __hiloint2double(__double2hiint(tj) + ((n >> PRB_ETAB_BITS) << 20), __double2loint(tj));
+    const double ts = PRB_ETAB_SCALED(tab, n);
     const double s = ts + c;
     double r = fma(nd, PRB_EXP_HI, z);
     r = fma(nd, PRB_EXP_K[1], r);
-#if PRB_EXP_ESTRIN
-    const double r2 = r * r;
-    const double q = fma(r2, fma(r, PRB_EXP_C3, 0.5), r);
-#else
-    double q = fma(r, PRB_EXP_C3, 0.5);
-    q = fma(q, r, 1.0);
-    q = q * r;
-#endif
-    return fma(ts, q, s);
+    return fma(ts, prb_exp_poly(r), s);
 }
-__device__ __forceinline__ double prb_spec_div(const double a, const double b, bool& bad) {
+__device__ __forceinline__ double prb_spec_div(const double a, const double b, PrbBad& bad) {
     bad |= (((unsigned int)__double2hiint(b) & 0x7ff00000u) - 0x04000000u) >= 0x77c00000u;   // |b| outside ~[1e-289, 1e288]
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
@@ -602,7 +680,7 @@ __device__ __forceinline__ double prb_spec_rcp_nc(const double b) {
     const double e = fma(-b, r, 1.0);
     return fma(r, fma(e, e, e), r);
 }
-__device__ __forceinline__ double prb_spec_rcp(const double b, bool& bad) {
+__device__ __forceinline__ double prb_spec_rcp(const double b, PrbBad& bad) {
     bad |= (((unsigned int)__double2hiint(b) & 0x7ff00000u) - 0x04000000u) >= 0x77c00000u;
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
@@ -651,7 +729,7 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
         vals = body.pop(0)[len("// PRB_LIT = {"):-1]
         src.append(f"__device__ __constant__ double PRB_LIT[{vals.count(',') + 1}] = {{{vals}}};")
     init = ["__device__ __forceinline__ void prb_thread_init(PrbThread& T, const prb_kernel_args& A, long long b) {",
-            "    T.b = b; T.B = A.n_inst; T.etab = nullptr; T.etab_s = 0u; T.pbase = (const real*)A.params;",
+            "    T.b = b; T.B = A.n_inst; T.etab = nullptr; T.etab_s = 0u; T.ek0 = 0.0; T.pbase = (const real*)A.params;",
             "    T.slots = (real*)A.slots; T.rings = (real*)A.rings; T.tables = (const real*)A.tables;"]
     if np_:
         init.append("    const real* __restrict__ P = (const real*)A.params;")
@@ -698,20 +776,23 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
         src.append("}")
     if spec:
         # speculative evaluation: `bad` is only accumulated; the caller decides when to look at it.  The fixed-step solver
-        # template checks it ONCE PER STEP (PRB_SPEC_STEP): the stages of a step then form one basic block (no reconvergence
-        # point after every evaluation), and a step that saw an out-of-range argument is recomputed by prb_step_exact.
-        # Opt-in (PRB_SPEC_PER_STEP=1).  Measured A/B on one B200 (JRC RK4 sweep): the per-step form issues 7 % fewer
-        # instructions but takes the same number of cycles (the kernel is bound by dependency latency at 4 warps per
-        # scheduler) while drawing 1009 W instead of 743 W — the board then power-caps to 1822 MHz and the run is 8.6 %
-        # SLOWER (218.0 vs 200.5 ms).  The per-evaluation check stays the default.
-        if os.environ.get("PRB_SPEC_PER_STEP") == "1":
+        # template checks it ONCE PER STEP (PRB_SPEC_STEP): the stages of a step then form one basic block (one reconvergence
+        # point per step instead of one per evaluation — a branch construct costs ~5 issue cycles next to a saturated FP64
+        # pipe, profiles/r02_issue_probe2.txt), and a step that saw an out-of-range argument is recomputed by prb_step_exact.
+        # Default since round 2 (PRB_SPEC_PER_STEP=0 restores the per-evaluation check).  History: the round-1 form of this
+        # option handed y / yn to the out-of-line exact step by reference, which put both arrays in local memory (8 x
+        # STL.128 per step on the FAST path) and copied yn -> y at the join; it was measured slower then.  Now the step
+        # returns its increment and both outcomes update y in place (inst_kernel.cuh).
+        if os.environ.get("PRB_SPEC_PER_STEP", "1") == "1":
             src.append("#define PRB_SPEC_STEP 1")
-        src.append("__device__ __forceinline__ void prb_rhs_spec(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NDY], PrbThread& T, bool& bad) {")
+        if os.environ.get("PRB_BURST_UNROLL", "1") != "1":
+            src.append(f"#define PRB_BURST_UNROLL _Pragma(\"unroll {int(os.environ['PRB_BURST_UNROLL'])}\")")
+        src.append("__device__ __forceinline__ void prb_rhs_spec(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NDY], PrbThread& T, PrbBad& bad) {")
         src.extend("    " + l for l in body)
         src.append("}")
     src.append("__device__ __forceinline__ void prb_rhs(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NDY], PrbThread& T) {")
     if spec:
-        src.append("    bool bad = false;")
+        src.append("    PrbBad bad;")
         src.append("    prb_rhs_spec(t, y, dy, T, bad);")
         src.append("    if (bad) {                  // an exp / division argument left the fast range: redo this evaluation exactly")
         src.append("        areal yl[PRB_NS], dl[PRB_NDY];")

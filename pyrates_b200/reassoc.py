@@ -25,6 +25,7 @@ float32: `__expf` / `__fdividef` kernels — JRC RK4 sweep 3.7e11 -> 4.0e11 node
 from __future__ import annotations
 
 import copy
+import os
 from typing import Dict, List, Optional, Tuple
 
 from .scalarize import Graph, ScalarRhs, Sym
@@ -89,7 +90,16 @@ def fold_invariants(rhs: ScalarRhs, max_terms: int = 6) -> ScalarRhs:
         # shallow bases first: the term that hangs on the longest chain (a sigmoid's reciprocal) joins the sum LAST, so
         # only one FMA follows it on the critical path of the evaluation (the kernels are bound by dependency latency)
         acc = lc.inv
-        for k, b in sorted(lc.terms, key=lambda kb: depth(kb[1].id)):
+        terms = sorted(lc.terms, key=lambda kb: depth(kb[1].id))
+        if acc is None and os.environ.get("PRB_MAT_REGFIRST", "1") == "1":
+            # register-file reads (B200: an FP64 instruction with three distinct register operands issues in 3 cycles instead
+            # of 2, profiles/r02_issue_probe.txt): literal coefficients are instruction immediates, per-thread coefficients
+            # sit in registers — a sum without an invariant offset starts with ONE such product as a plain multiply (two
+            # reads) and adds the literal-coefficient terms by FMA (two reads each), at the price of a longer chain behind it
+            reg = [kb for kb in terms if kb[0] is not None and not ng.is_const(kb[0].id)]
+            if len(reg) >= 1 and len(terms) >= 2:
+                terms = [reg[-1]] + [kb for kb in terms if kb is not reg[-1]]
+        for k, b in terms:
             t = b if k is None else ng.binop("mul", b, k)
             acc = t if acc is None else ng.binop("add", acc, t)
         return acc if acc is not None else ng.const(0.0, weak=True)
