@@ -502,6 +502,41 @@ __device__ __forceinline__ void prb_step(const long long t, const real (&y)[PRB_
     PRB_UNROLL_NS
     for (int j = 0; j < PRB_NS; ++j) yn[j] = prb_ysm_ld(T, j) + dt6 * (acc[j] + k[j]);
     (void)y;
+#elif PRB_SOLVER == PRB_SOLVER_RK4 && defined(PRB_INTEG_PAIRS)
+    if constexpr (FINAL) {                                  // the out-of-line exact step: plain RK4
+        real ys[PRB_NS], acc[PRB_NS];
+        prb_stage<SPEC>(t, y, k, T, bad);
+        PRB_UNROLL_NS
+        for (int j = 0; j < PRB_NS; ++j) { acc[j] = k[j]; ys[j] = y[j] + hdt * k[j]; }
+        prb_stage<SPEC>(t, ys, k, T, bad);
+        PRB_UNROLL_NS
+        for (int j = 0; j < PRB_NS; ++j) { acc[j] = acc[j] + (real)2 * k[j]; ys[j] = y[j] + hdt * k[j]; }
+        prb_stage<SPEC>(t, ys, k, T, bad);
+        PRB_UNROLL_NS
+        for (int j = 0; j < PRB_NS; ++j) { acc[j] = acc[j] + (real)2 * k[j]; ys[j] = y[j] + dt * k[j]; }
+        prb_stage<SPEC>(t, ys, k, T, bad);
+        PRB_UNROLL_NS
+        for (int j = 0; j < PRB_NS; ++j) yn[j] = y[j] + dt6 * (acc[j] + k[j]);
+    } else {
+    // Integrator chains (PRB_INTEG[j] = b >= 0: dy_j == y_b, so k_j of a stage IS that stage's y_b).  Such a state needs no
+    // accumulator:  y_j' = y_j + dt y_b + dt^2/6 (k1 + k2 + k3)_b  exactly, and every other state takes its increment from the
+    // same sum:  k1 + 2 k2 + 2 k3 + k4 = 2 S + (k4 - k1),  S = k1 + k2 + k3.  Only instantiated with FINAL = false: `yn`
+    // receives S of the SOURCE state for chain states (prb_step_finish applies the formula) and 2 S + (k4 - k1) otherwise.
+    real ys[PRB_NS], k1[PRB_NS], S[PRB_NS];
+    prb_stage<SPEC>(t, y, k, T, bad);                       // k1
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) { k1[j] = k[j]; ys[j] = y[j] + hdt * k[j]; }
+    prb_stage<SPEC>(t, ys, k, T, bad);                      // k2
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) { S[j] = k1[j] + k[j]; ys[j] = y[j] + hdt * k[j]; }
+    prb_stage<SPEC>(t, ys, k, T, bad);                      // k3
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j) { S[j] = S[j] + k[j]; ys[j] = y[j] + dt * k[j]; }
+    prb_stage<SPEC>(t, ys, k, T, bad);                      // k4
+    PRB_UNROLL_NS
+    for (int j = 0; j < PRB_NS; ++j)
+        yn[j] = PRB_INTEG[j] >= 0 ? S[PRB_INTEG[j]] : (real)2 * S[j] + (k[j] - k1[j]);
+    }
 #elif PRB_SOLVER == PRB_SOLVER_RK4
     real ys[PRB_NS], acc[PRB_NS];
     prb_stage<SPEC>(t, y, k, T, bad);                       // k1
@@ -636,8 +671,17 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
                 PRB_UNROLL_NS
                 for (int j = 0; j < PRB_NS; ++j) y[j] = ynl[j];
             } else {                                                 // both outcomes write y in place: no copies at the join
+#ifdef PRB_INTEG_PAIRS
+                real yo[PRB_NS];
+                PRB_UNROLL_NS
+                for (int j = 0; j < PRB_NS; ++j) yo[j] = y[j];
+                PRB_UNROLL_NS
+                for (int j = 0; j < PRB_NS; ++j)
+                    y[j] = PRB_INTEG[j] >= 0 ? (yo[j] + dt * yo[PRB_INTEG[j]]) + (dt * dt6) * d[j] : yo[j] + dt6 * d[j];
+#else
                 PRB_UNROLL_NS
                 for (int j = 0; j < PRB_NS; ++j) y[j] = y[j] + prb_step_coef(dt, hdt, dt6) * d[j];
+#endif
             }
         }
 #else

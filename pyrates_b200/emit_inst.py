@@ -30,8 +30,12 @@ ETAB_BITS = 11
 # Integer side of the fast exp (round 2): scaled shared-memory index, pre-compensated table, min / max range checks — 4 instead
 # of 8 non-fp64 instructions per call (profiles/r02_issue_probe.txt: instructions of other pipes are NOT free next to a
 # saturated FP64 pipe on B200).  PRB_EXP_LEAN=0 restores the round-1 form.
-def exp_lean() -> bool:
-    return os.environ.get("PRB_EXP_LEAN", "1") == "1"
+def exp_lean() -> int:
+    """0: round-1 integer side; 1: pre-compensated table, 2^k applied to the table value BEFORE the final FMA (3 integer
+    instructions per call, but the first consumer of the shared-memory load is an early integer instruction: the load latency
+    is exposed); 2: plain table, the exponent bits (n & ~2047) << 9 are prepared early and added to the FMA RESULT (4 integer
+    instructions, the load's first consumer is the final FMA behind the polynomial)."""
+    return int(os.environ.get("PRB_EXP_LEAN", "1"))
 
 
 def exp_tables() -> str:
@@ -50,14 +54,15 @@ def exp_tables() -> str:
         return float(np.array([np.float64(x).view(np.uint64) & ~np.uint64(0xFFFFFFFF)], dtype=np.uint64).view(np.float64)[0])
     hi = high_word(float(c))
     lo = float(c - ld(hi))
-    if exp_lean():
+    if exp_lean() == 1:
         # entry j is stored with its high word lowered by j << (20 - ETAB_BITS): the kernel then scales by 2^k with ONE integer
         # multiply-add  hi' + (n << (20 - ETAB_BITS))  (n = 2048 k + j), instead of shift + mask + add
         raw = np.array(tab, dtype=np.float64).view(np.uint64)
         raw = raw - (np.arange(n, dtype=np.uint64) << np.uint64(32 + 20 - ETAB_BITS))
         tab = [float(v) for v in raw.view(np.float64)]
-    return (f"#define PRB_ETAB_BITS {ETAB_BITS}\n#define PRB_ETAB_N {n}\n#define PRB_EXP_LEAN {1 if exp_lean() else 0}\n"
+    return (f"#define PRB_ETAB_BITS {ETAB_BITS}\n#define PRB_ETAB_N {n}\n#define PRB_EXP_LEAN {exp_lean()}\n"
             f"#define PRB_EXP_PINK0 {1 if os.environ.get('PRB_EXP_PINK0', '1') == '1' else 0}\n"
+            f"#define PRB_RANGE_SHIFT {1 if os.environ.get('PRB_RANGE_SHIFT', '0') == '1' else 0}\n"
             f"#define PRB_EXP_ESTRIN {1 if os.environ.get('PRB_EXP_ESTRIN', '1') == '1' else 0}\n"
             f"#define PRB_EXP_HI ({hi!r})\n#define PRB_EXP_C3 ({high_word(1.0 / 6.0)!r})\n"
             f"__device__ __constant__ double PRB_EXP_TAB[{n}] = {{" + ", ".join(repr(v) for v in tab) + "};\n"
@@ -572,20 +577,43 @@ struct PrbBad {
     int smax; unsigned int umax; bool flag;
     __device__ __forceinline__ PrbBad() : smax((int)0x80000000), umax(0u), flag(false) {}
     __device__ __forceinline__ PrbBad& operator|=(const bool b) { flag |= b; return *this; }
+#if PRB_RANGE_SHIFT
+    // variant: drop the sign with a shift (an IMAD.SHL, nearly free next to the FP64 pipe) and keep ONE unsigned maximum
+    __device__ __forceinline__ void exp_arg(const int hi) { umax = max(umax, (unsigned int)hi << 1); }
+    __device__ __forceinline__ operator bool() const { return flag | (umax > 0x810bc000u); }
+#else
     __device__ __forceinline__ void exp_arg(const int hi) { smax = max(smax, hi); umax = max(umax, (unsigned int)hi); }
     __device__ __forceinline__ operator bool() const { return flag | (smax > 0x4085e000) | (umax > 0xc085e000u); }
+#endif
 };
 #if PRB_EXP_LEAN
-// shared-memory copy of the table at file scope: the accessor sees a __shared__ array, so the load takes a scaled index
-// (LDS.64 [R.X8 + base]) and the entry — stored with its high word lowered by j << 9 — is scaled by 2^k with one integer
-// multiply-add: hi' + (n << 9) = hi(2^(j/2048)) + (k << 20) for n = 2048 k + j
+// shared-memory copy of the table at file scope: the accessors see a __shared__ array
 __shared__ double prb_etab[PRB_ETAB_N + 2];
 #define PRB_ETAB_FILE_SCOPE 1
+#endif
+#if PRB_EXP_LEAN == 1
+// the entry — stored with its high word lowered by j << 9 — is scaled by 2^k with one integer multiply-add:
+// hi' + (n << 9) = hi(2^(j/2048)) + (k << 20) for n = 2048 k + j
 __device__ __forceinline__ double prb_etab_scaled(const int n) {
     const double tj = prb_etab[n & (PRB_ETAB_N - 1)];
     return __hiloint2double(__double2hiint(tj) + (n << (20 - PRB_ETAB_BITS)), __double2loint(tj));
 }
 #define PRB_ETAB_SCALED(tab, n) prb_etab_scaled(n)
+// 2^k T (1 + q) + c
+__device__ __forceinline__ double prb_exp_finish(const int n, const double q, const double c, const bool plus) {
+    const double ts = prb_etab_scaled(n);
+    return plus ? fma(ts, q, ts + c) : fma(ts, q, ts);
+}
+#elif PRB_EXP_LEAN == 2
+// plain table; the exponent bits are prepared from n alone (no dependence on the load) and join AFTER the FMA, so the load's
+// first consumer sits behind the polynomial
+__device__ __forceinline__ double prb_exp_finish(const int n, const double q, const double c, const bool plus) {
+    const double tj = prb_etab[n & (PRB_ETAB_N - 1)];
+    const int kb = n & ~(PRB_ETAB_N - 1);
+    const double e = fma(tj, q, tj);
+    const double es = __hiloint2double(__double2hiint(e) + (kb << (20 - PRB_ETAB_BITS)), __double2loint(e));
+    return plus ? es + c : es;
+}
 #else
 __device__ __forceinline__ double prb_etab_scaled_s(const unsigned int tab, const int n) {
     double tj;
@@ -614,8 +642,7 @@ __device__ __forceinline__ double prb_fast_exp(const double z, const double* __r
     r = fma(nd, PRB_EXP_K[1], r);                                            //            low part
     const double q = prb_exp_poly(r);
 #if PRB_EXP_LEAN
-    const double ts = prb_etab_scaled(n);                                    // 2^k * 2^(j/2048): |x| <= 700 keeps it normal
-    return fma(ts, q, ts);
+    return prb_exp_finish(n, q, 0.0, false);                                 // 2^k * 2^(j/2048) (1 + q): |x| <= 700 keeps it normal
 #else
     const double tj = tab[n & (PRB_ETAB_N - 1)];
     const double e = fma(tj, q, tj);
@@ -640,8 +667,7 @@ __device__ __forceinline__ double prb_spec_exp(const double z, const double k0, 
     r = fma(nd, PRB_EXP_K[1], r);
     const double q = prb_exp_poly(r);
 #if PRB_EXP_LEAN
-    const double ts = PRB_ETAB_SCALED(tab, n);
-    return fma(ts, q, ts);
+    return prb_exp_finish(n, q, 0.0, false);
 #else
     double tj;
     asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab + ((unsigned int)(n & (PRB_ETAB_N - 1)) << 3)));
@@ -660,11 +686,17 @@ __device__ __forceinline__ double prb_spec_exp_plus(const double z, const double
     const double t = fma(z, k0, 6755399441055744.0);
     const int n = __double2loint(t);
     const double nd = t - 6755399441055744.0;
+#if PRB_EXP_LEAN
+    double r = fma(nd, PRB_EXP_HI, z);
+    r = fma(nd, PRB_EXP_K[1], r);
+    return prb_exp_finish(n, prb_exp_poly(r), c, true);
+#else
     const double ts = PRB_ETAB_SCALED(tab, n);
     const double s = ts + c;
     double r = fma(nd, PRB_EXP_HI, z);
     r = fma(nd, PRB_EXP_K[1], r);
     return fma(ts, prb_exp_poly(r), s);
+#endif
 }
 __device__ __forceinline__ double prb_spec_div(const double a, const double b, PrbBad& bad) {
     bad |= (((unsigned int)__double2hiint(b) & 0x7ff00000u) - 0x04000000u) >= 0x77c00000u;   // |b| outside ~[1e-289, 1e288]
@@ -785,6 +817,16 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
         # returns its increment and both outcomes update y in place (inst_kernel.cuh).
         if os.environ.get("PRB_SPEC_PER_STEP", "1") == "1":
             src.append("#define PRB_SPEC_STEP 1")
+        # integrator chains (dy_j == y_b, e.g. dV/dt = I of every second-order synapse): RK4 needs no stage accumulator for
+        # such a state — V_new = V + dt I + dt^2/6 (k1 + k2 + k3)_I exactly — which saves one FP64 instruction per chain and
+        # step (fast_math sweeps only: algebraically exact, different rounding at the 1e-16 level).  Opt-in
+        # (PRB_INTEG_PAIRS=1): measured on the JRC sweep 260 instead of 264 fp64 instructions but 3 more integer ones and 4
+        # more three-operand FMAs — 18.16 vs 18.07 ms per 1000 steps, no gain (profiles/r02_tune_lean8.jsonl)
+        integ = [(int(fast_rhs.graph.payload[n]) if fast_rhs.graph.ops[n] == "state" else -1) for n in fast_rhs.dy]
+        if solver == "rk4" and not f32 and os.environ.get("PRB_INTEG_PAIRS", "0") == "1" and any(b >= 0 for b in integ) \
+                and len(integ) == ns and os.environ.get("PRB_SPEC_PER_STEP", "1") == "1":
+            src.append("#define PRB_INTEG_PAIRS 1")
+            src.append(f"__device__ constexpr int PRB_INTEG[PRB_NS] = {{{', '.join(str(b) for b in integ)}}};")
         if os.environ.get("PRB_BURST_UNROLL", "1") != "1":
             src.append(f"#define PRB_BURST_UNROLL _Pragma(\"unroll {int(os.environ['PRB_BURST_UNROLL'])}\")")
         src.append("__device__ __forceinline__ void prb_rhs_spec(const prb_time t, const areal (&y)[PRB_NS], areal (&dy)[PRB_NDY], PrbThread& T, PrbBad& bad) {")

@@ -41,7 +41,7 @@ def test_delay_differential_kernels_carry_a_history():
     k = fixed.kernel
     # delays 0.0173 / 0.0091 at dt = 1e-4: 173 steps back, interpolation needs two neighbours -> ring of 256 steps
     assert k.n_hist == 2 and k.hist_vars == [0, 1] and k.hist_depth == 256 and fixed.rhs.hist_dt == 1e-4
-    assert "prb_hist_push(T, y, A.step0 + i + 1)" in k.source and "#define PRB_SOLVER 0" in k.source
+    assert "prb_hist_push(T, y, A.step0 + i + s + 1)" in k.source and "#define PRB_SOLVER 0" in k.source
     adaptive = InstanceModel(Program.load(golden_path("dde_mg_dopri5")), solver="scipy")
     assert adaptive.kernel_solver == "dopri5_dde" and adaptive.kernel.hist_depth == 0 and "#define PRB_SOLVER 5" in adaptive.kernel.source
     assert list(adaptive.hist_y0) == [1.2, 0.4]
