@@ -615,8 +615,16 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
 #ifndef PRB_BURST_UNROLL
 #define PRB_BURST_UNROLL
 #endif
+    // One thread / one warp runs (CircuitTemplate.run of a small circuit, C1) keep the plain per-step loop: the burst
+    // bookkeeping is a chain of dependent uniform-datapath instructions, which a single warp cannot hide when every step is
+    // stored (measured: 48 -> 132 ns per Euler step of the QIF model).  PRB_BURST_LOOP is defined for sweep kernels.
+#ifdef PRB_BURST_LOOP
     long long i = 0;
     while (i < A.n_steps) {
+#else
+    for (long long i = 0; i < A.n_steps; ++i, ++t) {
+        const int s = 0;
+#endif
         if (until_store == 0) {
 #ifdef PRB_REDUCE
             if (sample >= A.sample0) {
@@ -644,6 +652,7 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
             ++sample;
             until_store = store_step;
         }
+#ifdef PRB_BURST_LOOP
         long long left = A.n_steps - i;
         if (until_store < left) left = until_store;
         if (left > 0x40000000LL) left = 0x40000000LL;
@@ -651,6 +660,10 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
         until_store -= burst;
         PRB_BURST_UNROLL
         for (int s = 0; s < burst; ++s, ++t) {
+#else
+        --until_store;
+        {
+#endif
 
         PrbBad bad;
 #if defined(PRB_SPEC_STEP) && !defined(PRB_Y_SMEM)
@@ -715,7 +728,9 @@ prb_integrate(const __grid_constant__ prb_kernel_args A)
         prb_hist_push(T, y, A.step0 + i + s + 1);    // DDEHistory.update((i + 1) * dt, y)
 #endif
         }   // burst
+#ifdef PRB_BURST_LOOP
         i += burst;
+#endif
     }
 
 #ifdef PRB_REDUCE

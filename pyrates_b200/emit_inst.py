@@ -379,9 +379,11 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
 def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: Sequence[int],
                      block: int = 128, const_div_to_mul: bool = False, min_blocks: int = 1,
                      fast_math: bool = False, rk_method: str = "RK45", reduce: bool = False,
-                     hist_max_delay: Optional[float] = None, y_smem: bool = False) -> InstKernel:
+                     hist_max_delay: Optional[float] = None, y_smem: bool = False, burst: Optional[bool] = None) -> InstKernel:
     """Generate the full CUDA C source of the fused rhs+solver instance kernel.  ``reduce``: the kernel keeps running
-    statistics of the observers (mean, var, min, max, last) instead of storing every sample (fixed-step solvers)."""
+    statistics of the observers (mean, var, min, max, last) instead of storing every sample (fixed-step solvers).
+    ``burst``: time loop in bursts between stored samples (32-bit counter, nothing else in the loop) — the default for
+    kernels with per-instance parameters (sweeps: many warps, issue-bound); single runs keep the plain per-step loop."""
     if solver not in SOLVER_IDS:
         raise ValueError(f"unknown solver `{solver}`; supported: {sorted(SOLVER_IDS)}")
     f32 = precision == "float32"
@@ -456,6 +458,8 @@ def emit_inst_kernel(rhs: ScalarRhs, *, solver: str, precision: str, observers: 
     src.append(f"typedef {'float' if f32 else 'double'} real;")
     src.append(f"typedef {'double' if (adaptive and f32) else 'real'} areal;        // arithmetic type of the generated rhs")
     src.append(f"typedef {'double' if adaptive else 'long long'} prb_time;     // adaptive solvers hand the rhs a float time")
+    if (bool(rhs.params) if burst is None else burst) and not adaptive:
+        src.append("#define PRB_BURST_LOOP 1")
     src.append(f"#define PRB_NS {ns}")
     src.append(f"#define PRB_NDY {rhs.n_out if rhs.n_out is not None else ns}        // outputs of prb_rhs (Jacobian programs: n*n)")
     if rhs.n_out is not None:

@@ -38,7 +38,7 @@ class InstanceModel:
                  observers: Optional[Sequence[int]] = None, block: int = 128, fmad: bool = True,
                  const_div_to_mul: bool = False, max_nodes: int = 6000, min_blocks: int = 1, fast_math: bool = False,
                  rk_method: Optional[str] = None, reduce: bool = False, hist_max_delay: Optional[float] = None,
-                 y_smem: bool = False):
+                 y_smem: bool = False, burst: Optional[bool] = None):
         if solver not in FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS:
             raise rt.CudaBackendError(f"Backend `CudaBackend` does not support solver `{solver}`. "
                                       f"Supported solvers: {list(FIXED_STEP_SOLVERS + ADAPTIVE_SOLVERS)}.")
@@ -61,7 +61,7 @@ class InstanceModel:
                                                    observers=self.observers, block=block,
                                                    const_div_to_mul=const_div_to_mul, min_blocks=min_blocks,
                                                    fast_math=fast_math, rk_method=self.rk_method or "RK45", reduce=reduce,
-                                                   hist_max_delay=hist_max_delay, y_smem=y_smem)
+                                                   hist_max_delay=hist_max_delay, y_smem=y_smem, burst=burst)
         # swept delays of delay-differential models: the bound the history was sized for (checked against every table)
         self.hist_max_delay = None if hist_max_delay is None else float(hist_max_delay)
         self.reduce = bool(reduce)
