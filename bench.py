@@ -43,8 +43,8 @@ B_ALG = (2 * 8 + 5) * 8 + 8 / 10   # (2*n_sv + n_pp)*s + n_obs*s
 SWEEP = [("u", 0), ("weight_v2", 0), ("weight_v2", 1), ("weight", 0), ("weight_v1", 0)]
 # dram__bytes_read.sum + dram__bytes_write.sum of one prb_integrate launch from `ncu --set full` captures: 1000-step launches
 # (--chunk-samples 100; profiles/r01_c2_fastmath_prb_integrate_ncu_full.txt) and the default 250-step launches
-# (--chunk-samples 25; 109.19 + 221.97 MB, profiles/r01_c2_reassoc_prb_integrate_ncu_full.txt)
-NCU_TRAFFIC = {2 ** 20 * 1000: 958.2e6, 2 ** 20 * 250: 331.16e6}
+# (--chunk-samples 25; 109.31 + 228.36 MB, profiles/r02_lean_c2_prb_integrate_ncu_full.txt)
+NCU_TRAFFIC = {2 ** 20 * 1000: 958.2e6, 2 ** 20 * 250: 337.66e6}
 # fp64-pipe warp instructions per instance-step inside the SASS time loop (cuobjdump; tests/test_compile_inst.py pins them)
 FP64_INSTR = {True: 264, False: 505}
 METRIC = "state-updates/sec (nodes x sweeps x steps/s), JRC RK4 grid_search"
