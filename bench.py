@@ -744,8 +744,11 @@ def main():
     if "strong" in want and world > 1:
         Bs_lo, Bs_hi = _bounds(B, world, rank)
         Bs = Bs_hi - Bs_lo
+        # a GPU's share shrinks with the world size; twice the samples per launch keeps the launches long enough (one GPU's
+        # share of 8, 131072 instances, on one B200: 25.24 ms per simulation at 25 samples per launch, 24.72 at 50, e2e 26.35
+        # / 26.18; longer chunks lengthen the un-overlapped D2H tail — profiles/r02_strong_probe.jsonl)
         ss = BatchedSweep(prog, SWEEP, observers=[0], solver="rk4", T=a.sim_time, dt=1e-4, dts=1e-3, n_inst=Bs,
-                          chunk_samples=a.chunk_samples, const_div_to_mul=not a.strict_div)
+                          chunk_samples=a.chunk_samples * (2 if world >= 4 else 1), const_div_to_mul=not a.strict_div)
         ss.model.compile(shared=True)
         tb = param_table(a.grid, a.grid, Bs_lo, Bs_hi)
         ss.stage_params(tb)
