@@ -351,7 +351,11 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
         elif op == "sign":
             expr = f"prb_sign({ref(a[0])})"
         elif op == "exp" and fast_math and f32:
-            expr = f"__expf({ref(a[0])})"                               # ex2.approx(x * log2 e): ~2 ulp + |x| 2^-24
+            # ex2.approx(x * log2 e): ~2 ulp + |x| 2^-24.  The flush-to-zero form (default) drops __expf's handling of results
+            # below 2^-126 — a compare and two predicated multiplies per call, 36 of the 208 instructions of a JRC RK4 step
+            expr = (f"prb_expf_ftz({ref(a[0])})" if os.environ.get("PRB_EXPF_FTZ", "1") == "1" else f"__expf({ref(a[0])})")
+        elif op == "exp2":                                               # reassoc.py: exp(x) of float32 fast_math kernels
+            expr = f"prb_ex2_ftz({ref(a[0])})" if f32 else f"exp2({ref(a[0])})"
         elif op == "exp" and fast_math and not f32:
             expr = f"prb_spec_exp({ref(a[0])}, T.ek0, T.etab_s, bad)" if spec else f"prb_fast_exp({ref(a[0])}, T.etab)"
         elif op in _FUNC:
@@ -571,6 +575,17 @@ __device__ __forceinline__ double prb_hist(PrbThread& T, const int k, const doub
 // outside.  Division: rcp.approx.ftz.f64 + two Newton steps (5 fp64 instructions), IEEE division for zero / denormal /
 // huge / non-finite divisors.  Both stay far inside the 1e-9 trajectory tolerance; off by default in CudaBackend.run.
 @@EXP_TABLES@@
+__device__ __forceinline__ float prb_ex2_ftz(const float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// float32 fast_math exp: one multiply + MUFU.EX2; results below 2^-126 flush to zero (absolute error < 1.2e-38)
+__device__ __forceinline__ float prb_expf_ftz(const float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
 __device__ __noinline__ double prb_exp_slow(const double z) { return exp(z); }
 __device__ __noinline__ double prb_div_slow(const double a, const double b) { return a / b; }
 // Range violations of one speculative evaluation (or step).  exp arguments are checked through the running signed AND unsigned

@@ -49,6 +49,8 @@ def fold_invariants(rhs: ScalarRhs, max_terms: int = 6) -> ScalarRhs:
     """Return an equivalent ScalarRhs whose graph groups thread-invariant factors (see module docstring)."""
     g = rhs.graph
     ng = Graph(g.real)
+    import numpy as _np
+    exp2_f32 = _np.dtype(g.real) == _np.float32 and os.environ.get("PRB_EXPF_FTZ", "1") == "1"
     one = lambda: ng.const(1.0, weak=True)
     memo: Dict[int, _LC] = {}
     imemo: Dict[int, Sym] = {}
@@ -77,7 +79,7 @@ def fold_invariants(rhs: ScalarRhs, max_terms: int = 6) -> ScalarRhs:
         return ng.binop("mul", a, b)
 
     depth_memo: Dict[int, int] = {}
-    cost = {"exp": 8, "div": 5, "log": 8, "sin": 12, "cos": 12, "tan": 14, "tanh": 12, "pow": 16, "sqrt": 5}
+    cost = {"exp": 8, "exp2": 8, "div": 5, "log": 8, "sin": 12, "cos": 12, "tan": 14, "tanh": 12, "pow": 16, "sqrt": 5}
 
     def depth(i: int) -> int:
         """Length of the dependency chain that ends in node i of the new graph (rough instruction latencies)."""
@@ -202,7 +204,12 @@ def fold_invariants(rhs: ScalarRhs, max_terms: int = 6) -> ScalarRhs:
             r = _LC(s, []) if (x.invariant and y.invariant) else as_dynamic(s)
         else:                                       # unary functions
             x = form(a[0])
-            s = ng.unop(op, mat(x))
+            if op == "exp" and exp2_f32 and not x.invariant:
+                # float32 fast_math: e^x = 2^(x log2 e) on MUFU.EX2 — the factor log2 e joins the coefficients of the
+                # argument's combination instead of costing a multiply per call
+                s = ng.unop("exp2", mat(scale(x, ng.const(1.4426950408889634, weak=True))))
+            else:
+                s = ng.unop(op, mat(x))
             r = _LC(s, []) if x.invariant else as_dynamic(s)
         memo[i] = r
         return r

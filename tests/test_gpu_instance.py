@@ -427,7 +427,7 @@ def test_fast_math_float32_sweep_keeps_fp32_parity(gpu):
     B = 256
     table = bench.param_table(16, 16, 0, B)
     m = InstanceModel(prog, solver="rk4", sweep=bench.SWEEP, observers=[0, 2], const_div_to_mul=True, fast_math=True, min_blocks=8)
-    assert "__expf(" in m.kernel.source and "__fdividef(" in m.kernel.source
+    assert "prb_expf_ftz(" in m.kernel.source and "__fdividef(" in m.kernel.source
     order = [(p.arg, p.elem) for p in m.rhs.params]
     out, _ = m.run(0.2, 1e-4, 1e-3, params=np.stack([table[bench.SWEEP.index(k)] for k in order]))
     f = orc.build_vector_field(prog.source())
