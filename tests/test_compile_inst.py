@@ -193,3 +193,41 @@ def test_fast_math_exp_algorithm_is_within_2_ulp_on_the_host():
     # models with mutable buffers keep the branching variant (a speculative re-evaluation would replay side effects)
     src2 = InstanceModel(Program.load(golden_path("jrc_2delay")), solver="heun", fast_math=True).kernel.source
     assert "prb_fast_div(" in src2 and "#define PRB_SPEC_STEP" not in src2 and "void prb_rhs_exact(" not in src2
+
+
+@pytest.mark.parametrize("env", [{"PRB_EXP_LEAN": "0"}, {"PRB_EXP_LEAN": "2"}, {"PRB_SPEC_PER_STEP": "0"}, {"PRB_RANGE_SHIFT": "1"},
+                                 {"PRB_INTEG_PAIRS": "1"}, {"PRB_MAT_REGFIRST": "0", "PRB_EXP_ESTRIN": "0", "PRB_EXP_PINK0": "0"},
+                                 {"PRB_EXP_PLUS": "1"}, {"PRB_BURST_UNROLL": "2"}])
+def test_measured_but_not_adopted_emitter_variants_still_build(env, monkeypatch):
+    """DESIGN.md 2.1 lists emitter variants that were measured on B200 and kept as opt-in switches; each must keep
+    compiling for sm_100a (they are the A/B partners of scripts/tune_inst.py)."""
+    monkeypatch.setenv("PRB_CACHE_DIR", "off")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    sweep = [("u", 0), ("weight_v2", 0), ("weight_v2", 1), ("weight", 0), ("weight_v1", 0)]
+    m = InstanceModel(Program.load(golden_path("jrc")), solver="rk4", sweep=sweep, observers=[0], const_div_to_mul=True,
+                      fast_math=True, block=64, min_blocks=7)
+    assert m.module.cubin[:4] == b"\x7fELF"
+    src = m.kernel.source
+    if env.get("PRB_SPEC_PER_STEP") == "0":
+        assert "#define PRB_SPEC_STEP 1" not in src
+    if env.get("PRB_INTEG_PAIRS") == "1":
+        assert "PRB_INTEG[PRB_NS] = {1, -1, 3, -1, 6, 7, -1, -1}" in src      # dV/dt = I chains of the three JRC populations
+
+
+def test_float32_fast_math_exp_is_a_flushing_exp2_with_folded_log2e(monkeypatch):
+    """float32 sweeps: exp(x) -> ex2.approx.ftz(x log2 e) with log2 e absorbed by the argument's coefficients (-560 log2 e)."""
+    import numpy as np
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench_configs as bc
+    sweep = [("u", 0), ("weight_v2", 0), ("weight_v2", 1), ("weight", 0), ("weight_v1", 0)]
+    prog = bc.to_float32(Program.load(golden_path("jrc")))
+    src = InstanceModel(prog, solver="rk4", sweep=sweep, observers=[0], const_div_to_mul=True, fast_math=True).kernel.source
+    body = src[src.index("void prb_rhs("):src.index("void prb_record(")]
+    assert body.count("prb_ex2_ftz(") == 3 and "__expf(" not in body and "exp(" not in body.replace("prb_ex2_ftz(", "")
+    c = float(np.float32(-560.0) * np.float32(1.4426950408889634))
+    assert f"({c!r}f)" in body or f"({float(np.float32(c))!r}f)" in body
+    monkeypatch.setenv("PRB_EXPF_FTZ", "0")
+    src0 = InstanceModel(prog, solver="rk4", sweep=sweep, observers=[0], const_div_to_mul=True, fast_math=True).kernel.source
+    assert "__expf(" in src0[src0.index("void prb_rhs("):src0.index("void prb_record(")]
