@@ -231,3 +231,48 @@ def test_float32_fast_math_exp_is_a_flushing_exp2_with_folded_log2e(monkeypatch)
     monkeypatch.setenv("PRB_EXPF_FTZ", "0")
     src0 = InstanceModel(prog, solver="rk4", sweep=sweep, observers=[0], const_div_to_mul=True, fast_math=True).kernel.source
     assert "__expf(" in src0[src0.index("void prb_rhs("):src0.index("void prb_record(")]
+
+
+def test_burst_time_loop_keeps_the_sampling_schedule_of_the_per_step_loop():
+    """Python twins of the two time loops of inst_kernel.cuh (PRB_BURST_LOOP and the plain one): for chained launches with
+    arbitrary step offsets and decimations they must record the same samples at the same steps and advance the same
+    counters — the rule of BaseBackend._solve (row k = state at step k * store_step, sampled BEFORE the update)."""
+    import re
+    import numpy as np
+    src = open(os.path.join(os.path.dirname(rt.__file__), "csrc", "templates", "inst_kernel.cuh")).read()
+    # the twins below restate these lines; fail when the template drifts away from them
+    for line in ("long long until_store = (store_step - (A.step0 % store_step)) % store_step;", "if (until_store < left) left = until_store;",
+                 "if (left > 0x40000000LL) left = 0x40000000LL;", "until_store -= burst;", "for (int s = 0; s < burst; ++s, ++t) {", "i += burst;"):
+        assert line in src, line
+    assert re.search(r"#ifdef PRB_BURST_LOOP\s+long long i = 0;\s+while \(i < A.n_steps\) \{\s+#else\s+for \(long long i = 0; i < A.n_steps; \+\+i, \+\+t\)", src)
+
+    def plain(step0, n_steps, store_step, sample0):
+        until, sample, t, rec, steps = (store_step - step0 % store_step) % store_step, sample0, step0, [], []
+        for i in range(n_steps):
+            if until == 0:
+                rec.append((sample, t)); sample += 1; until = store_step
+            until -= 1
+            steps.append(t); t += 1
+        return rec, steps, sample, t
+
+    def burst(step0, n_steps, store_step, sample0, cap=0x40000000):
+        until, sample, t, rec, steps, i = (store_step - step0 % store_step) % store_step, sample0, step0, [], [], 0
+        while i < n_steps:
+            if until == 0:
+                rec.append((sample, t)); sample += 1; until = store_step
+            left = min(n_steps - i, until, cap)
+            assert left >= 1
+            until -= left
+            for s in range(left):
+                steps.append(t); t += 1
+            i += left
+        return rec, steps, sample, t
+
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        store_step = int(rng.integers(1, 12))
+        step0, sample0 = 0, 0
+        for n_steps in rng.integers(0, 40, size=4):                       # a chain of launches (BatchedSweep chunks)
+            a, b = plain(step0, int(n_steps), store_step, sample0), burst(step0, int(n_steps), store_step, sample0, cap=int(rng.integers(1, 9)))
+            assert a == b
+            step0, sample0 = a[3], a[2]
