@@ -521,7 +521,8 @@ __device__ __forceinline__ void prb_step(const long long t, const real (&y)[PRB_
     // Integrator chains (PRB_INTEG[j] = b >= 0: dy_j == y_b, so k_j of a stage IS that stage's y_b).  Such a state needs no
     // accumulator:  y_j' = y_j + dt y_b + dt^2/6 (k1 + k2 + k3)_b  exactly, and every other state takes its increment from the
     // same sum:  k1 + 2 k2 + 2 k3 + k4 = 2 S + (k4 - k1),  S = k1 + k2 + k3.  Only instantiated with FINAL = false: `yn`
-    // receives S of the SOURCE state for chain states (prb_step_finish applies the formula) and 2 S + (k4 - k1) otherwise.
+    // receives S of the SOURCE state for chain states (the in-place finish of the time loop applies the formula) and
+    // 2 S + (k4 - k1) otherwise.
     real ys[PRB_NS], k1[PRB_NS], S[PRB_NS];
     prb_stage<SPEC>(t, y, k, T, bad);                       // k1
     PRB_UNROLL_NS
