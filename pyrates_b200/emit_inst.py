@@ -38,7 +38,7 @@ def exp_lean() -> int:
     return int(os.environ.get("PRB_EXP_LEAN", "1"))
 
 
-def exp_tables() -> str:
+def exp_tables(zmax: float = 700.0) -> str:
     """Constants of prb_fast_exp / prb_spec_exp: 2^(j/2048) rounded from extended precision, 2048/ln2, and -ln2/2048 split
     into a high part whose LOW WORD IS ZERO (21 significant bits: n * hi is exact for |x| <= 700, and the value is an
     instruction immediate instead of a constant-bank load) and a low part.  The degree-3 polynomial r + r^2/2 + c3 r^3 on
@@ -60,7 +60,12 @@ def exp_tables() -> str:
         raw = np.array(tab, dtype=np.float64).view(np.uint64)
         raw = raw - (np.arange(n, dtype=np.uint64) << np.uint64(32 + 20 - ETAB_BITS))
         tab = [float(v) for v in raw.view(np.float64)]
-    return (f"#define PRB_ETAB_BITS {ETAB_BITS}\n#define PRB_ETAB_N {n}\n#define PRB_EXP_LEAN {exp_lean()}\n"
+    # speculative range |z| <= zmax as thresholds on the argument's high word (zmax = 700, or 220 in kernels with batched
+    # reciprocals: a product of three 1 + e^z must stay finite)
+    zhi = int(np.float64(zmax).view(np.uint64) >> np.uint64(32))
+    assert np.float64(zmax).view(np.uint64) & np.uint64(0xFFFFFFFF) == 0
+    return (f"#define PRB_EXP_ZHI 0x{zhi:08x}\n"
+            f"#define PRB_ETAB_BITS {ETAB_BITS}\n#define PRB_ETAB_N {n}\n#define PRB_EXP_LEAN {exp_lean()}\n"
             f"#define PRB_EXP_PINK0 {1 if os.environ.get('PRB_EXP_PINK0', '1') == '1' else 0}\n"
             f"#define PRB_RANGE_SHIFT {1 if os.environ.get('PRB_RANGE_SHIFT', '0') == '1' else 0}\n"
             f"#define PRB_EXP_ESTRIN {1 if os.environ.get('PRB_EXP_ESTRIN', '1') == '1' else 0}\n"
@@ -237,6 +242,48 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
         skip_exp = set()
     litscaled: dict = {}
     regfirst = bool(spec and hoist is not None and os.environ.get("PRB_MAT_REGFIRST", "1") == "1")
+    # Batched reciprocals (Montgomery's trick): k bare reciprocals 1 / d_j whose divisors are `c + exp(.)` share ONE
+    # reciprocal of the product — 1 / d_1 = R d_2 d_3 with R = 1 / (d_1 d_2 d_3): 3 (k - 1) multiplies replace k - 1 seeds
+    # (MUFU + zeroed low word) and cubic steps, the same number of fp64 instructions and two instructions of other pipes less
+    # per saved reciprocal.  The product must not overflow: the speculative range of every exp of such a kernel shrinks to
+    # |z| <= 220 (PRB_EXP_ZHI; arguments beyond it take the exact path like any other range violation) and the constants
+    # are confined to [1e-30, 1e30], so the product stays inside [1e-90, 5e286], the fast range of the reciprocal.
+    # Opt-in (PRB_RCP_BATCH=1).  Measured on the JRC sweep (profiles/r02_tune_lean9.jsonl): 82 instead of 96 non-fp64
+    # instructions per step, 18.07 -> 17.93 ms per 1000 steps (17.82 with the Horner polynomial), trajectories within 9e-16,
+    # tests/test_gpu_fullsize.py green with it — 0.8-1.4 % where the issue model predicts 2.2 % (the three sigmoid chains
+    # of an evaluation now join in one product, which exposes latency).  Not the default: the narrower fast range and the
+    # untested breadth (GPU budget of the round) outweigh 1 %.
+    rcp_group: dict = {}            # last member (node id) -> [member ids]; every member -> its group's leader
+    rcp_member: dict = {}
+    if spec and os.environ.get("PRB_RCP_BATCH", "0") == "1":
+        def _batchable(i):
+            if g.ops[i] != "div" or g.isint[i] or i in (invariant or {}) and invariant.get(i):
+                return False
+            a0, a1 = g.args[i]
+            if not (g.is_const(a0) and float(g.const_value(a0)) == 1.0 and safe_divisor(a1)):
+                return False
+            c = next(float(g.const_value(c_)) for c_ in g.args[a1] if g.is_const(c_))
+            return 1e-30 <= c <= 1e30
+        cand = [i for i in live if _batchable(i)]
+        users: dict = {}
+        for i in live:
+            for x in g.args[i]:
+                users.setdefault(x, []).append(i)
+            if fast_math and not g.isint[i] and g.ops[i] in ("mul", "div"):
+                base = const_chain(i)[0]
+                if base != i:
+                    users.setdefault(base, []).append(i)                  # folded constant chains reference their base
+        for k0 in range(0, len(cand), 3):
+            grp = cand[k0:k0 + 3]
+            if len(grp) < 2:
+                continue
+            last = max(grp)
+            # every consumer of a member must come after the group's last member in emission order, and no member's divisor
+            # may depend on another member (divisors are c + exp(state terms): check direct use only)
+            if all(u > last for m_ in grp for u in users.get(m_, [])) and not any(m2 in g.args[g.args[m_][1]] for m_ in grp for m2 in grp):
+                rcp_group[last] = grp
+                for m_ in grp:
+                    rcp_member[m_] = last
     lone_mul: set = set()            # register products that START a sum of literal-coefficient terms: kept a plain multiply
     if regfirst:
         def _litscaled(n):
@@ -253,6 +300,20 @@ def emit_rhs_body(rhs: ScalarRhs, f32: bool, const_div_to_mul: bool, float_time:
     for i in live:
         op, a = g.ops[i], g.args[i]
         if op in ("const", "state", "param", "t") or i in skip_exp:
+            continue
+        if i in rcp_member:
+            if i not in rcp_group:
+                continue                                                  # emitted with the group's last member
+            grp = rcp_group[i]
+            d = [ref(g.args[m_][1]) for m_ in grp]
+            if len(grp) == 2:
+                lines += [f"const areal w{i}p = __dmul_rn({d[0]}, {d[1]});", f"const areal w{i}r = prb_spec_rcp_nc(w{i}p);",
+                          f"const areal v{grp[0]} = __dmul_rn(w{i}r, {d[1]});", f"const areal v{grp[1]} = __dmul_rn(w{i}r, {d[0]});"]
+            else:
+                lines += [f"const areal w{i}a = __dmul_rn({d[0]}, {d[1]});", f"const areal w{i}p = __dmul_rn(w{i}a, {d[2]});",
+                          f"const areal w{i}r = prb_spec_rcp_nc(w{i}p);", f"const areal v{grp[2]} = __dmul_rn(w{i}r, w{i}a);",
+                          f"const areal w{i}t = __dmul_rn(w{i}r, {d[2]});", f"const areal v{grp[0]} = __dmul_rn(w{i}t, {d[1]});",
+                          f"const areal v{grp[1]} = __dmul_rn(w{i}t, {d[0]});"]
             continue
         if i in fused_exp:
             e, c = fused_exp[i]
@@ -599,10 +660,10 @@ struct PrbBad {
 #if PRB_RANGE_SHIFT
     // variant: drop the sign with a shift (an IMAD.SHL, nearly free next to the FP64 pipe) and keep ONE unsigned maximum
     __device__ __forceinline__ void exp_arg(const int hi) { umax = max(umax, (unsigned int)hi << 1); }
-    __device__ __forceinline__ operator bool() const { return flag | (umax > 0x810bc000u); }
+    __device__ __forceinline__ operator bool() const { return flag | (umax > ((unsigned int)PRB_EXP_ZHI << 1)); }
 #else
     __device__ __forceinline__ void exp_arg(const int hi) { smax = max(smax, hi); umax = max(umax, (unsigned int)hi); }
-    __device__ __forceinline__ operator bool() const { return flag | (smax > 0x4085e000) | (umax > 0xc085e000u); }
+    __device__ __forceinline__ operator bool() const { return flag | (smax > (int)PRB_EXP_ZHI) | (umax > (0x80000000u | PRB_EXP_ZHI)); }
 #endif
 };
 #if PRB_EXP_LEAN
@@ -677,7 +738,7 @@ __device__ __forceinline__ double prb_spec_exp(const double z, const double k0, 
 #if PRB_EXP_LEAN
     bad.exp_arg(__double2hiint(z));                                          // |z| > 700 (or NaN)
 #else
-    bad |= (unsigned int)(__double2hiint(z) & 0x7fffffff) > 0x4085e000u;
+    bad |= (unsigned int)(__double2hiint(z) & 0x7fffffff) > (unsigned int)PRB_EXP_ZHI;
 #endif
     const double t = fma(z, k0, 6755399441055744.0);
     const int n = __double2loint(t);
@@ -700,7 +761,7 @@ __device__ __forceinline__ double prb_spec_exp_plus(const double z, const double
 #if PRB_EXP_LEAN
     bad.exp_arg(__double2hiint(z));
 #else
-    bad |= (unsigned int)(__double2hiint(z) & 0x7fffffff) > 0x4085e000u;
+    bad |= (unsigned int)(__double2hiint(z) & 0x7fffffff) > (unsigned int)PRB_EXP_ZHI;
 #endif
     const double t = fma(z, k0, 6755399441055744.0);
     const int n = __double2loint(t);
@@ -773,7 +834,7 @@ __device__ __forceinline__ long long prb_ring_pos(int head, int col, int L) {
     p += (p < 0) ? L : 0;
     return (long long)p;
 }
-""".replace("@@EXP_TABLES@@\n", exp_tables()))
+""".replace("@@EXP_TABLES@@\n", exp_tables(220.0 if any("prb_spec_rcp_nc(w" in l for l in body) else 700.0)))
     if use_etab:
         src.append("#define PRB_USE_ETAB 1")
     if body and body[0].startswith("// PRB_LIT = {"):

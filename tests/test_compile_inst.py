@@ -197,7 +197,7 @@ def test_fast_math_exp_algorithm_is_within_2_ulp_on_the_host():
 
 @pytest.mark.parametrize("env", [{"PRB_EXP_LEAN": "0"}, {"PRB_EXP_LEAN": "2"}, {"PRB_SPEC_PER_STEP": "0"}, {"PRB_RANGE_SHIFT": "1"},
                                  {"PRB_INTEG_PAIRS": "1"}, {"PRB_MAT_REGFIRST": "0", "PRB_EXP_ESTRIN": "0", "PRB_EXP_PINK0": "0"},
-                                 {"PRB_EXP_PLUS": "1"}, {"PRB_BURST_UNROLL": "2"}])
+                                 {"PRB_EXP_PLUS": "1"}, {"PRB_BURST_UNROLL": "2"}, {"PRB_RCP_BATCH": "1"}])
 def test_measured_but_not_adopted_emitter_variants_still_build(env, monkeypatch):
     """DESIGN.md 2.1 lists emitter variants that were measured on B200 and kept as opt-in switches; each must keep
     compiling for sm_100a (they are the A/B partners of scripts/tune_inst.py)."""
@@ -211,6 +211,12 @@ def test_measured_but_not_adopted_emitter_variants_still_build(env, monkeypatch)
     src = m.kernel.source
     if env.get("PRB_SPEC_PER_STEP") == "0":
         assert "#define PRB_SPEC_STEP 1" not in src
+    if env.get("PRB_RCP_BATCH") == "1":
+        body = src[src.index("void prb_rhs_spec("):src.index("void prb_rhs(")]
+        # one reciprocal of the product of the three sigmoid denominators; the fast exp range shrinks so that it stays finite
+        assert body.count("prb_spec_rcp_nc(") == 1 and body.count("__dmul_rn(") >= 6 and "#define PRB_EXP_ZHI 0x406b8000" in src
+    else:
+        assert "#define PRB_EXP_ZHI 0x4085e000" in src
     if env.get("PRB_INTEG_PAIRS") == "1":
         assert "PRB_INTEG[PRB_NS] = {1, -1, 3, -1, 6, 7, -1, -1}" in src      # dV/dt = I chains of the three JRC populations
 
